@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.npz by running the UNMODIFIED reference compiled under oracle/_ref (make -C oracle ref;
+needs /root/reference, i.e. this container).  Each fixture holds the reference-assembled csr_mat and the
+reference's own outputs on it:
+  y1          = csr_mat::MultMv(vec_randomize(seed=1))                     (src/sparse.cc:291-297)
+  lanczos_a/b = lanczos(0, 999, 1000, ..., "sr_val0") coefficients + steps (src/lanczos.cc:134-266)
+  E0          = hess_eigen(...)[0]                                         (src/lanczos.cc:355-390)
+  cg_vec      = eigenvec_CG ground-state vector + steps (small cases)      (src/lanczos.cc:281-341)
+  escale      = energy_scale(extend=0.1, iters=40)                         (src/kpm.cc:45-88)
+  dn_a/dn_b   = lanczos(..., "dnmcs") with maxit=60 from vec_randomize(seed=1)
+and the published golden value the case is pinned by (reference file:line).
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import oracle_lib as O  # noqa: E402
+
+CASES = {
+    # name: (qb_ref case args, published golden E0 or None, citation, keep cg vector?)
+    "heis12_full": (["heis_chain", 12, "none"], None, "same model as src/main_test.cc:18-111 at L=12", True),
+    "heis16_full": (["heis_chain", 16, "none"], -7.142296361, "src/main_test.cc:88", False),
+    "heis16_k3": (["heis_chain_k", 16, 0, 3], -5.615175598,
+                  "examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_half.cc:102-117 (k=3)", True),
+    "tri4x4_k00": (["tri_k", 4, 4, 0, 0, 0], -8.555514918,
+                   "examples/trans_symmetric/latt_triangular/triangular_Heisenberg_spin_half.cc:135", True),
+    "tri4x4_k01": (["tri_k", 4, 4, 0, 0, 1], -8.002263841,
+                   "examples/trans_symmetric/latt_triangular/triangular_Heisenberg_spin_half.cc:136", True),
+    "tri4x4_k12": (["tri_k", 4, 4, 0, 1, 2], -7.588987242,
+                   "examples/trans_symmetric/latt_triangular/triangular_Heisenberg_spin_half.cc:139 (E0_list[6])", True),
+    "hubbard4x2": (["hubbard", 4, 2, 4, 4, 1, 1.1], -14.07605866,
+                   "examples/trans_absent/latt_square/square_Fermi_Hubbard.cc:113", True),
+    "honeycomb3x2_general": (["honeycomb", 3, 2], -28.60363167,
+                             "examples/trans_absent/latt_honeycomb/honeycomb_Spinless_Fermion.cc:129", True),
+    "tj12": (["tj_chain", 12, 8, 0], -9.762087307, "src/main_test.cc:207-208 (ARPACK E0=E1)", False),
+}
+
+
+def main():
+    assert O.have_qb_ref(), "build oracle/_ref first: make -C oracle ref"
+    only = sys.argv[1:]
+    for name, (args, golden, cite, keep_cg) in CASES.items():
+        if only and name not in only:
+            continue
+        wd = tempfile.mkdtemp(prefix="qbgold_")
+        csr = os.path.join(wd, "H.qbcsr"); y1 = os.path.join(wd, "y1.bin")
+        res = O.run_qb_ref(args + ["--dump", csr, "--mv", 1, y1, "--lanczos", "sr_val0", 1000,
+                                   "--energy-scale", 40], threads=1, workdir=wd)
+        A = O.read_qbcsr(csr)
+        y = np.fromfile(y1, dtype=np.complex128)
+        extra = {"y1": y, "lanczos_a": np.array(res["lanczos_a"]), "lanczos_b": np.array(res["lanczos_b"])}
+        meta = {"case": name, "qb_ref_args": [str(a) for a in args], "golden_E0": golden, "golden_cite": cite,
+                "lanczos_steps": res["lanczos_steps"], "lanczos_E0": res["lanczos_E0"],
+                "escale_lo": res["escale_lo"], "escale_hi": res["escale_hi"], "max_abs_imag": res["max_abs_imag"]}
+        if golden is not None and name != "tj12":
+            assert abs(res["lanczos_E0"] - golden) < 1e-8, (name, res["lanczos_E0"], golden)
+        if keep_cg:
+            cgv = os.path.join(wd, "cg.bin")
+            r2 = O.run_qb_ref(["file_z", csr, "--cg", repr(res["lanczos_E0"]), cgv], threads=1, workdir=wd)
+            extra["cg_vec"] = np.fromfile(cgv, dtype=np.complex128)
+            meta["cg_steps"] = r2["cg_steps"]; meta["cg_accuracy"] = r2["cg_accuracy"]
+        r3 = O.run_qb_ref(["file_z", csr, "--lanczos", "dnmcs", 60], threads=1, workdir=wd)
+        extra["dn_a"] = np.array(r3["lanczos_a"]); extra["dn_b"] = np.array(r3["lanczos_b"])
+        meta["dn_steps"] = r3["lanczos_steps"]
+        out = os.path.join(O.GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(out, dim=A.dim, ia=A.ia, ja=A.ja, val=A.val, sym=A.sym, meta=json.dumps(meta), **extra)
+        print(f"{name}: dim={A.dim} nnz={A.nnz} sym={A.sym} steps={res['lanczos_steps']} E0={res['lanczos_E0']:.12f} "
+              f"golden={golden} -> {os.path.getsize(out)/1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()

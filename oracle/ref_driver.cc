@@ -1,0 +1,409 @@
+/* oracle/ref_driver.cc -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A command-line driver over the UNMODIFIED reference library compiled from /root/reference/src
+ * (see oracle/Makefile).  It builds the reference's own models through the reference's public API
+ * (the way examples/ and src/main_test.cc do), and
+ *   - dumps the reference-assembled csr_mat (dim, nnz, sym, ia, ja, val) to a .qbcsr file,
+ *   - runs the reference's locate_E0_lanczos / lanczos / eigenvec_CG / energy_scale on it,
+ *   - times the reference's csr_mat<T>::MultMv and lanczos step (CPU baseline),
+ *   - or loads a .qbcsr produced elsewhere (e.g. by the product's builders) into a reference csr_mat
+ *     and runs the same reference routines on it.
+ * Results are written as one JSON object to --out.  The reference's own chatter goes to stdout.
+ *
+ * .qbcsr layout (little endian): char magic[8]="QBCSR1\0\0"; int64 dim; int64 nnz; int32 sym;
+ * int32 is_complex; int64 ia[dim+1]; int64 ja[nnz]; (double | double[2]) val[nnz].
+ */
+#include <cassert>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <algorithm>
+#include <sstream>
+#include <unistd.h>
+#include <omp.h>
+#include "qbasis.h"
+
+using cplx = std::complex<double>;
+using Model = qbasis::model<cplx>;
+using Opr = qbasis::opr<cplx>;
+using Mopr = qbasis::mopr<cplx>;
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+/* ----------------------------------------------------------------- qbcsr i/o */
+template <typename T>
+static void dump_csr(const qbasis::csr_mat<T> &A, const std::string &path) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); exit(2); }
+    char magic[8] = {'Q','B','C','S','R','1',0,0};
+    int64_t dim = A.dim, nnz = A.nnz;
+    int32_t sym = A.sym ? 1 : 0, isc = sizeof(T) == sizeof(cplx) ? 1 : 0;
+    fwrite(magic, 1, 8, f); fwrite(&dim, 8, 1, f); fwrite(&nnz, 8, 1, f); fwrite(&sym, 4, 1, f); fwrite(&isc, 4, 1, f);
+    fwrite(A.ia, 8, dim + 1, f); fwrite(A.ja, 8, nnz, f); fwrite(A.val, sizeof(T), nnz, f);
+    fclose(f);
+}
+
+template <typename T>
+static void load_csr(qbasis::csr_mat<T> &A, const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); exit(2); }
+    char magic[8]; int64_t dim, nnz; int32_t sym, isc;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "QBCSR1", 6) != 0) { fprintf(stderr, "bad magic\n"); exit(2); }
+    if (fread(&dim, 8, 1, f) != 1 || fread(&nnz, 8, 1, f) != 1 || fread(&sym, 4, 1, f) != 1 || fread(&isc, 4, 1, f) != 1) exit(2);
+    if ((isc != 0) != (sizeof(T) == sizeof(cplx))) { fprintf(stderr, "scalar type mismatch\n"); exit(2); }
+    A.dim = dim; A.nnz = nnz; A.sym = sym != 0;
+    A.ia = new MKL_INT[dim + 1]; A.ja = new MKL_INT[nnz]; A.val = new T[nnz];
+    if (fread(A.ia, 8, dim + 1, f) != (size_t)(dim + 1) || fread(A.ja, 8, nnz, f) != (size_t)nnz ||
+        fread(A.val, sizeof(T), nnz, f) != (size_t)nnz) { fprintf(stderr, "short file\n"); exit(2); }
+    fclose(f);
+    /* the same handle creation csr_mat's own constructors perform (reference src/sparse.cc:129,258) */
+    sparse_status_t st;
+    if constexpr (sizeof(T) == sizeof(cplx)) st = mkl_sparse_z_create_csr(&A.handle, SPARSE_INDEX_BASE_ZERO, dim, dim, A.ia, A.ia + 1, A.ja, (MKL_Complex16 *)A.val);
+    else                                     st = mkl_sparse_d_create_csr(&A.handle, SPARSE_INDEX_BASE_ZERO, dim, dim, A.ia, A.ia + 1, A.ja, (double *)A.val);
+    if (st != SPARSE_STATUS_SUCCESS) { fprintf(stderr, "create_handle failed\n"); exit(2); }
+}
+
+static void dump_vec(const std::string &path, const void *p, size_t bytes) {
+    FILE *f = fopen(path.c_str(), "wb"); if (!f) { perror(path.c_str()); exit(2); }
+    fwrite(p, 1, bytes, f); fclose(f);
+}
+
+/* ------------------------------------------------------------ local matrices */
+static std::vector<std::vector<cplx>> mat2(cplx a00, cplx a01, cplx a10, cplx a11) { return {{a00, a01}, {a10, a11}}; }
+
+struct Built {
+    std::unique_ptr<Model> model;
+    qbasis::which_sym sym = qbasis::which_sym::full;
+    std::string name;
+};
+
+static void add_heisenberg_bond(Model &M, uint32_t i, uint32_t j, double J) {
+    auto Sp = mat2(0, 1, 0, 0), Sm = mat2(0, 0, 1, 0);
+    std::vector<cplx> Sz{0.5, -0.5};
+    Opr Spi(i, 0, false, Sp), Smi(i, 0, false, Sm), Szi(i, 0, false, Sz);
+    Opr Spj(j, 0, false, Sp), Smj(j, 0, false, Sm), Szj(j, 0, false, Sz);
+    M.add_Ham(cplx(0.5 * J, 0.0) * (Spi * Smj + Smi * Spj));
+    M.add_Ham(cplx(J, 0.0) * (Szi * Szj));
+}
+
+static Mopr total_sz(uint32_t nsites) {
+    std::vector<cplx> Sz{0.5, -0.5};
+    Mopr S;
+    for (uint32_t s = 0; s < nsites; s++) S += Opr(s, 0, false, Sz);
+    return S;
+}
+
+/* Heisenberg chain, PBC.  mode "none": no conserved quantity (main_test.cc:18-111); "sz": Sz_total = szval. */
+static Built build_heis_chain(int L, bool use_sz, double szval, int k /* -1: no translation */) {
+    Built b; b.name = "heis_chain";
+    qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    M.add_orbital(latt.Nsites, "spin-1/2");
+    for (int x = 0; x < L; x++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x}, 0, si, work); latt.coor2site({x + 1}, 0, sj, work);
+        add_heisenberg_bond(M, si, sj, 1.0);
+    }
+    if (k < 0) {
+        if (use_sz) M.enumerate_basis_full({total_sz(latt.Nsites)}, {szval}); else M.enumerate_basis_full({}, {});
+        M.generate_Ham_sparse_full();
+        b.sym = qbasis::which_sym::full;
+    } else {
+        M.fill_Weisse_table();
+        if (use_sz) M.enumerate_basis_repr({k}, {total_sz(latt.Nsites)}, {szval}); else M.enumerate_basis_repr({k}, {}, {});
+        M.generate_Ham_sparse_repr();
+        b.sym = qbasis::which_sym::repr;
+    }
+    return b;
+}
+
+/* Heisenberg on the triangular lattice, PBC, Sz_total = szval, momentum (m,n) or full basis (m<0). */
+static Built build_triangular(int Lx, int Ly, double szval, int m, int n) {
+    Built b; b.name = "triangular";
+    qbasis::lattice latt("triangular", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    M.add_orbital(latt.Nsites, "spin-1/2");
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x, y}, 0, si, work);
+        latt.coor2site({x + 1, y}, 0, sj, work);     add_heisenberg_bond(M, si, sj, 1.0);
+        latt.coor2site({x + 1, y + 1}, 0, sj, work); add_heisenberg_bond(M, si, sj, 1.0);
+        latt.coor2site({x, y + 1}, 0, sj, work);     add_heisenberg_bond(M, si, sj, 1.0);
+    }
+    if (m < 0) {
+        M.enumerate_basis_full({total_sz(latt.Nsites)}, {szval});
+        M.generate_Ham_sparse_full();
+        b.sym = qbasis::which_sym::full;
+    } else {
+        M.fill_Weisse_table();
+        M.enumerate_basis_repr({m, n}, {total_sz(latt.Nsites)}, {szval});
+        M.generate_Ham_sparse_repr();
+        b.sym = qbasis::which_sym::repr;
+    }
+    return b;
+}
+
+/* Fermi-Hubbard on the square lattice, PBC (examples/trans_absent/latt_square/square_Fermi_Hubbard.cc). */
+static Built build_hubbard(int Lx, int Ly, double nup, double ndn, double t, double U) {
+    Built b; b.name = "hubbard";
+    qbasis::lattice latt("square", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    auto cu = std::vector<std::vector<cplx>>(4, std::vector<cplx>(4, 0.0));
+    auto cd = cu;
+    cu[0][1] = 1.0; cu[2][3] = 1.0; cd[0][2] = 1.0; cd[1][3] = -1.0;
+    M.add_orbital(latt.Nsites, "electron");
+    Mopr Nup, Ndn;
+    auto hop = [&](uint32_t i, uint32_t j) {
+        Opr cui(i, 0, true, cu), cdi(i, 0, true, cd), cuj(j, 0, true, cu), cdj(j, 0, true, cd);
+        auto cuid = cui; cuid.dagger(); auto cdid = cdi; cdid.dagger();
+        auto cujd = cuj; cujd.dagger(); auto cdjd = cdj; cdjd.dagger();
+        M.add_Ham(cplx(-t, 0.0) * (cuid * cuj)); M.add_Ham(cplx(-t, 0.0) * (cujd * cui));
+        M.add_Ham(cplx(-t, 0.0) * (cdid * cdj)); M.add_Ham(cplx(-t, 0.0) * (cdjd * cdi));
+    };
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x, y}, 0, si, work);
+        Opr cui(si, 0, true, cu), cdi(si, 0, true, cd);
+        auto cuid = cui; cuid.dagger(); auto cdid = cdi; cdid.dagger();
+        auto nu = cuid * cui; auto nd = cdid * cdi;
+        latt.coor2site({x + 1, y}, 0, sj, work); hop(si, sj);
+        latt.coor2site({x, y + 1}, 0, sj, work); hop(si, sj);
+        M.add_Ham(cplx(U, 0.0) * (nu * nd));
+        Nup += nu; Ndn += nd;
+    }
+    M.enumerate_basis_full({Nup, Ndn}, {nup, ndn});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* t-J chain (src/main_test.cc:113-211). */
+static Built build_tj_chain(int L, double ntot, double sz) {
+    Built b; b.name = "tj_chain";
+    qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    auto cu = std::vector<std::vector<cplx>>(3, std::vector<cplx>(3, 0.0));
+    auto cd = cu; cu[0][1] = 1.0; cd[0][2] = 1.0;
+    M.add_orbital(latt.Nsites, "tJ");
+    Mopr Sz_tot, N_tot;
+    const double t = 1.0, J = 1.0;
+    for (int m = 0; m < L; m++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({m}, 0, si, work); latt.coor2site({m + 1}, 0, sj, work);
+        Opr cui(si, 0, true, cu), cdi(si, 0, true, cd), cuj(sj, 0, true, cu), cdj(sj, 0, true, cd);
+        auto cuid = cui; cuid.dagger(); auto cdid = cdi; cdid.dagger();
+        auto cujd = cuj; cujd.dagger(); auto cdjd = cdj; cdjd.dagger();
+        auto Spi = cuid * cdi; auto Smi = cdid * cui; auto Spj = cujd * cdj; auto Smj = cdjd * cuj;
+        auto Szi = cplx(0.5, 0.0) * (cuid * cui - cdid * cdi); auto Szj = cplx(0.5, 0.0) * (cujd * cuj - cdjd * cdj);
+        auto Ni = (cuid * cui + cdid * cdi); auto Nj = (cujd * cuj + cdjd * cdj);
+        M.add_Ham(cplx(-t, 0.0) * (cuid * cuj)); M.add_Ham(cplx(-t, 0.0) * (cujd * cui));
+        M.add_Ham(cplx(-t, 0.0) * (cdid * cdj)); M.add_Ham(cplx(-t, 0.0) * (cdjd * cdi));
+        M.add_Ham(cplx(0.5 * J, 0.0) * (Spi * Smj + Smi * Spj));
+        M.add_Ham(cplx(J, 0.0) * (Szi * Szj));
+        M.add_Ham(cplx(-0.25 * J, 0.0) * (Ni * Nj));
+        Sz_tot += Szi; N_tot += Ni;
+    }
+    M.enumerate_basis_full({Sz_tot, N_tot}, {sz, ntot});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* Spinless fermions on the honeycomb lattice, stored as a GENERAL (full, non-symmetric-storage) CSR
+ * (examples/trans_absent/latt_honeycomb/honeycomb_Spinless_Fermion.cc). */
+static Built build_honeycomb(int Lx, int Ly) {
+    Built b; b.name = "honeycomb";
+    const double t = 1.0, V1 = 4.0;
+    qbasis::lattice latt("honeycomb", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    auto c = std::vector<std::vector<cplx>>(2, std::vector<cplx>(2, 0.0)); c[0][1] = 1.0;
+    M.add_orbital(latt.Nsites, "spinless-fermion");
+    Mopr Nf;
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x, y}, 0, si, work);
+        Opr ci(si, 0, true, c); auto cid = ci; cid.dagger(); auto ni = cid * ci;
+        const int nb[3][2] = {{x, y}, {x - 1, y}, {x - 1, y - 1}};
+        for (auto &r : nb) {
+            latt.coor2site({r[0], r[1]}, 1, sj, work);
+            Opr cj(sj, 0, true, c); auto cjd = cj; cjd.dagger(); auto nj = cjd * cj;
+            M.add_Ham(cplx(-t, 0.0) * (cid * cj)); M.add_Ham(cplx(-t, 0.0) * (cjd * ci));
+            M.add_Ham(cplx(V1, 0.0) * (ni * nj)); M.add_Ham(cplx(-0.5 * V1, 0.0) * (ni + nj));
+        }
+        latt.coor2site({x, y}, 1, sj, work);
+        Opr cj(sj, 0, true, c); auto cjd = cj; cjd.dagger();
+        Nf += (ni + cjd * cj);
+    }
+    M.enumerate_basis_full({Nf}, {double(Lx * Ly - 2)});
+    M.generate_Ham_sparse_full(0, false);
+    return b;
+}
+
+/* ------------------------------------------------------------------ actions */
+struct Json {
+    std::ostringstream o; bool first = true;
+    Json() { o << std::setprecision(17) << "{"; }
+    void key(const std::string &k) { if (!first) o << ", "; first = false; o << "\"" << k << "\": "; }
+    void num(const std::string &k, double v) { key(k); o << v; }
+    void integer(const std::string &k, long long v) { key(k); o << v; }
+    void str(const std::string &k, const std::string &v) { key(k); o << "\"" << v << "\""; }
+    void arr(const std::string &k, const double *p, long long n) { key(k); o << "["; for (long long i = 0; i < n; i++) o << (i ? ", " : "") << p[i]; o << "]"; }
+    std::string done() { o << "}"; return o.str(); }
+};
+
+template <typename T>
+static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, Json &js)
+{
+    const MKL_INT n = H.dim;
+    js.integer("dim", n); js.integer("nnz", H.nnz); js.integer("sym", H.sym ? 1 : 0);
+    js.integer("is_complex", sizeof(T) == sizeof(cplx));
+    double maximag = 0.0;
+    if constexpr (sizeof(T) == sizeof(cplx)) for (MKL_INT p = 0; p < H.nnz; p++) maximag = std::max(maximag, std::abs(H.val[p].imag()));
+    js.num("max_abs_imag", maximag);
+    for (int a = argi; a < argc; a++) {
+        std::string opt = argv[a];
+        if (opt == "--dump" && a + 1 < argc) {
+            dump_csr(H, argv[++a]);
+        } else if (opt == "--mv" && a + 2 < argc) {
+            /* y = H x for x = vec_randomize(seed); dump y (reference csr_mat::MultMv, src/sparse.cc:291-297) */
+            uint32_t seed = (uint32_t)atoi(argv[++a]);
+            std::vector<T> x(n), y(n);
+            qbasis::vec_randomize(n, x.data(), seed);
+            H.MultMv(x.data(), y.data());
+            dump_vec(argv[++a], y.data(), sizeof(T) * n);
+        } else if (opt == "--time-mv" && a + 1 < argc) {
+            int reps = atoi(argv[++a]);
+            std::vector<T> x(n), y(n);
+            qbasis::vec_randomize(n, x.data(), 1);
+            for (int w = 0; w < 2; w++) H.MultMv(x.data(), y.data());
+            std::vector<double> ts;
+            for (int r = 0; r < reps; r++) { double t0 = now_s(); H.MultMv(x.data(), y.data()); ts.push_back(now_s() - t0); }
+            std::sort(ts.begin(), ts.end());
+            js.num("mv_median_s", ts[ts.size() / 2]); js.num("mv_min_s", ts[0]); js.integer("mv_reps", reps);
+            js.integer("threads", qb_shim_get_spmv_threads());
+        } else if (opt == "--lanczos" && a + 2 < argc) {
+            /* reference lanczos(0, maxit-1, maxit, m, dim, H, v, hess, purpose) from vec_randomize(seed=1),
+               exactly as model::locate_E0_lanczos starts it (src/model.cc:1158-1186) */
+            std::string purpose = argv[++a];
+            MKL_INT maxit = atoll(argv[++a]);
+            std::vector<double> hess(2 * maxit, 0.0), ritz, s;
+            std::vector<T> v(2 * n);
+            qbasis::vec_randomize(n, v.data(), 1);
+            MKL_INT m = 0;
+            double t0 = now_s();
+            qbasis::lanczos(static_cast<MKL_INT>(0), maxit - 1, maxit, m, n, H, v.data(), hess.data(), purpose);
+            double dt = now_s() - t0;
+            qbasis::hess_eigen(hess.data(), maxit, m, "sr", ritz, s);
+            js.integer("lanczos_steps", m); js.num("lanczos_E0", ritz[0]); js.num("lanczos_seconds", dt);
+            if (m > 1) js.num("lanczos_E1_ritz", ritz[1]);
+            js.arr("lanczos_b", hess.data(), m + 1); js.arr("lanczos_a", hess.data() + maxit, m);
+        } else if (opt == "--cg" && a + 2 < argc) {
+            /* reference eigenvec_CG as called from locate_E0_lanczos (src/model.cc:1209-1218) */
+            double E0 = atof(argv[++a]);
+            MKL_INT maxit = 1000, m = 0; double accu = 0.0;
+            std::vector<T> v(4 * n);
+            qbasis::vec_randomize(n, v.data() + 2 * n, 1);
+            double t0 = now_s();
+            qbasis::eigenvec_CG(n, maxit, m, H, static_cast<T>(E0), accu, v.data() + 2 * n, v.data(), v.data() + n, v.data() + 3 * n);
+            js.integer("cg_steps", m); js.num("cg_accuracy", accu); js.num("cg_seconds", now_s() - t0);
+            dump_vec(argv[++a], v.data() + 2 * n, sizeof(T) * n);
+        } else if (opt == "--energy-scale" && a + 1 < argc) {
+            /* reference energy_scale (src/kpm.cc:45-88); start vector = vec_randomize default seed */
+            MKL_INT iters = atoll(argv[++a]);
+            std::vector<T> v(2 * n); double lo, hi;
+            qbasis::energy_scale(n, H, v.data(), lo, hi, 0.1, iters);
+            js.num("escale_lo", lo); js.num("escale_hi", hi);
+        } else {
+            fprintf(stderr, "unknown option %s\n", opt.c_str()); exit(2);
+        }
+    }
+}
+
+static void usage() {
+    fprintf(stderr,
+        "usage: qb_ref [--threads T] [--workdir D] --out results.json <case> <args...> [actions]\n"
+        " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
+        "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr\n"
+        " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
+        " matrix actions: --dump F | --mv SEED F | --time-mv REPS | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
+    exit(2);
+}
+
+int main(int argc, char **argv)
+{
+    int a = 1, threads = 1;
+    std::string out = "", workdir = "/tmp/qb_ref_work";
+    while (a < argc && argv[a][0] == '-') {
+        std::string o = argv[a];
+        if (o == "--threads" && a + 1 < argc) threads = atoi(argv[++a]);
+        else if (o == "--out" && a + 1 < argc) out = argv[++a];
+        else if (o == "--workdir" && a + 1 < argc) workdir = argv[++a];
+        else usage();
+        a++;
+    }
+    if (a >= argc || out.empty()) usage();
+    /* absolute-ise paths before chdir: the reference appends log_Lanczos_*.txt / log_CG.txt to cwd */
+    auto absolutise = [](std::string p) { if (!p.empty() && p[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) p = std::string(cwd) + "/" + p; } return p; };
+    out = absolutise(out);
+    std::vector<std::string> av(argv, argv + argc);
+    for (int i = a; i < argc; i++) {
+        const std::string &s = av[i];
+        if ((s == "--dump" || s == "file_z" || s == "file_d") && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
+        if ((s == "--mv" || s == "--cg") && i + 2 < argc) av[i + 2] = absolutise(av[i + 2]);
+    }
+    std::vector<char *> cargv;
+    for (auto &s : av) cargv.push_back(const_cast<char *>(s.c_str()));
+    argv = cargv.data();
+    std::string cmd = "mkdir -p " + workdir; if (system(cmd.c_str()) != 0) return 2;
+    if (chdir(workdir.c_str()) != 0) { perror("chdir"); return 2; }
+    omp_set_num_threads(threads);
+    qb_shim_set_spmv_threads(threads);
+    std::cout << std::setprecision(14);
+
+    Json js;
+    std::string c = argv[a++];
+    js.str("case", c);
+    double t0 = now_s();
+    if (c == "file_z" || c == "file_d") {
+        if (a >= argc) usage();
+        std::string path = argv[a++];
+        if (c == "file_z") { qbasis::csr_mat<cplx> H; load_csr(H, path); run_actions(H, argc, argv, a, js); }
+        else               { qbasis::csr_mat<double> H; load_csr(H, path); run_actions(H, argc, argv, a, js); }
+    } else {
+        Built b;
+        auto need = [&](int k) { if (a + k > argc) usage(); };
+        if (c == "heis_chain") { need(2); int L = atoi(argv[a++]); std::string mode = argv[a++]; double sz = 0; if (mode == "sz") { need(1); sz = atof(argv[a++]); } b = build_heis_chain(L, mode == "sz", sz, -1); }
+        else if (c == "heis_chain_k") { need(3); int L = atoi(argv[a++]); double sz = atof(argv[a++]); int k = atoi(argv[a++]); b = build_heis_chain(L, true, sz, k); }
+        else if (c == "tri") { need(3); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_triangular(Lx, Ly, sz, -1, -1); }
+        else if (c == "tri_k") { need(5); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); int m = atoi(argv[a++]), n = atoi(argv[a++]); b = build_triangular(Lx, Ly, sz, m, n); }
+        else if (c == "hubbard") { need(6); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double nu = atof(argv[a++]), nd = atof(argv[a++]), t = atof(argv[a++]), U = atof(argv[a++]); b = build_hubbard(Lx, Ly, nu, nd, t, U); }
+        else if (c == "tj_chain") { need(3); int L = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_tj_chain(L, N, sz); }
+        else if (c == "honeycomb") { need(2); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); b = build_honeycomb(Lx, Ly); }
+        else usage();
+        js.num("build_seconds", now_s() - t0);
+        Model &M = *b.model;
+        while (a < argc && std::string(argv[a]) == "--locate-E0") {
+            if (a + 2 >= argc) usage();
+            MKL_INT nev = atoll(argv[a + 1]), ncv = atoll(argv[a + 2]); a += 3;
+            double t1 = now_s();
+            M.locate_E0_lanczos(b.sym, nev, ncv);
+            js.num("locate_seconds", now_s() - t1);
+            auto &ev = b.sym == qbasis::which_sym::full ? M.eigenvals_full : M.eigenvals_repr;
+            js.arr("locate_eigenvals", ev.data(), (long long)ev.size());
+        }
+        auto &H = b.sym == qbasis::which_sym::full ? M.HamMat_csr_full[0] : M.HamMat_csr_repr[0];
+        run_actions(H, argc, argv, a, js);
+    }
+    std::ofstream fo(out); fo << js.done() << std::endl; fo.close();
+    std::cout << std::endl << "QBREF done -> " << out << std::endl;
+    return 0;
+}

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- H*v throughput of the B200-native path (BASELINE.json metric: H*v/sec and achieved HBM GB/s; Lanczos
+iterations/s and E0 time-to-solution ride along as extra keys).
+
+  python bench.py --gpus 1 --steps K --warmup W                       our arm, one GPU
+  torchrun ... bench.py --gpus N --steps K --warmup W                  our arm, H row-sharded over N GPUs (strong scaling)
+  python bench.py --impl reference --gpus N --steps K --warmup W       the reference's CPU implementation (oracle/_ref)
+
+A step is one product y = H x (csr_mat::MultMv) on the workload named in config.workload.  Default workload =
+BASELINE config 3, Fermi-Hubbard 4x4, N_up = N_dn = 8 (dim 165,636,900; 5.82e9 stored entries), generated directly in
+HBM in the reference's basis order (the reference's own assembler cannot produce it).  `value` = products/s
+with vectors resident in HBM; `e2e` = the same through the reference-facing call with HOST vectors (x H2D and y D2H
+inside the timed region: what the ARPACK callback of src/lanczos.cc:476 pays).  The matrix is far larger than L2
+(126 MB), so no L2 flush is needed between steps; smaller workloads flush L2 between timed products.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (family, params)
+    "hubbard4x4": ("hubbard", dict(Lx=4, Ly=4, nup=8, ndn=8, t=1.0, U=1.1)),       # BASELINE config 3
+    "hubbard4x3": ("hubbard", dict(Lx=4, Ly=3, nup=6, ndn=6, t=1.0, U=1.1)),       # CPU-sized sample of the same model
+    "heis_chain20": ("heisenberg", dict(L=20)),                                     # BASELINE config 1
+    "heis_chain24": ("heisenberg", dict(L=24)),
+    "heis_chain28": ("heisenberg", dict(L=28)),
+    "heis_chain30": ("heisenberg", dict(L=30)),
+}
+L2_BYTES = 126e6
+
+
+def square_bonds(Lx, Ly):
+    site = lambda x, y: (x % Lx) + (y % Ly) * Lx   # noqa: E731
+    b = []
+    for x in range(Lx):
+        for y in range(Ly):
+            b += [(site(x, y), site(x + 1, y)), (site(x, y), site(x, y + 1))]
+    return b
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (clocks + throttle reasons)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(nnz, nrows_local, n, s_val, s_vec):
+    """B_spmv = Z*(S_val+4) + 8*(rows+1) + (n + rows)*S_vec  (one compulsory read of x, one write of y)."""
+    return nnz * (s_val + 4) + 8 * (nrows_local + 1) + (n + nrows_local) * s_vec
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, workload):
+    """The reference's own CPU implementation (unmodified sources compiled under oracle/_ref) on this host's cores.
+    Each step is one csr_mat<complex<double>>::MultMv on a bounded sample: the same model family at the largest size the
+    reference's own assembler builds in seconds; the rate is scaled to the workload by stored entries."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    fam, p = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    if fam == "hubbard":
+        sample_args = ["hubbard", 4, 3, 6, 6, p["t"], p["U"]]
+        sample_desc = "Fermi-Hubbard 4x3, N_up=N_dn=6 (dim 853,776; 12,030,480 stored upper-triangle entries), reference-assembled"
+    else:
+        Ls = min(p["L"], 22)
+        sample_args = ["heis_chain", Ls, "sz", 0]
+        sample_desc = f"Heisenberg chain L={Ls}, Sz=0, reference-assembled"
+    if not O.have_qb_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/qb_ref was not built (needs /root/reference at build time)"}))
+        return
+    res = O.run_qb_ref(sample_args + ["--time-mv", max(1, args.steps), max(0, args.warmup)], threads=cores, timeout=3000)
+    t_step = res["mv_total_s"] / res["mv_reps"]
+    nnz_sample = res["nnz"]
+    # stored (upper-triangle) entries of the full workload: closed form from the expanded count of the generator family
+    nnz_upper_full = workload_upper_nnz(workload)
+    scale = nnz_upper_full / nnz_sample
+    value = 1.0 / (t_step * scale)
+    line = {"metric": "H*v/sec", "value": value, "unit": "H*v/s", "impl": "reference", "n_gpus": 0, "steps": res["mv_reps"],
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_step * scale, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64 (complex128 values and vectors, int64 indices)", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample_desc, "scaled_by_stored_entries": scale},
+            "cpu_baseline": {"value": value, "unit": "H*v/s", "cores": cores, "kind": "reference",
+                             "sample": f"{sample_desc}; {res['mv_reps']} x csr_mat::MultMv at {1e3 * t_step:.2f} ms each "
+                                       f"({1e9 * t_step / nnz_sample:.2f} ns per stored entry), scaled x{scale:.1f} to {workload}; "
+                                       "MKL replaced by the shim's restated mkl_sparse_z_mv (row-partitioned OpenMP), BLAS-1 = OpenBLAS"},
+            "e2e": {"value": value, "unit": "H*v/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_upper_nnz(workload):
+    """Entries the reference stores (upper triangle incl. every diagonal) for a workload: (Z + n) / 2."""
+    from math import comb
+    fam, p = WORKLOADS[workload]
+    if fam == "hubbard":
+        ns = p["Lx"] * p["Ly"]
+        n = comb(ns, p["nup"]) * comb(ns, p["ndn"])
+        bonds = {tuple(sorted(b)) for b in square_bonds(p["Lx"], p["Ly"])}
+        # each undirected bond, each spin: states with exactly one of the two sites occupied by that spin
+        z_off = 0
+        for _ in bonds:
+            z_off += 2 * comb(ns - 2, p["nup"] - 1) * comb(ns, p["ndn"]) + 2 * comb(ns - 2, p["ndn"] - 1) * comb(ns, p["nup"])
+        return (z_off + n + n) // 2
+    L = p["L"]
+    n = comb(L, L // 2)
+    z_off = L * 2 * comb(L - 2, L // 2 - 1)
+    return (z_off + n + n) // 2
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def build_matrix(qb, workload, row_range=None, flags=0):
+    fam, p = WORKLOADS[workload]
+    import numpy as np
+    L = qb.lib()
+    h = C.c_void_p()
+    lo, hi = (0, -1) if row_range is None else row_range
+    if fam == "hubbard":
+        bonds = np.array(square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
+        rc = L.qbgpu_build_hubbard(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data,
+                                   p["t"], p["U"], 1, flags, lo, hi)
+    else:
+        n = p["L"]
+        bonds = np.array([(x, (x + 1) % n) for x in range(n)], dtype=np.int32).ravel()
+        rc = L.qbgpu_build_heisenberg(C.byref(h), n, n // 2, n, bonds.ctypes.data, 1.0, 1, flags, lo, hi)
+    if rc != 0:
+        raise RuntimeError(L.qbgpu_last_error().decode())
+    return qb.csr_mat._adopt(h, True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("QB_WORKLOAD", "hubbard4x4"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-lanczos", action="store_true", help="skip the E0 time-to-solution leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, args.workload)
+        return
+
+    import numpy as np
+    import torch
+    import quantum_basis_b200 as qb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libqbgpu has no CPU fallback")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L = qb.lib()
+    assert L.qbgpu_init(local_rank) == 0, L.qbgpu_last_error()
+    stream = torch.cuda.current_stream()
+    assert L.qbgpu_set_stream(C.c_void_p(stream.cuda_stream)) == 0
+
+    if world > 1:
+        from quantum_basis_b200 import dist as qdist
+        return qdist.bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_peak, ClockSampler, workload_upper_nnz)
+
+    # ---------------------------------------------------------------- single GPU
+    t0 = time.time()
+    M = build_matrix(qb, args.workload)
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    inf = M.info
+    n, Z = inf.n, inf.nnz_stored
+    s_val = 8 if inf.val_is_real else 16
+    s_vec = 16
+    B = algorithmic_bytes(Z, n, n, s_val, s_vec)
+    need_flush = B < 2 * L2_BYTES
+    flush_buf = torch.empty(int(256e6) // 4, dtype=torch.float32, device="cuda") if need_flush else None
+
+    x = qb.vec_randomize(n, 1, device=True)
+    y = qb.DeviceVector(n)
+    for _ in range(args.warmup):
+        M.MultMv(x, y)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.qbgpu_kernel_launches(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.time()
+    for k in range(args.steps):
+        if need_flush:
+            flush_buf.zero_()
+        ev[k][0].record(stream)
+        M.MultMv(x, y)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    wall = time.time() - wall0
+    launches = int(L.qbgpu_kernel_launches(0))
+    per_step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(per_step_ms)
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+    peak, peak_src = measured_peak()
+    achieved = B / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------------------------------------------------------- e2e: host vectors through the reference-facing call
+    xh_t = torch.empty(2 * n, dtype=torch.float64).pin_memory()
+    yh_t = torch.empty(2 * n, dtype=torch.float64).pin_memory()
+    xh = xh_t.numpy().view(np.complex128)
+    yh = yh_t.numpy().view(np.complex128)
+    xh[:] = x.to_numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        M.MultMv(xh, yh)
+    torch.cuda.synchronize()
+    te = time.time()
+    for _ in range(e2e_steps):
+        M.MultMv(xh, yh)                  # H2D(x) + product + D2H(y), synchronous like the reference's call
+    torch.cuda.synchronize()
+    e2e_s = (time.time() - te) / e2e_steps
+    y_dev = y.to_numpy()
+    assert np.array_equal(y_dev, yh), "host-vector and device-vector products disagree"
+
+    line = {"metric": "H*v/sec", "value": value, "unit": "H*v/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "reference_upper_entries": workload_upper_nnz(args.workload),
+                       "S_val": s_val, "S_vec": s_vec, "lanes": inf.lanes, "l2": "flush between steps" if need_flush else "inputs larger than L2",
+                       "matrix_bytes": inf.device_bytes},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0},
+            "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
+                    "ms_per_step": 1e3 * e2e_s},
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+            "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds}}
+
+    # ---------------------------------------------------------------- Lanczos iterations/s and E0 time-to-solution
+    if not args.no_lanczos:
+        v = qb.DeviceVector(2 * n)
+        rnd = L.qbgpu_vec_randomize_z
+        assert rnd(n, C.c_void_p(v.ptr), 1) == 0
+        hess = np.zeros(2000)
+        torch.cuda.synchronize()
+        tl = time.time()
+        m = qb.lanczos(0, 999, 1000, n, M, v, hess, "sr_val0")
+        torch.cuda.synchronize()
+        tl = time.time() - tl
+        ritz, _ = qb.hess_eigen(hess, 1000, m)
+        line["lanczos"] = {"steps": m, "seconds": tl, "iters_per_s": m / tl, "E0": float(ritz[0]),
+                           "algorithmic_bytes_per_iter": Z * (s_val + 4) + 8 * (n + 1) + 6 * n * s_vec,
+                           "achieved_GBs": (Z * (s_val + 4) + 8 * (n + 1) + 6 * n * s_vec) * m / tl / 1e9}
+        v.free()
+
+    # ---------------------------------------------------------------- CPU baseline beside it (bounded sample)
+    if not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as O
+            fam, p = WORKLOADS[args.workload]
+            cores = os.cpu_count() or 1
+            if O.have_qb_ref():
+                sample_args = ["hubbard", 4, 3, 6, 6, 1.0, 1.1] if fam == "hubbard" else ["heis_chain", min(p["L"], 22), "sz", 0]
+                res = O.run_qb_ref(sample_args + ["--time-mv", 5, 2], threads=cores, timeout=1200)
+                t_step = res["mv_total_s"] / res["mv_reps"]
+                scale = workload_upper_nnz(args.workload) / res["nnz"]
+                line["cpu_baseline"] = {"value": 1.0 / (t_step * scale), "unit": "H*v/s", "cores": cores, "kind": "reference",
+                                        "sample": f"qb_ref {' '.join(map(str, sample_args))}: dim {res['dim']}, {res['nnz']} stored entries, "
+                                                  f"{1e3 * t_step:.2f} ms per csr_mat::MultMv ({1e9 * t_step / res['nnz']:.2f} ns/entry), scaled x{scale:.1f} "
+                                                  f"by stored entries to {args.workload}; shim-restated mkl_sparse_z_mv, OpenMP {cores} threads"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/qb_ref not built"}
+        except Exception as e:   # the baseline is informative; never lose the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

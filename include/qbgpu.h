@@ -1,0 +1,198 @@
+/* include/qbgpu.h -- C ABI of the B200-native H*v path (libqbgpu.so).
+ *
+ * Drop-in boundary for wztzjhn/quantum_basis.  The reference keeps its sparse backend behind an opaque MKL
+ * inspector-executor handle (`sparse_matrix_t handle`, src/qbasis.h:985): created in csr_mat's constructors
+ * (src/sparse.cc:129,258), used by csr_mat<T>::MultMv2 (src/sparse.cc:262-289) and destroyed in destroy()/dtor
+ * (src/sparse.cc:165,185).  This header declares the same quartet (create / mv / destroy) for a B200, plus the
+ * device-resident Krylov loops that replace the bodies of lanczos(), eigenvec_CG() and energy_scale()
+ * (src/lanczos.cc:134-341, src/kpm.cc:45-88) so that one Krylov step makes one pass over H and the vectors.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; complex numbers are interleaved (re,im) doubles, layout-compatible with
+ *     std::complex<double> / MKL_Complex16; indices on the host side are int64 (MKL_INT under -DMKL_ILP64).
+ *   - every function returns 0 on success, non-zero on failure; qbgpu_last_error() gives the message (the C++
+ *     adaptor include/qbgpu_csr_mat.hpp turns it into std::runtime_error like src/sparse.cc:130,259,288).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with QBGPU_ERR_CUDA.
+ *   - `where` says where vector pointers live: QBGPU_HOST (the reference's calling convention: std::vector /
+ *     ARPACK workd) or QBGPU_DEVICE (already resident, e.g. a torch tensor's data_ptr).
+ *   - all work is issued on one CUDA stream per thread context (qbgpu_set_stream to adopt the caller's).
+ */
+#ifndef QBGPU_H
+#define QBGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QBGPU_OK            0
+#define QBGPU_ERR_ARG       1
+#define QBGPU_ERR_CUDA      2
+#define QBGPU_ERR_ALLOC     3
+#define QBGPU_ERR_STATE     4
+#define QBGPU_ERR_NUMERIC   5   /* breakdown, non-Hermitian input, ... */
+
+#define QBGPU_HOST   0
+#define QBGPU_DEVICE 1
+
+/* create flags */
+#define QBGPU_KEEP_COMPLEX   1   /* do not demote an all-real complex matrix to fp64 values */
+#define QBGPU_NO_AUTOTUNE    2   /* skip the kernel-variant timing pass at create */
+#define QBGPU_FORMAT_CSR     4   /* force the expanded-CSR kernels  */
+#define QBGPU_FORMAT_SELL    8   /* force the SELL-C-sigma kernels  */
+
+typedef struct qbgpu_matrix *qbgpu_matrix_t;     /* replaces `sparse_matrix_t handle` (src/qbasis.h:985) */
+
+typedef struct {
+    int64_t n;              /* global dimension                                                    */
+    int64_t row_lo, row_hi; /* rows held by this handle ([0,n) unless created as a shard)          */
+    int64_t nnz_stored;     /* entries in the device layout (full expanded Hermitian rows)         */
+    int64_t nnz_input;      /* entries of the host CSR it was created from (upper triangle if sym) */
+    int     val_is_real;    /* 1: values stored as fp64 (input was real or all imaginary parts == 0) */
+    int     api_is_complex; /* 1: created through a z entry point                                  */
+    int     format;         /* QBGPU_FORMAT_CSR or QBGPU_FORMAT_SELL                               */
+    int     lanes;          /* threads per row chosen for the CSR-vector kernel                    */
+    int64_t device_bytes;   /* HBM held by the matrix                                              */
+    double  upload_seconds, convert_seconds, autotune_seconds;
+} qbgpu_matrix_info;
+
+/* ------------------------------------------------------------------------------------------- context */
+int         qbgpu_init(int device);              /* binds the calling thread to `device`; idempotent          */
+int         qbgpu_finalize(void);
+int         qbgpu_device_count(int *count);
+int         qbgpu_set_stream(void *cuda_stream); /* NULL: back to the context's own stream                    */
+int         qbgpu_synchronize(void);
+const char *qbgpu_last_error(void);
+const char *qbgpu_version(void);
+
+/* --------------------------------------------------------------------------- matrix create / destroy
+ * Replaces mkl_sparse_{d,z}_create_csr as called by create_handle (src/sparse.cc:24-40): 4-array zero-based CSR,
+ * row i = [row_start[i], row_end[i]).  sym_upper != 0 is csr_mat::sym (src/qbasis.h:981): only col >= row is
+ * stored and (i,j>i,v) stands for v at (i,j) and conj(v) at (j,i).  The device copy is independent of the host
+ * arrays (they may be freed, cf. HamMat_csr_repr[0].destroy() in the reference's examples).
+ * The *_shard variants keep only rows [row_lo,row_hi) of the expanded matrix (multi-GPU row partition). */
+int qbgpu_create_dcsr(qbgpu_matrix_t *A, int64_t n, const int64_t *row_start, const int64_t *row_end,
+                      const int64_t *col, const double *val, int sym_upper, int flags);
+int qbgpu_create_zcsr(qbgpu_matrix_t *A, int64_t n, const int64_t *row_start, const int64_t *row_end,
+                      const int64_t *col, const void *val, int sym_upper, int flags);
+int qbgpu_create_dcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *row_start, const int64_t *row_end,
+                            const int64_t *col, const double *val, int sym_upper, int flags,
+                            int64_t row_lo, int64_t row_hi);
+int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *row_start, const int64_t *row_end,
+                            const int64_t *col, const void *val, int sym_upper, int flags,
+                            int64_t row_lo, int64_t row_hi);
+int qbgpu_destroy(qbgpu_matrix_t A);             /* replaces mkl_sparse_destroy (src/sparse.cc:165,185)        */
+int qbgpu_matrix_get_info(qbgpu_matrix_t A, qbgpu_matrix_info *info);
+/* csr_mat<T>::to_dense (src/sparse.cc:299-315): column-major n x n, complex interleaved when api_is_complex. */
+int qbgpu_to_dense(qbgpu_matrix_t A, void *dense_host);
+/* copy the expanded device rows back (tests): rowptr[n_local+1], col[nnz], val[nnz] (complex unless val_is_real) */
+int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, void *val);
+
+/* nnz-balanced contiguous row partition of the EXPANDED matrix over `parts` shards (host only, no GPU needed):
+ * bounds[parts+1], bounds[0]=0, bounds[parts]=n. */
+int qbgpu_partition_rows(int64_t n, const int64_t *row_start, const int64_t *row_end, const int64_t *col,
+                         int sym_upper, int parts, int64_t *bounds);
+
+/* ------------------------------------------------------------------------------------ H*v products
+ * Replaces mkl_sparse_{d,z}_mv as csr_mat<T>::MultMv2 calls it (src/sparse.cc:287): y = alpha*H*x + beta*y.
+ * MultMv2 is (alpha,beta) = (1,1); MultMv (src/sparse.cc:291-297) is (1,0).  x has n entries; y has the handle's
+ * row_hi-row_lo entries.  A `z` handle with real stored values still takes complex x,y. */
+int qbgpu_dmv(qbgpu_matrix_t A, double alpha, const double *x, double beta, double *y, int where);
+int qbgpu_zmv(qbgpu_matrix_t A, const double alpha[2], const void *x, const double beta[2], void *y, int where);
+/* pin a host range so that `where == QBGPU_HOST` products use asynchronous chunked copies (ARPACK's workd) */
+int qbgpu_host_register(void *ptr, size_t bytes);
+int qbgpu_host_unregister(void *ptr);
+
+/* ------------------------------------------------------------------------------ device vector helpers */
+int qbgpu_malloc(void **dptr, size_t bytes);
+int qbgpu_free(void *dptr);
+int qbgpu_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int qbgpu_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int qbgpu_memset0(void *dptr, size_t bytes);
+/* vec_randomize (src/miscellaneous.cc:371-388) generated on the device, bit-identical element values */
+int qbgpu_vec_randomize_d(int64_t n, double *x_dev, uint32_t seed);
+int qbgpu_vec_randomize_z(int64_t n, void *x_dev, uint32_t seed);
+/* BLAS-1 on device vectors, the calls lanczos.cc makes through cblas_* (src/lanczos.cc:10-53). */
+int qbgpu_zdotc(int64_t n, const void *x, const void *y, double result[2]);   /* conj(x).y */
+int qbgpu_ddot(int64_t n, const double *x, const double *y, double *result);
+int qbgpu_dznrm2(int64_t n, const void *x, double *result);
+int qbgpu_dnrm2(int64_t n, const double *x, double *result);
+int qbgpu_zaxpy(int64_t n, const double a[2], const void *x, void *y);
+int qbgpu_daxpy(int64_t n, double a, const double *x, double *y);
+int qbgpu_zscal(int64_t n, const double a[2], void *x);
+int qbgpu_dscal(int64_t n, double a, double *x);
+
+/* -------------------------------------------------------------------------------- fused Krylov loops
+ * Same arguments and meaning as the reference templates; `v` etc. are HOST or DEVICE per `where`.
+ *
+ * qbgpu_lanczos_*: lanczos<T,MAT>(k, np, maxit, m, dim, mat, v, hessenberg, purpose), src/lanczos.cc:134-266,
+ *   for k == 0 and purposes "sr_val0", "sr_val1" (phi0 at v+2n) and "dnmcs".  hessenberg[2*maxit]: b in
+ *   [0,maxit), a in [maxit,2maxit).  On return *m = steps performed; v[(m%2)*n] holds v_m and v[((m+1)%2)*n]
+ *   holds v_{m-1} like the reference (normalised).
+ * qbgpu_eigenvec_cg_*: eigenvec_CG<T,MAT>(dim, maxit, m, mat, E0, accu, v, r, p, pp), src/lanczos.cc:281-341,
+ *   entered with *m == 0.
+ * qbgpu_energy_scale_*: energy_scale<T,MAT>(dim, mat, v, lo, hi, extend, iters), src/kpm.cc:45-88 (start vector
+ *   vec_randomize(seed=1) drawn inside, as the reference does).
+ * qbgpu_kpm_moments_*: NEW (the reference has no Chebyshev code): mu_k = <phi|T_k((H-c)/s)|phi>, k < nmom,
+ *   c=(hi+lo)/2, s=(hi-lo)/2, with the 2n/2n+1 doubling identities (nmom/2 products).
+ * Only single-GPU handles (row_lo == 0, row_hi == n); the sharded loops are driven from
+ * quantum_basis_b200/dist.py through the *_step entry points below. */
+int qbgpu_lanczos_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, double *v,
+                    double *hessenberg, const char *purpose, int where);
+int qbgpu_lanczos_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v,
+                    double *hessenberg, const char *purpose, int where);
+int qbgpu_eigenvec_cg_d(qbgpu_matrix_t A, int64_t maxit, int64_t *m, double E0, double *accu,
+                        double *v, double *r, double *p, double *pp, int where);
+int qbgpu_eigenvec_cg_z(qbgpu_matrix_t A, int64_t maxit, int64_t *m, const double E0[2], double *accu,
+                        void *v, void *r, void *p, void *pp, int where);
+int qbgpu_energy_scale_z(qbgpu_matrix_t A, void *v, double *lo, double *hi, double extend, int64_t iters, int where);
+int qbgpu_energy_scale_d(qbgpu_matrix_t A, double *v, double *lo, double *hi, double extend, int64_t iters, int where);
+int qbgpu_kpm_moments_z(qbgpu_matrix_t A, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where);
+int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double hi, int64_t nmom, double *mu, int where);
+/* hess_eigen (src/lanczos.cc:355-390, order "sr"): host-side tridiagonal Ritz solve used by the stop rule.
+ * ritz[m]; s[m*m] column-major eigenvectors or NULL. */
+int qbgpu_hess_eigen(const double *hessenberg, int64_t maxit, int64_t m, double *ritz, double *s);
+
+/* ------------------------------------------------------------------ step-level entry points (DEVICE only)
+ * One fused pass each; scalars live in a device array `sc` so that no host synchronisation is needed between
+ * them and a collective can be inserted on a slot (multi-GPU: allreduce sc[slot]).  Vector element type follows
+ * the handle (complex for z handles, double for d handles).
+ *
+ *   spmv_fused:  y_i = alpha*(H x)_i + gamma*x_{row_lo+i} + beta*z_i        (z may alias y; z may be NULL if beta==0)
+ *                dots[0,1] = sum conj(x_{row_lo+i}) y_i,  dots[2] = sum |y_i|^2 over the local rows (dots may be NULL)
+ */
+int qbgpu_spmv_fused(qbgpu_matrix_t A, const void *x, const void *z, void *y,
+                     const double alpha[2], const double gamma[2], const double beta[2], double *dots_dev);
+/* Lanczos step pieces on the local rows (row_lo..row_hi) of a (possibly sharded) handle.
+ *   state (8 device doubles): [0]=sx [1]=sz [2]=b_prev [3]=alpha_partial [4],[5]=scratch [6]=norm2_partial [7]=spare
+ *   lanczos_step_a : w = sx*H*(ux) - b_prev*sz*uz  -> uz ;  state[3] = sum Re conj(sx*ux_i) w_i   (local rows)
+ *   lanczos_step_b : w' = uz - state[3]*sx*ux_local -> uz ; state[6] = sum |w'_i|^2
+ *   lanczos_step_c : b = sqrt(state[6]); a_dev[m-1] = state[3]; b_dev[m] = b; rotate (sx,sz,b_prev) <- (1/b,sx,b)
+ * ux is the FULL gathered vector (n entries); uz and the local slice of ux have row_hi-row_lo entries. */
+int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev);
+int qbgpu_lanczos_step_b(qbgpu_matrix_t A, const void *ux_local, void *uz_local, double *state_dev);
+int qbgpu_lanczos_step_c(double *state_dev, double *a_dev, double *b_dev, int64_t m);
+
+/* --------------------------------------------------------------------- on-device Hamiltonian generators
+ * The reference assembles H on the host (model::generate_Ham_sparse_full, src/model.cc:619-716) in Lin-table
+ * order (src/basis.cc:1144-1190).  For the BASELINE sizes the reference's own assembler cannot run,
+ * so these generators build the SAME expanded matrix (same basis order, same values) directly in HBM; they are
+ * checked entry-for-entry against matrices assembled by the compiled reference at sizes it can handle.
+ *   heisenberg: spin-1/2, H = sum_bonds J (S_i.S_j), fixed number of up spins `nup`, bonds[2*nbonds] site pairs.
+ *   hubbard:    single "electron" orbital, H = -t sum_{<ij>,s} (c+_is c_js + h.c.) + U sum n_up n_dn.
+ * row_lo/row_hi select a row shard (0,-1 = all rows). */
+int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int nup, int nbonds, const int32_t *bonds, double J,
+                           int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
+                        double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* dimension of those sectors (host only) */
+int64_t qbgpu_dim_heisenberg(int nsites, int nup);
+int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
+
+/* counters for bench.py's `gpu_launches` (kernels launched by this library since the last reset) */
+int64_t qbgpu_kernel_launches(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBGPU_H */

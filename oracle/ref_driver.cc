@@ -280,15 +280,18 @@ static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, 
             qbasis::vec_randomize(n, x.data(), seed);
             H.MultMv(x.data(), y.data());
             dump_vec(argv[++a], y.data(), sizeof(T) * n);
-        } else if (opt == "--time-mv" && a + 1 < argc) {
-            int reps = atoi(argv[++a]);
+        } else if (opt == "--time-mv" && a + 2 < argc) {
+            /* CPU baseline: the reference's csr_mat::MultMv (src/sparse.cc:291-297) timed REPS times after WARM warm-ups */
+            int reps = atoi(argv[++a]), warm = atoi(argv[++a]);
             std::vector<T> x(n), y(n);
             qbasis::vec_randomize(n, x.data(), 1);
-            for (int w = 0; w < 2; w++) H.MultMv(x.data(), y.data());
+            for (int w = 0; w < warm; w++) H.MultMv(x.data(), y.data());
             std::vector<double> ts;
+            double tall0 = now_s();
             for (int r = 0; r < reps; r++) { double t0 = now_s(); H.MultMv(x.data(), y.data()); ts.push_back(now_s() - t0); }
+            double tall = now_s() - tall0;
             std::sort(ts.begin(), ts.end());
-            js.num("mv_median_s", ts[ts.size() / 2]); js.num("mv_min_s", ts[0]); js.integer("mv_reps", reps);
+            js.num("mv_median_s", ts[ts.size() / 2]); js.num("mv_min_s", ts[0]); js.num("mv_total_s", tall); js.integer("mv_reps", reps);
             js.integer("threads", qb_shim_get_spmv_threads());
         } else if (opt == "--lanczos" && a + 2 < argc) {
             /* reference lanczos(0, maxit-1, maxit, m, dim, H, v, hess, purpose) from vec_randomize(seed=1),
@@ -334,7 +337,7 @@ static void usage() {
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
         "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
-        " matrix actions: --dump F | --mv SEED F | --time-mv REPS | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
+        " matrix actions: --dump F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
     exit(2);
 }
 

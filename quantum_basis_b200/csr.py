@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's interface for the H*v path, over the C ABI (include/qbgpu.h).
+
+Names, argument meaning and error behaviour follow the reference so that parity tests read like its own:
+  csr_mat.MultMv / MultMv2 / to_dense   reference src/sparse.cc:262-315 (qbasis.h:976-1021)
+  lanczos                               src/lanczos.cc:134-266
+  eigenvec_CG                           src/lanczos.cc:281-341
+  hess_eigen                            src/lanczos.cc:355-390
+  energy_scale                          src/kpm.cc:45-88
+  vec_randomize                         src/miscellaneous.cc:371-388
+  locate_E0_lanczos                     src/model.cc:1124-1316 (the csr_mat branch; model's bookkeeping stays host-side)
+Host vectors are numpy arrays (complex128 / float64); device-resident vectors are DeviceVector.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import QbgpuError, check, lib
+
+lanczos_precision = 2e-12      # reference src/miscellaneous.cc:47
+
+
+def _ptr(a):
+    if isinstance(a, DeviceVector):
+        return C.c_void_p(a.ptr)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _where(*arrs):
+    dev = [isinstance(a, DeviceVector) for a in arrs]
+    if all(dev):
+        return _lib.QBGPU_DEVICE
+    if not any(dev):
+        return _lib.QBGPU_HOST
+    raise QbgpuError("mixing host and device vectors in one call")
+
+
+def _host_vec(a, dtype, n=None, name="vector"):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise QbgpuError(f"{name} must be a C-contiguous numpy array of dtype {np.dtype(dtype).name}")
+    if n is not None and a.size < n:
+        raise QbgpuError(f"{name} has {a.size} entries, needs {n}")
+    return a
+
+
+class DeviceVector:
+    """A vector resident in HBM (qbgpu_malloc)."""
+
+    def __init__(self, n, dtype=np.complex128):
+        self.n = int(n)
+        self.dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        check(lib().qbgpu_malloc(C.byref(p), self.n * self.dtype.itemsize))
+        self.ptr = p.value
+        self._owned = True
+
+    @classmethod
+    def from_numpy(cls, a):
+        a = np.ascontiguousarray(a)
+        v = cls(a.size, a.dtype)
+        check(lib().qbgpu_memcpy_h2d(C.c_void_p(v.ptr), C.c_void_p(a.ctypes.data), a.nbytes))
+        return v
+
+    def view(self, offset, n):
+        """A non-owning window [offset, offset+n) (e.g. one column of the reference's v[] workspace)."""
+        w = object.__new__(DeviceVector)
+        w.n, w.dtype, w.ptr, w._owned, w._parent = int(n), self.dtype, self.ptr + offset * self.dtype.itemsize, False, self
+        return w
+
+    def to_numpy(self):
+        out = np.empty(self.n, dtype=self.dtype)
+        check(lib().qbgpu_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr), out.nbytes))
+        return out
+
+    def zero(self):
+        check(lib().qbgpu_memset0(C.c_void_p(self.ptr), self.n * self.dtype.itemsize))
+
+    def free(self):
+        if self._owned and self.ptr:
+            lib().qbgpu_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class csr_mat:
+    """Device-resident counterpart of the reference's csr_mat<T> (qbasis.h:976-1021).
+
+    Constructed from the reference's own arrays: ``dim``, ``ia[dim+1]``, ``ja[nnz]`` (int64), ``val[nnz]`` (float64 ->
+    csr_mat<double>, complex128 -> csr_mat<complex<double>>) and ``sym`` (upper triangle only).  The arrays are
+    uploaded once, like the MKL handle the reference creates in its constructors (src/sparse.cc:129,258).
+    """
+
+    def __init__(self, dim, ia, ja, val, sym, flags=0, rows=None):
+        ia = np.ascontiguousarray(ia, dtype=np.int64)
+        ja = np.ascontiguousarray(ja, dtype=np.int64)
+        val = np.ascontiguousarray(val)
+        if val.dtype not in (np.float64, np.complex128):
+            raise QbgpuError("val must be float64 or complex128")
+        if ia.size != dim + 1:
+            raise QbgpuError("ia must have dim+1 entries")
+        self.dim = int(dim)
+        self.sym = bool(sym)
+        self.dtype = val.dtype
+        self.is_complex = val.dtype == np.complex128
+        h = C.c_void_p()
+        L = lib()
+        rs, re = C.c_void_p(ia.ctypes.data), C.c_void_p(ia.ctypes.data + 8)
+        if rows is None:
+            f = L.qbgpu_create_zcsr if self.is_complex else L.qbgpu_create_dcsr
+            check(f(C.byref(h), dim, rs, re, C.c_void_p(ja.ctypes.data), C.c_void_p(val.ctypes.data), int(self.sym), flags))
+        else:
+            f = L.qbgpu_create_zcsr_shard if self.is_complex else L.qbgpu_create_dcsr_shard
+            check(f(C.byref(h), dim, rs, re, C.c_void_p(ja.ctypes.data), C.c_void_p(val.ctypes.data), int(self.sym), flags,
+                    int(rows[0]), int(rows[1])))
+        self.handle = h
+
+    @classmethod
+    def _adopt(cls, handle, is_complex):
+        self = object.__new__(cls)
+        self.handle = handle
+        self.is_complex = bool(is_complex)
+        self.dtype = np.dtype(np.complex128 if is_complex else np.float64)
+        info = self.info
+        self.dim = info.n
+        self.sym = True
+        return self
+
+    @property
+    def info(self):
+        inf = _lib.MatrixInfo()
+        check(lib().qbgpu_matrix_get_info(self.handle, C.byref(inf)))
+        return inf
+
+    @property
+    def nrows_local(self):
+        inf = self.info
+        return inf.row_hi - inf.row_lo
+
+    def dimension(self):
+        return self.dim
+
+    # y = alpha*H*x + beta*y : what csr_mat::MultMv2 asks of mkl_sparse_?_mv (src/sparse.cc:287)
+    def _mv(self, alpha, x, beta, y):
+        if self.handle is None:
+            raise QbgpuError("matrix was destroyed")
+        where = _where(x, y)
+        if where == _lib.QBGPU_HOST:
+            _host_vec(x, self.dtype, self.dim, "x")
+            _host_vec(y, self.dtype, self.nrows_local, "y")
+        if self.is_complex:
+            a = (C.c_double * 2)(alpha.real, alpha.imag)
+            b = (C.c_double * 2)(beta.real, beta.imag)
+            check(lib().qbgpu_zmv(self.handle, a, _ptr(x), b, _ptr(y), where))
+        else:
+            check(lib().qbgpu_dmv(self.handle, float(alpha), _ptr(x), float(beta), _ptr(y), where))
+
+    def MultMv2(self, x, y):
+        """y = H*x + y (src/sparse.cc:262-289)."""
+        self._mv(complex(1.0), x, complex(1.0), y)
+
+    def MultMv(self, x, y):
+        """y = H*x (src/sparse.cc:291-297)."""
+        self._mv(complex(1.0), x, complex(0.0), y)
+
+    def to_dense(self):
+        """Column-major dense copy, returned as an (n, n) array with out[row, col] (src/sparse.cc:299-315)."""
+        out = np.zeros(self.dim * self.dim, dtype=self.dtype)
+        check(lib().qbgpu_to_dense(self.handle, C.c_void_p(out.ctypes.data)))
+        return out.reshape(self.dim, self.dim).T
+
+    def download_expanded(self):
+        inf = self.info
+        nloc = inf.row_hi - inf.row_lo
+        rowptr = np.zeros(nloc + 1, dtype=np.int64)
+        col = np.zeros(inf.nnz_stored, dtype=np.int32)
+        val = np.zeros(inf.nnz_stored, dtype=np.float64 if inf.val_is_real else np.complex128)
+        check(lib().qbgpu_download_expanded(self.handle, C.c_void_p(rowptr.ctypes.data), C.c_void_p(col.ctypes.data),
+                                            C.c_void_p(val.ctypes.data)))
+        return rowptr, col, val
+
+    def destroy(self):
+        """Explicitly free the device copy (csr_mat::destroy, src/sparse.cc:150-169)."""
+        if getattr(self, "handle", None) is not None:
+            check(lib().qbgpu_destroy(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def vec_randomize(n, seed=1, dtype=np.complex128, device=False):
+    """src/miscellaneous.cc:371-388, generated on the device."""
+    v = DeviceVector(n, dtype)
+    f = lib().qbgpu_vec_randomize_z if np.dtype(dtype) == np.complex128 else lib().qbgpu_vec_randomize_d
+    check(f(n, C.c_void_p(v.ptr), seed))
+    if device:
+        return v
+    out = v.to_numpy()
+    v.free()
+    return out
+
+
+def hess_eigen(hessenberg, maxit, m, order="sr"):
+    """src/lanczos.cc:355-390 -> (ritz[m], s[m, m]) with s[:, j] the j-th Ritz vector."""
+    if order.lower() not in ("sr", "sa"):
+        raise QbgpuError("only order 'sr' is implemented")
+    hess = _host_vec(np.ascontiguousarray(hessenberg, dtype=np.float64), np.float64, 2 * maxit, "hessenberg")
+    ritz = np.zeros(m)
+    s = np.zeros(m * m)
+    check(lib().qbgpu_hess_eigen(_ptr(hess), maxit, m, _ptr(ritz), _ptr(s)))
+    return ritz, s.reshape(m, m).T
+
+
+def lanczos(k, np_, maxit, dim, mat, v, hessenberg, purpose):
+    """lanczos<T,MAT>(k, np, maxit, m, dim, mat, v, hessenberg, purpose); returns m (src/lanczos.cc:134-266)."""
+    if dim != mat.dim:
+        raise QbgpuError("dim does not match the matrix")
+    hess = _host_vec(hessenberg, np.float64, 2 * maxit, "hessenberg")
+    nvec = 3 if "val1" in purpose else 2
+    where = _where(v)
+    if where == _lib.QBGPU_HOST:
+        _host_vec(v, mat.dtype, nvec * dim, "v")
+    m = C.c_int64(0)
+    f = lib().qbgpu_lanczos_z if mat.is_complex else lib().qbgpu_lanczos_d
+    check(f(mat.handle, k, np_, maxit, C.byref(m), _ptr(v), _ptr(hess), purpose.encode(), where))
+    return m.value
+
+
+def eigenvec_CG(dim, maxit, m, mat, E0, v, r, p, pp):
+    """eigenvec_CG<T,MAT>(dim, maxit, m, mat, E0, accu, v, r, p, pp); returns (m, accu) (src/lanczos.cc:281-341)."""
+    if dim != mat.dim:
+        raise QbgpuError("dim does not match the matrix")
+    where = _where(v, r, p, pp)
+    if where == _lib.QBGPU_HOST:
+        for name, a in (("v", v), ("r", r), ("p", p), ("pp", pp)):
+            _host_vec(a, mat.dtype, dim, name)
+    mm = C.c_int64(m)
+    accu = C.c_double(0.0)
+    if mat.is_complex:
+        e = (C.c_double * 2)(complex(E0).real, complex(E0).imag)
+        check(lib().qbgpu_eigenvec_cg_z(mat.handle, maxit, C.byref(mm), e, C.byref(accu), _ptr(v), _ptr(r), _ptr(p), _ptr(pp), where))
+    else:
+        check(lib().qbgpu_eigenvec_cg_d(mat.handle, maxit, C.byref(mm), float(E0), C.byref(accu), _ptr(v), _ptr(r), _ptr(p), _ptr(pp), where))
+    return mm.value, accu.value
+
+
+def energy_scale(dim, mat, v, extend=0.1, iters=128):
+    """energy_scale<T,MAT>(dim, mat, v, lo, hi, extend, iters); returns (lo, hi) (src/kpm.cc:45-88)."""
+    where = _where(v)
+    if where == _lib.QBGPU_HOST:
+        _host_vec(v, mat.dtype, 2 * dim, "v")
+    lo, hi = C.c_double(), C.c_double()
+    f = lib().qbgpu_energy_scale_z if mat.is_complex else lib().qbgpu_energy_scale_d
+    check(f(mat.handle, _ptr(v), C.byref(lo), C.byref(hi), extend, iters, where))
+    return lo.value, hi.value
+
+
+def kpm_moments(mat, phi, lo, hi, nmom):
+    """Chebyshev moments mu_k = <phi|T_k((H-c)/s)|phi> (new functionality; the reference has none)."""
+    where = _where(phi)
+    if where == _lib.QBGPU_HOST:
+        _host_vec(phi, mat.dtype, mat.dim, "phi")
+    mu = np.zeros(nmom)
+    f = lib().qbgpu_kpm_moments_z if mat.is_complex else lib().qbgpu_kpm_moments_d
+    check(f(mat.handle, _ptr(phi), lo, hi, nmom, _ptr(mu), where))
+    return mu
+
+
+def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000):
+    """The csr_mat branch of model<T>::locate_E0_lanczos (src/model.cc:1124-1316): E0 by simple Lanczos, ground-state
+    vector by CG, optionally E1 (re-orthogonalised Lanczos) and its vector.  Everything stays on the device; returns a
+    dict with eigenvals, eigenvecs (host arrays), step counts and accuracies."""
+    if not (0 < nev <= 2 and nev - 1 <= ncv <= nev):
+        raise QbgpuError("need 0 < nev <= 2 and nev-1 <= ncv <= nev")          # the reference's assert, :1141
+    n, dt, seed = mat.dim, mat.dtype, 1
+    out = {"eigenvals": [], "eigenvecs": []}
+    v = DeviceVector((5 if ncv == 2 else 4 if ncv > 0 else 2) * n, dt)
+    col = lambda j: v.view(j * n, n)                                           # noqa: E731
+    rnd = lib().qbgpu_vec_randomize_z if mat.is_complex else lib().qbgpu_vec_randomize_d
+    check(rnd(n, C.c_void_p(col(0).ptr), seed))                                # :1165
+    hess = np.zeros(2 * maxit)
+    m = lanczos(0, maxit - 1, maxit, n, mat, v, hess, "sr_val0")               # :1176-1181
+    ritz, s = hess_eigen(hess, maxit, m)
+    E0 = ritz[0]
+    out["eigenvals"].append(E0)
+    out["lanczos_steps"] = m
+    out["lanczos_accuracy"] = abs(hess[m] * s[m - 1, 0])
+    if ncv == 0:
+        return out
+    check(rnd(n, C.c_void_p(col(2).ptr), seed))                                # :1209
+    mcg, accu = eigenvec_CG(n, maxit, 0, mat, E0, col(2), col(0), col(1), col(3))   # :1216-1217
+    out["cg_steps"], out["cg_accuracy"] = mcg, accu
+    if nev == 2:                                                               # :1233-1265
+        check(rnd(n, C.c_void_p(col(0).ptr), seed))
+        L = lib()
+        if mat.is_complex:
+            d = (C.c_double * 2)()
+            check(L.qbgpu_zdotc(n, C.c_void_p(col(2).ptr), C.c_void_p(col(0).ptr), d))
+            na = (C.c_double * 2)(-d[0], -d[1])
+            check(L.qbgpu_zaxpy(n, na, C.c_void_p(col(2).ptr), C.c_void_p(col(0).ptr)))
+            nr = C.c_double()
+            check(L.qbgpu_dznrm2(n, C.c_void_p(col(0).ptr), C.byref(nr)))
+            check(L.qbgpu_zscal(n, (C.c_double * 2)(1.0 / nr.value, 0.0), C.c_void_p(col(0).ptr)))
+        else:
+            d = C.c_double()
+            check(L.qbgpu_ddot(n, C.c_void_p(col(2).ptr), C.c_void_p(col(0).ptr), C.byref(d)))
+            check(L.qbgpu_daxpy(n, -d.value, C.c_void_p(col(2).ptr), C.c_void_p(col(0).ptr)))
+            nr = C.c_double()
+            check(L.qbgpu_dnrm2(n, C.c_void_p(col(0).ptr), C.byref(nr)))
+            check(L.qbgpu_dscal(n, 1.0 / nr.value, C.c_void_p(col(0).ptr)))
+        hess[:] = 0.0
+        m1 = lanczos(0, maxit - 1, maxit, n, mat, v, hess, "sr_val1")
+        ritz, s = hess_eigen(hess, maxit, m1)
+        out["eigenvals"].append(ritz[0])
+        out["gap"] = ritz[0] - E0
+        out["lanczos_steps_E1"] = m1
+    out["eigenvecs"].append(col(2).to_numpy())
+    if ncv == 2:                                                               # :1275-1315
+        check(rnd(n, C.c_void_p(col(3).ptr), seed + 7))
+        mcg1, accu1 = eigenvec_CG(n, maxit, 0, mat, out["eigenvals"][1], col(3), col(0), col(1), col(4))
+        out["cg_steps_E1"], out["cg_accuracy_E1"] = mcg1, accu1
+        v1 = col(3).to_numpy()
+        if out["gap"] < lanczos_precision:                                     # orthogonalise a degenerate pair, :1302-1311
+            v0 = out["eigenvecs"][0]
+            v1 = v1 - np.vdot(v0, v1) * v0
+            v1 /= np.linalg.norm(v1)
+        out["eigenvecs"].append(v1)
+    v.free()
+    return out

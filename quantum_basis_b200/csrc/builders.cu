@@ -1,0 +1,350 @@
+// quantum_basis_b200/csrc/builders.cu -- on-device Hamiltonian generators in the reference's Lin-table order.
+//
+// The reference enumerates the basis on the host (src/basis.cc:998-1110), orders it by (label of the odd-numbered
+// sites, label of the even-numbered sites) -- the Lin-table convention, src/basis.cc:1144-1190, labels from
+// mbasis_elem::label_sub, src/basis.cc:428-450 -- and assembles H row by row by applying every Hamiltonian term
+// to the row's basis state (model::generate_Ham_sparse_full, src/model.cc:619-686; fermion signs from oprXphi,
+// src/basis.cc:2717-2731: parity of the fermions on sites below the operator's site, operators applied right to
+// left).  At the BASELINE sizes that assembler cannot run (> 140 GB of LIL nodes for the 4x4 Hubbard
+// model), so the same matrix is generated here directly in its expanded device layout: one thread per row
+// re-derives the row's basis state from its index (binary search in the Jb table + class-list lookup), applies
+// the bond terms with bit operations, looks the columns up through the same Ja/Jb tables, and sorts the row.
+// tests/test_builders.py checks the result entry for entry against matrices assembled by the compiled reference.
+#include "internal.hpp"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
+namespace qb {
+
+static double wall_b() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+constexpr int kBBlock = 128;
+constexpr int kMaxBonds = 256;
+
+// Tables describing the sector.  Site s lives on sublattice A (even s, position s/2) or B (odd s, position s/2);
+// a sublattice label packs `bps` bits per site (bps = 1: spin-1/2 digit; bps = 2: electron digit = up + 2*dn).
+struct SectorTables {
+    int nsites, bps, nA, nB;
+    int t0, t1;                       // conserved counts: (#digit-1 sites, 0) for spins, (N_up, N_dn) for electrons
+    int64_t dim;
+    const int64_t *Jb;                // [sizeB + 1] first row index of each B label (Lin_Jb)
+    const int32_t *rankA;             // [sizeA] rank of an A label inside its class (Lin_Ja relative to the class)
+    const uint32_t *alist;            // A labels grouped by class, ascending inside a class
+    const int32_t *class_off;         // [(nA+1)*(nA+1)] offset of class (c0,c1) in alist
+    uint32_t sizeB;
+};
+
+struct Bond { int i, j; int w; };    // site pair with multiplicity (duplicates in the caller's list are merged)
+
+struct ModelParams {
+    int kind;                         // 0 heisenberg, 1 hubbard
+    double J, t, U;
+    int nbonds;
+    Bond bonds[kMaxBonds];
+};
+
+__device__ __forceinline__ void label_counts(uint32_t lab, int bps, int &c0, int &c1)
+{
+    if (bps == 1) { c0 = __popc(lab); c1 = 0; }
+    else { c0 = __popc(lab & 0x55555555u); c1 = __popc(lab & 0xAAAAAAAAu); }
+}
+
+__device__ __forceinline__ void unrank_row(const SectorTables &S, int64_t row, uint32_t &la, uint32_t &lb)
+{
+    // largest lb with Jb[lb] <= row  (empty B labels share their successor's offset and are skipped)
+    uint32_t lo = 0, hi = S.sizeB;                          // answer in [lo, hi)
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.Jb[mid] <= row) lo = mid; else hi = mid; }
+    lb = lo;
+    int cb0, cb1;
+    label_counts(lb, S.bps, cb0, cb1);
+    const int32_t off = S.class_off[(S.t0 - cb0) * (S.nA + 1) + (S.t1 - cb1)];
+    la = S.alist[off + (int32_t)(row - S.Jb[lb])];
+}
+
+__device__ __forceinline__ int64_t col_of(const SectorTables &S, uint32_t la, uint32_t lb) { return S.Jb[lb] + S.rankA[la]; }
+
+// parity of the fermions on sites < s (electron digits 0,1,2,3 carry 0,1,1,2 fermions: popcount of the 2-bit digit)
+__device__ __forceinline__ int parity_below(uint32_t la, uint32_t lb, int s)
+{
+    const int ka = (s + 1) >> 1, kb = s >> 1;               // A sites 0,2,..,<s : ceil(s/2) of them; B sites: floor(s/2)
+    const uint32_t ma = ka >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ka)) - 1u);
+    const uint32_t mb = kb >= 16 ? 0xFFFFFFFFu : ((1u << (2 * kb)) - 1u);
+    return (__popc(la & ma) + __popc(lb & mb)) & 1;
+}
+
+// Enumerate the off-diagonal entries of the row whose basis state is (la, lb); returns the diagonal value.
+// emit(col, val) is called once per entry; distinct calls give distinct columns.
+template <class Emit>
+__device__ __forceinline__ double row_entries(const SectorTables &S, const ModelParams &M, uint32_t la, uint32_t lb, Emit emit)
+{
+    double diag = 0.0;
+    if (M.kind == 0) {
+        // H = sum_b J (S_i.S_j): diagonal J*Sz_i*Sz_j (digit 0 -> +1/2, 1 -> -1/2); off-diagonal J/2 on antiparallel pairs
+        for (int b = 0; b < M.nbonds; b++) {
+            const int i = M.bonds[b].i, j = M.bonds[b].j;
+            const uint32_t bi = 1u << (i >> 1), bj = 1u << (j >> 1);
+            const int di = ((i & 1) ? lb : la) & bi ? 1 : 0;
+            const int dj = ((j & 1) ? lb : la) & bj ? 1 : 0;
+            const double zz = (di == dj) ? 0.25 * M.J : -0.25 * M.J;
+            double off = 0.0;
+            for (int r = 0; r < M.bonds[b].w; r++) { diag += zz; off += 0.5 * M.J; }
+            if (di != dj) {
+                uint32_t na = la, nb = lb;
+                if (i & 1) nb ^= bi; else na ^= bi;
+                if (j & 1) nb ^= bj; else na ^= bj;
+                emit(col_of(S, na, nb), off);
+            }
+        }
+    } else {
+        // H = -t sum_{b,s} (c+_is c_js + h.c.) + U sum_i n_up n_dn ; digit = up + 2*dn
+        const uint32_t dbl = (la & (la >> 1) & 0x55555555u);
+        const uint32_t dbl_b = (lb & (lb >> 1) & 0x55555555u);
+        const int ndbl = __popc(dbl) + __popc(dbl_b);
+        for (int r = 0; r < ndbl; r++) diag += M.U;
+        for (int b = 0; b < M.nbonds; b++) {
+            double amp = 0.0;
+            for (int r = 0; r < M.bonds[b].w; r++) amp += -M.t;
+            for (int dir = 0; dir < 2; dir++) {
+                const int to = dir ? M.bonds[b].j : M.bonds[b].i, from = dir ? M.bonds[b].i : M.bonds[b].j;
+                for (int sp = 0; sp < 2; sp++) {            // sp 0: up (bit 0 of the digit), 1: dn (bit 1)
+                    const uint32_t bf = 1u << (2 * (from >> 1) + sp), bt = 1u << (2 * (to >> 1) + sp);
+                    const uint32_t lf = (from & 1) ? lb : la, lt = (to & 1) ? lb : la;
+                    if (!(lf & bf) || (lt & bt)) continue;
+                    // c_{from,sp}: sign from fermions below `from`; local element -1 for c_dn on a doubly occupied site
+                    int sg = parity_below(la, lb, from);
+                    if (sp == 1 && (lf & (1u << (2 * (from >> 1))))) sg ^= 1;
+                    uint32_t na = la, nb = lb;
+                    if (from & 1) nb ^= bf; else na ^= bf;
+                    // c+_{to,sp} on the intermediate state
+                    sg ^= parity_below(na, nb, to);
+                    const uint32_t lt2 = (to & 1) ? nb : na;
+                    if (sp == 1 && (lt2 & (1u << (2 * (to >> 1))))) sg ^= 1;
+                    if (to & 1) nb ^= bt; else na ^= bt;
+                    emit(col_of(S, na, nb), sg ? -amp : amp);
+                }
+            }
+        }
+    }
+    return diag;
+}
+
+__global__ void __launch_bounds__(kBBlock) build_count_kernel(SectorTables S, const ModelParams *Mp, int64_t row_lo, int64_t nloc, int64_t *len)
+{
+    __shared__ ModelParams M;
+    for (int k = threadIdx.x; k < (int)(sizeof(ModelParams) / 4); k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= nloc; r += (int64_t)gridDim.x * blockDim.x) {
+        if (r == nloc) { len[r] = 0; continue; }
+        uint32_t la, lb;
+        unrank_row(S, row_lo + r, la, lb);
+        int cnt = 1;                                        // the diagonal is always stored (src/sparse.cc:44-54)
+        row_entries(S, M, la, lb, [&](int64_t, double) { cnt++; });
+        len[r] = cnt;
+    }
+}
+
+template <typename ValT>
+__global__ void __launch_bounds__(kBBlock) build_fill_kernel(SectorTables S, const ModelParams *Mp, int64_t row_lo, int64_t nloc,
+                                                             const int64_t *__restrict__ rowptr, int32_t *col, ValT *val)
+{
+    __shared__ ModelParams M;
+    for (int k = threadIdx.x; k < (int)(sizeof(ModelParams) / 4); k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t la, lb;
+        unrank_row(S, row_lo + r, la, lb);
+        const int64_t s = rowptr[r];
+        int cnt = 1;
+        auto put = [&](int64_t at, int32_t c, double v) {
+            col[at] = c;
+            if constexpr (sizeof(ValT) == 16) val[at] = make_double2(v, 0.0); else val[at] = v;
+        };
+        // insertion into the sorted prefix of the row (rows are short: 1 + number of active bond terms)
+        auto insert = [&](int64_t c64, double v) {
+            const int32_t c = (int32_t)c64;
+            int64_t p = s + cnt - 1;
+            while (p >= s && col[p] > c) { col[p + 1] = col[p]; val[p + 1] = val[p]; p--; }
+            put(p + 1, c, v);
+            cnt++;
+        };
+        put(s, (int32_t)(row_lo + r), 0.0);                 // diagonal placeholder, value patched below
+        const double diag = row_entries(S, M, la, lb, insert);
+        for (int64_t p = s; p < s + cnt; p++)
+            if (col[p] == (int32_t)(row_lo + r)) { put(p, (int32_t)(row_lo + r), diag); break; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host-side tables
+struct HostTables {
+    int nsites = 0, bps = 1, nA = 0, nB = 0, t0 = 0, t1 = 0;
+    int64_t dim = 0;
+    std::vector<int64_t> Jb;
+    std::vector<int32_t> rankA, class_off;
+    std::vector<uint32_t> alist;
+};
+
+static void counts_host(uint32_t lab, int bps, int &c0, int &c1)
+{
+    if (bps == 1) { c0 = __builtin_popcount(lab); c1 = 0; }
+    else { c0 = __builtin_popcount(lab & 0x55555555u); c1 = __builtin_popcount(lab & 0xAAAAAAAAu); }
+}
+
+static int make_tables(int nsites, int bps, int t0, int t1, HostTables &T)
+{
+    T.nsites = nsites; T.bps = bps; T.nA = (nsites + 1) / 2; T.nB = nsites / 2; T.t0 = t0; T.t1 = t1;
+    if (bps * T.nA > 24) return fail(QBGPU_ERR_ARG, "builder: sublattice label too wide (max 24 bits per sublattice)");
+    const uint32_t sizeA = 1u << (bps * T.nA), sizeB = 1u << (bps * T.nB);
+    const int nc = T.nA + 1;
+    std::vector<int32_t> csize(nc * nc, 0);
+    T.rankA.assign(sizeA, -1);
+    for (uint32_t a = 0; a < sizeA; a++) { int c0, c1; counts_host(a, bps, c0, c1); T.rankA[a] = csize[c0 * nc + c1]++; }
+    T.class_off.assign(nc * nc, 0);
+    int32_t acc = 0;
+    for (int k = 0; k < nc * nc; k++) { T.class_off[k] = acc; acc += csize[k]; }
+    T.alist.assign(sizeA, 0);
+    for (uint32_t a = 0; a < sizeA; a++) { int c0, c1; counts_host(a, bps, c0, c1); T.alist[T.class_off[c0 * nc + c1] + T.rankA[a]] = a; }
+    T.Jb.assign((size_t)sizeB + 1, 0);
+    int64_t run = 0;
+    for (uint32_t b = 0; b < sizeB; b++) {
+        T.Jb[b] = run;
+        int c0, c1; counts_host(b, bps, c0, c1);
+        const int n0 = t0 - c0, n1 = t1 - c1;
+        if (n0 >= 0 && n0 <= T.nA && n1 >= 0 && n1 <= T.nA && (bps == 2 || n1 == 0)) run += csize[n0 * nc + n1];
+    }
+    T.Jb[sizeB] = run;
+    T.dim = run;
+    return QBGPU_OK;
+}
+
+static int merge_bonds(int nsites, int nbonds, const int32_t *bonds, ModelParams &M)
+{
+    M.nbonds = 0;
+    for (int b = 0; b < nbonds; b++) {
+        int i = bonds[2 * b], j = bonds[2 * b + 1];
+        if (i < 0 || j < 0 || i >= nsites || j >= nsites || i == j) return fail(QBGPU_ERR_ARG, "builder: bad bond");
+        bool found = false;
+        for (int k = 0; k < M.nbonds; k++)
+            if ((M.bonds[k].i == i && M.bonds[k].j == j) || (M.bonds[k].i == j && M.bonds[k].j == i)) { M.bonds[k].w++; found = true; break; }
+        if (!found) {
+            if (M.nbonds == kMaxBonds) return fail(QBGPU_ERR_ARG, "builder: too many bonds");
+            M.bonds[M.nbonds++] = Bond{i, j, 1};
+        }
+    }
+    return QBGPU_OK;
+}
+
+static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags,
+                         int64_t row_lo, int64_t row_hi)
+{
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    if (T.dim <= 0) return fail(QBGPU_ERR_ARG, "builder: empty sector");
+    if (T.dim > 2147483647LL) return fail(QBGPU_ERR_ARG, "builder: dimension exceeds the int32 column range");
+    if (row_hi < 0) row_hi = T.dim;
+    if (row_lo < 0 || row_lo > row_hi || row_hi > T.dim) return fail(QBGPU_ERR_ARG, "builder: bad row shard");
+    const int64_t nloc = row_hi - row_lo;
+    const double t0 = wall_b();
+    auto *A = new qbgpu_matrix;
+    A->n = T.dim; A->row_lo = row_lo; A->row_hi = row_hi; A->api_complex = api_complex != 0;
+    A->val_real = !(flags & QBGPU_KEEP_COMPLEX) || !api_complex;
+
+    int64_t *d_Jb = nullptr, *d_len = nullptr;
+    int32_t *d_rank = nullptr, *d_off = nullptr;
+    uint32_t *d_alist = nullptr;
+    ModelParams *d_M = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_Jb); cudaFree(d_len); cudaFree(d_rank); cudaFree(d_off); cudaFree(d_alist); cudaFree(d_M); cudaFree(d_tmp); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_Jb, sizeof(int64_t) * T.Jb.size()));
+    QB_CU(cudaMalloc(&d_rank, sizeof(int32_t) * T.rankA.size()));
+    QB_CU(cudaMalloc(&d_alist, sizeof(uint32_t) * T.alist.size()));
+    QB_CU(cudaMalloc(&d_off, sizeof(int32_t) * T.class_off.size()));
+    QB_CU(cudaMalloc(&d_M, sizeof(ModelParams)));
+    QB_CU(cudaMemcpyAsync(d_Jb, T.Jb.data(), sizeof(int64_t) * T.Jb.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_rank, T.rankA.data(), sizeof(int32_t) * T.rankA.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_M, &M, sizeof(ModelParams), cudaMemcpyHostToDevice, c.stream));
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = d_Jb; S.rankA = d_rank; S.alist = d_alist; S.class_off = d_off; S.sizeB = (uint32_t)(T.Jb.size() - 1);
+
+    QB_CU(cudaMalloc(&d_len, sizeof(int64_t) * (nloc + 1)));
+    QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (nloc + 1)));
+    int64_t g = (nloc + 1 + kBBlock - 1) / kBBlock;
+    if (g > 148 * 64) g = 148 * 64;
+    build_count_kernel<<<(int)g, kBBlock, 0, c.stream>>>(S, d_M, row_lo, nloc, d_len);
+    QB_LAUNCH_COUNT();
+    size_t tmp_bytes = 0;
+    QB_CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, A->rowptr, nloc + 1, c.stream));
+    QB_CU(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    QB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len, A->rowptr, nloc + 1, c.stream));
+    int64_t nnz = 0;
+    QB_CU(cudaMemcpyAsync(&nnz, A->rowptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+    A->nnz = nnz;
+    A->nnz_input = (nnz + T.dim) / 2;                       // what the reference would store (upper triangle incl. diagonal), full handle
+    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1)));
+    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (nnz ? nnz : 1)));
+    if (A->val_real) build_fill_kernel<double><<<(int)g, kBBlock, 0, c.stream>>>(S, d_M, row_lo, nloc, A->rowptr, A->col, (double *)A->val);
+    else             build_fill_kernel<double2><<<(int)g, kBBlock, 0, c.stream>>>(S, d_M, row_lo, nloc, A->rowptr, A->col, (double2 *)A->val);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+    cleanup();
+#undef QB_CU
+    A->convert_s = wall_b() - t0;
+    if (!(flags & QBGPU_NO_AUTOTUNE)) { int rc = autotune(A); if (rc) { qbgpu_destroy(A); return rc; } } else A->lanes = 8;
+    *out = A;
+    return QBGPU_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int64_t qbgpu_dim_heisenberg(int nsites, int ndown)
+{
+    HostTables T;
+    if (nsites < 2 || ndown < 0 || ndown > nsites || make_tables(nsites, 1, ndown, 0, T)) return -1;
+    return T.dim;
+}
+
+int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn)
+{
+    HostTables T;
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || make_tables(nsites, 2, nup, ndn, T)) return -1;
+    return T.dim;
+}
+
+int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
+                           int api_complex, int flags, int64_t row_lo, int64_t row_hi)
+{
+    if (nsites < 2 || ndown < 0 || ndown > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "build_heisenberg: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 1, ndown, 0, T));
+    static thread_local ModelParams M;
+    M.kind = 0; M.J = J; M.t = 0; M.U = 0;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    return build_generic(A, T, M, api_complex, flags, row_lo, row_hi);
+}
+
+int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U,
+                        int api_complex, int flags, int64_t row_lo, int64_t row_hi)
+{
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "build_hubbard: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 2, nup, ndn, T));
+    static thread_local ModelParams M;
+    M.kind = 1; M.J = 0; M.t = t; M.U = U;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    return build_generic(A, T, M, api_complex, flags, row_lo, row_hi);
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// quantum_basis_b200/csrc/internal.hpp -- types shared by the translation units of libqbgpu.
+#pragma once
+#include "common.cuh"
+#include "../../include/qbgpu.h"
+
+// Device-resident matrix behind qbgpu_matrix_t.
+//
+// HBM layout ("expanded CSR"): the full Hermitian matrix, i.e. the reference's upper triangle plus its
+// materialised conjugate transpose, so that every row is complete and a product needs no atomics:
+//   rowptr[n_local+1]  int64   offsets into col/val (local to this handle: rowptr[0] == 0)
+//   col[nnz]           int32   global column indices, ascending within a row
+//   val[nnz]           fp64 or (re,im) fp64 pairs (fp64 when the input was real or had all imag == 0)
+// n_local = row_hi - row_lo rows of the global n x n matrix (a row shard for multi-GPU runs).
+struct qbgpu_matrix {
+    int64_t n = 0, row_lo = 0, row_hi = 0;
+    int64_t nnz = 0, nnz_input = 0;
+    bool    val_real = false, api_complex = false;
+    int     format = QBGPU_FORMAT_CSR;
+    int     lanes = 8;
+    int64_t *rowptr = nullptr;
+    int32_t *col = nullptr;
+    void    *val = nullptr;
+    double  upload_s = 0, convert_s = 0, autotune_s = 0;
+    int64_t nrows() const { return row_hi - row_lo; }
+    size_t  val_bytes() const { return val_real ? 8 : 16; }
+    size_t  vec_bytes() const { return api_complex ? 16 : 8; }
+};
+
+namespace qb {
+
+// Arguments of the fused product  y_i = alpha*(H x)_i + gamma*x_{row_lo+i} + beta*z_i  (+ running dots).
+// scal_mode 0: alpha/gamma/beta are the immediates below.
+// scal_mode 1 (Lanczos step a): alpha = sc[0], gamma = 0, beta = -sc[2]*sc[1]; dot[0..1] scaled by sc[0].
+struct FusedArgs {
+    const void *x = nullptr;       // full vector, n entries
+    const void *z = nullptr;       // local rows (may alias y), or null
+    void       *y = nullptr;       // local rows
+    double2     alpha = {1.0, 0.0}, gamma = {0.0, 0.0}, beta = {0.0, 0.0};
+    int         scal_mode = 0;
+    const double *sc = nullptr;    // device scalars for scal_mode != 0
+    double     *dots = nullptr;    // device: out[0]=Re sum conj(x)y, out[1]=Im, out[2]=sum|y|^2 ; null = no dots
+};
+
+// spmv.cu
+int launch_spmv(const qbgpu_matrix *A, const FusedArgs &args, int lanes_override = 0);
+int autotune(qbgpu_matrix *A);
+// matrix.cu
+int alloc_matrix_arrays(qbgpu_matrix *A);
+// vecops.cu
+int vec_dotc(int64_t n, bool cplx, const void *x, const void *y, double *out_dev3);   // out: re, im, (unused)
+int vec_nrm2sq(int64_t n, bool cplx, const void *x, double *out_dev);
+int vec_axpy(int64_t n, bool cplx, double2 a, const void *x, void *y);
+int vec_scal(int64_t n, bool cplx, double2 a, void *x);
+int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed);
+int read_scalars(const double *dev, double *host, int count);   // stream-ordered D2H + sync
+int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state);
+int lanczos_step_c(double *state, double *a_dev, double *b_dev, int64_t m);
+int cg_update_vr(int64_t n, bool cplx, const double *sc, void *v, void *r, const void *p, const void *pp);
+int cg_update_p(int64_t n, bool cplx, double *sc, const void *r, void *p);
+int scale_copy(int64_t n, bool cplx, const double *scale_dev, double scale_imm, const void *src, void *dst);
+
+}  // namespace qb

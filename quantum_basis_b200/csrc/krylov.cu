@@ -1,0 +1,383 @@
+// quantum_basis_b200/csrc/krylov.cu -- device-resident Krylov loops behind the reference's lanczos(), eigenvec_CG()
+// and energy_scale() signatures, plus Chebyshev/KPM moments (new functionality).
+//
+// Reference loops: src/lanczos.cc:134-266 (lanczos), :281-341 (eigenvec_CG), :355-390 (hess_eigen),
+// src/kpm.cc:45-88 (energy_scale).  What changes is the data flow, not the mathematics: vectors stay in HBM, each
+// step is 2-3 fused kernels (one pass over H, one over each vector), scalars chain through device memory, and the
+// host only sees (a_m, b_m) to evaluate the reference's stop rule.  The checkpoint hooks and the per-step log
+// files of the reference (ckpt_lanczos_update, log_Lanczos_srval, log_CG.txt) are host I/O outside the path.
+#include "internal.hpp"
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace qb {
+
+constexpr double kLanczosPrecision = 2e-12;   // reference src/miscellaneous.cc:47
+
+// ---------------------------------------------------------------------------------------------- hess_eigen
+// Implicit QL with Wilkinson shifts for the symmetric tridiagonal (diag d, off-diag e).  The reference calls
+// LAPACKE_dstedc('I') (src/lanczos.cc:367).  z: full eigenvector matrix (m x m column-major, identity on entry),
+// or null; zlast: only the last row of the eigenvector matrix (e_m^T Q), or null -- the stop rule needs
+// s[m-1] of the lowest Ritz vector only (src/lanczos.cc:231), which keeps the per-step cost O(m^2).
+static int tridiag_ql(int64_t m, double *d, double *e, double *z, double *zlast)
+{
+    for (int64_t l = 0; l < m; l++) {
+        int iter = 0;
+        int64_t mm;
+        do {
+            for (mm = l; mm < m - 1; mm++) {
+                const double dd = fabs(d[mm]) + fabs(d[mm + 1]);
+                if (fabs(e[mm]) <= DBL_EPSILON * dd) break;
+            }
+            if (mm != l) {
+                if (iter++ == 300) return 1;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = hypot(g, 1.0);
+                g = d[mm] - d[l] + e[l] / (g + copysign(r, g));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int64_t i;
+                bool underflow = false;
+                for (i = mm - 1; i >= l; i--) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    r = hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) { d[i + 1] -= p; e[mm] = 0.0; underflow = true; break; }
+                    s = f / r; c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    if (z) for (int64_t k = 0; k < m; k++) {
+                        f = z[k + (i + 1) * m];
+                        z[k + (i + 1) * m] = s * z[k + i * m] + c * f;
+                        z[k + i * m] = c * z[k + i * m] - s * f;
+                    }
+                    if (zlast) { f = zlast[i + 1]; zlast[i + 1] = s * zlast[i] + c * f; zlast[i] = c * zlast[i] - s * f; }
+                }
+                if (underflow) continue;
+                d[l] -= p; e[l] = g; e[mm] = 0.0;
+            }
+        } while (mm != l);
+    }
+    return 0;
+}
+
+// ritz ascending ("sr"); s (optional) full vectors; s_last0 (optional) = last component of the lowest vector
+static int hess_eigen_host(const double *hess, int64_t maxit, int64_t m, double *ritz, double *s, double *s_last0)
+{
+    std::vector<double> d(m), e(m), z, zl;
+    std::vector<int64_t> ord(m);
+    for (int64_t j = 0; j < m; j++) { d[j] = hess[maxit + j]; e[j] = (j + 1 < m) ? hess[j + 1] : 0.0; ord[j] = j; }
+    if (s) { z.assign((size_t)m * m, 0.0); for (int64_t j = 0; j < m; j++) z[j + j * m] = 1.0; }
+    if (s_last0) { zl.assign(m, 0.0); zl[m - 1] = 1.0; }
+    if (tridiag_ql(m, d.data(), e.data(), s ? z.data() : nullptr, s_last0 ? zl.data() : nullptr)) return 1;
+    for (int64_t i = 1; i < m; i++) { const int64_t k = ord[i]; int64_t j = i - 1; while (j >= 0 && d[ord[j]] > d[k]) { ord[j + 1] = ord[j]; j--; } ord[j + 1] = k; }
+    for (int64_t j = 0; j < m; j++) {
+        ritz[j] = d[ord[j]];
+        if (s) memcpy(s + m * j, z.data() + m * ord[j], sizeof(double) * (size_t)m);
+    }
+    if (s_last0) *s_last0 = zl[ord[0]];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- helpers
+struct DevBuf {             // RAII-ish device scratch
+    void *p = nullptr;
+    int alloc(size_t bytes) { cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1); if (e != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return fail(QBGPU_ERR_ALLOC, "cudaMalloc failed in a Krylov driver"); } return 0; }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+static int check_single(const qbgpu_matrix *A, bool cplx)
+{
+    if (!A) return fail(QBGPU_ERR_ARG, "null matrix handle");
+    if (A->api_complex != cplx) return fail(QBGPU_ERR_ARG, "handle scalar type does not match this entry point");
+    if (A->row_lo != 0 || A->row_hi != A->n) return fail(QBGPU_ERR_STATE, "this loop needs an unsharded handle (use quantum_basis_b200.dist for shards)");
+    return QBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- lanczos
+// state layout: see include/qbgpu.h (lanczos_step_*).
+static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
+                        double *hess, const char *purpose, int where, bool stop_on_breakdown = true)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!m_out || !v || !hess || !purpose) return fail(QBGPU_ERR_ARG, "lanczos: null argument");
+    const bool is_val = strstr(purpose, "val") != nullptr;
+    const bool is_val1 = strstr(purpose, "val1") != nullptr;
+    const bool is_dn = strcmp(purpose, "dnmcs") == 0;
+    if (!is_val && !is_dn) return fail(QBGPU_ERR_ARG, "lanczos: purpose must be sr_val0, sr_val1 or dnmcs");
+    if (k != 0) return fail(QBGPU_ERR_STATE, "lanczos: resuming from k > 0 (checkpoint restart) is not supported");
+    const int64_t mm = k + np;
+    if (!(mm < maxit && np >= 0)) return fail(QBGPU_ERR_ARG, "lanczos: need k + np < maxit");      // src/lanczos.cc:147
+    *m_out = k;
+    if (np == 0) return QBGPU_OK;                                                                  // :150
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    const int nvec = is_val1 ? 3 : 2;
+
+    DevBuf dv, dstate, dhess;
+    char *U;
+    if (where == QBGPU_HOST) {
+        QB_TRY(dv.alloc(vb * n * nvec));
+        U = (char *)dv.p;
+        QB_CUDA(cudaMemcpyAsync(U, v, vb * n, cudaMemcpyHostToDevice, c.stream));
+        if (is_val1) QB_CUDA(cudaMemcpyAsync(U + 2 * vb * n, (char *)v + 2 * vb * n, vb * n, cudaMemcpyHostToDevice, c.stream));
+    } else if (where == QBGPU_DEVICE) {
+        U = (char *)v;
+    } else return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    char *Ubuf[2] = {U, U + vb * n};
+    char *phi = U + 2 * vb * n;
+    QB_TRY(dstate.alloc(sizeof(double) * 8));
+    QB_TRY(dhess.alloc(sizeof(double) * 2 * maxit));
+    double *state = (double *)dstate.p;
+    double *b_dev = (double *)dhess.p, *a_dev = b_dev + maxit;
+    const double init[8] = {1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    QB_CUDA(cudaMemcpyAsync(state, init, sizeof init, cudaMemcpyHostToDevice, c.stream));
+    QB_CUDA(cudaMemsetAsync(dhess.p, 0, sizeof(double) * 2 * maxit, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));              // `init` is on the host stack
+    for (int64_t j = 0; j < 2 * maxit; j++) hess[j] = 0.0; // the caller's array as the reference leaves it (zeros beyond m)
+
+    std::vector<double> ritz(mm + 1);
+    int cnt_accuE0 = 0;
+    double theta0_prev = 0.0;
+    int64_t m = 0;
+    while (m < mm) {
+        m++;
+        // one fused Lanczos step (src/lanczos.cc:167-187 for m == 1, :194-214 otherwise)
+        const void *ux = Ubuf[(m - 1) % 2];
+        void *uz = Ubuf[m % 2];
+        FusedArgs fa;
+        fa.x = ux; fa.z = uz; fa.y = uz; fa.scal_mode = 1; fa.sc = state; fa.beta = make_double2(1.0, 0.0); fa.dots = state + 3;
+        QB_TRY(launch_spmv(A, fa));
+        QB_TRY(lanczos_step_b(n, cplx, ux, uz, state));
+        QB_TRY(lanczos_step_c(state, a_dev, b_dev, m));
+        double ab[2];
+        QB_CUDA(cudaMemcpyAsync(c.scal_host, a_dev + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaMemcpyAsync(c.scal_host + 1, b_dev + m, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaStreamSynchronize(c.stream));
+        ab[0] = c.scal_host[0]; ab[1] = c.scal_host[1];
+        hess[maxit + m - 1] = ab[0];
+        hess[m] = ab[1];
+        if (m == 1) continue;                               // the start-up step has no checks in the reference (:167-191)
+        if (stop_on_breakdown && fabs(hess[m]) < kLanczosPrecision) break;                         // :216
+        if (is_val1) {                                      // re-orthogonalise against phi0, :218-226
+            double *dd = c.scal_dev + 52;
+            QB_TRY(vec_dotc(n, cplx, phi, uz, dd));
+            double h[3];
+            QB_TRY(read_scalars(dd, h, 2));
+            double sx;
+            QB_TRY(read_scalars(state, &sx, 1));
+            const double tr = h[0] * sx, ti = cplx ? h[1] * sx : 0.0;
+            if (sqrt(tr * tr + ti * ti) > kLanczosPrecision) {
+                // v_m = sx*U ;  v_m -= tmp*phi  <=>  U -= (tmp/sx)*phi ;  then renormalise: sx <- 1/||U||
+                QB_TRY(vec_axpy(n, cplx, make_double2(-h[0], cplx ? -h[1] : 0.0), phi, uz));
+                QB_TRY(vec_nrm2sq(n, cplx, uz, dd));
+                double nn;
+                QB_TRY(read_scalars(dd, &nn, 1));
+                const double nsx = 1.0 / sqrt(nn);
+                QB_CUDA(cudaMemcpyAsync(state, &nsx, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+                QB_CUDA(cudaStreamSynchronize(c.stream));
+            }
+        }
+        if (is_val) {                                       // stop rule, :228-248
+            double s_last = 0.0;
+            if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+            if (m > 3) {
+                const double accuracy = fabs(hess[m] * s_last);
+                const double accu_E0 = fabs((ritz[0] - theta0_prev) / ritz[0]);
+                if (accu_E0 < kLanczosPrecision) cnt_accuE0++; else cnt_accuE0 = 0;
+                if (cnt_accuE0 > 15 && accuracy < kLanczosPrecision) break;
+            }
+            theta0_prev = ritz[0];
+        }
+    }
+    *m_out = m;
+    // hand the two live vectors back normalised, in the reference's slots: v_m at (m%2), v_{m-1} at ((m-1)%2)
+    QB_TRY(scale_copy(n, cplx, state + 0, 1.0, Ubuf[m % 2], Ubuf[m % 2]));
+    QB_TRY(scale_copy(n, cplx, state + 1, 1.0, Ubuf[(m - 1) % 2], Ubuf[(m - 1) % 2]));
+    if (where == QBGPU_HOST) QB_CUDA(cudaMemcpyAsync(v, U, vb * n * 2, cudaMemcpyDeviceToHost, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+// --------------------------------------------------------------------------------------------- eigenvec_CG
+static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, double2 E0, double *accu_out,
+                   void *v, void *r, void *p, void *pp, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!m_io || !accu_out || !v || !r || !p || !pp) return fail(QBGPU_ERR_ARG, "eigenvec_CG: null argument");
+    if (*m_io != 0) return fail(QBGPU_ERR_STATE, "eigenvec_CG: resuming from m > 0 (checkpoint restart) is not supported");
+    if (maxit <= 0) return fail(QBGPU_ERR_ARG, "eigenvec_CG: maxit must be positive");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    DevBuf buf, dsc;
+    char *dv, *dr, *dp, *dpp;
+    if (where == QBGPU_HOST) {
+        QB_TRY(buf.alloc(vb * n * 4));
+        dv = (char *)buf.p; dr = dv + vb * n; dp = dr + vb * n; dpp = dp + vb * n;
+        QB_CUDA(cudaMemcpyAsync(dv, v, vb * n, cudaMemcpyHostToDevice, c.stream));
+    } else if (where == QBGPU_DEVICE) {
+        dv = (char *)v; dr = (char *)r; dp = (char *)p; dpp = (char *)pp;
+    } else return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    QB_TRY(dsc.alloc(sizeof(double) * 8));
+    double *sc = (double *)dsc.p;                           // [0]=gamma [1,2]=delta [3]=|pp|^2 [4]=|r|^2 [5]=gamma_next
+    QB_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, c.stream));
+
+    int64_t m = 0;
+    double accu = 0.0;                                      // src/lanczos.cc:288-289
+    while (m < maxit) {
+        if (accu < kLanczosPrecision) {                     // :295
+            double nn;
+            QB_TRY(vec_nrm2sq(n, cplx, dv, sc + 6));
+            QB_TRY(read_scalars(sc + 6, &nn, 1));
+            const double rnorm = sqrt(nn);
+            if (m == 0 || fabs(rnorm - 1.0) > kLanczosPrecision) {       // :297 re-normalise and restart
+                QB_TRY(vec_scal(n, cplx, make_double2(1.0 / rnorm, 0.0), dv));
+                FusedArgs fa;                               // r = (E0 - H) v in one pass; |r|^2 from the epilogue
+                fa.x = dv; fa.y = dr; fa.alpha = make_double2(-1.0, 0.0); fa.gamma = E0; fa.dots = sc + 1;
+                QB_TRY(launch_spmv(A, fa));
+                QB_CUDA(cudaMemcpyAsync(dp, dr, vb * n, cudaMemcpyDeviceToDevice, c.stream));   // p = r
+                double h[3];
+                QB_TRY(read_scalars(sc + 1, h, 3));
+                accu = sqrt(h[2]);
+                QB_CUDA(cudaMemcpyAsync(sc, &accu, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+                QB_CUDA(cudaStreamSynchronize(c.stream));
+                m++;
+                if (accu < kLanczosPrecision) break;        // :315
+            } else {
+                break;                                      // :317
+            }
+        } else {
+            FusedArgs fa;                                   // pp = (H - E0 + eps) p ; delta = <p,pp>   (:320-323)
+            fa.x = dp; fa.y = dpp; fa.alpha = make_double2(1.0, 0.0);
+            fa.gamma = make_double2(DBL_EPSILON - E0.x, -E0.y); fa.dots = sc + 1;
+            QB_TRY(launch_spmv(A, fa));
+            QB_TRY(cg_update_vr(n, cplx, sc, dv, dr, dp, dpp));          // :324-327
+            QB_TRY(cg_update_p(n, cplx, sc, dr, dp));                    // :327-330
+            QB_CUDA(cudaMemcpyAsync(sc, sc + 5, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            QB_TRY(read_scalars(sc, &accu, 1));
+            m++;
+        }
+    }
+    *m_io = m;
+    *accu_out = accu;
+    if (where == QBGPU_HOST) {
+        QB_CUDA(cudaMemcpyAsync(v, dv, vb * n, cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaMemcpyAsync(r, dr, vb * n, cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaMemcpyAsync(p, dp, vb * n, cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaMemcpyAsync(pp, dpp, vb * n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+// -------------------------------------------------------------------------------------------- energy_scale
+static int energy_scale_impl(qbgpu_matrix *A, bool cplx, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!v || !lo || !hi || iters < 3) return fail(QBGPU_ERR_ARG, "energy_scale: bad argument");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    const int64_t mm = iters - 1;                          // src/kpm.cc:53
+    // the reference draws vec_randomize(dim, vpt[0]) itself (default seed 1, src/kpm.cc:60)
+    DevBuf dv;
+    void *U = v;
+    if (where == QBGPU_HOST) { QB_TRY(dv.alloc(vb * n * 2)); U = dv.p; }
+    QB_TRY(vec_randomize(n, cplx, U, 1));
+    std::vector<double> hess(2 * iters, 0.0), ritz(mm);
+    int64_t m = 0;
+    QB_TRY(lanczos_impl(A, cplx, 0, mm, iters, &m, U, hess.data(), "dnmcs", QBGPU_DEVICE, /*stop_on_breakdown=*/false));
+    if (hess_eigen_host(hess.data(), iters, mm, ritz.data(), nullptr, nullptr)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+    const double l = ritz[0], h = ritz[mm - 1], slack = extend * (h - l);                          // :83-87
+    *lo = l - slack; *hi = h + slack;
+    if (where == QBGPU_HOST) { QB_CUDA(cudaMemcpyAsync(v, U, vb * n * 2, cudaMemcpyDeviceToHost, c.stream)); QB_CUDA(cudaStreamSynchronize(c.stream)); }
+    return QBGPU_OK;
+}
+
+// --------------------------------------------------------------------------------------------- KPM moments
+// mu_k = <phi| T_k(Ht) |phi>, Ht = (H - c)/s.  One fused product per TWO moments:
+//   T_{k+1} = 2 Ht T_k - T_{k-1}   (alpha = 2/s, gamma = -2c/s, beta = -1, written over T_{k-1})
+//   mu_{2k+1} = 2 <T_k, T_{k+1}> - mu_1 ,  mu_{2k+2} = 2 <T_{k+1}, T_{k+1}> - mu_0
+// both inner products come out of the product's epilogue into a device array; the host reads them once at the end.
+static int kpm_impl(qbgpu_matrix *A, bool cplx, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!phi || !mu || nmom < 1 || !(hi > lo)) return fail(QBGPU_ERR_ARG, "kpm_moments: bad argument");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    const double cc = 0.5 * (hi + lo), ss = 0.5 * (hi - lo);
+    DevBuf t, ddots;
+    QB_TRY(t.alloc(vb * n * 2));
+    char *T[2] = {(char *)t.p, (char *)t.p + vb * n};
+    const int64_t nprod = nmom / 2 + 1;                    // products needed to reach index nmom-1
+    QB_TRY(ddots.alloc(sizeof(double) * 4 * (nprod + 1)));
+    double *dots = (double *)ddots.p;
+    QB_CUDA(cudaMemcpyAsync(T[0], phi, vb * n, where == QBGPU_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c.stream));
+    QB_TRY(vec_nrm2sq(n, cplx, T[0], dots));               // mu_0 = <phi,phi>
+    for (int64_t k = 0; k < nprod; k++) {
+        FusedArgs fa;
+        fa.x = T[k % 2]; fa.y = T[(k + 1) % 2]; fa.dots = dots + 4 * (k + 1);
+        if (k == 0) { fa.alpha = make_double2(1.0 / ss, 0.0); fa.gamma = make_double2(-cc / ss, 0.0); }
+        else { fa.alpha = make_double2(2.0 / ss, 0.0); fa.gamma = make_double2(-2.0 * cc / ss, 0.0); fa.beta = make_double2(-1.0, 0.0); fa.z = fa.y; }
+        QB_TRY(launch_spmv(A, fa));
+    }
+    std::vector<double> h(4 * (nprod + 1));
+    QB_CUDA(cudaMemcpyAsync(h.data(), dots, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    const double mu0 = h[0];
+    const double mu1 = h[4 + 0];                           // <T0,T1>
+    for (int64_t j = 0; j < nmom; j++) {
+        if (j == 0) mu[j] = mu0;
+        else if (j == 1) mu[j] = mu1;
+        else if (j % 2 == 0) { const int64_t k = j / 2 - 1; mu[j] = 2.0 * h[4 * (k + 1) + 2] - mu0; }      // 2<T_{k+1},T_{k+1}> - mu0
+        else { const int64_t k = (j - 1) / 2; mu[j] = 2.0 * h[4 * (k + 1) + 0] - mu1; }                    // 2<T_k,T_{k+1}> - mu1
+    }
+    return QBGPU_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qbgpu_hess_eigen(const double *hess, int64_t maxit, int64_t m, double *ritz, double *s)
+{
+    if (!hess || !ritz || m < 1 || m >= maxit) return fail(QBGPU_ERR_ARG, "hess_eigen: need 0 < m < maxit");   // src/lanczos.cc:358
+    if (hess_eigen_host(hess, maxit, m, ritz, s, nullptr)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+    return QBGPU_OK;
+}
+
+int qbgpu_lanczos_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, double *v, double *hess, const char *purpose, int where)
+{ return lanczos_impl(A, false, k, np, maxit, m, v, hess, purpose, where); }
+int qbgpu_lanczos_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v, double *hess, const char *purpose, int where)
+{ return lanczos_impl(A, true, k, np, maxit, m, v, hess, purpose, where); }
+
+int qbgpu_eigenvec_cg_d(qbgpu_matrix_t A, int64_t maxit, int64_t *m, double E0, double *accu, double *v, double *r, double *p, double *pp, int where)
+{ return cg_impl(A, false, maxit, m, make_double2(E0, 0.0), accu, v, r, p, pp, where); }
+int qbgpu_eigenvec_cg_z(qbgpu_matrix_t A, int64_t maxit, int64_t *m, const double E0[2], double *accu, void *v, void *r, void *p, void *pp, int where)
+{ if (!E0) return fail(QBGPU_ERR_ARG, "null E0"); return cg_impl(A, true, maxit, m, make_double2(E0[0], E0[1]), accu, v, r, p, pp, where); }
+
+int qbgpu_energy_scale_d(qbgpu_matrix_t A, double *v, double *lo, double *hi, double extend, int64_t iters, int where)
+{ return energy_scale_impl(A, false, v, lo, hi, extend, iters, where); }
+int qbgpu_energy_scale_z(qbgpu_matrix_t A, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
+{ return energy_scale_impl(A, true, v, lo, hi, extend, iters, where); }
+
+int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double hi, int64_t nmom, double *mu, int where)
+{ return kpm_impl(A, false, phi, lo, hi, nmom, mu, where); }
+int qbgpu_kpm_moments_z(qbgpu_matrix_t A, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
+{ return kpm_impl(A, true, phi, lo, hi, nmom, mu, where); }
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+"""Row-sharded H*v and Lanczos over several GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no distributed mode; this follows SURVEY section 8(e): H is partitioned into
+contiguous row blocks, each rank holds the complete rows of the expanded Hermitian matrix for its block (no cross-GPU
+writes), vectors are sharded by the same row ranges, and per product the Krylov vector is all-gathered over
+NVLink (NCCL).  The two Lanczos scalars are all-reduced as device-resident doubles between the fused passes
+(include/qbgpu.h: qbgpu_lanczos_step_a/b/c), so the step needs no host synchronisation.
+
+The orchestration is written against a small `kernels` provider so that the same code runs
+  - on GPUs: DeviceKernels (C-ABI calls on torch-allocated device buffers, NCCL collectives), and
+  - in the CPU tests: any object with the same methods (tests/test_dist_gloo.py supplies an oracle-backed one over gloo).
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+def equal_row_bounds(n, parts):
+    """Contiguous row partition with equal row counts (the last block may be shorter); chunk = rows per block."""
+    chunk = (n + parts - 1) // parts
+    return [min(n, p * chunk) for p in range(parts + 1)], chunk
+
+
+class ShardedOperator:
+    """y_local = H[rows, :] x with x assembled from every rank's slice."""
+
+    def __init__(self, kernels, n, rank, world, comm):
+        self.k, self.n, self.rank, self.world, self.comm = kernels, n, rank, world, comm
+        self.bounds, self.chunk = equal_row_bounds(n, world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.nloc = self.hi - self.lo
+        self.x_full = kernels.alloc(self.chunk * world)      # padded so every rank contributes `chunk` entries
+
+    def gather(self, x_local_padded):
+        """all-gather the padded local slices into x_full (entries [p*chunk, p*chunk + n_p) are rank p's rows)."""
+        self.comm.all_gather_into_tensor(self.x_full, x_local_padded)
+        return self.x_full
+
+    def matvec(self, x_local_padded, y_local):
+        self.gather(x_local_padded)
+        self.k.multmv(self.x_full, y_local)
+
+
+def sharded_lanczos(op, u0, u1, maxit, steps, state, a_dev, b_dev):
+    """`steps` fused Lanczos steps (src/lanczos.cc:167-214) on the shards.  u0/u1: padded local buffers (chunk entries),
+    u0 holds this rank's slice of the normalised start vector.  state: 8 device doubles initialised to
+    [1,0,0,0,0,0,0,0]; a_dev/b_dev: device arrays of maxit doubles.  Returns after `steps` steps without any host
+    synchronisation; the caller reads a_dev/b_dev."""
+    k, comm = op.k, op.comm
+    U = [u0, u1]
+    for m in range(1, steps + 1):
+        ux, uz = U[(m - 1) % 2], U[m % 2]
+        op.gather(ux)
+        k.lanczos_step_a(op.x_full, uz, state)                # w = sx*H*ux - b*sz*uz ; state[3] = partial <v,w>
+        comm.all_reduce(k.slot(state, 3))
+        k.lanczos_step_b(ux, uz, state)                       # w -= a*v ; state[6] = partial |w|^2
+        comm.all_reduce(k.slot(state, 6))
+        k.lanczos_step_c(state, a_dev, b_dev, m)              # b = sqrt(.), rotate the scales
+    return U
+
+
+# ----------------------------------------------------------------------------------------------- GPU provider
+class TorchComm:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+
+    def all_gather_into_tensor(self, out, inp):
+        self.dist.all_gather_into_tensor(out, inp)
+
+    def all_reduce(self, t):
+        self.dist.all_reduce(t)
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+class DeviceKernels:
+    """C-ABI calls on torch device tensors (complex128 vectors as float64 pairs)."""
+
+    def __init__(self, qb, matrix):
+        import torch
+        self.torch, self.qb, self.L, self.M = torch, qb, qb.lib(), matrix
+
+    def alloc(self, nentries):
+        return self.torch.zeros(2 * nentries, dtype=self.torch.float64, device="cuda")
+
+    def slot(self, state, i):
+        return state[i:i + 1]
+
+    def _p(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def multmv(self, x_full, y_local):
+        one = (C.c_double * 2)(1.0, 0.0); zero = (C.c_double * 2)(0.0, 0.0)
+        rc = self.L.qbgpu_zmv(self.M.handle, one, self._p(x_full), zero, self._p(y_local), 1)
+        assert rc == 0, self.L.qbgpu_last_error()
+
+    def lanczos_step_a(self, x_full, uz, state):
+        assert self.L.qbgpu_lanczos_step_a(self.M.handle, self._p(x_full), self._p(uz), self._p(state)) == 0, self.L.qbgpu_last_error()
+
+    def lanczos_step_b(self, ux, uz, state):
+        assert self.L.qbgpu_lanczos_step_b(self.M.handle, self._p(ux), self._p(uz), self._p(state)) == 0, self.L.qbgpu_last_error()
+
+    def lanczos_step_c(self, state, a_dev, b_dev, m):
+        assert self.L.qbgpu_lanczos_step_c(self._p(state), self._p(a_dev), self._p(b_dev), m) == 0, self.L.qbgpu_last_error()
+
+
+def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_peak, ClockSampler, workload_upper_nnz):
+    """bench.py's N > 1 arm: H row-sharded over the ranks (strong scaling: the total work is fixed), one product =
+    all-gather of x + the local rows' product; timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import quantum_basis_b200 as qb
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = qb.lib()
+    stream = torch.cuda.current_stream()
+    fam, p = WORKLOADS[args.workload]
+    if fam == "hubbard":
+        n = L.qbgpu_dim_hubbard(p["Lx"] * p["Ly"], p["nup"], p["ndn"])
+    else:
+        n = L.qbgpu_dim_heisenberg(p["L"], p["L"] // 2)
+    bounds, chunk = equal_row_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    t0 = time.time()
+    M = build_matrix(qb, args.workload, row_range=(lo, hi))
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    inf = M.info
+    kern = DeviceKernels(qb, M)
+    comm = TorchComm()
+    op = ShardedOperator(kern, n, rank, world, comm)
+    x_loc = kern.alloc(chunk)
+    y_loc = kern.alloc(chunk)
+    # this rank's slice of vec_randomize(seed=1) (generated on the device, sliced on the host)
+    full = qb.vec_randomize(n, 1)
+    x_loc[:2 * (hi - lo)] = torch.from_numpy(np.ascontiguousarray(full[lo:hi]).view(np.float64)).cuda()
+    del full
+
+    for _ in range(args.warmup):
+        op.matvec(x_loc, y_loc)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.qbgpu_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record(stream)
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        op.gather(x_loc)
+        k0.record(stream)
+        kern.multmv(op.x_full, y_loc)
+        k1.record(stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = int(L.qbgpu_kernel_launches(0))
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    kernel_ms = k0.elapsed_time(k1)                            # last step's local product
+    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = t.tolist()
+    nnz_all = torch.tensor([inf.nnz_stored], dtype=torch.int64, device="cuda")
+    dist.all_reduce(nnz_all)
+    Z = int(nnz_all.item())
+    s_val = 8 if inf.val_is_real else 16
+    s_vec = 16
+    ms_per_step = total_ms / args.steps
+    B_local = algorithmic_bytes(inf.nnz_stored, hi - lo, n, s_val, s_vec)
+    peak, peak_src = measured_peak()
+
+    # sharded Lanczos: iterations/s (no stop rule here: fixed 50 steps, the rate is what is measured)
+    lan = None
+    if not args.no_lanczos:
+        state = torch.zeros(8, dtype=torch.float64, device="cuda"); state[0] = 1.0
+        a_dev = torch.zeros(256, dtype=torch.float64, device="cuda"); b_dev = torch.zeros(256, dtype=torch.float64, device="cuda")
+        u1 = kern.alloc(chunk)
+        steps = 50
+        torch.cuda.synchronize(); dist.barrier()
+        tl = time.time()
+        sharded_lanczos(op, x_loc.clone(), u1, 256, steps, state, a_dev, b_dev)
+        torch.cuda.synchronize(); dist.barrier()
+        tl = time.time() - tl
+        lan = {"steps": steps, "seconds": tl, "iters_per_s": steps / tl, "a0": float(a_dev[0].item()), "b1": float(b_dev[1].item())}
+
+    if rank == 0:
+        line = {"metric": "H*v/sec", "value": 1e3 / ms_per_step, "unit": "H*v/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "S_val": s_val, "S_vec": s_vec,
+                           "partition": "contiguous equal-row blocks, full expanded rows per rank",
+                           "exchange": "NCCL all_gather_into_tensor of x per product", "l2": "inputs larger than L2"},
+                "roofline": {"bound": "hbm", "achieved": B_local / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": B_local / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU: local rows' product only (max over ranks), exchange excluded"},
+                "e2e": None, "gpu_launches": launches, "clocks": clocks,
+                "host_phases": {"generate_matrix_s": t_build}}
+        if lan:
+            line["lanczos"] = lan
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

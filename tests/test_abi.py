@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/qbgpu.h declares,
+fails loudly without a GPU (no CPU fallback), and the host-only helpers work."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import quantum_basis_b200 as qb
+from quantum_basis_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "qbgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qbgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not os.path.exists(qb.LIB_PATH):
+        qb.build_library()
+    return qb.lib()
+
+
+def test_every_declared_symbol_is_exported_and_bound(L):
+    decl = declared_symbols()
+    assert len(decl) > 40
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in include/qbgpu.h but not exported by libqbgpu.so"
+    assert sorted(_lib.EXPORTS) == decl, "python binding table and header disagree"
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", qb.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_means_loud_failure_not_fallback(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rc = L.qbgpu_init(0)
+    assert rc == 2
+    assert b"no CUDA device" in L.qbgpu_last_error()
+    ia = np.array([0, 1, 2], dtype=np.int64); ja = np.array([0, 1], dtype=np.int64); val = np.ones(2)
+    with pytest.raises(qb.QbgpuError):
+        qb.csr_mat(2, ia, ja, val, True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "quantum_basis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in txt and "qb_oracle" not in txt and "libqb_oracle" not in txt, f
+
+
+def test_sector_dimensions(L):
+    from math import comb
+    assert L.qbgpu_dim_heisenberg(20, 10) == comb(20, 10) == 184756          # BASELINE config 1
+    assert L.qbgpu_dim_hubbard(16, 8, 8) == comb(16, 8) ** 2 == 165636900    # BASELINE config 3
+    assert L.qbgpu_dim_hubbard(8, 4, 4) == 4900
+    assert L.qbgpu_dim_heisenberg(15, 7) == comb(15, 7)
+
+
+def test_partition_rows_balances_expanded_nnz(L, oracle):
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    ia_full, _, _ = oracle.expand_upper(A)
+    for parts in (1, 2, 3, 8):
+        b = np.zeros(parts + 1, dtype=np.int64)
+        rc = L.qbgpu_partition_rows(A.dim, A.ia.ctypes.data, A.ia.ctypes.data + 8, A.ja.ctypes.data, 1, parts, b.ctypes.data)
+        assert rc == 0
+        assert b[0] == 0 and b[-1] == A.dim and np.all(np.diff(b) >= 0)
+        per = np.diff(ia_full[b])
+        assert per.sum() == ia_full[-1]
+        assert per.max() - per.min() <= 2 * np.diff(ia_full).max() + 1
+
+
+def test_hess_eigen_host(L):
+    rng = np.random.default_rng(3)
+    m, maxit = 60, 100
+    hess = np.zeros(2 * maxit)
+    hess[1:m + 1] = rng.uniform(0.2, 1.5, m)
+    hess[maxit:maxit + m] = rng.normal(size=m)
+    ritz, s = qb.hess_eigen(hess, maxit, m)
+    Tm = np.diag(hess[maxit:maxit + m]) + np.diag(hess[1:m], 1) + np.diag(hess[1:m], -1)
+    w = np.linalg.eigvalsh(Tm)
+    assert np.abs(ritz - w).max() < 1e-12
+    assert np.abs(Tm @ s - s * ritz[None, :]).max() < 1e-12
+    with pytest.raises(qb.QbgpuError):
+        qb.hess_eigen(hess, maxit, maxit)          # the reference asserts m < maxit (src/lanczos.cc:358)

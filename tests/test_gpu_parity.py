@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libqbgpu.so via quantum_basis_b200), against the oracle,
+the committed reference outputs (tests/golden) and the reference's published golden values.
+
+Tolerances (BASELINE.json north_star): per-product relative l2 <= 1e-12; E0 relative <= 1e-10; KPM moments <= 1e-9.
+Integer/index work (expanded layout, generator output, vec_randomize sequence) is compared exactly.
+"""
+import numpy as np
+import pytest
+
+import lin_builders as B
+import quantum_basis_b200 as qb
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["heis12_full", "heis16_full", "heis16_k3", "tri4x4_k00", "tri4x4_k01", "tri4x4_k12", "hubbard4x2",
+       "honeycomb3x2_general", "tj12"]
+SMALL = [c for c in ALL if c not in ("heis16_full", "tj12")]
+TOL_MV = 1e-12
+TOL_E0 = 1e-10
+TOL_KPM = 1e-9
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def make(A, **kw):
+    return qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ layout
+@pytest.mark.parametrize("name", ALL)
+def test_expanded_layout_is_exact(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    M = make(A)
+    rowptr, col, val = M.download_expanded()
+    inf = M.info
+    if A.sym:
+        ia, ja, v = oracle.expand_upper(A)
+    else:
+        ia, ja, v = A.ia, A.ja, A.val
+    assert np.array_equal(rowptr, ia)
+    assert np.array_equal(col.astype(np.int64), ja)
+    all_real = np.abs(A.val.imag).max() == 0.0
+    assert bool(inf.val_is_real) == all_real                 # fp64 storage iff every imaginary part is exactly 0
+    assert np.array_equal(val, v.real if all_real else v)    # bit-exact values (conjugated lower half)
+    assert inf.nnz_stored == ia[-1] and inf.nnz_input == A.nnz and inf.n == A.dim
+    K = make(A, flags=1)                                     # QBGPU_KEEP_COMPLEX
+    assert not K.info.val_is_real
+    assert np.array_equal(K.download_expanded()[2], v)
+
+
+def test_to_dense_matches_reference_semantics(oracle):
+    A, meta, ex = oracle.load_golden("honeycomb3x2_general")
+    D = make(A).to_dense()
+    assert np.array_equal(D, A.to_scipy_full().toarray())
+    A, meta, ex = oracle.load_golden("tri4x4_k01")
+    D = make(A).to_dense()
+    assert np.array_equal(D, A.to_scipy_full().toarray())
+    assert np.abs(D - D.conj().T).max() == 0.0
+
+
+def test_create_rejects_bad_input(oracle):
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    ja = A.ja.copy(); ja[5] = A.dim + 3
+    with pytest.raises(qb.QbgpuError):
+        qb.csr_mat(A.dim, A.ia, ja, A.val, True)
+    with pytest.raises(qb.QbgpuError):
+        qb.csr_mat(A.dim, A.ia[:-1], A.ja, A.val, True)
+
+
+# ---------------------------------------------------------------------------------------------- products
+@pytest.mark.parametrize("name", ALL)
+def test_multmv_matches_reference_product(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    M = make(A)
+    x = oracle.vec_randomize(A.dim, 1)
+    y = np.full(A.dim, 7.0 + 1.0j)                           # MultMv must overwrite, not accumulate
+    M.MultMv(x, y)
+    assert rel_l2(y, ex["y1"]) <= TOL_MV                     # vs the compiled reference's csr_mat::MultMv
+    assert rel_l2(y, oracle.spmv_ld(A, x)) <= TOL_MV         # vs the long-double arbiter
+    y2 = y.copy()
+    M.MultMv2(x, y2)                                         # y += H x
+    assert rel_l2(y2, 2 * ex["y1"]) <= TOL_MV
+    # device-resident vectors
+    dx = qb.DeviceVector.from_numpy(x); dy = qb.DeviceVector(A.dim)
+    M.MultMv(dx, dy)
+    assert np.array_equal(dy.to_numpy(), y)                  # same kernel, same order: bit-identical
+    # every lane width gives the same product within rounding
+    for flags in (2,):                                       # QBGPU_NO_AUTOTUNE -> default lanes
+        y3 = np.zeros(A.dim, dtype=np.complex128)
+        make(A, flags=flags).MultMv(x, y3)
+        assert rel_l2(y3, ex["y1"]) <= TOL_MV
+    # complex values kept complex
+    y4 = np.zeros(A.dim, dtype=np.complex128)
+    make(A, flags=1).MultMv(x, y4)
+    assert rel_l2(y4, ex["y1"]) <= TOL_MV
+
+
+@pytest.mark.parametrize("name", ["heis12_full", "hubbard4x2", "tri4x4_k00", "tj12"])
+def test_double_precision_real_matrix_path(oracle, name):
+    """csr_mat<double> (reachable in the reference only by constructing it directly)."""
+    A, meta, ex = oracle.load_golden(name)
+    assert np.abs(A.val.imag).max() == 0.0
+    Ad = A.astype(np.float64)
+    M = make(Ad)
+    assert not M.is_complex
+    x = oracle.vec_randomize(A.dim, 1, dtype=np.float64)
+    y = np.zeros(A.dim)
+    M.MultMv(x, y)
+    assert rel_l2(y, ex["y1"].real) <= TOL_MV
+    assert rel_l2(y, oracle.spmv(Ad, x)) <= TOL_MV
+    hess = np.zeros(2000)
+    v = np.zeros(2 * A.dim); v[:A.dim] = x
+    m = qb.lanczos(0, 999, 1000, A.dim, M, v, hess, "sr_val0")
+    ritz, _ = qb.hess_eigen(hess, 1000, m)
+    assert abs(ritz[0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+
+
+def test_complex_x_with_nonzero_imag(oracle):
+    A, meta, ex = oracle.load_golden("tri4x4_k12")
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=A.dim) + 1j * rng.normal(size=A.dim)
+    for flags in (0, 1):
+        y = np.zeros(A.dim, dtype=np.complex128)
+        make(A, flags=flags).MultMv(x, y)
+        assert rel_l2(y, oracle.spmv_ld(A, x)) <= TOL_MV
+    A, meta, ex = oracle.load_golden("hubbard4x2")           # real values, complex vector
+    x = rng.normal(size=A.dim) + 1j * rng.normal(size=A.dim)
+    y = np.zeros(A.dim, dtype=np.complex128)
+    make(A).MultMv(x, y)
+    assert rel_l2(y, oracle.spmv_ld(A, x)) <= TOL_MV
+
+
+def test_row_shards_reproduce_the_full_product(oracle):
+    A, meta, ex = oracle.load_golden("tj12")
+    x = oracle.vec_randomize(A.dim, 1)
+    L = qb.lib()
+    for parts in (2, 3):
+        b = np.zeros(parts + 1, dtype=np.int64)
+        assert L.qbgpu_partition_rows(A.dim, A.ia.ctypes.data, A.ia.ctypes.data + 8, A.ja.ctypes.data, 1, parts, b.ctypes.data) == 0
+        ys = []
+        for p in range(parts):
+            S = qb.csr_mat(A.dim, A.ia, A.ja, A.val, True, rows=(b[p], b[p + 1]))
+            y = np.zeros(b[p + 1] - b[p], dtype=np.complex128)
+            S.MultMv(x, y)
+            ys.append(y)
+        assert rel_l2(np.concatenate(ys), ex["y1"]) <= TOL_MV
+
+
+# ---------------------------------------------------------------------------------------- vec_randomize
+def test_vec_randomize_is_the_reference_sequence(oracle):
+    for n, seed in ((10, 1), (65536, 1), (100003, 8), (7, 0)):
+        g = qb.vec_randomize(n, seed)
+        o = oracle.vec_randomize(n, seed)
+        assert np.abs(g.imag).max() == 0.0
+        assert np.abs(g.real - o.real).max() <= 4 * np.finfo(float).eps * np.abs(o.real).max()
+        assert abs(np.linalg.norm(g) - 1.0) < 1e-14
+    gd = qb.vec_randomize(1000, 1, dtype=np.float64)
+    assert np.abs(gd - oracle.vec_randomize(1000, 1, dtype=np.float64)).max() <= 4e-16
+
+
+# ------------------------------------------------------------------------------------------------ Lanczos
+@pytest.mark.parametrize("name", ALL)
+def test_lanczos_E0_matches_reference_and_published_golden(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    M = make(A)
+    n = A.dim
+    v = np.zeros(2 * n, dtype=np.complex128)
+    v[:n] = oracle.vec_randomize(n, 1)
+    hess = np.zeros(2000)
+    m = qb.lanczos(0, 999, 1000, n, M, v, hess, "sr_val0")
+    ritz, s = qb.hess_eigen(hess, 1000, m)
+    assert abs(m - meta["lanczos_steps"]) <= 2                                   # stop rule parity
+    assert abs(ritz[0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+    if meta["golden_E0"] is not None:
+        assert abs(ritz[0] - meta["golden_E0"]) < 1e-8                           # the reference's own assert
+    k = min(20, m - 1)
+    assert np.abs(hess[1000:1000 + k] - ex["lanczos_a"][:k]).max() < 1e-11
+    assert np.abs(hess[:k] - ex["lanczos_b"][:k]).max() < 1e-11
+    assert hess[0] == 0.0 and np.all(hess[m + 1:1000] == 0.0)
+    # the two live vectors come back normalised and mutually orthogonal like the reference's v[]
+    assert abs(np.linalg.norm(v[:n]) - 1.0) < 1e-10 and abs(np.linalg.norm(v[n:]) - 1.0) < 1e-10
+    assert abs(np.vdot(v[:n], v[n:])) < 1e-6
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_dnmcs_coefficients(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    M = make(A)
+    n = A.dim
+    dv = qb.DeviceVector(2 * n)
+    dv.zero()
+    x = qb.DeviceVector.from_numpy(oracle.vec_randomize(n, 1))
+    v = np.zeros(2 * n, dtype=np.complex128); v[:n] = x.to_numpy()
+    hess = np.zeros(120)
+    m = qb.lanczos(0, 59, 60, n, M, v, hess, "dnmcs")
+    assert m == meta["dn_steps"] == 59                       # no stop rule in dnmcs mode (src/lanczos.cc:228)
+    assert np.abs(hess[60:80] - ex["dn_a"][:20]).max() < 1e-11
+    assert np.abs(hess[:20] - ex["dn_b"][:20]).max() < 1e-11
+
+
+def test_lanczos_argument_checks(oracle):
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    M = make(A)
+    v = np.zeros(2 * A.dim, dtype=np.complex128); v[:A.dim] = oracle.vec_randomize(A.dim, 1)
+    hess = np.zeros(20)
+    with pytest.raises(qb.QbgpuError):
+        qb.lanczos(0, 10, 10, A.dim, M, v, hess, "sr_val0")  # the reference asserts k+np < maxit (src/lanczos.cc:147)
+    with pytest.raises(qb.QbgpuError):
+        qb.lanczos(0, 5, 10, A.dim, M, v, hess, "bogus")
+    assert qb.lanczos(0, 0, 10, A.dim, M, v, hess, "sr_val0") == 0   # np == 0 returns immediately (:150)
+
+
+# ---------------------------------------------------------------------------------------------------- CG
+@pytest.mark.parametrize("name", SMALL)
+def test_eigenvec_cg(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    M = make(A)
+    n = A.dim
+    v = oracle.vec_randomize(n, 1)
+    r = np.zeros(n, dtype=np.complex128); p = np.zeros_like(r); pp = np.zeros_like(r)
+    m, accu = qb.eigenvec_CG(n, 1000, 0, M, meta["lanczos_E0"], v, r, p, pp)
+    assert accu < 2e-12
+    assert abs(m - meta["cg_steps"]) <= 5
+    res = oracle.spmv(A, v) - meta["lanczos_E0"] * v
+    assert np.linalg.norm(res) < 1e-9
+    assert abs(np.linalg.norm(v) - 1.0) < 1e-9
+    ov = abs(np.vdot(ex["cg_vec"], v))
+    if name not in ("tri4x4_k01", "tri4x4_k12", "heis16_k3"):        # non-degenerate ground states
+        assert ov > 1 - 1e-8
+
+
+def test_locate_E0_lanczos_heisenberg16_golden(oracle):
+    """src/main_test.cc:18-111: E0 and the three ground-state correlators."""
+    A, meta, ex = oracle.load_golden("heis16_full")
+    out = qb.locate_E0_lanczos(make(A), nev=1, ncv=1)
+    assert abs(out["eigenvals"][0] + 7.142296361) < 1e-8
+    v = out["eigenvecs"][0]
+    st = B.basis_states(16, 1, (None,))
+    sz = lambda s: 0.5 - ((st >> s) & 1)                     # noqa: E731
+    w = np.abs(v) ** 2
+    assert abs((w * sz(0) * sz(1)).sum() + 0.1487978408) < 1e-8
+    assert abs((w * sz(0) * sz(2)).sum() - 0.0617414604) < 1e-8
+    # <S+_0 S-_1>: flips (down at 0, up at 1) -> (up at 0, down at 1)
+    byval = np.argsort(st); sv = st[byval]
+    act = np.nonzero((((st >> 0) & 1) == 0) & (((st >> 1) & 1) == 1))[0]     # result states: site0 up(0), site1 down(1)
+    src = byval[np.searchsorted(sv, st[act] ^ 0b11)]
+    assert abs(np.vdot(v[act], v[src]).real + 0.2975956817) < 1e-8
+
+
+def test_locate_E0_lanczos_gap_and_excited_vector(oracle):
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    out = qb.locate_E0_lanczos(make(A), nev=2, ncv=2)
+    F = A.to_scipy_full().toarray()
+    w = np.linalg.eigvalsh(F)
+    assert abs(out["eigenvals"][0] - w[0]) < 1e-9
+    assert abs(out["eigenvals"][0] + 14.07605866) < 1e-8     # examples/trans_absent/latt_square/square_Fermi_Hubbard.cc:113
+    e1 = w[np.nonzero(w - w[0] > 1e-9)[0][0]] if out["gap"] > 1e-9 else w[1]
+    assert abs(out["eigenvals"][1] - e1) < 1e-8
+    for E, vec in zip(out["eigenvals"], out["eigenvecs"]):
+        assert np.linalg.norm(F @ vec - E * vec) < 1e-7
+
+
+# ------------------------------------------------------------------------------------- energy_scale / KPM
+@pytest.mark.parametrize("name", ["heis12_full", "tri4x4_k01", "hubbard4x2"])
+def test_energy_scale_matches_reference(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    v = np.zeros(2 * A.dim, dtype=np.complex128)
+    lo, hi = qb.energy_scale(A.dim, make(A), v, 0.1, 40)
+    assert abs(lo - meta["escale_lo"]) < 1e-8 * abs(meta["escale_lo"])
+    assert abs(hi - meta["escale_hi"]) < 1e-8 * abs(meta["escale_hi"])
+
+
+@pytest.mark.parametrize("name", ["tri4x4_k01", "hubbard4x2", "heis16_k3"])
+def test_kpm_moments(oracle, name):
+    A, meta, ex = oracle.load_golden(name)
+    phi = oracle.vec_randomize(A.dim, 3)
+    lo, hi = meta["escale_lo"], meta["escale_hi"]
+    for nmom in (1, 2, 7, 64, 129):
+        mu = qb.kpm_moments(make(A), phi, lo, hi, nmom)
+        ref = oracle.kpm_moments(A, phi, lo, hi, nmom)
+        assert np.abs(mu - ref).max() <= TOL_KPM
+
+
+# --------------------------------------------------------------------------------------------- generators
+def _expanded(n, ia, ja, val, oracle):
+    from oracle_lib import Csr
+    return oracle.expand_upper(Csr(n, ia, ja, val, True))
+
+
+@pytest.mark.parametrize("case", ["heis12", "heis15", "hub4x2", "hub3x3"])
+def test_device_generators_match_the_reference_matrix(oracle, case):
+    L = qb.lib()
+    import ctypes as C
+    if case == "heis12":
+        bonds, args = B.chain_bonds(12), (12, 6)
+        n, ia, ja, val = B.heisenberg_upper_csr(12, 6, bonds)
+    elif case == "heis15":
+        bonds, args = B.chain_bonds(15), (15, 7)
+        n, ia, ja, val = B.heisenberg_upper_csr(15, 7, bonds)
+    elif case == "hub4x2":
+        bonds, args = B.square_bonds(4, 2), (8, 4, 4)
+        n, ia, ja, val = B.hubbard_upper_csr(8, 4, 4, bonds, 1.0, 1.1)
+    else:
+        bonds, args = B.square_bonds(3, 3), (9, 4, 5)
+        n, ia, ja, val = B.hubbard_upper_csr(9, 4, 5, bonds, 1.0, 2.3)
+    barr = np.array(bonds, dtype=np.int32).ravel()
+    h = C.c_void_p()
+    if case.startswith("heis"):
+        rc = L.qbgpu_build_heisenberg(C.byref(h), args[0], args[1], len(bonds), barr.ctypes.data, 1.0, 1, 0, 0, -1)
+    else:
+        U = 1.1 if case == "hub4x2" else 2.3
+        rc = L.qbgpu_build_hubbard(C.byref(h), args[0], args[1], args[2], len(bonds), barr.ctypes.data, 1.0, U, 1, 0, 0, -1)
+    assert rc == 0, L.qbgpu_last_error()
+    M = qb.csr_mat._adopt(h, True)
+    rowptr, col, v = M.download_expanded()
+    eia, eja, ev = _expanded(n, ia, ja, val, oracle)
+    assert M.dim == n
+    assert np.array_equal(rowptr, eia) and np.array_equal(col.astype(np.int64), eja)
+    assert np.array_equal(v, ev.real)                        # bit-identical values, fp64 storage
+    if case == "hub4x2":
+        A, meta, ex = oracle.load_golden("hubbard4x2")       # and therefore equal to the reference-assembled matrix
+        rp2, c2, v2 = make(A).download_expanded()
+        assert np.array_equal(rowptr, rp2) and np.array_equal(col, c2) and np.array_equal(v, v2)
+
+
+def test_config1_heisenberg_L20_E0(oracle):
+    """BASELINE config 1: Heisenberg chain L=20, Sz=0 (dim 184,756); E0 from the compiled reference = -8.9043865298764
+    in 77 steps (SURVEY.md section 6 / BASELINE.md section 3)."""
+    L = qb.lib()
+    import ctypes as C
+    bonds = np.array(B.chain_bonds(20), dtype=np.int32).ravel()
+    h = C.c_void_p()
+    assert L.qbgpu_build_heisenberg(C.byref(h), 20, 10, 20, bonds.ctypes.data, 1.0, 1, 0, 0, -1) == 0, L.qbgpu_last_error()
+    M = qb.csr_mat._adopt(h, True)
+    inf = M.info
+    assert inf.n == 184756 and inf.nnz_stored == 2129556 and inf.val_is_real == 1
+    out = qb.locate_E0_lanczos(M, nev=1, ncv=0)
+    assert abs(out["eigenvals"][0] + 8.9043865298764) <= TOL_E0 * 8.9043865298764
+    assert abs(out["lanczos_steps"] - 77) <= 2
+
+
+def test_large_generated_matrix_properties(oracle):
+    """Size-independent properties at a size the oracle would not finish quickly: Heisenberg chain L=26, Sz=0
+    (dim 10,400,600): Hermiticity <x,Hy> = conj<y,Hx>, linearity, and agreement between row shards and the whole."""
+    L = qb.lib()
+    import ctypes as C
+    nsites = 26
+    bonds = np.array(B.chain_bonds(nsites), dtype=np.int32).ravel()
+    h = C.c_void_p()
+    assert L.qbgpu_build_heisenberg(C.byref(h), nsites, nsites // 2, nsites, bonds.ctypes.data, 1.0, 1, 0, 0, -1) == 0, L.qbgpu_last_error()
+    M = qb.csr_mat._adopt(h, True)
+    n = M.dim
+    assert n == 10400600
+    x = qb.vec_randomize(n, 1, device=True); y = qb.vec_randomize(n, 8, device=True)
+    hx = qb.DeviceVector(n); hy = qb.DeviceVector(n)
+    M.MultMv(x, hx); M.MultMv(y, hy)
+    d1 = (C.c_double * 2)(); d2 = (C.c_double * 2)()
+    L.qbgpu_zdotc(n, C.c_void_p(x.ptr), C.c_void_p(hy.ptr), d1)
+    L.qbgpu_zdotc(n, C.c_void_p(y.ptr), C.c_void_p(hx.ptr), d2)
+    assert abs(complex(d1[0], d1[1]) - complex(d2[0], -d2[1])) < 1e-12
+    # a shard of the same generator gives the same rows
+    lo, hi = n // 3, n // 3 + 100000
+    h2 = C.c_void_p()
+    assert L.qbgpu_build_heisenberg(C.byref(h2), nsites, nsites // 2, nsites, bonds.ctypes.data, 1.0, 1, 0, lo, hi) == 0
+    S = qb.csr_mat._adopt(h2, True)
+    ys = qb.DeviceVector(hi - lo)
+    S.MultMv(x, ys)
+    assert np.array_equal(ys.to_numpy(), hx.to_numpy()[lo:hi])
+    # sum of each row of H for the Heisenberg chain in the Sz=0 sector: H applied to the uniform vector is an
+    # eigenvector-free check of the generator: (H 1)_i = diag_i + 0.5 * (#antiparallel bonds) = L/4 for every i
+    ones = qb.DeviceVector.from_numpy(np.ones(n, dtype=np.complex128))
+    M.MultMv(ones, hx)
+    assert np.abs(hx.to_numpy() - nsites * 0.25).max() < 1e-12

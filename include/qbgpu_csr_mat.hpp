@@ -1,0 +1,100 @@
+// include/qbgpu_csr_mat.hpp -- C++ adaptor over the C ABI with the shape of the reference's csr_mat<T>.
+//
+// The reference's Krylov routines are templates over a duck-typed matrix `MAT` that only needs
+//     void MultMv2(const T *x, T *y) const;   // y = H*x + y      (src/sparse.cc:262-289)
+//     void MultMv (const T *x, T *y) const;   // y = H*x          (src/sparse.cc:291-297)
+//     std::vector<T> to_dense() const;        //                  (src/sparse.cc:299-315)
+// (qbasis.h:1065-1093,1654: lanczos, eigenvec_CG, iram, energy_scale).  qbgpu::csr_mat<T> provides exactly those
+// members on top of libqbgpu, so `lanczos<T, qbgpu::csr_mat<T>>` etc. instantiate unchanged, and adds the fused
+// device-resident loops as members with the reference's argument lists.  Errors become std::runtime_error like the
+// reference's (src/sparse.cc:130,259,288).  Header-only; link with -lqbgpu.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+#include "qbgpu.h"
+
+namespace qbgpu {
+
+inline void check(int rc, const char *what)
+{
+    if (rc != QBGPU_OK) throw std::runtime_error(std::string(what) + " failed: " + qbgpu_last_error());
+}
+
+template <typename T> class csr_mat {
+    static_assert(std::is_same<T, double>::value || std::is_same<T, std::complex<double>>::value, "T must be double or complex<double>");
+    static constexpr bool is_complex = !std::is_same<T, double>::value;
+public:
+    int64_t dim = 0;
+    int64_t nnz = 0;
+    bool sym = false;
+    qbgpu_matrix_t handle = nullptr;       // replaces `sparse_matrix_t handle` (qbasis.h:985)
+
+    csr_mat() = default;
+    // from the reference's arrays (csr_mat<T>::dim, nnz, sym, val, ja, ia; MKL_INT == int64 under -DMKL_ILP64).
+    // Upload + conversion happen here, where the reference creates its MKL handle (src/sparse.cc:129,258).
+    csr_mat(int64_t dim_, int64_t nnz_, bool sym_, const T *val, const long long *ja, const long long *ia, int flags = 0)
+        : dim(dim_), nnz(nnz_), sym(sym_)
+    {
+        const int64_t *ia64 = reinterpret_cast<const int64_t *>(ia), *ja64 = reinterpret_cast<const int64_t *>(ja);
+        if (is_complex) check(qbgpu_create_zcsr(&handle, dim, ia64, ia64 + 1, ja64, val, sym ? 1 : 0, flags), "qbgpu_create_zcsr");
+        else check(qbgpu_create_dcsr(&handle, dim, ia64, ia64 + 1, ja64, reinterpret_cast<const double *>(val), sym ? 1 : 0, flags), "qbgpu_create_dcsr");
+    }
+    // from any object with the reference csr_mat's public members (qbasis.h:976-985)
+    template <typename RefCsr> explicit csr_mat(const RefCsr &ref, int flags = 0) : csr_mat(ref.dim, ref.nnz, ref.sym, ref.val, ref.ja, ref.ia, flags) {}
+    csr_mat(const csr_mat &) = delete;
+    csr_mat &operator=(const csr_mat &) = delete;
+    csr_mat(csr_mat &&o) noexcept : dim(o.dim), nnz(o.nnz), sym(o.sym), handle(o.handle) { o.handle = nullptr; }
+    csr_mat &operator=(csr_mat &&o) noexcept { if (this != &o) { destroy(); dim = o.dim; nnz = o.nnz; sym = o.sym; handle = o.handle; o.handle = nullptr; } return *this; }
+    ~csr_mat() { if (handle) qbgpu_destroy(handle); }
+    void destroy() { if (handle) { check(qbgpu_destroy(handle), "qbgpu_destroy"); handle = nullptr; } }   // src/sparse.cc:150-169
+    int64_t dimension() const { return dim; }
+
+    void MultMv2(const T *x, T *y) const { mv(1.0, x, 1.0, y); }
+    void MultMv(const T *x, T *y) const { mv(1.0, x, 0.0, y); }
+    std::vector<T> to_dense() const
+    {
+        std::vector<T> res(static_cast<size_t>(dim) * dim);
+        check(qbgpu_to_dense(handle, res.data()), "qbgpu_to_dense");
+        return res;
+    }
+
+    // fused device-resident loops with the reference's argument lists (host pointers)
+    void lanczos(int64_t k, int64_t np, int64_t maxit, int64_t &m, T *v, double *hessenberg, const std::string &purpose) const
+    {
+        if (is_complex) check(qbgpu_lanczos_z(handle, k, np, maxit, &m, v, hessenberg, purpose.c_str(), QBGPU_HOST), "qbgpu_lanczos_z");
+        else check(qbgpu_lanczos_d(handle, k, np, maxit, &m, reinterpret_cast<double *>(v), hessenberg, purpose.c_str(), QBGPU_HOST), "qbgpu_lanczos_d");
+    }
+    void eigenvec_CG(int64_t maxit, int64_t &m, const T &E0, double &accu, T *v, T *r, T *p, T *pp) const
+    {
+        if (is_complex) {
+            const double e[2] = {std::real(E0), std::imag(E0)};
+            check(qbgpu_eigenvec_cg_z(handle, maxit, &m, e, &accu, v, r, p, pp, QBGPU_HOST), "qbgpu_eigenvec_cg_z");
+        } else {
+            check(qbgpu_eigenvec_cg_d(handle, maxit, &m, std::real(E0), &accu, reinterpret_cast<double *>(v), reinterpret_cast<double *>(r),
+                                      reinterpret_cast<double *>(p), reinterpret_cast<double *>(pp), QBGPU_HOST), "qbgpu_eigenvec_cg_d");
+        }
+    }
+    void energy_scale(T *v, double &lo, double &hi, double extend, int64_t iters) const
+    {
+        if (is_complex) check(qbgpu_energy_scale_z(handle, v, &lo, &hi, extend, iters, QBGPU_HOST), "qbgpu_energy_scale_z");
+        else check(qbgpu_energy_scale_d(handle, reinterpret_cast<double *>(v), &lo, &hi, extend, iters, QBGPU_HOST), "qbgpu_energy_scale_d");
+    }
+
+private:
+    void mv(double alpha, const T *x, double beta, T *y) const
+    {
+        if (!handle) throw std::runtime_error("qbgpu::csr_mat: matrix-vector product on an empty matrix");
+        if (is_complex) {
+            const double a[2] = {alpha, 0.0}, b[2] = {beta, 0.0};
+            check(qbgpu_zmv(handle, a, x, b, y, QBGPU_HOST), "matrix-vector product");
+        } else {
+            check(qbgpu_dmv(handle, alpha, reinterpret_cast<const double *>(x), beta, reinterpret_cast<double *>(y), QBGPU_HOST), "matrix-vector product");
+        }
+    }
+};
+
+}  // namespace qbgpu

@@ -298,7 +298,7 @@ static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     cleanup();
 #undef QB_CU
     A->convert_s = wall_b() - t0;
-    if (!(flags & QBGPU_NO_AUTOTUNE)) { int rc = autotune(A); if (rc) { qbgpu_destroy(A); return rc; } } else A->lanes = 8;
+    { int rc = autotune(A, flags); if (rc) { qbgpu_destroy(A); return rc; } }
     *out = A;
     return QBGPU_OK;
 }

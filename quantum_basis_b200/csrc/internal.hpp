@@ -20,6 +20,11 @@ struct qbgpu_matrix {
     int64_t *rowptr = nullptr;
     int32_t *col = nullptr;
     void    *val = nullptr;
+    // QBGPU_FORMAT_SELL ("sliced jagged"): same arrays, but inside every slice of 32 consecutive rows the entries
+    // are stored jagged-diagonal-wise: rows ranked by length (descending), then for k = 0,1,.. the k-th entry of
+    // every row that has one, in rank order.  Slice s still occupies [rowptr[32 s], rowptr[32 s + 32]) -- no padding.
+    // rowinfo[32 s + rank] = (row-in-slice << 24) | length.
+    uint32_t *rowinfo = nullptr;
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return val_real ? 8 : 16; }
@@ -43,7 +48,9 @@ struct FusedArgs {
 
 // spmv.cu
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &args, int lanes_override = 0);
-int autotune(qbgpu_matrix *A);
+int autotune(qbgpu_matrix *A, int flags = 0);
+int sjds_convert(qbgpu_matrix *A, bool forward);
+int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // vecops.cu

@@ -221,12 +221,7 @@ static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, c
     cleanup();
 #undef QB_CU
     A->convert_s = wall() - t1;
-    if (!(flags & QBGPU_NO_AUTOTUNE)) {
-        int rc = autotune(A);
-        if (rc) { qbgpu_destroy(A); return rc; }
-    } else {
-        A->lanes = 8;
-    }
+    { int rc = autotune(A, flags); if (rc) { qbgpu_destroy(A); return rc; } }
     *out = A;
     return QBGPU_OK;
 }
@@ -256,7 +251,7 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
-    cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val);
+    cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo);
     delete A;
     return QBGPU_OK;
 }
@@ -277,10 +272,13 @@ int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, voi
 {
     QB_TRY(ensure_init());
     if (!A || !rowptr || !col || !val) return fail(QBGPU_ERR_ARG, "null argument");
+    const bool jag = (A->format == QBGPU_FORMAT_SELL);      // hand back plain CSR order whatever the resident layout
+    if (jag) QB_TRY(sjds_convert(A, false));
     QB_CUDA(cudaStreamSynchronize(ctx().stream));
     QB_CUDA(cudaMemcpy(rowptr, A->rowptr, sizeof(int64_t) * (A->nrows() + 1), cudaMemcpyDeviceToHost));
     QB_CUDA(cudaMemcpy(col, A->col, sizeof(int32_t) * A->nnz, cudaMemcpyDeviceToHost));
     QB_CUDA(cudaMemcpy(val, A->val, A->val_bytes() * A->nnz, cudaMemcpyDeviceToHost));
+    if (jag) QB_TRY(sjds_convert(A, true));
     return QBGPU_OK;
 }
 

@@ -119,6 +119,7 @@ static int launch_lanes(const qbgpu_matrix *A, const FusedArgs &a, int lanes)
 
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
 {
+    if (A->format == QBGPU_FORMAT_SELL) return launch_spmv_sjds(A, a);
     const int lanes = lanes_override ? lanes_override : A->lanes;
     const bool dots = a.dots != nullptr;
     if (!A->api_complex) {
@@ -132,7 +133,7 @@ int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
 
 // Pick the lane count per matrix by timing the plain product (the analogue of mkl_sparse_optimize; the reference
 // never calls it, src/sparse.cc:258).  Cheap: 5 variants x 3 products.
-int autotune(qbgpu_matrix *A)
+int autotune(qbgpu_matrix *A, int flags)
 {
     Context &c = ctx();
     const int64_t nrows = A->nrows();
@@ -141,37 +142,52 @@ int autotune(qbgpu_matrix *A)
     int lanes = 2;
     while (lanes < 32 && mean > 4.0 * lanes) lanes *= 2;
     A->lanes = lanes;
-    if (nrows < 4096) return QBGPU_OK;
+    if (flags & QBGPU_FORMAT_SELL) return sjds_convert(A, true);
+    if ((flags & QBGPU_NO_AUTOTUNE) || nrows < 4096) return QBGPU_OK;
+    const bool verbose = getenv("QBGPU_VERBOSE") != nullptr;
     const size_t vb = A->vec_bytes();
     void *x = nullptr, *y = nullptr;
     QB_CUDA(cudaMalloc(&x, vb * (size_t)A->n));
     QB_CUDA(cudaMalloc(&y, vb * (size_t)nrows));
     QB_TRY(vec_randomize(A->n, A->api_complex, x, 1));
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1, t0;
     QB_CUDA(cudaEventCreate(&e0));
     QB_CUDA(cudaEventCreate(&e1));
+    QB_CUDA(cudaEventCreate(&t0));
     FusedArgs a;
     a.x = x; a.y = y;
-    float best = 1e30f;
-    int best_lanes = lanes;
-    cudaEvent_t t0;
-    QB_CUDA(cudaEventCreate(&t0));
-    QB_CUDA(cudaEventRecord(t0, c.stream));
-    for (int l = 2; l <= 32; l *= 2) {
+    auto time3 = [&](int l, float &ms) -> int {
         QB_TRY(launch_spmv(A, a, l));                       // warm-up
         QB_CUDA(cudaEventRecord(e0, c.stream));
         for (int r = 0; r < 3; r++) QB_TRY(launch_spmv(A, a, l));
         QB_CUDA(cudaEventRecord(e1, c.stream));
         QB_CUDA(cudaEventSynchronize(e1));
-        float ms = 0;
         QB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        if (getenv("QBGPU_VERBOSE")) fprintf(stderr, "[qbgpu autotune] lanes=%2d  %.4f ms/product  (n=%lld nnz=%lld)\n", l, ms / 3.0f, (long long)A->n, (long long)A->nnz);
+        ms /= 3.0f;
+        return QBGPU_OK;
+    };
+    float best = 1e30f;
+    int best_lanes = lanes;
+    QB_CUDA(cudaEventRecord(t0, c.stream));
+    for (int l = 2; l <= 32; l *= 2) {
+        float ms = 0;
+        QB_TRY(time3(l, ms));
+        if (verbose) fprintf(stderr, "[qbgpu autotune] csr-vector lanes=%2d  %.4f ms/product  (n=%lld nnz=%lld)\n", l, ms, (long long)A->n, (long long)A->nnz);
         if (ms < best) { best = ms; best_lanes = l; }
     }
+    A->lanes = best_lanes;
+    if (!(flags & QBGPU_FORMAT_CSR)) {                       // try the sliced-jagged layout; keep it only if faster
+        QB_TRY(sjds_convert(A, true));
+        float ms = 0;
+        QB_TRY(time3(0, ms));
+        if (verbose) fprintf(stderr, "[qbgpu autotune] sliced-jagged      %.4f ms/product\n", ms);
+        if (ms >= best) QB_TRY(sjds_convert(A, false));
+    }
     float tot = 0;
+    QB_CUDA(cudaEventRecord(e1, c.stream));
+    QB_CUDA(cudaEventSynchronize(e1));
     QB_CUDA(cudaEventElapsedTime(&tot, t0, e1));
     A->autotune_s = tot * 1e-3;
-    A->lanes = best_lanes;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0);
     cudaFree(x); cudaFree(y);
     return QBGPU_OK;

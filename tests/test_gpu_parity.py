@@ -97,6 +97,34 @@ def test_multmv_matches_reference_product(oracle, name):
     assert rel_l2(y4, ex["y1"]) <= TOL_MV
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_sliced_jagged_layout_gives_the_same_product(oracle, name):
+    """QBGPU_FORMAT_SELL (8): in-place re-ordering of every 32-row slice; QBGPU_FORMAT_CSR (4): forced CSR-vector."""
+    A, meta, ex = oracle.load_golden(name)
+    x = oracle.vec_randomize(A.dim, 1)
+    J = make(A, flags=8)
+    assert J.info.format == 8
+    C4 = make(A, flags=4 | 2)
+    assert C4.info.format == 4
+    yj = np.zeros(A.dim, dtype=np.complex128); yc = np.zeros_like(yj)
+    J.MultMv(x, yj); C4.MultMv(x, yc)
+    assert rel_l2(yj, ex["y1"]) <= TOL_MV and rel_l2(yc, ex["y1"]) <= TOL_MV
+    # the conversion is a pure permutation: converting back returns the exact CSR arrays
+    rp, cj, vj = J.download_expanded()
+    rp2, cc, vc = C4.download_expanded()
+    assert np.array_equal(rp, rp2) and np.array_equal(cj, cc) and np.array_equal(vj, vc)
+    assert J.info.format == 8                                   # and the resident layout is restored afterwards
+    y2 = np.zeros_like(yj)
+    J.MultMv(x, y2)
+    assert np.array_equal(y2, yj)
+    # fused Lanczos on the jagged layout
+    v = np.zeros(2 * A.dim, dtype=np.complex128); v[:A.dim] = x
+    hess = np.zeros(2000)
+    m = qb.lanczos(0, 999, 1000, A.dim, J, v, hess, "sr_val0")
+    ritz, _ = qb.hess_eigen(hess, 1000, m)
+    assert abs(ritz[0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+
+
 @pytest.mark.parametrize("name", ["heis12_full", "hubbard4x2", "tri4x4_k00", "tj12"])
 def test_double_precision_real_matrix_path(oracle, name):
     """csr_mat<double> (reachable in the reference only by constructing it directly)."""

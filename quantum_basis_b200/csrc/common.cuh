@@ -73,7 +73,7 @@ template <> struct VecTraits<double> {
     __device__ static __forceinline__ double rscale(double s, double a) { return s * a; }
     __device__ static __forceinline__ double2 conj_mul(double a, double b) { return make_double2(a * b, 0.0); }   // conj(a)*b
     __device__ static __forceinline__ double abs2(double a) { return a * a; }
-    __device__ static __forceinline__ double shfl_xor(double a, int m, int w) { return __shfl_xor_sync(0xffffffffu, a, m, w); }
+    __device__ static __forceinline__ double shfl_xor(double a, int m, int w, unsigned mask) { return __shfl_xor_sync(mask, a, m, w); }
 };
 template <> struct VecTraits<double2> {
     static constexpr int ncomp = 2;
@@ -83,8 +83,8 @@ template <> struct VecTraits<double2> {
     __device__ static __forceinline__ double2 rscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
     __device__ static __forceinline__ double2 conj_mul(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
     __device__ static __forceinline__ double abs2(double2 a) { return a.x * a.x + a.y * a.y; }
-    __device__ static __forceinline__ double2 shfl_xor(double2 a, int m, int w)
-    { return make_double2(__shfl_xor_sync(0xffffffffu, a.x, m, w), __shfl_xor_sync(0xffffffffu, a.y, m, w)); }
+    __device__ static __forceinline__ double2 shfl_xor(double2 a, int m, int w, unsigned mask)
+    { return make_double2(__shfl_xor_sync(mask, a.x, m, w), __shfl_xor_sync(mask, a.y, m, w)); }
 };
 
 // ------------------------------------------------------------------------------------------ cache hints

@@ -60,6 +60,9 @@ int vec_axpy(int64_t n, bool cplx, double2 a, const void *x, void *y);
 int vec_scal(int64_t n, bool cplx, double2 a, void *x);
 int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed);
 int read_scalars(const double *dev, double *host, int count);   // stream-ordered D2H + sync
+int vec_imag_norm2(int64_t n, const void *x, double *out_dev);
+int vec_take_real(int64_t n, const void *cplx_in, double *real_out);
+int vec_put_real(int64_t n, const double *real_in, void *cplx_out);
 int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state);
 int lanczos_step_c(double *state, double *a_dev, double *b_dev, int64_t m);
 int cg_update_vr(int64_t n, bool cplx, const double *sc, void *v, void *r, const void *p, const void *pp);

@@ -9,6 +9,7 @@
 #include "internal.hpp"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -88,7 +89,8 @@ static int hess_eigen_host(const double *hess, int64_t maxit, int64_t m, double 
 struct DevBuf {             // RAII-ish device scratch
     void *p = nullptr;
     int alloc(size_t bytes) { cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1); if (e != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return fail(QBGPU_ERR_ALLOC, "cudaMalloc failed in a Krylov driver"); } return 0; }
-    ~DevBuf() { if (p) cudaFree(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+    ~DevBuf() { release(); }
 };
 
 static int check_single(const qbgpu_matrix *A, bool cplx)
@@ -347,6 +349,144 @@ static int kpm_impl(qbgpu_matrix *A, bool cplx, const void *phi, double lo, doub
     return QBGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ real-mode dispatch
+// Through the reference's public API every vector is complex<double> (only model<complex> is instantiated, SURVEY
+// F3), but when the stored values are real (all imaginary parts exactly 0) and the start vector is real -- which
+// vec_randomize always is (src/miscellaneous.cc:382: imag = 0) -- the whole Krylov recurrence stays real.  The loop
+// is then run on fp64 vectors (half the vector bytes, half the gather sectors) and the results are widened at the
+// end.  Row sums go through the identical fma sequence; (a_m, b_m) agree with the complex run to round-off (only the
+// grouping of the block-level reductions differs).
+static bool real_mode_enabled(const qbgpu_matrix *A, bool cplx) { return cplx && A->val_real && !getenv("QBGPU_NO_REAL_MODE"); }
+
+static int is_all_real(int64_t n, const void *dvec, bool *out)
+{
+    double *t = ctx().scal_dev + 56;
+    QB_TRY(vec_imag_norm2(n, dvec, t));
+    double h;
+    QB_TRY(read_scalars(t, &h, 1));
+    *out = (h == 0.0);
+    return QBGPU_OK;
+}
+
+static int lanczos_dispatch(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
+                            double *hess, const char *purpose, int where)
+{
+    if (!A || !real_mode_enabled(A, cplx) || !v || !purpose || np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const bool val1 = strstr(purpose, "val1") != nullptr;
+    const int nvec = val1 ? 3 : 2;
+    DevBuf dc, dr;
+    char *Uc = (char *)v;
+    if (where == QBGPU_HOST) {
+        QB_TRY(dc.alloc(16 * n * nvec));
+        Uc = (char *)dc.p;
+        QB_CUDA(cudaMemcpyAsync(Uc, v, 16 * n, cudaMemcpyHostToDevice, c.stream));
+        if (val1) QB_CUDA(cudaMemcpyAsync(Uc + 32 * n, (char *)v + 32 * n, 16 * n, cudaMemcpyHostToDevice, c.stream));
+    } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    bool real0 = false, real2 = true;
+    QB_TRY(is_all_real(n, Uc, &real0));
+    if (val1) QB_TRY(is_all_real(n, Uc + 32 * n, &real2));
+    int rc;
+    if (real0 && real2) {
+        QB_TRY(dr.alloc(8 * n * nvec));
+        double *Ur = (double *)dr.p;
+        QB_TRY(vec_take_real(n, Uc, Ur));
+        if (val1) QB_TRY(vec_take_real(n, Uc + 32 * n, Ur + 2 * n));
+        qbgpu_matrix R = *A;                               // same arrays, fp64 vectors
+        R.api_complex = false;
+        rc = lanczos_impl(&R, false, k, np, maxit, m_out, Ur, hess, purpose, QBGPU_DEVICE);
+        if (rc == QBGPU_OK) { QB_TRY(vec_put_real(n, Ur, Uc)); QB_TRY(vec_put_real(n, Ur + n, Uc + 16 * n)); }
+    } else {
+        rc = lanczos_impl(A, true, k, np, maxit, m_out, Uc, hess, purpose, QBGPU_DEVICE);
+    }
+    if (rc == QBGPU_OK && where == QBGPU_HOST) QB_CUDA(cudaMemcpyAsync(v, Uc, 32 * n, cudaMemcpyDeviceToHost, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return rc;
+}
+
+static int cg_dispatch(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, double2 E0, double *accu_out,
+                       void *v, void *r, void *p, void *pp, int where)
+{
+    if (!A || !real_mode_enabled(A, cplx) || E0.y != 0.0 || !v || !r || !p || !pp) return cg_impl(A, cplx, maxit, m_io, E0, accu_out, v, r, p, pp, where);
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    const int64_t n = A->n;
+    DevBuf dc, dr;
+    char *vc = (char *)v;
+    if (where == QBGPU_HOST) {
+        QB_TRY(dc.alloc(16 * n));
+        vc = (char *)dc.p;
+        QB_CUDA(cudaMemcpyAsync(vc, v, 16 * n, cudaMemcpyHostToDevice, c.stream));
+    } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    bool real0 = false;
+    QB_TRY(is_all_real(n, vc, &real0));
+    if (!real0) { dc.release(); return cg_impl(A, true, maxit, m_io, E0, accu_out, v, r, p, pp, where); }
+    QB_TRY(dr.alloc(8 * n * 4));
+    double *R4 = (double *)dr.p;
+    QB_TRY(vec_take_real(n, vc, R4));
+    qbgpu_matrix R = *A;
+    R.api_complex = false;
+    QB_TRY(cg_impl(&R, false, maxit, m_io, E0, accu_out, R4, R4 + n, R4 + 2 * n, R4 + 3 * n, QBGPU_DEVICE));
+    void *outs[4] = {v, r, p, pp};
+    if (where == QBGPU_DEVICE) {
+        for (int j = 0; j < 4; j++) QB_TRY(vec_put_real(n, R4 + j * n, outs[j]));
+    } else {
+        for (int j = 0; j < 4; j++) {
+            QB_TRY(vec_put_real(n, R4 + j * n, vc));
+            QB_CUDA(cudaMemcpyAsync(outs[j], vc, 16 * n, cudaMemcpyDeviceToHost, c.stream));
+            QB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    }
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+static int energy_scale_dispatch(qbgpu_matrix *A, bool cplx, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
+{
+    if (!A || !real_mode_enabled(A, cplx) || !v) return energy_scale_impl(A, cplx, v, lo, hi, extend, iters, where);
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    const int64_t n = A->n;
+    DevBuf dr, dc;
+    QB_TRY(dr.alloc(8 * n * 2));
+    qbgpu_matrix R = *A;
+    R.api_complex = false;
+    QB_TRY(energy_scale_impl(&R, false, dr.p, lo, hi, extend, iters, QBGPU_DEVICE));   // start vector = vec_randomize: real
+    char *vc = (char *)v;
+    if (where == QBGPU_HOST) { QB_TRY(dc.alloc(32 * n)); vc = (char *)dc.p; }
+    QB_TRY(vec_put_real(n, (double *)dr.p, vc));
+    QB_TRY(vec_put_real(n, (double *)dr.p + n, vc + 16 * n));
+    if (where == QBGPU_HOST) QB_CUDA(cudaMemcpyAsync(v, vc, 32 * n, cudaMemcpyDeviceToHost, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+static int kpm_dispatch(qbgpu_matrix *A, bool cplx, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
+{
+    if (!A || !real_mode_enabled(A, cplx) || !phi) return kpm_impl(A, cplx, phi, lo, hi, nmom, mu, where);
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    const int64_t n = A->n;
+    DevBuf dc, dr;
+    const char *pc = (const char *)phi;
+    if (where == QBGPU_HOST) {
+        QB_TRY(dc.alloc(16 * n));
+        QB_CUDA(cudaMemcpyAsync(dc.p, phi, 16 * n, cudaMemcpyHostToDevice, c.stream));
+        pc = (const char *)dc.p;
+    } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    bool real0 = false;
+    QB_TRY(is_all_real(n, pc, &real0));
+    if (!real0) return kpm_impl(A, true, pc, lo, hi, nmom, mu, QBGPU_DEVICE);
+    QB_TRY(dr.alloc(8 * n));
+    QB_TRY(vec_take_real(n, pc, (double *)dr.p));
+    qbgpu_matrix R = *A;
+    R.api_complex = false;
+    return kpm_impl(&R, false, dr.p, lo, hi, nmom, mu, QBGPU_DEVICE);
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -361,23 +501,23 @@ int qbgpu_hess_eigen(const double *hess, int64_t maxit, int64_t m, double *ritz,
 }
 
 int qbgpu_lanczos_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, double *v, double *hess, const char *purpose, int where)
-{ return lanczos_impl(A, false, k, np, maxit, m, v, hess, purpose, where); }
+{ return lanczos_dispatch(A, false, k, np, maxit, m, v, hess, purpose, where); }
 int qbgpu_lanczos_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v, double *hess, const char *purpose, int where)
-{ return lanczos_impl(A, true, k, np, maxit, m, v, hess, purpose, where); }
+{ return lanczos_dispatch(A, true, k, np, maxit, m, v, hess, purpose, where); }
 
 int qbgpu_eigenvec_cg_d(qbgpu_matrix_t A, int64_t maxit, int64_t *m, double E0, double *accu, double *v, double *r, double *p, double *pp, int where)
-{ return cg_impl(A, false, maxit, m, make_double2(E0, 0.0), accu, v, r, p, pp, where); }
+{ return cg_dispatch(A, false, maxit, m, make_double2(E0, 0.0), accu, v, r, p, pp, where); }
 int qbgpu_eigenvec_cg_z(qbgpu_matrix_t A, int64_t maxit, int64_t *m, const double E0[2], double *accu, void *v, void *r, void *p, void *pp, int where)
-{ if (!E0) return fail(QBGPU_ERR_ARG, "null E0"); return cg_impl(A, true, maxit, m, make_double2(E0[0], E0[1]), accu, v, r, p, pp, where); }
+{ if (!E0) return fail(QBGPU_ERR_ARG, "null E0"); return cg_dispatch(A, true, maxit, m, make_double2(E0[0], E0[1]), accu, v, r, p, pp, where); }
 
 int qbgpu_energy_scale_d(qbgpu_matrix_t A, double *v, double *lo, double *hi, double extend, int64_t iters, int where)
-{ return energy_scale_impl(A, false, v, lo, hi, extend, iters, where); }
+{ return energy_scale_dispatch(A, false, v, lo, hi, extend, iters, where); }
 int qbgpu_energy_scale_z(qbgpu_matrix_t A, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
-{ return energy_scale_impl(A, true, v, lo, hi, extend, iters, where); }
+{ return energy_scale_dispatch(A, true, v, lo, hi, extend, iters, where); }
 
 int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double hi, int64_t nmom, double *mu, int where)
-{ return kpm_impl(A, false, phi, lo, hi, nmom, mu, where); }
+{ return kpm_dispatch(A, false, phi, lo, hi, nmom, mu, where); }
 int qbgpu_kpm_moments_z(qbgpu_matrix_t A, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
-{ return kpm_impl(A, true, phi, lo, hi, nmom, mu, where); }
+{ return kpm_dispatch(A, true, phi, lo, hi, nmom, mu, where); }
 
 }  // extern "C"

@@ -29,6 +29,9 @@ spmv_csr_vector_kernel(int64_t nrows, int64_t row_lo, const int64_t *__restrict_
     constexpr int RPB = kBlock / LANES;                    // rows per block per sweep
     const int lane = threadIdx.x & (LANES - 1);
     const int grp = threadIdx.x / LANES;
+    // shuffle mask = the LANES threads of this row group only: groups of one warp leave the row loop at different
+    // trips, and a full-warp mask would wait for lanes that already left
+    const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
     double dot_scale = 1.0;
     if (scal_mode == 1) {                                  // Lanczos step a: scalars produced by earlier kernels
         const double sx = sc[0], sz = sc[1], bprev = sc[2];
@@ -59,7 +62,7 @@ spmv_csr_vector_kernel(int64_t nrows, int64_t row_lo, const int64_t *__restrict_
         }
         VecT acc = VT::add(acc0, acc1);
 #pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) acc = VT::add(acc, VT::shfl_xor(acc, o, LANES));
+        for (int o = LANES / 2; o > 0; o >>= 1) acc = VT::add(acc, VT::shfl_xor(acc, o, LANES, gmask));
         if (lane == 0) {
             VecT out = VT::scale(alpha, acc);
             VecT xi = VT::zero();

@@ -102,6 +102,25 @@ int scale_copy(int64_t n, bool cplx, const double *scale_dev, double scale_imm, 
     return QBGPU_OK;
 }
 
+// ----------------------------------------------------------------- real <-> complex views of an all-real vector
+__global__ void __launch_bounds__(kVBlock) imag_abs2_kernel(int64_t n, const double2 *__restrict__ x, double *out, double *partials, unsigned *ticket)
+{
+    double d[1] = {0.0};
+    GRID_STRIDE(i, n) { const double im = x[i].y; d[0] += im * im; }
+    block_reduce_finalize<1, kVBlock>(d, partials, ticket, out);
+}
+__global__ void __launch_bounds__(kVBlock) take_real_kernel(int64_t n, const double2 *__restrict__ in, double *out) { GRID_STRIDE(i, n) out[i] = in[i].x; }
+__global__ void __launch_bounds__(kVBlock) put_real_kernel(int64_t n, const double *__restrict__ in, double2 *out) { GRID_STRIDE(i, n) out[i] = make_double2(in[i], 0.0); }
+
+int vec_imag_norm2(int64_t n, const void *x, double *out_dev)
+{
+    Context &c = ctx();
+    LAUNCH_V(imag_abs2_kernel, n, n, (const double2 *)x, out_dev, c.partials, c.ticket);
+    return QBGPU_OK;
+}
+int vec_take_real(int64_t n, const void *cplx_in, double *real_out) { LAUNCH_V(take_real_kernel, n, n, (const double2 *)cplx_in, real_out); return QBGPU_OK; }
+int vec_put_real(int64_t n, const double *real_in, void *cplx_out) { LAUNCH_V(put_real_kernel, n, n, real_in, (double2 *)cplx_out); return QBGPU_OK; }
+
 int read_scalars(const double *dev, double *host, int count)
 {
     Context &c = ctx();

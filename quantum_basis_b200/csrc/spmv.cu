@@ -231,10 +231,13 @@ static int mv_host(const qbgpu_matrix *A, double2 alpha, const void *x, double2 
     cudaEvent_t ev[8];
     for (int k = 0; k < chunks; k++) QB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
     for (int k = 0; k < chunks; k++) {
-        const int64_t r0 = nloc * k / chunks, r1 = nloc * (k + 1) / chunks;
+        // chunk boundaries on multiples of 32 rows so that a chunk is a whole number of slices in either layout
+        const int64_t r0 = (nloc * k / chunks) & ~31LL, r1 = (k + 1 == chunks) ? nloc : ((nloc * (k + 1) / chunks) & ~31LL);
+        if (r1 <= r0) { QB_CUDA(cudaEventRecord(ev[k], c.stream)); continue; }
         qbgpu_matrix sub = *A;                              // a view on rows [r0, r1) of this handle
         sub.row_lo = A->row_lo + r0; sub.row_hi = A->row_lo + r1;
         sub.rowptr = A->rowptr + r0;
+        if (A->rowinfo) sub.rowinfo = A->rowinfo + r0;
         FusedArgs a;
         a.x = c.stage_x;
         a.y = (char *)c.stage_y + vb * (size_t)r0;

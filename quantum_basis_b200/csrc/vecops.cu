@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kVBlock) scal_kernel(int64_t n, double2 a, Vec
 // dst = s * src with s = (scale_dev ? *scale_dev : 1) * scale_imm
 template <typename VecT>
 __global__ void __launch_bounds__(kVBlock) scale_copy_kernel(int64_t n, const double *scale_dev, double scale_imm,
-                                                             const VecT *__restrict__ src, VecT *dst)
+                                                             const VecT *src, VecT *dst)      // src may alias dst
 {
     using VT = VecTraits<VecT>;
     const double s = (scale_dev ? *scale_dev : 1.0) * scale_imm;

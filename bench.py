@@ -199,7 +199,10 @@ def main():
     torch.cuda.set_device(local_rank)
     L = qb.lib()
     assert L.qbgpu_init(local_rank) == 0, L.qbgpu_last_error()
-    stream = torch.cuda.current_stream()
+    # the library adopts a torch stream so that torch.cuda.Event timing sees its kernels (the legacy default stream has
+    # handle 0, which qbgpu_set_stream reads as "use your own stream": hence a dedicated non-default stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     assert L.qbgpu_set_stream(C.c_void_p(stream.cuda_stream)) == 0
 
     if world > 1:

@@ -88,6 +88,11 @@ int qbgpu_to_dense(qbgpu_matrix_t A, void *dense_host);
 /* copy the expanded device rows back (tests): rowptr[n_local+1], col[nnz], val[nnz] (complex unless val_is_real) */
 int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, void *val);
 
+/* Split a (shard) handle into `nparts` handles by column range: part p keeps the entries with
+ * col_bounds[p] <= col < col_bounds[p+1] of the same rows (col_bounds[0] = 0, col_bounds[nparts] = n, nparts <= 16).
+ * Used to multiply the block owned by rank p as soon as p's slice of x has arrived.  A is left intact. */
+int qbgpu_split_columns(qbgpu_matrix_t A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts, int flags);
+
 /* nnz-balanced contiguous row partition of the EXPANDED matrix over `parts` shards (host only, no GPU needed):
  * bounds[parts+1], bounds[0]=0, bounds[parts]=n. */
 int qbgpu_partition_rows(int64_t n, const int64_t *row_start, const int64_t *row_end, const int64_t *col,
@@ -170,6 +175,9 @@ int qbgpu_spmv_fused(qbgpu_matrix_t A, const void *x, const void *z, void *y,
  *   lanczos_step_c : b = sqrt(state[6]); a_dev[m-1] = state[3]; b_dev[m] = b; rotate (sx,sz,b_prev) <- (1/b,sx,b)
  * ux is the FULL gathered vector (n entries); uz and the local slice of ux have row_hi-row_lo entries. */
 int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev);
+/* the same pass on one column block of a split shard: first != 0 applies the -b*sz*uz term, later blocks accumulate
+ * into uz; last != 0 also reduces state[3] (uz then holds the complete w for the local rows) */
+int qbgpu_lanczos_step_a_part(qbgpu_matrix_t A_part, const void *ux_full, void *uz_local, double *state_dev, int first, int last);
 int qbgpu_lanczos_step_b(qbgpu_matrix_t A, const void *ux_local, void *uz_local, double *state_dev);
 int qbgpu_lanczos_step_c(double *state_dev, double *a_dev, double *b_dev, int64_t m);
 
@@ -188,6 +196,10 @@ int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbo
 /* dimension of those sectors (host only) */
 int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
+
+/* tuning hook used by scripts/kbench.py: selects an experimental instantiation of the sliced-jagged kernel
+ * (only in builds with -DQBGPU_TUNING_VARIANTS; otherwise a no-op).  id 0 = production configuration. */
+int qbgpu_debug_set_variant(int id);
 
 /* counters for bench.py's `gpu_launches` (kernels launched by this library since the last reset) */
 int64_t qbgpu_kernel_launches(int reset);

@@ -157,7 +157,7 @@ class csr_mat:
             b = (C.c_double * 2)(beta.real, beta.imag)
             check(lib().qbgpu_zmv(self.handle, a, _ptr(x), b, _ptr(y), where))
         else:
-            check(lib().qbgpu_dmv(self.handle, float(alpha), _ptr(x), float(beta), _ptr(y), where))
+            check(lib().qbgpu_dmv(self.handle, float(complex(alpha).real), _ptr(x), float(complex(beta).real), _ptr(y), where))
 
     def MultMv2(self, x, y):
         """y = H*x + y (src/sparse.cc:262-289)."""

@@ -156,6 +156,12 @@ int qbgpu_host_unregister(void *ptr)
     return QBGPU_OK;
 }
 
+int qbgpu_debug_set_variant(int id)
+{
+    qb::set_sjds_variant(id);
+    return QBGPU_OK;
+}
+
 int64_t qbgpu_kernel_launches(int reset)
 {
     long long v = g_ctx.launches;

@@ -50,7 +50,8 @@ struct FusedArgs {
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &args, int lanes_override = 0);
 int autotune(qbgpu_matrix *A, int flags = 0);
 int sjds_convert(qbgpu_matrix *A, bool forward);
-int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);      // in-place CSR <-> sliced-jagged re-ordering of col/val
+int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);
+void set_sjds_variant(int v);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // vecops.cu

@@ -226,6 +226,93 @@ static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, c
     return QBGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------- split by column owner
+// Multi-GPU pipelining (quantum_basis_b200/dist.py): a row shard is split into one block per column owner so that
+// the block of rank p can be multiplied as soon as p's slice of x has arrived.  Columns are sorted inside a row, so
+// every block is a contiguous sub-range of the row.
+constexpr int kMaxParts = 16;
+struct PartBounds { int64_t b[kMaxParts + 1]; };
+
+__global__ void __launch_bounds__(kCBlock) split_count_kernel(int64_t nloc, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                              int nparts, PartBounds pb, int64_t *len /* [nparts][nloc+1] */)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nloc; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i == nloc) { for (int p = 0; p < nparts; p++) len[(int64_t)p * (nloc + 1) + i] = 0; continue; }
+        int p = 0;
+        int64_t cnt = 0;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) {
+            const int64_t c = col[k];
+            while (c >= pb.b[p + 1]) { len[(int64_t)p * (nloc + 1) + i] = cnt; cnt = 0; p++; }
+            cnt++;
+        }
+        for (; p < nparts; p++) { len[(int64_t)p * (nloc + 1) + i] = cnt; cnt = 0; }
+    }
+}
+
+template <typename ValT>
+__global__ void __launch_bounds__(kCBlock) split_copy_kernel(int64_t nloc, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                             const ValT *__restrict__ val, int part, int64_t lo, int64_t hi,
+                                                             const int64_t *__restrict__ prow, int32_t *pcol, ValT *pval)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = prow[i];
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) {
+            const int64_t c = col[k];
+            if (c >= hi) break;
+            if (c >= lo) { pcol[o] = (int32_t)c; pval[o] = val[k]; o++; }
+        }
+    }
+}
+
+static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matrix_t *out, int flags)
+{
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    if (!A || !bounds || !out || nparts < 1 || nparts > kMaxParts) return fail(QBGPU_ERR_ARG, "split_columns: bad argument (1..16 parts)");
+    if (bounds[0] != 0 || bounds[nparts] != A->n) return fail(QBGPU_ERR_ARG, "split_columns: bounds must run from 0 to n");
+    for (int p = 0; p < nparts; p++) if (bounds[p + 1] < bounds[p]) return fail(QBGPU_ERR_ARG, "split_columns: bounds must be non-decreasing");
+    QB_TRY(sjds_convert(A, false));                         // needs plain CSR order
+    const int64_t nloc = A->nrows();
+    PartBounds pb;
+    for (int p = 0; p <= nparts; p++) pb.b[p] = bounds[p];
+    for (int p = nparts + 1; p <= kMaxParts; p++) pb.b[p] = A->n;
+    for (int p = 0; p < nparts; p++) out[p] = nullptr;
+    int64_t *d_len = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_len); cudaFree(d_tmp); };
+    auto abort_all = [&]() { cleanup(); for (int p = 0; p < nparts; p++) { qbgpu_destroy(out[p]); out[p] = nullptr; } };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { abort_all(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_len, sizeof(int64_t) * (size_t)nparts * (nloc + 1)));
+    split_count_kernel<<<grid_for(nloc + 1), kCBlock, 0, c.stream>>>(nloc, A->rowptr, A->col, nparts, pb, d_len);
+    QB_LAUNCH_COUNT();
+    size_t tmp_bytes = 0;
+    QB_CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_len, nloc + 1, c.stream));
+    QB_CU(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    for (int p = 0; p < nparts; p++) {
+        auto *P = new qbgpu_matrix;
+        out[p] = P;
+        P->n = A->n; P->row_lo = A->row_lo; P->row_hi = A->row_hi; P->val_real = A->val_real; P->api_complex = A->api_complex;
+        QB_CU(cudaMalloc(&P->rowptr, sizeof(int64_t) * (nloc + 1)));
+        QB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len + (int64_t)p * (nloc + 1), P->rowptr, nloc + 1, c.stream));
+        int64_t nnz = 0;
+        QB_CU(cudaMemcpyAsync(&nnz, P->rowptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+        QB_CU(cudaStreamSynchronize(c.stream));
+        P->nnz = nnz; P->nnz_input = nnz;
+        QB_CU(cudaMalloc(&P->col, sizeof(int32_t) * (nnz ? nnz : 1)));
+        QB_CU(cudaMalloc(&P->val, P->val_bytes() * (nnz ? nnz : 1)));
+        if (A->val_real) split_copy_kernel<double><<<grid_for(nloc), kCBlock, 0, c.stream>>>(nloc, A->rowptr, A->col, (const double *)A->val, p, bounds[p], bounds[p + 1], P->rowptr, P->col, (double *)P->val);
+        else             split_copy_kernel<double2><<<grid_for(nloc), kCBlock, 0, c.stream>>>(nloc, A->rowptr, A->col, (const double2 *)A->val, p, bounds[p], bounds[p + 1], P->rowptr, P->col, (double2 *)P->val);
+        QB_LAUNCH_COUNT();
+        QB_CU(cudaStreamSynchronize(c.stream));
+        QB_CU(cudaGetLastError());
+    }
+    cleanup();
+#undef QB_CU
+    for (int p = 0; p < nparts; p++) { int rc = autotune(out[p], flags); if (rc) { abort_all(); return rc; } }
+    return QBGPU_OK;
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -303,6 +390,11 @@ int qbgpu_to_dense(qbgpu_matrix_t A, void *dense)
             if (A->val_real) D[at] = vv[p]; else { D[at] = vv[2 * p]; D[at + 1] = vv[2 * p + 1]; }
         }
     return QBGPU_OK;
+}
+
+int qbgpu_split_columns(qbgpu_matrix_t A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts, int flags)
+{
+    return split_columns(A, nparts, col_bounds, parts, flags);
 }
 
 int qbgpu_partition_rows(int64_t n, const int64_t *rs, const int64_t *re, const int64_t *col, int sym, int parts, int64_t *bounds)

@@ -22,8 +22,64 @@ namespace qb {
 constexpr int kSBlock = 256;
 constexpr uint32_t kLenMask = 0xFFFFFFu;
 
-template <typename ValT, typename VecT, bool DOTS>
-__global__ void __launch_bounds__(kSBlock)
+// ---- cache-policy helpers (PTX): the matrix stream should leave L2 first, the gathered vector last ------------
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last()  { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+
+// All loads of the inner loop are volatile asm so that they are issued in program order -- first the U column and
+// value loads of a trip, then the U gathers -- instead of ptxas' register-frugal "load, gather, fma" chain per
+// diagonal, which leaves a warp with a single dependent pair of loads in flight.
+template <int POL> __device__ __forceinline__ int ld_i32(const int *p, uint64_t pol)
+{
+    int v;
+    if (POL == 0) asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (POL == 1) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (POL == 2) asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int POL> __device__ __forceinline__ double ld_f64(const double *p, uint64_t pol)
+{
+    double v;
+    if (POL == 0) asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (POL == 1) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (POL == 2) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int POL> __device__ __forceinline__ double2 ld_f64(const double2 *p, uint64_t pol)
+{
+    double2 v;
+    if (POL == 0) asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else if (POL == 1) asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else if (POL == 2) asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+// gathered vector: XPOL 0 = read-only path, default policy; 1 = read-only path + L2 evict_last
+template <int XPOL> __device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
+{
+    double v;
+    if (XPOL == 0) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int XPOL> __device__ __forceinline__ double2 ld_x(const double2 *p, uint64_t pol)
+{
+    double2 v;
+    if (XPOL == 0) asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+// U = jagged diagonals per trip (U independent col/val loads, then U gathers); SPOL/XPOL = cache policies above;
+// UL = unconditional loads: lanes whose row has ended re-read the slice's first entry (always valid, L1-resident)
+// instead of branching around the loads, so that all 3U loads of a trip can be in flight together;
+// MINB = __launch_bounds__ min blocks/SM: without it ptxas schedules for 32 registers (full occupancy) and chains
+// "load column, load value, gather, fma" one diagonal at a time -- a single dependent pair of loads in flight per
+// warp; with MINB <= 4 it batches the U column loads, the U value loads and the U gathers (checked in the SASS).
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB>
+__global__ void __launch_bounds__(kSBlock, MINB)
 spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
                  const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
@@ -32,12 +88,13 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
     using VT = VecTraits<VecT>;
     constexpr int WPB = kSBlock / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol_s = SPOL >= 2 ? l2_policy_evict_first() : 0, pol_x = XPOL >= 1 ? l2_policy_evict_last() : 0;
     double dot_scale = 1.0;
-    if (scal_mode == 1) {
+    if (scal_mode != 0) {                                  // Lanczos step a: 1 = first column block, 2 = a later one
         const double sx = sc[0], sz = sc[1], bprev = sc[2];
         alpha = make_double2(sx, 0.0);
         gamma = make_double2(0.0, 0.0);
-        beta = make_double2(-bprev * sz, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
         dot_scale = sx;
     }
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
@@ -49,33 +106,47 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
         const int len = (int)(info & kLenMask);
         const int64_t row = s * 32 + (info >> 24);
         const int maxlen = __shfl_sync(0xffffffffu, len, 0);
-        int64_t off = rowptr[s * 32] + lane;               // this lane's entry at step k is off_k + lane
+        const int64_t base = rowptr[s * 32];
+        int64_t off = base + lane;                          // this lane's entry at step k is off_k + lane
         VecT acc0 = VT::zero(), acc1 = VT::zero();
-        int k = 0;
-        for (; k + 4 <= maxlen; k += 4) {                  // 4 jagged diagonals per trip: 12 independent loads per lane
-            const bool a0 = k < len, a1 = k + 1 < len, a2 = k + 2 < len, a3 = k + 3 < len;
-            const int n0 = __popc(__ballot_sync(0xffffffffu, a0)), n1 = __popc(__ballot_sync(0xffffffffu, a1));
-            const int n2 = __popc(__ballot_sync(0xffffffffu, a2)), n3 = __popc(__ballot_sync(0xffffffffu, a3));
-            const int64_t o0 = off, o1 = o0 + n0, o2 = o1 + n1, o3 = o2 + n2;
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            ValT v0{}, v1{}, v2{}, v3{};
-            if (a0) { c0 = ld_stream(col + o0); v0 = ld_stream(val + o0); }
-            if (a1) { c1 = ld_stream(col + o1); v1 = ld_stream(val + o1); }
-            if (a2) { c2 = ld_stream(col + o2); v2 = ld_stream(val + o2); }
-            if (a3) { c3 = ld_stream(col + o3); v3 = ld_stream(val + o3); }
-            if (a0) mac(acc0, v0, ld_vec(x + c0));
-            if (a1) mac(acc1, v1, ld_vec(x + c1));
-            if (a2) mac(acc0, v2, ld_vec(x + c2));
-            if (a3) mac(acc1, v3, ld_vec(x + c3));
-            off = o3 + n3;
+        for (int k = 0; k < maxlen; k += U) {              // U jagged diagonals per trip; the tail is predicated off
+            bool a[U];
+            int64_t o[U];
+            int c[U];
+            ValT v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                a[u] = k + u < len;
+                o[u] = (UL && !a[u]) ? base : off;
+                off += __popc(__ballot_sync(0xffffffffu, a[u]));
+            }
+            if (UL) {
+                VecT xv[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) c[u] = ld_i32<SPOL>(col + o[u], pol_s);
+#pragma unroll
+                for (int u = 0; u < U; u++) v[u] = ld_f64<SPOL>(val + o[u], pol_s);
+#pragma unroll
+                for (int u = 0; u < U; u++) xv[u] = ld_x<XPOL>(x + c[u], pol_x);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    VecT t = (u & 1) ? acc1 : acc0;
+                    mac(t, v[u], xv[u]);
+                    if (a[u]) { if (u & 1) acc1 = t; else acc0 = t; }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    c[u] = 0; v[u] = ValT{};
+                    if (a[u]) { c[u] = ld_i32<SPOL>(col + o[u], pol_s); v[u] = ld_f64<SPOL>(val + o[u], pol_s); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (a[u]) { if (u & 1) mac(acc1, v[u], ld_x<XPOL>(x + c[u], pol_x)); else mac(acc0, v[u], ld_x<XPOL>(x + c[u], pol_x)); }
+                }
+            }
         }
-        for (; k < maxlen; k++) {
-            const bool a0 = k < len;
-            const int n0 = __popc(__ballot_sync(0xffffffffu, a0));
-            if (a0) { const int c0 = ld_stream(col + off); const ValT v0 = ld_stream(val + off); mac(acc0, v0, ld_vec(x + c0)); }
-            off += n0;
-        }
-        if (len > 0) {                                      // padding ranks of the last slice have length 0
+        if (row < nrows) {                                  // padding ranks of the last slice point past the last row
             const VecT acc = VT::add(acc0, acc1);
             VecT out = VT::scale(alpha, acc);
             VecT xi = VT::zero();
@@ -95,11 +166,16 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
     }
 }
 
-template <typename ValT, typename VecT, bool DOTS>
+// tuning hook (qbgpu_debug_set_variant): variant id = 1 + MINB_index*16 + UL*8 + U_index*4 + SPOL_index*2 + XPOL
+// (MINB_index 0 -> 2 blocks/SM, 1 -> 4; U_index 0 -> 4, 1 -> 8; SPOL_index 0 -> .cs, 1 -> L2 evict_first hint)
+static int g_sjds_variant = 0;
+void set_sjds_variant(int v) { g_sjds_variant = v; }
+
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB>
 static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
-    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS>;
+    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS, U, SPOL, XPOL, UL, MINB>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kSBlock, 0));
@@ -121,12 +197,39 @@ static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
     return QBGPU_OK;
 }
 
-int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)
+// production configuration of the template (chosen from the measurements in profiles/)
+constexpr int kProdU = 8, kProdS = 0, kProdX = 0, kProdMinB = 2;
+constexpr bool kProdUL = true;
+
+template <typename ValT, typename VecT>
+static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
 {
     const bool dots = a.dots != nullptr;
-    if (!A->api_complex) return dots ? launch_sjds_variant<double, double, true>(A, a) : launch_sjds_variant<double, double, false>(A, a);
-    if (A->val_real) return dots ? launch_sjds_variant<double, double2, true>(A, a) : launch_sjds_variant<double, double2, false>(A, a);
-    return dots ? launch_sjds_variant<double2, double2, true>(A, a) : launch_sjds_variant<double2, double2, false>(A, a);
+#ifdef QBGPU_TUNING_VARIANTS
+    if constexpr (sizeof(ValT) == 8) {                      // experimental instantiations only for fp64 values
+        if (!dots && g_sjds_variant > 0) {
+            switch (g_sjds_variant - 1) {
+#define QB_V1(M, MI, L, U, UI, S, SI, X) case (MI * 16 + (L ? 8 : 0) + UI * 4 + SI * 2 + X): return launch_sjds_variant<ValT, VecT, false, U, S, X, L, M>(A, a);
+#define QB_V2(M, MI, L, U, UI) QB_V1(M, MI, L, U, UI, 0, 0, 0) QB_V1(M, MI, L, U, UI, 0, 0, 1) QB_V1(M, MI, L, U, UI, 2, 1, 0) QB_V1(M, MI, L, U, UI, 2, 1, 1)
+#define QB_V3(M, MI) QB_V2(M, MI, false, 4, 0) QB_V2(M, MI, false, 8, 1) QB_V2(M, MI, true, 4, 0) QB_V2(M, MI, true, 8, 1)
+                QB_V3(2, 0) QB_V3(4, 1)
+#undef QB_V1
+#undef QB_V2
+#undef QB_V3
+            default: break;
+            }
+        }
+    }
+#endif
+    return dots ? launch_sjds_variant<ValT, VecT, true, kProdU, kProdS, kProdX, kProdUL, kProdMinB>(A, a)
+                : launch_sjds_variant<ValT, VecT, false, kProdU, kProdS, kProdX, kProdUL, kProdMinB>(A, a);
+}
+
+int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    if (!A->api_complex) return launch_sjds_typed<double, double>(A, a);
+    if (A->val_real) return launch_sjds_typed<double, double2>(A, a);
+    return launch_sjds_typed<double2, double2>(A, a);
 }
 
 // ------------------------------------------------------------------------------------------ format conversion

@@ -19,7 +19,7 @@ namespace qb {
 constexpr int kBlock = 256;
 
 template <typename ValT, typename VecT, int LANES, bool DOTS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)     // min 3 blocks/SM: lets ptxas keep ~8 column/value/gather loads in flight per lane
 spmv_csr_vector_kernel(int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                        const ValT *__restrict__ val, const VecT *__restrict__ x, const VecT *z, VecT *y,
                        double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc,
@@ -33,11 +33,11 @@ spmv_csr_vector_kernel(int64_t nrows, int64_t row_lo, const int64_t *__restrict_
     // trips, and a full-warp mask would wait for lanes that already left
     const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
     double dot_scale = 1.0;
-    if (scal_mode == 1) {                                  // Lanczos step a: scalars produced by earlier kernels
-        const double sx = sc[0], sz = sc[1], bprev = sc[2];
-        alpha = make_double2(sx, 0.0);
+    if (scal_mode != 0) {                                  // Lanczos step a (scalars produced by earlier kernels):
+        const double sx = sc[0], sz = sc[1], bprev = sc[2]; // 1 = first column block (w = sx*H*ux - b*sz*uz),
+        alpha = make_double2(sx, 0.0);                      // 2 = a later column block (w += sx*H_p*ux)
         gamma = make_double2(0.0, 0.0);
-        beta = make_double2(-bprev * sz, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
         dot_scale = sx;
     }
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
@@ -298,17 +298,22 @@ int qbgpu_spmv_fused(qbgpu_matrix_t A, const void *x, const void *z, void *y, co
     return launch_spmv(A, a);
 }
 
-int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev)
+int qbgpu_lanczos_step_a_part(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev, int first, int last)
 {
     QB_TRY(ensure_init());
     if (!A || !ux_full || !uz_local || !state_dev) return fail(QBGPU_ERR_ARG, "null argument");
     FusedArgs a;
     a.x = ux_full; a.z = uz_local; a.y = uz_local;
-    a.scal_mode = 1; a.sc = state_dev;
+    a.scal_mode = first ? 1 : 2; a.sc = state_dev;
     a.beta = make_double2(1.0, 0.0);                       // placeholder: the kernel derives beta from the state
-    a.dots = state_dev + 3;                                // state[3]=alpha partial, [4]=Im (unused), [5]=|w|^2 (unused)
+    a.dots = last ? state_dev + 3 : nullptr;               // state[3]=alpha partial, [4]=Im (unused), [5]=|w|^2 (unused)
     QB_TRY(launch_spmv(A, a));
     return QBGPU_OK;
+}
+
+int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev)
+{
+    return qbgpu_lanczos_step_a_part(A, ux_full, uz_local, state_dev, 1, 1);
 }
 
 }  // extern "C"

@@ -62,6 +62,57 @@ def sharded_lanczos(op, u0, u1, maxit, steps, state, a_dev, b_dev):
     return U
 
 
+class PipelinedOperator(ShardedOperator):
+    """The same product with the exchange overlapped: x travels as one broadcast per owner (issued asynchronously, in
+    rank order), the shard is split into one column block per owner (qbgpu_split_columns), and block p is multiplied
+    as soon as p's slice has arrived -- the own block first, while the first transfers are in flight."""
+
+    def __init__(self, kernels, n, rank, world, comm):
+        super().__init__(kernels, n, rank, world, comm)
+        self.order = [rank] + [p for p in range(world) if p != rank]
+        self.col_bounds = [min(n, p * self.chunk) for p in range(world)] + [n]
+
+    def gather_async(self, x_local_padded):
+        works = []
+        for p in range(self.world):
+            seg = self.k.segment(self.x_full, p * self.chunk, self.chunk)
+            if p == self.rank:
+                seg.copy_(x_local_padded)
+            works.append(self.comm.broadcast_async(seg, p))
+        return works
+
+    def matvec(self, x_local_padded, y_local):
+        works = self.gather_async(x_local_padded)
+        for idx, p in enumerate(self.order):
+            if p != self.rank:
+                works[p].wait()
+            self.k.multmv_part(p, self.x_full, y_local, accumulate=(idx > 0))
+        works[self.rank].wait()
+
+    def lanczos_step_a(self, ux, uz, state):
+        works = self.gather_async(ux)
+        last = len(self.order) - 1
+        for idx, p in enumerate(self.order):
+            if p != self.rank:
+                works[p].wait()
+            self.k.lanczos_step_a_part(p, self.x_full, uz, state, idx == 0, idx == last)
+        works[self.rank].wait()
+
+
+def pipelined_lanczos(op, u0, u1, maxit, steps, state, a_dev, b_dev):
+    """sharded_lanczos with the overlapped exchange of PipelinedOperator."""
+    k, comm = op.k, op.comm
+    U = [u0, u1]
+    for m in range(1, steps + 1):
+        ux, uz = U[(m - 1) % 2], U[m % 2]
+        op.lanczos_step_a(ux, uz, state)
+        comm.all_reduce(k.slot(state, 3))
+        k.lanczos_step_b(ux, uz, state)
+        comm.all_reduce(k.slot(state, 6))
+        k.lanczos_step_c(state, a_dev, b_dev, m)
+    return U
+
+
 # ----------------------------------------------------------------------------------------------- GPU provider
 class TorchComm:
     def __init__(self):
@@ -73,6 +124,9 @@ class TorchComm:
 
     def all_reduce(self, t):
         self.dist.all_reduce(t)
+
+    def broadcast_async(self, t, src):
+        return self.dist.broadcast(t, src=src, async_op=True)
 
     def barrier(self):
         self.dist.barrier()
@@ -91,8 +145,30 @@ class DeviceKernels:
     def slot(self, state, i):
         return state[i:i + 1]
 
+    def segment(self, t, first_entry, nentries):
+        return t[2 * first_entry: 2 * (first_entry + nentries)]
+
     def _p(self, t):
         return C.c_void_p(t.data_ptr())
+
+    def split(self, col_bounds, flags=0):
+        """one handle per column owner (qbgpu_split_columns)"""
+        nparts = len(col_bounds) - 1
+        b = np.array(col_bounds, dtype=np.int64)
+        hs = (C.c_void_p * nparts)()
+        rc = self.L.qbgpu_split_columns(self.M.handle, nparts, b.ctypes.data, hs, flags)
+        assert rc == 0, self.L.qbgpu_last_error()
+        self.parts = [self.qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
+        return self.parts
+
+    def multmv_part(self, p, x_full, y_local, accumulate):
+        one = (C.c_double * 2)(1.0, 0.0); beta = (C.c_double * 2)(1.0 if accumulate else 0.0, 0.0)
+        rc = self.L.qbgpu_zmv(self.parts[p].handle, one, self._p(x_full), beta, self._p(y_local), 1)
+        assert rc == 0, self.L.qbgpu_last_error()
+
+    def lanczos_step_a_part(self, p, x_full, uz, state, first, last):
+        rc = self.L.qbgpu_lanczos_step_a_part(self.parts[p].handle, self._p(x_full), self._p(uz), self._p(state), int(first), int(last))
+        assert rc == 0, self.L.qbgpu_last_error()
 
     def multmv(self, x_full, y_local):
         one = (C.c_double * 2)(1.0, 0.0); zero = (C.c_double * 2)(0.0, 0.0)
@@ -119,7 +195,7 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = qb.lib()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.current_stream()          # bench.py installed a dedicated stream and handed it to the library
     fam, p = WORKLOADS[args.workload]
     if fam == "hubbard":
         n = L.qbgpu_dim_hubbard(p["Lx"] * p["Ly"], p["nup"], p["ndn"])

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Kernel-variant micro-benchmark (tuning aid, not the product bench): times every experimental instantiation of the
+sliced-jagged H*v kernel (qbgpu_debug_set_variant) and the CSR-vector lane widths on one workload.
+Usage: python scripts/kbench.py <workload> [--real] [--ids a,b,c] [--reps N]"""
+import argparse
+import ctypes as C
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import bench  # noqa: E402
+import quantum_basis_b200 as qb  # noqa: E402
+
+
+def describe(v):
+    if v == 0:
+        return "production"
+    w = v - 1
+    return f"minb={2 if w // 16 == 0 else 4} UL={(w // 8) % 2} U={4 if (w // 4) % 2 == 0 else 8} S={'cs' if (w // 2) % 2 == 0 else 'L2ef'} X={'nc' if w % 2 == 0 else 'L2el'}"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("workload")
+    ap.add_argument("--real", action="store_true", help="fp64 vectors (a `d` handle) instead of complex")
+    ap.add_argument("--ids", default="")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
+    a = ap.parse_args()
+    L = qb.lib()
+    assert L.qbgpu_init(0) == 0
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    L.qbgpu_set_stream(C.c_void_p(stream.cuda_stream))
+    fam, p = bench.WORKLOADS[a.workload]
+    t0 = time.time()
+    h = C.c_void_p()
+    cplx = 0 if a.real else 1
+    flags = 8 | 2          # sliced-jagged, no autotune
+    if fam == "hubbard":
+        bonds = np.array(bench.square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
+        rc = L.qbgpu_build_hubbard(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data, p["t"], p["U"], cplx, flags, 0, -1)
+    else:
+        n = p["L"]
+        bonds = np.array([(x, (x + 1) % n) for x in range(n)], dtype=np.int32).ravel()
+        rc = L.qbgpu_build_heisenberg(C.byref(h), n, n // 2, n, bonds.ctypes.data, 1.0, cplx, flags, 0, -1)
+    assert rc == 0, L.qbgpu_last_error()
+    M = qb.csr_mat._adopt(h, bool(cplx))
+    torch.cuda.synchronize()
+    inf = M.info
+    n, Z = inf.n, inf.nnz_stored
+    s_vec = 16 if cplx else 8
+    B = bench.algorithmic_bytes(Z, n, n, 8, s_vec)
+    print(f"# {a.workload}: n={n} Z={Z} B_spmv={B/1e9:.2f} GB (S_val=8,S_vec={s_vec}) build {time.time()-t0:.1f}s", flush=True)
+    dt = np.complex128 if cplx else np.float64
+    x = qb.vec_randomize(n, 1, dtype=dt, device=True)
+    y = qb.DeviceVector(n, dt)
+    ids = [int(t) for t in a.ids.split(",")] if a.ids else list(range(0, 33))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = []
+    for v in ids:
+        L.qbgpu_debug_set_variant(v)
+        for _ in range(2):
+            M.MultMv(x, y)
+        e0.record(stream)
+        for _ in range(a.reps):
+            M.MultMv(x, y)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.reps
+        res.append((ms, v))
+        print(f"variant {v:2d} [{describe(v):44s}] {ms:8.3f} ms  {B/ms/1e6:7.0f} GB/s  {B/ms/1e6/6451.8:5.3f} of measured peak", flush=True)
+    L.qbgpu_debug_set_variant(0)
+    res.sort()
+    print("# best:", ", ".join(f"{v}:{ms:.3f}" for ms, v in res[:5]))
+    if a.csr:
+        M.destroy()
+        for lanes_flag in (4 | 2,):
+            h2 = C.c_void_p()
+            os.environ["QBGPU_VERBOSE"] = "1"
+            if fam == "hubbard":
+                rc = L.qbgpu_build_hubbard(C.byref(h2), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data, p["t"], p["U"], cplx, 4, 0, -1)
+            else:
+                rc = L.qbgpu_build_heisenberg(C.byref(h2), p["L"], p["L"] // 2, p["L"], bonds.ctypes.data, 1.0, cplx, 4, 0, -1)
+            assert rc == 0, L.qbgpu_last_error()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,37 @@ class OracleKernels:
         xl = x[dist.get_rank() * chunk: dist.get_rank() * chunk + nl]
         state[3] = float(np.real(np.vdot(sx * xl, w)))
 
+    def segment(self, t, first_entry, nentries):
+        return t[2 * first_entry: 2 * (first_entry + nentries)]
+
+    def set_col_bounds(self, col_bounds):
+        self.cb = col_bounds
+        Fc = self.F.tocsc()
+        self.Fp = [Fc[:, col_bounds[p]:col_bounds[p + 1]].tocsr() for p in range(len(col_bounds) - 1)]
+
+    def multmv_part(self, p, x_full, y_local, accumulate):
+        nl = self.hi - self.lo
+        part = self.Fp[p] @ self._c(x_full)[self.cb[p]:self.cb[p + 1]]
+        y = self._c(y_local)
+        y[:nl] = y[:nl] + part if accumulate else part
+
+    def lanczos_step_a_part(self, p, x_full, uz, state, first, last):
+        sx, sz, bprev = state[0].item(), state[1].item(), state[2].item()
+        nl = self.hi - self.lo
+        x = self._c(x_full)
+        z = self._c(uz)
+        w = sx * (self.Fp[p] @ x[self.cb[p]:self.cb[p + 1]])
+        if first:
+            if bprev * sz != 0.0:
+                w = w - bprev * sz * z[:nl]
+        else:
+            w = w + z[:nl]
+        z[:nl] = w
+        if last:
+            chunk = x_full.numel() // 2 // dist.get_world_size()
+            xl = x[dist.get_rank() * chunk: dist.get_rank() * chunk + nl]
+            state[3] = float(np.real(np.vdot(sx * xl, w)))
+
     def lanczos_step_b(self, ux, uz, state):
         nl = self.hi - self.lo
         z = self._c(uz)
@@ -89,7 +120,17 @@ def _worker(rank, world, port, name, q):
     steps = 25
     state = torch.zeros(8, dtype=torch.float64); state[0] = 1.0
     a_dev = torch.zeros(64, dtype=torch.float64); b_dev = torch.zeros(64, dtype=torch.float64)
-    qdist.sharded_lanczos(op, x_loc, kern.alloc(chunk), 64, steps, state, a_dev, b_dev)
+    qdist.sharded_lanczos(op, x_loc.clone(), kern.alloc(chunk), 64, steps, state, a_dev, b_dev)
+    # the pipelined variant (one broadcast per owner, one column block per owner) must give the same numbers
+    pop = qdist.PipelinedOperator(kern, n, rank, world, qdist.TorchComm())
+    kern.set_col_bounds(pop.col_bounds)
+    y2 = kern.alloc(chunk)
+    pop.matvec(x_loc, y2)
+    err_pipe = np.linalg.norm(OracleKernels._c(y2)[: hi - lo] - ex["y1"][lo:hi]) / np.linalg.norm(ex["y1"][lo:hi])
+    state2 = torch.zeros(8, dtype=torch.float64); state2[0] = 1.0
+    a2 = torch.zeros(64, dtype=torch.float64); b2 = torch.zeros(64, dtype=torch.float64)
+    qdist.pipelined_lanczos(pop, x_loc.clone(), kern.alloc(chunk), 64, steps, state2, a2, b2)
+    err_mv = max(err_mv, err_pipe, float((a2 - a_dev).abs().max()) * 1e-2, float((b2 - b_dev).abs().max()) * 1e-2)
     q.put((rank, err_mv, a_dev.numpy().copy(), b_dev.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()

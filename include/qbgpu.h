@@ -88,6 +88,11 @@ int qbgpu_to_dense(qbgpu_matrix_t A, void *dense_host);
 /* copy the expanded device rows back (tests): rowptr[n_local+1], col[nnz], val[nnz] (complex unless val_is_real) */
 int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, void *val);
 
+/* A second handle on the SAME device arrays that takes fp64 vectors (d entry points).  Only for handles whose stored
+ * values are real (val_is_real): a real H applied to a real vector stays real, so a Krylov loop started from
+ * vec_randomize (imag = 0, src/miscellaneous.cc:382) can run on half the vector bytes.  Destroy the view before A. */
+int qbgpu_real_view(qbgpu_matrix_t A, qbgpu_matrix_t *view);
+
 /* Split a (shard) handle into `nparts` handles by column range: part p keeps the entries with
  * col_bounds[p] <= col < col_bounds[p+1] of the same rows (col_bounds[0] = 0, col_bounds[nparts] = n, nparts <= 16).
  * Used to multiply the block owned by rank p as soon as p's slice of x has arrived.  A is left intact. */
@@ -200,6 +205,9 @@ int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
 /* tuning hook used by scripts/kbench.py: selects an experimental instantiation of the sliced-jagged kernel
  * (only in builds with -DQBGPU_TUNING_VARIANTS; otherwise a no-op).  id 0 = production configuration. */
 int qbgpu_debug_set_variant(int id);
+/* |col - row| beyond which a gathered entry is loaded with the L2 evict-first policy (kernels with the per-entry
+ * gather policy only) */
+int qbgpu_debug_set_far_rows(int64_t rows);
 
 /* counters for bench.py's `gpu_launches` (kernels launched by this library since the last reset) */
 int64_t qbgpu_kernel_launches(int reset);

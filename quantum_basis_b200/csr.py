@@ -144,6 +144,14 @@ class csr_mat:
     def dimension(self):
         return self.dim
 
+    def real_view(self):
+        """A csr_mat<double>-typed view on the same device arrays (only when the stored values are real)."""
+        h = C.c_void_p()
+        check(lib().qbgpu_real_view(self.handle, C.byref(h)))
+        v = csr_mat._adopt(h, False)
+        v._parent = self                                   # keep the owner alive
+        return v
+
     # y = alpha*H*x + beta*y : what csr_mat::MultMv2 asks of mkl_sparse_?_mv (src/sparse.cc:287)
     def _mv(self, alpha, x, beta, y):
         if self.handle is None:

@@ -162,6 +162,12 @@ int qbgpu_debug_set_variant(int id)
     return QBGPU_OK;
 }
 
+int qbgpu_debug_set_far_rows(int64_t rows)
+{
+    qb::set_sjds_far_rows(rows);
+    return QBGPU_OK;
+}
+
 int64_t qbgpu_kernel_launches(int reset)
 {
     long long v = g_ctx.launches;

@@ -15,6 +15,7 @@ struct qbgpu_matrix {
     int64_t n = 0, row_lo = 0, row_hi = 0;
     int64_t nnz = 0, nnz_input = 0;
     bool    val_real = false, api_complex = false;
+    bool    borrowed = false;      // a view sharing another handle's arrays (qbgpu_real_view): destroy frees nothing
     int     format = QBGPU_FORMAT_CSR;
     int     lanes = 8;
     int64_t *rowptr = nullptr;
@@ -51,7 +52,8 @@ int launch_spmv(const qbgpu_matrix *A, const FusedArgs &args, int lanes_override
 int autotune(qbgpu_matrix *A, int flags = 0);
 int sjds_convert(qbgpu_matrix *A, bool forward);
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);
-void set_sjds_variant(int v);      // in-place CSR <-> sliced-jagged re-ordering of col/val
+void set_sjds_variant(int v);
+void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // vecops.cu

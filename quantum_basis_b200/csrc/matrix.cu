@@ -338,7 +338,7 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
-    cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo);
+    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); }
     delete A;
     return QBGPU_OK;
 }
@@ -389,6 +389,17 @@ int qbgpu_to_dense(qbgpu_matrix_t A, void *dense)
             const int64_t at = (r + (int64_t)cc[p] * n) * nc;
             if (A->val_real) D[at] = vv[p]; else { D[at] = vv[2 * p]; D[at + 1] = vv[2 * p + 1]; }
         }
+    return QBGPU_OK;
+}
+
+int qbgpu_real_view(qbgpu_matrix_t A, qbgpu_matrix_t *view)
+{
+    if (!A || !view) return fail(QBGPU_ERR_ARG, "null argument");
+    if (!A->val_real) return fail(QBGPU_ERR_STATE, "real_view: the stored values are complex");
+    auto *V = new qbgpu_matrix(*A);
+    V->api_complex = false;
+    V->borrowed = true;
+    *view = V;
     return QBGPU_OK;
 }
 

@@ -56,11 +56,13 @@ template <int POL> __device__ __forceinline__ double2 ld_f64(const double2 *p, u
     else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
-// gathered vector: XPOL 0 = read-only path, default policy; 1 = read-only path + L2 evict_last
+// gathered vector: XPOL 0 = read-only path, default policy; 1 = read-only path + L2 evict_last; 2 = per entry:
+// evict_last when the column is within `far_rows` of the row (it will be gathered again soon by a neighbouring
+// jagged diagonal), evict_first for the long-range terms, whose next use is further away than L2 can hold
 template <int XPOL> __device__ __forceinline__ double ld_x(const double *p, uint64_t pol)
 {
     double v;
-    if (XPOL == 0) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    if (XPOL == 0) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));  // XPOL 1,2: policy operand
     else asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
@@ -83,12 +85,13 @@ __global__ void __launch_bounds__(kSBlock, MINB)
 spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
                  const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
-                 int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+                 int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
+                 int64_t far_rows)
 {
     using VT = VecTraits<VecT>;
     constexpr int WPB = kSBlock / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t pol_s = SPOL >= 2 ? l2_policy_evict_first() : 0, pol_x = XPOL >= 1 ? l2_policy_evict_last() : 0;
+    const uint64_t pol_s = (SPOL >= 2 || XPOL == 2) ? l2_policy_evict_first() : 0, pol_x = XPOL >= 1 ? l2_policy_evict_last() : 0;
     double dot_scale = 1.0;
     if (scal_mode != 0) {                                  // Lanczos step a: 1 = first column block, 2 = a later one
         const double sx = sc[0], sz = sc[1], bprev = sc[2];
@@ -127,7 +130,7 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
 #pragma unroll
                 for (int u = 0; u < U; u++) v[u] = ld_f64<SPOL>(val + o[u], pol_s);
 #pragma unroll
-                for (int u = 0; u < U; u++) xv[u] = ld_x<XPOL>(x + c[u], pol_x);
+                for (int u = 0; u < U; u++) xv[u] = ld_x<XPOL>(x + c[u], (XPOL == 2 && llabs((long long)c[u] - (long long)(row_lo + row)) > far_rows) ? pol_s : pol_x);
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     VecT t = (u & 1) ? acc1 : acc0;
@@ -142,7 +145,10 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    if (a[u]) { if (u & 1) mac(acc1, v[u], ld_x<XPOL>(x + c[u], pol_x)); else mac(acc0, v[u], ld_x<XPOL>(x + c[u], pol_x)); }
+                    if (a[u]) {
+                        const uint64_t px = (XPOL == 2 && llabs((long long)c[u] - (long long)(row_lo + row)) > far_rows) ? pol_s : pol_x;
+                        if (u & 1) mac(acc1, v[u], ld_x<XPOL>(x + c[u], px)); else mac(acc0, v[u], ld_x<XPOL>(x + c[u], px));
+                    }
                 }
             }
         }
@@ -169,7 +175,9 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
 // tuning hook (qbgpu_debug_set_variant): variant id = 1 + MINB_index*16 + UL*8 + U_index*4 + SPOL_index*2 + XPOL
 // (MINB_index 0 -> 2 blocks/SM, 1 -> 4; U_index 0 -> 4, 1 -> 8; SPOL_index 0 -> .cs, 1 -> L2 evict_first hint)
 static int g_sjds_variant = 0;
+static int64_t g_far_rows = 1 << 21;                      // rows; ~32 MB of complex vector either side
 void set_sjds_variant(int v) { g_sjds_variant = v; }
+void set_sjds_far_rows(int64_t r) { g_far_rows = r; }
 
 template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB>
 static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
@@ -191,15 +199,17 @@ static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
     const int grid = (int)(want < cap ? want : cap);
     kern<<<grid, kSBlock, 0, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                          (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
-                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
+                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, g_far_rows);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
 }
 
 // production configuration of the template (chosen from the measurements in profiles/)
-constexpr int kProdU = 8, kProdS = 0, kProdX = 0, kProdMinB = 2;
-constexpr bool kProdUL = true;
+// complex vectors: 4 diagonals per trip, branchy tail, 4 blocks/SM; fp64 vectors: 8 per trip, unconditional loads
+// (scripts/kbench.py sweeps, profiles/r01_kbench_*.txt)
+template <typename VecT> struct Prod { static constexpr int U = 4, S = 2, X = 1, MinB = 4; static constexpr bool UL = false; };
+template <> struct Prod<double> { static constexpr int U = 8, S = 2, X = 0, MinB = 4; static constexpr bool UL = true; };
 
 template <typename ValT, typename VecT>
 static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
@@ -216,13 +226,27 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
 #undef QB_V1
 #undef QB_V2
 #undef QB_V3
+            // second sweep: per-entry gather policy (X=2) and more launch-bound / unroll points, stream policy L2ef
+            case 32: return launch_sjds_variant<ValT, VecT, false, 4, 2, 2, false, 4>(A, a);
+            case 33: return launch_sjds_variant<ValT, VecT, false, 8, 2, 2, true, 4>(A, a);
+            case 34: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 3>(A, a);
+            case 35: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 5>(A, a);
+            case 36: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 6>(A, a);
+            case 37: return launch_sjds_variant<ValT, VecT, false, 2, 2, 1, false, 6>(A, a);
+            case 38: return launch_sjds_variant<ValT, VecT, false, 6, 2, 1, false, 4>(A, a);
+            case 39: return launch_sjds_variant<ValT, VecT, false, 4, 2, 2, false, 5>(A, a);
+            case 40: return launch_sjds_variant<ValT, VecT, false, 8, 2, 0, true, 3>(A, a);
+            case 41: return launch_sjds_variant<ValT, VecT, false, 8, 2, 0, true, 5>(A, a);
+            case 42: return launch_sjds_variant<ValT, VecT, false, 12, 2, 0, true, 3>(A, a);
+            case 43: return launch_sjds_variant<ValT, VecT, false, 6, 2, 2, false, 4>(A, a);
             default: break;
             }
         }
     }
 #endif
-    return dots ? launch_sjds_variant<ValT, VecT, true, kProdU, kProdS, kProdX, kProdUL, kProdMinB>(A, a)
-                : launch_sjds_variant<ValT, VecT, false, kProdU, kProdS, kProdX, kProdUL, kProdMinB>(A, a);
+    using P = Prod<VecT>;
+    return dots ? launch_sjds_variant<ValT, VecT, true, P::U, P::S, P::X, P::UL, P::MinB>(A, a)
+                : launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB>(A, a);
 }
 
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)

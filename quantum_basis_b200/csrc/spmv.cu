@@ -13,6 +13,7 @@
 // Grid = resident blocks per SM x number of SMs (persistent, grid-stride over row groups).
 #include "internal.hpp"
 #include <cstdlib>
+#include <cstring>
 
 namespace qb {
 
@@ -145,6 +146,12 @@ int autotune(qbgpu_matrix *A, int flags)
     int lanes = 2;
     while (lanes < 32 && mean > 4.0 * lanes) lanes *= 2;
     A->lanes = lanes;
+    // profiling aid: QBGPU_FORCE_FORMAT=sell|csr pins the layout (under ncu every launch is replayed cold and
+    // serialised, which would mislead the timing pass below)
+    if (const char *ff = getenv("QBGPU_FORCE_FORMAT")) {
+        if (!strcmp(ff, "sell")) flags |= QBGPU_FORMAT_SELL;
+        else if (!strcmp(ff, "csr")) flags |= QBGPU_FORMAT_CSR | QBGPU_NO_AUTOTUNE;
+    }
     if (flags & QBGPU_FORMAT_SELL) return sjds_convert(A, true);
     if ((flags & QBGPU_NO_AUTOTUNE) || nrows < 4096) return QBGPU_OK;
     const bool verbose = getenv("QBGPU_VERBOSE") != nullptr;

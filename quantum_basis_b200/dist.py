@@ -133,50 +133,62 @@ class TorchComm:
 
 
 class DeviceKernels:
-    """C-ABI calls on torch device tensors (complex128 vectors as float64 pairs)."""
+    """C-ABI calls on torch device tensors.  real=False: complex128 vectors stored as float64 pairs (z entry points);
+    real=True: float64 vectors through qbgpu_real_view handles (d entry points) -- for Krylov loops that stay real."""
 
-    def __init__(self, qb, matrix):
+    def __init__(self, qb, matrix, real=False, parts=None):
         import torch
-        self.torch, self.qb, self.L, self.M = torch, qb, qb.lib(), matrix
+        self.torch, self.qb, self.L = torch, qb, qb.lib()
+        self.real, self.ncomp = real, (1 if real else 2)
+        self.owner = matrix
+        self.M = matrix.real_view() if real else matrix
+        self.parts = None
+        if parts is not None:
+            self.parts = [p.real_view() for p in parts] if real else parts
 
     def alloc(self, nentries):
-        return self.torch.zeros(2 * nentries, dtype=self.torch.float64, device="cuda")
+        return self.torch.zeros(self.ncomp * nentries, dtype=self.torch.float64, device="cuda")
 
     def slot(self, state, i):
         return state[i:i + 1]
 
     def segment(self, t, first_entry, nentries):
-        return t[2 * first_entry: 2 * (first_entry + nentries)]
+        return t[self.ncomp * first_entry: self.ncomp * (first_entry + nentries)]
 
     def _p(self, t):
         return C.c_void_p(t.data_ptr())
 
-    def split(self, col_bounds, flags=0):
-        """one handle per column owner (qbgpu_split_columns)"""
+    @staticmethod
+    def split(qb, matrix, col_bounds, flags=0):
+        """one handle per column owner (qbgpu_split_columns) of a complex-API shard"""
+        L = qb.lib()
         nparts = len(col_bounds) - 1
         b = np.array(col_bounds, dtype=np.int64)
         hs = (C.c_void_p * nparts)()
-        rc = self.L.qbgpu_split_columns(self.M.handle, nparts, b.ctypes.data, hs, flags)
+        rc = L.qbgpu_split_columns(matrix.handle, nparts, b.ctypes.data, hs, flags)
+        assert rc == 0, L.qbgpu_last_error()
+        return [qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
+
+    def _mv(self, handle, x, beta, y):
+        if self.real:
+            rc = self.L.qbgpu_dmv(handle, 1.0, self._p(x), float(beta), self._p(y), 1)
+        else:
+            one = (C.c_double * 2)(1.0, 0.0); b = (C.c_double * 2)(float(beta), 0.0)
+            rc = self.L.qbgpu_zmv(handle, one, self._p(x), b, self._p(y), 1)
         assert rc == 0, self.L.qbgpu_last_error()
-        self.parts = [self.qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
-        return self.parts
+
+    def multmv(self, x_full, y_local):
+        self._mv(self.M.handle, x_full, 0.0, y_local)
 
     def multmv_part(self, p, x_full, y_local, accumulate):
-        one = (C.c_double * 2)(1.0, 0.0); beta = (C.c_double * 2)(1.0 if accumulate else 0.0, 0.0)
-        rc = self.L.qbgpu_zmv(self.parts[p].handle, one, self._p(x_full), beta, self._p(y_local), 1)
-        assert rc == 0, self.L.qbgpu_last_error()
+        self._mv(self.parts[p].handle, x_full, 1.0 if accumulate else 0.0, y_local)
+
+    def lanczos_step_a(self, x_full, uz, state):
+        assert self.L.qbgpu_lanczos_step_a(self.M.handle, self._p(x_full), self._p(uz), self._p(state)) == 0, self.L.qbgpu_last_error()
 
     def lanczos_step_a_part(self, p, x_full, uz, state, first, last):
         rc = self.L.qbgpu_lanczos_step_a_part(self.parts[p].handle, self._p(x_full), self._p(uz), self._p(state), int(first), int(last))
         assert rc == 0, self.L.qbgpu_last_error()
-
-    def multmv(self, x_full, y_local):
-        one = (C.c_double * 2)(1.0, 0.0); zero = (C.c_double * 2)(0.0, 0.0)
-        rc = self.L.qbgpu_zmv(self.M.handle, one, self._p(x_full), zero, self._p(y_local), 1)
-        assert rc == 0, self.L.qbgpu_last_error()
-
-    def lanczos_step_a(self, x_full, uz, state):
-        assert self.L.qbgpu_lanczos_step_a(self.M.handle, self._p(x_full), self._p(uz), self._p(state)) == 0, self.L.qbgpu_last_error()
 
     def lanczos_step_b(self, ux, uz, state):
         assert self.L.qbgpu_lanczos_step_b(self.M.handle, self._p(ux), self._p(uz), self._p(state)) == 0, self.L.qbgpu_last_error()
@@ -185,9 +197,27 @@ class DeviceKernels:
         assert self.L.qbgpu_lanczos_step_c(self._p(state), self._p(a_dev), self._p(b_dev), m) == 0, self.L.qbgpu_last_error()
 
 
+def _timed(torch, dist, stream, fn, steps, warmup):
+    """warmup + `steps` timed calls bracketed by barrier + synchronize; device time, max over ranks (ms per step)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_peak, ClockSampler, workload_upper_nnz):
-    """bench.py's N > 1 arm: H row-sharded over the ranks (strong scaling: the total work is fixed), one product =
-    all-gather of x + the local rows' product; timed on the device, max over ranks."""
+    """bench.py's N > 1 arm: H row-sharded over the ranks (strong scaling: the total work is fixed).  One product =
+    exchange of x + the local rows' product, timed on the device, max over ranks.  Two exchange schemes are timed and the
+    faster is the headline: (A) one all_gather then the whole shard, (B) one broadcast per owner overlapped with the
+    per-owner column blocks."""
     import torch
     import torch.distributed as dist
     import quantum_basis_b200 as qb
@@ -208,66 +238,100 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
     torch.cuda.synchronize()
     t_build = time.time() - t0
     inf = M.info
-    kern = DeviceKernels(qb, M)
     comm = TorchComm()
-    op = ShardedOperator(kern, n, rank, world, comm)
+    col_bounds = [min(n, q * chunk) for q in range(world)] + [n]
+    t0 = time.time()
+    parts = DeviceKernels.split(qb, M, col_bounds)
+    torch.cuda.synchronize()
+    t_split = time.time() - t0
+    kern = DeviceKernels(qb, M, real=False, parts=parts)
+    opA = ShardedOperator(kern, n, rank, world, comm)
+    opB = PipelinedOperator(kern, n, rank, world, comm)
     x_loc = kern.alloc(chunk)
     y_loc = kern.alloc(chunk)
-    # this rank's slice of vec_randomize(seed=1) (generated on the device, sliced on the host)
-    full = qb.vec_randomize(n, 1)
+    y_ref = kern.alloc(chunk)
+    full = qb.vec_randomize(n, 1)                  # generated on the device, sliced on the host
     x_loc[:2 * (hi - lo)] = torch.from_numpy(np.ascontiguousarray(full[lo:hi]).view(np.float64)).cuda()
-    del full
 
-    for _ in range(args.warmup):
-        op.matvec(x_loc, y_loc)
-    torch.cuda.synchronize()
-    dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     L.qbgpu_kernel_launches(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record(stream)
-    kernel_ms = 0.0
-    for _ in range(args.steps):
-        op.gather(x_loc)
-        k0.record(stream)
-        kern.multmv(op.x_full, y_loc)
-        k1.record(stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches = int(L.qbgpu_kernel_launches(0))
+    msA = _timed(torch, dist, stream, lambda: opA.matvec(x_loc, y_ref), args.steps, args.warmup)
+    launchesA = int(L.qbgpu_kernel_launches(1))
+    msB = _timed(torch, dist, stream, lambda: opB.matvec(x_loc, y_loc), args.steps, args.warmup)
+    launchesB = int(L.qbgpu_kernel_launches(1))
     clocks = sampler.stop()
-    total_ms = e0.elapsed_time(e1)
-    kernel_ms = k0.elapsed_time(k1)                            # last step's local product
-    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms = t.tolist()
+    agree = float((y_loc - y_ref).abs().max().item()) / max(1e-300, float(y_ref.abs().max().item()))
+    # the local product alone (no exchange): the per-GPU roofline number
+    opA.gather(x_loc)
+    ms_kernel = _timed(torch, dist, stream, lambda: kern.multmv(opA.x_full, y_ref), max(3, args.steps // 2), 2)
+
+    # e2e: host vectors -- every rank uploads its slice of x from pinned memory and downloads its slice of y
+    xh = torch.empty(2 * chunk, dtype=torch.float64).pin_memory(); xh.copy_(x_loc.cpu())
+    yh = torch.empty(2 * chunk, dtype=torch.float64).pin_memory()
+    best = opB if msB < msA else opA
+
+    def e2e_step():
+        x_loc.copy_(xh, non_blocking=True)
+        best.matvec(x_loc, y_loc)
+        yh.copy_(y_loc, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    te = time.time()
+    ne = max(3, min(args.steps, 10))
+    for _ in range(ne):
+        e2e_step()
+        torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([(time.time() - te) / ne], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
     nnz_all = torch.tensor([inf.nnz_stored], dtype=torch.int64, device="cuda")
     dist.all_reduce(nnz_all)
     Z = int(nnz_all.item())
     s_val = 8 if inf.val_is_real else 16
     s_vec = 16
-    ms_per_step = total_ms / args.steps
+    ms_per_step = min(msA, msB)
     B_local = algorithmic_bytes(inf.nnz_stored, hi - lo, n, s_val, s_vec)
     peak, peak_src = measured_peak()
 
-    # sharded Lanczos: iterations/s (no stop rule here: fixed 50 steps, the rate is what is measured)
+    # sharded Lanczos (real mode when the stored values are real: the start vector vec_randomize is real), fixed step
+    # count: the rate is what is measured here; the stop rule lives in the single-GPU driver
     lan = None
     if not args.no_lanczos:
-        state = torch.zeros(8, dtype=torch.float64, device="cuda"); state[0] = 1.0
-        a_dev = torch.zeros(256, dtype=torch.float64, device="cuda"); b_dev = torch.zeros(256, dtype=torch.float64, device="cuda")
-        u1 = kern.alloc(chunk)
-        steps = 50
-        torch.cuda.synchronize(); dist.barrier()
-        tl = time.time()
-        sharded_lanczos(op, x_loc.clone(), u1, 256, steps, state, a_dev, b_dev)
-        torch.cuda.synchronize(); dist.barrier()
-        tl = time.time() - tl
-        lan = {"steps": steps, "seconds": tl, "iters_per_s": steps / tl, "a0": float(a_dev[0].item()), "b1": float(b_dev[1].item())}
+        real = bool(inf.val_is_real)
+        kr = DeviceKernels(qb, M, real=real, parts=parts)
+        oA = ShardedOperator(kr, n, rank, world, comm)
+        oB = PipelinedOperator(kr, n, rank, world, comm)
+        u0 = kr.alloc(chunk)
+        if real:
+            u0[: hi - lo] = torch.from_numpy(np.ascontiguousarray(full[lo:hi].real)).cuda()
+        else:
+            u0.copy_(x_loc)
+        steps = 40
+        out = {}
+        for tag, fn, op in (("allgather", sharded_lanczos, oA), ("pipelined", pipelined_lanczos, oB)):
+            state = torch.zeros(8, dtype=torch.float64, device="cuda"); state[0] = 1.0
+            a_dev = torch.zeros(256, dtype=torch.float64, device="cuda"); b_dev = torch.zeros(256, dtype=torch.float64, device="cuda")
+            ua, ub = u0.clone(), kr.alloc(chunk)
+            fn(op, ua, ub, 256, 3, state, a_dev, b_dev)          # warm-up steps continue into the timed ones
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            state[:] = 0.0; state[0] = 1.0
+            ua.copy_(u0)
+            e0.record(stream)
+            fn(op, ua, ub, 256, steps, state, a_dev, b_dev)
+            e1.record(stream)
+            torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[tag] = {"steps": steps, "seconds": float(t.item()), "iters_per_s": steps / float(t.item()),
+                        "a0": float(a_dev[0].item()), "b1": float(b_dev[1].item()), "a_last": float(a_dev[steps - 1].item())}
+        lan = {"vectors": "fp64 (real mode)" if real else "complex128", **out,
+               "iters_per_s": max(out["allgather"]["iters_per_s"], out["pipelined"]["iters_per_s"])}
+    del full
 
     if rank == 0:
         line = {"metric": "H*v/sec", "value": 1e3 / ms_per_step, "unit": "H*v/s", "n_gpus": world, "steps": args.steps,
@@ -275,12 +339,17 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "S_val": s_val, "S_vec": s_vec,
                            "partition": "contiguous equal-row blocks, full expanded rows per rank",
-                           "exchange": "NCCL all_gather_into_tensor of x per product", "l2": "inputs larger than L2"},
-                "roofline": {"bound": "hbm", "achieved": B_local / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": B_local / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "note": "per GPU: local rows' product only (max over ranks), exchange excluded"},
-                "e2e": None, "gpu_launches": launches, "clocks": clocks,
-                "host_phases": {"generate_matrix_s": t_build}}
+                           "exchange": {"allgather_ms": msA, "pipelined_broadcast_ms": msB, "used": "pipelined" if msB < msA else "allgather",
+                                        "schemes_agree_rel": agree},
+                           "l2": "inputs larger than L2"},
+                "roofline": {"bound": "hbm", "achieved": B_local / (ms_kernel * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": B_local / (ms_kernel * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "local_product_ms": ms_kernel,
+                             "note": "per GPU: the local rows' product alone (max over ranks); the exchange is in `value`, not here"},
+                "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": (hi - lo) * s_vec, "d2h_bytes_per_step": (hi - lo) * s_vec,
+                        "ms_per_step": 1e3 * e2e_s, "note": "per rank: its slice of x up, its slice of y down, pinned host memory"},
+                "gpu_launches": launchesA + launchesB, "clocks": clocks,
+                "host_phases": {"generate_matrix_s": t_build, "split_columns_s": t_split}}
         if lan:
             line["lanczos"] = lan
         print(json.dumps(line))

@@ -16,9 +16,17 @@ import bench  # noqa: E402
 import quantum_basis_b200 as qb  # noqa: E402
 
 
+EXTRA = {33: "minb=4 UL=0 U=4 S=L2ef X=adaptive", 34: "minb=4 UL=1 U=8 S=L2ef X=adaptive", 35: "minb=3 UL=0 U=4 S=L2ef X=L2el",
+         36: "minb=5 UL=0 U=4 S=L2ef X=L2el", 37: "minb=6 UL=0 U=4 S=L2ef X=L2el", 38: "minb=6 UL=0 U=2 S=L2ef X=L2el",
+         39: "minb=4 UL=0 U=6 S=L2ef X=L2el", 40: "minb=5 UL=0 U=4 S=L2ef X=adaptive", 41: "minb=3 UL=1 U=8 S=L2ef X=nc",
+         42: "minb=5 UL=1 U=8 S=L2ef X=nc", 43: "minb=3 UL=1 U=12 S=L2ef X=nc", 44: "minb=4 UL=0 U=6 S=L2ef X=adaptive"}
+
+
 def describe(v):
     if v == 0:
         return "production"
+    if v in EXTRA:
+        return EXTRA[v]
     w = v - 1
     return f"minb={2 if w // 16 == 0 else 4} UL={(w // 8) % 2} U={4 if (w // 4) % 2 == 0 else 8} S={'cs' if (w // 2) % 2 == 0 else 'L2ef'} X={'nc' if w % 2 == 0 else 'L2el'}"
 
@@ -30,6 +38,7 @@ def main():
     ap.add_argument("--ids", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
+    ap.add_argument("--far", default="", help="comma list of log2(far_rows) to sweep for the adaptive-policy variants")
     a = ap.parse_args()
     L = qb.lib()
     assert L.qbgpu_init(0) == 0
@@ -61,7 +70,15 @@ def main():
     ids = [int(t) for t in a.ids.split(",")] if a.ids else list(range(0, 33))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = []
+    fars = [int(t) for t in a.far.split(",")] if a.far else [21]
+    runs = []
     for v in ids:
+        if "adaptive" in describe(v):
+            runs += [(v, f) for f in fars]
+        else:
+            runs.append((v, 21))
+    for v, f in runs:
+        L.qbgpu_debug_set_far_rows(1 << f)
         L.qbgpu_debug_set_variant(v)
         for _ in range(2):
             M.MultMv(x, y)
@@ -72,7 +89,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
         res.append((ms, v))
-        print(f"variant {v:2d} [{describe(v):44s}] {ms:8.3f} ms  {B/ms/1e6:7.0f} GB/s  {B/ms/1e6/6451.8:5.3f} of measured peak", flush=True)
+        print(f"variant {v:2d} far=2^{f:<2d} [{describe(v):40s}] {ms:8.3f} ms  {B/ms/1e6:7.0f} GB/s  {B/ms/1e6/6451.8:5.3f} of measured peak", flush=True)
     L.qbgpu_debug_set_variant(0)
     res.sort()
     print("# best:", ", ".join(f"{v}:{ms:.3f}" for ms, v in res[:5]))

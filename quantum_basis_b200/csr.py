@@ -282,6 +282,56 @@ def kpm_moments(mat, phi, lo, hi, nmom):
     return mu
 
 
+def iram(dim, mat, v0, nev, ncv, maxit, order="sr"):
+    """iram<T,MAT>(dim, mat, v0, nev, ncv, maxit, order, nconv, eigenvals, eigenvecs) (src/lanczos.cc:497-603): ARPACK's
+    implicitly restarted Arnoldi with every product served by mat.MultMv on ARPACK's own HOST work vectors -- the
+    reverse-communication callback of src/lanczos.cc:426,476.  ARPACK itself stays on the host, as in the reference
+    (arpack-ng there; here scipy's bundled ARPACK, driven through scipy.sparse.linalg.eigsh).  dim <= 30 falls back to
+    dense diagonalisation of mat.to_dense() like src/lanczos.cc:508-542.  Returns (nconv, eigenvals, eigenvecs[:, j])."""
+    if nev <= 0 or nev >= dim - 1:
+        raise ValueError("0 < nev < N-1 should be satisfied.")                  # src/lanczos.cc:502
+    if maxit < 20:
+        raise ValueError("maxit should not be smaller than 20!")               # :504
+    order = order.upper()
+    which = {"SR": "SA", "SA": "SA", "LR": "LA", "LA": "LA", "SM": "SM", "LM": "LM"}.get(order)
+    if which is None:
+        raise ValueError("Invalid argument orderC.")
+    if dim <= 30:
+        w, U = np.linalg.eigh(mat.to_dense())
+        idx = {"SA": np.argsort(w), "LA": np.argsort(-w), "SM": np.argsort(np.abs(w)), "LM": np.argsort(-np.abs(w))}[which][:nev]
+        return nev, w[idx], U[:, idx]
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    nprod = [0]
+
+    def matvec(x):
+        x = np.ascontiguousarray(x, dtype=mat.dtype).ravel()
+        y = np.empty(dim, dtype=mat.dtype)
+        mat.MultMv(x, y)                                                         # host pointers in, host pointers out
+        nprod[0] += 1
+        return y
+
+    A = LinearOperator((dim, dim), matvec=matvec, dtype=mat.dtype)
+    w, U = eigsh(A, k=nev, which=which, ncv=ncv, maxiter=maxit, tol=0.0)         # tol <= 0: machine precision (:405,452)
+    key = {"SA": w, "LA": -w, "SM": np.abs(w), "LM": -np.abs(w)}[which]
+    idx = np.argsort(key, kind="stable")                                         # the reference's post-sort, :583-595
+    iram.last_products = nprod[0]
+    return len(w), w[idx], U[:, idx]
+
+
+def locate_E0_iram(mat, nev=2, ncv=6, maxit=0):
+    """The csr_mat branch of model<T>::locate_E0_iram (src/model.cc:1320-1366): returns dict(eigenvals, eigenvecs, nconv, gap)."""
+    if not (nev > 0 and ncv > nev + 1):
+        raise QbgpuError("need nev > 0 and ncv > nev + 1")                        # the reference's asserts, :1337-1338
+    if maxit <= 0:
+        maxit = nev * 100                                                        # :1339
+    v0 = np.ones(mat.dim, dtype=mat.dtype)                                       # :1352 (ARPACK ignores it with info = 0)
+    nconv, w, U = iram(mat.dim, mat, v0, nev, ncv, maxit, "sr")
+    out = {"eigenvals": list(w), "eigenvecs": [U[:, j].copy() for j in range(U.shape[1])], "nconv": nconv}
+    if nconv > 1:
+        out["gap"] = w[1] - w[0]
+    return out
+
+
 def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000):
     """The csr_mat branch of model<T>::locate_E0_lanczos (src/model.cc:1124-1316): E0 by simple Lanczos, ground-state
     vector by CG, optionally E1 (re-orthogonalised Lanczos) and its vector.  Everything stays on the device; returns a

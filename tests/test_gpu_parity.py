@@ -325,6 +325,37 @@ def test_locate_E0_lanczos_gap_and_excited_vector(oracle):
         assert np.linalg.norm(F @ vec - E * vec) < 1e-7
 
 
+# ------------------------------------------------------------------------------------------- ARPACK seam
+def test_arpack_callback_seam_tJ_golden(oracle):
+    """src/main_test.cc:113-211: t-J chain L=12, locate_E0_iram(full, 4, 8) -> E0 = E1 = -9.762087307.  ARPACK (scipy's
+    bundled copy, complex znaupd like the reference's call_arpack) runs on the host and calls MultMv on its own host work
+    vectors: the reverse-communication seam of src/lanczos.cc:476."""
+    A, meta, ex = oracle.load_golden("tj12")
+    out = qb.locate_E0_iram(make(A), nev=4, ncv=8)
+    assert out["nconv"] == 4
+    assert abs(out["eigenvals"][0] + 9.762087307) < 1e-8
+    assert abs(out["eigenvals"][1] + 9.762087307) < 1e-8
+    for E, v in zip(out["eigenvals"], out["eigenvecs"]):
+        assert np.linalg.norm(oracle.spmv(A, v) - E * v) < 1e-7
+    assert qb.iram.last_products > 8
+
+
+def test_iram_small_matrix_uses_dense_fallback(oracle):
+    """dim <= 30: mat.to_dense() + dense eigensolver (src/lanczos.cc:508-542)."""
+    import scipy.sparse as sp
+    from oracle_lib import Csr
+    rng = np.random.default_rng(2)
+    n = 24
+    Mx = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    Hd = np.triu(Mx + Mx.conj().T)
+    S = sp.csr_matrix(Hd)
+    S.sort_indices()
+    A = Csr(n, S.indptr, S.indices, S.data.astype(np.complex128), True)
+    nconv, w, U = qb.iram(n, make(A), np.ones(n, dtype=np.complex128), 3, 8, 100, "sr")
+    full = Hd + np.triu(Hd, 1).conj().T
+    assert np.abs(w - np.linalg.eigvalsh(full)[:3]).max() < 1e-12
+
+
 # ------------------------------------------------------------------------------------- energy_scale / KPM
 @pytest.mark.parametrize("name", ["heis12_full", "tri4x4_k01", "hubbard4x2"])
 def test_energy_scale_matches_reference(oracle, name):

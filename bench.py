@@ -35,6 +35,8 @@ WORKLOADS = {
     "heis_chain30": ("heisenberg", dict(L=30)),
 }
 L2_BYTES = 126e6
+# DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
+TRAFFIC_NCU = {"hubbard4x4": None}
 
 
 def square_bonds(Lx, Ly):
@@ -153,6 +155,7 @@ def workload_upper_nnz(workload):
 
 # ------------------------------------------------------------------------------------------------------ our arm
 def build_matrix(qb, workload, row_range=None, flags=0):
+    """BASELINE matrices generated directly in HBM (qbgpu_build_*), bit-identical to what the reference assembles."""
     fam, p = WORKLOADS[workload]
     import numpy as np
     L = qb.lib()
@@ -250,7 +253,44 @@ def main():
     peak, peak_src = measured_peak()
     achieved = B / (ms_per_step * 1e-3) / 1e9
 
+    def time_products(mat, xv, yv, steps):
+        for _ in range(3):
+            mat.MultMv(xv, yv)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(steps):
+            mat.MultMv(xv, yv)
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def roof(bytes_, ms):
+        g = bytes_ / (ms * 1e-3) / 1e9
+        return {"ms_per_product": ms, "products_per_s": 1e3 / ms, "algorithmic_bytes": bytes_, "achieved_GBs": g, "frac_of_measured_peak": g / peak}
+
+    # ---------------------------------------------------------------- the same matrix with fp64 vectors (what the fused
+    # Krylov loops run when H and the start vector are real) and with 1-byte dictionary-coded values (opt-in layout)
+    extras = {}
+    Md = None
+    if inf.val_is_real and not need_flush:
+        Mr = M.real_view()
+        xr = qb.vec_randomize(n, 1, dtype=np.float64, device=True)
+        yr = qb.DeviceVector(n, np.float64)
+        extras["real_vectors"] = dict(S_val=s_val, S_vec=8, **roof(algorithmic_bytes(Z, n, n, s_val, 8), time_products(Mr, xr, yr, args.steps)))
+        try:
+            Md = build_matrix(qb, args.workload, flags=16)
+            if Md.info.value_dict:
+                nd = Md.info.value_dict
+                extras["value_dict_complex_vectors"] = dict(S_val=1, S_vec=16, dict_entries=nd, **roof(algorithmic_bytes(Z, n, n, 1, 16), time_products(Md, x, y, args.steps)))
+                extras["value_dict_real_vectors"] = dict(S_val=1, S_vec=8, dict_entries=nd, **roof(algorithmic_bytes(Z, n, n, 1, 8), time_products(Md.real_view(), xr, yr, args.steps)))
+        except Exception as e:
+            Md = None
+            extras["value_dict_error"] = str(e)
+        xr.free(); yr.free()
+
     # ---------------------------------------------------------------- e2e: host vectors through the reference-facing call
+    M.MultMv(x, y)
     xh_t = torch.empty(2 * n, dtype=torch.float64).pin_memory()
     yh_t = torch.empty(2 * n, dtype=torch.float64).pin_memory()
     xh = xh_t.numpy().view(np.complex128)
@@ -272,31 +312,42 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "reference_upper_entries": workload_upper_nnz(args.workload),
-                       "S_val": s_val, "S_vec": s_vec, "lanes": inf.lanes, "l2": "flush between steps" if need_flush else "inputs larger than L2",
-                       "matrix_bytes": inf.device_bytes},
+                       "S_val": s_val, "S_vec": s_vec, "layout": "sliced-jagged" if inf.format == 8 else f"csr-vector lanes={inf.lanes}",
+                       "l2": "flush between steps" if need_flush else "inputs larger than L2", "matrix_bytes": inf.device_bytes,
+                       "vectors": "complex128 x and y (the reference's model<complex<double>> calling convention)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0},
+                         "traffic": TRAFFIC_NCU.get(args.workload), "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
+                         "kernel": "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel"},
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
                     "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
             "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds}}
+    line.update(extras)
 
     # ---------------------------------------------------------------- Lanczos iterations/s and E0 time-to-solution
     if not args.no_lanczos:
-        v = qb.DeviceVector(2 * n)
-        rnd = L.qbgpu_vec_randomize_z
-        assert rnd(n, C.c_void_p(v.ptr), 1) == 0
-        hess = np.zeros(2000)
-        torch.cuda.synchronize()
-        tl = time.time()
-        m = qb.lanczos(0, 999, 1000, n, M, v, hess, "sr_val0")
-        torch.cuda.synchronize()
-        tl = time.time() - tl
-        ritz, _ = qb.hess_eigen(hess, 1000, m)
-        line["lanczos"] = {"steps": m, "seconds": tl, "iters_per_s": m / tl, "E0": float(ritz[0]),
-                           "algorithmic_bytes_per_iter": Z * (s_val + 4) + 8 * (n + 1) + 6 * n * s_vec,
-                           "achieved_GBs": (Z * (s_val + 4) + 8 * (n + 1) + 6 * n * s_vec) * m / tl / 1e9}
-        v.free()
+        def lanczos_leg(mat, sv):
+            v = qb.DeviceVector(2 * n)
+            assert L.qbgpu_vec_randomize_z(n, C.c_void_p(v.ptr), 1) == 0
+            hess = np.zeros(2000)
+            torch.cuda.synchronize()
+            tl = time.time()
+            m = qb.lanczos(0, 999, 1000, n, mat, v, hess, "sr_val0")      # the reference's call, stop rule included
+            torch.cuda.synchronize()
+            tl = time.time() - tl
+            ritz, _ = qb.hess_eigen(hess, 1000, m)
+            v.free()
+            # real-mode loop: fp64 vectors when H and the start vector are real
+            svec = 8 if inf.val_is_real else 16
+            b_iter = Z * (sv + 4) + 8 * (n + 1) + 6 * n * svec
+            return {"steps": m, "seconds": tl, "iters_per_s": m / tl, "E0": float(ritz[0]), "S_val": sv, "S_vec": svec,
+                    "algorithmic_bytes_per_iter": b_iter, "achieved_GBs": b_iter * m / tl / 1e9,
+                    "frac_of_measured_peak": b_iter * m / tl / 1e9 / peak}
+        line["lanczos"] = lanczos_leg(M, s_val)
+        if Md is not None and Md.info.value_dict:
+            line["lanczos_value_dict"] = lanczos_leg(Md, 1)
+    if Md is not None:
+        Md.destroy()
 
     # ---------------------------------------------------------------- CPU baseline beside it (bounded sample)
     if not args.no_cpu:

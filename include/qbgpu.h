@@ -39,7 +39,9 @@ extern "C" {
 #define QBGPU_KEEP_COMPLEX   1   /* do not demote an all-real complex matrix to fp64 values */
 #define QBGPU_NO_AUTOTUNE    2   /* skip the kernel-variant timing pass at create */
 #define QBGPU_FORMAT_CSR     4   /* force the expanded-CSR kernels  */
-#define QBGPU_FORMAT_SELL    8   /* force the SELL-C-sigma kernels  */
+#define QBGPU_FORMAT_SELL    8   /* force the sliced-jagged kernels (32-row slices, jagged diagonals, no padding) */
+#define QBGPU_VALUE_DICT    16   /* opt-in: store fp64 values as 1-byte codes into a table of the distinct values when there
+                                    are at most 256 of them (lossless; products are bit-identical); implies FORMAT_SELL */
 
 typedef struct qbgpu_matrix *qbgpu_matrix_t;     /* replaces `sparse_matrix_t handle` (src/qbasis.h:985) */
 
@@ -49,6 +51,7 @@ typedef struct {
     int64_t nnz_stored;     /* entries in the device layout (full expanded Hermitian rows)         */
     int64_t nnz_input;      /* entries of the host CSR it was created from (upper triangle if sym) */
     int     val_is_real;    /* 1: values stored as fp64 (input was real or all imaginary parts == 0) */
+    int     value_dict;     /* > 0: number of dictionary entries; values are stored as 1-byte codes (QBGPU_VALUE_DICT) */
     int     api_is_complex; /* 1: created through a z entry point                                  */
     int     format;         /* QBGPU_FORMAT_CSR or QBGPU_FORMAT_SELL                               */
     int     lanes;          /* threads per row chosen for the CSR-vector kernel                    */

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libqbgpu.so")
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
 QBGPU_HOST, QBGPU_DEVICE = 0, 1
-KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL = 1, 2, 4, 8
+KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL, VALUE_DICT = 1, 2, 4, 8, 16
 
 
 class QbgpuError(RuntimeError):
@@ -18,7 +18,7 @@ class QbgpuError(RuntimeError):
 
 class MatrixInfo(C.Structure):
     _fields_ = [("n", C.c_int64), ("row_lo", C.c_int64), ("row_hi", C.c_int64), ("nnz_stored", C.c_int64),
-                ("nnz_input", C.c_int64), ("val_is_real", C.c_int), ("api_is_complex", C.c_int), ("format", C.c_int),
+                ("nnz_input", C.c_int64), ("val_is_real", C.c_int), ("value_dict", C.c_int), ("api_is_complex", C.c_int), ("format", C.c_int),
                 ("lanes", C.c_int), ("device_bytes", C.c_int64), ("upload_seconds", C.c_double),
                 ("convert_seconds", C.c_double), ("autotune_seconds", C.c_double)]
 

@@ -26,9 +26,13 @@ struct qbgpu_matrix {
     // every row that has one, in rank order.  Slice s still occupies [rowptr[32 s], rowptr[32 s + 32]) -- no padding.
     // rowinfo[32 s + rank] = (row-in-slice << 24) | length.
     uint32_t *rowinfo = nullptr;
+    // optional value dictionary (QBGPU_VALUE_DICT, fp64 values with <= 256 distinct bit patterns): val is then an array
+    // of 1-byte codes into vdict[ndict]; products decode through shared memory and are bit-identical.
+    double  *vdict = nullptr;
+    int      ndict = 0;
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
-    size_t  val_bytes() const { return val_real ? 8 : 16; }
+    size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
     size_t  vec_bytes() const { return api_complex ? 16 : 8; }
 };
 
@@ -51,6 +55,7 @@ struct FusedArgs {
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &args, int lanes_override = 0);
 int autotune(qbgpu_matrix *A, int flags = 0);
 int sjds_convert(qbgpu_matrix *A, bool forward);
+int value_dict_encode(qbgpu_matrix *A);               // matrix.cu: try to replace fp64 values by 1-byte codes
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);
 void set_sjds_variant(int v);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val

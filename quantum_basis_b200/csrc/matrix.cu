@@ -15,7 +15,10 @@
 //              layout -- and therefore every floating-point sum -- is deterministic
 #include "internal.hpp"
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace qb {
@@ -227,6 +230,95 @@ static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, c
 }
 
 
+// ------------------------------------------------------------------------------------------ value dictionary
+// Exact-diagonalisation Hamiltonians carry very few distinct matrix elements (Heisenberg: J/2 and multiples of J/4;
+// Hubbard: +-t and multiples of U), so the 8-byte value stream can be replaced by 1-byte codes into a table of the
+// distinct fp64 bit patterns (QBGPU_VALUE_DICT).  Lossless: the product decodes the identical doubles.
+constexpr int kDictSlots = 1024;                           // open-addressing hash set, at most 256 live keys
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;   // a NaN payload no finite matrix element has
+
+__device__ __forceinline__ unsigned dict_hash(unsigned long long k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; return (unsigned)k & (kDictSlots - 1); }
+
+__global__ void __launch_bounds__(kCBlock) dict_collect_kernel(int64_t nnz, const double *__restrict__ val, unsigned long long *slots, int *count)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        if (*(volatile int *)count > 256) return;          // too many distinct values: give up early
+        const unsigned long long k = (unsigned long long)__double_as_longlong(val[i]);
+        unsigned h = dict_hash(k);
+        for (int probe = 0; probe < kDictSlots; probe++, h = (h + 1) & (kDictSlots - 1)) {
+            unsigned long long cur = slots[h];
+            if (cur == k) break;
+            if (cur == kEmptyKey) {
+                cur = atomicCAS(&slots[h], kEmptyKey, k);
+                if (cur == kEmptyKey) { atomicAdd(count, 1); break; }
+                if (cur == k) break;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCBlock) dict_encode_kernel(int64_t nnz, const double *__restrict__ val, const unsigned long long *__restrict__ slots,
+                                                              const int *__restrict__ slot_code, uint8_t *code)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(val[i]);
+        unsigned h = dict_hash(k);
+        while (slots[h] != k) h = (h + 1) & (kDictSlots - 1);
+        code[i] = (uint8_t)slot_code[h];
+    }
+}
+
+int value_dict_encode(qbgpu_matrix *A)
+{
+    Context &c = ctx();
+    if (!A->val_real || A->ndict || A->format != QBGPU_FORMAT_CSR || A->nnz == 0) return QBGPU_OK;
+    unsigned long long *d_slots = nullptr;
+    int *d_count = nullptr, *d_slot_code = nullptr;
+    uint8_t *d_code = nullptr;
+    double *d_dict = nullptr;
+    auto cleanup = [&]() { cudaFree(d_slots); cudaFree(d_count); cudaFree(d_slot_code); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); cudaFree(d_code); cudaFree(d_dict); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_slots, sizeof(unsigned long long) * kDictSlots));
+    QB_CU(cudaMalloc(&d_count, sizeof(int)));
+    QB_CU(cudaMemsetAsync(d_slots, 0xFF, sizeof(unsigned long long) * kDictSlots, c.stream));
+    QB_CU(cudaMemsetAsync(d_count, 0, sizeof(int), c.stream));
+    dict_collect_kernel<<<grid_for(A->nnz), kCBlock, 0, c.stream>>>(A->nnz, (const double *)A->val, d_slots, d_count);
+    QB_LAUNCH_COUNT();
+    std::vector<unsigned long long> slots(kDictSlots);
+    int count = 0;
+    QB_CU(cudaMemcpyAsync(slots.data(), d_slots, sizeof(unsigned long long) * kDictSlots, cudaMemcpyDeviceToHost, c.stream));
+    QB_CU(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+    if (count > 256) { cleanup(); return QBGPU_OK; }        // not compressible: keep the fp64 values
+    // order the dictionary by value so that the layout does not depend on thread timing
+    std::vector<std::pair<double, int>> keys;
+    for (int h = 0; h < kDictSlots; h++)
+        if (slots[h] != kEmptyKey) { double v; memcpy(&v, &slots[h], 8); keys.push_back({v, h}); }
+    std::sort(keys.begin(), keys.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+        if (a.first != b.first) return a.first < b.first;
+        return std::signbit(a.first) > std::signbit(b.first);       // -0.0 before +0.0: distinct bit patterns
+    });
+    std::vector<int> slot_code(kDictSlots, 0);
+    std::vector<double> dict(256, 0.0);
+    for (size_t j = 0; j < keys.size(); j++) { dict[j] = keys[j].first; slot_code[keys[j].second] = (int)j; }
+    QB_CU(cudaMalloc(&d_slot_code, sizeof(int) * kDictSlots));
+    QB_CU(cudaMalloc(&d_dict, sizeof(double) * 256));
+    QB_CU(cudaMalloc(&d_code, (size_t)A->nnz));
+    QB_CU(cudaMemcpyAsync(d_slot_code, slot_code.data(), sizeof(int) * kDictSlots, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_dict, dict.data(), sizeof(double) * 256, cudaMemcpyHostToDevice, c.stream));
+    dict_encode_kernel<<<grid_for(A->nnz), kCBlock, 0, c.stream>>>(A->nnz, (const double *)A->val, d_slots, d_slot_code, d_code);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+    cleanup();
+#undef QB_CU
+    cudaFree(A->val);
+    A->val = d_code;
+    A->vdict = d_dict;
+    A->ndict = (int)keys.size();
+    return QBGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------- split by column owner
 // Multi-GPU pipelining (quantum_basis_b200/dist.py): a row shard is split into one block per column owner so that
 // the block of rank p can be multiplied as soon as p's slice of x has arrived.  Columns are sorted inside a row, so
@@ -272,7 +364,9 @@ static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbg
     if (!A || !bounds || !out || nparts < 1 || nparts > kMaxParts) return fail(QBGPU_ERR_ARG, "split_columns: bad argument (1..16 parts)");
     if (bounds[0] != 0 || bounds[nparts] != A->n) return fail(QBGPU_ERR_ARG, "split_columns: bounds must run from 0 to n");
     for (int p = 0; p < nparts; p++) if (bounds[p + 1] < bounds[p]) return fail(QBGPU_ERR_ARG, "split_columns: bounds must be non-decreasing");
-    QB_TRY(sjds_convert(A, false));                         // needs plain CSR order
+    if (A->ndict) return fail(QBGPU_ERR_STATE, "split_columns: not available for dictionary-coded handles");
+    const bool was_jagged = (A->format == QBGPU_FORMAT_SELL);
+    QB_TRY(sjds_convert(A, false));                         // needs plain CSR order (restored below)
     const int64_t nloc = A->nrows();
     PartBounds pb;
     for (int p = 0; p <= nparts; p++) pb.b[p] = bounds[p];
@@ -309,6 +403,7 @@ static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbg
     }
     cleanup();
 #undef QB_CU
+    if (was_jagged) QB_TRY(sjds_convert(A, true));
     for (int p = 0; p < nparts; p++) { int rc = autotune(out[p], flags); if (rc) { abort_all(); return rc; } }
     return QBGPU_OK;
 }
@@ -338,7 +433,7 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
-    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); }
+    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); }
     delete A;
     return QBGPU_OK;
 }
@@ -348,7 +443,7 @@ int qbgpu_matrix_get_info(qbgpu_matrix_t A, qbgpu_matrix_info *info)
     if (!A || !info) return fail(QBGPU_ERR_ARG, "null argument");
     info->n = A->n; info->row_lo = A->row_lo; info->row_hi = A->row_hi;
     info->nnz_stored = A->nnz; info->nnz_input = A->nnz_input;
-    info->val_is_real = A->val_real; info->api_is_complex = A->api_complex;
+    info->val_is_real = A->val_real; info->value_dict = A->ndict; info->api_is_complex = A->api_complex;
     info->format = A->format; info->lanes = A->lanes;
     info->device_bytes = (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
     info->upload_seconds = A->upload_s; info->convert_seconds = A->convert_s; info->autotune_seconds = A->autotune_s;
@@ -364,7 +459,15 @@ int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, voi
     QB_CUDA(cudaStreamSynchronize(ctx().stream));
     QB_CUDA(cudaMemcpy(rowptr, A->rowptr, sizeof(int64_t) * (A->nrows() + 1), cudaMemcpyDeviceToHost));
     QB_CUDA(cudaMemcpy(col, A->col, sizeof(int32_t) * A->nnz, cudaMemcpyDeviceToHost));
-    QB_CUDA(cudaMemcpy(val, A->val, A->val_bytes() * A->nnz, cudaMemcpyDeviceToHost));
+    if (A->ndict) {                                         // decode the 1-byte codes back to the fp64 values
+        std::vector<uint8_t> codes(A->nnz);
+        double dict[256];
+        QB_CUDA(cudaMemcpy(codes.data(), A->val, (size_t)A->nnz, cudaMemcpyDeviceToHost));
+        QB_CUDA(cudaMemcpy(dict, A->vdict, sizeof dict, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < A->nnz; i++) ((double *)val)[i] = dict[codes[i]];
+    } else {
+        QB_CUDA(cudaMemcpy(val, A->val, A->val_bytes() * A->nnz, cudaMemcpyDeviceToHost));
+    }
     if (jag) QB_TRY(sjds_convert(A, true));
     return QBGPU_OK;
 }

@@ -15,6 +15,7 @@
 // (4 bytes of rowinfo per row replace nothing: rowptr is still read once per slice).
 #include "internal.hpp"
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 namespace qb {
@@ -46,6 +47,15 @@ template <int POL> __device__ __forceinline__ double ld_f64(const double *p, uin
     else if (POL == 2) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
+}
+template <int POL> __device__ __forceinline__ uint8_t ld_f64(const uint8_t *p, uint64_t pol)      // dictionary codes
+{
+    unsigned v;
+    if (POL == 0) asm volatile("ld.global.cs.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (POL == 1) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (POL == 2) asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return (uint8_t)v;
 }
 template <int POL> __device__ __forceinline__ double2 ld_f64(const double2 *p, uint64_t pol)
 {
@@ -86,9 +96,13 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
                  const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                  int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
-                 int64_t far_rows)
+                 int64_t far_rows, const double *__restrict__ vdict)
 {
     using VT = VecTraits<VecT>;
+    constexpr bool kDict = sizeof(ValT) == 1;               // 1-byte codes into a <= 256-entry fp64 dictionary
+    using ArithT = typename std::conditional<kDict, double, ValT>::type;
+    __shared__ double sdict[kDict ? 256 : 1];
+    if (kDict) { sdict[threadIdx.x] = vdict[threadIdx.x]; __syncthreads(); }      // kSBlock == 256 threads
     constexpr int WPB = kSBlock / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t pol_s = (SPOL >= 2 || XPOL == 2) ? l2_policy_evict_first() : 0, pol_x = XPOL >= 1 ? l2_policy_evict_last() : 0;
@@ -134,7 +148,9 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     VecT t = (u & 1) ? acc1 : acc0;
-                    mac(t, v[u], xv[u]);
+                    ArithT w;
+                    if constexpr (kDict) w = sdict[v[u]]; else w = v[u];
+                    mac(t, w, xv[u]);
                     if (a[u]) { if (u & 1) acc1 = t; else acc0 = t; }
                 }
             } else {
@@ -147,7 +163,9 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
                 for (int u = 0; u < U; u++) {
                     if (a[u]) {
                         const uint64_t px = (XPOL == 2 && llabs((long long)c[u] - (long long)(row_lo + row)) > far_rows) ? pol_s : pol_x;
-                        if (u & 1) mac(acc1, v[u], ld_x<XPOL>(x + c[u], px)); else mac(acc0, v[u], ld_x<XPOL>(x + c[u], px));
+                        ArithT w;
+                        if constexpr (kDict) w = sdict[v[u]]; else w = v[u];
+                        if (u & 1) mac(acc1, w, ld_x<XPOL>(x + c[u], px)); else mac(acc0, w, ld_x<XPOL>(x + c[u], px));
                     }
                 }
             }
@@ -199,7 +217,7 @@ static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
     const int grid = (int)(want < cap ? want : cap);
     kern<<<grid, kSBlock, 0, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                          (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
-                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, g_far_rows);
+                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, g_far_rows, A->vdict);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
@@ -251,6 +269,7 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
 
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)
 {
+    if (A->ndict) return A->api_complex ? launch_sjds_typed<uint8_t, double2>(A, a) : launch_sjds_typed<uint8_t, double>(A, a);
     if (!A->api_complex) return launch_sjds_typed<double, double>(A, a);
     if (A->val_real) return launch_sjds_typed<double, double2>(A, a);
     return launch_sjds_typed<double2, double2>(A, a);
@@ -347,6 +366,7 @@ static int sjds_convert_typed(qbgpu_matrix *A, bool forward)
 int sjds_convert(qbgpu_matrix *A, bool forward)
 {
     if (forward == (A->format == QBGPU_FORMAT_SELL)) return QBGPU_OK;
+    if (A->ndict) return sjds_convert_typed<uint8_t>(A, forward);
     return A->val_real ? sjds_convert_typed<double>(A, forward) : sjds_convert_typed<double2>(A, forward);
 }
 

@@ -124,6 +124,7 @@ static int launch_lanes(const qbgpu_matrix *A, const FusedArgs &a, int lanes)
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
 {
     if (A->format == QBGPU_FORMAT_SELL) return launch_spmv_sjds(A, a);
+    if (A->ndict) return fail(QBGPU_ERR_STATE, "dictionary-coded values need the sliced-jagged layout");
     const int lanes = lanes_override ? lanes_override : A->lanes;
     const bool dots = a.dots != nullptr;
     if (!A->api_complex) {
@@ -151,6 +152,10 @@ int autotune(qbgpu_matrix *A, int flags)
     if (const char *ff = getenv("QBGPU_FORCE_FORMAT")) {
         if (!strcmp(ff, "sell")) flags |= QBGPU_FORMAT_SELL;
         else if (!strcmp(ff, "csr")) flags |= QBGPU_FORMAT_CSR | QBGPU_NO_AUTOTUNE;
+    }
+    if ((flags & QBGPU_VALUE_DICT) || getenv("QBGPU_VALUE_DICT")) {
+        QB_TRY(value_dict_encode(A));                       // opt-in 1-byte value codes; only the sliced-jagged kernel decodes them
+        if (A->ndict) return sjds_convert(A, true);
     }
     if (flags & QBGPU_FORMAT_SELL) return sjds_convert(A, true);
     if ((flags & QBGPU_NO_AUTOTUNE) || nrows < 4096) return QBGPU_OK;

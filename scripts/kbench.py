@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--ids", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
+    ap.add_argument("--dict", action="store_true", help="1-byte value codes (QBGPU_VALUE_DICT)")
     ap.add_argument("--far", default="", help="comma list of log2(far_rows) to sweep for the adaptive-policy variants")
     a = ap.parse_args()
     L = qb.lib()
@@ -48,7 +49,7 @@ def main():
     t0 = time.time()
     h = C.c_void_p()
     cplx = 0 if a.real else 1
-    flags = 8 | 2          # sliced-jagged, no autotune
+    flags = 8 | 2 | (16 if a.dict else 0)          # sliced-jagged, no autotune
     if fam == "hubbard":
         bonds = np.array(bench.square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
         rc = L.qbgpu_build_hubbard(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data, p["t"], p["U"], cplx, flags, 0, -1)
@@ -62,8 +63,9 @@ def main():
     inf = M.info
     n, Z = inf.n, inf.nnz_stored
     s_vec = 16 if cplx else 8
-    B = bench.algorithmic_bytes(Z, n, n, 8, s_vec)
-    print(f"# {a.workload}: n={n} Z={Z} B_spmv={B/1e9:.2f} GB (S_val=8,S_vec={s_vec}) build {time.time()-t0:.1f}s", flush=True)
+    s_val = 1 if inf.value_dict else 8
+    B = bench.algorithmic_bytes(Z, n, n, s_val, s_vec)
+    print(f"# {a.workload}: n={n} Z={Z} B_spmv={B/1e9:.2f} GB (S_val={s_val},S_vec={s_vec}) dict={inf.value_dict} build {time.time()-t0:.1f}s", flush=True)
     dt = np.complex128 if cplx else np.float64
     x = qb.vec_randomize(n, 1, dtype=dt, device=True)
     y = qb.DeviceVector(n, dt)

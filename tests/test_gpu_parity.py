@@ -125,6 +125,35 @@ def test_sliced_jagged_layout_gives_the_same_product(oracle, name):
     assert abs(ritz[0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_value_dictionary_is_lossless(oracle, name):
+    """QBGPU_VALUE_DICT (16): fp64 values replaced by 1-byte codes when there are <= 256 distinct ones."""
+    A, meta, ex = oracle.load_golden(name)
+    x = oracle.vec_randomize(A.dim, 1)
+    D = make(A, flags=16 | 2)
+    J = make(A, flags=8 | 2)
+    all_real = np.abs(A.val.imag).max() == 0.0
+    ndistinct = len(np.unique(oracle.expand_upper(A)[2].real)) if (all_real and A.sym) else None
+    inf = D.info
+    if all_real and ndistinct is not None and ndistinct <= 256:
+        assert inf.value_dict == ndistinct and inf.format == 8
+        assert inf.device_bytes < J.info.device_bytes
+    if not all_real:
+        assert inf.value_dict == 0                           # complex values are left alone
+    yd = np.zeros(A.dim, dtype=np.complex128); yj = np.zeros_like(yd)
+    D.MultMv(x, yd); J.MultMv(x, yj)
+    assert np.array_equal(yd, yj)                            # decoded values are the identical doubles
+    assert rel_l2(yd, ex["y1"]) <= TOL_MV
+    rp, c1, v1 = D.download_expanded()
+    rp2, c2, v2 = J.download_expanded()
+    assert np.array_equal(rp, rp2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
+    v = np.zeros(2 * A.dim, dtype=np.complex128); v[:A.dim] = x
+    hess = np.zeros(2000)
+    m = qb.lanczos(0, 999, 1000, A.dim, D, v, hess, "sr_val0")
+    ritz, _ = qb.hess_eigen(hess, 1000, m)
+    assert abs(ritz[0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+
+
 @pytest.mark.parametrize("name", ["heis12_full", "hubbard4x2", "tri4x4_k00", "tj12"])
 def test_double_precision_real_matrix_path(oracle, name):
     """csr_mat<double> (reachable in the reference only by constructing it directly)."""

@@ -1,5 +1,6 @@
 // quantum_basis_b200/csrc/context.cu -- per-thread context, error reporting, device-memory helpers of libqbgpu.
 #include "internal.hpp"
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -58,6 +59,14 @@ int qbgpu_init(int device)
     cudaDeviceProp prop;
     QB_CUDA(cudaGetDeviceProperties(&prop, device));
     c.num_sms = prop.multiProcessorCount;
+    // L2 evict_last / persisting accesses only take effect inside the persisting set-aside, which defaults to 0 bytes
+    if (prop.persistingL2CacheMaxSize > 0 && !getenv("QBGPU_NO_L2_PERSIST")) {
+        size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        if (const char *e = getenv("QBGPU_L2_PERSIST_MB")) want = (size_t)atol(e) << 20;
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (getenv("QBGPU_VERBOSE")) fprintf(stderr, "[qbgpu] L2 %d MB, persisting set-aside %zu MB (max %d MB)\n", prop.l2CacheSize >> 20, want >> 20, prop.persistingL2CacheMaxSize >> 20);
+    }
     QB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     QB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;

@@ -8,6 +8,7 @@
 // files of the reference (ckpt_lanczos_update, log_Lanczos_srval, log_CG.txt) are host I/O outside the path.
 #include "internal.hpp"
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -149,6 +150,11 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     int cnt_accuE0 = 0;
     double theta0_prev = 0.0;
     int64_t m = 0;
+    // QBGPU_VERBOSE: per-phase device time of the loop (events around the three passes) and host time of the stop rule
+    const bool prof = getenv("QBGPU_VERBOSE") != nullptr;
+    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+    double t_a = 0, t_b = 0, t_c = 0, t_host = 0;
+    if (prof) for (auto &e : pe) QB_CUDA(cudaEventCreate(&e));
     while (m < mm) {
         m++;
         // one fused Lanczos step (src/lanczos.cc:167-187 for m == 1, :194-214 otherwise)
@@ -156,9 +162,13 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
         void *uz = Ubuf[m % 2];
         FusedArgs fa;
         fa.x = ux; fa.z = uz; fa.y = uz; fa.scal_mode = 1; fa.sc = state; fa.beta = make_double2(1.0, 0.0); fa.dots = state + 3;
+        if (prof) QB_CUDA(cudaEventRecord(pe[0], c.stream));
         QB_TRY(launch_spmv(A, fa));
+        if (prof) QB_CUDA(cudaEventRecord(pe[1], c.stream));
         QB_TRY(lanczos_step_b(n, cplx, ux, uz, state));
+        if (prof) QB_CUDA(cudaEventRecord(pe[2], c.stream));
         QB_TRY(lanczos_step_c(state, a_dev, b_dev, m));
+        if (prof) QB_CUDA(cudaEventRecord(pe[3], c.stream));
         double ab[2];
         QB_CUDA(cudaMemcpyAsync(c.scal_host, a_dev + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         QB_CUDA(cudaMemcpyAsync(c.scal_host + 1, b_dev + m, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -166,6 +176,14 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
         ab[0] = c.scal_host[0]; ab[1] = c.scal_host[1];
         hess[maxit + m - 1] = ab[0];
         hess[m] = ab[1];
+        if (prof) {
+            float f;
+            cudaEventElapsedTime(&f, pe[0], pe[1]); t_a += f;
+            cudaEventElapsedTime(&f, pe[1], pe[2]); t_b += f;
+            cudaEventElapsedTime(&f, pe[2], pe[3]); t_c += f;
+        }
+        const auto th0 = std::chrono::steady_clock::now();
+        struct HostTimer { const std::chrono::steady_clock::time_point t0; double &acc; ~HostTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } host_timer{th0, t_host};
         if (m == 1) continue;                               // the start-up step has no checks in the reference (:167-191)
         if (stop_on_breakdown && fabs(hess[m]) < kLanczosPrecision) break;                         // :216
         if (is_val1) {                                      // re-orthogonalise against phi0, :218-226
@@ -198,6 +216,11 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
             }
             theta0_prev = ritz[0];
         }
+    }
+    if (prof) {
+        fprintf(stderr, "[qbgpu lanczos] %lld steps, per step: product+epilogue %.3f ms, update pass %.3f ms, scalar kernel %.4f ms, host stop rule %.3f ms (n=%lld, %s vectors)\n",
+                (long long)m, t_a / m, t_b / m, t_c / m, t_host / m, (long long)n, cplx ? "complex" : "fp64");
+        for (auto &e : pe) cudaEventDestroy(e);
     }
     *m_out = m;
     // hand the two live vectors back normalised, in the reference's slots: v_m at (m%2), v_{m-1} at ((m-1)%2)

@@ -142,7 +142,10 @@ def test_value_dictionary_is_lossless(oracle, name):
         assert inf.value_dict == 0                           # complex values are left alone
     yd = np.zeros(A.dim, dtype=np.complex128); yj = np.zeros_like(yd)
     D.MultMv(x, yd); J.MultMv(x, yj)
-    assert np.array_equal(yd, yj)                            # decoded values are the identical doubles
+    if inf.value_dict:
+        assert np.array_equal(yd, yj)                        # decoded values are the identical doubles, same kernel order
+    else:
+        assert rel_l2(yd, yj) <= 1e-14
     assert rel_l2(yd, ex["y1"]) <= TOL_MV
     rp, c1, v1 = D.download_expanded()
     rp2, c2, v2 = J.download_expanded()

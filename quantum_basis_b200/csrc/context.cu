@@ -60,9 +60,10 @@ int qbgpu_init(int device)
     QB_CUDA(cudaGetDeviceProperties(&prop, device));
     c.num_sms = prop.multiProcessorCount;
     // L2 evict_last / persisting accesses only take effect inside the persisting set-aside, which defaults to 0 bytes
-    if (prop.persistingL2CacheMaxSize > 0 && !getenv("QBGPU_NO_L2_PERSIST")) {
-        size_t want = (size_t)prop.persistingL2CacheMaxSize;
-        if (const char *e = getenv("QBGPU_L2_PERSIST_MB")) want = (size_t)atol(e) << 20;
+    // (measured, profiles/r01_kbench_sweep3_l2_persist.txt: a set-aside does not help this kernel and the maximum one
+    // costs 7-13 %, so it stays off unless QBGPU_L2_PERSIST_MB asks for it)
+    if (prop.persistingL2CacheMaxSize > 0 && getenv("QBGPU_L2_PERSIST_MB")) {
+        size_t want = (size_t)atol(getenv("QBGPU_L2_PERSIST_MB")) << 20;
         if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
         (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
         if (getenv("QBGPU_VERBOSE")) fprintf(stderr, "[qbgpu] L2 %d MB, persisting set-aside %zu MB (max %d MB)\n", prop.l2CacheSize >> 20, want >> 20, prop.persistingL2CacheMaxSize >> 20);

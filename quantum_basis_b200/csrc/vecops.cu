@@ -20,11 +20,12 @@ static int vec_grid(int64_t n)
     return (int)(want < cap ? want : cap);
 }
 
-#define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+// grid-stride loop, unrolled by 4 so that each thread keeps 4 independent element loads per operand in flight
+#define GRID_STRIDE(i, n) _Pragma("unroll 4") for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
 // ------------------------------------------------------------------------------------- dot / nrm2 / axpy / scal
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) dotc_kernel(int64_t n, const VecT *__restrict__ x, const VecT *__restrict__ y,
+__global__ void __launch_bounds__(kVBlock, 4) dotc_kernel(int64_t n, const VecT *__restrict__ x, const VecT *__restrict__ y,
                                                        double *out, double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(kVBlock) dotc_kernel(int64_t n, const VecT *__
     block_reduce_finalize<3, kVBlock>(d, partials, ticket, out);
 }
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) nrm2sq_kernel(int64_t n, const VecT *__restrict__ x, double *out, double *partials, unsigned *ticket)
+__global__ void __launch_bounds__(kVBlock, 4) nrm2sq_kernel(int64_t n, const VecT *__restrict__ x, double *out, double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
     double d[1] = {0.0};
@@ -41,20 +42,20 @@ __global__ void __launch_bounds__(kVBlock) nrm2sq_kernel(int64_t n, const VecT *
     block_reduce_finalize<1, kVBlock>(d, partials, ticket, out);
 }
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) axpy_kernel(int64_t n, double2 a, const VecT *__restrict__ x, VecT *y)
+__global__ void __launch_bounds__(kVBlock, 4) axpy_kernel(int64_t n, double2 a, const VecT *__restrict__ x, VecT *y)
 {
     using VT = VecTraits<VecT>;
     GRID_STRIDE(i, n) y[i] = VT::add(y[i], VT::scale(a, x[i]));
 }
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) scal_kernel(int64_t n, double2 a, VecT *x)
+__global__ void __launch_bounds__(kVBlock, 4) scal_kernel(int64_t n, double2 a, VecT *x)
 {
     using VT = VecTraits<VecT>;
     GRID_STRIDE(i, n) x[i] = VT::scale(a, x[i]);
 }
 // dst = s * src with s = (scale_dev ? *scale_dev : 1) * scale_imm
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) scale_copy_kernel(int64_t n, const double *scale_dev, double scale_imm,
+__global__ void __launch_bounds__(kVBlock, 4) scale_copy_kernel(int64_t n, const double *scale_dev, double scale_imm,
                                                              const VecT *src, VecT *dst)      // src may alias dst
 {
     using VT = VecTraits<VecT>;
@@ -103,14 +104,14 @@ int scale_copy(int64_t n, bool cplx, const double *scale_dev, double scale_imm, 
 }
 
 // ----------------------------------------------------------------- real <-> complex views of an all-real vector
-__global__ void __launch_bounds__(kVBlock) imag_abs2_kernel(int64_t n, const double2 *__restrict__ x, double *out, double *partials, unsigned *ticket)
+__global__ void __launch_bounds__(kVBlock, 4) imag_abs2_kernel(int64_t n, const double2 *__restrict__ x, double *out, double *partials, unsigned *ticket)
 {
     double d[1] = {0.0};
     GRID_STRIDE(i, n) { const double im = x[i].y; d[0] += im * im; }
     block_reduce_finalize<1, kVBlock>(d, partials, ticket, out);
 }
-__global__ void __launch_bounds__(kVBlock) take_real_kernel(int64_t n, const double2 *__restrict__ in, double *out) { GRID_STRIDE(i, n) out[i] = in[i].x; }
-__global__ void __launch_bounds__(kVBlock) put_real_kernel(int64_t n, const double *__restrict__ in, double2 *out) { GRID_STRIDE(i, n) out[i] = make_double2(in[i], 0.0); }
+__global__ void __launch_bounds__(kVBlock, 4) take_real_kernel(int64_t n, const double2 *__restrict__ in, double *out) { GRID_STRIDE(i, n) out[i] = in[i].x; }
+__global__ void __launch_bounds__(kVBlock, 4) put_real_kernel(int64_t n, const double *__restrict__ in, double2 *out) { GRID_STRIDE(i, n) out[i] = make_double2(in[i], 0.0); }
 
 int vec_imag_norm2(int64_t n, const void *x, double *out_dev)
 {
@@ -144,7 +145,7 @@ __device__ __forceinline__ uint64_t lehmer_pow(uint64_t base, uint64_t e)
     return r;
 }
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) randomize_kernel(int64_t n, VecT *x, uint32_t seed, int64_t per_thread)
+__global__ void __launch_bounds__(kVBlock, 4) randomize_kernel(int64_t n, VecT *x, uint32_t seed, int64_t per_thread)
 {
     const uint64_t p = 2147483647ull;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kVBlock) randomize_kernel(int64_t n, VecT *x, 
     }
 }
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) fill_kernel(int64_t n, VecT *x, double v)
+__global__ void __launch_bounds__(kVBlock, 4) fill_kernel(int64_t n, VecT *x, double v)
 {
     GRID_STRIDE(i, n) { if constexpr (sizeof(VecT) == 16) x[i] = make_double2(v, 0.0); else x[i] = v; }
 }
@@ -197,16 +198,24 @@ int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed)
 // state: [0]=sx [1]=sz [2]=b_prev [3]=alpha [4],[5] scratch [6]=norm2 [7] spare  (see include/qbgpu.h)
 // step b: w' = uz - alpha*sx*ux -> uz ; state[6] = sum |w'|^2   (reference: axpy + nrm2, src/lanczos.cc:206-208)
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) lanczos_b_kernel(int64_t n, const VecT *__restrict__ ux, VecT *uz, double *state,
-                                                            double *partials, unsigned *ticket)
+__global__ void __launch_bounds__(kVBlock, 4) lanczos_b_kernel(int64_t n, const VecT *__restrict__ ux, VecT *uz, double *state,
+                                                               double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
     const double f = -state[3] * state[0];
     double d[1] = {0.0};
-    GRID_STRIDE(i, n) {
-        const VecT w = VT::add(uz[i], VT::rscale(f, ux[i]));
-        uz[i] = w;
-        d[0] += VT::abs2(w);
+    // 4 elements per thread per trip, all loads first: uz is read and written, so without the explicit batching the
+    // compiler keeps each load behind the previous store
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+        VecT w[4], v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t j = i + k * stride; if (j < n) { w[k] = uz[j]; v[k] = ux[j]; } }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t j = i + k * stride;
+            if (j < n) { const VecT r = VT::add(w[k], VT::rscale(f, v[k])); uz[j] = r; d[0] += VT::abs2(r); }
+        }
     }
     block_reduce_finalize<1, kVBlock>(d, partials, ticket, state + 6);
 }
@@ -242,7 +251,7 @@ int lanczos_step_c(double *state, double *a_dev, double *b_dev, int64_t m)
 // sc (device): [0]=gamma (residual norm, `accu`) [1],[2]=delta=<p,pp> (re,im) [3]=|pp|^2 scratch [4]=|r|^2
 // pass 1 (src/lanczos.cc:324-327): alpha = gamma^2/delta ; v += alpha p ; r -= alpha pp ; sc[4] = |r|^2
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) cg_vr_kernel(int64_t n, const double *__restrict__ sc, VecT *v, VecT *r,
+__global__ void __launch_bounds__(kVBlock, 4) cg_vr_kernel(int64_t n, const double *__restrict__ sc, VecT *v, VecT *r,
                                                         const VecT *__restrict__ p, const VecT *__restrict__ pp,
                                                         double *out, double *partials, unsigned *ticket)
 {
@@ -253,22 +262,39 @@ __global__ void __launch_bounds__(kVBlock) cg_vr_kernel(int64_t n, const double 
     else { const double den = sc[1] * sc[1] + sc[2] * sc[2]; alpha = make_double2(g2 * sc[1] / den, -g2 * sc[2] / den); }
     const double2 nalpha = make_double2(-alpha.x, -alpha.y);
     double d[1] = {0.0};
-    GRID_STRIDE(i, n) {
-        v[i] = VT::add(v[i], VT::scale(alpha, p[i]));
-        const VecT ri = VT::add(r[i], VT::scale(nalpha, pp[i]));
-        r[i] = ri;
-        d[0] += VT::abs2(ri);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {     // loads batched, see lanczos_b_kernel
+        VecT vv[2], rr[2], pv[2], qv[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) { const int64_t j = i + k * stride; if (j < n) { vv[k] = v[j]; rr[k] = r[j]; pv[k] = p[j]; qv[k] = pp[j]; } }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int64_t j = i + k * stride;
+            if (j < n) {
+                v[j] = VT::add(vv[k], VT::scale(alpha, pv[k]));
+                const VecT ri = VT::add(rr[k], VT::scale(nalpha, qv[k]));
+                r[j] = ri;
+                d[0] += VT::abs2(ri);
+            }
+        }
     }
     block_reduce_finalize<1, kVBlock>(d, partials, ticket, out);
 }
 // pass 2 (src/lanczos.cc:327-330): beta = |r|/gamma ; p = r + beta^2 p ; gamma *= beta (written to sc[5])
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock) cg_p_kernel(int64_t n, double *sc, const VecT *__restrict__ r, VecT *p)
+__global__ void __launch_bounds__(kVBlock, 4) cg_p_kernel(int64_t n, double *sc, const VecT *__restrict__ r, VecT *p)
 {
     using VT = VecTraits<VecT>;
     const double beta = sqrt(sc[4]) / sc[0];
     const double b2 = beta * beta;
-    GRID_STRIDE(i, n) p[i] = VT::add(r[i], VT::rscale(b2, p[i]));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+        VecT rv[4], pv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t j = i + k * stride; if (j < n) { rv[k] = r[j]; pv[k] = p[j]; } }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t j = i + k * stride; if (j < n) p[j] = VT::add(rv[k], VT::rscale(b2, pv[k])); }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) sc[5] = sc[0] * beta;
 }
 

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--ids", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
+    ap.add_argument("--fused", action="store_true", help="time the fused-epilogue variants of the production kernel")
     ap.add_argument("--dict", action="store_true", help="1-byte value codes (QBGPU_VALUE_DICT)")
     ap.add_argument("--far", default="", help="comma list of log2(far_rows) to sweep for the adaptive-policy variants")
     a = ap.parse_args()
@@ -93,6 +94,25 @@ def main():
         res.append((ms, v))
         print(f"variant {v:2d} far=2^{f:<2d} [{describe(v):40s}] {ms:8.3f} ms  {B/ms/1e6:7.0f} GB/s  {B/ms/1e6/6451.8:5.3f} of measured peak", flush=True)
     L.qbgpu_debug_set_variant(0)
+    if a.fused:
+        dots = qb.DeviceVector(4, np.float64)
+        one = (C.c_double * 2)(1.0, 0.0); zero = (C.c_double * 2)(0.0, 0.0); half = (C.c_double * 2)(-0.5, 0.0)
+        cases = [("plain y=Hx", zero, zero, False, False), ("beta*z (z=y)", zero, half, True, False), ("dots", zero, zero, False, True),
+                 ("beta*z + dots (Lanczos step a)", zero, half, True, True), ("gamma*x + dots (CG)", half, zero, False, True)]
+        for label, gam, bet, usez, used in cases:
+            def call():
+                rc = L.qbgpu_spmv_fused(M.handle, C.c_void_p(x.ptr), C.c_void_p(y.ptr) if usez else None, C.c_void_p(y.ptr), one, gam, bet,
+                                        C.c_void_p(dots.ptr) if used else None)
+                assert rc == 0, L.qbgpu_last_error()
+            for _ in range(2):
+                call()
+            e0.record(stream)
+            for _ in range(a.reps):
+                call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.reps
+            print(f"fused [{label:32s}] {ms:8.3f} ms", flush=True)
     res.sort()
     print("# best:", ", ".join(f"{v}:{ms:.3f}" for ms, v in res[:5]))
     if a.csr:

@@ -1,0 +1,92 @@
+// quantum_basis_b200/csrc/peer.cu -- peer-memory exchange of the Krylov vector over NVLink (one process per GPU).
+//
+// The reference has no distributed mode; SURVEY section 8(e) asks for the gathered vector to arrive while the local
+// block is being multiplied.  Instead of a collective, every rank maps its peers' vector buffers (CUDA IPC) and PULLS
+// the slices it needs with copy-engine transfers on one stream per peer; the product of column block p is ordered
+// behind the arrival of slice p with an event, so transfers and products overlap block by block and all seven
+// incoming NVLink paths of a GPU are busy at once.  Cross-process ordering (a slice is final before it is pulled, and
+// is not overwritten while it is being pulled) comes from the collectives the Krylov loop already contains (the
+// all-reduce of the Lanczos scalars) or from an explicit barrier in the plain product loop, plus ping-pong buffers.
+#include "internal.hpp"
+#include <cstring>
+
+namespace qb {
+
+constexpr int kPeerLanes = 16;
+struct PeerState {
+    cudaStream_t lane[kPeerLanes] = {};
+    cudaEvent_t arrived[kPeerLanes] = {};
+    cudaEvent_t fence = nullptr;
+    bool ready = false;
+};
+static thread_local PeerState g_peer;
+
+static int peer_init()
+{
+    if (g_peer.ready) return QBGPU_OK;
+    for (int i = 0; i < kPeerLanes; i++) {
+        QB_CUDA(cudaStreamCreateWithFlags(&g_peer.lane[i], cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&g_peer.arrived[i], cudaEventDisableTiming));
+    }
+    QB_CUDA(cudaEventCreateWithFlags(&g_peer.fence, cudaEventDisableTiming));
+    g_peer.ready = true;
+    return QBGPU_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qbgpu_ipc_export(void *dptr, void *handle64)
+{
+    QB_TRY(ensure_init());
+    if (!dptr || !handle64) return fail(QBGPU_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    QB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, dptr));
+    return QBGPU_OK;
+}
+
+int qbgpu_ipc_open(const void *handle64, void **peer_ptr)
+{
+    QB_TRY(ensure_init());
+    if (!handle64 || !peer_ptr) return fail(QBGPU_ERR_ARG, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    QB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return QBGPU_OK;
+}
+
+int qbgpu_ipc_close(void *peer_ptr)
+{
+    if (peer_ptr) QB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return QBGPU_OK;
+}
+
+/* Enqueue, on copy lane `lane`, a pull of `bytes` from a peer-mapped (or local) source into local memory, ordered after
+ * everything issued so far on the compute stream; the arrival is recorded for qbgpu_peer_wait. */
+int qbgpu_peer_pull_async(int lane, void *dst_local, const void *src_peer, size_t bytes)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    if (lane < 0 || lane >= kPeerLanes || !dst_local || !src_peer) return fail(QBGPU_ERR_ARG, "peer_pull: bad argument");
+    Context &c = ctx();
+    QB_CUDA(cudaEventRecord(g_peer.fence, c.stream));
+    QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
+    QB_CUDA(cudaMemcpyAsync(dst_local, src_peer, bytes, cudaMemcpyDefault, g_peer.lane[lane]));
+    QB_CUDA(cudaEventRecord(g_peer.arrived[lane], g_peer.lane[lane]));
+    return QBGPU_OK;
+}
+
+/* Order everything issued afterwards on the compute stream behind the last pull of `lane`. */
+int qbgpu_peer_wait(int lane)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    if (lane < 0 || lane >= kPeerLanes) return fail(QBGPU_ERR_ARG, "peer_wait: bad lane");
+    QB_CUDA(cudaStreamWaitEvent(ctx().stream, g_peer.arrived[lane], 0));
+    return QBGPU_OK;
+}
+
+}  // extern "C"

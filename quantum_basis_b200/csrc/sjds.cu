@@ -235,6 +235,17 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
     const bool dots = a.dots != nullptr;
 #ifdef QBGPU_TUNING_VARIANTS
     if constexpr (sizeof(ValT) == 8) {                      // experimental instantiations only for fp64 values
+        if (dots && g_sjds_variant >= 45) {                 // configurations of the fused-epilogue (DOTS) kernel
+            switch (g_sjds_variant) {
+            case 45: return launch_sjds_variant<ValT, VecT, true, 8, 2, 0, true, 3>(A, a);
+            case 46: return launch_sjds_variant<ValT, VecT, true, 8, 2, 0, true, 2>(A, a);
+            case 47: return launch_sjds_variant<ValT, VecT, true, 4, 2, 1, false, 4>(A, a);
+            case 48: return launch_sjds_variant<ValT, VecT, true, 4, 2, 1, false, 3>(A, a);
+            case 49: return launch_sjds_variant<ValT, VecT, true, 6, 2, 0, true, 3>(A, a);
+            case 50: return launch_sjds_variant<ValT, VecT, true, 4, 2, 0, true, 4>(A, a);
+            default: break;
+            }
+        }
         if (!dots && g_sjds_variant > 0) {
             switch (g_sjds_variant - 1) {
 #define QB_V1(M, MI, L, U, UI, S, SI, X) case (MI * 16 + (L ? 8 : 0) + UI * 4 + SI * 2 + X): return launch_sjds_variant<ValT, VecT, false, U, S, X, L, M>(A, a);
@@ -244,19 +255,9 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
 #undef QB_V1
 #undef QB_V2
 #undef QB_V3
-            // second sweep: per-entry gather policy (X=2) and more launch-bound / unroll points, stream policy L2ef
-            case 32: return launch_sjds_variant<ValT, VecT, false, 4, 2, 2, false, 4>(A, a);
-            case 33: return launch_sjds_variant<ValT, VecT, false, 8, 2, 2, true, 4>(A, a);
             case 34: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 3>(A, a);
-            case 35: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 5>(A, a);
-            case 36: return launch_sjds_variant<ValT, VecT, false, 4, 2, 1, false, 6>(A, a);
             case 37: return launch_sjds_variant<ValT, VecT, false, 2, 2, 1, false, 6>(A, a);
-            case 38: return launch_sjds_variant<ValT, VecT, false, 6, 2, 1, false, 4>(A, a);
-            case 39: return launch_sjds_variant<ValT, VecT, false, 4, 2, 2, false, 5>(A, a);
             case 40: return launch_sjds_variant<ValT, VecT, false, 8, 2, 0, true, 3>(A, a);
-            case 41: return launch_sjds_variant<ValT, VecT, false, 8, 2, 0, true, 5>(A, a);
-            case 42: return launch_sjds_variant<ValT, VecT, false, 12, 2, 0, true, 3>(A, a);
-            case 43: return launch_sjds_variant<ValT, VecT, false, 6, 2, 2, false, 4>(A, a);
             default: break;
             }
         }

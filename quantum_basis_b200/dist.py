@@ -113,6 +113,123 @@ def pipelined_lanczos(op, u0, u1, maxit, steps, state, a_dev, b_dev):
     return U
 
 
+class RawBuf:
+    """A device buffer owned by libqbgpu (cudaMalloc, hence exportable through CUDA IPC) with the two methods the
+    kernels provider needs from a tensor."""
+
+    def __init__(self, qb, nbytes):
+        self.qb, self.L, self.nbytes = qb, qb.lib(), int(nbytes)
+        p = C.c_void_p()
+        assert self.L.qbgpu_malloc(C.byref(p), self.nbytes) == 0, self.L.qbgpu_last_error()
+        self.ptr = p.value
+        assert self.L.qbgpu_memset0(C.c_void_p(self.ptr), self.nbytes) == 0
+
+    def data_ptr(self):
+        return self.ptr
+
+    def view(self, byte_offset):
+        v = object.__new__(RawBuf)
+        v.qb, v.L, v.ptr, v.nbytes = self.qb, self.L, self.ptr + byte_offset, self.nbytes - byte_offset
+        return v
+
+    def upload(self, arr, byte_offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert self.L.qbgpu_memcpy_h2d(C.c_void_p(self.ptr + byte_offset), C.c_void_p(arr.ctypes.data), arr.nbytes) == 0
+
+    def download(self, dtype, count, byte_offset=0):
+        out = np.empty(count, dtype=dtype)
+        assert self.L.qbgpu_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr + byte_offset), out.nbytes) == 0
+        return out
+
+
+class PeerExchangeOperator:
+    """The sharded product with the exchange done by peer-memory pulls over NVLink instead of a collective.
+
+    Every rank owns two full-length vector buffers X[0], X[1] (ping-pong) allocated by libqbgpu and exported through
+    CUDA IPC; its own slice of the current vector lives in X[b][lo:hi].  A product on buffer b
+      1. passes a barrier (a 1-element all-reduce, or -- inside Lanczos -- the scalar all-reduce that is there anyway),
+         after which every rank's slice of X[b] is final,
+      2. enqueues, on one copy stream per peer, the pull of that peer's slice from the peer's X[b] into the local X[b],
+      3. multiplies the own column block at once and each other block as soon as its slice has arrived (event wait).
+    The ping-pong plus the barrier make the pulls race-free: a slice is overwritten only two products later, after a
+    barrier that every puller has passed."""
+
+    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod):
+        self.qb, self.L, self.k, self.n, self.rank, self.world, self.comm, self.torch = qb, qb.lib(), kernels, n, rank, world, comm, torch_mod
+        self.bounds, self.chunk = equal_row_bounds(n, world)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.esize = 8 * kernels.ncomp
+        self.order = [(rank + d) % world for d in range(1, world)]
+        self.col_bounds = [min(n, p * self.chunk) for p in range(world)] + [n]
+        nbytes = self.chunk * world * self.esize
+        self.X = [RawBuf(qb, nbytes), RawBuf(qb, nbytes)]
+        import torch.distributed as dist
+        handles = []
+        for b in range(2):
+            h = (C.c_ubyte * 64)()
+            assert self.L.qbgpu_ipc_export(C.c_void_p(self.X[b].ptr), h) == 0, self.L.qbgpu_last_error()
+            handles.append(bytes(h))
+        allh = [None] * world
+        dist.all_gather_object(allh, handles)
+        self.peer = [[None] * world for _ in range(2)]
+        for p in range(world):
+            if p == rank:
+                continue
+            for b in range(2):
+                out = C.c_void_p()
+                hb = (C.c_ubyte * 64).from_buffer_copy(allh[p][b])
+                assert self.L.qbgpu_ipc_open(hb, C.byref(out)) == 0, self.L.qbgpu_last_error()
+                self.peer[b][p] = out.value
+        self.token = torch_mod.zeros(1, dtype=torch_mod.float64, device="cuda")
+
+    def own(self, b):
+        """this rank's slice of buffer b (where the caller writes its part of the vector)"""
+        return self.X[b].view(self.lo * self.esize)
+
+    def pull(self, b):
+        for p in self.order:
+            off = self.bounds[p] * self.esize
+            nb = (self.bounds[p + 1] - self.bounds[p]) * self.esize
+            if nb:
+                rc = self.L.qbgpu_peer_pull_async(p, C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off), nb)
+                assert rc == 0, self.L.qbgpu_last_error()
+
+    def _wait(self, p):
+        assert self.L.qbgpu_peer_wait(p) == 0, self.L.qbgpu_last_error()
+
+    def matvec(self, b, y_local, barrier=True):
+        if barrier:
+            self.comm.all_reduce(self.token)
+        self.pull(b)
+        self.k.multmv_part(self.rank, self.X[b], y_local, accumulate=False)
+        for p in self.order:
+            self._wait(p)
+            self.k.multmv_part(p, self.X[b], y_local, accumulate=True)
+
+    def lanczos_step_a(self, b, uz, state):
+        """x = X[b] (all slices final: the caller's previous all-reduce is the barrier), w accumulated into uz"""
+        self.pull(b)
+        last = len(self.order)
+        self.k.lanczos_step_a_part(self.rank, self.X[b], uz, state, True, last == 0)
+        for idx, p in enumerate(self.order):
+            self._wait(p)
+            self.k.lanczos_step_a_part(p, self.X[b], uz, state, False, idx == last - 1)
+
+
+def peer_lanczos(op, steps, state, a_dev, b_dev, start_buffer=0):
+    """Fused Lanczos on the shards with the peer-pull exchange.  The normalised start slice is in op.own(start_buffer)
+    and must already be visible to the peers (call op.comm.all_reduce(op.token) after writing it)."""
+    k, comm = op.k, op.comm
+    for m in range(1, steps + 1):
+        bx, bz = (start_buffer + m - 1) % 2, (start_buffer + m) % 2
+        ux, uz = op.own(bx), op.own(bz)
+        op.lanczos_step_a(bx, uz, state)
+        comm.all_reduce(k.slot(state, 3))
+        k.lanczos_step_b(ux, uz, state)
+        comm.all_reduce(k.slot(state, 6))                      # also the barrier that makes X[bz] final everywhere
+        k.lanczos_step_c(state, a_dev, b_dev, m)
+
+
 # ----------------------------------------------------------------------------------------------- GPU provider
 class TorchComm:
     def __init__(self):
@@ -156,7 +273,7 @@ class DeviceKernels:
         return t[self.ncomp * first_entry: self.ncomp * (first_entry + nentries)]
 
     def _p(self, t):
-        return C.c_void_p(t.data_ptr())
+        return C.c_void_p(t.data_ptr())             # torch tensor or RawBuf
 
     @staticmethod
     def split(qb, matrix, col_bounds, flags=0):
@@ -260,8 +377,20 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
     launchesA = int(L.qbgpu_kernel_launches(1))
     msB = _timed(torch, dist, stream, lambda: opB.matvec(x_loc, y_loc), args.steps, args.warmup)
     launchesB = int(L.qbgpu_kernel_launches(1))
-    clocks = sampler.stop()
     agree = float((y_loc - y_ref).abs().max().item()) / max(1e-300, float(y_ref.abs().max().item()))
+    # (C) peer-memory pulls over NVLink (copy engines, one stream per peer) overlapped with the column blocks
+    msC, agreeC = None, None
+    try:
+        opC = PeerExchangeOperator(qb, kern, n, rank, world, comm, torch)
+        opC.own(0).upload(np.ascontiguousarray(full[lo:hi]))
+        comm.all_reduce(opC.token)
+        y_c = kern.alloc(chunk)
+        msC = _timed(torch, dist, stream, lambda: opC.matvec(0, y_c), args.steps, args.warmup)
+        agreeC = float((y_c - y_ref).abs().max().item()) / max(1e-300, float(y_ref.abs().max().item()))
+    except Exception as e:                                     # e.g. no peer access between the GPUs of this box
+        msC, agreeC = None, f"unavailable: {e}"
+    launchesC = int(L.qbgpu_kernel_launches(1))
+    clocks = sampler.stop()
     # the local product alone (no exchange): the per-GPU roofline number
     opA.gather(x_loc)
     ms_kernel = _timed(torch, dist, stream, lambda: kern.multmv(opA.x_full, y_ref), max(3, args.steps // 2), 2)
@@ -293,7 +422,10 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
     Z = int(nnz_all.item())
     s_val = 8 if inf.val_is_real else 16
     s_vec = 16
-    ms_per_step = min(msA, msB)
+    ms_per_step = min(m for m in (msA, msB, msC) if m is not None)
+    used = {msA: "allgather", msB: "pipelined_broadcast"}
+    if msC is not None:
+        used[msC] = "peer_pull"
     B_local = algorithmic_bytes(inf.nnz_stored, hi - lo, n, s_val, s_vec)
     peak, peak_src = measured_peak()
 
@@ -312,17 +444,41 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
             u0.copy_(x_loc)
         steps = 40
         out = {}
-        for tag, fn, op in (("allgather", sharded_lanczos, oA), ("pipelined", pipelined_lanczos, oB)):
+        try:
+            oC = PeerExchangeOperator(qb, kr, n, rank, world, comm, torch)
+        except Exception:
+            oC = None
+        schemes = [("allgather", sharded_lanczos, oA), ("pipelined", pipelined_lanczos, oB)]
+        if oC is not None:
+            schemes.append(("peer_pull", None, oC))
+        for tag, fn, op in schemes:
             state = torch.zeros(8, dtype=torch.float64, device="cuda"); state[0] = 1.0
             a_dev = torch.zeros(256, dtype=torch.float64, device="cuda"); b_dev = torch.zeros(256, dtype=torch.float64, device="cuda")
             ua, ub = u0.clone(), kr.alloc(chunk)
-            fn(op, ua, ub, 256, 3, state, a_dev, b_dev)          # warm-up steps continue into the timed ones
+
+            def run(nsteps):
+                if tag == "peer_pull":
+                    op.own(0).upload(u0[: kr.ncomp * (hi - lo)].cpu().numpy())
+                    comm.all_reduce(op.token)
+                    peer_lanczos(op, nsteps, state, a_dev, b_dev)
+                else:
+                    ua.copy_(u0)
+                    fn(op, ua, ub, 256, nsteps, state, a_dev, b_dev)
+            run(3)                                               # warm-up
             torch.cuda.synchronize(); dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             state[:] = 0.0; state[0] = 1.0
-            ua.copy_(u0)
+            if tag == "peer_pull":
+                op.own(0).upload(u0[: kr.ncomp * (hi - lo)].cpu().numpy())
+                comm.all_reduce(op.token)
+            else:
+                ua.copy_(u0)
+            torch.cuda.synchronize(); dist.barrier()
             e0.record(stream)
-            fn(op, ua, ub, 256, steps, state, a_dev, b_dev)
+            if tag == "peer_pull":
+                peer_lanczos(op, steps, state, a_dev, b_dev)
+            else:
+                fn(op, ua, ub, 256, steps, state, a_dev, b_dev)
             e1.record(stream)
             torch.cuda.synchronize(); dist.barrier()
             t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
@@ -330,7 +486,7 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
             out[tag] = {"steps": steps, "seconds": float(t.item()), "iters_per_s": steps / float(t.item()),
                         "a0": float(a_dev[0].item()), "b1": float(b_dev[1].item()), "a_last": float(a_dev[steps - 1].item())}
         lan = {"vectors": "fp64 (real mode)" if real else "complex128", **out,
-               "iters_per_s": max(out["allgather"]["iters_per_s"], out["pipelined"]["iters_per_s"])}
+               "iters_per_s": max(v["iters_per_s"] for v in out.values())}
     del full
 
     if rank == 0:
@@ -339,8 +495,8 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "S_val": s_val, "S_vec": s_vec,
                            "partition": "contiguous equal-row blocks, full expanded rows per rank",
-                           "exchange": {"allgather_ms": msA, "pipelined_broadcast_ms": msB, "used": "pipelined" if msB < msA else "allgather",
-                                        "schemes_agree_rel": agree},
+                           "exchange": {"allgather_ms": msA, "pipelined_broadcast_ms": msB, "peer_pull_ms": msC, "used": used[ms_per_step],
+                                        "schemes_agree_rel": agree, "peer_pull_agree_rel": agreeC},
                            "l2": "inputs larger than L2"},
                 "roofline": {"bound": "hbm", "achieved": B_local / (ms_kernel * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": B_local / (ms_kernel * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -348,7 +504,7 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
                              "note": "per GPU: the local rows' product alone (max over ranks); the exchange is in `value`, not here"},
                 "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": (hi - lo) * s_vec, "d2h_bytes_per_step": (hi - lo) * s_vec,
                         "ms_per_step": 1e3 * e2e_s, "note": "per rank: its slice of x up, its slice of y down, pinned host memory"},
-                "gpu_launches": launchesA + launchesB, "clocks": clocks,
+                "gpu_launches": launchesA + launchesB + launchesC, "clocks": clocks,
                 "host_phases": {"generate_matrix_s": t_build, "split_columns_s": t_split}}
         if lan:
             line["lanczos"] = lan

@@ -48,6 +48,10 @@ def main():
     yref = np.zeros(n, dtype=np.complex128)
     Mfull.MultMv(qb.DeviceVector.from_numpy(xfull), (ydev := qb.DeviceVector(n)))
     yref = ydev.to_numpy()
+    x0 = qb.vec_randomize(n, 1)
+    v = np.zeros(2 * n, dtype=np.complex128); v[:n] = x0
+    hess = np.zeros(200)
+    m = qb.lanczos(0, 60, 100, n, Mfull, v, hess, "dnmcs")
     kern = qd.DeviceKernels(qb, M, real=False, parts=parts)
     for name, Op in (("allgather", qd.ShardedOperator), ("pipelined", qd.PipelinedOperator)):
         op = Op(kern, n, rank, world, comm)
@@ -60,11 +64,35 @@ def main():
         e = torch.tensor([err], device="cuda"); dist.all_reduce(e, op=dist.ReduceOp.MAX)
         report(f"sharded product ({name}, complex x)", e.item() < 1e-13, f"rel_l2={e.item():.2e}")
 
+    # peer-memory pull exchange (CUDA IPC + copy engines)
+    try:
+        opC = qd.PeerExchangeOperator(qb, kern, n, rank, world, comm, torch)
+        opC.own(0).upload(np.ascontiguousarray(xfull[lo:hi]))
+        comm.all_reduce(opC.token)
+        yl = kern.alloc(chunk)
+        for _ in range(3):
+            opC.matvec(0, yl)
+        torch.cuda.synchronize()
+        y = yl.cpu().numpy().view(np.complex128)[: hi - lo]
+        err = np.linalg.norm(y - yref[lo:hi]) / np.linalg.norm(yref[lo:hi])
+        e = torch.tensor([err], device="cuda"); dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        report("sharded product (peer pull, complex x)", e.item() < 1e-13, f"rel_l2={e.item():.2e}")
+        for real in (True, False):
+            kr = qd.DeviceKernels(qb, M, real=real, parts=parts)
+            oC = qd.PeerExchangeOperator(qb, kr, n, rank, world, comm, torch)
+            oC.own(0).upload(np.ascontiguousarray(x0[lo:hi].real if real else x0[lo:hi]))
+            comm.all_reduce(oC.token)
+            state = torch.zeros(8, dtype=torch.float64, device="cuda"); state[0] = 1.0
+            a_dev = torch.zeros(100, dtype=torch.float64, device="cuda"); b_dev = torch.zeros(100, dtype=torch.float64, device="cuda")
+            qd.peer_lanczos(oC, 30, state, a_dev, b_dev)
+            torch.cuda.synchronize()
+            a = a_dev.cpu().numpy(); b = b_dev.cpu().numpy()
+            da = np.abs(a[:25] - hess[100:125]).max(); db = np.abs(b[1:25] - hess[1:25]).max()
+            report(f"sharded Lanczos (peer pull, {'fp64' if real else 'complex'} vectors) vs single GPU", da < 1e-11 and db < 1e-11, f"max|da|={da:.1e} max|db|={db:.1e}")
+    except AssertionError as ex:
+        report("peer pull exchange", False, f"unavailable or failed: {ex}")
+
     # Lanczos: single-GPU fused loop (real mode) vs sharded loops, real and complex vectors
-    x0 = qb.vec_randomize(n, 1)
-    v = np.zeros(2 * n, dtype=np.complex128); v[:n] = x0
-    hess = np.zeros(200)
-    m = qb.lanczos(0, 60, 100, n, Mfull, v, hess, "dnmcs")
     for real in (True, False):
         kr = qd.DeviceKernels(qb, M, real=real, parts=parts)
         for name, Op, fn in (("allgather", qd.ShardedOperator, qd.sharded_lanczos), ("pipelined", qd.PipelinedOperator, qd.pipelined_lanczos)):

@@ -99,7 +99,10 @@ def main():
         one = (C.c_double * 2)(1.0, 0.0); zero = (C.c_double * 2)(0.0, 0.0); half = (C.c_double * 2)(-0.5, 0.0)
         cases = [("plain y=Hx", zero, zero, False, False), ("beta*z (z=y)", zero, half, True, False), ("dots", zero, zero, False, True),
                  ("beta*z + dots (Lanczos step a)", zero, half, True, True), ("gamma*x + dots (CG)", half, zero, False, True)]
-        for label, gam, bet, usez, used in cases:
+        dot_cfgs = [0, 45, 46, 47, 48, 49, 50]
+        names = {0: "production", 45: "U8 UL1 minb3", 46: "U8 UL1 minb2", 47: "U4 UL0 minb4", 48: "U4 UL0 minb3", 49: "U6 UL1 minb3", 50: "U4 UL1 minb4"}
+        for label, gam, bet, usez, used, *rest in [(c + (0,)) for c in cases] + [(f"step a, dots cfg {names[v]}", zero, half, True, True, v) for v in dot_cfgs[1:]]:
+            L.qbgpu_debug_set_variant(rest[0])
             def call():
                 rc = L.qbgpu_spmv_fused(M.handle, C.c_void_p(x.ptr), C.c_void_p(y.ptr) if usez else None, C.c_void_p(y.ptr), one, gam, bet,
                                         C.c_void_p(dots.ptr) if used else None)
@@ -113,6 +116,7 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.reps
             print(f"fused [{label:32s}] {ms:8.3f} ms", flush=True)
+        L.qbgpu_debug_set_variant(0)
     res.sort()
     print("# best:", ", ".join(f"{v}:{ms:.3f}" for ms, v in res[:5]))
     if a.csr:

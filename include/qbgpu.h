@@ -40,6 +40,7 @@ extern "C" {
 #define QBGPU_NO_AUTOTUNE    2   /* skip the kernel-variant timing pass at create */
 #define QBGPU_FORMAT_CSR     4   /* force the expanded-CSR kernels  */
 #define QBGPU_FORMAT_SELL    8   /* force the sliced-jagged kernels (32-row slices, jagged diagonals, no padding) */
+#define QBGPU_FORMAT_MATFREE 32  /* (info only) matrix-free handle: rows are regenerated inside the product */
 #define QBGPU_VALUE_DICT    16   /* opt-in: store fp64 values as 1-byte codes into a table of the distinct values when there
                                     are at most 256 of them (lossless; products are bit-identical); implies FORMAT_SELL */
 
@@ -214,6 +215,16 @@ int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int nup, int nbonds, c
                            int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                         double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* Matrix-free handles: the counterpart of the reference's model<T>::MultMv / MultMv2 with matrix_free == true
+ * (src/model.cc:942-1121: every row is recomputed on the fly from the Hamiltonian terms and the Lin tables instead of
+ * being read from a stored matrix).  Same arguments as the generators; nothing but the basis states (8 bytes per row)
+ * and the Lin tables is kept in HBM, so sectors whose stored matrix would not fit (e.g. the Heisenberg chain L = 32,
+ * Sz = 0: 601,080,390 states, 238 GB of CSR) still run on one GPU.  The handle works with every entry point above
+ * (products, fused Lanczos / CG / KPM loops) and gives the same results as the stored matrix up to summation order. */
+int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
+                                    int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
+                                 double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 /* dimension of those sectors (host only) */
 int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);

@@ -303,6 +303,160 @@ static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     return QBGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ matrix-free
+// The product with no stored matrix: one thread per row (32 consecutive rows per warp, like the sliced-jagged
+// kernel, so one Hamiltonian term sends the lanes of a warp to neighbouring columns), the row's entries regenerated by
+// row_entries() and consumed at once.  The reference's counterpart is model<T>::MultMv2 with matrix_free == true
+// (src/model.cc:942-1109): same per-row recomputation, same Lin-table lookup j = Ja[i_a] + Jb[i_b] (:985-988).
+struct MatFree {
+    SectorTables S;                 // device pointers into the arrays below
+    ModelParams *d_M = nullptr;
+    int64_t *d_Jb = nullptr;
+    int32_t *d_rank = nullptr, *d_off = nullptr;
+    uint32_t *d_alist = nullptr;
+    uint2 *d_states = nullptr;      // (la, lb) of every local row
+    int64_t bytes = 0;
+};
+
+__global__ void __launch_bounds__(kBBlock) matfree_states_kernel(SectorTables S, int64_t row_lo, int64_t nloc, uint2 *states)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t la, lb;
+        unrank_row(S, row_lo + r, la, lb);
+        states[r] = make_uint2(la, lb);
+    }
+}
+
+constexpr int kMFBlock = 256;
+
+template <typename VecT, bool DOTS>
+__global__ void __launch_bounds__(kMFBlock, 3)
+spmv_matfree_kernel(SectorTables S, const ModelParams *Mp, const uint2 *__restrict__ states, int64_t nrows, int64_t row_lo,
+                    const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
+                    int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+{
+    using VT = VecTraits<VecT>;
+    __shared__ ModelParams M;
+    for (int k = threadIdx.x; k < (int)(sizeof(ModelParams) / 4); k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    __syncthreads();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+        dot_scale = sx;
+    }
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 st = states[row];
+        VecT acc = VT::zero();
+        const double diag = row_entries(S, M, st.x, st.y, [&](int64_t c, double v) { mac(acc, v, ld_vec(x + c)); });
+        const VecT xi = x[row_lo + row];
+        mac(acc, diag, xi);
+        VecT out = VT::scale(alpha, acc);
+        if (gamma.x != 0.0 || gamma.y != 0.0) out = VT::add(out, VT::scale(gamma, xi));
+        if (use_beta) out = VT::add(out, VT::scale(beta, z[row]));
+        y[row] = out;
+        if (DOTS) {
+            const double2 p = VT::conj_mul(xi, out);
+            d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kMFBlock>(d, partials, ticket, dots_out);
+    }
+}
+
+template <typename VecT, bool DOTS>
+static int launch_matfree_variant(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    Context &c = ctx();
+    const MatFree *mf = (const MatFree *)A->mf;
+    auto kern = spmv_matfree_kernel<VecT, DOTS>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMFBlock, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int64_t nrows = A->nrows();
+    if (nrows == 0) return QBGPU_OK;
+    int64_t want = (nrows + kMFBlock - 1) / kMFBlock;
+    int64_t cap = (int64_t)c.num_sms * blocks_per_sm;
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    const int grid = (int)(want < cap ? want : cap);
+    kern<<<grid, kMFBlock, 0, c.stream>>>(mf->S, mf->d_M, mf->d_states, nrows, A->row_lo, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                          a.alpha, a.gamma, a.beta, a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    const bool dots = a.dots != nullptr;
+    if (A->api_complex) return dots ? launch_matfree_variant<double2, true>(A, a) : launch_matfree_variant<double2, false>(A, a);
+    return dots ? launch_matfree_variant<double, true>(A, a) : launch_matfree_variant<double, false>(A, a);
+}
+
+void matfree_destroy(qbgpu_matrix *A)
+{
+    MatFree *mf = (MatFree *)A->mf;
+    if (!mf) return;
+    cudaFree(mf->d_M); cudaFree(mf->d_Jb); cudaFree(mf->d_rank); cudaFree(mf->d_off); cudaFree(mf->d_alist); cudaFree(mf->d_states);
+    delete mf;
+    A->mf = nullptr;
+}
+
+static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int64_t row_lo, int64_t row_hi)
+{
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    if (T.dim <= 0) return fail(QBGPU_ERR_ARG, "matrix-free: empty sector");
+    if (T.dim > 2147483647LL) return fail(QBGPU_ERR_ARG, "matrix-free: dimension exceeds the int32 column range");
+    if (row_hi < 0) row_hi = T.dim;
+    if (row_lo < 0 || row_lo > row_hi || row_hi > T.dim) return fail(QBGPU_ERR_ARG, "matrix-free: bad row shard");
+    const int64_t nloc = row_hi - row_lo;
+    auto *A = new qbgpu_matrix;
+    A->n = T.dim; A->row_lo = row_lo; A->row_hi = row_hi; A->api_complex = api_complex != 0;
+    A->val_real = true; A->format = QBGPU_FORMAT_MATFREE; A->nnz = 0; A->nnz_input = 0;
+    auto *mf = new MatFree;
+    A->mf = mf;
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&mf->d_Jb, sizeof(int64_t) * T.Jb.size()));
+    QB_CU(cudaMalloc(&mf->d_rank, sizeof(int32_t) * T.rankA.size()));
+    QB_CU(cudaMalloc(&mf->d_alist, sizeof(uint32_t) * T.alist.size()));
+    QB_CU(cudaMalloc(&mf->d_off, sizeof(int32_t) * T.class_off.size()));
+    QB_CU(cudaMalloc(&mf->d_M, sizeof(ModelParams)));
+    QB_CU(cudaMalloc(&mf->d_states, sizeof(uint2) * (nloc ? nloc : 1)));
+    QB_CU(cudaMemcpyAsync(mf->d_Jb, T.Jb.data(), sizeof(int64_t) * T.Jb.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(mf->d_rank, T.rankA.data(), sizeof(int32_t) * T.rankA.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(mf->d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(mf->d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(mf->d_M, &M, sizeof(ModelParams), cudaMemcpyHostToDevice, c.stream));
+    SectorTables &S = mf->S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = mf->d_Jb; S.rankA = mf->d_rank; S.alist = mf->d_alist; S.class_off = mf->d_off; S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    int64_t g = (nloc + kBBlock - 1) / kBBlock;
+    if (g < 1) g = 1;
+    if (g > 148 * 64) g = 148 * 64;
+    matfree_states_kernel<<<(int)g, kBBlock, 0, c.stream>>>(S, row_lo, nloc, mf->d_states);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+#undef QB_CU
+    mf->bytes = (int64_t)(sizeof(uint2) * nloc + sizeof(int64_t) * T.Jb.size() + 4 * (T.rankA.size() + T.alist.size() + T.class_off.size()) + sizeof(ModelParams));
+    *out = A;
+    return QBGPU_OK;
+}
+
+int64_t matfree_bytes(const qbgpu_matrix *A) { return A->mf ? ((const MatFree *)A->mf)->bytes : 0; }
+
 }  // namespace qb
 
 using namespace qb;
@@ -321,6 +475,32 @@ int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn)
     HostTables T;
     if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || make_tables(nsites, 2, nup, ndn, T)) return -1;
     return T.dim;
+}
+
+int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
+                                    int api_complex, int flags, int64_t row_lo, int64_t row_hi)
+{
+    (void)flags;
+    if (nsites < 2 || ndown < 0 || ndown > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "create_matfree_heisenberg: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 1, ndown, 0, T));
+    static thread_local ModelParams M;
+    M.kind = 0; M.J = J; M.t = 0; M.U = 0;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    return create_matfree(A, T, M, api_complex, row_lo, row_hi);
+}
+
+int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U,
+                                 int api_complex, int flags, int64_t row_lo, int64_t row_hi)
+{
+    (void)flags;
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "create_matfree_hubbard: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 2, nup, ndn, T));
+    static thread_local ModelParams M;
+    M.kind = 1; M.J = 0; M.t = t; M.U = U;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    return create_matfree(A, T, M, api_complex, row_lo, row_hi);
 }
 
 int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,

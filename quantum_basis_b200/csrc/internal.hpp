@@ -30,6 +30,9 @@ struct qbgpu_matrix {
     // of 1-byte codes into vdict[ndict]; products decode through shared memory and are bit-identical.
     double  *vdict = nullptr;
     int      ndict = 0;
+    // QBGPU_FORMAT_MATFREE: no stored entries at all; `mf` owns the sector tables, the bond list and the per-row
+    // basis states from which every row is regenerated inside the product (builders.cu).
+    void    *mf = nullptr;
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
@@ -58,12 +61,19 @@ int sjds_convert(qbgpu_matrix *A, bool forward);
 int value_dict_encode(qbgpu_matrix *A);               // matrix.cu: try to replace fp64 values by 1-byte codes
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);
 void set_sjds_variant(int v);
+int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &args);     // builders.cu
+void matfree_destroy(qbgpu_matrix *A);
+int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // vecops.cu
 int vec_dotc(int64_t n, bool cplx, const void *x, const void *y, double *out_dev3);   // out: re, im, (unused)
+int vec_dotc_scaled(int64_t n, bool cplx, const void *x, const void *y, double *out_dev3, const double *scale_dev);
 int vec_nrm2sq(int64_t n, bool cplx, const void *x, double *out_dev);
+// Lanczos step a on one (block of a) handle: w = sx*H*ux - b*sz*uz (first) or w += sx*H_p*ux (later blocks) written to uz;
+// when `last`, state[3] = sum Re conj(sx*ux_i) w_i over the local rows.
+int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last);
 int vec_axpy(int64_t n, bool cplx, double2 a, const void *x, void *y);
 int vec_scal(int64_t n, bool cplx, double2 a, void *x);
 int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed);

@@ -160,10 +160,8 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
         // one fused Lanczos step (src/lanczos.cc:167-187 for m == 1, :194-214 otherwise)
         const void *ux = Ubuf[(m - 1) % 2];
         void *uz = Ubuf[m % 2];
-        FusedArgs fa;
-        fa.x = ux; fa.z = uz; fa.y = uz; fa.scal_mode = 1; fa.sc = state; fa.beta = make_double2(1.0, 0.0); fa.dots = state + 3;
         if (prof) QB_CUDA(cudaEventRecord(pe[0], c.stream));
-        QB_TRY(launch_spmv(A, fa));
+        QB_TRY(lanczos_step_a(A, ux, uz, state, true, true));
         if (prof) QB_CUDA(cudaEventRecord(pe[1], c.stream));
         QB_TRY(lanczos_step_b(n, cplx, ux, uz, state));
         if (prof) QB_CUDA(cudaEventRecord(pe[2], c.stream));

@@ -364,7 +364,7 @@ static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbg
     if (!A || !bounds || !out || nparts < 1 || nparts > kMaxParts) return fail(QBGPU_ERR_ARG, "split_columns: bad argument (1..16 parts)");
     if (bounds[0] != 0 || bounds[nparts] != A->n) return fail(QBGPU_ERR_ARG, "split_columns: bounds must run from 0 to n");
     for (int p = 0; p < nparts; p++) if (bounds[p + 1] < bounds[p]) return fail(QBGPU_ERR_ARG, "split_columns: bounds must be non-decreasing");
-    if (A->ndict) return fail(QBGPU_ERR_STATE, "split_columns: not available for dictionary-coded handles");
+    if (A->ndict || A->mf) return fail(QBGPU_ERR_STATE, "split_columns: not available for dictionary-coded or matrix-free handles");
     const bool was_jagged = (A->format == QBGPU_FORMAT_SELL);
     QB_TRY(sjds_convert(A, false));                         // needs plain CSR order (restored below)
     const int64_t nloc = A->nrows();
@@ -433,6 +433,7 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
+    if (!A->borrowed) matfree_destroy(A);
     if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); }
     delete A;
     return QBGPU_OK;
@@ -445,7 +446,7 @@ int qbgpu_matrix_get_info(qbgpu_matrix_t A, qbgpu_matrix_info *info)
     info->nnz_stored = A->nnz; info->nnz_input = A->nnz_input;
     info->val_is_real = A->val_real; info->value_dict = A->ndict; info->api_is_complex = A->api_complex;
     info->format = A->format; info->lanes = A->lanes;
-    info->device_bytes = (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
+    info->device_bytes = A->mf ? matfree_bytes(A) : (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
     info->upload_seconds = A->upload_s; info->convert_seconds = A->convert_s; info->autotune_seconds = A->autotune_s;
     return QBGPU_OK;
 }
@@ -454,6 +455,7 @@ int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, voi
 {
     QB_TRY(ensure_init());
     if (!A || !rowptr || !col || !val) return fail(QBGPU_ERR_ARG, "null argument");
+    if (A->mf) return fail(QBGPU_ERR_STATE, "matrix-free handle: there are no stored entries to download");
     const bool jag = (A->format == QBGPU_FORMAT_SELL);      // hand back plain CSR order whatever the resident layout
     if (jag) QB_TRY(sjds_convert(A, false));
     QB_CUDA(cudaStreamSynchronize(ctx().stream));

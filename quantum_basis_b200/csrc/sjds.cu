@@ -226,8 +226,8 @@ static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
 // production configuration of the template (chosen from the measurements in profiles/)
 // complex vectors: 4 diagonals per trip, branchy tail, 4 blocks/SM; fp64 vectors: 8 per trip, unconditional loads
 // (scripts/kbench.py sweeps, profiles/r01_kbench_*.txt)
-template <typename VecT> struct Prod { static constexpr int U = 4, S = 2, X = 1, MinB = 4; static constexpr bool UL = false; };
-template <> struct Prod<double> { static constexpr int U = 8, S = 2, X = 0, MinB = 4; static constexpr bool UL = true; };
+template <typename VecT> struct Prod { static constexpr int U = 4, S = 2, X = 1, MinB = 4, DotsMinB = 4; static constexpr bool UL = false; };
+template <> struct Prod<double> { static constexpr int U = 8, S = 2, X = 0, MinB = 4, DotsMinB = 3; static constexpr bool UL = true; };
 
 template <typename ValT, typename VecT>
 static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
@@ -264,7 +264,8 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
     }
 #endif
     using P = Prod<VecT>;
-    return dots ? launch_sjds_variant<ValT, VecT, true, P::U, P::S, P::X, P::UL, P::MinB>(A, a)
+    // (with fp64 vectors the epilogue variant needs a few more registers: 3 blocks/SM keeps its loads batched)
+    return dots ? launch_sjds_variant<ValT, VecT, true, P::U, P::S, P::X, P::UL, P::DotsMinB>(A, a)
                 : launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB>(A, a);
 }
 

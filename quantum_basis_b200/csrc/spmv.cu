@@ -123,6 +123,7 @@ static int launch_lanes(const qbgpu_matrix *A, const FusedArgs &a, int lanes)
 
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
 {
+    if (A->format == QBGPU_FORMAT_MATFREE) return launch_spmv_matfree(A, a);
     if (A->format == QBGPU_FORMAT_SELL) return launch_spmv_sjds(A, a);
     if (A->ndict) return fail(QBGPU_ERR_STATE, "dictionary-coded values need the sliced-jagged layout");
     const int lanes = lanes_override ? lanes_override : A->lanes;
@@ -278,6 +279,23 @@ static int mv_any(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, v
     return launch_spmv(A, a);
 }
 
+int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last)
+{
+    FusedArgs a;
+    a.x = ux_full; a.z = uz_local; a.y = uz_local;
+    a.scal_mode = first ? 1 : 2; a.sc = state;
+    a.beta = make_double2(1.0, 0.0);                       // placeholder: the kernel derives beta from the state
+    // complex vectors: the dot rides in the product's epilogue (+0.5 ms on BASELINE config 3).  fp64 vectors: the
+    // epilogue variant of the kernel costs 2-4 ms there (profiles/r01_kbench_fused_*.txt) while a separate pass over
+    // the two local vectors costs 0.45 ms, so the dot is a second kernel.
+    const bool fuse_dot = A->api_complex;
+    a.dots = (last && fuse_dot) ? state + 3 : nullptr;     // state[3]=alpha partial, [4]=Im (unused), [5]=|w|^2 (unused)
+    QB_TRY(launch_spmv(A, a));
+    if (last && !fuse_dot)
+        QB_TRY(vec_dotc_scaled(A->nrows(), false, (const double *)ux_full + A->row_lo, uz_local, state + 3, state + 0));
+    return QBGPU_OK;
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -314,13 +332,7 @@ int qbgpu_lanczos_step_a_part(qbgpu_matrix_t A, const void *ux_full, void *uz_lo
 {
     QB_TRY(ensure_init());
     if (!A || !ux_full || !uz_local || !state_dev) return fail(QBGPU_ERR_ARG, "null argument");
-    FusedArgs a;
-    a.x = ux_full; a.z = uz_local; a.y = uz_local;
-    a.scal_mode = first ? 1 : 2; a.sc = state_dev;
-    a.beta = make_double2(1.0, 0.0);                       // placeholder: the kernel derives beta from the state
-    a.dots = last ? state_dev + 3 : nullptr;               // state[3]=alpha partial, [4]=Im (unused), [5]=|w|^2 (unused)
-    QB_TRY(launch_spmv(A, a));
-    return QBGPU_OK;
+    return lanczos_step_a(A, ux_full, uz_local, state_dev, first != 0, last != 0);
 }
 
 int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, double *state_dev)

@@ -26,11 +26,12 @@ static int vec_grid(int64_t n)
 // ------------------------------------------------------------------------------------- dot / nrm2 / axpy / scal
 template <typename VecT>
 __global__ void __launch_bounds__(kVBlock, 4) dotc_kernel(int64_t n, const VecT *__restrict__ x, const VecT *__restrict__ y,
-                                                       double *out, double *partials, unsigned *ticket)
+                                                       double *out, double *partials, unsigned *ticket, const double *scale_dev)
 {
     using VT = VecTraits<VecT>;
     double d[3] = {0.0, 0.0, 0.0};
     GRID_STRIDE(i, n) { const VecT xi = x[i], yi = y[i]; const double2 p = VT::conj_mul(xi, yi); d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(yi); }
+    if (scale_dev) { const double s = *scale_dev; d[0] *= s; d[1] *= s; }      // <s*x, y> for an unnormalised x
     block_reduce_finalize<3, kVBlock>(d, partials, ticket, out);
 }
 template <typename VecT>
@@ -70,13 +71,14 @@ __global__ void __launch_bounds__(kVBlock, 4) scale_copy_kernel(int64_t n, const
         QB_CUDA(cudaGetLastError());                                              \
     } while (0)
 
-int vec_dotc(int64_t n, bool cplx, const void *x, const void *y, double *out3)
+int vec_dotc_scaled(int64_t n, bool cplx, const void *x, const void *y, double *out3, const double *scale_dev)
 {
     Context &c = ctx();
-    if (cplx) LAUNCH_V(dotc_kernel<double2>, n, n, (const double2 *)x, (const double2 *)y, out3, c.partials, c.ticket);
-    else      LAUNCH_V(dotc_kernel<double>, n, n, (const double *)x, (const double *)y, out3, c.partials, c.ticket);
+    if (cplx) LAUNCH_V(dotc_kernel<double2>, n, n, (const double2 *)x, (const double2 *)y, out3, c.partials, c.ticket, scale_dev);
+    else      LAUNCH_V(dotc_kernel<double>, n, n, (const double *)x, (const double *)y, out3, c.partials, c.ticket, scale_dev);
     return QBGPU_OK;
 }
+int vec_dotc(int64_t n, bool cplx, const void *x, const void *y, double *out3) { return vec_dotc_scaled(n, cplx, x, y, out3, nullptr); }
 int vec_nrm2sq(int64_t n, bool cplx, const void *x, double *out)
 {
     Context &c = ctx();

@@ -204,6 +204,36 @@ class csr_mat:
             pass
 
 
+def _bond_array(bonds):
+    b = np.ascontiguousarray(np.asarray(bonds, dtype=np.int32).reshape(-1, 2))
+    return b, b.shape[0]
+
+
+def heisenberg(nsites, ndown, bonds, J=1.0, is_complex=True, flags=0, rows=None, matrix_free=False):
+    """Spin-1/2 Heisenberg model H = J sum_<ij> S_i.S_j in the sector with `ndown` down spins (Sz_total = nsites/2 - ndown),
+    in the reference's Lin-table basis order.  Stored (the matrix model::generate_Ham_sparse_full would assemble,
+    src/model.cc:619-686, generated directly in HBM) or matrix_free (the counterpart of model::MultMv2 with
+    matrix_free == true, src/model.cc:942-1109).  Returns a csr_mat."""
+    b, nb = _bond_array(bonds)
+    h = C.c_void_p()
+    lo, hi = (0, -1) if rows is None else (int(rows[0]), int(rows[1]))
+    f = lib().qbgpu_create_matfree_heisenberg if matrix_free else lib().qbgpu_build_heisenberg
+    check(f(C.byref(h), nsites, ndown, nb, C.c_void_p(b.ctypes.data), float(J), int(is_complex), flags, lo, hi))
+    return csr_mat._adopt(h, is_complex)
+
+
+def hubbard(nsites, nup, ndn, bonds, t=1.0, U=0.0, is_complex=True, flags=0, rows=None, matrix_free=False):
+    """Single-orbital Fermi-Hubbard model H = -t sum_<ij>,s (c+_is c_js + h.c.) + U sum_i n_up n_dn with N_up, N_dn fixed,
+    in the reference's Lin-table basis order and fermion-sign convention (src/basis.cc:2717-2731).  Stored or
+    matrix_free as for heisenberg()."""
+    b, nb = _bond_array(bonds)
+    h = C.c_void_p()
+    lo, hi = (0, -1) if rows is None else (int(rows[0]), int(rows[1]))
+    f = lib().qbgpu_create_matfree_hubbard if matrix_free else lib().qbgpu_build_hubbard
+    check(f(C.byref(h), nsites, nup, ndn, nb, C.c_void_p(b.ctypes.data), float(t), float(U), int(is_complex), flags, lo, hi))
+    return csr_mat._adopt(h, is_complex)
+
+
 def vec_randomize(n, seed=1, dtype=np.complex128, device=False):
     """src/miscellaneous.cc:371-388, generated on the device."""
     v = DeviceVector(n, dtype)

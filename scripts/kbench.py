@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--ids", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
+    ap.add_argument("--matfree", action="store_true", help="time the matrix-free product instead of a stored layout")
     ap.add_argument("--fused", action="store_true", help="time the fused-epilogue variants of the production kernel")
     ap.add_argument("--dict", action="store_true", help="1-byte value codes (QBGPU_VALUE_DICT)")
     ap.add_argument("--far", default="", help="comma list of log2(far_rows) to sweep for the adaptive-policy variants")
@@ -53,16 +54,20 @@ def main():
     flags = 8 | 2 | (16 if a.dict else 0)          # sliced-jagged, no autotune
     if fam == "hubbard":
         bonds = np.array(bench.square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
-        rc = L.qbgpu_build_hubbard(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data, p["t"], p["U"], cplx, flags, 0, -1)
+        f = L.qbgpu_create_matfree_hubbard if a.matfree else L.qbgpu_build_hubbard
+        rc = f(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data, p["t"], p["U"], cplx, flags, 0, -1)
     else:
         n = p["L"]
         bonds = np.array([(x, (x + 1) % n) for x in range(n)], dtype=np.int32).ravel()
-        rc = L.qbgpu_build_heisenberg(C.byref(h), n, n // 2, n, bonds.ctypes.data, 1.0, cplx, flags, 0, -1)
+        f = L.qbgpu_create_matfree_heisenberg if a.matfree else L.qbgpu_build_heisenberg
+        rc = f(C.byref(h), n, n // 2, n, bonds.ctypes.data, 1.0, cplx, flags, 0, -1)
     assert rc == 0, L.qbgpu_last_error()
     M = qb.csr_mat._adopt(h, bool(cplx))
     torch.cuda.synchronize()
     inf = M.info
     n, Z = inf.n, inf.nnz_stored
+    if a.matfree:
+        Z = 2 * bench.workload_upper_nnz(a.workload) - n        # entries regenerated per product
     s_vec = 16 if cplx else 8
     s_val = 1 if inf.value_dict else 8
     B = bench.algorithmic_bytes(Z, n, n, s_val, s_vec)

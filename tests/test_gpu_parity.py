@@ -451,6 +451,65 @@ def test_device_generators_match_the_reference_matrix(oracle, case):
         assert np.array_equal(rowptr, rp2) and np.array_equal(col, c2) and np.array_equal(v, v2)
 
 
+@pytest.mark.parametrize("case", ["heis12", "heis15", "hub4x2", "hub3x3"])
+def test_matrix_free_product_equals_the_stored_matrix(oracle, case):
+    """The device counterpart of model::MultMv2 with matrix_free == true (src/model.cc:942-1109): no stored H."""
+    from oracle_lib import Csr
+    if case == "heis12":
+        bonds = B.chain_bonds(12); n, ia, ja, val = B.heisenberg_upper_csr(12, 6, bonds)
+        mk = lambda mf, cx=True: qb.heisenberg(12, 6, bonds, 1.0, is_complex=cx, matrix_free=mf)      # noqa: E731
+    elif case == "heis15":
+        bonds = B.chain_bonds(15); n, ia, ja, val = B.heisenberg_upper_csr(15, 7, bonds)
+        mk = lambda mf, cx=True: qb.heisenberg(15, 7, bonds, 1.0, is_complex=cx, matrix_free=mf)      # noqa: E731
+    elif case == "hub4x2":
+        bonds = B.square_bonds(4, 2); n, ia, ja, val = B.hubbard_upper_csr(8, 4, 4, bonds, 1.0, 1.1)
+        mk = lambda mf, cx=True: qb.hubbard(8, 4, 4, bonds, 1.0, 1.1, is_complex=cx, matrix_free=mf)  # noqa: E731
+    else:
+        bonds = B.square_bonds(3, 3); n, ia, ja, val = B.hubbard_upper_csr(9, 4, 5, bonds, 1.0, 2.3)
+        mk = lambda mf, cx=True: qb.hubbard(9, 4, 5, bonds, 1.0, 2.3, is_complex=cx, matrix_free=mf)  # noqa: E731
+    A = Csr(n, ia, ja, val, True)
+    F = mk(True)
+    assert F.info.format == 32 and F.info.nnz_stored == 0 and F.dim == n
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    y = np.zeros(n, dtype=np.complex128)
+    F.MultMv(x, y)
+    assert rel_l2(y, oracle.spmv_ld(A, x)) <= TOL_MV                 # vs the reference-identical matrix on the CPU
+    ys = np.zeros(n, dtype=np.complex128)
+    mk(False).MultMv(x, ys)
+    assert rel_l2(y, ys) <= 1e-14                                    # vs the stored device matrix
+    y2 = y.copy()
+    F.MultMv2(x, y2)
+    assert rel_l2(y2, 2 * y) <= 1e-14
+    # fp64 handle and the fused loops on the matrix-free handle
+    Fd = mk(True, False)
+    xr = rng.normal(size=n); yr = np.zeros(n)
+    Fd.MultMv(xr, yr)
+    assert rel_l2(yr, oracle.spmv_ld(A, xr).real) <= TOL_MV
+    out_f = qb.locate_E0_lanczos(F, nev=1, ncv=1)
+    out_s = qb.locate_E0_lanczos(mk(False), nev=1, ncv=1)
+    assert abs(out_f["eigenvals"][0] - out_s["eigenvals"][0]) <= TOL_E0 * abs(out_s["eigenvals"][0])
+    v = out_f["eigenvecs"][0]
+    assert np.linalg.norm(oracle.spmv(A, v) - out_f["eigenvals"][0] * v) < 1e-8
+    with pytest.raises(qb.QbgpuError):
+        F.download_expanded()
+
+
+def test_matrix_free_config1_and_a_sector_too_large_to_store(oracle):
+    """BASELINE config 1 through the matrix-free handle (E0 = -8.9043865298764 from the compiled reference), and the uniform
+    vector check (H 1 = L/4 * 1 in any Sz sector) on the Heisenberg chain L = 30, Sz = 0: 155,117,520 states whose stored
+    matrix would take 57 GB; the matrix-free handle keeps 1.2 GB."""
+    F = qb.heisenberg(20, 10, B.chain_bonds(20), 1.0, matrix_free=True)
+    out = qb.locate_E0_lanczos(F, nev=1, ncv=0)
+    assert abs(out["eigenvals"][0] + 8.9043865298764) <= TOL_E0 * 8.9043865298764
+    L30 = qb.heisenberg(30, 15, B.chain_bonds(30), 1.0, is_complex=False, matrix_free=True)
+    n = L30.dim
+    assert n == 155117520 and L30.info.device_bytes < 1.5e9
+    ones = qb.DeviceVector.from_numpy(np.ones(n)); y = qb.DeviceVector(n, np.float64)
+    L30.MultMv(ones, y)
+    assert np.abs(y.to_numpy() - 7.5).max() < 1e-12
+
+
 def test_config1_heisenberg_L20_E0(oracle):
     """BASELINE config 1: Heisenberg chain L=20, Sz=0 (dim 184,756); E0 from the compiled reference = -8.9043865298764
     in 77 steps (SURVEY.md section 6 / BASELINE.md section 3)."""

@@ -163,6 +163,16 @@ int qbgpu_energy_scale_z(qbgpu_matrix_t A, void *v, double *lo, double *hi, doub
 int qbgpu_energy_scale_d(qbgpu_matrix_t A, double *v, double *lo, double *hi, double extend, int64_t iters, int where);
 int qbgpu_kpm_moments_z(qbgpu_matrix_t A, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where);
 int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double hi, int64_t nmom, double *mu, int where);
+/* Device-resident thick-restart Lanczos for the `nev` eigenpairs of smallest algebraic value with a basis of `ncv`
+ * vectors kept in HBM: the contract of iram<T,MAT>() / model<T>::locate_E0_iram (src/lanczos.cc:497-603,
+ * src/model.cc:1320-1366; maxit <= 0 -> nev*100 restarts, tol <= 0 -> machine precision) without the PCIe round trip
+ * ARPACK's reverse communication costs per product.  eigenvals[nev] ascending; eigenvecs (may be NULL) nev vectors of
+ * length n, HOST or DEVICE per `where`, element type of the handle.  *nconv = converged pairs, *nprod = products used. */
+int qbgpu_trlan(qbgpu_matrix_t A, int nev, int ncv, int maxit, double tol, int *nconv, int *nprod, double *eigenvals,
+                void *eigenvecs, int where);
+/* host-side dense Hermitian eigensolver used for the projected matrix (cyclic complex Jacobi): a and s are m x m complex,
+ * column-major; w ascending, columns of s are the eigenvectors */
+int qbgpu_herm_eigen(int m, const void *a_colmajor, double *w, void *s_colmajor);
 /* hess_eigen (src/lanczos.cc:355-390, order "sr"): host-side tridiagonal Ritz solve used by the stop rule.
  * ritz[m]; s[m*m] column-major eigenvectors or NULL. */
 int qbgpu_hess_eigen(const double *hessenberg, int64_t maxit, int64_t m, double *ritz, double *s);

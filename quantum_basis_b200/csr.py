@@ -348,12 +348,42 @@ def iram(dim, mat, v0, nev, ncv, maxit, order="sr"):
     return len(w), w[idx], U[:, idx]
 
 
-def locate_E0_iram(mat, nev=2, ncv=6, maxit=0):
-    """The csr_mat branch of model<T>::locate_E0_iram (src/model.cc:1320-1366): returns dict(eigenvals, eigenvecs, nconv, gap)."""
+def trlan(mat, nev, ncv, maxit=0, tol=0.0, vectors=True):
+    """Device-resident thick-restart Lanczos (qbgpu_trlan): the `nev` lowest eigenpairs with `ncv` basis vectors in HBM.
+    Returns (nconv, eigenvals[nev], eigenvecs[n, nev] or None, products)."""
+    w = np.zeros(nev)
+    U = np.zeros(mat.dim * nev, dtype=mat.dtype) if vectors else None
+    nconv, nprod = C.c_int(0), C.c_int(0)
+    check(lib().qbgpu_trlan(mat.handle, nev, ncv, maxit, tol, C.byref(nconv), C.byref(nprod), _ptr(w),
+                            _ptr(U) if vectors else None, _lib.QBGPU_HOST))
+    return nconv.value, w, (U.reshape(nev, mat.dim).T if vectors else None), nprod.value
+
+
+def herm_eigen(a):
+    """Host dense Hermitian eigensolver used by trlan for the projected matrix (complex Jacobi)."""
+    a = np.asarray(a, dtype=np.complex128)
+    m = a.shape[0]
+    acm = np.asfortranarray(a).ravel(order="F").copy()
+    w = np.zeros(m)
+    s = np.zeros(m * m, dtype=np.complex128)
+    check(lib().qbgpu_herm_eigen(m, _ptr(acm), _ptr(w), _ptr(s)))
+    return w, s.reshape(m, m, order="F")
+
+
+def locate_E0_iram(mat, nev=2, ncv=6, maxit=0, device_resident=False):
+    """The csr_mat branch of model<T>::locate_E0_iram (src/model.cc:1320-1366): returns dict(eigenvals, eigenvecs, nconv, gap).
+    device_resident=False: ARPACK on the host calling MultMv per product (the reference's data flow);
+    device_resident=True: the same contract served by the thick-restart Lanczos that keeps the basis in HBM."""
     if not (nev > 0 and ncv > nev + 1):
         raise QbgpuError("need nev > 0 and ncv > nev + 1")                        # the reference's asserts, :1337-1338
     if maxit <= 0:
         maxit = nev * 100                                                        # :1339
+    if device_resident and mat.dim > 30:
+        nconv, w, U, nprod = trlan(mat, nev, ncv, maxit)
+        out = {"eigenvals": list(w), "eigenvecs": [U[:, j].copy() for j in range(nev)], "nconv": nconv, "products": nprod}
+        if nev > 1:
+            out["gap"] = w[1] - w[0]
+        return out
     v0 = np.ones(mat.dim, dtype=mat.dtype)                                       # :1352 (ARPACK ignores it with info = 0)
     nconv, w, U = iram(mat.dim, mat, v0, nev, ncv, maxit, "sr")
     out = {"eigenvals": list(w), "eigenvecs": [U[:, j].copy() for j in range(U.shape[1])], "nconv": nconv}

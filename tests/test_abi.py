@@ -96,3 +96,17 @@ def test_hess_eigen_host(L):
     assert np.abs(Tm @ s - s * ritz[None, :]).max() < 1e-12
     with pytest.raises(qb.QbgpuError):
         qb.hess_eigen(hess, maxit, maxit)          # the reference asserts m < maxit (src/lanczos.cc:358)
+
+
+def test_herm_eigen_host(L):
+    rng = np.random.default_rng(4)
+    for m in (1, 2, 3, 8, 24):
+        X = rng.normal(size=(m, m)) + 1j * rng.normal(size=(m, m))
+        A = X + X.conj().T
+        if m == 8:                                   # a degenerate pair and a real-symmetric case
+            A = np.diag([1.0, 1.0, 2.0, 3.0, 3.0, 3.0, -1.0, 0.5]).astype(np.complex128)
+            Q, _ = np.linalg.qr(X); A = Q @ A @ Q.conj().T
+        w, S = qb.herm_eigen(A)
+        assert np.abs(w - np.linalg.eigvalsh(A)).max() < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.abs(A @ S - S * w[None, :]).max() < 1e-11 * max(1.0, np.abs(A).max())
+        assert np.abs(S.conj().T @ S - np.eye(m)).max() < 1e-12

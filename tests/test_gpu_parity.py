@@ -208,6 +208,56 @@ def test_row_shards_reproduce_the_full_product(oracle):
         assert rel_l2(np.concatenate(ys), ex["y1"]) <= TOL_MV
 
 
+@pytest.mark.parametrize("name,nparts", [("tj12", 8), ("heis16_full", 8), ("heis16_full", 3), ("tri4x4_k12", 5)])
+def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts):
+    """qbgpu_split_columns + qbgpu_lanczos_step_a_part (what every rank does in the overlapped multi-GPU exchange) on ONE
+    GPU: the per-owner column blocks, multiplied one after the other with the accumulate flags, must give the same w and
+    the same alpha as the unsplit fused step -- for complex and for fp64 (real-view) vectors."""
+    import ctypes as C
+    A, meta, ex = oracle.load_golden(name)
+    L = qb.lib()
+    n = A.dim
+    M = make(A)
+    chunk = (n + nparts - 1) // nparts
+    bounds = np.array([min(n, p * chunk) for p in range(nparts)] + [n], dtype=np.int64)
+    hs = (C.c_void_p * nparts)()
+    assert L.qbgpu_split_columns(M.handle, nparts, bounds.ctypes.data, hs, 0) == 0, L.qbgpu_last_error()
+    parts = [qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
+    assert sum(p.info.nnz_stored for p in parts) == M.info.nnz_stored
+    real_ok = bool(M.info.val_is_real)
+    for real in ([False, True] if real_ok else [False]):
+        dt = np.float64 if real else np.complex128
+        H = M.real_view() if real else M
+        P = [p.real_view() for p in parts] if real else parts
+        rng = np.random.default_rng(3)
+        ux = rng.normal(size=n) if real else rng.normal(size=n) + 1j * rng.normal(size=n)
+        uz0 = rng.normal(size=n) if real else rng.normal(size=n) + 1j * rng.normal(size=n)
+        state0 = np.array([0.7, 1.3, 0.9, 0, 0, 0, 0, 0], dtype=np.float64)       # sx, sz, b_prev
+        dux = qb.DeviceVector.from_numpy(ux.astype(dt))
+        # unsplit
+        duz = qb.DeviceVector.from_numpy(uz0.astype(dt)); st = qb.DeviceVector.from_numpy(state0)
+        assert L.qbgpu_lanczos_step_a(H.handle, C.c_void_p(dux.ptr), C.c_void_p(duz.ptr), C.c_void_p(st.ptr)) == 0
+        w_ref, a_ref = duz.to_numpy(), st.to_numpy()[3]
+        w_exact = 0.7 * oracle.spmv_ld(A, ux) - 0.9 * 1.3 * uz0
+        assert rel_l2(w_ref, w_exact if not real else w_exact.real) <= TOL_MV
+        assert abs(a_ref - np.real(np.vdot(0.7 * ux, w_ref))) <= 1e-12 * abs(a_ref)
+        # per-owner blocks, own block first (rank r = 2 of nparts), the others in ring order
+        order = [2 % nparts] + [(2 + d) % nparts for d in range(1, nparts)]
+        duz2 = qb.DeviceVector.from_numpy(uz0.astype(dt)); st2 = qb.DeviceVector.from_numpy(state0)
+        for idx, p in enumerate(order):
+            rc = L.qbgpu_lanczos_step_a_part(P[p].handle, C.c_void_p(dux.ptr), C.c_void_p(duz2.ptr), C.c_void_p(st2.ptr),
+                                             int(idx == 0), int(idx == nparts - 1))
+            assert rc == 0, L.qbgpu_last_error()
+        w_blk, a_blk = duz2.to_numpy(), st2.to_numpy()[3]
+        assert rel_l2(w_blk, w_ref) <= 1e-14
+        assert abs(a_blk - a_ref) <= 1e-12 * abs(a_ref)
+        # and the plain accumulate form (y = sum_p H_p x)
+        y = qb.DeviceVector(n, dt)
+        for idx, p in enumerate(order):
+            P[p]._mv(complex(1.0), dux, complex(1.0 if idx else 0.0), y)
+        assert rel_l2(y.to_numpy(), oracle.spmv_ld(A, ux) if not real else oracle.spmv_ld(A, ux).real) <= TOL_MV
+
+
 # ---------------------------------------------------------------------------------------- vec_randomize
 def test_vec_randomize_is_the_reference_sequence(oracle):
     for n, seed in ((10, 1), (65536, 1), (100003, 8), (7, 0)):
@@ -370,6 +420,33 @@ def test_arpack_callback_seam_tJ_golden(oracle):
     for E, v in zip(out["eigenvals"], out["eigenvecs"]):
         assert np.linalg.norm(oracle.spmv(A, v) - E * v) < 1e-7
     assert qb.iram.last_products > 8
+
+
+def test_device_resident_thick_restart_lanczos(oracle):
+    """qbgpu_trlan: the locate_E0_iram contract with the Krylov basis kept in HBM.  Eigenvalue parity with the reference's
+    ARPACK golden (t-J chain, nev=4, ncv=8: E0 = E1 = -9.762087307, src/main_test.cc:207-208) and with dense
+    diagonalisation; eigenvectors checked through their residuals and orthonormality."""
+    A, meta, ex = oracle.load_golden("tj12")
+    out = qb.locate_E0_iram(make(A), nev=4, ncv=8, device_resident=True)
+    assert out["nconv"] == 4
+    assert abs(out["eigenvals"][0] + 9.762087307) < 1e-8 and abs(out["eigenvals"][1] + 9.762087307) < 1e-8
+    U = np.stack(out["eigenvecs"], axis=1)
+    for j, E in enumerate(out["eigenvals"]):
+        assert np.linalg.norm(oracle.spmv(A, U[:, j]) - E * U[:, j]) < 1e-7
+    assert np.abs(U.conj().T @ U - np.eye(4)).max() < 1e-9
+    host = qb.locate_E0_iram(make(A), nev=4, ncv=8)                            # ARPACK on the host through the MultMv seam
+    assert np.abs(np.array(out["eigenvals"]) - np.array(host["eigenvals"])).max() < 1e-9
+    for name, nev, ncv in (("hubbard4x2", 3, 10), ("tri4x4_k12", 2, 12), ("honeycomb3x2_general", 2, 8)):
+        A, meta, ex = oracle.load_golden(name)
+        w = np.linalg.eigvalsh(A.to_scipy_full().toarray())
+        nconv, ev, U, nprod = qb.trlan(make(A), nev, ncv)
+        assert nconv == nev and np.abs(ev - w[:nev]).max() < 1e-9
+        assert abs(ev[0] - meta["lanczos_E0"]) <= 1e-9 * abs(meta["lanczos_E0"])
+    A, meta, ex = oracle.load_golden("hubbard4x2")                             # csr_mat<double> handle
+    nconv, ev, U, nprod = qb.trlan(make(A.astype(np.float64)), 2, 8)
+    assert nconv == 2 and abs(ev[0] + 14.07605866) < 1e-8 and U.dtype == np.float64
+    with pytest.raises(qb.QbgpuError):
+        qb.trlan(make(A), 4, 5)                                                # the reference asserts ncv > nev + 1
 
 
 def test_iram_small_matrix_uses_dense_fallback(oracle):

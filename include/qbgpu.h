@@ -205,13 +205,14 @@ int qbgpu_lanczos_step_c(double *state_dev, double *a_dev, double *b_dev, int64_
  * with copy-engine transfers, one stream ("lane") per peer, overlapped with the products of the column blocks that
  * have already arrived (quantum_basis_b200/dist.py: PeerExchangeOperator).
  *   ipc_export: 64-byte handle of a qbgpu_malloc'ed buffer;  ipc_open: map a peer's handle -> device pointer
- *   peer_pull_async(lane, dst, src, bytes): enqueue on `lane` a copy ordered after the compute stream's current tail
- *   peer_wait(lane): order the compute stream behind that lane's last pull */
+ *   peer_pull_async(lane, slot, dst, src, bytes): enqueue on copy stream `lane` a transfer ordered after the compute
+ *       stream's current tail; its completion is event `slot` (0..15)
+ *   peer_wait(slot): order the compute stream behind that transfer */
 int qbgpu_ipc_export(void *dptr, void *handle64);
 int qbgpu_ipc_open(const void *handle64, void **peer_ptr);
 int qbgpu_ipc_close(void *peer_ptr);
-int qbgpu_peer_pull_async(int lane, void *dst_local, const void *src_peer, size_t bytes);
-int qbgpu_peer_wait(int lane);
+int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes);
+int qbgpu_peer_wait(int slot);
 
 /* --------------------------------------------------------------------- on-device Hamiltonian generators
  * The reference assembles H on the host (model::generate_Ham_sparse_full, src/model.cc:619-716) in Lin-table

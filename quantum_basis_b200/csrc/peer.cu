@@ -64,28 +64,30 @@ int qbgpu_ipc_close(void *peer_ptr)
     return QBGPU_OK;
 }
 
-/* Enqueue, on copy lane `lane`, a pull of `bytes` from a peer-mapped (or local) source into local memory, ordered after
- * everything issued so far on the compute stream; the arrival is recorded for qbgpu_peer_wait. */
-int qbgpu_peer_pull_async(int lane, void *dst_local, const void *src_peer, size_t bytes)
+/* Enqueue, on copy stream `lane`, a pull of `bytes` from a peer-mapped (or local) source into local memory, ordered
+ * after everything issued so far on the compute stream; its arrival is recorded in event `slot` for qbgpu_peer_wait.
+ * Pulls on one lane run one after the other (each at the full NVLink rate), so the slices arrive in the order the
+ * column blocks are multiplied; several lanes keep more than one transfer in flight. */
+int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes)
 {
     QB_TRY(ensure_init());
     QB_TRY(peer_init());
-    if (lane < 0 || lane >= kPeerLanes || !dst_local || !src_peer) return fail(QBGPU_ERR_ARG, "peer_pull: bad argument");
+    if (lane < 0 || lane >= kPeerLanes || slot < 0 || slot >= kPeerLanes || !dst_local || !src_peer) return fail(QBGPU_ERR_ARG, "peer_pull: bad argument");
     Context &c = ctx();
     QB_CUDA(cudaEventRecord(g_peer.fence, c.stream));
     QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
     QB_CUDA(cudaMemcpyAsync(dst_local, src_peer, bytes, cudaMemcpyDefault, g_peer.lane[lane]));
-    QB_CUDA(cudaEventRecord(g_peer.arrived[lane], g_peer.lane[lane]));
+    QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
     return QBGPU_OK;
 }
 
-/* Order everything issued afterwards on the compute stream behind the last pull of `lane`. */
-int qbgpu_peer_wait(int lane)
+/* Order everything issued afterwards on the compute stream behind the pull recorded in `slot`. */
+int qbgpu_peer_wait(int slot)
 {
     QB_TRY(ensure_init());
     QB_TRY(peer_init());
-    if (lane < 0 || lane >= kPeerLanes) return fail(QBGPU_ERR_ARG, "peer_wait: bad lane");
-    QB_CUDA(cudaStreamWaitEvent(ctx().stream, g_peer.arrived[lane], 0));
+    if (slot < 0 || slot >= kPeerLanes) return fail(QBGPU_ERR_ARG, "peer_wait: bad slot");
+    QB_CUDA(cudaStreamWaitEvent(ctx().stream, g_peer.arrived[slot], 0));
     return QBGPU_OK;
 }
 

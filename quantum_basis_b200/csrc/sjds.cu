@@ -346,13 +346,15 @@ static int sjds_convert_typed(qbgpu_matrix *A, bool forward)
     for (int64_t b = 0; b < nb; b++) {
         const int64_t s0 = b * batch, s1 = std::min(nslices, (b + 1) * batch);
         const int64_t span = bofs[b + 1] - bofs[b];
-        if (span == 0) continue;
+        if (span == 0 && !forward) continue;               // (forward still has to write rowinfo for all-empty slices)
         const int grid = (int)std::min<int64_t>((s1 - s0 + 7) / 8, 148 * 16);
         if (forward) sjds_permute_kernel<ValT, true><<<grid, kSBlock, 0, c.stream>>>(s0, s1, nrows, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val, bofs[b], tcol, tval, d_flag);
         else         sjds_permute_kernel<ValT, false><<<grid, kSBlock, 0, c.stream>>>(s0, s1, nrows, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val, bofs[b], tcol, tval, d_flag);
         QB_LAUNCH_COUNT();
-        QB_CU(cudaMemcpyAsync(A->col + bofs[b], tcol, sizeof(int32_t) * span, cudaMemcpyDeviceToDevice, c.stream));
-        QB_CU(cudaMemcpyAsync((ValT *)A->val + bofs[b], tval, sizeof(ValT) * span, cudaMemcpyDeviceToDevice, c.stream));
+        if (span) {
+            QB_CU(cudaMemcpyAsync(A->col + bofs[b], tcol, sizeof(int32_t) * span, cudaMemcpyDeviceToDevice, c.stream));
+            QB_CU(cudaMemcpyAsync((ValT *)A->val + bofs[b], tval, sizeof(ValT) * span, cudaMemcpyDeviceToDevice, c.stream));
+        }
     }
     int flag = 0;
     QB_CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));

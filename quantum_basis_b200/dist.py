@@ -154,8 +154,11 @@ class PeerExchangeOperator:
     The ping-pong plus the barrier make the pulls race-free: a slice is overwritten only two products later, after a
     barrier that every puller has passed."""
 
-    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod):
+    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod, lanes=None):
         self.qb, self.L, self.k, self.n, self.rank, self.world, self.comm, self.torch = qb, qb.lib(), kernels, n, rank, world, comm, torch_mod
+        # copy streams in use: pulls on one stream run back to back at the full NVLink rate and therefore arrive in the
+        # order the blocks are multiplied (ring order: at distance d every GPU serves exactly one reader)
+        self.lanes = int(os.environ.get("QB_PEER_LANES", "2")) if lanes is None else lanes
         self.bounds, self.chunk = equal_row_bounds(n, world)
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.esize = 8 * kernels.ncomp
@@ -187,11 +190,11 @@ class PeerExchangeOperator:
         return self.X[b].view(self.lo * self.esize)
 
     def pull(self, b):
-        for p in self.order:
+        for idx, p in enumerate(self.order):
             off = self.bounds[p] * self.esize
             nb = (self.bounds[p + 1] - self.bounds[p]) * self.esize
             if nb:
-                rc = self.L.qbgpu_peer_pull_async(p, C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off), nb)
+                rc = self.L.qbgpu_peer_pull_async(idx % self.lanes, p, C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off), nb)
                 assert rc == 0, self.L.qbgpu_last_error()
 
     def _wait(self, p):

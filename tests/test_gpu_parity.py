@@ -208,8 +208,9 @@ def test_row_shards_reproduce_the_full_product(oracle):
         assert rel_l2(np.concatenate(ys), ex["y1"]) <= TOL_MV
 
 
-@pytest.mark.parametrize("name,nparts", [("tj12", 8), ("heis16_full", 8), ("heis16_full", 3), ("tri4x4_k12", 5)])
-def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts):
+@pytest.mark.parametrize("name,nparts,shard", [("tj12", 8, None), ("heis16_full", 8, None), ("heis16_full", 3, None), ("tri4x4_k12", 5, None),
+                                               ("tj12", 8, (0.375, 0.5)), ("heis16_full", 8, (0.125, 0.25)), ("heis16_full", 8, (0.875, 1.0))])
+def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts, shard):
     """qbgpu_split_columns + qbgpu_lanczos_step_a_part (what every rank does in the overlapped multi-GPU exchange) on ONE
     GPU: the per-owner column blocks, multiplied one after the other with the accumulate flags, must give the same w and
     the same alpha as the unsplit fused step -- for complex and for fp64 (real-view) vectors."""
@@ -217,7 +218,9 @@ def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts):
     A, meta, ex = oracle.load_golden(name)
     L = qb.lib()
     n = A.dim
-    M = make(A)
+    lo, hi = (0, n) if shard is None else (int(shard[0] * n), int(shard[1] * n))     # a rank's row block (row_lo != 0)
+    M = make(A) if shard is None else make(A, rows=(lo, hi))
+    nl = hi - lo
     chunk = (n + nparts - 1) // nparts
     bounds = np.array([min(n, p * chunk) for p in range(nparts)] + [n], dtype=np.int64)
     hs = (C.c_void_p * nparts)()
@@ -231,16 +234,16 @@ def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts):
         P = [p.real_view() for p in parts] if real else parts
         rng = np.random.default_rng(3)
         ux = rng.normal(size=n) if real else rng.normal(size=n) + 1j * rng.normal(size=n)
-        uz0 = rng.normal(size=n) if real else rng.normal(size=n) + 1j * rng.normal(size=n)
+        uz0 = rng.normal(size=nl) if real else rng.normal(size=nl) + 1j * rng.normal(size=nl)
         state0 = np.array([0.7, 1.3, 0.9, 0, 0, 0, 0, 0], dtype=np.float64)       # sx, sz, b_prev
         dux = qb.DeviceVector.from_numpy(ux.astype(dt))
         # unsplit
         duz = qb.DeviceVector.from_numpy(uz0.astype(dt)); st = qb.DeviceVector.from_numpy(state0)
         assert L.qbgpu_lanczos_step_a(H.handle, C.c_void_p(dux.ptr), C.c_void_p(duz.ptr), C.c_void_p(st.ptr)) == 0
         w_ref, a_ref = duz.to_numpy(), st.to_numpy()[3]
-        w_exact = 0.7 * oracle.spmv_ld(A, ux) - 0.9 * 1.3 * uz0
+        w_exact = 0.7 * oracle.spmv_ld(A, ux)[lo:hi] - 0.9 * 1.3 * uz0
         assert rel_l2(w_ref, w_exact if not real else w_exact.real) <= TOL_MV
-        assert abs(a_ref - np.real(np.vdot(0.7 * ux, w_ref))) <= 1e-12 * abs(a_ref)
+        assert abs(a_ref - np.real(np.vdot(0.7 * ux[lo:hi], w_ref))) <= 1e-12 * abs(a_ref)
         # per-owner blocks, own block first (rank r = 2 of nparts), the others in ring order
         order = [2 % nparts] + [(2 + d) % nparts for d in range(1, nparts)]
         duz2 = qb.DeviceVector.from_numpy(uz0.astype(dt)); st2 = qb.DeviceVector.from_numpy(state0)
@@ -252,10 +255,10 @@ def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts):
         assert rel_l2(w_blk, w_ref) <= 1e-14
         assert abs(a_blk - a_ref) <= 1e-12 * abs(a_ref)
         # and the plain accumulate form (y = sum_p H_p x)
-        y = qb.DeviceVector(n, dt)
+        y = qb.DeviceVector(nl, dt)
         for idx, p in enumerate(order):
             P[p]._mv(complex(1.0), dux, complex(1.0 if idx else 0.0), y)
-        assert rel_l2(y.to_numpy(), oracle.spmv_ld(A, ux) if not real else oracle.spmv_ld(A, ux).real) <= TOL_MV
+        assert rel_l2(y.to_numpy(), oracle.spmv_ld(A, ux)[lo:hi] if not real else oracle.spmv_ld(A, ux)[lo:hi].real) <= TOL_MV
 
 
 # ---------------------------------------------------------------------------------------- vec_randomize

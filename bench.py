@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 WORKLOADS = {
     # name: (family, params)
@@ -36,7 +38,7 @@ WORKLOADS = {
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
-TRAFFIC_NCU = {"hubbard4x4": None}
+TRAFFIC_NCU = {"hubbard4x4": 133686405000}     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
 
 
 def square_bonds(Lx, Ly):

@@ -223,12 +223,13 @@ def test_column_blocks_reproduce_the_fused_step(oracle, name, nparts, shard):
     nl = hi - lo
     chunk = (n + nparts - 1) // nparts
     bounds = np.array([min(n, p * chunk) for p in range(nparts)] + [n], dtype=np.int64)
-    hs = (C.c_void_p * nparts)()
-    assert L.qbgpu_split_columns(M.handle, nparts, bounds.ctypes.data, hs, 0) == 0, L.qbgpu_last_error()
-    parts = [qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
-    assert sum(p.info.nnz_stored for p in parts) == M.info.nnz_stored
     real_ok = bool(M.info.val_is_real)
-    for real in ([False, True] if real_ok else [False]):
+    for part_flags, real in [(f, r) for f in (0, 4 | 2, 8 | 2) for r in ([False, True] if real_ok else [False])]:
+        # part layouts: autotuned, forced CSR-vector, forced sliced-jagged
+        hs = (C.c_void_p * nparts)()
+        assert L.qbgpu_split_columns(M.handle, nparts, bounds.ctypes.data, hs, part_flags) == 0, L.qbgpu_last_error()
+        parts = [qb.csr_mat._adopt(C.c_void_p(hs[p]), True) for p in range(nparts)]
+        assert sum(p.info.nnz_stored for p in parts) == M.info.nnz_stored
         dt = np.float64 if real else np.complex128
         H = M.real_view() if real else M
         P = [p.real_view() for p in parts] if real else parts

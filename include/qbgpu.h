@@ -176,6 +176,8 @@ int qbgpu_herm_eigen(int m, const void *a_colmajor, double *w, void *s_colmajor)
 /* hess_eigen (src/lanczos.cc:355-390, order "sr"): host-side tridiagonal Ritz solve used by the stop rule.
  * ritz[m]; s[m*m] column-major eigenvectors or NULL. */
 int qbgpu_hess_eigen(const double *hessenberg, int64_t maxit, int64_t m, double *ritz, double *s);
+/* lowest Ritz value only, by Sturm bisection in O(m): what the per-step part of the stop rule needs (src/lanczos.cc:232) */
+int qbgpu_hess_smallest(const double *hessenberg, int64_t maxit, int64_t m, double *theta0);
 
 /* ------------------------------------------------------------------ step-level entry points (DEVICE only)
  * One fused pass each; scalars live in a device array `sc` so that no host synchronisation is needed between

@@ -58,7 +58,7 @@ _SIGS = {
     "qbgpu_energy_scale_z": [vp, vp, C.POINTER(dbl), C.POINTER(dbl), dbl, i64, C.c_int],
     "qbgpu_kpm_moments_d": [vp, vp, dbl, dbl, i64, vp, C.c_int],
     "qbgpu_kpm_moments_z": [vp, vp, dbl, dbl, i64, vp, C.c_int],
-    "qbgpu_hess_eigen": [vp, i64, i64, vp, vp], "qbgpu_herm_eigen": [C.c_int, vp, vp, vp],
+    "qbgpu_hess_eigen": [vp, i64, i64, vp, vp], "qbgpu_herm_eigen": [C.c_int, vp, vp, vp], "qbgpu_hess_smallest": [vp, i64, i64, C.POINTER(dbl)],
     "qbgpu_trlan": [vp, C.c_int, C.c_int, C.c_int, dbl, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, C.c_int],
     "qbgpu_spmv_fused": [vp, vp, vp, vp, vp, vp, vp, vp],
     "qbgpu_lanczos_step_a": [vp, vp, vp, vp], "qbgpu_lanczos_step_a_part": [vp, vp, vp, vp, C.c_int, C.c_int],

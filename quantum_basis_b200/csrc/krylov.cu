@@ -68,6 +68,38 @@ static int tridiag_ql(int64_t m, double *d, double *e, double *z, double *zlast)
     return 0;
 }
 
+// Smallest eigenvalue of the m x m tridiagonal (diag hess[maxit+j], off-diag hess[j+1]) by bisection on the Sturm
+// count, to machine precision.  O(m) per evaluation: the per-step part of the stop rule (the relative change of the
+// lowest Ritz value, src/lanczos.cc:232-239) needs nothing else; the O(m^2) QL solve for the residual estimate
+// |b_m s_{m-1}| (:231) is only run once that change has stayed below the threshold for more than 15 steps.
+static double tridiag_smallest(const double *hess, int64_t maxit, int64_t m)
+{
+    const double *a = hess + maxit, *b = hess;             // b[j] couples j-1 and j (j = 1..m-1)
+    double lo = a[0], hi = a[0];
+    for (int64_t j = 0; j < m; j++) {
+        const double r = (j > 0 ? fabs(b[j]) : 0.0) + (j + 1 < m ? fabs(b[j + 1]) : 0.0);
+        lo = fmin(lo, a[j] - r); hi = fmax(hi, a[j] + r);
+    }
+    auto count_below = [&](double x) {                     // number of eigenvalues < x
+        int64_t cnt = 0;
+        double q = 1.0;
+        for (int64_t j = 0; j < m; j++) {
+            const double off2 = j > 0 ? b[j] * b[j] : 0.0;
+            q = a[j] - x - (j > 0 ? off2 / q : 0.0);
+            if (q == 0.0) q = -DBL_MIN;
+            if (q < 0.0) cnt++;
+        }
+        return cnt;
+    };
+    hi = fmin(hi, a[0]);                                   // the smallest eigenvalue is <= any diagonal entry
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid <= lo || mid >= hi) break;
+        if (count_below(mid) >= 1) hi = mid; else lo = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+
 // ritz ascending ("sr"); s (optional) full vectors; s_last0 (optional) = last component of the lowest vector
 static int hess_eigen_host(const double *hess, int64_t maxit, int64_t m, double *ritz, double *s, double *s_last0)
 {
@@ -204,15 +236,17 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
             }
         }
         if (is_val) {                                       // stop rule, :228-248
-            double s_last = 0.0;
-            if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+            const double theta0 = tridiag_smallest(hess, maxit, m);
             if (m > 3) {
-                const double accuracy = fabs(hess[m] * s_last);
-                const double accu_E0 = fabs((ritz[0] - theta0_prev) / ritz[0]);
+                const double accu_E0 = fabs((theta0 - theta0_prev) / theta0);
                 if (accu_E0 < kLanczosPrecision) cnt_accuE0++; else cnt_accuE0 = 0;
-                if (cnt_accuE0 > 15 && accuracy < kLanczosPrecision) break;
+                if (cnt_accuE0 > 15) {                      // only now is the residual estimate |b_m s_{m-1}| needed
+                    double s_last = 0.0;
+                    if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+                    if (fabs(hess[m] * s_last) < kLanczosPrecision) break;
+                }
             }
-            theta0_prev = ritz[0];
+            theta0_prev = theta0;
         }
     }
     if (prof) {
@@ -518,6 +552,13 @@ int qbgpu_hess_eigen(const double *hess, int64_t maxit, int64_t m, double *ritz,
 {
     if (!hess || !ritz || m < 1 || m >= maxit) return fail(QBGPU_ERR_ARG, "hess_eigen: need 0 < m < maxit");   // src/lanczos.cc:358
     if (hess_eigen_host(hess, maxit, m, ritz, s, nullptr)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+    return QBGPU_OK;
+}
+
+int qbgpu_hess_smallest(const double *hess, int64_t maxit, int64_t m, double *theta0)
+{
+    if (!hess || !theta0 || m < 1 || m >= maxit) return fail(QBGPU_ERR_ARG, "hess_smallest: need 0 < m < maxit");
+    *theta0 = tridiag_smallest(hess, maxit, m);
     return QBGPU_OK;
 }
 

@@ -110,3 +110,26 @@ def test_herm_eigen_host(L):
         assert np.abs(w - np.linalg.eigvalsh(A)).max() < 1e-12 * max(1.0, np.abs(A).max())
         assert np.abs(A @ S - S * w[None, :]).max() < 1e-11 * max(1.0, np.abs(A).max())
         assert np.abs(S.conj().T @ S - np.eye(m)).max() < 1e-12
+
+
+def test_hess_smallest_matches_full_solve(L, oracle):
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    for m in (1, 2, 3, 10, 77, 300):
+        maxit = 512
+        hess = np.zeros(2 * maxit)
+        hess[1:m + 1] = rng.uniform(1e-3, 3.0, m)
+        hess[maxit:maxit + m] = rng.normal(size=m) * 5
+        t = C.c_double()
+        assert L.qbgpu_hess_smallest(hess.ctypes.data, maxit, m, C.byref(t)) == 0
+        Tm = np.diag(hess[maxit:maxit + m]) + np.diag(hess[1:m], 1) + np.diag(hess[1:m], -1)
+        w0 = np.linalg.eigvalsh(Tm)[0]
+        assert abs(t.value - w0) <= 4e-15 * max(1.0, abs(w0))
+    # a real Lanczos tridiagonal (converged ground state, tiny couplings at the end)
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    a, b = ex["lanczos_a"], ex["lanczos_b"]
+    m = len(a); maxit = 1000
+    hess = np.zeros(2 * maxit); hess[:m + 1] = b; hess[maxit:maxit + m] = a
+    t = C.c_double()
+    assert L.qbgpu_hess_smallest(hess.ctypes.data, maxit, m, C.byref(t)) == 0
+    assert abs(t.value - meta["lanczos_E0"]) <= 1e-13 * abs(meta["lanczos_E0"])

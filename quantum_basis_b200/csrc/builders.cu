@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <vector>
 
 namespace qb {
@@ -305,6 +306,85 @@ static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
 
 
 // ------------------------------------------------------------------------------------------------ matrix-free
+// Neighbour tables for the matrix-free kernel: instead of testing every (bond, direction, spin) -- 128 tests per row on
+// the 4x4 lattice, a quarter of which fire -- the kernel walks the set bits of "occupied site" words and, for each,
+// the set bits of (neighbours of that site) & ~occupied, so that the number of trips equals the number of entries.
+struct SiteTables {
+    int nsites;
+    uint32_t nbr[32];            // nbr[f]: bit t set when sites f and t share a bond
+    uint8_t wgt[32][32];         // bond multiplicity (duplicates in the caller's list are merged)
+    int wbonds;                  // sum of multiplicities (for the Heisenberg diagonal)
+};
+
+// bit k -> bit 2k (k < 16)
+__host__ __device__ __forceinline__ uint32_t spread16(uint32_t x)
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// Entries of the row of basis state (la, lb), generated in neighbour-walk order; returns the diagonal.
+template <class Emit>
+__device__ __forceinline__ double row_entries_walk(const SectorTables &S, const ModelParams &M, const SiteTables &N, uint32_t la, uint32_t lb, Emit emit)
+{
+    if (M.kind == 0) {
+        // site-indexed "down" word: A-site k is site 2k, B-site k is site 2k+1
+        const uint32_t dn = spread16(la) | (spread16(lb) << 1);
+        int anti = 0;                                        // weighted number of antiparallel bonds
+        uint32_t m = dn;
+        while (m) {
+            const int f = __ffs(m) - 1; m &= m - 1;
+            uint32_t cand = N.nbr[f] & ~dn;
+            while (cand) {
+                const int t = __ffs(cand) - 1; cand &= cand - 1;
+                const int w = N.wgt[f][t];
+                anti += w;
+                uint32_t na = la, nb = lb;
+                if (f & 1) nb ^= 1u << (f >> 1); else na ^= 1u << (f >> 1);
+                if (t & 1) nb ^= 1u << (t >> 1); else na ^= 1u << (t >> 1);
+                emit(col_of(S, na, nb), 0.5 * M.J * w);
+            }
+        }
+        return 0.25 * M.J * (double)(N.wbonds - 2 * anti);
+    }
+    // electrons: digit = up + 2*dn at bit pair k of a sublattice label; site-indexed occupancy words per spin
+    const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);
+    const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+    const int ndbl = __popc(occ0 & occ1);
+    double diag = 0.0;
+    for (int r = 0; r < ndbl; r++) diag += M.U;
+#pragma unroll
+    for (int sp = 0; sp < 2; sp++) {
+        const uint32_t occ = sp ? occ1 : occ0;
+        uint32_t m = occ;
+        while (m) {
+            const int f = __ffs(m) - 1; m &= m - 1;
+            uint32_t cand = N.nbr[f] & ~occ;
+            // c_{f,sp}: fermions on sites below f (both spins); c_dn next to an up electron on the same site: -1
+            const uint32_t below_f = (1u << f) - 1u;
+            const int sg_f = (__popc(occ0 & below_f) + __popc(occ1 & below_f) + (sp == 1 ? (int)((occ0 >> f) & 1u) : 0)) & 1;
+            while (cand) {
+                const int t = __ffs(cand) - 1; cand &= cand - 1;
+                // c+_{t,sp} on the state with (f,sp) removed
+                const uint32_t below_t = (1u << t) - 1u;
+                int sg = sg_f + __popc(occ0 & below_t) + __popc(occ1 & below_t) + (sp == 1 ? (int)((occ0 >> t) & 1u) : 0);
+                if (f < t) sg += 1;                          // the removed electron sat below t
+                uint32_t na = la, nb = lb;
+                if (f & 1) nb ^= 1u << (2 * (f >> 1) + sp); else na ^= 1u << (2 * (f >> 1) + sp);
+                if (t & 1) nb ^= 1u << (2 * (t >> 1) + sp); else na ^= 1u << (2 * (t >> 1) + sp);
+                double amp = 0.0;
+                for (int r = 0; r < N.wgt[f][t]; r++) amp += -M.t;
+                emit(col_of(S, na, nb), (sg & 1) ? -amp : amp);
+            }
+        }
+    }
+    return diag;
+}
+
 // The product with no stored matrix: one thread per row (32 consecutive rows per warp, like the sliced-jagged
 // kernel, so one Hamiltonian term sends the lanes of a warp to neighbouring columns), the row's entries regenerated by
 // row_entries() and consumed at once.  The reference's counterpart is model<T>::MultMv2 with matrix_free == true
@@ -316,6 +396,7 @@ struct MatFree {
     int32_t *d_rank = nullptr, *d_off = nullptr;
     uint32_t *d_alist = nullptr;
     uint2 *d_states = nullptr;      // (la, lb) of every local row
+    SiteTables *d_N = nullptr;
     int64_t bytes = 0;
 };
 
@@ -332,13 +413,15 @@ constexpr int kMFBlock = 256;
 
 template <typename VecT, bool DOTS>
 __global__ void __launch_bounds__(kMFBlock, 3)
-spmv_matfree_kernel(SectorTables S, const ModelParams *Mp, const uint2 *__restrict__ states, int64_t nrows, int64_t row_lo,
+spmv_matfree_kernel(SectorTables S, const ModelParams *Mp, const SiteTables *Np, const uint2 *__restrict__ states, int64_t nrows, int64_t row_lo,
                     const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                     int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
-    __shared__ ModelParams M;
-    for (int k = threadIdx.x; k < (int)(sizeof(ModelParams) / 4); k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    __shared__ ModelParams M;                               // only the scalars are used here; the bonds live in N
+    __shared__ SiteTables N;
+    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(SiteTables) / 4); k += blockDim.x) ((int *)&N)[k] = ((const int *)Np)[k];
     __syncthreads();
     double dot_scale = 1.0;
     if (scal_mode != 0) {
@@ -353,7 +436,7 @@ spmv_matfree_kernel(SectorTables S, const ModelParams *Mp, const uint2 *__restri
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
         const uint2 st = states[row];
         VecT acc = VT::zero();
-        const double diag = row_entries(S, M, st.x, st.y, [&](int64_t c, double v) { mac(acc, v, ld_vec(x + c)); });
+        const double diag = row_entries_walk(S, M, N, st.x, st.y, [&](int64_t c, double v) { mac(acc, v, ld_vec(x + c)); });
         const VecT xi = x[row_lo + row];
         mac(acc, diag, xi);
         VecT out = VT::scale(alpha, acc);
@@ -388,7 +471,7 @@ static int launch_matfree_variant(const qbgpu_matrix *A, const FusedArgs &a)
     int64_t cap = (int64_t)c.num_sms * blocks_per_sm;
     if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
     const int grid = (int)(want < cap ? want : cap);
-    kern<<<grid, kMFBlock, 0, c.stream>>>(mf->S, mf->d_M, mf->d_states, nrows, A->row_lo, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+    kern<<<grid, kMFBlock, 0, c.stream>>>(mf->S, mf->d_M, mf->d_N, mf->d_states, nrows, A->row_lo, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
                                           a.alpha, a.gamma, a.beta, a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
@@ -406,7 +489,7 @@ void matfree_destroy(qbgpu_matrix *A)
 {
     MatFree *mf = (MatFree *)A->mf;
     if (!mf) return;
-    cudaFree(mf->d_M); cudaFree(mf->d_Jb); cudaFree(mf->d_rank); cudaFree(mf->d_off); cudaFree(mf->d_alist); cudaFree(mf->d_states);
+    cudaFree(mf->d_N); cudaFree(mf->d_M); cudaFree(mf->d_Jb); cudaFree(mf->d_rank); cudaFree(mf->d_off); cudaFree(mf->d_alist); cudaFree(mf->d_states);
     delete mf;
     A->mf = nullptr;
 }
@@ -419,6 +502,7 @@ static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
     *out = nullptr;
     if (T.dim <= 0) return fail(QBGPU_ERR_ARG, "matrix-free: empty sector");
     if (T.dim > 2147483647LL) return fail(QBGPU_ERR_ARG, "matrix-free: dimension exceeds the int32 column range");
+    if (T.nsites > 32) return fail(QBGPU_ERR_ARG, "matrix-free: at most 32 sites");
     if (row_hi < 0) row_hi = T.dim;
     if (row_lo < 0 || row_lo > row_hi || row_hi > T.dim) return fail(QBGPU_ERR_ARG, "matrix-free: bad row shard");
     const int64_t nloc = row_hi - row_lo;
@@ -439,6 +523,17 @@ static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
     QB_CU(cudaMemcpyAsync(mf->d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
     QB_CU(cudaMemcpyAsync(mf->d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
     QB_CU(cudaMemcpyAsync(mf->d_M, &M, sizeof(ModelParams), cudaMemcpyHostToDevice, c.stream));
+    static thread_local SiteTables N;
+    memset(&N, 0, sizeof N);
+    N.nsites = T.nsites;
+    for (int b = 0; b < M.nbonds; b++) {
+        const int i = M.bonds[b].i, j = M.bonds[b].j, w = M.bonds[b].w;
+        N.nbr[i] |= 1u << j; N.nbr[j] |= 1u << i;
+        N.wgt[i][j] = (uint8_t)w; N.wgt[j][i] = (uint8_t)w;
+        N.wbonds += w;
+    }
+    QB_CU(cudaMalloc(&mf->d_N, sizeof(SiteTables)));
+    QB_CU(cudaMemcpyAsync(mf->d_N, &N, sizeof(SiteTables), cudaMemcpyHostToDevice, c.stream));
     SectorTables &S = mf->S;
     S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
     S.Jb = mf->d_Jb; S.rankA = mf->d_rank; S.alist = mf->d_alist; S.class_off = mf->d_off; S.sizeB = (uint32_t)(T.Jb.size() - 1);

@@ -238,6 +238,33 @@ int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, in
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                                  double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* --------------------------------------------------------------------- translation-symmetric sectors
+ * Device counterpart of model::fill_Weisse_table + enumerate_basis_repr + generate_Ham_sparse_repr
+ * (src/model.cc:205-249, 275-487, 688-836) for spin-1/2 models on untilted lattices with one site per unit cell and
+ * periodic boundaries in every direction (chain, square, triangular; at most 32 sites, at least one even direction):
+ * the representatives, their order (Lin order when the reference's Lin tables exist, bisection order otherwise),
+ * the norms and every matrix element are those of the reference bit for bit (tests/repr_builders.py restates the
+ * convention and is pinned against 39 sectors assembled by the compiled reference).  BASELINE configs 2 and 5.
+ *   L[dim]: lattice extents; k[dim]: momentum integers as passed to enumerate_basis_repr; ndown: number of down spins
+ *   (digit 1), Sz_total = nsites/2 - ndown.  Sites are numbered like the reference's lattice class: first even
+ *   direction fastest (src/lattice.cc:591-615). */
+typedef struct qbgpu_sector *qbgpu_sector_t;
+typedef struct {
+    int64_t dim;                 /* number of representatives, including those of zero norm */
+    int64_t zero_norm;           /* representatives whose norm vanishes at this momentum (rows fake_pos + i/dim) */
+    int     nsites;
+    int     lin_order;           /* 1: Lin-table order (odd-site label, even-site label); 0: integer order */
+    double  enumerate_seconds, norms_seconds;
+} qbgpu_sector_info;
+int qbgpu_sector_create(qbgpu_sector_t *S, int dim, const int32_t *L, int ndown, const int32_t *k);
+int qbgpu_sector_destroy(qbgpu_sector_t S);
+int qbgpu_sector_get_info(qbgpu_sector_t S, qbgpu_sector_info *info);
+int qbgpu_sector_states(qbgpu_sector_t S, uint32_t *states_host);      /* bit s set = site s down, row order */
+int qbgpu_sector_norms(qbgpu_sector_t S, double *nu_host);
+/* H = J sum_bonds S_i.S_j in that sector (bonds[2*nbonds] site pairs, duplicates are separate terms like repeated
+ * add_Ham calls); fake_pos is model's constructor argument (default 100, src/qbasis.h:1337). */
+int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J,
+                                  double fake_pos, int flags);
 /* dimension of those sectors (host only) */
 int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);

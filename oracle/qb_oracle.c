@@ -193,3 +193,11 @@ void qbo_kpm_moments_z(int64_t n, const int64_t *ia, const int64_t *ja, const do
     }
     free(t0); free(t1); free(w);
 }
+
+/* Same as qbo_eigenvec_cg_z with E0 behind a pointer (re, im): complex scalars by value do not cross every FFI. */
+int64_t qbo_eigenvec_cg_zp(int64_t n, const int64_t *ia, const int64_t *ja, const double _Complex *val, int sym,
+                           const double *E0_reim, int64_t maxit, double *accu, double _Complex *v, double _Complex *r,
+                           double _Complex *p, double _Complex *pp, int nthreads)
+{
+    return qbo_eigenvec_cg_z(n, ia, ja, val, sym, E0_reim[0] + E0_reim[1] * I, maxit, accu, v, r, p, pp, nthreads);
+}

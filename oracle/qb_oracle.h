@@ -64,6 +64,10 @@ int64_t qbo_eigenvec_cg_d(int64_t n, const int64_t *ia, const int64_t *ja, const
 int64_t qbo_eigenvec_cg_z(int64_t n, const int64_t *ia, const int64_t *ja, const double _Complex *val, int sym,
                           double _Complex E0, int64_t maxit, double *accu, double _Complex *v, double _Complex *r,
                           double _Complex *p, double _Complex *pp, int nthreads);
+/* E0 as a pointer to (re, im) for callers whose FFI cannot pass a complex scalar by value (ctypes) */
+int64_t qbo_eigenvec_cg_zp(int64_t n, const int64_t *ia, const int64_t *ja, const double _Complex *val, int sym,
+                           const double *E0_reim, int64_t maxit, double *accu, double _Complex *v, double _Complex *r,
+                           double _Complex *p, double _Complex *pp, int nthreads);
 
 /* energy_scale<T,MAT> (src/kpm.cc:45-88) with the start vector given in v[0..n) (the reference draws
  * vec_randomize(seed=1)); v needs 2n entries. */

@@ -16,6 +16,11 @@ class QbgpuError(RuntimeError):
     reference src/sparse.cc:130,259,288)."""
 
 
+class SectorInfo(C.Structure):
+    _fields_ = [("dim", C.c_int64), ("zero_norm", C.c_int64), ("nsites", C.c_int), ("lin_order", C.c_int),
+                ("enumerate_seconds", C.c_double), ("norms_seconds", C.c_double)]
+
+
 class MatrixInfo(C.Structure):
     _fields_ = [("n", C.c_int64), ("row_lo", C.c_int64), ("row_hi", C.c_int64), ("nnz_stored", C.c_int64),
                 ("nnz_input", C.c_int64), ("val_is_real", C.c_int), ("value_dict", C.c_int), ("api_is_complex", C.c_int), ("format", C.c_int),
@@ -70,6 +75,9 @@ _SIGS = {
     "qbgpu_build_hubbard": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, dbl, dbl, C.c_int, C.c_int, i64, i64],
     "qbgpu_create_matfree_heisenberg": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, dbl, C.c_int, C.c_int, i64, i64],
     "qbgpu_create_matfree_hubbard": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, dbl, dbl, C.c_int, C.c_int, i64, i64],
+    "qbgpu_sector_create": [C.POINTER(vp), C.c_int, vp, C.c_int, vp], "qbgpu_sector_destroy": [vp],
+    "qbgpu_sector_get_info": [vp, C.POINTER(SectorInfo)], "qbgpu_sector_states": [vp, vp], "qbgpu_sector_norms": [vp, vp],
+    "qbgpu_sector_build_heisenberg": [vp, C.POINTER(vp), C.c_int, vp, dbl, dbl, C.c_int],
 }
 _RESTYPES = {"qbgpu_last_error": C.c_char_p, "qbgpu_version": C.c_char_p, "qbgpu_kernel_launches": C.c_int64,
              "qbgpu_dim_heisenberg": C.c_int64, "qbgpu_dim_hubbard": C.c_int64}

@@ -234,6 +234,54 @@ def hubbard(nsites, nup, ndn, bonds, t=1.0, U=0.0, is_complex=True, flags=0, row
     return csr_mat._adopt(h, is_complex)
 
 
+class Sector:
+    """One (Sz, momentum) sector of a spin-1/2 model on an untilted lattice: the device counterpart of
+    model::fill_Weisse_table + enumerate_basis_repr (src/model.cc:205-249, 275-487).  Representatives, their order and
+    their norms are the reference's; `heisenberg()` assembles generate_Ham_sparse_repr's matrix (src/model.cc:688-836)
+    directly in HBM and returns a csr_mat."""
+
+    def __init__(self, L, ndown, momentum):
+        La = np.ascontiguousarray(L, dtype=np.int32)
+        ka = np.ascontiguousarray(momentum, dtype=np.int32)
+        if La.size != ka.size:
+            raise QbgpuError("momentum needs one integer per lattice direction")
+        self._h = C.c_void_p()
+        check(lib().qbgpu_sector_create(C.byref(self._h), int(La.size), C.c_void_p(La.ctypes.data), int(ndown), C.c_void_p(ka.ctypes.data)))
+        info = _lib.SectorInfo()
+        check(lib().qbgpu_sector_get_info(self._h, C.byref(info)))
+        self.dim, self.zero_norm, self.nsites, self.lin_order = info.dim, info.zero_norm, info.nsites, bool(info.lin_order)
+        self.enumerate_seconds, self.norms_seconds = info.enumerate_seconds, info.norms_seconds
+
+    def states(self):
+        """Bit patterns of the representatives in row order (bit s set = site s down)."""
+        out = np.empty(self.dim, dtype=np.uint32)
+        check(lib().qbgpu_sector_states(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def norms(self):
+        """norm_repr of the reference (src/basis.cc:2104-2202): orbit size, or 0 when the momentum kills the state."""
+        out = np.empty(self.dim, dtype=np.float64)
+        check(lib().qbgpu_sector_norms(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def heisenberg(self, bonds, J=1.0, fake_pos=100.0, flags=0):
+        b, nb = _bond_array(bonds)
+        h = C.c_void_p()
+        check(lib().qbgpu_sector_build_heisenberg(self._h, C.byref(h), nb, C.c_void_p(b.ctypes.data), float(J), float(fake_pos), flags))
+        return csr_mat._adopt(h, True)
+
+    def free(self):
+        if self._h:
+            lib().qbgpu_sector_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def vec_randomize(n, seed=1, dtype=np.complex128, device=False):
     """src/miscellaneous.cc:371-388, generated on the device."""
     v = DeviceVector(n, dtype)

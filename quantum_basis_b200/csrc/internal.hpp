@@ -67,6 +67,9 @@ int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
+// expand a device-resident reference-format CSR (int64 row_start/row_end/col, offsets from 0) into a new handle
+int create_from_device_csr(qbgpu_matrix_t *out, int64_t n, const int64_t *d_rs, const int64_t *d_re, const int64_t *d_col,
+                           const void *d_val, bool val_complex, int64_t nnz_input, int sym, int flags, bool api_complex);
 // vecops.cu
 int vec_dotc(int64_t n, bool cplx, const void *x, const void *y, double *out_dev3);   // out: re, im, (unused)
 int vec_dotc_scaled(int64_t n, bool cplx, const void *x, const void *y, double *out_dev3, const double *scale_dev);

@@ -120,52 +120,24 @@ __global__ void __launch_bounds__(kCBlock) demote_kernel(int64_t nnz, const doub
 
 static int grid_for(int64_t n) { int64_t g = (n + kCBlock - 1) / kCBlock; if (g < 1) g = 1; if (g > 148 * 32) g = 148 * 32; return (int)g; }
 
+// Expansion of a DEVICE-resident reference-format CSR (int64 row_start/row_end/col, base-relative offsets, values T)
+// into the handle's layout.  Shared by the host entry points (after their upload) and by the on-device sector
+// assembler (sectors.cu), whose upper triangle never leaves HBM.  Does not free its inputs.
 template <typename T>   // T = double or double2 (input scalar type)
-static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, const int64_t *re, const int64_t *col,
-                            const void *val, int sym, int flags, int64_t lo, int64_t hi, bool api_complex)
+static int convert_device(qbgpu_matrix *A, int64_t n, int64_t base, const int64_t *d_rs, const int64_t *d_re, const int64_t *d_col,
+                          const T *d_val, int sym, int flags, int64_t lo, int64_t hi)
 {
-    QB_TRY(ensure_init());
     Context &c = ctx();
-    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
-    *out = nullptr;
-    if (n <= 0 || !rs || !re || !col || !val) return fail(QBGPU_ERR_ARG, "create_csr: null array or n <= 0");
-    if (n > 2147483647LL) return fail(QBGPU_ERR_ARG, "create_csr: n exceeds the int32 column range of the device layout");
-    if (hi < 0) hi = n;
-    if (lo < 0 || lo > hi || hi > n) return fail(QBGPU_ERR_ARG, "create_csr: bad row shard");
-    int64_t base = rs[0], top = re[0];
-    for (int64_t i = 0; i < n; i++) {
-        if (re[i] < rs[i]) return fail(QBGPU_ERR_ARG, "create_csr: row_end < row_start");
-        if (rs[i] < base) base = rs[i];
-        if (re[i] > top) top = re[i];
-    }
-    const int64_t span = top - base;                        // entries of col/val that are referenced
     const int64_t nloc = hi - lo;
-    auto *A = new qbgpu_matrix;
-    A->n = n; A->row_lo = lo; A->row_hi = hi; A->api_complex = api_complex; A->nnz_input = span;
-
-    const double t0 = wall();
-    int64_t *d_rs = nullptr, *d_re = nullptr, *d_col = nullptr, *d_len = nullptr;
-    T *d_val = nullptr;
+    const double t1 = wall();
+    int64_t *d_len = nullptr;
     int *d_cnt_u = nullptr, *d_cnt_t = nullptr, *d_cursor = nullptr, *d_err = nullptr;
     double *d_maximag = nullptr;
     void *d_tmp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_rs); cudaFree(d_re); cudaFree(d_col); cudaFree(d_val); cudaFree(d_len); cudaFree(d_cnt_u); cudaFree(d_cnt_t);
-        cudaFree(d_cursor); cudaFree(d_err); cudaFree(d_maximag); cudaFree(d_tmp);
+        cudaFree(d_len); cudaFree(d_cnt_u); cudaFree(d_cnt_t); cudaFree(d_cursor); cudaFree(d_err); cudaFree(d_maximag); cudaFree(d_tmp);
     };
-#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
-    QB_CU(cudaMalloc(&d_rs, sizeof(int64_t) * n));
-    QB_CU(cudaMalloc(&d_re, sizeof(int64_t) * n));
-    QB_CU(cudaMalloc(&d_col, sizeof(int64_t) * (span ? span : 1)));
-    QB_CU(cudaMalloc(&d_val, sizeof(T) * (span ? span : 1)));
-    QB_CU(cudaMemcpyAsync(d_rs, rs, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c.stream));
-    QB_CU(cudaMemcpyAsync(d_re, re, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c.stream));
-    QB_CU(cudaMemcpyAsync(d_col, col + base, sizeof(int64_t) * span, cudaMemcpyHostToDevice, c.stream));
-    QB_CU(cudaMemcpyAsync(d_val, (const T *)val + base, sizeof(T) * span, cudaMemcpyHostToDevice, c.stream));
-    QB_CU(cudaStreamSynchronize(c.stream));
-    A->upload_s = wall() - t0;
-
-    const double t1 = wall();
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
     QB_CU(cudaMalloc(&d_cnt_u, sizeof(int) * (nloc + 1)));
     QB_CU(cudaMalloc(&d_cnt_t, sizeof(int) * (nloc + 1)));
     QB_CU(cudaMalloc(&d_cursor, sizeof(int) * (nloc + 1)));
@@ -191,7 +163,7 @@ static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, c
     QB_CU(cudaMemcpyAsync(&nnz, A->rowptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
     QB_CU(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     QB_CU(cudaStreamSynchronize(c.stream));
-    if (herr & kErrColRange) { cleanup(); qbgpu_destroy(A); return fail(QBGPU_ERR_ARG, "create_csr: column index out of range"); }
+    if (herr & kErrColRange) { cleanup(); return fail(QBGPU_ERR_ARG, "create_csr: column index out of range"); }
     A->nnz = nnz;
     T *oval = nullptr;
     QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1)));
@@ -224,7 +196,67 @@ static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, c
     cleanup();
 #undef QB_CU
     A->convert_s = wall() - t1;
-    { int rc = autotune(A, flags); if (rc) { qbgpu_destroy(A); return rc; } }
+    return QBGPU_OK;
+}
+
+int create_from_device_csr(qbgpu_matrix_t *out, int64_t n, const int64_t *d_rs, const int64_t *d_re, const int64_t *d_col,
+                           const void *d_val, bool val_complex, int64_t nnz_input, int sym, int flags, bool api_complex)
+{
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    if (n <= 0 || n > 2147483647LL) return fail(QBGPU_ERR_ARG, "device csr: bad dimension");
+    auto *A = new qbgpu_matrix;
+    A->n = n; A->row_lo = 0; A->row_hi = n; A->api_complex = api_complex; A->nnz_input = nnz_input;
+    int rc = val_complex ? convert_device<double2>(A, n, 0, d_rs, d_re, d_col, (const double2 *)d_val, sym, flags, 0, n)
+                         : convert_device<double>(A, n, 0, d_rs, d_re, d_col, (const double *)d_val, sym, flags, 0, n);
+    if (rc == QBGPU_OK) rc = autotune(A, flags);
+    if (rc) { qbgpu_destroy(A); return rc; }
+    *out = A;
+    return QBGPU_OK;
+}
+
+template <typename T>   // T = double or double2 (input scalar type)
+static int create_from_host(qbgpu_matrix_t *out, int64_t n, const int64_t *rs, const int64_t *re, const int64_t *col,
+                            const void *val, int sym, int flags, int64_t lo, int64_t hi, bool api_complex)
+{
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    if (n <= 0 || !rs || !re || !col || !val) return fail(QBGPU_ERR_ARG, "create_csr: null array or n <= 0");
+    if (n > 2147483647LL) return fail(QBGPU_ERR_ARG, "create_csr: n exceeds the int32 column range of the device layout");
+    if (hi < 0) hi = n;
+    if (lo < 0 || lo > hi || hi > n) return fail(QBGPU_ERR_ARG, "create_csr: bad row shard");
+    int64_t base = rs[0], top = re[0];
+    for (int64_t i = 0; i < n; i++) {
+        if (re[i] < rs[i]) return fail(QBGPU_ERR_ARG, "create_csr: row_end < row_start");
+        if (rs[i] < base) base = rs[i];
+        if (re[i] > top) top = re[i];
+    }
+    const int64_t span = top - base;                        // entries of col/val that are referenced
+    auto *A = new qbgpu_matrix;
+    A->n = n; A->row_lo = lo; A->row_hi = hi; A->api_complex = api_complex; A->nnz_input = span;
+
+    const double t0 = wall();
+    int64_t *d_rs = nullptr, *d_re = nullptr, *d_col = nullptr;
+    T *d_val = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rs); cudaFree(d_re); cudaFree(d_col); cudaFree(d_val); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_rs, sizeof(int64_t) * n));
+    QB_CU(cudaMalloc(&d_re, sizeof(int64_t) * n));
+    QB_CU(cudaMalloc(&d_col, sizeof(int64_t) * (span ? span : 1)));
+    QB_CU(cudaMalloc(&d_val, sizeof(T) * (span ? span : 1)));
+    QB_CU(cudaMemcpyAsync(d_rs, rs, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_re, re, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_col, col + base, sizeof(int64_t) * span, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_val, (const T *)val + base, sizeof(T) * span, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+#undef QB_CU
+    A->upload_s = wall() - t0;
+    int rc = convert_device<T>(A, n, base, d_rs, d_re, d_col, d_val, sym, flags, lo, hi);
+    cleanup();
+    if (rc == QBGPU_OK) rc = autotune(A, flags);
+    if (rc) { qbgpu_destroy(A); return rc; }
     *out = A;
     return QBGPU_OK;
 }

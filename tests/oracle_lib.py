@@ -49,9 +49,9 @@ def lib():
     L.qbo_eigenvec_cg_d.argtypes = [C.c_int64, i64p, i64p, f64p, C.c_int, C.c_double, C.c_int64,
                                     C.POINTER(C.c_double), f64p, f64p, f64p, f64p, C.c_int]
     L.qbo_eigenvec_cg_d.restype = C.c_int64
-    L.qbo_eigenvec_cg_z.argtypes = [C.c_int64, i64p, i64p, c128p, C.c_int, C.c_double * 2, C.c_int64,
-                                    C.POINTER(C.c_double), c128p, c128p, c128p, c128p, C.c_int]
-    L.qbo_eigenvec_cg_z.restype = C.c_int64
+    L.qbo_eigenvec_cg_zp.argtypes = [C.c_int64, i64p, i64p, c128p, C.c_int, C.POINTER(C.c_double), C.c_int64,
+                                     C.POINTER(C.c_double), c128p, c128p, c128p, c128p, C.c_int]
+    L.qbo_eigenvec_cg_zp.restype = C.c_int64
     L.qbo_energy_scale_z.argtypes = [C.c_int64, i64p, i64p, c128p, C.c_int, c128p, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int]
     L.qbo_kpm_moments_z.argtypes = [C.c_int64, i64p, i64p, c128p, C.c_int, c128p, C.c_double, C.c_double,
@@ -187,7 +187,7 @@ def eigenvec_cg(A, E0, v0, maxit=1000, nthreads=1):
     accu = C.c_double(0.0)
     if A.is_complex:
         e = (C.c_double * 2)(float(np.real(E0)), float(np.imag(E0)))
-        m = lib().qbo_eigenvec_cg_z(n, A.ia, A.ja, A.val, int(A.sym), e, maxit, C.byref(accu), v, r, p, pp, nthreads)
+        m = lib().qbo_eigenvec_cg_zp(n, A.ia, A.ja, A.val, int(A.sym), e, maxit, C.byref(accu), v, r, p, pp, nthreads)
     else:
         m = lib().qbo_eigenvec_cg_d(n, A.ia, A.ja, A.val, int(A.sym), float(E0), maxit, C.byref(accu), v, r, p, pp, nthreads)
     return m, accu.value, v

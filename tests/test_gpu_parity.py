@@ -639,3 +639,60 @@ def test_large_generated_matrix_properties(oracle):
     ones = qb.DeviceVector.from_numpy(np.ones(n, dtype=np.complex128))
     M.MultMv(ones, hx)
     assert np.abs(hx.to_numpy() - nsites * 0.25).max() < 1e-12
+
+
+# ------------------------------------------------------------------ translation-symmetric sectors built on the device
+_SECTOR_CASES = [
+    ("chain16_k3", [16], 8, [3]), ("chain12_k5", [12], 6, [5]), ("chain14_sz1_k2", [14], 6, [2]),
+    ("chain20_k7", [20], 10, [7]), ("chain22_sz1_k5", [22], 10, [5]), ("chain24_k0", [24], 12, [0]),
+    ("tri4x4_k12", [4, 4], 8, [1, 2]), ("tri3x4_k23", [3, 4], 6, [2, 3]), ("tri6x3_k12", [6, 3], 9, [1, 2]),
+    ("tri4x5_k32", [4, 5], 10, [3, 2]),
+]
+
+
+def _sector_bonds(L):
+    import repr_builders as R
+    return R.chain_bonds(L[0]) if len(L) == 1 else R.triangular_bonds(*L)
+
+
+@pytest.mark.parametrize("name,L,ndown,k", _SECTOR_CASES, ids=[c[0] for c in _SECTOR_CASES])
+def test_device_sector_builder_is_bit_identical_to_the_reference_convention(oracle, name, L, ndown, k):
+    """Representatives, row order, norms and every matrix element of generate_Ham_sparse_repr (src/model.cc:688-836)
+    against tests/repr_builders.py, which is itself pinned bit for bit to matrices assembled by the compiled
+    reference (tests/golden/repr_hashes.json)."""
+    import repr_builders as R
+    bonds = _sector_bonds(L)
+    S, ia, ja, val = R.heisenberg_sector_upper_csr(L, ndown, k, bonds)
+    sec = qb.Sector(L, ndown, k)
+    assert sec.dim == S.n and sec.lin_order == S.lin_order and sec.zero_norm == int((S.nu == 0).sum())
+    assert np.array_equal(sec.states().astype(np.uint64), S.states)
+    assert np.array_equal(sec.norms(), S.nu)
+    M = sec.heisenberg(bonds, flags=1)                       # QBGPU_KEEP_COMPLEX: compare complex values as assembled
+    rowptr, col, v = M.download_expanded()
+    eia, eja, ev = _expanded(S.n, ia, ja, val, oracle)
+    assert M.dim == S.n and M.info.nnz_input == ja.size
+    assert np.array_equal(rowptr, eia) and np.array_equal(col.astype(np.int64), eja)
+    assert np.array_equal(v, ev)
+    sec.free()
+
+
+def test_device_sector_matches_the_golden_reference_matrix_and_E0(oracle):
+    """The k=3 sector of the L=16 chain: same matrix as the one the reference assembled (golden), and its published
+    E0 (examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_half.cc:102-117) from the device Lanczos."""
+    A, meta, ex = oracle.load_golden("heis16_k3")
+    sec = qb.Sector([16], 8, [3])
+    M = sec.heisenberg(_sector_bonds([16]), flags=1)
+    rowptr, col, v = M.download_expanded()
+    eia, eja, ev = oracle.expand_upper(A)
+    assert np.array_equal(rowptr, eia) and np.array_equal(col.astype(np.int64), eja) and np.array_equal(v, ev)
+    E = qb.locate_E0_lanczos(M, nev=1, ncv=0)["eigenvals"]
+    assert abs(E[0] - meta["golden_E0"]) < 1e-8
+
+
+def test_device_sector_real_momenta_are_stored_as_fp64_and_config2_style_sector_runs():
+    """k = 0 gives a real matrix (demoted to fp64 values); chain L=24: 112,720 representatives in well under a second."""
+    sec = qb.Sector([24], 12, [0])
+    M = sec.heisenberg(_sector_bonds([24]))
+    assert M.info.val_is_real == 1 and sec.zero_norm == 0 and sec.dim == 112720
+    E = qb.locate_E0_lanczos(M, nev=1, ncv=0)["eigenvals"]
+    assert abs(E[0] / 24 - (-0.4438)) < 2e-3         # Bethe-ansatz energy density -ln2 + 1/4 up to finite-size corrections

@@ -35,6 +35,10 @@ WORKLOADS = {
     "heis_chain24": ("heisenberg", dict(L=24)),
     "heis_chain28": ("heisenberg", dict(L=28)),
     "heis_chain30": ("heisenberg", dict(L=30)),
+    # translation-symmetric sectors assembled on the device in the reference's representative convention (sectors.cu)
+    "heis_chain32_k0": ("heisenberg_k", dict(L=32, k=0)),                           # BASELINE config 2
+    "heis_chain28_k1": ("heisenberg_k", dict(L=28, k=1)),                           # one sector of BASELINE config 5
+    "heis_chain24_k3": ("heisenberg_k", dict(L=24, k=3)),
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
@@ -110,6 +114,9 @@ def run_reference(args, workload):
     if fam == "hubbard":
         sample_args = ["hubbard", 4, 3, 6, 6, p["t"], p["U"]]
         sample_desc = "Fermi-Hubbard 4x3, N_up=N_dn=6 (dim 853,776; 12,030,480 stored upper-triangle entries), reference-assembled"
+    elif fam == "heisenberg_k":
+        sample_args = ["heis_chain_k", 20, 0, p["k"] % 20]
+        sample_desc = f"Heisenberg chain L=20, Sz=0, momentum sector k={p['k'] % 20}, reference-assembled"
     else:
         Ls = min(p["L"], 22)
         sample_args = ["heis_chain", Ls, "sz", 0]
@@ -140,6 +147,8 @@ def workload_upper_nnz(workload):
     """Entries the reference stores (upper triangle incl. every diagonal) for a workload: (Z + n) / 2."""
     from math import comb
     fam, p = WORKLOADS[workload]
+    if fam == "heisenberg_k":
+        return _SECTOR_UPPER[workload]          # counted by the device assembler (qbgpu_matrix_info.nnz_input)
     if fam == "hubbard":
         ns = p["Lx"] * p["Ly"]
         n = comb(ns, p["nup"]) * comb(ns, p["ndn"])
@@ -155,6 +164,10 @@ def workload_upper_nnz(workload):
     return (z_off + n + n) // 2
 
 
+_SECTOR_UPPER = {"heis_chain32_k0": 173901570, "heis_chain28_k1": 11831544, "heis_chain24_k3": 817580}   # from runs of the assembler
+SECTOR_PHASES = {}
+
+
 # ------------------------------------------------------------------------------------------------------ our arm
 def build_matrix(qb, workload, row_range=None, flags=0):
     """BASELINE matrices generated directly in HBM (qbgpu_build_*), bit-identical to what the reference assembles."""
@@ -163,6 +176,19 @@ def build_matrix(qb, workload, row_range=None, flags=0):
     L = qb.lib()
     h = C.c_void_p()
     lo, hi = (0, -1) if row_range is None else row_range
+    if fam == "heisenberg_k":
+        if row_range is not None:
+            raise SystemExit("sector workloads are single-GPU in this round")
+        n = p["L"]
+        t0 = time.time()
+        sec = qb.Sector([n], n // 2, [p["k"]])
+        t1 = time.time()
+        M = sec.heisenberg([(x, (x + 1) % n) for x in range(n)], flags=flags)
+        SECTOR_PHASES.update(enumerate_representatives_s=sec.enumerate_seconds, norms_s=sec.norms_seconds, sector_total_s=t1 - t0,
+                             assemble_and_expand_s=time.time() - t1, zero_norm=sec.zero_norm, lin_order=sec.lin_order)
+        _SECTOR_UPPER[workload] = M.info.nnz_input
+        sec.free()
+        return M
     if fam == "hubbard":
         bonds = np.array(square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
         rc = L.qbgpu_build_hubbard(C.byref(h), p["Lx"] * p["Ly"], p["nup"], p["ndn"], len(bonds) // 2, bonds.ctypes.data,
@@ -323,7 +349,7 @@ def main():
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
                     "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
-            "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds}}
+            "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds, **SECTOR_PHASES}}
     line.update(extras)
 
     # ---------------------------------------------------------------- Lanczos iterations/s and E0 time-to-solution
@@ -359,7 +385,8 @@ def main():
             fam, p = WORKLOADS[args.workload]
             cores = os.cpu_count() or 1
             if O.have_qb_ref():
-                sample_args = ["hubbard", 4, 3, 6, 6, 1.0, 1.1] if fam == "hubbard" else ["heis_chain", min(p["L"], 22), "sz", 0]
+                sample_args = (["hubbard", 4, 3, 6, 6, 1.0, 1.1] if fam == "hubbard" else
+                               ["heis_chain_k", 20, 0, p["k"] % 20] if fam == "heisenberg_k" else ["heis_chain", min(p["L"], 22), "sz", 0])
                 res = O.run_qb_ref(sample_args + ["--time-mv", 5, 2], threads=cores, timeout=1200)
                 t_step = res["mv_total_s"] / res["mv_reps"]
                 scale = workload_upper_nnz(args.workload) / res["nnz"]

@@ -122,6 +122,7 @@ int qbgpu_malloc(void **dptr, size_t bytes);
 int qbgpu_free(void *dptr);
 int qbgpu_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int qbgpu_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int qbgpu_memcpy_d2d(void *dst, const void *src, size_t bytes);     /* stream-ordered, asynchronous */
 int qbgpu_memset0(void *dptr, size_t bytes);
 /* vec_randomize (src/miscellaneous.cc:371-388) generated on the device, bit-identical element values */
 int qbgpu_vec_randomize_d(int64_t n, double *x_dev, uint32_t seed);
@@ -265,6 +266,11 @@ int qbgpu_sector_norms(qbgpu_sector_t S, double *nu_host);
  * add_Ham calls); fake_pos is model's constructor argument (default 100, src/qbasis.h:1337). */
 int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J,
                                   double fake_pos, int flags);
+/* model::moprXvec_repr (src/model.cc:1716-1846) for A = sum_r c_r S^z_r (coef_reim[2*nsites], site order): device
+ * vectors x_old (sector S_old) -> y_new (sector S_new, same lattice and Sz, momentum shifted by the operator's q).
+ * With measure_repr_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1897-1912. */
+int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const double *coef_reim, const void *x_old_dev,
+                          void *y_new_dev);
 /* dimension of those sectors (host only) */
 int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);

@@ -74,5 +74,32 @@ def main():
               f"golden={golden} -> {os.path.getsize(out)/1e3:.0f} kB")
 
 
+DYNAMIC_CASES = {
+    # name: (L, Sz, k0, q, maxit) -- qb_ref heis_chain_szq: E0 and phi0 of sector k0, then A = sum_x exp(-i 2 pi q x/L)/sqrt(L) S^z_x
+    # applied by model::moprXvec_repr into sector k0 - q and model::measure_repr_dynamic's Lanczos coefficients
+    # (src/model.cc:1716-1846, 1897-1912)
+    "heis16_szq3": (16, 0, 0, 3, 60),
+    "heis16_szq8": (16, 0, 0, 8, 60),
+    "heis12_szq1": (12, 0, 0, 1, 40),
+}
+
+
+def make_dynamic():
+    for name, (L, sz, k0, q, maxit) in DYNAMIC_CASES.items():
+        wd = tempfile.mkdtemp(prefix="qbdyn_")
+        pre = os.path.join(wd, "v")
+        res = O.run_qb_ref(["heis_chain_szq", L, sz, k0, q, maxit, "--dump-vecs", pre], threads=4, workdir=wd)
+        phi0 = np.fromfile(pre + "_phi0.bin", dtype=np.complex128)
+        aphi = np.fromfile(pre + "_Aphi0.bin", dtype=np.complex128)
+        meta = {"case": name, "L": L, "Sz": sz, "k0": k0, "q": q, "maxit": maxit, "E0": res["E0"], "dyn_norm": res["dyn_norm"],
+                "dyn_steps": res["dyn_steps"]}
+        out = os.path.join(O.GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(out, phi0=phi0, Aphi0=aphi, dyn_a=np.array(res["dyn_a"]), dyn_b=np.array(res["dyn_b"]), meta=json.dumps(meta))
+        print(f"{name}: dim={phi0.size} E0={res['E0']:.12f} norm={res['dyn_norm']:.12f} steps={res['dyn_steps']} -> {os.path.getsize(out)/1e3:.0f} kB")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:2] == ["dynamic"]:
+        make_dynamic()
+    else:
+        main()

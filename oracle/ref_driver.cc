@@ -249,6 +249,13 @@ static Built build_honeycomb(int Lx, int Ly) {
 }
 
 /* ------------------------------------------------------------------ actions */
+
+/* Config-5 style flow of the reference, end to end (examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_one_excitation.cc:
+ * 95-128 with S^z instead of S^-): ground state of the sector (Sz, k0), then for momentum transfer q the sector k0 - q is
+ * enumerated as sector 1, A = sum_x exp(-i 2 pi q x / L) / sqrt(L) S^z_x is applied to phi0 (model::moprXvec_repr,
+ * src/model.cc:1716-1846) and model::measure_repr_dynamic (src/model.cc:1897-1912) returns the Lanczos coefficients. */
+static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, struct Json &js);
+
 struct Json {
     std::ostringstream o; bool first = true;
     Json() { o << std::setprecision(17) << "{"; }
@@ -259,6 +266,48 @@ struct Json {
     void arr(const std::string &k, const double *p, long long n) { key(k); o << "["; for (long long i = 0; i < n; i++) o << (i ? ", " : "") << p[i]; o << "]"; }
     std::string done() { o << "}"; return o.str(); }
 };
+
+
+static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, Json &js)
+{
+    qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
+    Model M(latt);
+    M.add_orbital(latt.Nsites, "spin-1/2");
+    for (int x = 0; x < L; x++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x}, 0, si, work); latt.coor2site({x + 1}, 0, sj, work);
+        add_heisenberg_bond(M, si, sj, 1.0);
+    }
+    M.fill_Weisse_table();
+    M.enumerate_basis_repr({k0}, {total_sz(latt.Nsites)}, {szval});
+    M.generate_Ham_sparse_repr();
+    M.locate_E0_lanczos(qbasis::which_sym::repr, 1, 1);
+    js.num("E0", M.eigenvals_repr[0]);
+    js.integer("dim0", M.dim_repr[0]);
+    std::vector<cplx> Sz{0.5, -0.5};
+    Mopr Szq;
+    const double Q = 2.0 * 3.1415926535897932 * q / static_cast<double>(L);
+    for (int x = 0; x < L; x++) {
+        uint32_t si; std::vector<int> work(latt.dim);
+        latt.coor2site({x}, 0, si, work);
+        Szq += (std::exp(cplx(0.0, -Q * x)) / std::sqrt(static_cast<double>(L))) * Opr(si, 0, false, Sz);
+    }
+    M.enumerate_basis_repr({k0 - q}, {total_sz(latt.Nsites)}, {szval}, 1);
+    M.generate_Ham_sparse_repr(1);
+    M.switch_sec_mat(1);
+    js.integer("dim1", M.dim_repr[1]);
+    if (!vec_prefix.empty()) {
+        std::vector<cplx> vnew(M.dim_repr[1]);
+        M.moprXvec_repr(Szq, 0, 1, static_cast<MKL_INT>(0), vnew.data());
+        dump_vec(vec_prefix + "_phi0.bin", M.eigenvecs_repr.data(), sizeof(cplx) * M.dim_repr[0]);
+        dump_vec(vec_prefix + "_Aphi0.bin", vnew.data(), sizeof(cplx) * M.dim_repr[1]);
+    }
+    std::vector<double> hess(2 * maxit, 0.0);
+    MKL_INT m = 0; double norm = 0.0;
+    M.measure_repr_dynamic(Szq, 0, 1, maxit, m, norm, hess.data());
+    js.num("dyn_norm", norm); js.integer("dyn_steps", m);
+    js.arr("dyn_b", hess.data(), m); js.arr("dyn_a", hess.data() + maxit, m);
+}
 
 template <typename T>
 static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, Json &js)
@@ -335,7 +384,8 @@ static void usage() {
     fprintf(stderr,
         "usage: qb_ref [--threads T] [--workdir D] --out results.json <case> <args...> [actions]\n"
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
-        "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr\n"
+        "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
+        "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
         " matrix actions: --dump F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
     exit(2);
@@ -362,6 +412,7 @@ int main(int argc, char **argv)
         const std::string &s = av[i];
         if ((s == "--dump" || s == "file_z" || s == "file_d") && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
         if ((s == "--mv" || s == "--cg") && i + 2 < argc) av[i + 2] = absolutise(av[i + 2]);
+        if (s == "--dump-vecs" && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
     }
     std::vector<char *> cargv;
     for (auto &s : av) cargv.push_back(const_cast<char *>(s.c_str()));
@@ -376,7 +427,13 @@ int main(int argc, char **argv)
     std::string c = argv[a++];
     js.str("case", c);
     double t0 = now_s();
-    if (c == "file_z" || c == "file_d") {
+    if (c == "heis_chain_szq") {
+        if (a + 5 > argc) usage();
+        int L = atoi(argv[a]); double sz = atof(argv[a + 1]); int k0 = atoi(argv[a + 2]), q = atoi(argv[a + 3]); MKL_INT maxit = atoll(argv[a + 4]); a += 5;
+        std::string prefix;
+        if (a + 1 < argc && std::string(argv[a]) == "--dump-vecs") { prefix = argv[a + 1]; a += 2; }
+        flow_heis_chain_szq(L, sz, k0, q, maxit, prefix, js);
+    } else if (c == "file_z" || c == "file_d") {
         if (a >= argc) usage();
         std::string path = argv[a++];
         if (c == "file_z") { qbasis::csr_mat<cplx> H; load_csr(H, path); run_actions(H, argc, argv, a, js); }

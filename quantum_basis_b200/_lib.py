@@ -50,7 +50,7 @@ _SIGS = {
     "qbgpu_dmv": [vp, dbl, vp, dbl, vp, C.c_int], "qbgpu_zmv": [vp, vp, vp, vp, vp, C.c_int],
     "qbgpu_host_register": [vp, C.c_size_t], "qbgpu_host_unregister": [vp],
     "qbgpu_malloc": [C.POINTER(vp), C.c_size_t], "qbgpu_free": [vp], "qbgpu_memcpy_h2d": [vp, vp, C.c_size_t],
-    "qbgpu_memcpy_d2h": [vp, vp, C.c_size_t], "qbgpu_memset0": [vp, C.c_size_t],
+    "qbgpu_memcpy_d2h": [vp, vp, C.c_size_t], "qbgpu_memcpy_d2d": [vp, vp, C.c_size_t], "qbgpu_memset0": [vp, C.c_size_t],
     "qbgpu_vec_randomize_d": [i64, vp, C.c_uint32], "qbgpu_vec_randomize_z": [i64, vp, C.c_uint32],
     "qbgpu_zdotc": [i64, vp, vp, vp], "qbgpu_ddot": [i64, vp, vp, vp], "qbgpu_dznrm2": [i64, vp, vp],
     "qbgpu_dnrm2": [i64, vp, vp], "qbgpu_zaxpy": [i64, vp, vp, vp], "qbgpu_daxpy": [i64, dbl, vp, vp],
@@ -78,6 +78,7 @@ _SIGS = {
     "qbgpu_sector_create": [C.POINTER(vp), C.c_int, vp, C.c_int, vp], "qbgpu_sector_destroy": [vp],
     "qbgpu_sector_get_info": [vp, C.POINTER(SectorInfo)], "qbgpu_sector_states": [vp, vp], "qbgpu_sector_norms": [vp, vp],
     "qbgpu_sector_build_heisenberg": [vp, C.POINTER(vp), C.c_int, vp, dbl, dbl, C.c_int],
+    "qbgpu_sector_apply_sz": [vp, vp, vp, vp, vp],
 }
 _RESTYPES = {"qbgpu_last_error": C.c_char_p, "qbgpu_version": C.c_char_p, "qbgpu_kernel_launches": C.c_int64,
              "qbgpu_dim_heisenberg": C.c_int64, "qbgpu_dim_hubbard": C.c_int64}

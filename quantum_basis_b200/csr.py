@@ -67,6 +67,12 @@ class DeviceVector:
         w.n, w.dtype, w.ptr, w._owned, w._parent = int(n), self.dtype, self.ptr + offset * self.dtype.itemsize, False, self
         return w
 
+    def clone(self):
+        """A new device vector with the same contents (device-to-device copy)."""
+        v = DeviceVector(self.n, self.dtype)
+        check(lib().qbgpu_memcpy_d2d(C.c_void_p(v.ptr), C.c_void_p(self.ptr), self.n * self.dtype.itemsize))
+        return v
+
     def to_numpy(self):
         out = np.empty(self.n, dtype=self.dtype)
         check(lib().qbgpu_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr), out.nbytes))
@@ -270,6 +276,17 @@ class Sector:
         check(lib().qbgpu_sector_build_heisenberg(self._h, C.byref(h), nb, C.c_void_p(b.ctypes.data), float(J), float(fake_pos), flags))
         return csr_mat._adopt(h, True)
 
+    def apply_sz(self, new_sector, coef, x, out=None):
+        """model::moprXvec_repr (src/model.cc:1716-1846) for A = sum_r coef[r] S^z_r: x (DeviceVector or host array in this
+        sector) -> DeviceVector in `new_sector` (written into `out` when given)."""
+        cf = np.ascontiguousarray(coef, dtype=np.complex128)
+        if cf.size != self.nsites:
+            raise QbgpuError("one coefficient per site")
+        xd = x if isinstance(x, DeviceVector) else DeviceVector.from_numpy(np.ascontiguousarray(x, dtype=np.complex128))
+        y = out if out is not None else DeviceVector(self.dim)
+        check(lib().qbgpu_sector_apply_sz(self._h, new_sector._h, C.c_void_p(cf.ctypes.data), C.c_void_p(xd.ptr), C.c_void_p(y.ptr)))
+        return y
+
     def free(self):
         if self._h:
             lib().qbgpu_sector_destroy(self._h)
@@ -280,6 +297,25 @@ class Sector:
             self.free()
         except Exception:
             pass
+
+
+def measure_repr_dynamic(coef, sec_old, sec_new, mat_new, phi0, maxit, hessenberg):
+    """model<T>::measure_repr_dynamic (src/model.cc:1897-1912) for A = sum_r coef[r] S^z_r, everything on the device:
+    vec = A phi0 mapped into sec_new (moprXvec_repr), norm = |vec|, then lanczos(0, maxit-1, maxit, ..., "dnmcs") from
+    vec/norm on `mat_new`.  Returns (m, norm); hessenberg[2*maxit] receives b in [0, m) and a in [maxit, maxit+m)."""
+    n = sec_new.dim
+    v = DeviceVector(2 * n)
+    v.zero()
+    sec_old.apply_sz(sec_new, coef, phi0, out=v.view(0, n))
+    nr = C.c_double()
+    check(lib().qbgpu_dznrm2(n, C.c_void_p(v.ptr), C.byref(nr)))
+    if abs(nr.value) < lanczos_precision:
+        v.free()
+        return 0, nr.value
+    check(lib().qbgpu_zscal(n, (C.c_double * 2)(1.0 / nr.value, 0.0), C.c_void_p(v.ptr)))
+    m = lanczos(0, maxit - 1, maxit, n, mat_new, v, hessenberg, "dnmcs")
+    v.free()
+    return m, nr.value
 
 
 def vec_randomize(n, seed=1, dtype=np.complex128, device=False):
@@ -440,7 +476,7 @@ def locate_E0_iram(mat, nev=2, ncv=6, maxit=0, device_resident=False):
     return out
 
 
-def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000):
+def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000, device_vectors=False):
     """The csr_mat branch of model<T>::locate_E0_lanczos (src/model.cc:1124-1316): E0 by simple Lanczos, ground-state
     vector by CG, optionally E1 (re-orthogonalised Lanczos) and its vector.  Everything stays on the device; returns a
     dict with eigenvals, eigenvecs (host arrays), step counts and accuracies."""
@@ -489,6 +525,8 @@ def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000):
         out["gap"] = ritz[0] - E0
         out["lanczos_steps_E1"] = m1
     out["eigenvecs"].append(col(2).to_numpy())
+    if device_vectors:                       # keep phi0 in HBM for what follows (moprXvec / measure_*_dynamic)
+        out["eigenvecs_device"] = [col(2).clone()]
     if ncv == 2:                                                               # :1275-1315
         check(rnd(n, C.c_void_p(col(3).ptr), seed + 7))
         mcg1, accu1 = eigenvec_CG(n, maxit, 0, mat, out["eigenvals"][1], col(3), col(0), col(1), col(4))

@@ -129,6 +129,12 @@ int qbgpu_memcpy_h2d(void *dst, const void *src, size_t bytes)
     QB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return QBGPU_OK;
 }
+int qbgpu_memcpy_d2d(void *dst, const void *src, size_t bytes)
+{
+    QB_TRY(ensure_init());
+    QB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
+    return QBGPU_OK;
+}
 int qbgpu_memcpy_d2h(void *dst, const void *src, size_t bytes)
 {
     QB_TRY(ensure_init());

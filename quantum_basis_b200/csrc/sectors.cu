@@ -276,9 +276,36 @@ __global__ void __launch_bounds__(kSBlock) sec_len_kernel(int64_t n, const int64
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) len[r] = end[r] - start[r];
 }
 
-// y_new[j] of the target sector from x_old of the source sector for the diagonal operator
-//   A_q = sum_r exp(-2 pi i q.r / L) S^z_r     (the reference's S^z_q of measure_repr_dynamic's callers)
-// is built in moprXvec_repr (src/model.cc:1716-1848); see qbgpu_sector_apply_szq below.
+// model::moprXvec_repr (src/model.cc:1716-1846) for an operator made of diagonal one-site terms, A = sum_r c_r S^z_r
+// (S^z_q when c_r = exp(-i q.r)/sqrt(N)): only the momentum changes, the representative keeps its row index, and
+//   y[j] = sum_r  sqrt(nu_old[j] / nu_new[j]) * x[j] * (c_r * <state_j| S^z_r |state_j>)          (:1758-1761)
+// with rows skipped when |x[j]|, nu_old[j] or nu_new[j] is below lanczos_precision (:1752, :1760).
+__global__ void __launch_bounds__(kSBlock) sec_apply_sz_kernel(SecDev S, const double *__restrict__ nu_new, const double2 *__restrict__ coef,
+                                                               const double2 *__restrict__ x, double2 *y)
+{
+    __shared__ double2 c[kMaxTrans];
+    if (threadIdx.x < S.nsites) c[threadIdx.x] = coef[threadIdx.x];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double2 xj = x[r];
+        const double nj = S.nu[r], ni = nu_new[r];
+        double2 acc = make_double2(0.0, 0.0);
+        if (hypot(xj.x, xj.y) >= 2e-12 && fabs(nj) >= 2e-12 && fabs(ni) > 2e-12) {
+            uint32_t a, b;
+            sec_halves(S, S.keys[r], a, b);
+            const uint32_t st = spread_bits(a) | (spread_bits(b) << 1);
+            const double w = __dsqrt_rn(__ddiv_rn(nj, ni));
+            const double2 t = make_double2(__dmul_rn(w, xj.x), __dmul_rn(w, xj.y));
+            for (int site = 0; site < S.nsites; site++) {
+                const double sz = ((st >> site) & 1u) ? -0.5 : 0.5;
+                const double2 d = make_double2(__dmul_rn(c[site].x, sz), __dmul_rn(c[site].y, sz));
+                acc.x = __dadd_rn(acc.x, __dsub_rn(__dmul_rn(t.x, d.x), __dmul_rn(t.y, d.y)));
+                acc.y = __dadd_rn(acc.y, __dadd_rn(__dmul_rn(t.x, d.y), __dmul_rn(t.y, d.x)));
+            }
+        }
+        y[r] = acc;
+    }
+}
 
 static double wall_clock() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct FlagToInt { __host__ __device__ int operator()(uint8_t f) const { return (int)f; } };
@@ -578,6 +605,27 @@ int qbgpu_sector_norms(qbgpu_sector_t S, double *nu_host)
     Context &c = ctx();
     QB_CUDA(cudaMemcpyAsync(nu_host, S->d_nu, sizeof(double) * (size_t)S->n, cudaMemcpyDeviceToHost, c.stream));
     QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const double *coef_reim, const void *x_old_dev, void *y_new_dev)
+{
+    if (!S_old || !S_new || !coef_reim || !x_old_dev || !y_new_dev) return fail(QBGPU_ERR_ARG, "sector_apply_sz: null argument");
+    if (S_old->n != S_new->n || S_old->nsites != S_new->nsites || S_old->ndown != S_new->ndown || S_old->dim != S_new->dim ||
+        memcmp(S_old->L, S_new->L, sizeof(S_old->L)) != 0 || S_old->dev.lin_order != S_new->dev.lin_order)
+        return fail(QBGPU_ERR_ARG, "sector_apply_sz: the two sectors must share lattice and Sz (same representatives)");
+    Context &c = ctx();
+    double2 *d_coef = nullptr;
+    QB_CUDA(cudaMalloc(&d_coef, sizeof(double2) * kMaxTrans));
+    cudaError_t e = cudaMemcpyAsync(d_coef, coef_reim, sizeof(double2) * S_old->nsites, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) {
+        sec_apply_sz_kernel<<<sgrid(S_old->n), kSBlock, 0, c.stream>>>(S_old->dev, S_new->d_nu, d_coef, (const double2 *)x_old_dev, (double2 *)y_new_dev);
+        QB_LAUNCH_COUNT();
+        e = cudaStreamSynchronize(c.stream);
+    }
+    cudaFree(d_coef);
+    QB_CUDA(e);
+    QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
 }
 

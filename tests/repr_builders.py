@@ -346,3 +346,25 @@ def heisenberg_sector_upper_csr(L, ndown, k, bonds, J=1.0, fake_pos=100.0, secto
     ia = np.zeros(n + 1, dtype=np.int64)
     np.add.at(ia, gr + 1, 1)
     return S, np.cumsum(ia), gc.astype(np.int64), gv
+
+
+def apply_sz(S_old, S_new, coef, x):
+    """model::moprXvec_repr (src/model.cc:1716-1846) restricted to diagonal one-site terms A = sum_r coef[r] S^z_r:
+    y[j] = sum_r sqrt(nu_old[j]/nu_new[j]) * x[j] * coef[r] * sz_r(state_j); rows with |x[j]|, nu_old[j] or nu_new[j]
+    below lanczos_precision contribute nothing (:1752, :1760)."""
+    assert S_old.n == S_new.n and np.array_equal(S_old.states, S_new.states)
+    u = np.uint64
+    y = np.zeros(S_old.n, dtype=np.complex128)
+    ok = (np.abs(x) >= 2e-12) & (S_old.nu >= 2e-12) & (S_new.nu > 2e-12)
+    t = np.zeros(S_old.n, dtype=np.complex128)
+    t[ok] = np.sqrt(S_old.nu[ok] / S_new.nu[ok]) * x[ok]
+    for r in range(S_old.N):
+        sz = np.where((S_old.states >> u(r)) & u(1), -0.5, 0.5)
+        y += t * (coef[r] * sz)
+    return y
+
+
+def szq_coefficients(L, q):
+    """exp(-i 2 pi q x / L) / sqrt(L) per site of a chain (oracle/ref_driver.cc flow_heis_chain_szq)."""
+    Q = 2.0 * 3.1415926535897932 * q / float(L)
+    return np.array([cmath.exp(complex(0.0, -Q * x)) / math.sqrt(float(L)) for x in range(L)])

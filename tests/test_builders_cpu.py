@@ -68,3 +68,20 @@ def test_sector_builder_against_golden_matrices(oracle, name, L, k, tri):
     dead = np.nonzero(S.nu == 0)[0]
     for i in dead[:5]:
         assert ia[i + 1] - ia[i] == 1 and val[ia[i]] == 100.0 + i / S.n
+
+
+@pytest.mark.parametrize("name", ["heis16_szq3", "heis16_szq8", "heis12_szq1"])
+def test_sector_sz_operator_matches_reference_moprXvec(name):
+    """A = sum_x exp(-i 2 pi q x/L)/sqrt(L) S^z_x applied between momentum sectors: the restatement of
+    model::moprXvec_repr against the vector the compiled reference produced from its own phi0 (golden)."""
+    import json
+    import os
+    import repr_builders as R
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    L, q, k0 = meta["L"], meta["q"], meta["k0"]
+    S0 = R.Sector([L], L // 2, [k0])
+    S1 = R.Sector([L], L // 2, [k0 - q])
+    y = R.apply_sz(S0, S1, R.szq_coefficients(L, q), z["phi0"])
+    assert np.abs(y - z["Aphi0"]).max() < 1e-15
+    assert abs(np.linalg.norm(y) - meta["dyn_norm"]) < 1e-14

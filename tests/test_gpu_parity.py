@@ -696,3 +696,52 @@ def test_device_sector_real_momenta_are_stored_as_fp64_and_config2_style_sector_
     assert M.info.val_is_real == 1 and sec.zero_norm == 0 and sec.dim == 112720
     E = qb.locate_E0_lanczos(M, nev=1, ncv=0)["eigenvals"]
     assert abs(E[0] / 24 - (-0.4438)) < 2e-3         # Bethe-ansatz energy density -ln2 + 1/4 up to finite-size corrections
+
+
+# ------------------------------------------------------------------ S^z_q between momentum sectors + dnmcs Lanczos (config 5)
+def _dyn_golden(name):
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+@pytest.mark.parametrize("name", ["heis16_szq3", "heis16_szq8", "heis12_szq1"])
+def test_sector_sz_operator_and_dynamic_lanczos_match_the_reference(name):
+    """model::moprXvec_repr + measure_repr_dynamic (src/model.cc:1716-1846, 1897-1912) on the device against vectors and
+    Lanczos coefficients produced by the compiled reference (oracle/make_golden.py dynamic)."""
+    import repr_builders as R
+    z, meta = _dyn_golden(name)
+    L, q, k0, maxit = meta["L"], meta["q"], meta["k0"], meta["maxit"]
+    s0, s1 = qb.Sector([L], L // 2, [k0]), qb.Sector([L], L // 2, [k0 - q])
+    coef = R.szq_coefficients(L, q)
+    y = s0.apply_sz(s1, coef, z["phi0"]).to_numpy()
+    assert np.abs(y - z["Aphi0"]).max() < 1e-15
+    H1 = s1.heisenberg(R.chain_bonds(L))
+    hess = np.zeros(2 * maxit)
+    m, norm = qb.measure_repr_dynamic(coef, s0, s1, H1, z["phi0"], maxit, hess)
+    assert m == meta["dyn_steps"] and abs(norm - meta["dyn_norm"]) < 1e-14
+    # S^z_q phi0 lives in a small symmetry sector (total spin 1): once its Krylov space is exhausted the recursion only
+    # amplifies rounding, in the reference as well, so the comparison is on the leading coefficients
+    k = min(m, 10)
+    assert np.abs(hess[maxit:maxit + k] - z["dyn_a"][:k]).max() < 1e-10
+    assert np.abs(hess[:k] - z["dyn_b"][:k]).max() < 1e-10
+
+
+def test_config5_flow_on_the_device_end_to_end():
+    """E0 and phi0 of the (Sz=0, k=0) sector by Lanczos + CG, S^z_q phi0 in the k=-q sector, dnmcs coefficients and KPM
+    moments from it -- nothing leaves HBM between the steps.  E0, |S^z_q phi0| and the leading coefficients against the
+    reference's own run of the same flow."""
+    import repr_builders as R
+    z, meta = _dyn_golden("heis16_szq3")
+    L, q, maxit = 16, 3, 60
+    s0, s1 = qb.Sector([L], 8, [0]), qb.Sector([L], 8, [-q])
+    H0, H1 = s0.heisenberg(R.chain_bonds(L)), s1.heisenberg(R.chain_bonds(L))
+    res = qb.locate_E0_lanczos(H0, nev=1, ncv=1, device_vectors=True)
+    assert abs(res["eigenvals"][0] - meta["E0"]) < 1e-9
+    phi0 = res["eigenvecs_device"][0]
+    hess = np.zeros(2 * maxit)
+    m, norm = qb.measure_repr_dynamic(R.szq_coefficients(L, q), s0, s1, H1, phi0, maxit, hess)
+    assert abs(norm - meta["dyn_norm"]) < 1e-8
+    assert np.abs(hess[maxit:maxit + 10] - z["dyn_a"][:10]).max() < 1e-6
+    assert np.abs(hess[1:10] - z["dyn_b"][1:10]).max() < 1e-6

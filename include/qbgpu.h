@@ -215,6 +215,8 @@ int qbgpu_ipc_export(void *dptr, void *handle64);
 int qbgpu_ipc_open(const void *handle64, void **peer_ptr);
 int qbgpu_ipc_close(void *peer_ptr);
 int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes);
+/* same, moved by `ctas` thread blocks reading the peer mapping directly (16-byte aligned) instead of a copy engine */
+int qbgpu_peer_pull_sm(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ctas);
 int qbgpu_peer_wait(int slot);
 
 /* --------------------------------------------------------------------- on-device Hamiltonian generators

@@ -21,11 +21,37 @@ struct PeerState {
 };
 static thread_local PeerState g_peer;
 
+// SM-driven pull: a few CTAs read the peer's slice through the NVLink mapping with 16-byte volatile-cached loads (L1 is
+// not trusted across kernels for peer memory; nothing is kept) and store it locally.  Sixteen independent loads per
+// thread and trip keep enough requests in flight to cover the NVLink round trip; the lanes are highest-priority streams
+// so that these CTAs take SM slots ahead of the queued CTAs of the product that runs beside them.
+constexpr int kPullThreads = 256;
+constexpr int kPullUnroll = 16;            // 16 x 16 B per thread = 64 KB in flight per CTA (NVLink round trip ~2.5 us)
+__global__ void __launch_bounds__(kPullThreads) peer_pull_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    constexpr size_t kTile = (size_t)kPullThreads * kPullUnroll;
+    for (size_t base = (size_t)blockIdx.x * kTile; base < n16; base += (size_t)gridDim.x * kTile) {
+        uint4 r[kPullUnroll];
+#pragma unroll
+        for (int u = 0; u < kPullUnroll; u++) {
+            const size_t i = base + (size_t)u * kPullThreads + threadIdx.x;
+            if (i < n16) r[u] = __ldcv(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kPullUnroll; u++) {
+            const size_t i = base + (size_t)u * kPullThreads + threadIdx.x;
+            if (i < n16) __stcs(dst + i, r[u]);
+        }
+    }
+}
+
 static int peer_init()
 {
     if (g_peer.ready) return QBGPU_OK;
+    int prio_lo = 0, prio_hi = 0;
+    QB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int i = 0; i < kPeerLanes; i++) {
-        QB_CUDA(cudaStreamCreateWithFlags(&g_peer.lane[i], cudaStreamNonBlocking));
+        QB_CUDA(cudaStreamCreateWithPriority(&g_peer.lane[i], cudaStreamNonBlocking, prio_hi));
         QB_CUDA(cudaEventCreateWithFlags(&g_peer.arrived[i], cudaEventDisableTiming));
     }
     QB_CUDA(cudaEventCreateWithFlags(&g_peer.fence, cudaEventDisableTiming));
@@ -77,6 +103,24 @@ int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_p
     QB_CUDA(cudaEventRecord(g_peer.fence, c.stream));
     QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
     QB_CUDA(cudaMemcpyAsync(dst_local, src_peer, bytes, cudaMemcpyDefault, g_peer.lane[lane]));
+    QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
+    return QBGPU_OK;
+}
+
+/* The same pull done by `ctas` thread blocks instead of a copy engine (bytes and both pointers multiples of 16). */
+int qbgpu_peer_pull_sm(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ctas)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    if (lane < 0 || lane >= kPeerLanes || slot < 0 || slot >= kPeerLanes || !dst_local || !src_peer || ctas < 1) return fail(QBGPU_ERR_ARG, "peer_pull_sm: bad argument");
+    if ((bytes & 15) || ((uintptr_t)dst_local & 15) || ((uintptr_t)src_peer & 15)) return fail(QBGPU_ERR_ARG, "peer_pull_sm: 16-byte alignment required");
+    Context &c = ctx();
+    QB_CUDA(cudaEventRecord(g_peer.fence, c.stream));
+    QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
+    if (bytes) {
+        peer_pull_kernel<<<ctas, kPullThreads, 0, g_peer.lane[lane]>>>((uint4 *)dst_local, (const uint4 *)src_peer, bytes / 16);
+        QB_LAUNCH_COUNT();
+    }
     QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
     return QBGPU_OK;
 }

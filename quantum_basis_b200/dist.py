@@ -154,17 +154,21 @@ class PeerExchangeOperator:
     The ping-pong plus the barrier make the pulls race-free: a slice is overwritten only two products later, after a
     barrier that every puller has passed."""
 
-    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod, lanes=None):
+    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod, lanes=None, mode=None, ctas=None, groups=None):
         self.qb, self.L, self.k, self.n, self.rank, self.world, self.comm, self.torch = qb, qb.lib(), kernels, n, rank, world, comm, torch_mod
-        # copy streams in use: pulls on one stream run back to back at the full NVLink rate and therefore arrive in the
-        # order the blocks are multiplied (ring order: at distance d every GPU serves exactly one reader)
-        # (measured on 8 B200: all 7 pulls in flight at once 6.45 ms per product, 2 at a time 7.47 ms: the copy engines
-        # deliver ~310-390 GB/s per GPU either way, so keep every path busy)
-        self.lanes = int(os.environ.get("QB_PEER_LANES", str(max(1, min(world - 1, 8))))) if lanes is None else lanes
+        # copy streams in use.  One lane: the pulls run back to back, each at the full single-flow NVLink rate (measured
+        # 718-726 GB/s), and arrive in ring order -- the order the blocks are multiplied, and at ring distance d every
+        # GPU serves exactly one reader.  Measured on 8 B200 (profiles/r01_peer_variants_n8.jsonl): the exchange alone
+        # takes 3.2-3.3 ms with 1 or 7 lanes, but with 7 lanes every slice arrives at the end and nothing overlaps:
+        # 6.58 ms per product against 5.08 ms with one lane.
+        self.lanes = int(os.environ.get("QB_PEER_LANES", "1")) if lanes is None else lanes
+        # "ce": copy-engine transfers (cudaMemcpyAsync); "sm": qbgpu_peer_pull_sm, `ctas` thread blocks per transfer
+        self.mode = (mode or os.environ.get("QB_PEER_MODE", "ce")).lower()
+        self.ctas = int(os.environ.get("QB_PEER_CTAS", "16")) if ctas is None else ctas
         self.bounds, self.chunk = equal_row_bounds(n, world)
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.esize = 8 * kernels.ncomp
-        self.order = [(rank + d) % world for d in range(1, world)]
+        self.configure(kernels, groups)
         self.col_bounds = [min(n, p * self.chunk) for p in range(world)] + [n]
         nbytes = self.chunk * world * self.esize
         self.X = [RawBuf(qb, nbytes), RawBuf(qb, nbytes)]
@@ -187,6 +191,25 @@ class PeerExchangeOperator:
                 self.peer[b][p] = out.value
         self.token = torch_mod.zeros(1, dtype=torch_mod.float64, device="cuda")
 
+    def configure(self, kernels, groups=None, mode=None, ctas=None, lanes=None):
+        """(Re)select the column blocks -- kernels.parts[g] covers the owners groups[g] = (first, last+1), default one
+        block per owner -- and optionally the transfer mode, on the same exported buffers."""
+        rank, world = self.rank, self.world
+        assert 8 * kernels.ncomp == self.esize
+        self.k = kernels
+        self.groups = groups if groups is not None else [(p, p + 1) for p in range(world)]
+        self.own_group = next(g for g, (a, b) in enumerate(self.groups) if a <= rank < b)
+        assert self.groups[self.own_group] == (rank, rank + 1), "the own slice must be a block of its own"
+        others = [g for g in range(len(self.groups)) if g != self.own_group]
+        self.group_order = sorted(others, key=lambda g: (self.groups[g][0] - rank) % world)      # ring order
+        self.order = [p for g in self.group_order for p in range(*self.groups[g])]
+        if mode is not None:
+            self.mode = mode
+        if ctas is not None:
+            self.ctas = ctas
+        if lanes is not None:
+            self.lanes = lanes
+
     def own(self, b):
         """this rank's slice of buffer b (where the caller writes its part of the vector)"""
         return self.X[b].view(self.lo * self.esize)
@@ -196,29 +219,57 @@ class PeerExchangeOperator:
             off = self.bounds[p] * self.esize
             nb = (self.bounds[p + 1] - self.bounds[p]) * self.esize
             if nb:
-                rc = self.L.qbgpu_peer_pull_async(idx % self.lanes, p, C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off), nb)
+                dst, src = C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off)
+                if self.mode == "sm":
+                    rc = self.L.qbgpu_peer_pull_sm(idx % self.lanes, p, dst, src, nb, self.ctas)
+                else:
+                    rc = self.L.qbgpu_peer_pull_async(idx % self.lanes, p, dst, src, nb)
                 assert rc == 0, self.L.qbgpu_last_error()
 
-    def _wait(self, p):
-        assert self.L.qbgpu_peer_wait(p) == 0, self.L.qbgpu_last_error()
+    def _wait_group(self, g):
+        for p in range(*self.groups[g]):
+            if self.bounds[p + 1] > self.bounds[p]:
+                assert self.L.qbgpu_peer_wait(p) == 0, self.L.qbgpu_last_error()
+
+    def pull_only(self, b):
+        """the exchange alone (for measuring it): all pulls, then the compute stream waits for every arrival"""
+        self.comm.all_reduce(self.token)
+        self.pull(b)
+        for g in self.group_order:
+            self._wait_group(g)
 
     def matvec(self, b, y_local, barrier=True):
         if barrier:
             self.comm.all_reduce(self.token)
         self.pull(b)
-        self.k.multmv_part(self.rank, self.X[b], y_local, accumulate=False)
-        for p in self.order:
-            self._wait(p)
-            self.k.multmv_part(p, self.X[b], y_local, accumulate=True)
+        self.k.multmv_part(self.own_group, self.X[b], y_local, accumulate=False)
+        for g in self.group_order:
+            self._wait_group(g)
+            self.k.multmv_part(g, self.X[b], y_local, accumulate=True)
 
     def lanczos_step_a(self, b, uz, state):
         """x = X[b] (all slices final: the caller's previous all-reduce is the barrier), w accumulated into uz"""
         self.pull(b)
-        last = len(self.order)
-        self.k.lanczos_step_a_part(self.rank, self.X[b], uz, state, True, last == 0)
-        for idx, p in enumerate(self.order):
-            self._wait(p)
-            self.k.lanczos_step_a_part(p, self.X[b], uz, state, False, idx == last - 1)
+        last = len(self.group_order)
+        self.k.lanczos_step_a_part(self.own_group, self.X[b], uz, state, True, last == 0)
+        for idx, g in enumerate(self.group_order):
+            self._wait_group(g)
+            self.k.lanczos_step_a_part(g, self.X[b], uz, state, False, idx == last - 1)
+
+
+def peer_groups(world, rank, size):
+    """Column blocks for PeerExchangeOperator: the own slice alone, the other owners in runs of `size` neighbours growing
+    away from it -> [(first, last+1), ...] in column order."""
+    out = [(rank, rank + 1)]
+    p = rank
+    while p > 0:
+        out.append((max(0, p - size), p))
+        p = max(0, p - size)
+    p = rank + 1
+    while p < world:
+        out.append((p, min(world, p + size)))
+        p = min(world, p + size)
+    return sorted(out)
 
 
 def peer_lanczos(op, steps, state, a_dev, b_dev, start_buffer=0):

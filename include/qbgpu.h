@@ -218,6 +218,18 @@ int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_p
 /* same, moved by `ctas` thread blocks reading the peer mapping directly (16-byte aligned) instead of a copy engine */
 int qbgpu_peer_pull_sm(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ctas);
 int qbgpu_peer_wait(int slot);
+/* Ring-fused sharded product: ONE kernel that multiplies the whole row shard while the peers' vector slices are still
+ * arriving.  qbgpu_ring_prepare(A, rank, world, chunk, &view) re-orders every row of the shard A (rows [rank*chunk, ...),
+ * chunk a multiple of 4) so that its own rank's columns come first and the others in ring order, and returns a view
+ * handle sharing A's arrays (destroy it before A): every product with the VIEW (qbgpu_{d,z}mv, qbgpu_lanczos_step_a)
+ * waits, entry by entry, for the arrival flag of the slice it is about to gather from; A itself keeps working with the
+ * ordinary kernels.  Per product: qbgpu_peer_ring_reset(), then one qbgpu_peer_pull_flag(lane, slot, dst, src, bytes, d) per
+ * peer (d = (owner - rank + world) % world; every d in 1..world-1 must be issued, with bytes = 0 for an empty slice),
+ * then the product.  A waiter gives up after ~1 s instead of hanging the device: check qbgpu_peer_ring_status. */
+int qbgpu_ring_prepare(qbgpu_matrix_t A, int rank, int world, int64_t chunk, qbgpu_matrix_t *ring_view);
+int qbgpu_peer_ring_reset(void);
+int qbgpu_peer_pull_flag(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ring_distance);
+int qbgpu_peer_ring_status(int *timed_out);
 
 /* --------------------------------------------------------------------- on-device Hamiltonian generators
  * The reference assembles H on the host (model::generate_Ham_sparse_full, src/model.cc:619-716) in Lin-table

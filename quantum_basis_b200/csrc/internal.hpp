@@ -33,6 +33,11 @@ struct qbgpu_matrix {
     // QBGPU_FORMAT_MATFREE: no stored entries at all; `mf` owns the sector tables, the bond list and the per-row
     // basis states from which every row is regenerated inside the product (builders.cu).
     void    *mf = nullptr;
+    // ring-fused row shard (qbgpu_ring_prepare): every row's entries are rotated so that the columns owned by this rank
+    // come first, then those of rank+1, ... (ring order); the product then consumes the vector slices in the order the
+    // peer pulls deliver them and waits, entry by entry, on the arrival flags of peer.cu.
+    int      ring_world = 0, ring_rank = 0;
+    int64_t  ring_chunk = 0;
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
@@ -65,6 +70,8 @@ int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &args);     // bu
 void matfree_destroy(qbgpu_matrix *A);
 int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
+int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view);     // sjds.cu
+int peer_ring_flags(const int **flags, int **timeout_flag);                 // peer.cu: arrival flags by ring distance
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // expand a device-resident reference-format CSR (int64 row_start/row_end/col, offsets from 0) into a new handle

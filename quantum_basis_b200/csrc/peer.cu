@@ -17,6 +17,8 @@ struct PeerState {
     cudaStream_t lane[kPeerLanes] = {};
     cudaEvent_t arrived[kPeerLanes] = {};
     cudaEvent_t fence = nullptr;
+    int *flags = nullptr;              // [kPeerLanes + 1] arrival flags by ring distance; last entry: a waiter timed out
+    int *one = nullptr;                // device constant 1, the source of the flag-setting copies
     bool ready = false;
 };
 static thread_local PeerState g_peer;
@@ -55,7 +57,19 @@ static int peer_init()
         QB_CUDA(cudaEventCreateWithFlags(&g_peer.arrived[i], cudaEventDisableTiming));
     }
     QB_CUDA(cudaEventCreateWithFlags(&g_peer.fence, cudaEventDisableTiming));
+    QB_CUDA(cudaMalloc(&g_peer.flags, sizeof(int) * (kPeerLanes + 1)));
+    QB_CUDA(cudaMalloc(&g_peer.one, sizeof(int)));
+    QB_CUDA(cudaMemset(g_peer.flags, 0, sizeof(int) * (kPeerLanes + 1)));
+    const int h_one = 1;
+    QB_CUDA(cudaMemcpy(g_peer.one, &h_one, sizeof(int), cudaMemcpyHostToDevice));
     g_peer.ready = true;
+    return QBGPU_OK;
+}
+
+int peer_ring_flags(const int **flags, int **timeout_flag)
+{
+    QB_TRY(peer_init());
+    *flags = g_peer.flags; *timeout_flag = g_peer.flags + kPeerLanes;
     return QBGPU_OK;
 }
 
@@ -123,6 +137,49 @@ int qbgpu_peer_pull_sm(int lane, int slot, void *dst_local, const void *src_peer
     }
     QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
     return QBGPU_OK;
+}
+
+/* Ring-fused product (sjds.cu: spmv_sjds_ring_kernel).  qbgpu_peer_ring_reset clears the arrival flags on the compute
+ * stream; qbgpu_peer_pull_flag is qbgpu_peer_pull_async followed, on the same lane, by a 4-byte copy-engine write that
+ * sets flags[ring_distance] -- no SM is needed to signal an arrival, so the product kernel may occupy every SM and spin;
+ * qbgpu_peer_ring_status reports whether a waiter ever gave up (it does after ~1 s instead of hanging the GPU). */
+int qbgpu_peer_ring_reset(void)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    QB_CUDA(cudaMemsetAsync(g_peer.flags, 0, sizeof(int) * kPeerLanes, ctx().stream));
+    return QBGPU_OK;
+}
+
+int qbgpu_peer_pull_flag(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ring_distance)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    if (lane < 0 || lane >= kPeerLanes || slot < 0 || slot >= kPeerLanes || ring_distance < 1 || ring_distance >= kPeerLanes || !dst_local || !src_peer)
+        return fail(QBGPU_ERR_ARG, "peer_pull_flag: bad argument");
+    Context &c = ctx();
+    QB_CUDA(cudaEventRecord(g_peer.fence, c.stream));
+    QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
+    if (bytes) QB_CUDA(cudaMemcpyAsync(dst_local, src_peer, bytes, cudaMemcpyDefault, g_peer.lane[lane]));
+    QB_CUDA(cudaMemcpyAsync(g_peer.flags + ring_distance, g_peer.one, sizeof(int), cudaMemcpyDeviceToDevice, g_peer.lane[lane]));
+    QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
+    return QBGPU_OK;
+}
+
+int qbgpu_peer_ring_status(int *timed_out)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(peer_init());
+    if (!timed_out) return fail(QBGPU_ERR_ARG, "null argument");
+    QB_CUDA(cudaMemcpyAsync(timed_out, g_peer.flags + kPeerLanes, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    QB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QBGPU_OK;
+}
+
+int qbgpu_ring_prepare(qbgpu_matrix_t A, int rank, int world, int64_t chunk, qbgpu_matrix_t *ring_view)
+{
+    QB_TRY(ensure_init());
+    return ring_prepare(A, rank, world, chunk, ring_view);
 }
 
 /* Order everything issued afterwards on the compute stream behind the pull recorded in `slot`. */

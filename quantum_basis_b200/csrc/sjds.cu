@@ -269,8 +269,162 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
                 : launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB>(A, a);
 }
 
+
+// ------------------------------------------------------------------------------------------ ring-fused product
+// One kernel for "exchange, then multiply" on a row shard: the vector slices of the other ranks are pulled
+// over NVLink by copy engines while this kernel runs; each pull ends by setting flags[d] (d = ring distance of the
+// owner).  The rows of the shard were rotated into ring order by ring_prepare, so a row meets its own rank's columns
+// first and the others in the order of their arrival; before gathering x[c] a lane makes sure the slice c belongs to
+// has landed.  No column blocks, no partial y, no extra passes over rowptr/rowinfo: the unsplit shard is read once.
+__device__ __forceinline__ int ld_acquire_sys(const int *p) { int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+template <typename ValT, typename VecT, bool DOTS, int U>
+__global__ void __launch_bounds__(kSBlock, 4)
+spmv_sjds_ring_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
+                      const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
+                      const VecT *x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
+                      int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
+                      const double *__restrict__ vdict, const int *flags, int *timed_out, unsigned chunk, int rank, int world)
+{
+    using VT = VecTraits<VecT>;
+    constexpr bool kDict = sizeof(ValT) == 1;
+    using ArithT = typename std::conditional<kDict, double, ValT>::type;
+    __shared__ double sdict[kDict ? 256 : 1];
+    if (kDict) { sdict[threadIdx.x] = vdict[threadIdx.x]; __syncthreads(); }
+    constexpr int WPB = kSBlock / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol_s = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+        dot_scale = sx;
+    }
+    const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    double d[3] = {0.0, 0.0, 0.0};
+    int have = 0;                                           // flags[0 .. have] have been seen set by this lane (0 = own slice)
+
+    for (int64_t s = (int64_t)blockIdx.x * WPB + warp; s < nslices; s += (int64_t)gridDim.x * WPB) {
+        const uint32_t info = rowinfo[s * 32 + lane];
+        const int len = (int)(info & kLenMask);
+        const int64_t row = s * 32 + (info >> 24);
+        const int maxlen = __shfl_sync(0xffffffffu, len, 0);
+        const int64_t base = rowptr[s * 32];
+        int64_t off = base + lane;
+        VecT acc0 = VT::zero(), acc1 = VT::zero();
+        for (int k = 0; k < maxlen; k += U) {
+            bool a[U];
+            int64_t o[U];
+            int c[U];
+            ValT v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                a[u] = k + u < len;
+                o[u] = off;
+                off += __popc(__ballot_sync(0xffffffffu, a[u]));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                c[u] = 0; v[u] = ValT{};
+                if (a[u]) { c[u] = ld_i32<2>(col + o[u], pol_s); v[u] = ld_f64<2>(val + o[u], pol_s); }
+            }
+            // the furthest slice this trip needs (ring order inside a row: the distance never decreases)
+            int need = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (a[u]) {
+                    int owner = (int)((unsigned)c[u] / chunk);
+                    owner = owner < world ? owner : world - 1;
+                    int dist = owner - rank; dist += dist < 0 ? world : 0;
+                    need = dist > need ? dist : need;
+                }
+            }
+            if (need > have) {
+                for (int f = have + 1; f <= need; f++) {
+                    const long long t0 = clock64();
+                    while (ld_acquire_sys(flags + f) == 0) {
+                        if (clock64() - t0 > (1LL << 31)) { atomicExch(timed_out, 1); break; }     // ~1 s: never hang the GPU
+                        __nanosleep(200);
+                    }
+                }
+                have = need;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (a[u]) {
+                    ArithT w;
+                    if constexpr (kDict) w = sdict[v[u]]; else w = v[u];
+                    if (u & 1) mac(acc1, w, ld_x<1>(x + c[u], pol_x)); else mac(acc0, w, ld_x<1>(x + c[u], pol_x));
+                }
+            }
+        }
+        if (row < nrows) {
+            const VecT acc = VT::add(acc0, acc1);
+            VecT out = VT::scale(alpha, acc);
+            VecT xi = VT::zero();
+            if (use_gamma || DOTS) xi = x[row_lo + row];
+            if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
+            if (use_beta) out = VT::add(out, VT::scale(beta, z[row]));
+            y[row] = out;
+            if (DOTS) {
+                const double2 p = VT::conj_mul(xi, out);
+                d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
+            }
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kSBlock>(d, partials, ticket, dots_out);
+    }
+}
+
+template <typename ValT, typename VecT, bool DOTS>
+static int launch_sjds_ring(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    Context &c = ctx();
+    constexpr int U = sizeof(VecT) == 16 ? 4 : 8;
+    auto kern = spmv_sjds_ring_kernel<ValT, VecT, DOTS, U>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kSBlock, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int64_t nrows = A->nrows();
+    if (nrows == 0) return QBGPU_OK;
+    const int *flags = nullptr; int *timed_out = nullptr;
+    QB_TRY(peer_ring_flags(&flags, &timed_out));
+    const int64_t nslices = (nrows + 31) / 32;
+    constexpr int WPB = kSBlock / 32;
+    int64_t want = (nslices + WPB - 1) / WPB;
+    int64_t cap = (int64_t)c.num_sms * blocks_per_sm;
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    const int grid = (int)(want < cap ? want : cap);
+    kern<<<grid, kSBlock, 0, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
+                                         (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
+                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, A->vdict, flags, timed_out,
+                                         (unsigned)A->ring_chunk, A->ring_rank, A->ring_world);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+template <typename ValT, typename VecT>
+static int launch_sjds_ring_typed(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    return a.dots ? launch_sjds_ring<ValT, VecT, true>(A, a) : launch_sjds_ring<ValT, VecT, false>(A, a);
+}
+
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)
 {
+    if (A->ring_world > 1) {
+        if (A->ndict) return A->api_complex ? launch_sjds_ring_typed<uint8_t, double2>(A, a) : launch_sjds_ring_typed<uint8_t, double>(A, a);
+        if (!A->api_complex) return launch_sjds_ring_typed<double, double>(A, a);
+        if (A->val_real) return launch_sjds_ring_typed<double, double2>(A, a);
+        return launch_sjds_ring_typed<double2, double2>(A, a);
+    }
     if (A->ndict) return A->api_complex ? launch_sjds_typed<uint8_t, double2>(A, a) : launch_sjds_typed<uint8_t, double>(A, a);
     if (!A->api_complex) return launch_sjds_typed<double, double>(A, a);
     if (A->val_real) return launch_sjds_typed<double, double2>(A, a);
@@ -372,6 +526,58 @@ int sjds_convert(qbgpu_matrix *A, bool forward)
     if (forward == (A->format == QBGPU_FORMAT_SELL)) return QBGPU_OK;
     if (A->ndict) return sjds_convert_typed<uint8_t>(A, forward);
     return A->val_real ? sjds_convert_typed<double>(A, forward) : sjds_convert_typed<double2>(A, forward);
+}
+
+// ------------------------------------------------------------------------------------------ ring order of a shard
+// CSR layout, one thread per row: rotate the (ascending) entries so that the first one is the first column >= pivot
+// (three reversals, in place).
+template <typename ValT>
+__global__ void __launch_bounds__(kSBlock) ring_rotate_kernel(int64_t nrows, const int64_t *__restrict__ rowptr, int32_t *col, ValT *val, int32_t pivot_col)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = rowptr[r], e = rowptr[r + 1];
+        int64_t lo = s, hi = e;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (col[mid] < pivot_col) lo = mid + 1; else hi = mid; }
+        const int64_t p = lo;                               // entries [s, p) move behind [p, e)
+        if (p == s || p == e) continue;
+        auto rev = [&](int64_t i, int64_t j) {              // reverse [i, j)
+            for (j--; i < j; i++, j--) { const int32_t tc = col[i]; col[i] = col[j]; col[j] = tc; const ValT tv = val[i]; val[i] = val[j]; val[j] = tv; }
+        };
+        rev(s, p); rev(p, e); rev(s, e);
+    }
+}
+
+int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view)
+{
+    Context &c = ctx();
+    if (!A || A->mf || A->borrowed) return fail(QBGPU_ERR_ARG, "ring_prepare: needs an owning, stored matrix handle");
+    if (!view) return fail(QBGPU_ERR_ARG, "ring_prepare: null view pointer");
+    *view = nullptr;
+    if (A->ring_world) return fail(QBGPU_ERR_STATE, "ring_prepare: already in ring order");
+    if (world < 2 || rank < 0 || rank >= world || chunk <= 0 || chunk > 0x7fffffff) return fail(QBGPU_ERR_ARG, "ring_prepare: bad rank/world/chunk");
+    if (chunk % 4) return fail(QBGPU_ERR_ARG, "ring_prepare: the slice length must be a multiple of 4 rows (32-byte sectors must not straddle two owners)");
+    if (A->row_lo != (int64_t)rank * chunk) return fail(QBGPU_ERR_ARG, "ring_prepare: the shard does not start at rank * chunk");
+    const bool was_sell = A->format == QBGPU_FORMAT_SELL;
+    if (was_sell) QB_TRY(sjds_convert(A, false));
+    const int64_t nrows = A->nrows();
+    const int grid = (int)std::min<int64_t>((nrows + kSBlock - 1) / kSBlock, 148 * 32);
+    const int32_t pivot = (int32_t)A->row_lo;
+    if (nrows) {
+        if (A->ndict) ring_rotate_kernel<uint8_t><<<grid, kSBlock, 0, c.stream>>>(nrows, A->rowptr, A->col, (uint8_t *)A->val, pivot);
+        else if (A->val_real) ring_rotate_kernel<double><<<grid, kSBlock, 0, c.stream>>>(nrows, A->rowptr, A->col, (double *)A->val, pivot);
+        else ring_rotate_kernel<double2><<<grid, kSBlock, 0, c.stream>>>(nrows, A->rowptr, A->col, (double2 *)A->val, pivot);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+    }
+    QB_TRY(sjds_convert(A, true));                          // the ring kernel exists for the sliced-jagged layout only
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    // The waiting kernel is selected through a VIEW that shares A's arrays; A itself keeps working (its rows are merely in
+    // a different order) with the ordinary kernels, e.g. behind an all-gather.
+    auto *V = new qbgpu_matrix(*A);
+    V->borrowed = true;
+    V->ring_world = world; V->ring_rank = rank; V->ring_chunk = chunk;
+    *view = V;
+    return QBGPU_OK;
 }
 
 }  // namespace qb

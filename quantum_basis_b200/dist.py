@@ -19,8 +19,11 @@ import numpy as np
 
 
 def equal_row_bounds(n, parts):
-    """Contiguous row partition with equal row counts (the last block may be shorter); chunk = rows per block."""
+    """Contiguous row partition with equal row counts (the last block may be shorter); chunk = rows per block, a multiple
+    of 32 so that no 32-byte sector of a vector (and no 32-row slice of the layout) straddles two owners."""
     chunk = (n + parts - 1) // parts
+    if parts > 1:
+        chunk = (chunk + 31) // 32 * 32
     return [min(n, p * chunk) for p in range(parts + 1)], chunk
 
 
@@ -231,6 +234,42 @@ class PeerExchangeOperator:
             if self.bounds[p + 1] > self.bounds[p]:
                 assert self.L.qbgpu_peer_wait(p) == 0, self.L.qbgpu_last_error()
 
+    # ---- ring-fused product: ONE kernel over the unsplit shard that consumes the slices as they land (sjds.cu) ----
+    def enable_ring(self, ring_kernels):
+        """ring_kernels: DeviceKernels over the view returned by ring_view() (rows in ring order, waiting kernel)"""
+        self.kr = ring_kernels
+
+    @staticmethod
+    def ring_view(qb, matrix, rank, world, chunk):
+        h = C.c_void_p()
+        rc = qb.lib().qbgpu_ring_prepare(matrix.handle, rank, world, chunk, C.byref(h))
+        assert rc == 0, qb.lib().qbgpu_last_error()
+        return qb.csr_mat._adopt(h, True)
+
+    def pull_ring(self, b):
+        assert self.L.qbgpu_peer_ring_reset() == 0, self.L.qbgpu_last_error()
+        for d in range(1, self.world):
+            p = (self.rank + d) % self.world
+            off = self.bounds[p] * self.esize
+            nb = (self.bounds[p + 1] - self.bounds[p]) * self.esize
+            rc = self.L.qbgpu_peer_pull_flag((d - 1) % self.lanes, p, C.c_void_p(self.X[b].ptr + off), C.c_void_p(self.peer[b][p] + off), nb, d)
+            assert rc == 0, self.L.qbgpu_last_error()
+
+    def matvec_ring(self, b, y_local, barrier=True):
+        if barrier:
+            self.comm.all_reduce(self.token)
+        self.pull_ring(b)
+        self.kr.multmv(self.X[b], y_local)
+
+    def lanczos_step_a_ring(self, b, uz, state):
+        self.pull_ring(b)
+        self.kr.lanczos_step_a(self.X[b], uz, state)
+
+    def ring_timed_out(self):
+        t = C.c_int(0)
+        assert self.L.qbgpu_peer_ring_status(C.byref(t)) == 0, self.L.qbgpu_last_error()
+        return bool(t.value)
+
     def pull_only(self, b):
         """the exchange alone (for measuring it): all pulls, then the compute stream waits for every arrival"""
         self.comm.all_reduce(self.token)
@@ -272,14 +311,18 @@ def peer_groups(world, rank, size):
     return sorted(out)
 
 
-def peer_lanczos(op, steps, state, a_dev, b_dev, start_buffer=0):
+def peer_lanczos(op, steps, state, a_dev, b_dev, start_buffer=0, ring=False):
     """Fused Lanczos on the shards with the peer-pull exchange.  The normalised start slice is in op.own(start_buffer)
-    and must already be visible to the peers (call op.comm.all_reduce(op.token) after writing it)."""
-    k, comm = op.k, op.comm
+    and must already be visible to the peers (call op.comm.all_reduce(op.token) after writing it).  ring=True: the
+    ring-fused single-kernel product (op.enable_ring) instead of one product per column block."""
+    k, comm = (op.kr if ring else op.k), op.comm
     for m in range(1, steps + 1):
         bx, bz = (start_buffer + m - 1) % 2, (start_buffer + m) % 2
         ux, uz = op.own(bx), op.own(bz)
-        op.lanczos_step_a(bx, uz, state)
+        if ring:
+            op.lanczos_step_a_ring(bx, uz, state)
+        else:
+            op.lanczos_step_a(bx, uz, state)
         comm.all_reduce(k.slot(state, 3))
         k.lanczos_step_b(ux, uz, state)
         comm.all_reduce(k.slot(state, 6))                      # also the barrier that makes X[bz] final everywhere

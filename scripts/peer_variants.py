@@ -66,6 +66,8 @@ def main():
         [f"g1-ce-l{full_l}", f"g2-ce-l{full_l}", f"g4-ce-l{full_l}", "g2-ce-l2", "g4-ce-l1", "g1-ce-l1", f"g1-sm16-l{full_l}", f"g2-sm16-l{full_l}"])
     variants = []
     for v in spec:
+        if v.count("-") != 2:               # e.g. the "noring" switch
+            continue
         gs, ms_, ls = v.split("-")
         variants.append((int(gs[1:]), ms_[:2], int(ms_[2:] or 0), int(ls[1:])))
     results = []
@@ -106,6 +108,36 @@ def main():
         if rank == 0:
             print(json.dumps(rec), flush=True)
         del y
+    # ring-fused: one kernel over the unsplit shard (rows rotated into ring order) consuming the slices as they land
+    if op is not None and "noring" not in a.variants:
+        torch.cuda.synchronize(); dist.barrier()
+        ringM = qd.PeerExchangeOperator.ring_view(qb, M, rank, world, chunk)
+        kr = qd.DeviceKernels(qb, ringM, real=False)
+        op.enable_ring(kr)
+        op.configure(kern, groups, lanes=1, mode="ce")
+        y = kr.alloc(chunk)
+        op.matvec_ring(0, y)
+        torch.cuda.synchronize()
+        bad = torch.tensor([1.0 if op.ring_timed_out() else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(bad)
+        if float(bad.item()) == 0.0:
+            for lanes in ((1, 2) if world > 2 else (1,)):
+                op.configure(kern, groups, lanes=lanes, mode="ce")
+                ms = qd._timed(torch, dist, stream, lambda: op.matvec_ring(0, y), a.steps, a.warmup)
+                err = float((y - y_ref).abs().max().item()) / max(1e-300, float(y_ref.abs().max().item()))
+                errt = torch.tensor([err], dtype=torch.float64, device="cuda")
+                dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+                rec = {"variant": f"ring-fused-l{lanes}", "group": 0, "mode": "ce", "lanes": lanes, "ms": ms, "blocks": 1,
+                       "max_rel_err_vs_allgather": float(errt.item()), "timed_out": op.ring_timed_out()}
+                results.append(rec)
+                if rank == 0:
+                    print(json.dumps(rec), flush=True)
+            # the rotated shard behind a plain all-gather (ordinary kernel on the same arrays)
+            ms_rot = qd._timed(torch, dist, stream, lambda: kern0.multmv(opA.x_full, y), a.steps, a.warmup)
+            if rank == 0:
+                print(json.dumps({"variant": "local_product_rotated_rows", "ms": ms_rot}), flush=True)
+        elif rank == 0:
+            print(json.dumps({"variant": "ring-fused", "error": "a waiter timed out: arrival flags were not set"}), flush=True)
     if rank == 0 and results:
         best = min(results, key=lambda r: r["ms"])
         print(json.dumps({"summary": True, "n_gpus": world, "allgather_ms": msA, "local_product_ms": ms_local, "best": best}), flush=True)

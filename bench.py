@@ -39,6 +39,9 @@ WORKLOADS = {
     "heis_chain32_k0": ("heisenberg_k", dict(L=32, k=0)),                           # BASELINE config 2
     "heis_chain28_k1": ("heisenberg_k", dict(L=28, k=1)),                           # one sector of BASELINE config 5
     "heis_chain24_k3": ("heisenberg_k", dict(L=24, k=3)),
+    # tilted clusters: orbit-minimum representatives (orbit.cu); the reference cannot build these
+    "tri31_k10": ("orbit", dict(A0=(5, 1), A1=(-1, 6), ndown=15, m=(1, 0))),           # BASELINE config 4
+    "tri21_k10": ("orbit", dict(A0=(4, 1), A1=(-1, 5), ndown=10, m=(1, 0))),
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
@@ -117,6 +120,9 @@ def run_reference(args, workload):
     elif fam == "heisenberg_k":
         sample_args = ["heis_chain_k", 20, 0, p["k"] % 20]
         sample_desc = f"Heisenberg chain L=20, Sz=0, momentum sector k={p['k'] % 20}, reference-assembled"
+    elif fam == "orbit":
+        sample_args = ["tri_k", 4, 5, 0, 3, 2]
+        sample_desc = "triangular 4x5 Heisenberg, Sz=0, momentum sector (3,2) (complex csr_mat, the largest 2-D sector the reference assembles in seconds), reference-assembled"
     else:
         Ls = min(p["L"], 22)
         sample_args = ["heis_chain", Ls, "sz", 0]
@@ -147,7 +153,7 @@ def workload_upper_nnz(workload):
     """Entries the reference stores (upper triangle incl. every diagonal) for a workload: (Z + n) / 2."""
     from math import comb
     fam, p = WORKLOADS[workload]
-    if fam == "heisenberg_k":
+    if fam in ("heisenberg_k", "orbit"):
         return _SECTOR_UPPER[workload]          # counted by the device assembler (qbgpu_matrix_info.nnz_input)
     if fam == "hubbard":
         ns = p["Lx"] * p["Ly"]
@@ -164,7 +170,8 @@ def workload_upper_nnz(workload):
     return (z_off + n + n) // 2
 
 
-_SECTOR_UPPER = {"heis_chain32_k0": 173901570, "heis_chain28_k1": 11831544, "heis_chain24_k3": 817580}   # from runs of the assembler
+_SECTOR_UPPER = {"heis_chain32_k0": 173901570, "heis_chain28_k1": 11831544, "heis_chain24_k3": 817580,    # from runs of the assembler
+                 "tri31_k10": 242371008, "tri21_k10": 293829}
 SECTOR_PHASES = {}
 
 
@@ -176,6 +183,16 @@ def build_matrix(qb, workload, row_range=None, flags=0):
     L = qb.lib()
     h = C.c_void_p()
     lo, hi = (0, -1) if row_range is None else row_range
+    if fam == "orbit":
+        if row_range is not None:
+            raise SystemExit("sector workloads are single-GPU in this round")
+        from quantum_basis_b200.clusters import Cluster
+        cl = Cluster(p["A0"], p["A1"])
+        t0 = time.time()
+        M = qb.heisenberg_orbit(cl.det, p["ndown"], cl.translations(), cl.characters(p["m"]), cl.triangular_bonds(), flags=flags)
+        SECTOR_PHASES.update(enumerate_and_assemble_s=time.time() - t0, sites=cl.det)
+        _SECTOR_UPPER[workload] = M.info.nnz_input
+        return M
     if fam == "heisenberg_k":
         if row_range is not None:
             raise SystemExit("sector workloads are single-GPU in this round")
@@ -386,7 +403,8 @@ def main():
             cores = os.cpu_count() or 1
             if O.have_qb_ref():
                 sample_args = (["hubbard", 4, 3, 6, 6, 1.0, 1.1] if fam == "hubbard" else
-                               ["heis_chain_k", 20, 0, p["k"] % 20] if fam == "heisenberg_k" else ["heis_chain", min(p["L"], 22), "sz", 0])
+                               ["heis_chain_k", 20, 0, p["k"] % 20] if fam == "heisenberg_k" else
+                               ["tri_k", 4, 5, 0, 3, 2] if fam == "orbit" else ["heis_chain", min(p["L"], 22), "sz", 0])
                 res = O.run_qb_ref(sample_args + ["--time-mv", 5, 2], threads=cores, timeout=1200)
                 t_step = res["mv_total_s"] / res["mv_reps"]
                 scale = workload_upper_nnz(args.workload) / res["nnz"]

@@ -285,6 +285,15 @@ int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbond
  * With measure_repr_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1897-1912. */
 int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const double *coef_reim, const void *x_old_dev,
                           void *y_new_dev);
+/* Momentum sector for an ARBITRARY abelian symmetry group given as site permutations (BASELINE config 4: the tilted
+ * 31-site triangular cluster, which the reference itself cannot build -- SURVEY F5 -- so there is no reference convention
+ * to reproduce; representative = smallest bit pattern of the orbit, orbits on whose stabiliser the character is not
+ * trivial are dropped, rows ascending by representative).  perms[t*nsites + s] = image of site s under group element t
+ * (element 0 = identity), chi_reim[2t], chi_reim[2t+1] = character of element t in the wanted one-dimensional irrep.
+ * states_out (host, may be NULL) receives the representatives if states_capacity >= dimension. */
+int qbgpu_build_heisenberg_orbit(qbgpu_matrix_t *A, int nsites, int ndown, int ntrans, const int32_t *perms,
+                                 const double *chi_reim, int nbonds, const int32_t *bonds, double J, int flags,
+                                 uint32_t *states_out, int64_t states_capacity);
 /* dimension of those sectors (host only) */
 int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);

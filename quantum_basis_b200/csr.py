@@ -240,6 +240,26 @@ def hubbard(nsites, nup, ndn, bonds, t=1.0, U=0.0, is_complex=True, flags=0, row
     return csr_mat._adopt(h, is_complex)
 
 
+def heisenberg_orbit(nsites, ndown, perms, chi, bonds, J=1.0, flags=0, return_states=False):
+    """Spin-1/2 Heisenberg model in the sector of a one-dimensional irrep of an abelian symmetry group given as site
+    permutations `perms[t][s]` (element 0 the identity) with characters `chi[t]`: orbit-minimum representatives, no
+    reference counterpart (tilted clusters).  Returns a csr_mat (and the representatives)."""
+    pa = np.ascontiguousarray(perms, dtype=np.int32)
+    ca = np.ascontiguousarray(chi, dtype=np.complex128)
+    if pa.ndim != 2 or pa.shape[1] != nsites or ca.size != pa.shape[0]:
+        raise QbgpuError("perms must be [ntrans, nsites] with one character per group element")
+    b, nb = _bond_array(bonds)
+    h = C.c_void_p()
+    from math import comb
+    cap = comb(nsites, ndown) if return_states else 0
+    st = np.empty(max(1, cap), dtype=np.uint32)
+    check(lib().qbgpu_build_heisenberg_orbit(C.byref(h), nsites, ndown, pa.shape[0], C.c_void_p(pa.ctypes.data), C.c_void_p(ca.ctypes.data),
+                                             nb, C.c_void_p(b.ctypes.data), float(J), flags,
+                                             C.c_void_p(st.ctypes.data) if return_states else None, cap))
+    M = csr_mat._adopt(h, True)
+    return (M, st[:M.dim].copy()) if return_states else M
+
+
 class Sector:
     """One (Sz, momentum) sector of a spin-1/2 model on an untilted lattice: the device counterpart of
     model::fill_Weisse_table + enumerate_basis_repr (src/model.cc:205-249, 275-487).  Representatives, their order and

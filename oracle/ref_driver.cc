@@ -322,6 +322,12 @@ static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, 
         std::string opt = argv[a];
         if (opt == "--dump" && a + 1 < argc) {
             dump_csr(H, argv[++a]);
+        } else if (opt == "--vec-write" && a + 2 < argc) {
+            /* vec_randomize(seed) written by the reference's vec_disk_write (src/miscellaneous.cc:437-468) */
+            uint32_t seed = (uint32_t)atoi(argv[++a]);
+            std::vector<T> x(n);
+            qbasis::vec_randomize(n, x.data(), seed);
+            qbasis::vec_disk_write(argv[++a], n, x.data());
         } else if (opt == "--mv" && a + 2 < argc) {
             /* y = H x for x = vec_randomize(seed); dump y (reference csr_mat::MultMv, src/sparse.cc:291-297) */
             uint32_t seed = (uint32_t)atoi(argv[++a]);
@@ -387,7 +393,7 @@ static void usage() {
         "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
-        " matrix actions: --dump F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
+        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
     exit(2);
 }
 
@@ -411,7 +417,7 @@ int main(int argc, char **argv)
     for (int i = a; i < argc; i++) {
         const std::string &s = av[i];
         if ((s == "--dump" || s == "file_z" || s == "file_d") && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
-        if ((s == "--mv" || s == "--cg") && i + 2 < argc) av[i + 2] = absolutise(av[i + 2]);
+        if ((s == "--mv" || s == "--cg" || s == "--vec-write") && i + 2 < argc) av[i + 2] = absolutise(av[i + 2]);
         if (s == "--dump-vecs" && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
     }
     std::vector<char *> cargv;

@@ -93,6 +93,41 @@ class DeviceVector:
             pass
 
 
+def vec_disk_write(filename, x):
+    """vec_disk_write (src/miscellaneous.cc:437-468): int64 n, the raw elements, CRC-32 of both (boost::crc_32_type, the
+    zlib polynomial) -- the file format of the reference's checkpoints and saved eigenvectors, so vectors computed here
+    can be picked up by a CPU run of the reference and vice versa.  x: host array or DeviceVector (float64 / complex128)."""
+    import struct
+    import zlib
+    a = x.to_numpy() if isinstance(x, DeviceVector) else np.ascontiguousarray(x)
+    if a.dtype not in (np.float64, np.complex128):
+        raise QbgpuError("vec_disk_write: float64 or complex128")
+    head = struct.pack("<q", a.size)
+    crc = zlib.crc32(a.tobytes(), zlib.crc32(head)) & 0xFFFFFFFF
+    with open(filename, "wb") as f:
+        f.write(head)
+        f.write(a.tobytes())
+        f.write(struct.pack("<I", crc))
+    return 0
+
+
+def vec_disk_read(filename, n, dtype=np.complex128, device=False):
+    """vec_disk_read (src/miscellaneous.cc:391-434): returns the vector, or None where the reference returns 1 (missing
+    file, wrong size, wrong n, checksum mismatch)."""
+    import os
+    import struct
+    import zlib
+    dt = np.dtype(dtype)
+    if not os.path.exists(filename) or os.path.getsize(filename) != 8 + dt.itemsize * n + 4:
+        return None
+    with open(filename, "rb") as f:
+        b = f.read()
+    if struct.unpack("<q", b[:8])[0] != n or struct.unpack("<I", b[-4:])[0] != (zlib.crc32(b[:-4]) & 0xFFFFFFFF):
+        return None
+    a = np.frombuffer(b, dtype=dt, count=n, offset=8).copy()
+    return DeviceVector.from_numpy(a) if device else a
+
+
 class csr_mat:
     """Device-resident counterpart of the reference's csr_mat<T> (qbasis.h:976-1021).
 

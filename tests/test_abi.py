@@ -133,3 +133,20 @@ def test_hess_smallest_matches_full_solve(L, oracle):
     t = C.c_double()
     assert L.qbgpu_hess_smallest(hess.ctypes.data, maxit, m, C.byref(t)) == 0
     assert abs(t.value - meta["lanczos_E0"]) <= 1e-13 * abs(meta["lanczos_E0"])
+
+
+def test_vector_files_are_the_reference_format(tmp_path, oracle):
+    """vec_disk_write / vec_disk_read (src/miscellaneous.cc:391-468): a file written by the compiled reference
+    (tests/golden/vec70_seed3.qbvec = vec_randomize(70, seed 3)) is read back, and a file written here is byte-identical."""
+    import os
+    import quantum_basis_b200 as qb
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vec70_seed3.qbvec")
+    x = qb.vec_disk_read(g, 70)
+    assert x is not None and np.abs(x - oracle.vec_randomize(70, 3)).max() < 1e-15
+    assert qb.vec_disk_read(g, 71) is None and qb.vec_disk_read(g, 70, dtype=np.float64) is None
+    out = str(tmp_path / "v.qbvec")
+    qb.vec_disk_write(out, x)
+    assert open(out, "rb").read() == open(g, "rb").read()
+    bad = bytearray(open(g, "rb").read()); bad[100] ^= 1
+    open(out, "wb").write(bytes(bad))
+    assert qb.vec_disk_read(out, 70) is None                      # checksum mismatch -> the reference's return 1

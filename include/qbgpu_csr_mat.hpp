@@ -45,6 +45,15 @@ public:
     }
     // from any object with the reference csr_mat's public members (qbasis.h:976-985)
     template <typename RefCsr> explicit csr_mat(const RefCsr &ref, int flags = 0) : csr_mat(ref.dim, ref.nnz, ref.sym, ref.val, ref.ja, ref.ia, flags) {}
+    // adopt a handle produced by one of the on-device assemblers (qbgpu_build_*, qbgpu_sector_build_heisenberg, ...)
+    static csr_mat adopt(qbgpu_matrix_t h)
+    {
+        csr_mat m;
+        qbgpu_matrix_info inf;
+        check(qbgpu_matrix_get_info(h, &inf), "qbgpu_matrix_get_info");
+        m.dim = inf.n; m.nnz = inf.nnz_input; m.sym = true; m.handle = h;
+        return m;
+    }
     csr_mat(const csr_mat &) = delete;
     csr_mat &operator=(const csr_mat &) = delete;
     csr_mat(csr_mat &&o) noexcept : dim(o.dim), nnz(o.nnz), sym(o.sym), handle(o.handle) { o.handle = nullptr; }
@@ -94,6 +103,36 @@ private:
         } else {
             check(qbgpu_dmv(handle, alpha, reinterpret_cast<const double *>(x), beta, reinterpret_cast<double *>(y), QBGPU_HOST), "matrix-vector product");
         }
+    }
+};
+
+// One (Sz, momentum) sector of a spin-1/2 model: the device counterpart of model::fill_Weisse_table +
+// enumerate_basis_repr + generate_Ham_sparse_repr (src/model.cc:205-249, 275-487, 688-836) with the reference's
+// representatives, row order, norms and matrix elements.  A maintainer fills basis_repr / norm_repr from states() /
+// norms() and HamMat_csr_repr from heisenberg().
+class sector {
+public:
+    qbgpu_sector_t handle = nullptr;
+    qbgpu_sector_info info{};
+    sector(const std::vector<int> &L, int ndown, const std::vector<int> &momentum)
+    {
+        if (L.size() != momentum.size()) throw std::runtime_error("qbgpu::sector: one momentum integer per lattice direction");
+        std::vector<int32_t> l(L.begin(), L.end()), k(momentum.begin(), momentum.end());
+        check(qbgpu_sector_create(&handle, static_cast<int>(l.size()), l.data(), ndown, k.data()), "qbgpu_sector_create");
+        check(qbgpu_sector_get_info(handle, &info), "qbgpu_sector_get_info");
+    }
+    sector(const sector &) = delete;
+    sector &operator=(const sector &) = delete;
+    ~sector() { if (handle) qbgpu_sector_destroy(handle); }
+    int64_t dim() const { return info.dim; }
+    std::vector<uint32_t> states() const { std::vector<uint32_t> s(info.dim); check(qbgpu_sector_states(handle, s.data()), "qbgpu_sector_states"); return s; }
+    std::vector<double> norms() const { std::vector<double> s(info.dim); check(qbgpu_sector_norms(handle, s.data()), "qbgpu_sector_norms"); return s; }
+    // H = J sum_bonds S_i.S_j (bonds = {i0, j0, i1, j1, ...}); fake_pos as in model's constructor (qbasis.h:1337)
+    csr_mat<std::complex<double>> heisenberg(const std::vector<int32_t> &bonds, double J = 1.0, double fake_pos = 100.0, int flags = 0) const
+    {
+        qbgpu_matrix_t h = nullptr;
+        check(qbgpu_sector_build_heisenberg(handle, &h, static_cast<int>(bonds.size() / 2), bonds.data(), J, fake_pos, flags), "qbgpu_sector_build_heisenberg");
+        return csr_mat<std::complex<double>>::adopt(h);
     }
 };
 

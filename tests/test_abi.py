@@ -150,3 +150,37 @@ def test_vector_files_are_the_reference_format(tmp_path, oracle):
     bad = bytearray(open(g, "rb").read()); bad[100] ^= 1
     open(out, "wb").write(bytes(bad))
     assert qb.vec_disk_read(out, 70) is None                      # checksum mismatch -> the reference's return 1
+
+
+def test_cpp_adaptor_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/qbgpu_csr_mat.hpp (csr_mat<T> and sector) against libqbgpu.so with the image's g++: every entry point it
+    uses exists, and without a device the constructors throw std::runtime_error -- never a silent fallback."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "adaptor.cc"
+    src.write_text('''
+#include <cstdio>
+#include "qbgpu_csr_mat.hpp"
+int main() {
+    int thrown = 0;
+    try { qbgpu::sector s({16}, 8, {3}); auto H = s.heisenberg({0, 1, 1, 2}); std::printf("dim %lld\\n", (long long)H.dimension()); }
+    catch (const std::runtime_error &e) { std::printf("sector: %s\\n", e.what()); thrown++; }
+    long long ia[3] = {0, 1, 2}, ja[2] = {0, 1};
+    std::complex<double> val[2] = {1.0, 2.0};
+    try { qbgpu::csr_mat<std::complex<double>> A(2, 2, true, val, ja, ia); std::complex<double> x[2] = {1.0, 1.0}, y[2]; A.MultMv(x, y); std::printf("y %g %g\\n", y[0].real(), y[1].real()); }
+    catch (const std::runtime_error &e) { std::printf("csr_mat: %s\\n", e.what()); thrown++; }
+    return thrown;
+}
+''')
+    exe = tmp_path / "adaptor"
+    libdir = os.path.join(root, "quantum_basis_b200")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-lqbgpu",
+                    "-Wl,-rpath," + libdir], check=True)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 2, r.stdout + r.stderr               # both constructors threw
+    assert "sector:" in r.stdout and "csr_mat:" in r.stdout and "failed" in r.stdout

@@ -498,11 +498,19 @@ def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_pea
     xh = torch.empty(2 * chunk, dtype=torch.float64).pin_memory(); xh.copy_(x_loc.cpu())
     yh = torch.empty(2 * chunk, dtype=torch.float64).pin_memory()
     best = opB if msB < msA else opA
+    use_peer = msC is not None and msC < min(msA, msB)
+    nb_slice = (hi - lo) * 16
 
     def e2e_step():
-        x_loc.copy_(xh, non_blocking=True)
-        best.matvec(x_loc, y_loc)
-        yh.copy_(y_loc, non_blocking=True)
+        if use_peer:                       # host slice -> staging tensor -> this rank's exported buffer (all stream-ordered)
+            x_loc.copy_(xh, non_blocking=True)
+            assert L.qbgpu_memcpy_d2d(C.c_void_p(opC.own(0).ptr), C.c_void_p(x_loc.data_ptr()), nb_slice) == 0
+            opC.matvec(0, y_c)
+            yh.copy_(y_c, non_blocking=True)
+        else:
+            x_loc.copy_(xh, non_blocking=True)
+            best.matvec(x_loc, y_loc)
+            yh.copy_(y_loc, non_blocking=True)
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize(); dist.barrier()

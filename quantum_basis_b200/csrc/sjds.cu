@@ -90,7 +90,7 @@ template <int XPOL> __device__ __forceinline__ double2 ld_x(const double2 *p, ui
 // MINB = __launch_bounds__ min blocks/SM: without it ptxas schedules for 32 registers (full occupancy) and chains
 // "load column, load value, gather, fma" one diagonal at a time -- a single dependent pair of loads in flight per
 // warp; with MINB <= 4 it batches the U column loads, the U value loads and the U gathers (checked in the SASS).
-template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB>
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false>
 __global__ void __launch_bounds__(kSBlock, MINB)
 spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
                  const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
@@ -116,6 +116,10 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
     }
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
     const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    // KEEP: y += H_block x (a later column block of a sharded product, chosen by the launcher when beta == 1, z == y and
+    // there is no epilogue): rows without entries in this block keep their y -- neither read nor written.  A template
+    // parameter, not a run-time test: the plain instantiation must stay instruction-for-instruction what ptxas schedules
+    // well (a run-time flag here cost 15-25 % on the unsplit product).
     double d[3] = {0.0, 0.0, 0.0};
 
     for (int64_t s = (int64_t)blockIdx.x * WPB + warp; s < nslices; s += (int64_t)gridDim.x * WPB) {
@@ -123,6 +127,7 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
         const int len = (int)(info & kLenMask);
         const int64_t row = s * 32 + (info >> 24);
         const int maxlen = __shfl_sync(0xffffffffu, len, 0);
+        if constexpr (KEEP) { if (maxlen == 0) continue; }   // warp-uniform: the whole slice is empty
         const int64_t base = rowptr[s * 32];
         int64_t off = base + lane;                          // this lane's entry at step k is off_k + lane
         VecT acc0 = VT::zero(), acc1 = VT::zero();
@@ -170,7 +175,7 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
                 }
             }
         }
-        if (row < nrows) {                                  // padding ranks of the last slice point past the last row
+        if (row < nrows && !(KEEP && len == 0)) {           // padding ranks of the last slice point past the last row
             const VecT acc = VT::add(acc0, acc1);
             VecT out = VT::scale(alpha, acc);
             VecT xi = VT::zero();
@@ -197,11 +202,11 @@ static int64_t g_far_rows = 1 << 21;                      // rows; ~32 MB of com
 void set_sjds_variant(int v) { g_sjds_variant = v; }
 void set_sjds_far_rows(int64_t r) { g_far_rows = r; }
 
-template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB>
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false>
 static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
-    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS, U, SPOL, XPOL, UL, MINB>;
+    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS, U, SPOL, XPOL, UL, MINB, KEEP>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kSBlock, 0));
@@ -264,6 +269,9 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
     }
 #endif
     using P = Prod<VecT>;
+    // accumulating column block of a sharded product (y += H_p x, immediates only): skip the rows this block does not touch
+    if (!dots && a.scal_mode == 0 && a.z == a.y && a.beta.x == 1.0 && a.beta.y == 0.0 && a.gamma.x == 0.0 && a.gamma.y == 0.0)
+        return launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB, true>(A, a);
     // (with fp64 vectors the epilogue variant needs a few more registers: 3 blocks/SM keeps its loads batched)
     return dots ? launch_sjds_variant<ValT, VecT, true, P::U, P::S, P::X, P::UL, P::DotsMinB>(A, a)
                 : launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB>(A, a);

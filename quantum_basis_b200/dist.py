@@ -203,9 +203,15 @@ class PeerExchangeOperator:
         self.groups = groups if groups is not None else [(p, p + 1) for p in range(world)]
         self.own_group = next(g for g, (a, b) in enumerate(self.groups) if a <= rank < b)
         assert self.groups[self.own_group] == (rank, rank + 1), "the own slice must be a block of its own"
-        others = [g for g in range(len(self.groups)) if g != self.own_group]
+        # a column block without a single stored entry needs neither its slices nor a product (Hubbard 4x4 on 8 ranks:
+        # two of the seven remote blocks of every rank -- one hop cannot change the top site's occupation by two)
+        empty = set()
+        if kernels.parts is not None and os.environ.get("QB_PEER_KEEP_EMPTY", "0") != "1":
+            empty = {g for g in range(len(self.groups)) if kernels.parts[g].info.nnz_stored == 0}
+        others = [g for g in range(len(self.groups)) if g != self.own_group and g not in empty]
         self.group_order = sorted(others, key=lambda g: (self.groups[g][0] - rank) % world)      # ring order
         self.order = [p for g in self.group_order for p in range(*self.groups[g])]
+        self.skipped_blocks = len(empty)
         if mode is not None:
             self.mode = mode
         if ctas is not None:

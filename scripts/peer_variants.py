@@ -102,7 +102,7 @@ def main():
         errt = torch.tensor([err], dtype=torch.float64, device="cuda")
         dist.all_reduce(errt, op=dist.ReduceOp.MAX)
         rec = {"variant": f"g{g}-{mode}{ctas or ''}-l{lanes}", "group": g, "mode": mode, "ctas": ctas, "lanes": lanes, "ms": ms, "pull_only_ms": ms_pull,
-               "blocks_only_ms": ms_blocks, "blocks": len(groups), "max_rel_err_vs_allgather": float(errt.item()),
+               "blocks_only_ms": ms_blocks, "blocks": len(groups), "skipped_empty_blocks": op.skipped_blocks, "max_rel_err_vs_allgather": float(errt.item()),
                "pull_GBs_per_gpu": (n - (hi - lo)) * 16 / (ms_pull * 1e-3) / 1e9}
         results.append(rec)
         if rank == 0:

@@ -203,14 +203,21 @@ class PeerExchangeOperator:
         self.groups = groups if groups is not None else [(p, p + 1) for p in range(world)]
         self.own_group = next(g for g, (a, b) in enumerate(self.groups) if a <= rank < b)
         assert self.groups[self.own_group] == (rank, rank + 1), "the own slice must be a block of its own"
-        # a column block without a single stored entry needs neither its slices nor a product (Hubbard 4x4 on 8 ranks:
-        # two of the seven remote blocks of every rank -- one hop cannot change the top site's occupation by two)
+        # A column block without a single stored entry needs no product (Hubbard 4x4 on 8 ranks: two of the seven remote
+        # blocks of every rank -- one hop cannot change the top site's occupation by two).  Its slices are still pulled:
+        # dropping them was measured (profiles/r01_peer_variants_n8.jsonl, "skipped_empty_blocks") and is SLOWER, 6.43 ms
+        # against 5.06 ms, because the ring schedule -- at step d every GPU serves exactly one reader -- falls out of
+        # step and sources end up serving two or three readers at once (exchange alone 5.4 ms instead of 3.2 ms).
+        # A conflict-free schedule for the needed transfers only (an edge colouring of the reader/source graph) is the
+        # way to collect that saving; QB_PEER_SKIP_PULLS=1 reproduces the measurement.
         empty = set()
         if kernels.parts is not None and os.environ.get("QB_PEER_KEEP_EMPTY", "0") != "1":
             empty = {g for g in range(len(self.groups)) if kernels.parts[g].info.nnz_stored == 0}
-        others = [g for g in range(len(self.groups)) if g != self.own_group and g not in empty]
-        self.group_order = sorted(others, key=lambda g: (self.groups[g][0] - rank) % world)      # ring order
-        self.order = [p for g in self.group_order for p in range(*self.groups[g])]
+        ring = lambda g: (self.groups[g][0] - rank) % world                                       # noqa: E731
+        others = sorted((g for g in range(len(self.groups)) if g != self.own_group), key=ring)
+        self.group_order = [g for g in others if g not in empty]
+        pulled = self.group_order if os.environ.get("QB_PEER_SKIP_PULLS", "0") == "1" else others
+        self.order = [p for g in pulled for p in range(*self.groups[g])]
         self.skipped_blocks = len(empty)
         if mode is not None:
             self.mode = mode

@@ -194,7 +194,7 @@ class PeerExchangeOperator:
                 self.peer[b][p] = out.value
         self.token = torch_mod.zeros(1, dtype=torch_mod.float64, device="cuda")
 
-    def configure(self, kernels, groups=None, mode=None, ctas=None, lanes=None):
+    def configure(self, kernels, groups=None, mode=None, ctas=None, lanes=None, schedule=None):
         """(Re)select the column blocks -- kernels.parts[g] covers the owners groups[g] = (first, last+1), default one
         block per owner -- and optionally the transfer mode, on the same exported buffers."""
         rank, world = self.rank, self.world
@@ -219,6 +219,20 @@ class PeerExchangeOperator:
         pulled = self.group_order if os.environ.get("QB_PEER_SKIP_PULLS", "0") == "1" else others
         self.order = [p for g in pulled for p in range(*self.groups[g])]
         self.skipped_blocks = len(empty)
+        self.schedule = "ring"
+        if schedule == "matching" and len(self.groups) == world:
+            # conflict-free rounds for the NEEDED transfers only: every rank publishes which owners it needs, the
+            # reader/source graph is split into matchings (in a round every source serves at most one reader and every
+            # reader pulls from at most one source), and each rank pulls its sources in round order
+            import torch.distributed as dist
+            mine = [g not in empty and g != self.own_group for g in range(world)]
+            allneeds = [None] * world
+            dist.all_gather_object(allneeds, mine)
+            rounds = matching_rounds(allneeds)
+            seq = [rd[rank] for rd in rounds if rd[rank] is not None]
+            self.group_order = seq
+            self.order = list(seq)
+            self.schedule = f"matching ({len(rounds)} rounds)"
         if mode is not None:
             self.mode = mode
         if ctas is not None:
@@ -307,6 +321,39 @@ class PeerExchangeOperator:
         for idx, g in enumerate(self.group_order):
             self._wait_group(g)
             self.k.lanczos_step_a_part(g, self.X[b], uz, state, False, idx == last - 1)
+
+
+def matching_rounds(needs):
+    """needs[r][p]: reader r needs the slice of owner p.  Returns rounds; rounds[k][r] = the owner r pulls from in round k
+    (or None).  Repeated maximum bipartite matching (Kuhn's augmenting paths, deterministic): for a regular graph every
+    round is a perfect matching, so the number of rounds equals the degree."""
+    world = len(needs)
+    adj = [[p for p in range(world) if needs[r][p]] for r in range(world)]
+    rounds = []
+    while any(adj):
+        match_src = [None] * world                      # source -> reader
+
+        def augment(r, seen):
+            # try the sources in ring order from r, so that the rounds resemble the ring when everything is needed
+            for p in sorted(adj[r], key=lambda q: (q - r) % world):
+                if p in seen:
+                    continue
+                seen.add(p)
+                if match_src[p] is None or augment(match_src[p], seen):
+                    match_src[p] = r
+                    return True
+            return False
+
+        for r in sorted(range(world), key=lambda q: -len(adj[q])):
+            if adj[r]:
+                augment(r, set())
+        rd = [None] * world
+        for p, r in enumerate(match_src):
+            if r is not None:
+                rd[r] = p
+                adj[r].remove(p)
+        rounds.append(rd)
+    return rounds
 
 
 def peer_groups(world, rank, size):

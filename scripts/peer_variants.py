@@ -69,11 +69,13 @@ def main():
         if v.count("-") != 2:               # e.g. the "noring" switch
             continue
         gs, ms_, ls = v.split("-")
-        variants.append((int(gs[1:]), ms_[:2], int(ms_[2:] or 0), int(ls[1:])))
+        sched = "matching" if ms_.endswith("m") else None      # e.g. g1-cem-l1: needed transfers only, in matching rounds
+        ms_ = ms_.rstrip("m")
+        variants.append((int(gs[1:]), ms_[:2], int(ms_[2:] or 0), int(ls[1:]), sched))
     results = []
     parts_cache = {}
     op = None
-    for (g, mode, ctas, lanes) in variants:
+    for (g, mode, ctas, lanes, sched) in variants:
         groups = qd.peer_groups(world, rank, g)
         if g not in parts_cache:
             cb = [min(n, gr[0] * chunk) for gr in groups] + [n]
@@ -88,6 +90,8 @@ def main():
         else:
             torch.cuda.synchronize(); dist.barrier()
             op.configure(kern, groups, mode=mode, ctas=max(1, ctas), lanes=lanes)
+        if sched:
+            op.configure(kern, groups, schedule=sched)
         comm.all_reduce(op.token)
         y = kern.alloc(chunk)
         ms = qd._timed(torch, dist, stream, lambda: op.matvec(0, y), a.steps, a.warmup)
@@ -101,7 +105,7 @@ def main():
         ms_blocks = qd._timed(torch, dist, stream, blocks_only, a.steps, a.warmup)
         errt = torch.tensor([err], dtype=torch.float64, device="cuda")
         dist.all_reduce(errt, op=dist.ReduceOp.MAX)
-        rec = {"variant": f"g{g}-{mode}{ctas or ''}-l{lanes}", "group": g, "mode": mode, "ctas": ctas, "lanes": lanes, "ms": ms, "pull_only_ms": ms_pull,
+        rec = {"variant": f"g{g}-{mode}{ctas or ''}{'m' if sched else ''}-l{lanes}", "schedule": op.schedule, "group": g, "mode": mode, "ctas": ctas, "lanes": lanes, "ms": ms, "pull_only_ms": ms_pull,
                "blocks_only_ms": ms_blocks, "blocks": len(groups), "skipped_empty_blocks": op.skipped_blocks, "max_rel_err_vs_allgather": float(errt.item()),
                "pull_GBs_per_gpu": (n - (hi - lo)) * 16 / (ms_pull * 1e-3) / 1e9}
         results.append(rec)

@@ -164,3 +164,29 @@ def test_equal_row_bounds():
         assert b[0] == 0 and b[-1] == n and len(b) == parts + 1
         assert all(0 <= b[i + 1] - b[i] <= chunk for i in range(parts))
         assert chunk * parts >= n
+
+
+def test_matching_rounds_are_conflict_free_and_cover_every_needed_transfer():
+    """The pull schedule of PeerExchangeOperator(schedule="matching"): in every round a source serves at most one reader
+    and a reader pulls from at most one source; every needed (reader, source) pair appears exactly once; a d-regular
+    need graph takes exactly d rounds (Hubbard 4x4 on 8 ranks: 5 instead of the ring's 7)."""
+    from quantum_basis_b200.dist import matching_rounds
+    allowed = {0: {0, 1, 2}, 1: {0, 1, 3}, 2: {0, 2, 3}, 3: {1, 2, 3}}
+    cases = {
+        "hubbard8": [[(p // 2 in allowed[r // 2]) and p != r for p in range(8)] for r in range(8)],
+        "full4": [[p != r for p in range(4)] for r in range(4)],
+        "irregular": [[False, True, True, False, True], [True, False, False, False, False], [False, True, False, True, False],
+                      [False, False, False, False, False], [True, True, True, True, False]],
+    }
+    for name, needs in cases.items():
+        rounds = matching_rounds(needs)
+        seen = set()
+        for rd in rounds:
+            srcs = [p for p in rd if p is not None]
+            assert len(srcs) == len(set(srcs)), name
+            for r, p in enumerate(rd):
+                if p is not None:
+                    assert needs[r][p] and (r, p) not in seen, name
+                    seen.add((r, p))
+        assert seen == {(r, p) for r in range(len(needs)) for p in range(len(needs)) if needs[r][p]}, name
+    assert len(matching_rounds(cases["hubbard8"])) == 5 and len(matching_rounds(cases["full4"])) == 3

@@ -208,8 +208,8 @@ class PeerExchangeOperator:
         # dropping them was measured (profiles/r01_peer_variants_n8.jsonl, "skipped_empty_blocks") and is SLOWER, 6.43 ms
         # against 5.06 ms, because the ring schedule -- at step d every GPU serves exactly one reader -- falls out of
         # step and sources end up serving two or three readers at once (exchange alone 5.4 ms instead of 3.2 ms).
-        # A conflict-free schedule for the needed transfers only (an edge colouring of the reader/source graph) is the
-        # way to collect that saving; QB_PEER_SKIP_PULLS=1 reproduces the measurement.
+        # The saving is collected by the "matching" schedule below (conflict-free rounds over the needed transfers only:
+        # 4.74 ms); QB_PEER_SCHEDULE=ring with QB_PEER_SKIP_PULLS=1 reproduces the unbalanced measurement.
         empty = set()
         if kernels.parts is not None and os.environ.get("QB_PEER_KEEP_EMPTY", "0") != "1":
             empty = {g for g in range(len(self.groups)) if kernels.parts[g].info.nnz_stored == 0}
@@ -220,7 +220,9 @@ class PeerExchangeOperator:
         self.order = [p for g in pulled for p in range(*self.groups[g])]
         self.skipped_blocks = len(empty)
         self.schedule = "ring"
-        if schedule == "matching" and len(self.groups) == world:
+        if schedule is None:
+            schedule = os.environ.get("QB_PEER_SCHEDULE", "matching")
+        if schedule == "matching" and len(self.groups) == world and world > 2:
             # conflict-free rounds for the NEEDED transfers only: every rank publishes which owners it needs, the
             # reader/source graph is split into matchings (in a round every source serves at most one reader and every
             # reader pulls from at most one source), and each rank pulls its sources in round order

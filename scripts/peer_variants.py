@@ -87,11 +87,8 @@ def main():
         if op is None:                       # one set of exported ping-pong buffers serves every variant
             op = qd.PeerExchangeOperator(qb, kern, n, rank, world, comm, torch, lanes=lanes, mode=mode, ctas=max(1, ctas), groups=groups)
             op.own(0).upload(np.ascontiguousarray(full[lo:hi]))
-        else:
-            torch.cuda.synchronize(); dist.barrier()
-            op.configure(kern, groups, mode=mode, ctas=max(1, ctas), lanes=lanes)
-        if sched:
-            op.configure(kern, groups, schedule=sched)
+        torch.cuda.synchronize(); dist.barrier()
+        op.configure(kern, groups, mode=mode, ctas=max(1, ctas), lanes=lanes, schedule=sched or "ring")
         comm.all_reduce(op.token)
         y = kern.alloc(chunk)
         ms = qd._timed(torch, dist, stream, lambda: op.matvec(0, y), a.steps, a.warmup)
@@ -118,7 +115,7 @@ def main():
         ringM = qd.PeerExchangeOperator.ring_view(qb, M, rank, world, chunk)
         kr = qd.DeviceKernels(qb, ringM, real=False)
         op.enable_ring(kr)
-        op.configure(kern, groups, lanes=1, mode="ce")
+        op.configure(kern, groups, lanes=1, mode="ce", schedule="ring")
         y = kr.alloc(chunk)
         op.matvec_ring(0, y)
         torch.cuda.synchronize()
@@ -126,7 +123,7 @@ def main():
         dist.all_reduce(bad)
         if float(bad.item()) == 0.0:
             for lanes in ((1, 2) if world > 2 else (1,)):
-                op.configure(kern, groups, lanes=lanes, mode="ce")
+                op.configure(kern, groups, lanes=lanes, mode="ce", schedule="ring")
                 ms = qd._timed(torch, dist, stream, lambda: op.matvec_ring(0, y), a.steps, a.warmup)
                 err = float((y - y_ref).abs().max().item()) / max(1e-300, float(y_ref.abs().max().item()))
                 errt = torch.tensor([err], dtype=torch.float64, device="cuda")

@@ -190,3 +190,177 @@ def test_matching_rounds_are_conflict_free_and_cover_every_needed_transfer():
                     seen.add((r, p))
         assert seen == {(r, p) for r in range(len(needs)) for p in range(len(needs)) if needs[r][p]}, name
     assert len(matching_rounds(cases["hubbard8"])) == 5 and len(matching_rounds(cases["full4"])) == 3
+
+
+# ------------------------------------------------------------------ PeerExchangeOperator, simulated in one process
+class _FakePeerLib:
+    """The handful of C-ABI entry points PeerExchangeOperator uses, on host memory: every simulated rank is a thread of
+    this process, so a "peer mapping" is just the owner's address and a pull is a memmove."""
+    import ctypes as _C
+
+    def __init__(self):
+        self.keep = []
+        self.pulled = {}                                           # thread rank -> list of (slot) pulled in the last product
+
+    def qbgpu_last_error(self):
+        return b"fake"
+
+    def qbgpu_malloc(self, pref, nbytes):
+        import ctypes as C
+        buf = (C.c_char * max(1, int(nbytes)))()
+        self.keep.append(buf)
+        pref._obj.value = C.addressof(buf)
+        return 0
+
+    def qbgpu_memset0(self, p, nbytes):
+        import ctypes as C
+        C.memset(p.value, 0, int(nbytes))
+        return 0
+
+    def qbgpu_memcpy_h2d(self, dst, src, nbytes):
+        import ctypes as C
+        C.memmove(dst.value, src.value, int(nbytes))
+        return 0
+
+    qbgpu_memcpy_d2h = qbgpu_memcpy_h2d
+
+    def qbgpu_ipc_export(self, p, handle):
+        import ctypes as C
+        import struct
+        C.memmove(handle, struct.pack("<Q", p.value) + bytes(56), 64)
+        return 0
+
+    def qbgpu_ipc_open(self, handle, out):
+        import struct
+        out._obj.value = struct.unpack("<Q", bytes(handle)[:8])[0]
+        return 0
+
+    def qbgpu_peer_pull_async(self, lane, slot, dst, src, nbytes):
+        import ctypes as C
+        import threading
+        C.memmove(dst.value, src.value, int(nbytes))
+        self.pulled.setdefault(threading.current_thread().name, []).append(slot)
+        return 0
+
+    def qbgpu_peer_wait(self, slot):
+        return 0
+
+
+def _simulate_peer_exchange(world, n, F, schedule):
+    """Run PeerExchangeOperator.matvec on `world` threads; returns (y per rank, pulled owners per rank)."""
+    import ctypes as C
+    import threading
+    import types
+    import scipy.sparse as sp
+    from quantum_basis_b200 import dist as qd
+
+    lib = _FakePeerLib()
+    fake_qb = types.SimpleNamespace(lib=lambda: lib)
+    barrier = threading.Barrier(world)
+    slots = {}
+    lock = threading.Lock()
+    tl = threading.local()
+
+    def all_gather_object(out, obj):
+        with lock:
+            tl.calls = getattr(tl, "calls", 0) + 1
+            slots.setdefault(tl.calls, {})[tl.rank] = obj
+        barrier.wait()
+        for r in range(world):
+            out[r] = slots[tl.calls][r]
+        barrier.wait()
+
+    class Comm:
+        def all_reduce(self, t):
+            barrier.wait()
+
+    class Kern:
+        ncomp = 2
+
+        def __init__(self, rows, lo, hi, col_bounds):
+            Fc = rows.tocsc()
+            self.lo, self.hi, self.cb = lo, hi, col_bounds
+            self.blocks = [Fc[:, col_bounds[p]:col_bounds[p + 1]].tocsr() for p in range(len(col_bounds) - 1)]
+            self.parts = [types.SimpleNamespace(info=types.SimpleNamespace(nnz_stored=b.nnz)) for b in self.blocks]
+
+        def multmv_part(self, p, x_full, y_local, accumulate):
+            nb = (self.cb[p + 1] - self.cb[p]) * 16
+            raw = (C.c_char * nb).from_address(x_full.ptr + self.cb[p] * 16)
+            x = np.frombuffer(raw, dtype=np.complex128)
+            part = self.blocks[p] @ x
+            y_local[:] = y_local + part if accumulate else part
+
+    x = (np.arange(n) + 1.0) * np.exp(0.3j * np.arange(n))
+    bounds, chunk = qd.equal_row_bounds(n, world)
+    ys, errs = [None] * world, []
+    saved = qd.os.environ.get("QB_PEER_SCHEDULE")
+    qd.os.environ["QB_PEER_SCHEDULE"] = schedule
+    import torch.distributed as tdist
+    orig = tdist.all_gather_object
+    tdist.all_gather_object = all_gather_object
+
+    def run(rank):
+        try:
+            tl.rank = rank
+            lo, hi = bounds[rank], bounds[rank + 1]
+            cb = [min(n, q * chunk) for q in range(world)] + [n]
+            kern = Kern(F[lo:hi], lo, hi, cb)
+            host_torch = types.SimpleNamespace(float64=torch.float64,
+                                               zeros=lambda *a, **k: torch.zeros(*a, **{q: v for q, v in k.items() if q != "device"}))
+            op = qd.PeerExchangeOperator(fake_qb, kern, n, rank, world, Comm(), host_torch)
+            for b in range(2):                                       # poison everything that is not the own slice
+                raw = (C.c_char * (chunk * world * 16)).from_address(op.X[b].ptr)
+                np.frombuffer(raw, dtype=np.complex128)[:] = np.nan
+            op.own(0).upload(np.ascontiguousarray(x[lo:hi]))
+            y = np.zeros(hi - lo, dtype=np.complex128)
+            op.matvec(0, y)
+            ys[rank] = (y, op.schedule, op.skipped_blocks)
+        except Exception as e:                                       # surface thread failures in the main thread
+            errs.append((rank, repr(e)))
+            try:
+                barrier.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=run, args=(r,), name=f"rank{r}") for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    tdist.all_gather_object = orig
+    if saved is None:
+        qd.os.environ.pop("QB_PEER_SCHEDULE", None)
+    else:
+        qd.os.environ["QB_PEER_SCHEDULE"] = saved
+    assert not errs, errs
+    return ys, lib.pulled, bounds
+
+
+@pytest.mark.parametrize("schedule", ["matching", "ring"])
+def test_peer_exchange_operator_logic_with_empty_blocks(schedule):
+    """Four simulated ranks, a block structure in which rank r never touches the columns of rank (r+2)%4: the product is
+    exact although those slices are poisoned with NaN (their blocks are skipped), the matching schedule does not even
+    pull them, and the ring schedule pulls everything but multiplies only what exists."""
+    import scipy.sparse as sp
+    world, n = 4, 128
+    rng = np.random.default_rng(5)
+    dense = np.zeros((n, n), dtype=np.complex128)
+    for r in range(world):
+        for p in range(world):
+            if (p - r) % world == 2:
+                continue
+            blk = (rng.random((32, 32)) < 0.15) * (rng.normal(size=(32, 32)) + 1j * rng.normal(size=(32, 32)))
+            dense[32 * r:32 * r + 32, 32 * p:32 * p + 32] = blk
+    F = sp.csr_matrix(dense)
+    ys, pulled, bounds = _simulate_peer_exchange(world, n, F, schedule)
+    x = (np.arange(n) + 1.0) * np.exp(0.3j * np.arange(n))
+    ref = dense @ x
+    for r in range(world):
+        y, sched, skipped = ys[r]
+        assert skipped == 1
+        assert np.allclose(y, ref[bounds[r]:bounds[r + 1]], rtol=0, atol=1e-12) and not np.isnan(y).any()
+        got = sorted(pulled[f"rank{r}"])
+        if schedule == "matching":
+            assert sched.startswith("matching") and got == sorted(p for p in range(world) if p != r and (p - r) % world != 2)
+        else:
+            assert sched == "ring" and got == sorted(p for p in range(world) if p != r)

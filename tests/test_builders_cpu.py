@@ -85,3 +85,50 @@ def test_sector_sz_operator_matches_reference_moprXvec(name):
     y = R.apply_sz(S0, S1, R.szq_coefficients(L, q), z["phi0"])
     assert np.abs(y - z["Aphi0"]).max() < 1e-15
     assert abs(np.linalg.norm(y) - meta["dyn_norm"]) < 1e-14
+
+
+# ------------------------------------------------------------------ arbitrary translation groups (orbit_builders.py, config 4)
+def _dense_from_upper(n, ia, ja, val):
+    D = np.zeros((n, n), dtype=np.complex128)
+    for i in range(n):
+        for p in range(ia[i], ia[i + 1]):
+            D[i, ja[p]] = val[p]
+            if ja[p] != i:
+                D[ja[p], i] = np.conj(val[p])
+    return D
+
+
+def test_cluster_translation_groups_are_groups_with_homomorphic_characters():
+    from quantum_basis_b200.clusters import Cluster
+    for A in (((2, 1), (-1, 3)), ((3, 1), (-1, 4)), ((3, 1), (-1, 3)), ((5, 1), (-1, 6)), ((4, 0), (0, 3))):
+        c = Cluster(*A)
+        P = c.translations()
+        assert all(sorted(p) == list(range(c.det)) for p in P.tolist()) and P[0].tolist() == list(range(c.det))
+        index = {tuple(p): i for i, p in enumerate(P.tolist())}
+        mom = c.distinct_momenta()
+        assert len(mom) == c.det
+        chi = c.characters(mom[min(1, len(mom) - 1)])
+        for a in range(c.det):
+            for b in range(c.det):
+                ab = index[tuple(P[a][P[b]].tolist())]           # closure
+                assert abs(chi[ab] - chi[a] * chi[b]) < 1e-12     # chi is a character
+        assert len(c.triangular_bonds()) == 3 * c.det
+
+
+@pytest.mark.parametrize("A0,A1,ndown", [((2, 1), (-1, 3), 3), ((3, 1), (-1, 3), 5), ((3, 1), (-1, 4), 6), ((4, 0), (0, 3), 6)])
+def test_orbit_convention_partitions_the_full_spectrum(A0, A1, ndown):
+    """The convention the device assembler for tilted clusters follows (no reference exists for config 4): all
+    momentum sectors together have exactly the spectrum of the full Sz sector, whose matrix is the reference-pinned
+    full-basis restatement."""
+    import orbit_builders as OB
+    from quantum_basis_b200.clusters import Cluster
+    cl = Cluster(A0, A1)
+    bonds = cl.triangular_bonds()
+    n, ia, ja, val = B.heisenberg_upper_csr(cl.det, ndown, bonds)
+    full = np.linalg.eigvalsh(_dense_from_upper(n, ia, ja, val))
+    ev = []
+    for m in cl.distinct_momenta():
+        reps, stab, sia, sja, sval = OB.heisenberg_orbit_upper_csr(cl.det, ndown, cl.translations(), cl.characters(m), bonds)
+        ev.append(np.linalg.eigvalsh(_dense_from_upper(reps.size, sia, sja, sval)))
+    ev = np.sort(np.concatenate(ev))
+    assert ev.size == full.size and np.abs(ev - full).max() < 1e-10

@@ -835,3 +835,22 @@ def test_config4_tilted_31_site_cluster_builds_and_is_hermitian():
     assert abs(complex(d1[0], d1[1]) - complex(d2[0], d2[1])) < 1e-12
     res = qb.locate_E0_lanczos(M, nev=1, ncv=0)
     assert -0.60 * 31 < res["eigenvals"][0] < -0.45 * 31          # triangular-lattice Heisenberg: about -0.55 J per site
+
+
+@pytest.mark.parametrize("A0,A1,ndown,m", [((3, 1), (-1, 4), 6, (1, 0)), ((4, 0), (0, 3), 6, (1, 1)), ((4, 0), (0, 3), 4, (2, 0)),
+                                           ((4, 1), (-1, 5), 10, (1, 0)), ((4, 1), (-1, 5), 9, (3, 2))])
+def test_orbit_assembler_matches_its_cpu_restatement(oracle, A0, A1, ndown, m):
+    """Representatives, structure and matrix elements of the orbit assembler against tests/orbit_builders.py (which is
+    checked on the CPU by the spectrum-partition property): same representatives, same sparsity, values to 1e-14 (the
+    device contracts w*chi + acc into an fma, the restatement rounds twice)."""
+    import orbit_builders as OB
+    from quantum_basis_b200.clusters import Cluster
+    cl = Cluster(A0, A1)
+    bonds, perms, chi = cl.triangular_bonds(), cl.translations(), cl.characters(m)
+    reps, stab, ia, ja, val = OB.heisenberg_orbit_upper_csr(cl.det, ndown, perms, chi, bonds)
+    M, states = qb.heisenberg_orbit(cl.det, ndown, perms, chi, bonds, flags=1, return_states=True)
+    assert M.dim == reps.size and np.array_equal(states.astype(np.uint64), reps)
+    rowptr, col, v = M.download_expanded()
+    eia, eja, ev = _expanded(reps.size, ia, ja, val, oracle)
+    assert np.array_equal(rowptr, eia) and np.array_equal(col.astype(np.int64), eja)
+    assert np.abs(v - ev).max() < 1e-14

@@ -45,7 +45,9 @@ WORKLOADS = {
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
-TRAFFIC_NCU = {"hubbard4x4": 133686405000}     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
+TRAFFIC_NCU = {"hubbard4x4": 133686405000,     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
+               "tri31_k10": 13300097712,       # profiles/r01_ncu_full_spmv_sjds_tri31_k10_details.csv: 13.14 GB read + 0.158 GB write
+               "heis_chain32_k0": 8834161656}  # profiles/r01_ncu_full_spmv_sjds_heis_chain32_k0_details.csv: 8.53 GB read + 0.302 GB write
 
 
 def square_bonds(Lx, Ly):

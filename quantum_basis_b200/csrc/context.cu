@@ -62,6 +62,16 @@ int qbgpu_init(int device)
     // L2 evict_last / persisting accesses only take effect inside the persisting set-aside, which defaults to 0 bytes
     // (measured, profiles/r01_kbench_sweep3_l2_persist.txt: a set-aside does not help this kernel and the maximum one
     // costs 7-13 %, so it stays off unless QBGPU_L2_PERSIST_MB asks for it)
+    // L2 fetch granularity hint (32, 64 or 128 bytes): the gathers of x are 8/16-byte reads scattered over the vector, so
+    // anything fetched beyond the 32-byte sector would be wasted DRAM traffic.  Measured on B200: no effect at all
+    // (profiles/r01_kbench_l2_fetch_granularity.txt), so nothing is set unless QBGPU_L2_FETCH_BYTES asks for it
+    if (const char *fg = getenv("QBGPU_L2_FETCH_BYTES")) {
+        const long v = atol(fg);
+        if (v == 32 || v == 64 || v == 128) {
+            cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+            if (le != cudaSuccess) cudaGetLastError();      // a hint: not every device accepts it
+        }
+    }
     if (prop.persistingL2CacheMaxSize > 0 && getenv("QBGPU_L2_PERSIST_MB")) {
         size_t want = (size_t)atol(getenv("QBGPU_L2_PERSIST_MB")) << 20;
         if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;

@@ -41,6 +41,9 @@ extern "C" {
 #define QBGPU_FORMAT_CSR     4   /* force the expanded-CSR kernels  */
 #define QBGPU_FORMAT_SELL    8   /* force the sliced-jagged kernels (32-row slices, jagged diagonals, no padding) */
 #define QBGPU_FORMAT_MATFREE 32  /* (info only) matrix-free handle: rows are regenerated inside the product */
+#define QBGPU_MATFREE_TERMS 64  /* qbgpu_create_matfree_*: also store one byte per entry naming the Hamiltonian term that
+                                  * produces it (directed bond x spin), so the product replays each row -- column from the
+                                  * Lin tables, sign from the occupancy words -- without searching for applicable terms */
 #define QBGPU_VALUE_DICT    16   /* opt-in: store fp64 values as 1-byte codes into a table of the distinct values when there
                                     are at most 256 of them (lossless; products are bit-identical); implies FORMAT_SELL */
 

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libqbgpu.so")
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
 QBGPU_HOST, QBGPU_DEVICE = 0, 1
-KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL, VALUE_DICT = 1, 2, 4, 8, 16
+KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL, VALUE_DICT, MATFREE_TERMS = 1, 2, 4, 8, 16, 64
 
 
 class QbgpuError(RuntimeError):

@@ -397,7 +397,21 @@ struct MatFree {
     uint32_t *d_alist = nullptr;
     uint2 *d_states = nullptr;      // (la, lb) of every local row
     SiteTables *d_N = nullptr;
+    // term-coded variant (QBGPU_MATFREE_TERMS): one byte per entry naming the (directed bond, spin) that produces it, so
+    // the product replays the row without searching for the applicable terms.  Codes are packed four to a word and laid
+    // out per 32-row slice, word k of every row side by side (padded with 0xFF to the slice's longest row).
+    uint32_t *d_codes = nullptr;
+    int64_t *d_sliceptr = nullptr;  // [nslices + 1] word offsets
+    struct TermTable *d_terms = nullptr;
+    int wbonds = 0;
     int64_t bytes = 0;
+};
+
+struct TermTable {
+    int ncodes;
+    uint32_t hop[256];              // f | t << 5 | spin << 10 | weight << 11
+    double amp[256];                // Heisenberg: J/2 * weight;  Hubbard: -t added `weight` times (like the LIL accumulation)
+    uint8_t code_of[32][32];        // directed pair (f, t) -> code / 2 (Hubbard) or code (Heisenberg)
 };
 
 __global__ void __launch_bounds__(kBBlock) matfree_states_kernel(SectorTables S, int64_t row_lo, int64_t nloc, uint2 *states)
@@ -454,6 +468,218 @@ spmv_matfree_kernel(SectorTables S, const ModelParams *Mp, const SiteTables *Np,
     }
 }
 
+
+// ---- term-coded rows -------------------------------------------------------------------------------------------
+// count / fill: the neighbour walk once more, recording instead of multiplying
+__global__ void __launch_bounds__(kBBlock) terms_count_kernel(SectorTables S, const ModelParams *Mp, const SiteTables *Np, const uint2 *__restrict__ states,
+                                                              int64_t nrows, int64_t nslices, int64_t *slice_words)
+{
+    __shared__ ModelParams M;
+    __shared__ SiteTables N;
+    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(SiteTables) / 4); k += blockDim.x) ((int *)&N)[k] = ((const int *)Np)[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x / 32;
+    for (int64_t s = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); s <= nslices; s += (int64_t)gridDim.x * wpb) {
+        int words = 0;
+        const int64_t row = s * 32 + lane;
+        if (s < nslices && row < nrows) {
+            const uint2 st = states[row];
+            int cnt = 0;
+            row_entries_walk(S, M, N, st.x, st.y, [&](int64_t, double) { cnt++; });
+            words = (cnt + 3) >> 2;
+        }
+        for (int o = 16; o > 0; o >>= 1) words = max(words, __shfl_xor_sync(0xffffffffu, words, o));
+        if (lane == 0) slice_words[s] = s < nslices ? (int64_t)words * 32 : 0;
+    }
+}
+
+// the walk of row_entries_walk, emitting (f, t, spin) instead of (column, value)
+template <class Emit>
+__device__ __forceinline__ void row_terms_walk(const ModelParams &M, const SiteTables &N, uint32_t la, uint32_t lb, Emit emit)
+{
+    if (M.kind == 0) {
+        const uint32_t dn = spread16(la) | (spread16(lb) << 1);
+        uint32_t m = dn;
+        while (m) {
+            const int f = __ffs(m) - 1; m &= m - 1;
+            uint32_t cand = N.nbr[f] & ~dn;
+            while (cand) { const int t = __ffs(cand) - 1; cand &= cand - 1; emit(f, t, 0); }
+        }
+        return;
+    }
+    const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);
+    const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+#pragma unroll
+    for (int sp = 0; sp < 2; sp++) {
+        const uint32_t occ = sp ? occ1 : occ0;
+        uint32_t m = occ;
+        while (m) {
+            const int f = __ffs(m) - 1; m &= m - 1;
+            uint32_t cand = N.nbr[f] & ~occ;
+            while (cand) { const int t = __ffs(cand) - 1; cand &= cand - 1; emit(f, t, sp); }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBBlock) terms_fill_kernel(const ModelParams *Mp, const SiteTables *Np, const TermTable *Tp, const uint2 *__restrict__ states,
+                                                             int64_t nrows, int64_t nslices, const int64_t *__restrict__ sliceptr, uint32_t *codes)
+{
+    __shared__ ModelParams M;
+    __shared__ SiteTables N;
+    __shared__ uint8_t code_of[32][32];
+    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(SiteTables) / 4); k += blockDim.x) ((int *)&N)[k] = ((const int *)Np)[k];
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) ((uint8_t *)code_of)[k] = ((const uint8_t *)Tp->code_of)[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x / 32;
+    for (int64_t s = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < nslices; s += (int64_t)gridDim.x * wpb) {
+        const int64_t base = sliceptr[s];
+        const int maxw = (int)((sliceptr[s + 1] - base) >> 5);
+        const int64_t row = s * 32 + lane;
+        int k = 0, fill = 0;
+        uint32_t word = 0;
+        if (row < nrows) {
+            const uint2 st = states[row];
+            row_terms_walk(M, N, st.x, st.y, [&](int f, int t, int sp) {
+                const uint32_t code = M.kind == 0 ? (uint32_t)code_of[f][t] : ((uint32_t)code_of[f][t] * 2u + (uint32_t)sp);
+                word |= code << (8 * fill);
+                if (++fill == 4) { codes[base + (int64_t)k * 32 + lane] = word; k++; fill = 0; word = 0; }
+            });
+        }
+        if (fill) {                                           // last, partly filled word: pad with 0xFF codes
+            for (; fill < 4; fill++) word |= 0xFFu << (8 * fill);
+            codes[base + (int64_t)k * 32 + lane] = word; k++;
+        }
+        for (; k < maxw; k++) codes[base + (int64_t)k * 32 + lane] = 0xFFFFFFFFu;
+    }
+}
+
+// The product from the term codes: thread = row (32 consecutive rows per warp), four codes per trip: decode, flip the
+// two sites, sign from the occupancy words, column through the Lin tables, then the four gathers together.
+template <typename VecT, bool DOTS>
+__global__ void __launch_bounds__(kMFBlock, 3)
+spmv_terms_kernel(SectorTables S, const ModelParams *Mp, const TermTable *Tp, const uint2 *__restrict__ states, const int64_t *__restrict__ sliceptr,
+                  const uint32_t *__restrict__ codes, int64_t nrows, int64_t nslices, int64_t row_lo, int wbonds,
+                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
+                  int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+{
+    using VT = VecTraits<VecT>;
+    __shared__ ModelParams M;
+    __shared__ uint32_t hop[256];
+    __shared__ double amp[256];
+    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) { hop[k] = Tp->hop[k]; amp[k] = Tp->amp[k]; }
+    __syncthreads();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+        dot_scale = sx;
+    }
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    const bool spins = M.kind == 0;
+    double d[3] = {0.0, 0.0, 0.0};
+    const int lane = threadIdx.x & 31;
+    constexpr int WPB = kMFBlock / 32;
+    for (int64_t s = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5); s < nslices; s += (int64_t)gridDim.x * WPB) {
+        const int64_t base = sliceptr[s];
+        const int maxw = (int)((sliceptr[s + 1] - base) >> 5);
+        const int64_t row = s * 32 + lane;
+        const bool live = row < nrows;
+        const uint2 st = live ? states[row] : make_uint2(0u, 0u);
+        const uint32_t la = st.x, lb = st.y;
+        const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);         // electrons only
+        const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+        VecT acc = VT::zero();
+        int anti = 0;
+        for (int k = 0; k < maxw; k++) {
+            const uint32_t w4 = codes[base + (int64_t)k * 32 + lane];
+            int64_t c[4];
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t code = (w4 >> (8 * u)) & 255u;
+                c[u] = -1; v[u] = 0.0;
+                if (code != 255u) {
+                    const uint32_t h = hop[code];
+                    const int f = h & 31, t = (h >> 5) & 31, sp = (h >> 10) & 1;
+                    uint32_t na = la, nb = lb;
+                    if (spins) {
+                        if (f & 1) nb ^= 1u << (f >> 1); else na ^= 1u << (f >> 1);
+                        if (t & 1) nb ^= 1u << (t >> 1); else na ^= 1u << (t >> 1);
+                        anti += (int)(h >> 11);
+                        v[u] = amp[code];
+                    } else {
+                        const uint32_t below_f = (1u << f) - 1u, below_t = (1u << t) - 1u;
+                        int sg = __popc(occ0 & below_f) + __popc(occ1 & below_f) + __popc(occ0 & below_t) + __popc(occ1 & below_t);
+                        if (sp) sg += (int)((occ0 >> f) & 1u) + (int)((occ0 >> t) & 1u);
+                        if (f < t) sg += 1;
+                        if (f & 1) nb ^= 1u << (2 * (f >> 1) + sp); else na ^= 1u << (2 * (f >> 1) + sp);
+                        if (t & 1) nb ^= 1u << (2 * (t >> 1) + sp); else na ^= 1u << (2 * (t >> 1) + sp);
+                        v[u] = (sg & 1) ? -amp[code] : amp[code];
+                    }
+                    c[u] = col_of(S, na, nb);
+                }
+            }
+            VecT xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = c[u] >= 0 ? ld_vec(x + c[u]) : VT::zero();
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (c[u] >= 0) mac(acc, v[u], xv[u]);
+        }
+        if (live) {
+            double diag;
+            if (spins) diag = 0.25 * M.J * (double)(wbonds - 2 * anti);
+            else { diag = 0.0; const int ndbl = __popc(occ0 & occ1); for (int r = 0; r < ndbl; r++) diag += M.U; }
+            const VecT xi = x[row_lo + row];
+            mac(acc, diag, xi);
+            VecT out = VT::scale(alpha, acc);
+            if (gamma.x != 0.0 || gamma.y != 0.0) out = VT::add(out, VT::scale(gamma, xi));
+            if (use_beta) out = VT::add(out, VT::scale(beta, z[row]));
+            y[row] = out;
+            if (DOTS) {
+                const double2 p = VT::conj_mul(xi, out);
+                d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
+            }
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kMFBlock>(d, partials, ticket, dots_out);
+    }
+}
+
+template <typename VecT, bool DOTS>
+static int launch_terms_variant(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    Context &c = ctx();
+    const MatFree *mf = (const MatFree *)A->mf;
+    auto kern = spmv_terms_kernel<VecT, DOTS>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMFBlock, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int64_t nrows = A->nrows();
+    if (nrows == 0) return QBGPU_OK;
+    const int64_t nslices = (nrows + 31) / 32;
+    int64_t want = (nslices + (kMFBlock / 32) - 1) / (kMFBlock / 32);
+    int64_t cap = (int64_t)c.num_sms * blocks_per_sm;
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    const int grid = (int)(want < cap ? want : cap);
+    kern<<<grid, kMFBlock, 0, c.stream>>>(mf->S, mf->d_M, mf->d_terms, mf->d_states, mf->d_sliceptr, mf->d_codes, nrows, nslices, A->row_lo, mf->wbonds,
+                                          (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc, a.dots,
+                                          c.partials, c.ticket);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
 template <typename VecT, bool DOTS>
 static int launch_matfree_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
@@ -481,6 +707,10 @@ static int launch_matfree_variant(const qbgpu_matrix *A, const FusedArgs &a)
 int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &a)
 {
     const bool dots = a.dots != nullptr;
+    if (((const MatFree *)A->mf)->d_codes) {
+        if (A->api_complex) return dots ? launch_terms_variant<double2, true>(A, a) : launch_terms_variant<double2, false>(A, a);
+        return dots ? launch_terms_variant<double, true>(A, a) : launch_terms_variant<double, false>(A, a);
+    }
     if (A->api_complex) return dots ? launch_matfree_variant<double2, true>(A, a) : launch_matfree_variant<double2, false>(A, a);
     return dots ? launch_matfree_variant<double, true>(A, a) : launch_matfree_variant<double, false>(A, a);
 }
@@ -489,12 +719,12 @@ void matfree_destroy(qbgpu_matrix *A)
 {
     MatFree *mf = (MatFree *)A->mf;
     if (!mf) return;
-    cudaFree(mf->d_N); cudaFree(mf->d_M); cudaFree(mf->d_Jb); cudaFree(mf->d_rank); cudaFree(mf->d_off); cudaFree(mf->d_alist); cudaFree(mf->d_states);
+    cudaFree(mf->d_codes); cudaFree(mf->d_sliceptr); cudaFree(mf->d_terms); cudaFree(mf->d_N); cudaFree(mf->d_M); cudaFree(mf->d_Jb); cudaFree(mf->d_rank); cudaFree(mf->d_off); cudaFree(mf->d_alist); cudaFree(mf->d_states);
     delete mf;
     A->mf = nullptr;
 }
 
-static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int64_t row_lo, int64_t row_hi)
+static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int64_t row_lo, int64_t row_hi, int flags = 0)
 {
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -546,6 +776,58 @@ static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
     QB_CU(cudaGetLastError());
 #undef QB_CU
     mf->bytes = (int64_t)(sizeof(uint2) * nloc + sizeof(int64_t) * T.Jb.size() + 4 * (T.rankA.size() + T.alist.size() + T.class_off.size()) + sizeof(ModelParams));
+    mf->wbonds = N.wbonds;
+    if ((flags & QBGPU_MATFREE_TERMS) && nloc > 0) {
+        // code table: one code per directed bond (x spin for electrons)
+        static thread_local TermTable TT;
+        memset(&TT, 0, sizeof TT);
+        int npairs = 0;
+        for (int f = 0; f < T.nsites; f++)
+            for (int t = 0; t < T.nsites; t++)
+                if ((N.nbr[f] >> t) & 1u) {
+                    const int per = M.kind == 0 ? 1 : 2;
+                    if ((npairs + 1) * per > 255) { qbgpu_destroy(A); return fail(QBGPU_ERR_ARG, "matrix-free terms: more than 255 (directed bond, spin) codes"); }
+                    TT.code_of[f][t] = (uint8_t)npairs;
+                    for (int sp = 0; sp < per; sp++) {
+                        const int code = npairs * per + sp;
+                        const int w = N.wgt[f][t];
+                        TT.hop[code] = (uint32_t)f | ((uint32_t)t << 5) | ((uint32_t)sp << 10) | ((uint32_t)w << 11);
+                        if (M.kind == 0) TT.amp[code] = 0.5 * M.J * w;
+                        else { double amp = 0.0; for (int r = 0; r < w; r++) amp += -M.t; TT.amp[code] = amp; }
+                    }
+                    npairs++;
+                }
+        TT.ncodes = npairs * (M.kind == 0 ? 1 : 2);
+        const int64_t nslices = (nloc + 31) / 32;
+        int64_t *d_words = nullptr;
+        void *d_tmp = nullptr;
+        auto tclean = [&]() { cudaFree(d_words); cudaFree(d_tmp); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tclean(); qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+        QB_CU(cudaMalloc(&mf->d_terms, sizeof(TermTable)));
+        QB_CU(cudaMemcpyAsync(mf->d_terms, &TT, sizeof(TermTable), cudaMemcpyHostToDevice, c.stream));
+        QB_CU(cudaMalloc(&d_words, sizeof(int64_t) * (nslices + 1)));
+        QB_CU(cudaMalloc(&mf->d_sliceptr, sizeof(int64_t) * (nslices + 1)));
+        int64_t gs = (nslices + 1 + (kBBlock / 32) - 1) / (kBBlock / 32);
+        if (gs > 148 * 64) gs = 148 * 64;
+        terms_count_kernel<<<(int)gs, kBBlock, 0, c.stream>>>(S, mf->d_M, mf->d_N, mf->d_states, nloc, nslices, d_words);
+        QB_LAUNCH_COUNT();
+        size_t tb = 0;
+        QB_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_words, mf->d_sliceptr, nslices + 1, c.stream));
+        QB_CU(cudaMalloc(&d_tmp, tb ? tb : 1));
+        QB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_words, mf->d_sliceptr, nslices + 1, c.stream));
+        int64_t total_words = 0;
+        QB_CU(cudaMemcpyAsync(&total_words, mf->d_sliceptr + nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+        QB_CU(cudaStreamSynchronize(c.stream));
+        QB_CU(cudaMalloc(&mf->d_codes, sizeof(uint32_t) * (size_t)(total_words ? total_words : 1)));
+        terms_fill_kernel<<<(int)gs, kBBlock, 0, c.stream>>>(mf->d_M, mf->d_N, mf->d_terms, mf->d_states, nloc, nslices, mf->d_sliceptr, mf->d_codes);
+        QB_LAUNCH_COUNT();
+        QB_CU(cudaStreamSynchronize(c.stream));
+        QB_CU(cudaGetLastError());
+#undef QB_CU
+        tclean();
+        mf->bytes += (int64_t)(4 * total_words + 8 * (nslices + 1) + sizeof(TermTable));
+        A->nnz_input = 4 * total_words;                     // bytes of codes (padding included), for the bench's byte count
+    }
     *out = A;
     return QBGPU_OK;
 }
@@ -575,27 +857,25 @@ int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn)
 int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
-    (void)flags;
     if (nsites < 2 || ndown < 0 || ndown > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "create_matfree_heisenberg: bad argument");
     HostTables T;
     QB_TRY(make_tables(nsites, 1, ndown, 0, T));
     static thread_local ModelParams M;
     M.kind = 0; M.J = J; M.t = 0; M.U = 0;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
-    return create_matfree(A, T, M, api_complex, row_lo, row_hi);
+    return create_matfree(A, T, M, api_complex, row_lo, row_hi, flags);
 }
 
 int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U,
                                  int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
-    (void)flags;
     if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "create_matfree_hubbard: bad argument");
     HostTables T;
     QB_TRY(make_tables(nsites, 2, nup, ndn, T));
     static thread_local ModelParams M;
     M.kind = 1; M.J = 0; M.t = t; M.U = U;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
-    return create_matfree(A, T, M, api_complex, row_lo, row_hi);
+    return create_matfree(A, T, M, api_complex, row_lo, row_hi, flags);
 }
 
 int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,

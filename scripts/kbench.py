@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--csr", action="store_true", help="also time the CSR-vector kernel at every lane width")
     ap.add_argument("--matfree", action="store_true", help="time the matrix-free product instead of a stored layout")
+    ap.add_argument("--terms", action="store_true", help="with --matfree: the term-coded variant (QBGPU_MATFREE_TERMS)")
     ap.add_argument("--fused", action="store_true", help="time the fused-epilogue variants of the production kernel")
     ap.add_argument("--dict", action="store_true", help="1-byte value codes (QBGPU_VALUE_DICT)")
     ap.add_argument("--far", default="", help="comma list of log2(far_rows) to sweep for the adaptive-policy variants")
@@ -51,7 +52,7 @@ def main():
     t0 = time.time()
     h = C.c_void_p()
     cplx = 0 if a.real else 1
-    flags = 8 | 2 | (16 if a.dict else 0)          # sliced-jagged, no autotune
+    flags = 8 | 2 | (16 if a.dict else 0) | (64 if a.terms else 0)          # sliced-jagged, no autotune
     if fam == "hubbard":
         bonds = np.array(bench.square_bonds(p["Lx"], p["Ly"]), dtype=np.int32).ravel()
         f = L.qbgpu_create_matfree_hubbard if a.matfree else L.qbgpu_build_hubbard
@@ -71,6 +72,8 @@ def main():
     s_vec = 16 if cplx else 8
     s_val = 1 if inf.value_dict else 8
     B = bench.algorithmic_bytes(Z, n, n, s_val, s_vec)
+    if a.terms:
+        print(f"# term-coded: {inf.nnz_input} bytes of codes (padding included) = {inf.nnz_input / Z:.3f} B per entry, handle {inf.device_bytes/1e9:.2f} GB", flush=True)
     print(f"# {a.workload}: n={n} Z={Z} B_spmv={B/1e9:.2f} GB (S_val={s_val},S_vec={s_vec}) dict={inf.value_dict} build {time.time()-t0:.1f}s", flush=True)
     dt = np.complex128 if cplx else np.float64
     x = qb.vec_randomize(n, 1, dtype=dt, device=True)

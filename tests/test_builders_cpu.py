@@ -132,3 +132,37 @@ def test_orbit_convention_partitions_the_full_spectrum(A0, A1, ndown):
         ev.append(np.linalg.eigvalsh(_dense_from_upper(reps.size, sia, sja, sval)))
     ev = np.sort(np.concatenate(ev))
     assert ev.size == full.size and np.abs(ev - full).max() < 1e-10
+
+
+# published ground-state energies of the momentum sectors (the reference's own example asserts)
+CHAIN16_E0 = [-7.142296361, -6.523407057, -5.990986863, -5.615175598, -5.451965668, -5.525353087, -5.823231143, -6.298652725,
+              -6.872106678, -6.298652725, -5.823231143, -5.525353087, -5.451965668, -5.615175598, -5.990986863, -6.523407057]
+TRI4X4_E0 = {(0, 0): -8.555514918, (0, 1): -8.002263841, (0, 2): -7.944709784, (0, 3): -8.002263841, (1, 2): -7.588987242}
+
+
+def _oracle_E0(oracle, S, ia, ja, val):
+    from oracle_lib import Csr
+    A = Csr(S.n, ia, ja, val, True)
+    x = oracle.vec_randomize(S.n, 1)
+    m, a, b, _ = oracle.lanczos(A, x, 1000, "sr_val0")
+    hess = np.zeros(2000)
+    hess[:m + 1] = b
+    hess[1000:1000 + m] = a
+    return oracle.hess_eigen(hess, 1000, m, vectors=False)[0][0]
+
+
+@pytest.mark.parametrize("k", range(16))
+def test_chain16_sector_energies_match_the_published_list(oracle, k):
+    """examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_half.cc:102-117: E0 of every momentum sector of the
+    L = 16 chain, from the restated assembler + the restated Lanczos (start vector and stop rule of the reference)."""
+    import repr_builders as R
+    S, ia, ja, val = R.heisenberg_sector_upper_csr([16], 8, [k], R.chain_bonds(16))
+    assert abs(_oracle_E0(oracle, S, ia, ja, val) - CHAIN16_E0[k]) < 1e-8
+
+
+@pytest.mark.parametrize("mn", sorted(TRI4X4_E0))
+def test_triangular4x4_sector_energies_match_the_published_list(oracle, mn):
+    """examples/trans_symmetric/latt_triangular/triangular_Heisenberg_spin_half.cc:135-139 (E0_list index = 4 m + n)."""
+    import repr_builders as R
+    S, ia, ja, val = R.heisenberg_sector_upper_csr([4, 4], 8, list(mn), R.triangular_bonds(4, 4))
+    assert abs(_oracle_E0(oracle, S, ia, ja, val) - TRI4X4_E0[mn]) < 1e-8

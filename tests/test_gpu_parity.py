@@ -877,3 +877,25 @@ def test_term_coded_matrix_free_product_replays_the_walk_exactly(case):
     e_s = qb.locate_E0_lanczos(mk(is_complex=True), nev=1, ncv=0)["eigenvals"][0]
     e_t = qb.locate_E0_lanczos(mk(is_complex=True, matrix_free=True, flags=64), nev=1, ncv=0)["eigenvals"][0]
     assert abs(e_s - e_t) < 1e-10 * max(1.0, abs(e_s))
+
+
+_CHAIN16_E0 = [-7.142296361, -6.523407057, -5.990986863, -5.615175598, -5.451965668, -5.525353087, -5.823231143, -6.298652725,
+               -6.872106678, -6.298652725, -5.823231143, -5.525353087, -5.451965668, -5.615175598, -5.990986863, -6.523407057]
+_TRI4X4_E0 = {(0, 0): -8.555514918, (0, 1): -8.002263841, (0, 2): -7.944709784, (0, 3): -8.002263841, (1, 2): -7.588987242}
+
+
+def test_device_sectors_reproduce_the_published_sector_energies():
+    """The reference's example asserts (chain_Heisenberg_spin_half.cc:102-117, triangular_Heisenberg_spin_half.cc:135-139):
+    E0 of all sixteen momentum sectors of the L = 16 chain and of five sectors of the 4x4 triangular cluster, each
+    assembled on the device and solved by the fused device Lanczos with the reference's start vector and stop rule."""
+    import repr_builders as R
+    for k in range(16):
+        sec = qb.Sector([16], 8, [k])
+        E = qb.locate_E0_lanczos(sec.heisenberg(R.chain_bonds(16)), nev=1, ncv=0)["eigenvals"][0]
+        assert abs(E - _CHAIN16_E0[k]) < 1e-8, (k, E)
+        sec.free()
+    for mn, e0 in _TRI4X4_E0.items():
+        sec = qb.Sector([4, 4], 8, list(mn))
+        E = qb.locate_E0_lanczos(sec.heisenberg(R.triangular_bonds(4, 4)), nev=1, ncv=0)["eigenvals"][0]
+        assert abs(E - e0) < 1e-8, (mn, E)
+        sec.free()

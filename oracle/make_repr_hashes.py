@@ -26,11 +26,23 @@ CASES = (
        ["tri_k", 2, 4, 0, 0, 2], ["tri_k", 4, 3, 0, 1, 2], ["tri_k", 4, 3, 0, 0, 0], ["tri_k", 3, 4, 0, 1, 1],
        ["tri_k", 3, 4, 0, 2, 3], ["tri_k", 6, 2, 1, 3, 1], ["tri_k", 6, 3, 0, 1, 2], ["tri_k", 4, 5, 0, 3, 2],
        ["tri_k", 4, 4, 0, 0, 0], ["tri_k", 4, 4, 0, 0, 1], ["tri_k", 4, 4, 0, 1, 2], ["tri_k", 4, 4, 1, 3, 3]]
+    # single-orbital Hubbard model in momentum sectors (fermion signs of the translations): Lx Ly N_up N_dn t U m n
+    + [["hubbard_k", 4, 2, 4, 4, 1.0, 1.1, 0, 0], ["hubbard_k", 4, 2, 4, 4, 1.0, 1.1, 1, 0], ["hubbard_k", 4, 2, 4, 4, 1.0, 1.1, 2, 1],
+       ["hubbard_k", 4, 2, 3, 5, 1.0, 2.3, 1, 1], ["hubbard_k", 2, 4, 2, 3, 0.7, 1.9, 1, 2], ["hubbard_k", 4, 3, 2, 2, 1.0, 1.1, 1, 2],
+       ["hubbard_k", 6, 2, 3, 3, 1.0, 4.0, 5, 1]]
 )
 
 
 def sha(a):
-    return hashlib.sha256(a.tobytes()).hexdigest()
+    """SHA-256 of the raw array; floating-point arrays with -0.0 folded into +0.0 first (x + 0.0), so that the digest
+    pins every VALUE bit for bit without depending on the sign of a zero imaginary part"""
+    import numpy as np
+    a = np.ascontiguousarray(a)
+    if a.dtype.kind == "c":
+        a = (a.real + 0.0) + 1j * (a.imag + 0.0)
+    elif a.dtype.kind == "f":
+        a = a + 0.0
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def main():

@@ -152,7 +152,7 @@ static Built build_triangular(int Lx, int Ly, double szval, int m, int n) {
 }
 
 /* Fermi-Hubbard on the square lattice, PBC (examples/trans_absent/latt_square/square_Fermi_Hubbard.cc). */
-static Built build_hubbard(int Lx, int Ly, double nup, double ndn, double t, double U) {
+static Built build_hubbard(int Lx, int Ly, double nup, double ndn, double t, double U, int km = -1, int kn = -1) {
     Built b; b.name = "hubbard";
     qbasis::lattice latt("square", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
     b.model = std::make_unique<Model>(latt);
@@ -180,8 +180,15 @@ static Built build_hubbard(int Lx, int Ly, double nup, double ndn, double t, dou
         M.add_Ham(cplx(U, 0.0) * (nu * nd));
         Nup += nu; Ndn += nd;
     }
-    M.enumerate_basis_full({Nup, Ndn}, {nup, ndn});
-    M.generate_Ham_sparse_full();
+    if (km < 0) {
+        M.enumerate_basis_full({Nup, Ndn}, {nup, ndn});
+        M.generate_Ham_sparse_full();
+    } else {                 /* momentum sector (examples/trans_symmetric/latt_square/square_Fermi_Hubbard.cc:95-104) */
+        M.fill_Weisse_table();
+        M.enumerate_basis_repr({km, kn}, {Nup, Ndn}, {nup, ndn});
+        M.generate_Ham_sparse_repr();
+        b.sym = qbasis::which_sym::repr;
+    }
     return b;
 }
 
@@ -390,7 +397,7 @@ static void usage() {
     fprintf(stderr,
         "usage: qb_ref [--threads T] [--workdir D] --out results.json <case> <args...> [actions]\n"
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
-        "        hubbard Lx Ly NUP NDN T U | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
+        "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
         " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
@@ -452,6 +459,7 @@ int main(int argc, char **argv)
         else if (c == "tri") { need(3); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_triangular(Lx, Ly, sz, -1, -1); }
         else if (c == "tri_k") { need(5); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); int m = atoi(argv[a++]), n = atoi(argv[a++]); b = build_triangular(Lx, Ly, sz, m, n); }
         else if (c == "hubbard") { need(6); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double nu = atof(argv[a++]), nd = atof(argv[a++]), t = atof(argv[a++]), U = atof(argv[a++]); b = build_hubbard(Lx, Ly, nu, nd, t, U); }
+        else if (c == "hubbard_k") { need(8); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double nu = atof(argv[a++]), nd = atof(argv[a++]), t = atof(argv[a++]), U = atof(argv[a++]); int km = atoi(argv[a++]), kn = atoi(argv[a++]); b = build_hubbard(Lx, Ly, nu, nd, t, U, km, kn); }
         else if (c == "tj_chain") { need(3); int L = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_tj_chain(L, N, sz); }
         else if (c == "honeycomb") { need(2); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); b = build_honeycomb(Lx, Ly); }
         else usage();

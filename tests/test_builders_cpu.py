@@ -37,6 +37,10 @@ def _repr_cases():
 
 def _build_repr(args):
     import repr_builders as R
+    if args[0] == "hubbard_k":
+        import repr_builders_fermion as F
+        _, Lx, Ly, nup, ndn, t, U, m, n = args
+        return F.hubbard_sector_upper_csr([Lx, Ly], nup, ndn, [m, n], F.square_hops(Lx, Ly), t, U)
     if args[0] == "heis_chain_k":
         _, L, sz, k = args
         return R.heisenberg_sector_upper_csr([L], L // 2 - sz, [k], R.chain_bonds(L))
@@ -53,7 +57,9 @@ def test_sector_builder_reproduces_reference_hashes(case):
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
     assert S.n == case["dim"] and ja.size == case["nnz"]
     assert sha(ia.astype(np.int64)) == case["ia"] and sha(ja.astype(np.int64)) == case["ja"]
-    assert sha(val.astype(np.complex128)) == case["val"]
+    val = val.astype(np.complex128)
+    val = (val.real + 0.0) + 1j * (val.imag + 0.0)          # -0.0 -> +0.0, as in oracle/make_repr_hashes.py
+    assert sha(val) == case["val"]
 
 
 @pytest.mark.parametrize("name,L,k,tri", [("heis16_k3", [16], [3], False), ("tri4x4_k01", [4, 4], [0, 1], True),
@@ -166,3 +172,16 @@ def test_triangular4x4_sector_energies_match_the_published_list(oracle, mn):
     import repr_builders as R
     S, ia, ja, val = R.heisenberg_sector_upper_csr([4, 4], 8, list(mn), R.triangular_bonds(4, 4))
     assert abs(_oracle_E0(oracle, S, ia, ja, val) - TRI4X4_E0[mn]) < 1e-8
+
+
+HUBBARD4X2_E0 = [-14.07605866, -10.50470669, -12.16861094, -12.19847764, -10.54300366, -14.03137587, -12.16861094, -12.19847764]
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_hubbard4x2_sector_energies_match_the_published_list(oracle, idx):
+    """examples/trans_symmetric/latt_square/square_Fermi_Hubbard.cc:112-119 (E0_list index = Ly m + n = 2 m + n): the
+    fermionic restatement (translation signs in norms and matrix elements) + the restated Lanczos."""
+    import repr_builders_fermion as F
+    m, n = idx // 2, idx % 2
+    S, ia, ja, val = F.hubbard_sector_upper_csr([4, 2], 4, 4, [m, n], F.square_hops(4, 2), 1.0, 1.1)
+    assert abs(_oracle_E0(oracle, S, ia, ja, val) - HUBBARD4X2_E0[idx]) < 1e-8

@@ -403,7 +403,7 @@ struct MatFree {
     uint32_t *d_codes = nullptr;
     int64_t *d_sliceptr = nullptr;  // [nslices + 1] word offsets
     struct TermTable *d_terms = nullptr;
-    int wbonds = 0;
+    int wbonds = 0, kind = 0;
     int64_t bytes = 0;
 };
 
@@ -412,6 +412,9 @@ struct TermTable {
     uint32_t hop[256];              // f | t << 5 | spin << 10 | weight << 11
     double amp[256];                // Heisenberg: J/2 * weight;  Hubbard: -t added `weight` times (like the LIL accumulation)
     uint8_t code_of[32][32];        // directed pair (f, t) -> code / 2 (Hubbard) or code (Heisenberg)
+    // branch-free decode for spmv_terms_kernel_v2: XOR masks on the two sublattice labels and "sites below" masks; the
+    // padding code 255 has all-zero masks and amplitude 0, so it replays as "0 * x[own row]"
+    uint32_t mask_a[256], mask_b[256], below_f[256], below_t[256];
 };
 
 __global__ void __launch_bounds__(kBBlock) matfree_states_kernel(SectorTables S, int64_t row_lo, int64_t nloc, uint2 *states)
@@ -654,17 +657,116 @@ spmv_terms_kernel(SectorTables S, const ModelParams *Mp, const TermTable *Tp, co
     }
 }
 
+
+// Second version of the replay, written so that nothing in a trip depends on a branch: every code -- padding included --
+// runs the same straight-line decode (XOR masks and "below" masks from shared memory), so the compiler can issue the
+// eight Lin-table loads of a trip together and then the four gathers, and the next trip's code word is fetched a trip
+// ahead.  The first version chains, per entry, table loads -> add -> gather behind a divergent branch and is bound by
+// that latency (31.7 ms on config 3).  Selected with QBGPU_TERMS_KERNEL=2 until it has been timed on hardware.
+template <typename VecT, bool DOTS, int KIND>
+__global__ void __launch_bounds__(kMFBlock, 3)
+spmv_terms_kernel_v2(SectorTables S, const ModelParams *Mp, const TermTable *Tp, const uint2 *__restrict__ states, const int64_t *__restrict__ sliceptr,
+                     const uint32_t *__restrict__ codes, int64_t nrows, int64_t nslices, int64_t row_lo, int wbonds,
+                     const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
+                     int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+{
+    using VT = VecTraits<VecT>;
+    __shared__ ModelParams M;
+    __shared__ uint32_t hop[256], mA[256], mB[256], bF[256], bT[256];
+    __shared__ double amp[256];
+    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        hop[k] = Tp->hop[k]; amp[k] = Tp->amp[k]; mA[k] = Tp->mask_a[k]; mB[k] = Tp->mask_b[k]; bF[k] = Tp->below_f[k]; bT[k] = Tp->below_t[k];
+    }
+    __syncthreads();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+        dot_scale = sx;
+    }
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    double d[3] = {0.0, 0.0, 0.0};
+    const int lane = threadIdx.x & 31;
+    constexpr int WPB = kMFBlock / 32;
+    for (int64_t s = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5); s < nslices; s += (int64_t)gridDim.x * WPB) {
+        const int64_t base = sliceptr[s];
+        const int maxw = (int)((sliceptr[s + 1] - base) >> 5);
+        const int64_t row = s * 32 + lane;
+        const bool live = row < nrows;
+        const uint2 st = live ? states[row] : states[nrows - 1];      // padding lanes replay zeros on a valid state
+        const uint32_t la = st.x, lb = st.y;
+        const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);
+        const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+        VecT acc = VT::zero();
+        int anti = 0;
+        uint32_t wnext = maxw > 0 ? codes[base + lane] : 0xFFFFFFFFu;
+        for (int k = 0; k < maxw; k++) {
+            const uint32_t w4 = wnext;
+            if (k + 1 < maxw) wnext = codes[base + (int64_t)(k + 1) * 32 + lane];
+            uint32_t na[4], nb[4];
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t code = (w4 >> (8 * u)) & 255u;
+                na[u] = la ^ mA[code];
+                nb[u] = lb ^ mB[code];
+                const double a = amp[code];
+                if (KIND == 0) {
+                    anti += (int)(hop[code] >> 11);
+                    v[u] = a;
+                } else {
+                    const uint32_t h = hop[code], bf = bF[code], bt = bT[code];
+                    const int f = h & 31, t = (h >> 5) & 31, sp = (h >> 10) & 1;
+                    int sg = __popc(occ0 & bf) + __popc(occ1 & bf) + __popc(occ0 & bt) + __popc(occ1 & bt);
+                    sg += sp * ((int)((occ0 >> f) & 1u) + (int)((occ0 >> t) & 1u)) + (f < t ? 1 : 0);
+                    v[u] = (sg & 1) ? -a : a;
+                }
+            }
+            int64_t jb[4];
+            int32_t ra[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { jb[u] = __ldg(S.Jb + nb[u]); ra[u] = __ldg(S.rankA + na[u]); }
+            VecT xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = ld_vec(x + (jb[u] + ra[u]));
+#pragma unroll
+            for (int u = 0; u < 4; u++) mac(acc, v[u], xv[u]);
+        }
+        if (live) {
+            double diag;
+            if (KIND == 0) diag = 0.25 * M.J * (double)(wbonds - 2 * anti);
+            else { diag = 0.0; const int ndbl = __popc(occ0 & occ1); for (int r = 0; r < ndbl; r++) diag += M.U; }
+            const VecT xi = x[row_lo + row];
+            mac(acc, diag, xi);
+            VecT out = VT::scale(alpha, acc);
+            if (gamma.x != 0.0 || gamma.y != 0.0) out = VT::add(out, VT::scale(gamma, xi));
+            if (use_beta) out = VT::add(out, VT::scale(beta, z[row]));
+            y[row] = out;
+            if (DOTS) {
+                const double2 p = VT::conj_mul(xi, out);
+                d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
+            }
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kMFBlock>(d, partials, ticket, dots_out);
+    }
+}
+
 template <typename VecT, bool DOTS>
 static int launch_terms_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
     const MatFree *mf = (const MatFree *)A->mf;
-    auto kern = spmv_terms_kernel<VecT, DOTS>;
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMFBlock, 0));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static const int version = getenv("QBGPU_TERMS_KERNEL") ? atoi(getenv("QBGPU_TERMS_KERNEL")) : 1;
+    auto kern = version == 2 ? (mf->kind == 0 ? spmv_terms_kernel_v2<VecT, DOTS, 0> : spmv_terms_kernel_v2<VecT, DOTS, 1>) : spmv_terms_kernel<VecT, DOTS>;
+    int blocks_per_sm = 0;
+    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMFBlock, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     const int64_t nrows = A->nrows();
     if (nrows == 0) return QBGPU_OK;
     const int64_t nslices = (nrows + 31) / 32;
@@ -776,7 +878,7 @@ static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
     QB_CU(cudaGetLastError());
 #undef QB_CU
     mf->bytes = (int64_t)(sizeof(uint2) * nloc + sizeof(int64_t) * T.Jb.size() + 4 * (T.rankA.size() + T.alist.size() + T.class_off.size()) + sizeof(ModelParams));
-    mf->wbonds = N.wbonds;
+    mf->wbonds = N.wbonds; mf->kind = M.kind;
     if ((flags & QBGPU_MATFREE_TERMS) && nloc > 0) {
         // code table: one code per directed bond (x spin for electrons)
         static thread_local TermTable TT;
@@ -798,6 +900,17 @@ static int create_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
                     npairs++;
                 }
         TT.ncodes = npairs * (M.kind == 0 ? 1 : 2);
+        for (int code = 0; code < TT.ncodes; code++) {
+            const uint32_t h = TT.hop[code];
+            const int f = h & 31, t = (h >> 5) & 31, sp = (h >> 10) & 1;
+            const int bits = M.kind == 0 ? 1 : 2;
+            const uint32_t bit_f = 1u << (bits * (f >> 1) + (M.kind == 0 ? 0 : sp)), bit_t = 1u << (bits * (t >> 1) + (M.kind == 0 ? 0 : sp));
+            if (f & 1) TT.mask_b[code] ^= bit_f; else TT.mask_a[code] ^= bit_f;
+            if (t & 1) TT.mask_b[code] ^= bit_t; else TT.mask_a[code] ^= bit_t;
+            TT.below_f[code] = (1u << f) - 1u;
+            TT.below_t[code] = (1u << t) - 1u;
+        }
+        TT.hop[255] = 0; TT.amp[255] = 0.0;                    // padding: no flip, no weight, zero amplitude
         const int64_t nslices = (nloc + 31) / 32;
         int64_t *d_words = nullptr;
         void *d_tmp = nullptr;

@@ -81,17 +81,25 @@ DYNAMIC_CASES = {
     "heis16_szq3": (16, 0, 0, 3, 60),
     "heis16_szq8": (16, 0, 0, 8, 60),
     "heis12_szq1": (12, 0, 0, 1, 40),
+    # the same flow with S^-_q (qb_ref heis_chain_smq): the target sector has one more down spin
+    "heis16_smq3": (16, 0, 0, 3, 60, "heis_chain_smq"),
+    "heis12_smq5": (12, 0, 0, 5, 40, "heis_chain_smq"),
 }
 
 
 def make_dynamic():
-    for name, (L, sz, k0, q, maxit) in DYNAMIC_CASES.items():
+    only = sys.argv[2:]
+    for name, spec in DYNAMIC_CASES.items():
+        if only and name not in only:
+            continue
+        L, sz, k0, q, maxit = spec[:5]
+        flow = spec[5] if len(spec) > 5 else "heis_chain_szq"
         wd = tempfile.mkdtemp(prefix="qbdyn_")
         pre = os.path.join(wd, "v")
-        res = O.run_qb_ref(["heis_chain_szq", L, sz, k0, q, maxit, "--dump-vecs", pre], threads=4, workdir=wd)
+        res = O.run_qb_ref([flow, L, sz, k0, q, maxit, "--dump-vecs", pre], threads=4, workdir=wd)
         phi0 = np.fromfile(pre + "_phi0.bin", dtype=np.complex128)
         aphi = np.fromfile(pre + "_Aphi0.bin", dtype=np.complex128)
-        meta = {"case": name, "L": L, "Sz": sz, "k0": k0, "q": q, "maxit": maxit, "E0": res["E0"], "dyn_norm": res["dyn_norm"],
+        meta = {"case": name, "flow": flow, "L": L, "Sz": sz, "k0": k0, "q": q, "maxit": maxit, "E0": res["E0"], "dyn_norm": res["dyn_norm"],
                 "dyn_steps": res["dyn_steps"]}
         out = os.path.join(O.GOLDEN_DIR, name + ".npz")
         np.savez_compressed(out, phi0=phi0, Aphi0=aphi, dyn_a=np.array(res["dyn_a"]), dyn_b=np.array(res["dyn_b"]), meta=json.dumps(meta))

@@ -261,7 +261,7 @@ static Built build_honeycomb(int Lx, int Ly) {
  * 95-128 with S^z instead of S^-): ground state of the sector (Sz, k0), then for momentum transfer q the sector k0 - q is
  * enumerated as sector 1, A = sum_x exp(-i 2 pi q x / L) / sqrt(L) S^z_x is applied to phi0 (model::moprXvec_repr,
  * src/model.cc:1716-1846) and model::measure_repr_dynamic (src/model.cc:1897-1912) returns the Lanczos coefficients. */
-static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, struct Json &js);
+static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, struct Json &js, char kind = 'z');
 
 struct Json {
     std::ostringstream o; bool first = true;
@@ -275,7 +275,7 @@ struct Json {
 };
 
 
-static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, Json &js)
+static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, Json &js, char kind)
 {
     qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
     Model M(latt);
@@ -297,9 +297,11 @@ static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxi
     for (int x = 0; x < L; x++) {
         uint32_t si; std::vector<int> work(latt.dim);
         latt.coor2site({x}, 0, si, work);
-        Szq += (std::exp(cplx(0.0, -Q * x)) / std::sqrt(static_cast<double>(L))) * Opr(si, 0, false, Sz);
+        if (kind == 'm') Szq += (std::exp(cplx(0.0, -Q * x)) / std::sqrt(static_cast<double>(L))) * Opr(si, 0, false, mat2(0, 0, 1, 0));   /* S^-_x */
+        else             Szq += (std::exp(cplx(0.0, -Q * x)) / std::sqrt(static_cast<double>(L))) * Opr(si, 0, false, Sz);
     }
-    M.enumerate_basis_repr({k0 - q}, {total_sz(latt.Nsites)}, {szval}, 1);
+    /* S^- lowers Sz by one (examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_one_excitation.cc:121) */
+    M.enumerate_basis_repr({k0 - q}, {total_sz(latt.Nsites)}, {kind == 'm' ? szval - 1.0 : szval}, 1);
     M.generate_Ham_sparse_repr(1);
     M.switch_sec_mat(1);
     js.integer("dim1", M.dim_repr[1]);
@@ -399,6 +401,7 @@ static void usage() {
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
         "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
+        "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
         " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
     exit(2);
@@ -440,12 +443,12 @@ int main(int argc, char **argv)
     std::string c = argv[a++];
     js.str("case", c);
     double t0 = now_s();
-    if (c == "heis_chain_szq") {
+    if (c == "heis_chain_szq" || c == "heis_chain_smq") {
         if (a + 5 > argc) usage();
         int L = atoi(argv[a]); double sz = atof(argv[a + 1]); int k0 = atoi(argv[a + 2]), q = atoi(argv[a + 3]); MKL_INT maxit = atoll(argv[a + 4]); a += 5;
         std::string prefix;
         if (a + 1 < argc && std::string(argv[a]) == "--dump-vecs") { prefix = argv[a + 1]; a += 2; }
-        flow_heis_chain_szq(L, sz, k0, q, maxit, prefix, js);
+        flow_heis_chain_szq(L, sz, k0, q, maxit, prefix, js, c == "heis_chain_smq" ? 'm' : 'z');
     } else if (c == "file_z" || c == "file_d") {
         if (a >= argc) usage();
         std::string path = argv[a++];

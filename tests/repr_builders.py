@@ -368,3 +368,30 @@ def szq_coefficients(L, q):
     """exp(-i 2 pi q x / L) / sqrt(L) per site of a chain (oracle/ref_driver.cc flow_heis_chain_szq)."""
     Q = 2.0 * 3.1415926535897932 * q / float(L)
     return np.array([cmath.exp(complex(0.0, -Q * x)) / math.sqrt(float(L)) for x in range(L)])
+
+
+def apply_sminus(S_old, S_new, coef, x):
+    """model::moprXvec_repr (src/model.cc:1762-1834), off-diagonal branch, for A = sum_r coef[r] S^-_r on spin-1/2:
+    every term lowers one up spin of the old representative; the produced state is brought to its representative in the
+    NEW sector (one more down spin) and
+        y[i] += sqrt(nu_old[j] / nu_new[i]) * x[j] * coef[r] * exp(-2 pi i k_new . disp_i / L).
+    (The reference adds these from several threads; which order the contributions to one y[i] arrive in is not fixed,
+    so agreement is to rounding, not to the bit.)"""
+    u = np.uint64
+    y = np.zeros(S_new.n, dtype=np.complex128)
+    ok = (np.abs(x) >= 2e-12) & (S_old.nu >= 2e-12)
+    rows = np.nonzero(ok)[0]
+    phase = np.conj(np.asarray(S_new.phase))                     # exp(-2 pi i k_new . disp / L)
+    for r in range(S_old.N):
+        act = rows[((S_old.states[rows] >> u(r)) & u(1)) == 0]   # digit 0 = up: S^- acts
+        if act.size == 0:
+            continue
+        s2 = S_old.states[act] | (u(1) << u(r))
+        a2, b2 = S_new.unzip(s2)
+        i, ca, cb = S_new.canon(a2, b2)
+        tgt = S_new.index(ca, cb)
+        keep = S_new.nu[tgt] >= 2e-12
+        act, i, tgt = act[keep], i[keep], tgt[keep]
+        val = np.sqrt(S_old.nu[act] / S_new.nu[tgt]) * x[act] * coef[r] * phase[i]
+        np.add.at(y, tgt, val)
+    return y

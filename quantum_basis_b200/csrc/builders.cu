@@ -566,109 +566,12 @@ __global__ void __launch_bounds__(kBBlock) terms_fill_kernel(const ModelParams *
     }
 }
 
-// The product from the term codes: thread = row (32 consecutive rows per warp), four codes per trip: decode, flip the
-// two sites, sign from the occupancy words, column through the Lin tables, then the four gathers together.
-template <typename VecT, bool DOTS>
-__global__ void __launch_bounds__(kMFBlock, 3)
-spmv_terms_kernel(SectorTables S, const ModelParams *Mp, const TermTable *Tp, const uint2 *__restrict__ states, const int64_t *__restrict__ sliceptr,
-                  const uint32_t *__restrict__ codes, int64_t nrows, int64_t nslices, int64_t row_lo, int wbonds,
-                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
-                  int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
-{
-    using VT = VecTraits<VecT>;
-    __shared__ ModelParams M;
-    __shared__ uint32_t hop[256];
-    __shared__ double amp[256];
-    for (int k = threadIdx.x; k < 16; k += blockDim.x) ((int *)&M)[k] = ((const int *)Mp)[k];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) { hop[k] = Tp->hop[k]; amp[k] = Tp->amp[k]; }
-    __syncthreads();
-    double dot_scale = 1.0;
-    if (scal_mode != 0) {
-        const double sx = sc[0], sz = sc[1], bprev = sc[2];
-        alpha = make_double2(sx, 0.0);
-        gamma = make_double2(0.0, 0.0);
-        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
-        dot_scale = sx;
-    }
-    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
-    const bool spins = M.kind == 0;
-    double d[3] = {0.0, 0.0, 0.0};
-    const int lane = threadIdx.x & 31;
-    constexpr int WPB = kMFBlock / 32;
-    for (int64_t s = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5); s < nslices; s += (int64_t)gridDim.x * WPB) {
-        const int64_t base = sliceptr[s];
-        const int maxw = (int)((sliceptr[s + 1] - base) >> 5);
-        const int64_t row = s * 32 + lane;
-        const bool live = row < nrows;
-        const uint2 st = live ? states[row] : make_uint2(0u, 0u);
-        const uint32_t la = st.x, lb = st.y;
-        const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);         // electrons only
-        const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
-        VecT acc = VT::zero();
-        int anti = 0;
-        for (int k = 0; k < maxw; k++) {
-            const uint32_t w4 = codes[base + (int64_t)k * 32 + lane];
-            int64_t c[4];
-            double v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t code = (w4 >> (8 * u)) & 255u;
-                c[u] = -1; v[u] = 0.0;
-                if (code != 255u) {
-                    const uint32_t h = hop[code];
-                    const int f = h & 31, t = (h >> 5) & 31, sp = (h >> 10) & 1;
-                    uint32_t na = la, nb = lb;
-                    if (spins) {
-                        if (f & 1) nb ^= 1u << (f >> 1); else na ^= 1u << (f >> 1);
-                        if (t & 1) nb ^= 1u << (t >> 1); else na ^= 1u << (t >> 1);
-                        anti += (int)(h >> 11);
-                        v[u] = amp[code];
-                    } else {
-                        const uint32_t below_f = (1u << f) - 1u, below_t = (1u << t) - 1u;
-                        int sg = __popc(occ0 & below_f) + __popc(occ1 & below_f) + __popc(occ0 & below_t) + __popc(occ1 & below_t);
-                        if (sp) sg += (int)((occ0 >> f) & 1u) + (int)((occ0 >> t) & 1u);
-                        if (f < t) sg += 1;
-                        if (f & 1) nb ^= 1u << (2 * (f >> 1) + sp); else na ^= 1u << (2 * (f >> 1) + sp);
-                        if (t & 1) nb ^= 1u << (2 * (t >> 1) + sp); else na ^= 1u << (2 * (t >> 1) + sp);
-                        v[u] = (sg & 1) ? -amp[code] : amp[code];
-                    }
-                    c[u] = col_of(S, na, nb);
-                }
-            }
-            VecT xv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) xv[u] = c[u] >= 0 ? ld_vec(x + c[u]) : VT::zero();
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (c[u] >= 0) mac(acc, v[u], xv[u]);
-        }
-        if (live) {
-            double diag;
-            if (spins) diag = 0.25 * M.J * (double)(wbonds - 2 * anti);
-            else { diag = 0.0; const int ndbl = __popc(occ0 & occ1); for (int r = 0; r < ndbl; r++) diag += M.U; }
-            const VecT xi = x[row_lo + row];
-            mac(acc, diag, xi);
-            VecT out = VT::scale(alpha, acc);
-            if (gamma.x != 0.0 || gamma.y != 0.0) out = VT::add(out, VT::scale(gamma, xi));
-            if (use_beta) out = VT::add(out, VT::scale(beta, z[row]));
-            y[row] = out;
-            if (DOTS) {
-                const double2 p = VT::conj_mul(xi, out);
-                d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
-            }
-        }
-    }
-    if (DOTS) {
-        d[0] *= dot_scale; d[1] *= dot_scale;
-        block_reduce_finalize<3, kMFBlock>(d, partials, ticket, dots_out);
-    }
-}
-
-
-// Second version of the replay, written so that nothing in a trip depends on a branch: every code -- padding included --
-// runs the same straight-line decode (XOR masks and "below" masks from shared memory), so the compiler can issue the
-// eight Lin-table loads of a trip together and then the four gathers, and the next trip's code word is fetched a trip
-// ahead.  The first version chains, per entry, table loads -> add -> gather behind a divergent branch and is bound by
-// that latency (31.7 ms on config 3).  Selected with QBGPU_TERMS_KERNEL=2 until it has been timed on hardware.
+// The product from the term codes: thread = row (32 consecutive rows per warp), four codes per trip.  Nothing in a trip
+// depends on a branch: every code -- padding included -- runs the same straight-line decode (XOR masks and "below"
+// masks from shared memory), so the compiler issues the eight Lin-table loads of a trip together and then the four
+// gathers, and the next trip's code word is fetched a trip ahead.  (A first version decoded behind a divergent
+// `if (code != padding)` and chained table loads -> add -> gather per entry: 31.7 ms on config 3 against 28.6 ms for this
+// one; profiles/r01_terms_coded_first_run.txt, r01_terms_coded_v2_run.txt.)
 template <typename VecT, bool DOTS, int KIND>
 __global__ void __launch_bounds__(kMFBlock, 3)
 spmv_terms_kernel_v2(SectorTables S, const ModelParams *Mp, const TermTable *Tp, const uint2 *__restrict__ states, const int64_t *__restrict__ sliceptr,
@@ -764,8 +667,7 @@ spmv_terms_kernel_v2(SectorTables S, const ModelParams *Mp, const TermTable *Tp,
 }
 
 
-// Third version: the second one with its six per-entry shared-memory lookups (random code -> random bank: the lookups
-// alone replay to an estimated 16 ms on config 3) folded into one 64-bit and one 32-bit lookup; the "below" masks are
+// Experimental variant (QBGPU_TERMS_KERNEL=3): the six per-entry shared-memory lookups folded into one 64-bit and one 32-bit lookup; the "below" masks are
 // rebuilt with shifts and the amplitude comes from a table indexed by the bond multiplicity (almost always the same
 // address across a warp: a broadcast).  QBGPU_TERMS_KERNEL=3; not yet run on hardware.
 template <typename VecT, bool DOTS, int KIND>
@@ -871,10 +773,9 @@ static int launch_terms_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
     const MatFree *mf = (const MatFree *)A->mf;
-    static const int version = getenv("QBGPU_TERMS_KERNEL") ? atoi(getenv("QBGPU_TERMS_KERNEL")) : 1;
+    static const int version = getenv("QBGPU_TERMS_KERNEL") ? atoi(getenv("QBGPU_TERMS_KERNEL")) : 2;
     auto kern = version == 3 ? (mf->kind == 0 ? spmv_terms_kernel_v3<VecT, DOTS, 0> : spmv_terms_kernel_v3<VecT, DOTS, 1>)
-              : version == 2 ? (mf->kind == 0 ? spmv_terms_kernel_v2<VecT, DOTS, 0> : spmv_terms_kernel_v2<VecT, DOTS, 1>)
-                             : spmv_terms_kernel<VecT, DOTS>;
+                             : (mf->kind == 0 ? spmv_terms_kernel_v2<VecT, DOTS, 0> : spmv_terms_kernel_v2<VecT, DOTS, 1>);
     int blocks_per_sm = 0;
     QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kMFBlock, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;

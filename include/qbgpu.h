@@ -221,8 +221,9 @@ int qbgpu_peer_pull_async(int lane, int slot, void *dst_local, const void *src_p
 /* same, moved by `ctas` thread blocks reading the peer mapping directly (16-byte aligned) instead of a copy engine */
 int qbgpu_peer_pull_sm(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes, int ctas);
 int qbgpu_peer_wait(int slot);
-/* Ring-fused sharded product: ONE kernel that multiplies the whole row shard while the peers' vector slices are still
- * arriving.  qbgpu_ring_prepare(A, rank, world, chunk, &view) re-orders every row of the shard A (rows [rank*chunk, ...),
+/* Ring-fused sharded product (EXPERIMENTAL: correct, but measured slower than the column-block scheme -- a row needs every
+ * slice, so the kernel serialises behind the last arrival): ONE kernel that multiplies the whole row
+ * shard while the peers' vector slices are still arriving.  qbgpu_ring_prepare(A, rank, world, chunk, &view) re-orders every row of the shard A (rows [rank*chunk, ...),
  * chunk a multiple of 4) so that its own rank's columns come first and the others in ring order, and returns a view
  * handle sharing A's arrays (destroy it before A): every product with the VIEW (qbgpu_{d,z}mv, qbgpu_lanczos_step_a)
  * waits, entry by entry, for the arrival flag of the slice it is about to gather from; A itself keeps working with the
@@ -239,10 +240,11 @@ int qbgpu_peer_ring_status(int *timed_out);
  * order (src/basis.cc:1144-1190).  For the BASELINE sizes the reference's own assembler cannot run,
  * so these generators build the SAME expanded matrix (same basis order, same values) directly in HBM; they are
  * checked entry-for-entry against matrices assembled by the compiled reference at sizes it can handle.
- *   heisenberg: spin-1/2, H = sum_bonds J (S_i.S_j), fixed number of up spins `nup`, bonds[2*nbonds] site pairs.
+ *   heisenberg: spin-1/2, H = sum_bonds J (S_i.S_j), fixed number of DOWN spins `ndown` (the reference's digit 1;
+ *               Sz_total = nsites/2 - ndown), bonds[2*nbonds] site pairs.
  *   hubbard:    single "electron" orbital, H = -t sum_{<ij>,s} (c+_is c_js + h.c.) + U sum n_up n_dn.
  * row_lo/row_hi select a row shard (0,-1 = all rows). */
-int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int nup, int nbonds, const int32_t *bonds, double J,
+int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
                            int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                         double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
@@ -251,7 +253,8 @@ int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbo
  * being read from a stored matrix).  Same arguments as the generators; nothing but the basis states (8 bytes per row)
  * and the Lin tables is kept in HBM, so sectors whose stored matrix would not fit (e.g. the Heisenberg chain L = 32,
  * Sz = 0: 601,080,390 states, 238 GB of CSR) still run on one GPU.  The handle works with every entry point above
- * (products, fused Lanczos / CG / KPM loops) and gives the same results as the stored matrix up to summation order. */
+ * (products, fused Lanczos / CG / KPM loops) and gives the same results as the stored matrix up to summation order.
+ * flags: QBGPU_MATFREE_TERMS adds the one-byte-per-entry term codes (replay instead of search; bit-identical results). */
 int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds, const int32_t *bonds, double J,
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,

@@ -44,6 +44,9 @@ extern "C" {
 #define QBGPU_MATFREE_TERMS 64  /* qbgpu_create_matfree_*: also store one byte per entry naming the Hamiltonian term that
                                   * produces it (directed bond x spin), so the product replays each row -- column from the
                                   * Lin tables, sign from the occupancy words -- without searching for applicable terms */
+#define QBGPU_SPECIES_ORDER 128 /* qbgpu_build_hubbard / qbgpu_create_matfree_hubbard: keep the vectors INTERNALLY in the order
+                                  * (rank of the up configuration, rank of the down configuration) and multiply in two passes
+                                  * (see "species order" below); results and calling convention are unchanged */
 #define QBGPU_VALUE_DICT    16   /* opt-in: store fp64 values as 1-byte codes into a table of the distinct values when there
                                     are at most 256 of them (lossless; products are bit-identical); implies FORMAT_SELL */
 
@@ -259,6 +262,36 @@ int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, in
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                                  double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* --------------------------------------------------------------------- species order (Hubbard, QBGPU_SPECIES_ORDER)
+ * In the reference's Lin-table order every hopping term of the Hubbard matrix sends a row far away in the index space,
+ * and the gathers of x cost ~19 vector sizes of DRAM traffic per product instead of 1.  With QBGPU_SPECIES_ORDER the
+ * handle keeps its vectors INTERNALLY in the order  p = rank(up configuration) * D_dn + rank(down configuration)  and
+ * multiplies in two passes: (diagonal + hops of the down electrons), whose gathers stay inside one contiguous block of
+ * D_dn entries, then (hops of the up electrons) traversed by tiles of down indices whose gathered columns stay in L2.
+ *   qbgpu_build_hubbard          + flag: the two parts are stored (sliced-jagged layout, same entries and bytes as the
+ *                                  ordinary handle) and multiplied by the production kernel;
+ *   qbgpu_create_matfree_hubbard + flag: nothing is stored but per-species hop tables (a few MB).
+ * The calling convention does not change: qbgpu_{d,z}mv, qbgpu_lanczos_*, qbgpu_eigenvec_cg_*, qbgpu_energy_scale_*,
+ * qbgpu_kpm_moments_* and qbgpu_trlan take and return vectors in the REFERENCE's order (they permute on the way in and
+ * out; inside a Krylov loop nothing is permuted).  The fused low-level entry points (qbgpu_spmv_fused,
+ * qbgpu_lanczos_step_*) work in the internal order; the three functions below convert.  No row shards; not available:
+ * to_dense, download_expanded, split_columns, ring_prepare.  QBGPU_SPECIES_TILE (environment, default 128) sets the tile
+ * width in down indices. */
+int qbgpu_native_order(qbgpu_matrix_t A, int *has_internal_order);
+int qbgpu_vec_to_native(qbgpu_matrix_t A, const void *x_reference_order_dev, void *x_internal_order_dev);   /* out of place */
+int qbgpu_vec_from_native(qbgpu_matrix_t A, const void *x_internal_order_dev, void *x_reference_order_dev); /* out of place */
+int qbgpu_native_perm(qbgpu_matrix_t A, int32_t *perm_host);   /* perm[r] = internal index of the reference's row r */
+/* Test hook, HOST ONLY (no device is touched): runs the species-order index logic -- the same __host__ __device__ row
+ * functions the kernels call -- on host arrays, so that the CPU test-suite can check it against the reference-pinned
+ * restatement.  sizes[4] = {D_up, D_dn, up-hop entries, down-hop entries}; every other pointer may be NULL (skipped):
+ * perm[n]; the two stored parts as CSR (rowptr[n+1]; nnz_local = D_up*(dn_entries + D_dn), nnz_cross = D_dn*up_entries);
+ * slice_order[ceil(n/32)]; y[n] = H x by the two matrix-free passes (x, y real, internal order), touched[p] += 1 for every
+ * write of the cross pass (all ones afterwards). */
+int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U, int tile,
+                             int64_t *sizes, int32_t *perm, int64_t *rowptr_local, int32_t *col_local, double *val_local,
+                             int64_t *rowptr_cross, int32_t *col_cross, double *val_cross, int32_t *slice_order,
+                             const double *x, double *y, int32_t *touched);
+
 /* --------------------------------------------------------------------- translation-symmetric sectors
  * Device counterpart of model::fill_Weisse_table + enumerate_basis_repr + generate_Ham_sparse_repr
  * (src/model.cc:205-249, 275-487, 688-836) for spin-1/2 models on untilted lattices with one site per unit cell and

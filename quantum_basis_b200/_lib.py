@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libqbgpu.so")
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 
 QBGPU_HOST, QBGPU_DEVICE = 0, 1
-KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL, VALUE_DICT, MATFREE_TERMS = 1, 2, 4, 8, 16, 64
+KEEP_COMPLEX, NO_AUTOTUNE, FORMAT_CSR, FORMAT_SELL, VALUE_DICT, MATFREE_TERMS, SPECIES_ORDER = 1, 2, 4, 8, 16, 64, 128
 
 
 class QbgpuError(RuntimeError):
@@ -80,6 +80,9 @@ _SIGS = {
     "qbgpu_sector_get_info": [vp, C.POINTER(SectorInfo)], "qbgpu_sector_states": [vp, vp], "qbgpu_sector_norms": [vp, vp],
     "qbgpu_sector_build_heisenberg": [vp, C.POINTER(vp), C.c_int, vp, dbl, dbl, C.c_int],
     "qbgpu_sector_apply_sz": [vp, vp, vp, vp, vp],
+    "qbgpu_native_order": [vp, C.POINTER(C.c_int)], "qbgpu_vec_to_native": [vp, vp, vp], "qbgpu_vec_from_native": [vp, vp, vp],
+    "qbgpu_native_perm": [vp, vp],
+    "qbgpu_debug_species_host": [C.c_int, C.c_int, C.c_int, C.c_int, vp, dbl, dbl, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "qbgpu_build_heisenberg_orbit": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, dbl, C.c_int, vp, i64],
 }
 _RESTYPES = {"qbgpu_last_error": C.c_char_p, "qbgpu_version": C.c_char_p, "qbgpu_kernel_launches": C.c_int64,

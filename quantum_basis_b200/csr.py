@@ -216,6 +216,30 @@ class csr_mat:
         """y = H*x (src/sparse.cc:291-297)."""
         self._mv(complex(1.0), x, complex(0.0), y)
 
+    def has_internal_order(self):
+        """True for QBGPU_SPECIES_ORDER handles: the fused low-level entry points then work in the handle's internal order,
+        the reference-shaped ones (MultMv, lanczos, ...) keep the reference's."""
+        f = C.c_int(0)
+        check(lib().qbgpu_native_order(self.handle, C.byref(f)))
+        return bool(f.value)
+
+    def native_perm(self):
+        """perm[r] = internal index of the reference's basis state r (species-order handles)."""
+        p = np.empty(self.dim, dtype=np.int32)
+        check(lib().qbgpu_native_perm(self.handle, _ptr(p)))
+        return p
+
+    def to_native(self, x, out=None):
+        """Device vector in the reference's order -> the handle's internal order (out of place)."""
+        out = out if out is not None else DeviceVector(x.n, x.dtype)
+        check(lib().qbgpu_vec_to_native(self.handle, _ptr(x), _ptr(out)))
+        return out
+
+    def from_native(self, x, out=None):
+        out = out if out is not None else DeviceVector(x.n, x.dtype)
+        check(lib().qbgpu_vec_from_native(self.handle, _ptr(x), _ptr(out)))
+        return out
+
     def to_dense(self):
         """Column-major dense copy, returned as an (n, n) array with out[row, col] (src/sparse.cc:299-315)."""
         out = np.zeros(self.dim * self.dim, dtype=self.dtype)
@@ -266,7 +290,8 @@ def heisenberg(nsites, ndown, bonds, J=1.0, is_complex=True, flags=0, rows=None,
 def hubbard(nsites, nup, ndn, bonds, t=1.0, U=0.0, is_complex=True, flags=0, rows=None, matrix_free=False):
     """Single-orbital Fermi-Hubbard model H = -t sum_<ij>,s (c+_is c_js + h.c.) + U sum_i n_up n_dn with N_up, N_dn fixed,
     in the reference's Lin-table basis order and fermion-sign convention (src/basis.cc:2717-2731).  Stored or
-    matrix_free as for heisenberg()."""
+    matrix_free as for heisenberg().  flags | SPECIES_ORDER: same operator and calling convention, vectors kept
+    internally in (up configuration, down configuration) order and multiplied in two passes (include/qbgpu.h)."""
     b, nb = _bond_array(bonds)
     h = C.c_void_p()
     lo, hi = (0, -1) if rows is None else (int(rows[0]), int(rows[1]))

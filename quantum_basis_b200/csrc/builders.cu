@@ -11,6 +11,7 @@
 // the bond terms with bit operations, looks the columns up through the same Ja/Jb tables, and sorts the row.
 // tests/test_builders.py checks the result entry for entry against matrices assembled by the compiled reference.
 #include "internal.hpp"
+#include "lin_tables.hpp"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <chrono>
@@ -22,7 +23,6 @@ namespace qb {
 static double wall_b() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 constexpr int kBBlock = 128;
-constexpr int kMaxBonds = 256;
 
 // Tables describing the sector.  Site s lives on sublattice A (even s, position s/2) or B (odd s, position s/2);
 // a sublattice label packs `bps` bits per site (bps = 1: spin-1/2 digit; bps = 2: electron digit = up + 2*dn).
@@ -37,22 +37,13 @@ struct SectorTables {
     uint32_t sizeB;
 };
 
-struct Bond { int i, j; int w; };    // site pair with multiplicity (duplicates in the caller's list are merged)
-
-struct ModelParams {
-    int kind;                         // 0 heisenberg, 1 hubbard
-    double J, t, U;
-    int nbonds;
-    Bond bonds[kMaxBonds];
-};
-
-__device__ __forceinline__ void label_counts(uint32_t lab, int bps, int &c0, int &c1)
+__host__ __device__ __forceinline__ void label_counts(uint32_t lab, int bps, int &c0, int &c1)
 {
-    if (bps == 1) { c0 = __popc(lab); c1 = 0; }
-    else { c0 = __popc(lab & 0x55555555u); c1 = __popc(lab & 0xAAAAAAAAu); }
+    if (bps == 1) { c0 = popc_hd(lab); c1 = 0; }
+    else { c0 = popc_hd(lab & 0x55555555u); c1 = popc_hd(lab & 0xAAAAAAAAu); }
 }
 
-__device__ __forceinline__ void unrank_row(const SectorTables &S, int64_t row, uint32_t &la, uint32_t &lb)
+__host__ __device__ __forceinline__ void unrank_row(const SectorTables &S, int64_t row, uint32_t &la, uint32_t &lb)
 {
     // largest lb with Jb[lb] <= row  (empty B labels share their successor's offset and are skipped)
     uint32_t lo = 0, hi = S.sizeB;                          // answer in [lo, hi)
@@ -178,21 +169,13 @@ __global__ void __launch_bounds__(kBBlock) build_fill_kernel(SectorTables S, con
 }
 
 // ------------------------------------------------------------------------------------------ host-side tables
-struct HostTables {
-    int nsites = 0, bps = 1, nA = 0, nB = 0, t0 = 0, t1 = 0;
-    int64_t dim = 0;
-    std::vector<int64_t> Jb;
-    std::vector<int32_t> rankA, class_off;
-    std::vector<uint32_t> alist;
-};
-
 static void counts_host(uint32_t lab, int bps, int &c0, int &c1)
 {
     if (bps == 1) { c0 = __builtin_popcount(lab); c1 = 0; }
     else { c0 = __builtin_popcount(lab & 0x55555555u); c1 = __builtin_popcount(lab & 0xAAAAAAAAu); }
 }
 
-static int make_tables(int nsites, int bps, int t0, int t1, HostTables &T)
+int make_tables(int nsites, int bps, int t0, int t1, HostTables &T)
 {
     T.nsites = nsites; T.bps = bps; T.nA = (nsites + 1) / 2; T.nB = nsites / 2; T.t0 = t0; T.t1 = t1;
     if (bps * T.nA > 24) return fail(QBGPU_ERR_ARG, "builder: sublattice label too wide (max 24 bits per sublattice)");
@@ -219,7 +202,7 @@ static int make_tables(int nsites, int bps, int t0, int t1, HostTables &T)
     return QBGPU_OK;
 }
 
-static int merge_bonds(int nsites, int nbonds, const int32_t *bonds, ModelParams &M)
+int merge_bonds(int nsites, int nbonds, const int32_t *bonds, ModelParams &M)
 {
     M.nbonds = 0;
     for (int b = 0; b < nbonds; b++) {
@@ -304,6 +287,65 @@ static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     return QBGPU_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ Lin order -> species order
+// perm[r] for the species-order handles of species.cu: row r of the reference's Lin order is the electron state (la, lb);
+// its up / down occupancy words (site-indexed) are ranked among the words of equal popcount.
+__host__ __device__ __forceinline__ int32_t species_index_of_row(const SectorTables &S, int64_t r, const int32_t *rank_in_class, int64_t Dd)
+{
+    uint32_t la, lb;
+    unrank_row(S, r, la, lb);
+    const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);              // same words as row_entries_walk
+    const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+    return (int32_t)((int64_t)rank_in_class[occ0] * Dd + rank_in_class[occ1]);
+}
+
+__global__ void __launch_bounds__(kBBlock) species_perm_kernel(SectorTables S, int64_t n, const int32_t *__restrict__ rank_in_class, int64_t Dd, int32_t *perm)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        perm[r] = species_index_of_row(S, r, rank_in_class, Dd);
+}
+
+// the same row function on the host (qbgpu_debug_species_host: CPU tests of the index logic, no device involved)
+void species_perm_host(const HostTables &T, const int32_t *rank_in_class, int64_t Dd, int32_t *perm)
+{
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = T.Jb.data(); S.rankA = T.rankA.data(); S.alist = T.alist.data(); S.class_off = T.class_off.data(); S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    for (int64_t r = 0; r < T.dim; r++) perm[r] = species_index_of_row(S, r, rank_in_class, Dd);
+}
+
+int species_perm_build(const HostTables &T, const int32_t *d_rank_in_class, int64_t Dd, int32_t *d_perm)
+{
+    Context &c = ctx();
+    if (T.bps != 2) return fail(QBGPU_ERR_ARG, "species order: electron sectors only");
+    int64_t *d_Jb = nullptr;
+    int32_t *d_rank = nullptr, *d_off = nullptr;
+    uint32_t *d_alist = nullptr;
+    auto cleanup = [&]() { cudaFree(d_Jb); cudaFree(d_rank); cudaFree(d_off); cudaFree(d_alist); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_Jb, sizeof(int64_t) * T.Jb.size()));
+    QB_CU(cudaMalloc(&d_rank, sizeof(int32_t) * T.rankA.size()));
+    QB_CU(cudaMalloc(&d_alist, sizeof(uint32_t) * T.alist.size()));
+    QB_CU(cudaMalloc(&d_off, sizeof(int32_t) * T.class_off.size()));
+    QB_CU(cudaMemcpyAsync(d_Jb, T.Jb.data(), sizeof(int64_t) * T.Jb.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_rank, T.rankA.data(), sizeof(int32_t) * T.rankA.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = d_Jb; S.rankA = d_rank; S.alist = d_alist; S.class_off = d_off; S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    int64_t g = (T.dim + kBBlock - 1) / kBBlock;
+    if (g < 1) g = 1;
+    if (g > 148 * 64) g = 148 * 64;
+    species_perm_kernel<<<(int)g, kBBlock, 0, c.stream>>>(S, T.dim, d_rank_in_class, Dd, d_perm);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+#undef QB_CU
+    cleanup();
+    return QBGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ matrix-free
 // Neighbour tables for the matrix-free kernel: instead of testing every (bond, direction, spin) -- 128 tests per row on
@@ -993,6 +1035,7 @@ int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, in
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
     if (nsites < 2 || ndown < 0 || ndown > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "create_matfree_heisenberg: bad argument");
+    if (flags & QBGPU_SPECIES_ORDER) return fail(QBGPU_ERR_ARG, "create_matfree_heisenberg: QBGPU_SPECIES_ORDER is defined for the Hubbard model only");
     HostTables T;
     QB_TRY(make_tables(nsites, 1, ndown, 0, T));
     static thread_local ModelParams M;
@@ -1010,6 +1053,10 @@ int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn
     static thread_local ModelParams M;
     M.kind = 1; M.J = 0; M.t = t; M.U = U;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    if (flags & QBGPU_SPECIES_ORDER) {
+        if (row_lo != 0 || (row_hi >= 0 && row_hi != T.dim)) return fail(QBGPU_ERR_ARG, "create_matfree_hubbard: species order has no row shards");
+        return species_build_matfree(A, T, M, api_complex, flags);
+    }
     return create_matfree(A, T, M, api_complex, row_lo, row_hi, flags);
 }
 
@@ -1017,6 +1064,7 @@ int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds,
                            int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
     if (nsites < 2 || ndown < 0 || ndown > nsites || nbonds < 1 || !bonds) return fail(QBGPU_ERR_ARG, "build_heisenberg: bad argument");
+    if (flags & QBGPU_SPECIES_ORDER) return fail(QBGPU_ERR_ARG, "build_heisenberg: QBGPU_SPECIES_ORDER is defined for the Hubbard model only");
     HostTables T;
     QB_TRY(make_tables(nsites, 1, ndown, 0, T));
     static thread_local ModelParams M;
@@ -1034,6 +1082,10 @@ int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbo
     static thread_local ModelParams M;
     M.kind = 1; M.J = 0; M.t = t; M.U = U;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    if (flags & QBGPU_SPECIES_ORDER) {
+        if (row_lo != 0 || (row_hi >= 0 && row_hi != T.dim)) return fail(QBGPU_ERR_ARG, "build_hubbard: species order has no row shards");
+        return species_build_stored(A, T, M, api_complex, flags);
+    }
     return build_generic(A, T, M, api_complex, flags, row_lo, row_hi);
 }
 

@@ -47,42 +47,61 @@ int ensure_init();
 #define QB_LAUNCH_COUNT() (qb::ctx().launches++)
 
 // -------------------------------------------------------------------------------------- complex algebra
+// (host + device: species.cu runs its per-row functions on the host too, for the CPU tests of the index logic)
 struct cplx { double x, y; };   // layout-compatible with double2 / std::complex<double>
 
 __host__ __device__ inline double2 make_c(double re, double im) { return make_double2(re, im); }
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 
 // fma-style accumulate: acc += v * x for the (ValT, VecT) combinations used
-__device__ __forceinline__ void mac(double &acc, double v, double x) { acc = fma(v, x, acc); }
-__device__ __forceinline__ void mac(double2 &acc, double v, double2 x) { acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y); }
-__device__ __forceinline__ void mac(double2 &acc, double2 v, double2 x)
+__host__ __device__ __forceinline__ void mac(double &acc, double v, double x) { acc = fma(v, x, acc); }
+__host__ __device__ __forceinline__ void mac(double2 &acc, double v, double2 x) { acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y); }
+__host__ __device__ __forceinline__ void mac(double2 &acc, double2 v, double2 x)
 {
     acc.x = fma(v.x, x.x, acc.x); acc.x = fma(-v.y, x.y, acc.x);
     acc.y = fma(v.x, x.y, acc.y); acc.y = fma(v.y, x.x, acc.y);
 }
 
+__host__ __device__ __forceinline__ int popc_hd(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// read-only load: the non-coherent path on the device, a plain load on the host
+template <typename T> __host__ __device__ __forceinline__ T ld_ro(const T *p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 template <typename V> struct VecTraits;
 template <> struct VecTraits<double> {
     static constexpr int ncomp = 1;
-    __device__ static __forceinline__ double zero() { return 0.0; }
-    __device__ static __forceinline__ double add(double a, double b) { return a + b; }
+    __host__ __device__ static __forceinline__ double zero() { return 0.0; }
+    __host__ __device__ static __forceinline__ double add(double a, double b) { return a + b; }
     // s*a with complex scalar s: real vectors only use the real part
-    __device__ static __forceinline__ double scale(double2 s, double a) { return s.x * a; }
-    __device__ static __forceinline__ double rscale(double s, double a) { return s * a; }
-    __device__ static __forceinline__ double2 conj_mul(double a, double b) { return make_double2(a * b, 0.0); }   // conj(a)*b
-    __device__ static __forceinline__ double abs2(double a) { return a * a; }
+    __host__ __device__ static __forceinline__ double scale(double2 s, double a) { return s.x * a; }
+    __host__ __device__ static __forceinline__ double rscale(double s, double a) { return s * a; }
+    __host__ __device__ static __forceinline__ double2 conj_mul(double a, double b) { return make_double2(a * b, 0.0); }   // conj(a)*b
+    __host__ __device__ static __forceinline__ double abs2(double a) { return a * a; }
     __device__ static __forceinline__ double shfl_xor(double a, int m, int w, unsigned mask) { return __shfl_xor_sync(mask, a, m, w); }
 };
 template <> struct VecTraits<double2> {
     static constexpr int ncomp = 2;
-    __device__ static __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
-    __device__ static __forceinline__ double2 add(double2 a, double2 b) { return cadd(a, b); }
-    __device__ static __forceinline__ double2 scale(double2 s, double2 a) { return cmul(s, a); }
-    __device__ static __forceinline__ double2 rscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
-    __device__ static __forceinline__ double2 conj_mul(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
-    __device__ static __forceinline__ double abs2(double2 a) { return a.x * a.x + a.y * a.y; }
+    __host__ __device__ static __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+    __host__ __device__ static __forceinline__ double2 add(double2 a, double2 b) { return cadd(a, b); }
+    __host__ __device__ static __forceinline__ double2 scale(double2 s, double2 a) { return cmul(s, a); }
+    __host__ __device__ static __forceinline__ double2 rscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+    __host__ __device__ static __forceinline__ double2 conj_mul(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+    __host__ __device__ static __forceinline__ double abs2(double2 a) { return a.x * a.x + a.y * a.y; }
     __device__ static __forceinline__ double2 shfl_xor(double2 a, int m, int w, unsigned mask)
     { return make_double2(__shfl_xor_sync(mask, a.x, m, w), __shfl_xor_sync(mask, a.y, m, w)); }
 };

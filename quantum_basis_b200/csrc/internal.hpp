@@ -38,6 +38,17 @@ struct qbgpu_matrix {
     // peer pulls deliver them and waits, entry by entry, on the arrival flags of peer.cu.
     int      ring_world = 0, ring_rank = 0;
     int64_t  ring_chunk = 0;
+    // QBGPU_SPECIES_ORDER handles (species.cu; single-orbital Hubbard): vectors live INTERNALLY in the order
+    // p = rank(up configuration) * D_dn + rank(down configuration).  `perm[r]` = internal index of the reference's row r;
+    // the reference-shaped entry points (mv, lanczos, CG, energy_scale, KPM) permute through it, the fused low-level ones
+    // (spmv_fused, lanczos_step_*) work in the internal order.  `sp` owns the species tables.  A stored handle holds the
+    // "local" part (diagonal + hops of the down electrons: inside the block of one up configuration) and `second` the
+    // "cross" part (hops of the up electrons), whose 32-row slices are traversed in `slice_order` (tiles of down indices).
+    int32_t *perm = nullptr;
+    void    *sp = nullptr;
+    qbgpu_matrix *second = nullptr;
+    int32_t *slice_order = nullptr;
+    void    *perm_x = nullptr, *perm_y = nullptr;      // staging vectors of the reference-order product (lazily allocated)
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
@@ -72,6 +83,17 @@ int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view);     // sjds.cu
 int peer_ring_flags(const int **flags, int **timeout_flag);                 // peer.cu: arrival flags by ring distance
+// species.cu
+int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &args);      // the two-pass products of species-order handles
+void species_destroy(qbgpu_matrix *A);
+int64_t species_bytes(const qbgpu_matrix *A);
+// dst[perm[r]] = src[r]  (reference order -> internal order); complex -> real takes the real part, real -> complex sets imag = 0
+int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst);
+// dst[r] = a * src[perm[r]] + b * dst[r]  (internal order -> reference order; b == 0: dst is not read)
+int vec_from_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst, double2 a, double2 b);
+int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void *y, int where);   // y = alpha*H*x + beta*y, reference order
+inline int no_species(const qbgpu_matrix *A, const char *what)
+{ return (A && A->sp) ? fail(QBGPU_ERR_STATE, std::string(what) + ": not available for species-order handles") : QBGPU_OK; }
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
 // expand a device-resident reference-format CSR (int64 row_start/row_end/col, offsets from 0) into a new handle

@@ -424,9 +424,143 @@ static int is_all_real(int64_t n, const void *dvec, bool *out)
     return QBGPU_OK;
 }
 
+// ------------------------------------------------------------------------------- species-order handles (species.cu)
+// The loops above are order-agnostic: they see vectors in whatever order launch_spmv multiplies in.  For a handle with an
+// internal order the drivers below keep the reference's order at the boundary: the caller's vectors are permuted into
+// temporaries on the way in and back on the way out -- the same two passes the real-mode dispatch spends on
+// complex -> fp64 -> complex, with which the permutation is fused.  (a_m, b_m), E0, the KPM moments and the spectral
+// bounds do not depend on the order; vectors come back in the reference's order.
+struct NativeRun {
+    qbgpu_matrix R;            // the handle as the loop sees it (fp64 vectors in real mode)
+    bool loop_cplx = false;    // scalar type of the loop's vectors
+    DevBuf stage, work;        // device copy of host vectors (reference order); the loop's vectors (internal order)
+    char *ref = nullptr;       // the caller's vectors on the device, reference order
+    size_t vb_api = 8, vb_loop = 8;
+};
+
+// in_slots: which of the caller's `nvec` vectors are inputs (bit j = vector j); real mode needs all of them real
+static int native_begin(NativeRun &N, qbgpu_matrix *A, bool cplx, void *v, int nvec, unsigned in_slots, int where, bool allow_real)
+{
+    Context &c = ctx();
+    const int64_t n = A->n;
+    N.vb_api = cplx ? 16 : 8;
+    N.ref = (char *)v;
+    if (where == QBGPU_HOST) {
+        QB_TRY(N.stage.alloc(N.vb_api * n * nvec));
+        N.ref = (char *)N.stage.p;
+        for (int j = 0; j < nvec; j++)
+            if (in_slots & (1u << j)) QB_CUDA(cudaMemcpyAsync(N.ref + N.vb_api * n * j, (const char *)v + N.vb_api * n * j, N.vb_api * n, cudaMemcpyHostToDevice, c.stream));
+    } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    bool real = allow_real && real_mode_enabled(A, cplx);
+    for (int j = 0; real && j < nvec; j++)
+        if (in_slots & (1u << j)) { bool r = false; QB_TRY(is_all_real(n, N.ref + N.vb_api * n * j, &r)); real = real && r; }
+    N.loop_cplx = cplx && !real;
+    N.vb_loop = N.loop_cplx ? 16 : 8;
+    N.R = *A;
+    N.R.api_complex = N.loop_cplx;
+    QB_TRY(N.work.alloc(N.vb_loop * n * nvec));
+    QB_CUDA(cudaMemsetAsync(N.work.p, 0, N.vb_loop * n * nvec, c.stream));
+    for (int j = 0; j < nvec; j++)
+        if (in_slots & (1u << j)) QB_TRY(vec_to_native(A, cplx, N.loop_cplx, N.ref + N.vb_api * n * j, (char *)N.work.p + N.vb_loop * n * j));
+    return QBGPU_OK;
+}
+
+// out_slots: vectors handed back to the caller (internal order -> reference order, widened to the API's scalar type)
+static int native_end(NativeRun &N, qbgpu_matrix *A, bool cplx, void *v, unsigned out_slots, int nvec, int where)
+{
+    Context &c = ctx();
+    const int64_t n = A->n;
+    for (int j = 0; j < nvec; j++) {
+        if (!(out_slots & (1u << j))) continue;
+        QB_TRY(vec_from_native(A, N.loop_cplx, cplx, (char *)N.work.p + N.vb_loop * n * j, N.ref + N.vb_api * n * j, make_double2(1.0, 0.0), make_double2(0.0, 0.0)));
+        if (where == QBGPU_HOST) QB_CUDA(cudaMemcpyAsync((char *)v + N.vb_api * n * j, N.ref + N.vb_api * n * j, N.vb_api * n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+static int lanczos_native(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
+                          double *hess, const char *purpose, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!m_out || !v || !hess || !purpose) return fail(QBGPU_ERR_ARG, "lanczos: null argument");
+    if (np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);      // nothing to do / argument errors
+    const bool val1 = strstr(purpose, "val1") != nullptr;
+    const int nvec = val1 ? 3 : 2;
+    NativeRun N;
+    QB_TRY(native_begin(N, A, cplx, v, nvec, val1 ? 0x5u : 0x1u, where, true));
+    QB_TRY(lanczos_impl(&N.R, N.loop_cplx, k, np, maxit, m_out, N.work.p, hess, purpose, QBGPU_DEVICE));
+    return native_end(N, A, cplx, v, 0x3u, nvec, where);    // the two live vectors, like the reference's slots
+}
+
+static int cg_native(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, double2 E0, double *accu_out,
+                     void *v, void *r, void *p, void *pp, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!m_io || !accu_out || !v || !r || !p || !pp) return fail(QBGPU_ERR_ARG, "eigenvec_CG: null argument");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    NativeRun N;
+    QB_TRY(native_begin(N, A, cplx, v, 1, 0x1u, where, E0.y == 0.0));
+    DevBuf rest;                                            // r, p, pp of the loop (internal order)
+    QB_TRY(rest.alloc(N.vb_loop * n * 3));
+    char *w[4] = {(char *)N.work.p, (char *)rest.p, (char *)rest.p + N.vb_loop * n, (char *)rest.p + 2 * N.vb_loop * n};
+    QB_TRY(cg_impl(&N.R, N.loop_cplx, maxit, m_io, E0, accu_out, w[0], w[1], w[2], w[3], QBGPU_DEVICE));
+    void *outs[4] = {v, r, p, pp};
+    DevBuf tmp;                                             // host callers: one device vector in reference order at a time
+    if (where == QBGPU_HOST) QB_TRY(tmp.alloc(N.vb_api * n));
+    for (int j = 0; j < 4; j++) {
+        void *dst = where == QBGPU_HOST ? tmp.p : outs[j];
+        QB_TRY(vec_from_native(A, N.loop_cplx, cplx, w[j], dst, make_double2(1.0, 0.0), make_double2(0.0, 0.0)));
+        if (where == QBGPU_HOST) { QB_CUDA(cudaMemcpyAsync(outs[j], dst, N.vb_api * n, cudaMemcpyDeviceToHost, c.stream)); QB_CUDA(cudaStreamSynchronize(c.stream)); }
+    }
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+
+static int energy_scale_native(qbgpu_matrix *A, bool cplx, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!v || !lo || !hi || iters < 3) return fail(QBGPU_ERR_ARG, "energy_scale: bad argument");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    const int64_t mm = iters - 1;                          // src/kpm.cc:53
+    DevBuf dref;                                            // the reference draws its start vector itself (seed 1, src/kpm.cc:60)
+    char *ref = (char *)v;
+    if (where == QBGPU_HOST) { QB_TRY(dref.alloc(vb * n * 2)); ref = (char *)dref.p; }
+    else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    QB_TRY(vec_randomize(n, cplx, ref, 1));
+    NativeRun N;
+    QB_TRY(native_begin(N, A, cplx, ref, 2, 0x1u, QBGPU_DEVICE, true));
+    std::vector<double> hess(2 * iters, 0.0), ritz(mm);
+    int64_t m = 0;
+    QB_TRY(lanczos_impl(&N.R, N.loop_cplx, 0, mm, iters, &m, N.work.p, hess.data(), "dnmcs", QBGPU_DEVICE, /*stop_on_breakdown=*/false));
+    if (hess_eigen_host(hess.data(), iters, mm, ritz.data(), nullptr, nullptr)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+    const double l = ritz[0], h = ritz[mm - 1], slack = extend * (h - l);                          // :83-87
+    *lo = l - slack; *hi = h + slack;
+    QB_TRY(native_end(N, A, cplx, ref, 0x3u, 2, QBGPU_DEVICE));
+    if (where == QBGPU_HOST) { QB_CUDA(cudaMemcpyAsync(v, ref, vb * n * 2, cudaMemcpyDeviceToHost, c.stream)); QB_CUDA(cudaStreamSynchronize(c.stream)); }
+    return QBGPU_OK;
+}
+
+static int kpm_native(qbgpu_matrix *A, bool cplx, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
+{
+    QB_TRY(ensure_init());
+    QB_TRY(check_single(A, cplx));
+    if (!phi || !mu || nmom < 1 || !(hi > lo)) return fail(QBGPU_ERR_ARG, "kpm_moments: bad argument");
+    NativeRun N;
+    QB_TRY(native_begin(N, A, cplx, const_cast<void *>(phi), 1, 0x1u, where, true));
+    return kpm_impl(&N.R, N.loop_cplx, N.work.p, lo, hi, nmom, mu, QBGPU_DEVICE);
+}
+
 static int lanczos_dispatch(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
                             double *hess, const char *purpose, int where)
 {
+    if (A && A->perm) return lanczos_native(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);
     if (!A || !real_mode_enabled(A, cplx) || !v || !purpose || np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -465,6 +599,7 @@ static int lanczos_dispatch(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, i
 static int cg_dispatch(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, double2 E0, double *accu_out,
                        void *v, void *r, void *p, void *pp, int where)
 {
+    if (A && A->perm) return cg_native(A, cplx, maxit, m_io, E0, accu_out, v, r, p, pp, where);
     if (!A || !real_mode_enabled(A, cplx) || E0.y != 0.0 || !v || !r || !p || !pp) return cg_impl(A, cplx, maxit, m_io, E0, accu_out, v, r, p, pp, where);
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -501,6 +636,7 @@ static int cg_dispatch(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io,
 
 static int energy_scale_dispatch(qbgpu_matrix *A, bool cplx, void *v, double *lo, double *hi, double extend, int64_t iters, int where)
 {
+    if (A && A->perm) return energy_scale_native(A, cplx, v, lo, hi, extend, iters, where);
     if (!A || !real_mode_enabled(A, cplx) || !v) return energy_scale_impl(A, cplx, v, lo, hi, extend, iters, where);
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -521,6 +657,7 @@ static int energy_scale_dispatch(qbgpu_matrix *A, bool cplx, void *v, double *lo
 
 static int kpm_dispatch(qbgpu_matrix *A, bool cplx, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
 {
+    if (A && A->perm) return kpm_native(A, cplx, phi, lo, hi, nmom, mu, where);
     if (!A || !real_mode_enabled(A, cplx) || !phi) return kpm_impl(A, cplx, phi, lo, hi, nmom, mu, where);
     QB_TRY(ensure_init());
     Context &c = ctx();

@@ -465,8 +465,8 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
-    if (!A->borrowed) matfree_destroy(A);
-    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); }
+    if (!A->borrowed) { matfree_destroy(A); species_destroy(A); }
+    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); cudaFree(A->slice_order); }
     delete A;
     return QBGPU_OK;
 }
@@ -475,10 +475,10 @@ int qbgpu_matrix_get_info(qbgpu_matrix_t A, qbgpu_matrix_info *info)
 {
     if (!A || !info) return fail(QBGPU_ERR_ARG, "null argument");
     info->n = A->n; info->row_lo = A->row_lo; info->row_hi = A->row_hi;
-    info->nnz_stored = A->nnz; info->nnz_input = A->nnz_input;
+    info->nnz_stored = A->nnz + (A->second ? A->second->nnz : 0); info->nnz_input = A->nnz_input;
     info->val_is_real = A->val_real; info->value_dict = A->ndict; info->api_is_complex = A->api_complex;
     info->format = A->format; info->lanes = A->lanes;
-    info->device_bytes = A->mf ? matfree_bytes(A) : (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
+    info->device_bytes = A->sp ? species_bytes(A) : A->mf ? matfree_bytes(A) : (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
     info->upload_seconds = A->upload_s; info->convert_seconds = A->convert_s; info->autotune_seconds = A->autotune_s;
     return QBGPU_OK;
 }
@@ -487,6 +487,7 @@ int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, voi
 {
     QB_TRY(ensure_init());
     if (!A || !rowptr || !col || !val) return fail(QBGPU_ERR_ARG, "null argument");
+    QB_TRY(no_species(A, "download_expanded"));
     if (A->mf) return fail(QBGPU_ERR_STATE, "matrix-free handle: there are no stored entries to download");
     const bool jag = (A->format == QBGPU_FORMAT_SELL);      // hand back plain CSR order whatever the resident layout
     if (jag) QB_TRY(sjds_convert(A, false));
@@ -513,6 +514,7 @@ int qbgpu_to_dense(qbgpu_matrix_t A, void *dense)
     QB_TRY(ensure_init());
     if (!A || !dense) return fail(QBGPU_ERR_ARG, "null argument");
     if (A->row_lo != 0 || A->row_hi != A->n) return fail(QBGPU_ERR_STATE, "to_dense needs an unsharded handle");
+    QB_TRY(no_species(A, "to_dense"));
     const int64_t n = A->n;
     std::vector<int64_t> rp(n + 1);
     std::vector<int32_t> cc(A->nnz);
@@ -542,6 +544,7 @@ int qbgpu_real_view(qbgpu_matrix_t A, qbgpu_matrix_t *view)
 
 int qbgpu_split_columns(qbgpu_matrix_t A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts, int flags)
 {
+    QB_TRY(no_species(A, "split_columns"));
     return split_columns(A, nparts, col_bounds, parts, flags);
 }
 

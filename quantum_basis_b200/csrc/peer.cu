@@ -179,6 +179,7 @@ int qbgpu_peer_ring_status(int *timed_out)
 int qbgpu_ring_prepare(qbgpu_matrix_t A, int rank, int world, int64_t chunk, qbgpu_matrix_t *ring_view)
 {
     QB_TRY(ensure_init());
+    QB_TRY(no_species(A, "ring_prepare"));
     return ring_prepare(A, rank, world, chunk, ring_view);
 }
 

@@ -90,13 +90,16 @@ template <int XPOL> __device__ __forceinline__ double2 ld_x(const double2 *p, ui
 // MINB = __launch_bounds__ min blocks/SM: without it ptxas schedules for 32 registers (full occupancy) and chains
 // "load column, load value, gather, fma" one diagonal at a time -- a single dependent pair of loads in flight per
 // warp; with MINB <= 4 it batches the U column loads, the U value loads and the U gathers (checked in the SASS).
-template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false>
+// ORD = the slices are visited in the order given by `order` (the cross part of a species-order handle: tiles of down
+// indices, so that the gathered columns of a tile stay in L2) instead of ascending; a template parameter for the same
+// reason as KEEP.
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false, bool ORD = false>
 __global__ void __launch_bounds__(kSBlock, MINB)
 spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
                  const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                  int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
-                 int64_t far_rows, const double *__restrict__ vdict)
+                 int64_t far_rows, const double *__restrict__ vdict, const int32_t *__restrict__ order)
 {
     using VT = VecTraits<VecT>;
     constexpr bool kDict = sizeof(ValT) == 1;               // 1-byte codes into a <= 256-entry fp64 dictionary
@@ -122,7 +125,9 @@ spmv_sjds_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *
     // well (a run-time flag here cost 15-25 % on the unsplit product).
     double d[3] = {0.0, 0.0, 0.0};
 
-    for (int64_t s = (int64_t)blockIdx.x * WPB + warp; s < nslices; s += (int64_t)gridDim.x * WPB) {
+    for (int64_t it = (int64_t)blockIdx.x * WPB + warp; it < nslices; it += (int64_t)gridDim.x * WPB) {
+        int64_t s = it;
+        if constexpr (ORD) s = order[it];
         const uint32_t info = rowinfo[s * 32 + lane];
         const int len = (int)(info & kLenMask);
         const int64_t row = s * 32 + (info >> 24);
@@ -202,11 +207,11 @@ static int64_t g_far_rows = 1 << 21;                      // rows; ~32 MB of com
 void set_sjds_variant(int v) { g_sjds_variant = v; }
 void set_sjds_far_rows(int64_t r) { g_far_rows = r; }
 
-template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false>
+template <typename ValT, typename VecT, bool DOTS, int U, int SPOL, int XPOL, bool UL, int MINB, bool KEEP = false, bool ORD = false>
 static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
-    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS, U, SPOL, XPOL, UL, MINB, KEEP>;
+    auto kern = spmv_sjds_kernel<ValT, VecT, DOTS, U, SPOL, XPOL, UL, MINB, KEEP, ORD>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kSBlock, 0));
@@ -222,7 +227,7 @@ static int launch_sjds_variant(const qbgpu_matrix *A, const FusedArgs &a)
     const int grid = (int)(want < cap ? want : cap);
     kern<<<grid, kSBlock, 0, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                          (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
-                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, g_far_rows, A->vdict);
+                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket, g_far_rows, A->vdict, A->slice_order);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
@@ -269,6 +274,12 @@ static int launch_sjds_typed(const qbgpu_matrix *A, const FusedArgs &a)
     }
 #endif
     using P = Prod<VecT>;
+    if (A->slice_order) {                                   // cross part of a species-order handle: tile-ordered traversal
+        if (!dots && a.scal_mode == 0 && a.z == a.y && a.beta.x == 1.0 && a.beta.y == 0.0 && a.gamma.x == 0.0 && a.gamma.y == 0.0)
+            return launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB, true, true>(A, a);
+        return dots ? launch_sjds_variant<ValT, VecT, true, P::U, P::S, P::X, P::UL, P::DotsMinB, false, true>(A, a)
+                    : launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB, false, true>(A, a);
+    }
     // accumulating column block of a sharded product (y += H_p x, immediates only): skip the rows this block does not touch
     if (!dots && a.scal_mode == 0 && a.z == a.y && a.beta.x == 1.0 && a.beta.y == 0.0 && a.gamma.x == 0.0 && a.gamma.y == 0.0)
         return launch_sjds_variant<ValT, VecT, false, P::U, P::S, P::X, P::UL, P::MinB, true>(A, a);

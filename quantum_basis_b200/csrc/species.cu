@@ -1,0 +1,768 @@
+// quantum_basis_b200/csrc/species.cu -- "species order" for the single-orbital Fermi-Hubbard model (QBGPU_SPECIES_ORDER).
+//
+// Why: in the reference's Lin-table order (src/basis.cc:1144-1190) every hopping term of the 4x4 Hubbard matrix sends a
+// row far away in the index space -- 47 % of the off-diagonal entries lie more than 300 K rows from the diagonal -- so
+// the gathers of x cost about 50 GB of DRAM traffic per product where 2.65 GB would be compulsory.
+// No re-ordering of ONE pass over the rows removes that (profiles/r01_cache_sim_orders_and_tiles.txt).  Two passes do,
+// once the basis is indexed by the two spin species separately:
+//
+//     p = iu * D_dn + id ,   iu = rank of the up-occupancy word, id = rank of the down-occupancy word (ascending words)
+//
+//     H = [ U * (double occupancies) + hops of the DOWN electrons ]   "local" part: same iu, i.e. inside one contiguous
+//                                                                     block x[iu, :] of D_dn entries (206 KB for 4x4)
+//       + [ hops of the UP electrons ]                                "cross" part: same id, another iu
+//
+//   pass 1 (local part, rows ascending): every gather falls into the row's own block of x -> x is read once;
+//   pass 2 (cross part, y += ...): rows traversed by TILES of down indices (all iu for id in [tau W, tau W + W)), so the
+//          gathered columns x[iu', tile] of a whole tile (D_up * W entries: 26 MB for W = 128) stay in L2 -> x is read
+//          once more, y is read and written once more.
+//
+// Vector traffic 5 n S_vec instead of ~19 n S_vec; the matrix stream is unchanged.  Every matrix element factorises as
+// (amplitude and sign from the hopping species' own configuration) x (parity of the OTHER species on a site interval):
+// sign rule of the reference's oprXphi, src/basis.cc:2717-2731 (fermions ordered site-major, up before down on a site);
+// the factorisation is restated in tests/species_builders.py and checked there, entry for entry, against the
+// reference-pinned full-basis assembler.  Two kinds of handle share the tables:
+//   * stored (qbgpu_build_hubbard + QBGPU_SPECIES_ORDER): the two parts as sliced-jagged matrices, multiplied by the
+//     production kernel of sjds.cu (the cross part with its tile-ordered slice traversal);
+//   * matrix-free (qbgpu_create_matfree_hubbard + QBGPU_SPECIES_ORDER): nothing stored but the per-species hop tables
+//     (a few MB); the counterpart of model<T>::MultMv2 with matrix_free == true, src/model.cc:942-1109.
+// The reference-shaped entry points keep the reference's order at the boundary: vectors are permuted on the way in and
+// out (perm[r] = internal index of the reference's row r), fused with the real/complex conversion the Krylov drivers do
+// anyway.
+#include "internal.hpp"
+#include "lin_tables.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace qb {
+
+// the row functions are compiled for the host too, where g++ does not know the pragma
+#ifdef __CUDA_ARCH__
+#define QB_UNROLL _Pragma("unroll")
+#else
+#define QB_UNROLL
+#endif
+
+constexpr int kPBlock = 256;
+constexpr uint32_t kHopMask = 0xFFFFFFu;      // hop entry .y = interval mask (24 bits) | own sign << 24 | bond multiplicity << 25
+constexpr int kMaxWeight = 127;
+constexpr int kMaxDbl = 32;
+
+static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Device-resident tables of a species-order handle (owned through qbgpu_matrix::sp).
+struct Species {
+    int nsites = 0;
+    int64_t Du = 0, Dd = 0;
+    int64_t tot_u = 0, tot_d = 0;                 // hop-table entries of the two species
+    uint32_t *ulist = nullptr, *dlist = nullptr;  // occupancy words, ascending
+    int32_t *uptr = nullptr, *dptr = nullptr;     // [D + 1] offsets into the hop tables
+    uint2 *uhop = nullptr, *dhop = nullptr;       // (.x = target configuration index, .y = mask | sign | weight), sorted by target
+    double *ampw = nullptr;                       // [128] amplitude of a bond of multiplicity w: -t added w times (LIL accumulation)
+    double *diagk = nullptr;                      // [33]  U added k times
+    int tile = 128;                               // W: down indices per tile of the cross pass (multiple of 32)
+    bool matfree = false;
+    int64_t bytes = 0;
+};
+
+// Plain-pointer view of the tables (device pointers inside kernels, host pointers in the CPU-side debug entry): the
+// per-row functions below are __host__ __device__, so the index logic the kernels run is the logic the CPU tests check.
+struct SpeciesView {
+    int64_t Du, Dd, tot_u, tot_d;
+    const uint32_t *ulist, *dlist;
+    const int32_t *uptr, *dptr;
+    const uint2 *uhop, *dhop;
+};
+
+// value of a hop entry given the OTHER species' occupancy word
+__host__ __device__ __forceinline__ double hop_value(uint32_t meta, uint32_t other, const double *ampw)
+{
+    const double a = ampw[meta >> 25];
+    const int sg = (int)((meta >> 24) & 1u) ^ (popc_hd(other & (meta & kHopMask)) & 1);
+    return sg ? -a : a;
+}
+
+struct SpeciesHost {
+    std::vector<uint32_t> list[2];
+    std::vector<int32_t> ptr[2];
+    std::vector<uint2> hop[2];
+    std::vector<int32_t> rank;                    // rank of a word among the words with the same popcount
+    double ampw[kMaxWeight + 1];
+    double diagk[kMaxDbl + 1];
+};
+
+// The hop tables, with the formulas of tests/species_builders.py: for the hop f -> t of a species on the word `w`
+//   own sign = parity( popc(w & below_f) + popc(w & below_t) + [f < t] )
+//   the other species flips the sign by the parity of its electrons on   [min, max)  (up hop)   or   (min, max]  (down hop).
+static int build_host_tables(int nsites, int nup, int ndn, const ModelParams &M, SpeciesHost &H)
+{
+    if (nsites < 2 || nsites > 24) return fail(QBGPU_ERR_ARG, "species order: between 2 and 24 sites");
+    const uint32_t nw = 1u << nsites;
+    H.rank.assign(nw, 0);
+    std::vector<int32_t> cnt(nsites + 1, 0);
+    for (uint32_t w = 0; w < nw; w++) H.rank[w] = cnt[__builtin_popcount(w)]++;
+    const int nel[2] = {nup, ndn};
+    for (int b = 0; b < M.nbonds; b++)
+        if (M.bonds[b].w > kMaxWeight) return fail(QBGPU_ERR_ARG, "species order: a bond is repeated more than 127 times");
+    for (int sp = 0; sp < 2; sp++) {
+        H.list[sp].clear();
+        H.list[sp].reserve(cnt[nel[sp]]);
+        for (uint32_t w = 0; w < nw; w++) if (__builtin_popcount(w) == nel[sp]) H.list[sp].push_back(w);
+        const size_t D = H.list[sp].size();
+        H.ptr[sp].assign(D + 1, 0);
+        H.hop[sp].clear();
+        std::vector<uint2> row;
+        for (size_t c = 0; c < D; c++) {
+            const uint32_t word = H.list[sp][c];
+            row.clear();
+            for (int b = 0; b < M.nbonds; b++) {
+                for (int dir = 0; dir < 2; dir++) {
+                    const int f = dir ? M.bonds[b].j : M.bonds[b].i, t = dir ? M.bonds[b].i : M.bonds[b].j;
+                    if (!((word >> f) & 1u) || ((word >> t) & 1u)) continue;
+                    const uint32_t below_f = (1u << f) - 1u, below_t = (1u << t) - 1u;
+                    const uint32_t own = (uint32_t)(__builtin_popcount(word & below_f) + __builtin_popcount(word & below_t) + (f < t ? 1 : 0)) & 1u;
+                    const uint32_t mask = sp == 0 ? (below_f ^ below_t) : (((2u << f) - 1u) ^ ((2u << t) - 1u));
+                    const uint32_t nword = word ^ (1u << f) ^ (1u << t);
+                    uint2 e;
+                    e.x = (uint32_t)H.rank[nword];
+                    e.y = (mask & kHopMask) | (own << 24) | ((uint32_t)M.bonds[b].w << 25);
+                    row.push_back(e);
+                }
+            }
+            std::sort(row.begin(), row.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+            if (H.hop[sp].size() + row.size() > 2147483647ull) return fail(QBGPU_ERR_ARG, "species order: hop table exceeds the int32 range");
+            H.hop[sp].insert(H.hop[sp].end(), row.begin(), row.end());
+            H.ptr[sp][c + 1] = (int32_t)H.hop[sp].size();
+        }
+    }
+    for (int w = 0; w <= kMaxWeight; w++) { double a = 0.0; for (int r = 0; r < w; r++) a += -M.t; H.ampw[w] = a; }
+    for (int k = 0; k <= kMaxDbl; k++) { double d = 0.0; for (int r = 0; r < k; r++) d += M.U; H.diagk[k] = d; }
+    return QBGPU_OK;
+}
+
+static void species_free(Species *S)
+{
+    if (!S) return;
+    cudaFree(S->ulist); cudaFree(S->dlist); cudaFree(S->uptr); cudaFree(S->dptr); cudaFree(S->uhop); cudaFree(S->dhop);
+    cudaFree(S->ampw); cudaFree(S->diagk);
+    delete S;
+}
+
+static SpeciesView view_of(const Species *S)
+{
+    SpeciesView V;
+    V.Du = S->Du; V.Dd = S->Dd; V.tot_u = S->tot_u; V.tot_d = S->tot_d;
+    V.ulist = S->ulist; V.dlist = S->dlist; V.uptr = S->uptr; V.dptr = S->dptr; V.uhop = S->uhop; V.dhop = S->dhop;
+    return V;
+}
+
+template <typename T>
+static cudaError_t upload(T **dst, const T *src, size_t count, cudaStream_t st)
+{
+    cudaError_t e = cudaMalloc(dst, sizeof(T) * (count ? count : 1));
+    if (e != cudaSuccess) return e;
+    if (count) e = cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+// Common part of both handle kinds: tables in HBM, the permutation, and a bare handle that owns them.
+static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelParams &M, int api_complex, SpeciesHost &H)
+{
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    *out = nullptr;
+    if (T.bps != 2 || M.kind != 1) return fail(QBGPU_ERR_ARG, "species order: only the single-orbital Hubbard model has two species");
+    QB_TRY(build_host_tables(T.nsites, T.t0, T.t1, M, H));
+    const int64_t Du = (int64_t)H.list[0].size(), Dd = (int64_t)H.list[1].size();
+    if (Du <= 0 || Dd <= 0) return fail(QBGPU_ERR_ARG, "species order: empty sector");
+    if (Du > 2147483647LL / Dd) return fail(QBGPU_ERR_ARG, "species order: dimension exceeds the int32 column range");
+    if (Du * Dd != T.dim) return fail(QBGPU_ERR_STATE, "species order: dimension mismatch with the Lin tables");
+    auto *A = new qbgpu_matrix;
+    auto *S = new Species;
+    A->sp = S;
+    A->n = T.dim; A->row_lo = 0; A->row_hi = T.dim; A->api_complex = api_complex != 0; A->val_real = true;
+    S->nsites = T.nsites; S->Du = Du; S->Dd = Dd; S->tot_u = (int64_t)H.hop[0].size(); S->tot_d = (int64_t)H.hop[1].size();
+    int W = 128;
+    if (const char *e = getenv("QBGPU_SPECIES_TILE")) W = atoi(e);
+    if (W < 32) W = 32;
+    W = (W + 31) / 32 * 32;
+    S->tile = W;
+    int32_t *d_rank = nullptr;
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaFree(d_rank); qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(upload(&S->ulist, H.list[0].data(), H.list[0].size(), c.stream));
+    QB_CU(upload(&S->dlist, H.list[1].data(), H.list[1].size(), c.stream));
+    QB_CU(upload(&S->uptr, H.ptr[0].data(), H.ptr[0].size(), c.stream));
+    QB_CU(upload(&S->dptr, H.ptr[1].data(), H.ptr[1].size(), c.stream));
+    QB_CU(upload(&S->uhop, H.hop[0].data(), H.hop[0].size(), c.stream));
+    QB_CU(upload(&S->dhop, H.hop[1].data(), H.hop[1].size(), c.stream));
+    QB_CU(upload(&S->ampw, H.ampw, (size_t)kMaxWeight + 1, c.stream));
+    QB_CU(upload(&S->diagk, H.diagk, (size_t)kMaxDbl + 1, c.stream));
+    QB_CU(upload(&d_rank, H.rank.data(), H.rank.size(), c.stream));
+    QB_CU(cudaMalloc(&A->perm, sizeof(int32_t) * (size_t)T.dim));
+    { int rc = species_perm_build(T, d_rank, Dd, A->perm); if (rc) { cudaFree(d_rank); qbgpu_destroy(A); return rc; } }
+    QB_CU(cudaStreamSynchronize(c.stream));
+    cudaFree(d_rank); d_rank = nullptr;
+#undef QB_CU
+    S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + 4 * T.dim);
+    *out = A;
+    return QBGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- stored parts (generator)
+// Row offsets are closed-form:  local part  len(iu,id) = 1 + #down hops(id)   ->  iu * (tot_d + Dd) + dptr[id] + id
+//                               cross part  len(iu,id) = #up hops(iu)         ->  Dd * uptr[iu] + id * len
+__host__ __device__ __forceinline__ void species_rowptr_at(const SpeciesView &V, int64_t n, int64_t p, int64_t &rl, int64_t &rc)
+{
+    const int64_t iu = p / V.Dd, id = p - iu * V.Dd;        // p == n: iu = Du, id = 0 -> the totals
+    rl = iu * (V.tot_d + V.Dd) + (int64_t)V.dptr[id] + id;
+    const int64_t u0 = V.uptr[iu];
+    const int64_t len = p < n ? (int64_t)V.uptr[iu + 1] - u0 : 0;
+    rc = V.Dd * u0 + id * len;
+}
+
+__global__ void __launch_bounds__(kPBlock) species_rowptr_kernel(SpeciesView V, int64_t n, int64_t *rp_local, int64_t *rp_cross)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += (int64_t)gridDim.x * blockDim.x)
+        species_rowptr_at(V, n, p, rp_local[p], rp_cross[p]);
+}
+
+template <typename ValT> __host__ __device__ __forceinline__ void put_entry(int32_t *col, ValT *val, int64_t at, int32_t c, double v)
+{
+    col[at] = c;
+    if constexpr (sizeof(ValT) == 16) val[at] = make_double2(v, 0.0); else val[at] = v;
+}
+
+// both parts of row p, columns ascending
+template <typename ValT>
+__host__ __device__ __forceinline__ void species_fill_row(const SpeciesView &V, const double *ampw, const double *diagk, int64_t p,
+                                                          int32_t *col_l, ValT *val_l, int32_t *col_c, ValT *val_c)
+{
+    const int64_t iu = p / V.Dd, id = p - iu * V.Dd;
+    const uint32_t U = V.ulist[iu], D = V.dlist[id];
+    // local part: down hops sorted by target, the diagonal (always stored, src/sparse.cc:44-54) at its sorted position
+    int64_t at = iu * (V.tot_d + V.Dd) + (int64_t)V.dptr[id] + id;
+    bool diag_done = false;
+    for (int e = V.dptr[id]; e < V.dptr[id + 1]; e++) {
+        const uint2 h = V.dhop[e];
+        if (!diag_done && (int64_t)h.x > id) { put_entry(col_l, val_l, at++, (int32_t)p, diagk[popc_hd(U & D)]); diag_done = true; }
+        put_entry(col_l, val_l, at++, (int32_t)(iu * V.Dd + (int64_t)h.x), hop_value(h.y, U, ampw));
+    }
+    if (!diag_done) put_entry(col_l, val_l, at++, (int32_t)p, diagk[popc_hd(U & D)]);
+    // cross part: up hops, sorted by target
+    const int64_t u0 = V.uptr[iu], len = (int64_t)V.uptr[iu + 1] - u0;
+    at = V.Dd * u0 + id * len;
+    for (int64_t e = u0; e < u0 + len; e++) {
+        const uint2 h = V.uhop[e];
+        put_entry(col_c, val_c, at++, (int32_t)((int64_t)h.x * V.Dd + id), hop_value(h.y, D, ampw));
+    }
+}
+
+template <typename ValT>
+__global__ void __launch_bounds__(kPBlock) species_fill_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+                                                               int32_t *col_l, ValT *val_l, int32_t *col_c, ValT *val_c)
+{
+    __shared__ double ampw[kMaxWeight + 1], diagk[kMaxDbl + 1];
+    for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
+    for (int k = threadIdx.x; k <= kMaxDbl; k += blockDim.x) diagk[k] = diagk_g[k];
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        species_fill_row<ValT>(V, ampw, diagk, p, col_l, val_l, col_c, val_c);
+}
+
+static int grid_rows(int64_t n) { int64_t g = (n + kPBlock - 1) / kPBlock; if (g < 1) g = 1; if (g > 148 * 32) g = 148 * 32; return (int)g; }
+
+// traversal order of the cross part's 32-row slices: by (tile of the slice's first down index, slice index)
+static void make_slice_order(int64_t n, int64_t Dd, int W, std::vector<int32_t> &order)
+{
+    const int64_t ns = (n + 31) / 32;
+    const int64_t ntile = (Dd + W - 1) / W;
+    std::vector<int64_t> start(ntile + 1, 0);
+    for (int64_t s = 0; s < ns; s++) start[((s * 32) % Dd) / W + 1]++;
+    for (int64_t t = 0; t < ntile; t++) start[t + 1] += start[t];
+    order.assign(ns, 0);
+    for (int64_t s = 0; s < ns; s++) order[start[((s * 32) % Dd) / W]++] = (int32_t)s;
+}
+
+int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags)
+{
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    const double t0 = wall_s();
+    SpeciesHost H;
+    qbgpu_matrix *A = nullptr;
+    QB_TRY(species_common(&A, T, M, api_complex, H));
+    Context &c = ctx();
+    Species *S = (Species *)A->sp;
+    const int64_t n = A->n, Dd = S->Dd, Du = S->Du;
+    auto *C = new qbgpu_matrix;                             // the cross part
+    A->second = C;
+    C->n = n; C->row_lo = 0; C->row_hi = n; C->api_complex = A->api_complex;
+    A->val_real = C->val_real = !(flags & QBGPU_KEEP_COMPLEX) || !api_complex;
+    A->nnz = Du * (S->tot_d + Dd);
+    C->nnz = Dd * S->tot_u;
+    A->nnz_input = (A->nnz + C->nnz + n) / 2;               // what the reference would store: upper triangle incl. the diagonal
+    C->nnz_input = C->nnz;
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (n + 1)));
+    QB_CU(cudaMalloc(&C->rowptr, sizeof(int64_t) * (n + 1)));
+    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(A->nnz ? A->nnz : 1)));
+    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (size_t)(A->nnz ? A->nnz : 1)));
+    QB_CU(cudaMalloc(&C->col, sizeof(int32_t) * (size_t)(C->nnz ? C->nnz : 1)));
+    QB_CU(cudaMalloc(&C->val, C->val_bytes() * (size_t)(C->nnz ? C->nnz : 1)));
+    const SpeciesView V = view_of(S);
+    species_rowptr_kernel<<<grid_rows(n + 1), kPBlock, 0, c.stream>>>(V, n, A->rowptr, C->rowptr);
+    QB_LAUNCH_COUNT();
+    if (A->val_real)
+        species_fill_kernel<double><<<grid_rows(n), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, A->col, (double *)A->val, C->col, (double *)C->val);
+    else
+        species_fill_kernel<double2><<<grid_rows(n), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, A->col, (double2 *)A->val, C->col, (double2 *)C->val);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+    // layout: always the sliced-jagged kernels (the traversal order of the cross part exists only there)
+    if ((flags & QBGPU_VALUE_DICT) || getenv("QBGPU_VALUE_DICT")) {
+        int rc = value_dict_encode(A);
+        if (rc == QBGPU_OK) rc = value_dict_encode(C);
+        if (rc) { qbgpu_destroy(A); return rc; }
+    }
+    { int rc = sjds_convert(A, true); if (rc == QBGPU_OK) rc = sjds_convert(C, true); if (rc) { qbgpu_destroy(A); return rc; } }
+    std::vector<int32_t> order;
+    make_slice_order(n, Dd, S->tile, order);
+    QB_CU(upload(&C->slice_order, order.data(), order.size(), c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+#undef QB_CU
+    S->matfree = false;
+    A->convert_s = wall_s() - t0;
+    *out = A;
+    return QBGPU_OK;
+}
+
+int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags)
+{
+    (void)flags;
+    if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    const double t0 = wall_s();
+    SpeciesHost H;
+    qbgpu_matrix *A = nullptr;
+    QB_TRY(species_common(&A, T, M, api_complex, H));
+    Species *S = (Species *)A->sp;
+    S->matfree = true;
+    A->format = QBGPU_FORMAT_MATFREE;
+    A->nnz = 0; A->nnz_input = 0;
+    A->convert_s = wall_s() - t0;
+    *out = A;
+    return QBGPU_OK;
+}
+
+void species_destroy(qbgpu_matrix *A)
+{
+    if (!A || !A->sp) return;
+    species_free((Species *)A->sp);
+    A->sp = nullptr;
+    cudaFree(A->perm); A->perm = nullptr;
+    cudaFree(A->perm_x); cudaFree(A->perm_y); A->perm_x = A->perm_y = nullptr;
+    if (A->second) { qbgpu_destroy(A->second); A->second = nullptr; }
+}
+
+int64_t species_bytes(const qbgpu_matrix *A)
+{
+    const Species *S = (const Species *)A->sp;
+    int64_t b = S ? S->bytes : 0;
+    if (A->second) {
+        const int64_t ns = (A->n + 31) / 32;
+        b += A->nnz * (int64_t)(4 + A->val_bytes()) + A->second->nnz * (int64_t)(4 + A->second->val_bytes());
+        b += 2 * 8 * (A->n + 1) + 2 * 4 * ns * 32 + 4 * ns;        // two rowptr, two rowinfo, the slice order
+    }
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------ matrix-free product
+// pass 1: y = alpha * (diagonal + down hops) x + gamma x + beta z.  One thread per row, rows ascending: the gathers of a
+// row fall into its own block x[iu, :].  Four hop entries per trip: their table loads, then their gathers, are issued
+// together; past the end of the list the trip replays "0 * x[own row]".
+template <typename VecT>
+__host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, const double *ampw, const double *diagk, int64_t p, const VecT *x, VecT xi)
+{
+    using VT = VecTraits<VecT>;
+    const int64_t iu = p / V.Dd;
+    const int32_t id = (int32_t)(p - iu * V.Dd);
+    const uint32_t U = ld_ro(V.ulist + iu), D = ld_ro(V.dlist + id);
+    const VecT *xb = x + iu * V.Dd;
+    VecT acc = VT::zero();
+    mac(acc, diagk[popc_hd(U & D)], xi);
+    const int e1 = ld_ro(V.dptr + id + 1);
+    for (int e = ld_ro(V.dptr + id); e < e1; e += 4) {
+        uint2 h[4];
+        VecT xv[4];
+QB_UNROLL
+        for (int u = 0; u < 4; u++) h[u] = (e + u < e1) ? ld_ro(V.dhop + e + u) : make_uint2((uint32_t)id, 0u);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) xv[u] = ld_ro(xb + h[u].x);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
+    }
+    return acc;
+}
+
+template <typename VecT>
+__global__ void __launch_bounds__(kPBlock, 4)
+kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+                  const VecT *__restrict__ x, const VecT *z, VecT *y,
+                  double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
+{
+    using VT = VecTraits<VecT>;
+    __shared__ double ampw[kMaxWeight + 1], diagk[kMaxDbl + 1];
+    for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
+    for (int k = threadIdx.x; k <= kMaxDbl; k += blockDim.x) diagk[k] = diagk_g[k];
+    __syncthreads();
+    if (scal_mode != 0) {                                   // Lanczos step a, like the stored kernels (spmv.cu)
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+    }
+    const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const VecT xi = ld_ro(x + p);
+        const VecT acc = kron_local_acc<VecT>(V, ampw, diagk, p, x, xi);
+        VecT out = VT::scale(alpha, acc);
+        if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
+        if (use_beta) out = VT::add(out, VT::scale(beta, z[p]));
+        y[p] = out;
+    }
+}
+
+// pass 2: y += alpha * (up hops) x, with the running dots of the finished y.  One warp per 32 consecutive down indices
+// of one up configuration; the hop list is warp-uniform (broadcast loads) and every gather is a contiguous 32-entry
+// segment x[iu', id .. id+31].  Items are enumerated tile by tile (all iu for the down indices of one tile), so the
+// columns a tile gathers stay in L2.
+struct CrossItems {
+    int64_t nitems, full_items, per_tile;   // per_tile = Du * cpt warp items in every tile but the last
+    int W, cpt, cpt_last, ntile;            // tile width, 32-wide chunks per tile row (last tile: cpt_last)
+};
+
+__host__ __device__ __forceinline__ CrossItems cross_items(int64_t Du, int64_t Dd, int W)
+{
+    CrossItems I;
+    I.W = W; I.cpt = W / 32;
+    I.ntile = (int)((Dd + W - 1) / W);
+    const int64_t w_last = Dd - (int64_t)(I.ntile - 1) * W;
+    I.cpt_last = (int)((w_last + 31) / 32);
+    I.per_tile = Du * I.cpt;
+    I.full_items = (int64_t)(I.ntile - 1) * I.per_tile;
+    I.nitems = I.full_items + Du * I.cpt_last;
+    return I;
+}
+
+// warp item `it`, lane -> (iu, id); id may be >= Dd in the last chunk of a tile row (idle lane)
+__host__ __device__ __forceinline__ void cross_item_at(const CrossItems &I, int64_t it, int lane, int64_t &iu, int64_t &id)
+{
+    int64_t tau, ch;
+    if (it < I.full_items) { tau = it / I.per_tile; const int64_t rem = it - tau * I.per_tile; iu = rem / I.cpt; ch = rem - iu * I.cpt; }
+    else { const int64_t k2 = it - I.full_items; tau = I.ntile - 1; iu = k2 / I.cpt_last; ch = k2 - iu * I.cpt_last; }
+    id = tau * I.W + ch * 32 + lane;
+}
+
+template <typename VecT>
+__host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, const double *ampw, int64_t iu, int64_t idc, const VecT *x)
+{
+    using VT = VecTraits<VecT>;
+    const uint32_t D = ld_ro(V.dlist + idc);
+    const int e1 = ld_ro(V.uptr + iu + 1);
+    VecT acc = VT::zero();
+    for (int e = ld_ro(V.uptr + iu); e < e1; e += 4) {
+        uint2 h[4];
+        VecT xv[4];
+QB_UNROLL
+        for (int u = 0; u < 4; u++) h[u] = (e + u < e1) ? ld_ro(V.uhop + e + u) : make_uint2((uint32_t)iu, 0u);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, D, ampw), xv[u]);
+    }
+    return acc;
+}
+
+template <typename VecT, bool DOTS>
+__global__ void __launch_bounds__(kPBlock, 4)
+kron_cross_kernel(SpeciesView V, CrossItems I, const double *__restrict__ ampw_g, const VecT *__restrict__ x, VecT *y, double2 alpha, int scal_mode,
+                  const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+{
+    using VT = VecTraits<VecT>;
+    __shared__ double ampw[kMaxWeight + 1];
+    for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
+    __syncthreads();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) { alpha = make_double2(sc[0], 0.0); dot_scale = sc[0]; }
+    constexpr int WPB = kPBlock / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int64_t it = (int64_t)blockIdx.x * WPB + warp; it < I.nitems; it += (int64_t)gridDim.x * WPB) {
+        int64_t iu, id;
+        cross_item_at(I, it, lane, iu, id);
+        const bool live = id < V.Dd;
+        const int64_t idc = live ? id : V.Dd - 1;           // idle lanes of the last chunk replay a valid column
+        const VecT acc = kron_cross_acc<VecT>(V, ampw, iu, idc, x);
+        if (live) {
+            const int64_t p = iu * V.Dd + id;
+            const VecT out = VT::add(y[p], VT::scale(alpha, acc));
+            y[p] = out;
+            if (DOTS) {
+                const double2 q = VT::conj_mul(ld_ro(x + p), out);
+                d[0] += q.x; d[1] += q.y; d[2] += VT::abs2(out);
+            }
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kPBlock>(d, partials, ticket, dots_out);
+    }
+}
+
+template <typename VecT>
+static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    Context &c = ctx();
+    const Species *S = (const Species *)A->sp;
+    const int64_t n = A->n;
+    if (n == 0) return QBGPU_OK;
+    const SpeciesView V = view_of(S);
+    {
+        auto kern = kron_local_kernel<VecT>;
+        static int bps = 0;
+        if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
+        const int64_t want = (n + kPBlock - 1) / kPBlock, cap = (int64_t)c.num_sms * bps;
+        kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                                                        a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+    }
+    const CrossItems I = cross_items(S->Du, S->Dd, S->tile);
+    const int64_t want = (I.nitems + (kPBlock / 32) - 1) / (kPBlock / 32);
+    auto launch2 = [&](auto kern, int &bps) -> int {
+        if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
+        int64_t cap = (int64_t)c.num_sms * bps;
+        if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+        kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, I, S->ampw, (const VecT *)a.x, (VecT *)a.y, a.alpha, a.scal_mode, a.sc,
+                                                                        a.dots, c.partials, c.ticket);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+        return QBGPU_OK;
+    };
+    static int bps_dots = 0, bps_plain = 0;
+    if (a.dots) return launch2(kron_cross_kernel<VecT, true>, bps_dots);
+    return launch2(kron_cross_kernel<VecT, false>, bps_plain);
+}
+
+// Both handle kinds: pass 1 carries the caller's epilogue (alpha, gamma, beta*z) without the dots, pass 2 accumulates
+// into the same y and carries the dots -- exactly the first / later column blocks of a sharded product (spmv.cu).
+int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    const Species *S = (const Species *)A->sp;
+    if (!S) return fail(QBGPU_ERR_STATE, "not a species-order handle");
+    if (S->matfree) return A->api_complex ? launch_kron<double2>(A, a) : launch_kron<double>(A, a);
+    if (!A->second) return fail(QBGPU_ERR_STATE, "species-order handle without its cross part");
+    qbgpu_matrix L = *A;                                    // plain views: the production kernels see two ordinary matrices
+    L.sp = nullptr; L.second = nullptr; L.perm = nullptr;
+    FusedArgs a1 = a;
+    a1.dots = nullptr;
+    QB_TRY(launch_spmv(&L, a1));
+    qbgpu_matrix C = *A->second;
+    C.api_complex = A->api_complex;                        // a real view of the handle (fp64 vectors) covers both parts
+    FusedArgs a2;
+    a2.x = a.x; a2.y = a.y; a2.z = a.y; a2.dots = a.dots;
+    a2.beta = make_double2(1.0, 0.0);
+    if (a.scal_mode != 0) { a2.scal_mode = 2; a2.sc = a.sc; }
+    else a2.alpha = a.alpha;
+    return launch_spmv(&C, a2);
+}
+
+// --------------------------------------------------------------------------------------- order of the vectors
+template <typename DstT, typename SrcT> __device__ __forceinline__ DstT cvt(SrcT v);
+template <> __device__ __forceinline__ double cvt<double, double>(double v) { return v; }
+template <> __device__ __forceinline__ double2 cvt<double2, double>(double v) { return make_double2(v, 0.0); }
+template <> __device__ __forceinline__ double cvt<double, double2>(double2 v) { return v.x; }
+template <> __device__ __forceinline__ double2 cvt<double2, double2>(double2 v) { return v; }
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(kPBlock) to_native_kernel(int64_t n, const int32_t *__restrict__ perm, const SrcT *__restrict__ src, DstT *dst)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        dst[perm[r]] = cvt<DstT, SrcT>(src[r]);
+}
+
+template <typename SrcT, typename DstT, bool ACC>
+__global__ void __launch_bounds__(kPBlock) from_native_kernel(int64_t n, const int32_t *__restrict__ perm, const SrcT *__restrict__ src, DstT *dst,
+                                                              double2 a, double2 b)
+{
+    using VT = VecTraits<DstT>;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        DstT v = VT::scale(a, cvt<DstT, SrcT>(src[perm[r]]));
+        if (ACC) v = VT::add(v, VT::scale(b, dst[r]));
+        dst[r] = v;
+    }
+}
+
+int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst)
+{
+    if (!A || !A->perm) return fail(QBGPU_ERR_STATE, "vec_to_native: the handle has no internal order");
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const int g = grid_rows(n);
+    if (src_cplx && dst_cplx) to_native_kernel<double2, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double2 *)src, (double2 *)dst);
+    else if (src_cplx) to_native_kernel<double2, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double2 *)src, (double *)dst);
+    else if (dst_cplx) to_native_kernel<double, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double *)src, (double2 *)dst);
+    else to_native_kernel<double, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double *)src, (double *)dst);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+template <typename SrcT, typename DstT>
+static int from_native_typed(const qbgpu_matrix *A, const void *src, void *dst, double2 a, double2 b)
+{
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const int g = grid_rows(n);
+    if (b.x != 0.0 || b.y != 0.0) from_native_kernel<SrcT, DstT, true><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const SrcT *)src, (DstT *)dst, a, b);
+    else from_native_kernel<SrcT, DstT, false><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const SrcT *)src, (DstT *)dst, a, b);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+int vec_from_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst, double2 a, double2 b)
+{
+    if (!A || !A->perm) return fail(QBGPU_ERR_STATE, "vec_from_native: the handle has no internal order");
+    if (src_cplx && dst_cplx) return from_native_typed<double2, double2>(A, src, dst, a, b);
+    if (src_cplx) return from_native_typed<double2, double>(A, src, dst, a, b);
+    if (dst_cplx) return from_native_typed<double, double2>(A, src, dst, a, b);
+    return from_native_typed<double, double>(A, src, dst, a, b);
+}
+
+// y = alpha * H x + beta * y with the vectors in the REFERENCE's order (qbgpu_{d,z}mv): permute in, two passes, permute
+// out (the scaling and the beta*y term ride in the way out).
+int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void *y, int where)
+{
+    Context &c = ctx();
+    const bool cplx = A->api_complex;
+    const size_t vb = cplx ? 16 : 8;
+    const size_t bytes = vb * (size_t)A->n;
+    if (A->borrowed) return fail(QBGPU_ERR_STATE, "mv on a view of a species-order handle: use the owning handle");
+    if (!A->perm_x) QB_CUDA(cudaMalloc(&A->perm_x, bytes));
+    if (!A->perm_y) QB_CUDA(cudaMalloc(&A->perm_y, bytes));
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    const void *xd = x;
+    void *yd = y;
+    if (where == QBGPU_HOST) {
+        if (c.stage_x_bytes < bytes) { if (c.stage_x) QB_CUDA(cudaFree(c.stage_x)); c.stage_x = nullptr; c.stage_x_bytes = 0; QB_CUDA(cudaMalloc(&c.stage_x, bytes)); c.stage_x_bytes = bytes; }
+        if (c.stage_y_bytes < bytes) { if (c.stage_y) QB_CUDA(cudaFree(c.stage_y)); c.stage_y = nullptr; c.stage_y_bytes = 0; QB_CUDA(cudaMalloc(&c.stage_y, bytes)); c.stage_y_bytes = bytes; }
+        QB_CUDA(cudaMemcpyAsync(c.stage_x, x, bytes, cudaMemcpyHostToDevice, c.stream));
+        if (use_beta) QB_CUDA(cudaMemcpyAsync(c.stage_y, y, bytes, cudaMemcpyHostToDevice, c.stream));
+        xd = c.stage_x; yd = c.stage_y;
+    } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    QB_TRY(vec_to_native(A, cplx, cplx, xd, A->perm_x));
+    FusedArgs fa;
+    fa.x = A->perm_x; fa.y = A->perm_y;
+    QB_TRY(launch_spmv(A, fa));
+    QB_TRY(vec_from_native(A, cplx, cplx, A->perm_y, yd, alpha, beta));
+    if (where == QBGPU_HOST) {
+        QB_CUDA(cudaMemcpyAsync(y, yd, bytes, cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return QBGPU_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qbgpu_native_order(qbgpu_matrix_t A, int *has_internal_order)
+{
+    if (!A || !has_internal_order) return fail(QBGPU_ERR_ARG, "null argument");
+    *has_internal_order = A->perm ? 1 : 0;
+    return QBGPU_OK;
+}
+
+int qbgpu_vec_to_native(qbgpu_matrix_t A, const void *x_ref_dev, void *x_native_dev)
+{
+    QB_TRY(ensure_init());
+    if (!A || !x_ref_dev || !x_native_dev) return fail(QBGPU_ERR_ARG, "null argument");
+    if (x_ref_dev == x_native_dev) return fail(QBGPU_ERR_ARG, "vec_to_native works out of place");
+    return vec_to_native(A, A->api_complex, A->api_complex, x_ref_dev, x_native_dev);
+}
+
+int qbgpu_vec_from_native(qbgpu_matrix_t A, const void *x_native_dev, void *x_ref_dev)
+{
+    QB_TRY(ensure_init());
+    if (!A || !x_ref_dev || !x_native_dev) return fail(QBGPU_ERR_ARG, "null argument");
+    if (x_ref_dev == x_native_dev) return fail(QBGPU_ERR_ARG, "vec_from_native works out of place");
+    return vec_from_native(A, A->api_complex, A->api_complex, x_native_dev, x_ref_dev, make_double2(1.0, 0.0), make_double2(0.0, 0.0));
+}
+
+/* CPU-side execution of the species-order index logic: the SAME __host__ __device__ row functions the kernels call, on host
+ * arrays, with no device involved (tests/test_species_cpu.py compares the results with the reference-pinned numpy
+ * restatement).  sizes[4] = {Du, Dd, up-hop entries, down-hop entries}; every other pointer may be NULL (skipped):
+ *   perm[n]; the two stored parts as CSR (rowptr[n+1], col, val: nnz_local = Du*(tot_d+Dd), nnz_cross = Dd*tot_u);
+ *   slice_order[ceil(n/32)]; y[n] = H x through the two matrix-free passes with x, y in the internal order; the warp items
+ *   of the cross pass visited in the kernel's order, touched[p] counting how often row p was written (must end as all 1). */
+int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U, int tile,
+                             int64_t *sizes, int32_t *perm, int64_t *rp_local, int32_t *col_local, double *val_local,
+                             int64_t *rp_cross, int32_t *col_cross, double *val_cross, int32_t *slice_order,
+                             const double *x, double *y, int32_t *touched)
+{
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || nbonds < 1 || !bonds || !sizes) return fail(QBGPU_ERR_ARG, "debug_species_host: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 2, nup, ndn, T));
+    static thread_local ModelParams M;
+    M.kind = 1; M.J = 0; M.t = t; M.U = U;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    SpeciesHost H;
+    QB_TRY(build_host_tables(nsites, nup, ndn, M, H));
+    SpeciesView V;
+    V.Du = (int64_t)H.list[0].size(); V.Dd = (int64_t)H.list[1].size(); V.tot_u = (int64_t)H.hop[0].size(); V.tot_d = (int64_t)H.hop[1].size();
+    V.ulist = H.list[0].data(); V.dlist = H.list[1].data(); V.uptr = H.ptr[0].data(); V.dptr = H.ptr[1].data();
+    V.uhop = H.hop[0].data(); V.dhop = H.hop[1].data();
+    sizes[0] = V.Du; sizes[1] = V.Dd; sizes[2] = V.tot_u; sizes[3] = V.tot_d;
+    const int64_t n = V.Du * V.Dd;
+    if (n != T.dim) return fail(QBGPU_ERR_STATE, "debug_species_host: dimension mismatch with the Lin tables");
+    int W = tile < 32 ? 32 : (tile + 31) / 32 * 32;
+    if (perm) species_perm_host(T, H.rank.data(), V.Dd, perm);
+    if (rp_local && rp_cross) for (int64_t p = 0; p <= n; p++) species_rowptr_at(V, n, p, rp_local[p], rp_cross[p]);
+    if (col_local && val_local && col_cross && val_cross)
+        for (int64_t p = 0; p < n; p++) species_fill_row<double>(V, H.ampw, H.diagk, p, col_local, val_local, col_cross, val_cross);
+    if (slice_order) { std::vector<int32_t> o; make_slice_order(n, V.Dd, W, o); memcpy(slice_order, o.data(), sizeof(int32_t) * o.size()); }
+    if (x && y) {
+        for (int64_t p = 0; p < n; p++) y[p] = kron_local_acc<double>(V, H.ampw, H.diagk, p, x, x[p]);
+        const CrossItems I = cross_items(V.Du, V.Dd, W);
+        for (int64_t it = 0; it < I.nitems; it++)
+            for (int lane = 0; lane < 32; lane++) {
+                int64_t iu, id;
+                cross_item_at(I, it, lane, iu, id);
+                if (iu < 0 || iu >= V.Du || id < 0) return fail(QBGPU_ERR_STATE, "debug_species_host: warp item out of range");
+                const bool live = id < V.Dd;
+                const double acc = kron_cross_acc<double>(V, H.ampw, iu, live ? id : V.Dd - 1, x);
+                if (live) { y[iu * V.Dd + id] += acc; if (touched) touched[iu * V.Dd + id]++; }
+            }
+    }
+    return QBGPU_OK;
+}
+
+int qbgpu_native_perm(qbgpu_matrix_t A, int32_t *perm_host)
+{
+    QB_TRY(ensure_init());
+    if (!A || !perm_host) return fail(QBGPU_ERR_ARG, "null argument");
+    if (!A->perm) return fail(QBGPU_ERR_STATE, "the handle has no internal order");
+    QB_CUDA(cudaStreamSynchronize(ctx().stream));
+    QB_CUDA(cudaMemcpy(perm_host, A->perm, sizeof(int32_t) * (size_t)A->n, cudaMemcpyDeviceToHost));
+    return QBGPU_OK;
+}
+
+}  // extern "C"

@@ -123,6 +123,7 @@ static int launch_lanes(const qbgpu_matrix *A, const FusedArgs &a, int lanes)
 
 int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
 {
+    if (A->sp) return launch_spmv_species(A, a);             // two passes in the handle's internal order (species.cu)
     if (A->format == QBGPU_FORMAT_MATFREE) return launch_spmv_matfree(A, a);
     if (A->format == QBGPU_FORMAT_SELL) return launch_spmv_sjds(A, a);
     if (A->ndict) return fail(QBGPU_ERR_STATE, "dictionary-coded values need the sliced-jagged layout");
@@ -272,6 +273,7 @@ static int mv_any(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, v
 {
     QB_TRY(ensure_init());
     if (!x || !y) return fail(QBGPU_ERR_ARG, "null vector pointer");
+    if (A->sp) return mv_species(A, alpha, x, beta, y, where);   // reference order at the boundary, internal order inside
     if (where == QBGPU_HOST) return mv_host(A, alpha, x, beta, y);
     if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
     FusedArgs a;

@@ -299,7 +299,15 @@ static int trlan_typed(qbgpu_matrix *A, int nev, int ncv, int maxit, double tol,
         // the next pass starts at j = keep: its Gram-Schmidt recomputes column `keep` of T (diagonal and couplings)
     }
     for (int i = 0; i < nev; i++) evals[i] = theta[i];
-    if (evecs) {
+    if (evecs && A->perm) {
+        // species-order handle: the basis lives in the handle's internal order; hand the Ritz vectors back in the reference's
+        // (column ncv, the residual, is free by now and serves as the staging vector of host callers)
+        for (int i = 0; i < nev; i++) {
+            VecT *dst = where == QBGPU_HOST ? col(ncv) : (VecT *)evecs + (int64_t)i * n;
+            QB_TR(vec_from_native(A, cplx, cplx, col(i), dst, make_double2(1.0, 0.0), make_double2(0.0, 0.0)));
+            if (where == QBGPU_HOST) QB_CU(cudaMemcpyAsync((char *)evecs + vb * (size_t)n * i, dst, vb * (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+        }
+    } else if (evecs) {
         if (where == QBGPU_HOST) QB_CU(cudaMemcpyAsync(evecs, V, vb * (size_t)n * nev, cudaMemcpyDeviceToHost, c.stream));
         else QB_CU(cudaMemcpyAsync(evecs, V, vb * (size_t)n * nev, cudaMemcpyDeviceToDevice, c.stream));
     }

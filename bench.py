@@ -221,6 +221,102 @@ def build_matrix(qb, workload, row_range=None, flags=0):
     return qb.csr_mat._adopt(h, True)
 
 
+def species_probe(args):
+    """Child process of the single-GPU bench (hubbard workloads): the same H through the species-order handles
+    (QBGPU_SPECIES_ORDER, csrc/species.cu) -- parity against the ordinary handle first, then timings.  Run in a process of
+    its own because these kernels had not met hardware when they were committed: whatever happens here cannot touch the
+    numbers of the main line.  Prints one JSON object."""
+    import numpy as np
+    import torch
+    import quantum_basis_b200 as qb
+    torch.cuda.set_device(0)
+    L = qb.lib()
+    assert L.qbgpu_init(0) == 0, L.qbgpu_last_error()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert L.qbgpu_set_stream(C.c_void_p(stream.cuda_stream)) == 0
+    fam, p = WORKLOADS[args.workload]
+    ns = p["Lx"] * p["Ly"]
+    peak, _ = measured_peak()
+    out = {"workload": args.workload, "tile": int(os.environ.get("QBGPU_SPECIES_TILE", "128"))}
+
+    def timed(fn, steps):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def rel_err(ya, yref, n):
+        """|ya - yref| / |yref| on the device (ya is overwritten)."""
+        nr, nd = C.c_double(), C.c_double()
+        assert L.qbgpu_dznrm2(n, C.c_void_p(yref.ptr), C.byref(nr)) == 0
+        assert L.qbgpu_zaxpy(n, (C.c_double * 2)(-1.0, 0.0), C.c_void_p(yref.ptr), C.c_void_p(ya.ptr)) == 0
+        assert L.qbgpu_dznrm2(n, C.c_void_p(ya.ptr), C.byref(nd)) == 0
+        return nd.value / nr.value
+
+    P = build_matrix(qb, args.workload, flags=2 | 8)          # ordinary handle, production layout, no autotune pass
+    n, Z = P.info.n, P.info.nnz_stored
+    x = qb.vec_randomize(n, 1, device=True)
+    yref, y = qb.DeviceVector(n), qb.DeviceVector(n)
+    P.MultMv(x, yref)
+    out["ordinary_ms"] = timed(lambda: P.MultMv(x, y), max(3, args.steps // 2))
+    P.destroy()
+    bonds = square_bonds(p["Lx"], p["Ly"])
+    fused = L.qbgpu_spmv_fused
+    one, zero = (C.c_double * 2)(1.0, 0.0), (C.c_double * 2)(0.0, 0.0)
+    for kind in ("stored", "matrix_free"):
+        r = {}
+        out[kind] = r
+        try:
+            t0 = time.time()
+            M = qb.hubbard(ns, p["nup"], p["ndn"], bonds, p["t"], p["U"], flags=128, matrix_free=(kind == "matrix_free"))
+            torch.cuda.synchronize()
+            r["build_s"] = time.time() - t0
+            r["device_bytes"] = M.info.device_bytes
+            M.MultMv(x, y)
+            r["rel_err_vs_ordinary"] = rel_err(y, yref, n)
+            r["parity_ok"] = bool(r["rel_err_vs_ordinary"] <= 1e-12)
+            # (a) the reference-shaped call: vectors in the reference's order, permuted in and out around the two passes
+            ms = timed(lambda: M.MultMv(x, y), args.steps)
+            B16 = algorithmic_bytes(Z, n, n, 8, 16)
+            r["reference_order_complex"] = {"ms_per_product": ms, "achieved_GBs": B16 / ms / 1e6, "frac_of_measured_peak": B16 / ms / 1e6 / peak}
+            # (b) vectors kept in the internal order (what the Krylov loops do between their first and last step)
+            xn, yn = M.to_native(x), qb.DeviceVector(n)
+            ms = timed(lambda: fused(M.handle, C.c_void_p(xn.ptr), None, C.c_void_p(yn.ptr), one, zero, zero, None), args.steps)
+            r["internal_order_complex"] = {"ms_per_product": ms, "achieved_GBs": B16 / ms / 1e6, "frac_of_measured_peak": B16 / ms / 1e6 / peak}
+            xn.free(); yn.free()
+            # (c) fp64 vectors, internal order
+            Mr = M.real_view()
+            xr = qb.vec_randomize(n, 1, dtype=np.float64, device=True)
+            yr = qb.DeviceVector(n, np.float64)
+            ms = timed(lambda: fused(Mr.handle, C.c_void_p(xr.ptr), None, C.c_void_p(yr.ptr), one, zero, zero, None), args.steps)
+            B8 = algorithmic_bytes(Z, n, n, 8, 8)
+            r["internal_order_fp64"] = {"ms_per_product": ms, "achieved_GBs": B8 / ms / 1e6, "frac_of_measured_peak": B8 / ms / 1e6 / peak}
+            xr.free(); yr.free()
+            # (d) E0 through the reference-shaped Lanczos call
+            v = qb.DeviceVector(2 * n)
+            assert L.qbgpu_vec_randomize_z(n, C.c_void_p(v.ptr), 1) == 0
+            hess = np.zeros(2000)
+            torch.cuda.synchronize()
+            tl = time.time()
+            m = qb.lanczos(0, 999, 1000, n, M, v, hess, "sr_val0")
+            torch.cuda.synchronize()
+            tl = time.time() - tl
+            ritz, _ = qb.hess_eigen(hess, 1000, m)
+            r["lanczos"] = {"steps": m, "seconds": tl, "iters_per_s": m / tl, "E0": float(ritz[0])}
+            v.free()
+            M.destroy()
+        except Exception as e:                               # keep what was measured so far
+            r["error"] = str(e)[:500]
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,7 +326,11 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("QB_WORKLOAD", "hubbard4x4"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-lanczos", action="store_true", help="skip the E0 time-to-solution leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-species", action="store_true", help="skip the species-order probe (hubbard workloads, child process)")
+    ap.add_argument("--species-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.species_probe:
+        return species_probe(args)
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -418,6 +518,20 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/qb_ref not built"}
         except Exception as e:   # the baseline is informative; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    # ---------------------------------------------------------------- species-order handles, in a process of their own
+    # (hubbard workloads; everything above is already measured and this process gives its HBM back first)
+    if WORKLOADS[args.workload][0] == "hubbard" and not args.no_species:
+        try:
+            M.destroy(); x.free(); y.free()
+            del xh, yh, xh_t, yh_t, flush_buf
+            torch.cuda.empty_cache()
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--species-probe", "--workload", args.workload,
+                                  "--steps", str(max(5, min(args.steps, 20)))], capture_output=True, text=True, timeout=900)
+            lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            line["species_order"] = json.loads(lines[-1]) if lines else {"error": f"exit {res.returncode}: {res.stderr[-400:]}"}
+        except Exception as e:
+            line["species_order"] = {"error": str(e)[:400]}
 
     print(json.dumps(line))
 

@@ -1,0 +1,197 @@
+"""GPU tests of the species-order handles of the Hubbard model (QBGPU_SPECIES_ORDER; quantum_basis_b200/csrc/species.cu).
+
+STATUS: written after the round's GPU budget was spent -- these kernels have NOT run on hardware yet.  Their index logic
+(hop tables, permutation, generator of the two stored parts, slice order, the matrix-free passes and their warp items) is
+checked on the host by tests/test_species_cpu.py through the same __host__ __device__ functions; what only a device can
+show is here.  The module is xfail(strict=False) and named to be collected LAST, so that a defect in this unverified path
+can neither mask nor (through a poisoned CUDA context) take down the verified suite; an XPASS is the evidence that it
+works.  Remove the xfail marker after the first green run on a B200.
+
+What is compared: the species-order product, through the reference-shaped calls (vectors in the reference's order), against
+the CPU restatement of the reference's product on the reference-identical matrix (1e-12, BASELINE.json) and against the
+ordinary device handle; the Krylov drivers (E0 to 1e-10, KPM moments to 1e-9) against the ordinary handle.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import lin_builders as B
+import species_builders as SB
+import quantum_basis_b200 as qb
+from quantum_basis_b200 import _lib
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="species-order kernels: first hardware run pending (written without GPU access)")]
+
+SPECIES = _lib.SPECIES_ORDER
+TOL_MV, TOL_E0, TOL_KPM = 1e-12, 1e-10, 1e-9
+CASES = {"hub4x2_35": (4, 2, 3, 5, 1.1), "hub4x2_44": (4, 2, 4, 4, 1.1), "hub3x3_45": (3, 3, 4, 5, 2.3), "hub2x2_12": (2, 2, 1, 2, 0.7)}
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _case(name):
+    Lx, Ly, nu, nd, U = CASES[name]
+    ns, bonds = Lx * Ly, B.square_bonds(Lx, Ly)
+    mk = lambda cx=True, mf=False, flags=SPECIES: qb.hubbard(ns, nu, nd, bonds, 1.0, U, is_complex=cx, matrix_free=mf, flags=flags)   # noqa: E731
+    return ns, nu, nd, bonds, U, mk
+
+
+@pytest.mark.parametrize("name", ["hub4x2_35", "hub3x3_45"])
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_permutation_and_info(name, matrix_free):
+    ns, nu, nd, bonds, U, mk = _case(name)
+    M = mk(mf=matrix_free)
+    assert M.has_internal_order()
+    assert np.array_equal(M.native_perm(), SB.species_perm(ns, nu, nd))
+    plain = mk(flags=0)
+    assert not plain.has_internal_order()
+    inf = M.info
+    assert inf.n == plain.dim
+    if matrix_free:
+        assert inf.format == 32 and inf.nnz_stored == 0
+    else:
+        assert inf.nnz_stored == plain.info.nnz_stored and inf.nnz_input == plain.info.nnz_input    # same entries, split in two parts
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_product_in_the_reference_order(oracle, name, matrix_free):
+    from oracle_lib import Csr
+    ns, nu, nd, bonds, U, mk = _case(name)
+    n, ia, ja, val = B.hubbard_upper_csr(ns, nu, nd, bonds, 1.0, U)
+    A = Csr(n, ia, ja, val, True)
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    M = mk(mf=matrix_free)
+    y = np.full(n, 3.0 - 2.0j)
+    M.MultMv(x, y)                                                    # host vectors, complex
+    assert rel_l2(y, oracle.spmv_ld(A, x)) <= TOL_MV
+    ys = np.zeros(n, dtype=np.complex128)
+    mk(flags=0).MultMv(x, ys)
+    assert rel_l2(y, ys) <= 1e-14
+    y2 = y.copy()
+    M.MultMv2(x, y2)                                                  # y += H x
+    assert rel_l2(y2, 2 * y) <= 1e-14
+    xd, yd = qb.DeviceVector.from_numpy(x), qb.DeviceVector(n)        # device vectors
+    M.MultMv(xd, yd)
+    assert np.array_equal(yd.to_numpy(), y)
+    Md = mk(cx=False, mf=matrix_free)                                 # fp64 handle
+    xr = rng.normal(size=n); yr = np.zeros(n)
+    Md.MultMv(xr, yr)
+    assert rel_l2(yr, oracle.spmv_ld(A, xr).real) <= TOL_MV
+
+
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_internal_order_entry_points(matrix_free):
+    """to_native / from_native and the fused product (alpha, gamma, beta*z, running dots) in the internal order."""
+    import ctypes as C
+    ns, nu, nd, bonds, U, mk = _case("hub4x2_44")
+    M, P = mk(mf=matrix_free), mk(flags=0)
+    n = M.dim
+    perm = M.native_perm()
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    z = rng.normal(size=n) + 1j * rng.normal(size=n)
+    xd = qb.DeviceVector.from_numpy(x)
+    xn = M.to_native(xd)
+    x_int = np.empty_like(x); x_int[perm] = x
+    assert np.array_equal(xn.to_numpy(), x_int)
+    assert np.array_equal(M.from_native(xn).to_numpy(), x)
+    # y = alpha H x + gamma x + beta z with dots, internal order, against the ordinary handle in the reference's order
+    L = qb.lib()
+    z_int = np.empty_like(z); z_int[perm] = z
+    zn, yn = qb.DeviceVector.from_numpy(z_int), qb.DeviceVector(n)
+    dots = qb.DeviceVector(4, np.float64)
+    al, ga, be = (C.c_double * 2)(0.7, 0.0), (C.c_double * 2)(-0.3, 0.0), (C.c_double * 2)(1.5, 0.0)
+    _lib.check(L.qbgpu_spmv_fused(M.handle, C.c_void_p(xn.ptr), C.c_void_p(zn.ptr), C.c_void_p(yn.ptr), al, ga, be, C.c_void_p(dots.ptr)))
+    hx = np.zeros(n, dtype=np.complex128)
+    P.MultMv(x, hx)
+    want = 0.7 * hx - 0.3 * x + 1.5 * z
+    got = yn.to_numpy()[perm]
+    assert rel_l2(got, want) <= 1e-13
+    d = dots.to_numpy()
+    assert abs(d[0] + 1j * d[1] - np.vdot(x, want)) <= 1e-11 * abs(np.vdot(x, want)) + 1e-11
+    assert abs(d[2] - np.vdot(want, want).real) <= 1e-12 * np.vdot(want, want).real
+    # in place (z aliases y), the Lanczos / Chebyshev calling pattern
+    _lib.check(L.qbgpu_spmv_fused(M.handle, C.c_void_p(xn.ptr), C.c_void_p(zn.ptr), C.c_void_p(zn.ptr), al, ga, be, None))
+    assert rel_l2(zn.to_numpy()[perm], want) <= 1e-13
+
+
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_krylov_drivers_match_the_ordinary_handle(oracle, matrix_free):
+    from oracle_lib import Csr
+    ns, nu, nd, bonds, U, mk = _case("hub3x3_45")
+    n, ia, ja, val = B.hubbard_upper_csr(ns, nu, nd, bonds, 1.0, U)
+    A = Csr(n, ia, ja, val, True)
+    M, P = mk(mf=matrix_free), mk(flags=0)
+    # Lanczos coefficients from the reference's start vector (they do not depend on the order of the basis)
+    hs, hp = np.zeros(200), np.zeros(200)
+    vs, vp = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * n, dtype=np.complex128)
+    vs[:n] = oracle.vec_randomize(n, 1); vp[:n] = vs[:n]
+    ms = qb.lanczos(0, 40, 100, n, M, vs, hs, "dnmcs")
+    mp = qb.lanczos(0, 40, 100, n, P, vp, hp, "dnmcs")
+    assert ms == mp == 40
+    assert np.abs(hs[100:120] - hp[100:120]).max() <= 1e-10 and np.abs(hs[1:21] - hp[1:21]).max() <= 1e-10
+    assert rel_l2(vs[:n], vp[:n]) <= 1e-8 and rel_l2(vs[n:], vp[n:]) <= 1e-8          # live vectors, reference order
+    # E0, ground state, E1
+    out_s = qb.locate_E0_lanczos(M, nev=2, ncv=2)
+    out_p = qb.locate_E0_lanczos(P, nev=2, ncv=2)
+    for k in range(2):
+        assert abs(out_s["eigenvals"][k] - out_p["eigenvals"][k]) <= TOL_E0 * abs(out_p["eigenvals"][k])
+        v = out_s["eigenvecs"][k]
+        assert np.linalg.norm(oracle.spmv(A, v) - out_s["eigenvals"][k] * v) < 1e-7
+    # spectral bounds and Chebyshev moments
+    ws, wp = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * n, dtype=np.complex128)
+    lo_s, hi_s = qb.energy_scale(n, M, ws)
+    lo_p, hi_p = qb.energy_scale(n, P, wp)
+    assert abs(lo_s - lo_p) <= 1e-9 * abs(lo_p) and abs(hi_s - hi_p) <= 1e-9 * abs(hi_p)
+    phi = oracle.vec_randomize(n, 3)
+    mu_s = qb.kpm_moments(M, phi, lo_p, hi_p, 64)
+    mu_p = qb.kpm_moments(P, phi, lo_p, hi_p, 64)
+    assert np.abs(mu_s - mu_p).max() <= TOL_KPM
+    # thick-restart Lanczos: eigenvalues and Ritz vectors in the reference's order
+    nconv, w, Uv, nprod = qb.trlan(M, 2, 8, 400)
+    assert nconv >= 2 and abs(w[0] - out_p["eigenvals"][0]) <= 1e-9 * abs(w[0])
+    assert np.linalg.norm(oracle.spmv(A, Uv[:, 0].copy()) - w[0] * Uv[:, 0]) < 1e-6
+
+
+@pytest.mark.parametrize("tile", ["32", "256"])
+def test_midsize_sector_and_tile_widths(tile):
+    """Hubbard 4x3, N_up = N_dn = 6 (853,776 states): both handle kinds against the ordinary device handle, with tiles
+    narrower and wider than the default (the tile width is read when the handle is created)."""
+    ns, bonds = 12, B.square_bonds(4, 3)
+    os.environ["QBGPU_SPECIES_TILE"] = tile
+    try:
+        Ms = qb.hubbard(ns, 6, 6, bonds, 1.0, 1.1, flags=SPECIES)
+        Mf = qb.hubbard(ns, 6, 6, bonds, 1.0, 1.1, flags=SPECIES, matrix_free=True)
+    finally:
+        del os.environ["QBGPU_SPECIES_TILE"]
+    P = qb.hubbard(ns, 6, 6, bonds, 1.0, 1.1)
+    n = P.dim
+    assert n == 853776
+    x = qb.vec_randomize(n, 1, device=True)
+    yp, ys, yf = qb.DeviceVector(n), qb.DeviceVector(n), qb.DeviceVector(n)
+    P.MultMv(x, yp); Ms.MultMv(x, ys); Mf.MultMv(x, yf)
+    ref = yp.to_numpy()
+    assert rel_l2(ys.to_numpy(), ref) <= 1e-14 and rel_l2(yf.to_numpy(), ref) <= 1e-14
+    e_p = qb.locate_E0_lanczos(P, nev=1, ncv=0)["eigenvals"][0]
+    for M in (Ms, Mf):
+        e = qb.locate_E0_lanczos(M, nev=1, ncv=0)["eigenvals"][0]
+        assert abs(e - e_p) <= TOL_E0 * abs(e_p)
+
+
+def test_unsupported_uses_fail_loudly():
+    ns, nu, nd, bonds, U, mk = _case("hub4x2_35")
+    with pytest.raises(qb.QbgpuError):
+        qb.hubbard(ns, nu, nd, bonds, 1.0, U, flags=SPECIES, rows=(0, 100))           # no row shards
+    with pytest.raises(qb.QbgpuError):
+        qb.heisenberg(12, 6, B.chain_bonds(12), 1.0, flags=SPECIES)                   # one species only
+    M = mk()
+    with pytest.raises(qb.QbgpuError):
+        M.to_dense()
+    with pytest.raises(qb.QbgpuError):
+        M.download_expanded()

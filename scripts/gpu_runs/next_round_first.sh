@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU call of the next round: the species-order handles (written after round 1's GPU budget was spent).
+#   gpurun --timeout 900 -- 'bash scripts/gpu_runs/next_round_first.sh'
+set -x
+mkdir -p gpurun_out
+# 1. correctness: the xfail-marked module, run strictly (a failure here is a failure)
+python -m pytest tests/test_zz_gpu_species.py -q -x --runxfail -p no:cacheprovider > gpurun_out/pytest_species.log 2>&1; echo "pytest species rc=$?" >> gpurun_out/pytest_species.log
+tail -5 gpurun_out/pytest_species.log
+# 2. timings on BASELINE config 3 and the 4x3 sample, tile sweep
+for W in 64 128 256 512; do
+  QBGPU_SPECIES_TILE=$W timeout 600 python bench.py --species-probe --workload hubbard4x4 --steps 10 > gpurun_out/species_probe_W$W.json 2> gpurun_out/species_probe_W$W.err
+  tail -c 1500 gpurun_out/species_probe_W$W.json
+done
+# 3. the term-coded replay kernel v3 left over from round 1
+QBGPU_TERMS_KERNEL=3 timeout 300 python scripts/terms_check.py > gpurun_out/terms_check_v3.txt 2>&1; tail -3 gpurun_out/terms_check_v3.txt

@@ -290,6 +290,19 @@ def species_probe(args):
             xn, yn = M.to_native(x), qb.DeviceVector(n)
             ms = timed(lambda: fused(M.handle, C.c_void_p(xn.ptr), None, C.c_void_p(yn.ptr), one, zero, zero, None), args.steps)
             r["internal_order_complex"] = {"ms_per_product": ms, "achieved_GBs": B16 / ms / 1e6, "frac_of_measured_peak": B16 / ms / 1e6 / peak}
+            if kind == "matrix_free":                         # pass-1 variants of the matrix-free product (csrc/species.cu)
+                r["pass1_variants_complex_ms"] = {}
+                for vname, vid in (("grid_stride", 0), ("row_ranges", 1), ("smem_staged", 2)):
+                    assert L.qbgpu_debug_set_variant(1000 + vid) == 0
+                    fused(M.handle, C.c_void_p(xn.ptr), None, C.c_void_p(yn.ptr), one, zero, zero, None)
+                    xr_ = M.from_native(yn)
+                    err = rel_err(xr_, yref, n)
+                    xr_.free()
+                    r["pass1_variants_complex_ms"][vname] = {"ms": timed(lambda: fused(M.handle, C.c_void_p(xn.ptr), None, C.c_void_p(yn.ptr), one, zero, zero, None), args.steps),
+                                                             "rel_err_vs_ordinary": err}
+                best = min(r["pass1_variants_complex_ms"].items(), key=lambda kv: kv[1]["ms"] if kv[1]["rel_err_vs_ordinary"] <= 1e-12 else 1e30)
+                assert L.qbgpu_debug_set_variant(1000 + {"grid_stride": 0, "row_ranges": 1, "smem_staged": 2}[best[0]]) == 0
+                r["pass1_variant_used_below"] = best[0]
             xn.free(); yn.free()
             # (c) fp64 vectors, internal order
             Mr = M.real_view()

@@ -338,7 +338,9 @@ int64_t qbgpu_dim_heisenberg(int nsites, int nup);
 int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
 
 /* tuning hook used by scripts/kbench.py: selects an experimental instantiation of the sliced-jagged kernel
- * (only in builds with -DQBGPU_TUNING_VARIANTS; otherwise a no-op).  id 0 = production configuration. */
+ * (only in builds with -DQBGPU_TUNING_VARIANTS; otherwise a no-op).  id 0 = production configuration.
+ * id 1000 + v selects pass 1 of the matrix-free species-order product instead: v = 0 grid-stride rows (default),
+ * 1 contiguous row ranges with one 1024-thread CTA per SM, 2 block x[iu, :] staged in shared memory. */
 int qbgpu_debug_set_variant(int id);
 /* |col - row| beyond which a gathered entry is loaded with the L2 evict-first policy (kernels with the per-entry
  * gather policy only) */

@@ -184,6 +184,7 @@ int qbgpu_host_unregister(void *ptr)
 
 int qbgpu_debug_set_variant(int id)
 {
+    if (id >= 1000 && id < 1010) { qb::set_kron_local_variant(id - 1000); return QBGPU_OK; }   // pass 1 of the matrix-free species product
     qb::set_sjds_variant(id);
     return QBGPU_OK;
 }

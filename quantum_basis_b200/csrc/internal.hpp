@@ -86,6 +86,7 @@ int peer_ring_flags(const int **flags, int **timeout_flag);                 // p
 // species.cu
 int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &args);      // the two-pass products of species-order handles
 void species_destroy(qbgpu_matrix *A);
+void set_kron_local_variant(int v);       // tuning hook (qbgpu_debug_set_variant(1000 + v)); default from QBGPU_KRON_LOCAL
 int64_t species_bytes(const qbgpu_matrix *A);
 // dst[perm[r]] = src[r]  (reference order -> internal order); complex -> real takes the real part, real -> complex sets imag = 0
 int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst);

@@ -384,14 +384,13 @@ int64_t species_bytes(const qbgpu_matrix *A)
 // pass 1: y = alpha * (diagonal + down hops) x + gamma x + beta z.  One thread per row, rows ascending: the gathers of a
 // row fall into its own block x[iu, :].  Four hop entries per trip: their table loads, then their gathers, are issued
 // together; past the end of the list the trip replays "0 * x[own row]".
-template <typename VecT>
-__host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, const double *ampw, const double *diagk, int64_t p, const VecT *x, VecT xi)
+// xb = the block x[iu, :] of the row -- in global memory (GLOBAL: read-only path) or staged in shared memory
+template <typename VecT, bool GLOBAL>
+__host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, const double *ampw, const double *diagk, uint32_t U, int32_t id,
+                                                        const VecT *xb, VecT xi)
 {
     using VT = VecTraits<VecT>;
-    const int64_t iu = p / V.Dd;
-    const int32_t id = (int32_t)(p - iu * V.Dd);
-    const uint32_t U = ld_ro(V.ulist + iu), D = ld_ro(V.dlist + id);
-    const VecT *xb = x + iu * V.Dd;
+    const uint32_t D = ld_ro(V.dlist + id);
     VecT acc = VT::zero();
     mac(acc, diagk[popc_hd(U & D)], xi);
     const int e1 = ld_ro(V.dptr + id + 1);
@@ -401,15 +400,28 @@ __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, co
 QB_UNROLL
         for (int u = 0; u < 4; u++) h[u] = (e + u < e1) ? ld_ro(V.dhop + e + u) : make_uint2((uint32_t)id, 0u);
 QB_UNROLL
-        for (int u = 0; u < 4; u++) xv[u] = ld_ro(xb + h[u].x);
+        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + h[u].x); else xv[u] = xb[h[u].x]; }
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
     }
     return acc;
 }
 
-template <typename VecT>
-__global__ void __launch_bounds__(kPBlock, 4)
+// epilogue scalars of pass 1 (Lanczos step a like the stored kernels, spmv.cu)
+__device__ __forceinline__ void local_scalars(int scal_mode, const double *sc, double2 &alpha, double2 &gamma, double2 &beta)
+{
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+    }
+}
+
+// BLOCK = 256, grid-stride (default), or BLOCK = 1024 with one contiguous range of rows per CTA (QBGPU_KRON_LOCAL=1: one
+// CTA per SM then walks through the blocks x[iu, :] one after the other, so that L1 holds the block being gathered from)
+template <typename VecT, int BLOCK, bool RANGES>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
 kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
                   const VecT *__restrict__ x, const VecT *z, VecT *y,
                   double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
@@ -419,21 +431,60 @@ kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, c
     for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
     for (int k = threadIdx.x; k <= kMaxDbl; k += blockDim.x) diagk[k] = diagk_g[k];
     __syncthreads();
-    if (scal_mode != 0) {                                   // Lanczos step a, like the stored kernels (spmv.cu)
-        const double sx = sc[0], sz = sc[1], bprev = sc[2];
-        alpha = make_double2(sx, 0.0);
-        gamma = make_double2(0.0, 0.0);
-        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
-    }
+    local_scalars(scal_mode, sc, alpha, gamma, beta);
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
     const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p0, p1, step;
+    if (RANGES) {
+        const int64_t chunk = ((n + gridDim.x - 1) / gridDim.x + BLOCK - 1) / BLOCK * BLOCK;
+        p0 = (int64_t)blockIdx.x * chunk + threadIdx.x; p1 = min(n, ((int64_t)blockIdx.x + 1) * chunk); step = BLOCK;
+    } else {
+        p0 = (int64_t)blockIdx.x * BLOCK + threadIdx.x; p1 = n; step = (int64_t)gridDim.x * BLOCK;
+    }
+    for (int64_t p = p0; p < p1; p += step) {
+        const int64_t iu = p / V.Dd;
+        const int32_t id = (int32_t)(p - iu * V.Dd);
         const VecT xi = ld_ro(x + p);
-        const VecT acc = kron_local_acc<VecT>(V, ampw, diagk, p, x, xi);
+        const VecT acc = kron_local_acc<VecT, true>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x + iu * V.Dd, xi);
         VecT out = VT::scale(alpha, acc);
         if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
         if (use_beta) out = VT::add(out, VT::scale(beta, z[p]));
         y[p] = out;
+    }
+}
+
+// QBGPU_KRON_LOCAL=2: one CTA of 1024 threads per up configuration; the block x[iu, :] (D_dn entries: 206 KB of complex
+// numbers for the 4x4 lattice) is staged in shared memory once and every gather of the block's rows reads it from there.
+template <typename VecT>
+__global__ void __launch_bounds__(1024, 1)
+kron_local_smem_kernel(SpeciesView V, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+                       const VecT *__restrict__ x, const VecT *z, VecT *y,
+                       double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
+{
+    using VT = VecTraits<VecT>;
+    extern __shared__ double2 kron_smem_raw[];              // 16-byte aligned for either vector type
+    VecT *xs = reinterpret_cast<VecT *>(kron_smem_raw);
+    __shared__ double ampw[kMaxWeight + 1], diagk[kMaxDbl + 1];
+    for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
+    for (int k = threadIdx.x; k <= kMaxDbl; k += blockDim.x) diagk[k] = diagk_g[k];
+    local_scalars(scal_mode, sc, alpha, gamma, beta);
+    const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    const int32_t Dd = (int32_t)V.Dd;
+    for (int64_t iu = blockIdx.x; iu < V.Du; iu += gridDim.x) {
+        __syncthreads();                                    // the previous block's gathers are done (and the tables are loaded)
+        const VecT *xg = x + iu * V.Dd;
+        for (int32_t k = threadIdx.x; k < Dd; k += 1024) xs[k] = ld_ro(xg + k);
+        __syncthreads();
+        const uint32_t U = ld_ro(V.ulist + iu);
+        for (int32_t id = threadIdx.x; id < Dd; id += 1024) {
+            const VecT xi = xs[id];
+            const VecT acc = kron_local_acc<VecT, false>(V, ampw, diagk, U, id, xs, xi);
+            VecT out = VT::scale(alpha, acc);
+            if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
+            if (use_beta) out = VT::add(out, VT::scale(beta, z[iu * V.Dd + id]));
+            y[iu * V.Dd + id] = out;
+        }
     }
 }
 
@@ -524,6 +575,9 @@ kron_cross_kernel(SpeciesView V, CrossItems I, const double *__restrict__ ampw_g
     }
 }
 
+static int g_kron_local_variant = -1;      // -1: not chosen yet (environment QBGPU_KRON_LOCAL, else 0)
+void set_kron_local_variant(int v) { g_kron_local_variant = v; }
+
 template <typename VecT>
 static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
 {
@@ -532,8 +586,28 @@ static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
     const int64_t n = A->n;
     if (n == 0) return QBGPU_OK;
     const SpeciesView V = view_of(S);
-    {
-        auto kern = kron_local_kernel<VecT>;
+    // pass 1 variants (QBGPU_KRON_LOCAL): 0 grid-stride / 256 threads (default), 1 contiguous row ranges / 1024 threads,
+    // 2 block staged in shared memory (falls back to 0 when D_dn entries do not fit)
+    if (g_kron_local_variant < 0) g_kron_local_variant = getenv("QBGPU_KRON_LOCAL") ? atoi(getenv("QBGPU_KRON_LOCAL")) : 0;
+    const int variant = g_kron_local_variant;
+    const size_t stage_bytes = sizeof(VecT) * (size_t)S->Dd;
+    if (variant == 2 && stage_bytes <= 225 * 1024) {
+        auto kern = kron_local_smem_kernel<VecT>;
+        static bool attr_set = false;
+        if (!attr_set) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_set = true; }
+        const int64_t grid = S->Du < c.num_sms ? S->Du : c.num_sms;
+        kern<<<(int)grid, 1024, stage_bytes, c.stream>>>(V, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                                         a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+    } else if (variant == 1) {
+        auto kern = kron_local_kernel<VecT, 1024, true>;
+        kern<<<c.num_sms, 1024, 0, c.stream>>>(V, n, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                               a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+    } else {
+        auto kern = kron_local_kernel<VecT, kPBlock, false>;
         static int bps = 0;
         if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
         const int64_t want = (n + kPBlock - 1) / kPBlock, cap = (int64_t)c.num_sms * bps;
@@ -740,7 +814,10 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
         for (int64_t p = 0; p < n; p++) species_fill_row<double>(V, H.ampw, H.diagk, p, col_local, val_local, col_cross, val_cross);
     if (slice_order) { std::vector<int32_t> o; make_slice_order(n, V.Dd, W, o); memcpy(slice_order, o.data(), sizeof(int32_t) * o.size()); }
     if (x && y) {
-        for (int64_t p = 0; p < n; p++) y[p] = kron_local_acc<double>(V, H.ampw, H.diagk, p, x, x[p]);
+        for (int64_t p = 0; p < n; p++) {
+            const int64_t iu = p / V.Dd;
+            y[p] = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(p - iu * V.Dd), x + iu * V.Dd, x[p]);
+        }
         const CrossItems I = cross_items(V.Du, V.Dd, W);
         for (int64_t it = 0; it < I.nitems; it++)
             for (int lane = 0; lane < 32; lane++) {

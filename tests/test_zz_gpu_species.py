@@ -178,6 +178,15 @@ def test_midsize_sector_and_tile_widths(tile):
     P.MultMv(x, yp); Ms.MultMv(x, ys); Mf.MultMv(x, yf)
     ref = yp.to_numpy()
     assert rel_l2(ys.to_numpy(), ref) <= 1e-14 and rel_l2(yf.to_numpy(), ref) <= 1e-14
+    L = qb.lib()
+    try:                                                              # the three pass-1 variants of the matrix-free product
+        for vid in (1, 2, 0):
+            assert L.qbgpu_debug_set_variant(1000 + vid) == 0
+            yf.zero()
+            Mf.MultMv(x, yf)
+            assert rel_l2(yf.to_numpy(), ref) <= 1e-14, f"pass-1 variant {vid}"
+    finally:
+        L.qbgpu_debug_set_variant(1000)
     e_p = qb.locate_E0_lanczos(P, nev=1, ncv=0)["eigenvals"][0]
     for M in (Ms, Mf):
         e = qb.locate_E0_lanczos(M, nev=1, ncv=0)["eigenvals"][0]

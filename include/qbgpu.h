@@ -324,6 +324,12 @@ int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbond
  * With measure_repr_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1897-1912. */
 int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const double *coef_reim, const void *x_old_dev,
                           void *y_new_dev);
+/* The off-diagonal branch of the same routine (src/model.cc:1762-1834) for the spin-1/2 ladder operators:
+ * A = sum_r coef[r] S^-_r (lower = 1; S_new has one more down spin) or sum_r coef[r] S^+_r (lower = 0; one fewer).
+ * y_new (S_new's dimension) is overwritten.  Contributions are added with fp64 atomics -- the reference adds them from
+ * several threads in no fixed order either -- so results agree with it to rounding, not to the bit. */
+int qbgpu_sector_apply_ladder(qbgpu_sector_t S_old, qbgpu_sector_t S_new, int lower, const double *coef_reim,
+                              const void *x_old_dev, void *y_new_dev);
 /* Momentum sector for an ARBITRARY abelian symmetry group given as site permutations (BASELINE config 4: the tilted
  * 31-site triangular cluster, which the reference itself cannot build -- SURVEY F5 -- so there is no reference convention
  * to reproduce; representative = smallest bit pattern of the orbit, orbits on whose stabiliser the character is not

@@ -367,6 +367,18 @@ class Sector:
         check(lib().qbgpu_sector_apply_sz(self._h, new_sector._h, C.c_void_p(cf.ctypes.data), C.c_void_p(xd.ptr), C.c_void_p(y.ptr)))
         return y
 
+    def apply_ladder(self, new_sector, coef, x, lower=True, out=None):
+        """The off-diagonal branch of model::moprXvec_repr (src/model.cc:1762-1834) for A = sum_r coef[r] S^-_r (lower=True:
+        `new_sector` has one more down spin) or sum_r coef[r] S^+_r (lower=False): x in this sector -> DeviceVector in
+        `new_sector`."""
+        cf = np.ascontiguousarray(coef, dtype=np.complex128)
+        if cf.size != self.nsites:
+            raise QbgpuError("one coefficient per site")
+        xd = x if isinstance(x, DeviceVector) else DeviceVector.from_numpy(np.ascontiguousarray(x, dtype=np.complex128))
+        y = out if out is not None else DeviceVector(new_sector.dim)
+        check(lib().qbgpu_sector_apply_ladder(self._h, new_sector._h, int(bool(lower)), C.c_void_p(cf.ctypes.data), C.c_void_p(xd.ptr), C.c_void_p(y.ptr)))
+        return y
+
     def free(self):
         if self._h:
             lib().qbgpu_sector_destroy(self._h)
@@ -379,14 +391,20 @@ class Sector:
             pass
 
 
-def measure_repr_dynamic(coef, sec_old, sec_new, mat_new, phi0, maxit, hessenberg):
-    """model<T>::measure_repr_dynamic (src/model.cc:1897-1912) for A = sum_r coef[r] S^z_r, everything on the device:
-    vec = A phi0 mapped into sec_new (moprXvec_repr), norm = |vec|, then lanczos(0, maxit-1, maxit, ..., "dnmcs") from
-    vec/norm on `mat_new`.  Returns (m, norm); hessenberg[2*maxit] receives b in [0, m) and a in [maxit, maxit+m)."""
+def measure_repr_dynamic(coef, sec_old, sec_new, mat_new, phi0, maxit, hessenberg, op="sz"):
+    """model<T>::measure_repr_dynamic (src/model.cc:1897-1912) for A = sum_r coef[r] S^z_r (op="sz"), S^-_r ("s-") or
+    S^+_r ("s+"), everything on the device: vec = A phi0 mapped into sec_new (moprXvec_repr), norm = |vec|, then
+    lanczos(0, maxit-1, maxit, ..., "dnmcs") from vec/norm on `mat_new`.  Returns (m, norm); hessenberg[2*maxit] receives
+    b in [0, m) and a in [maxit, maxit+m)."""
     n = sec_new.dim
     v = DeviceVector(2 * n)
     v.zero()
-    sec_old.apply_sz(sec_new, coef, phi0, out=v.view(0, n))
+    if op == "sz":
+        sec_old.apply_sz(sec_new, coef, phi0, out=v.view(0, n))
+    elif op in ("s-", "s+"):
+        sec_old.apply_ladder(sec_new, coef, phi0, lower=(op == "s-"), out=v.view(0, n))
+    else:
+        raise QbgpuError("op must be 'sz', 's-' or 's+'")
     nr = C.c_double()
     check(lib().qbgpu_dznrm2(n, C.c_void_p(v.ptr), C.byref(nr)))
     if abs(nr.value) < lanczos_precision:

@@ -307,6 +307,48 @@ __global__ void __launch_bounds__(kSBlock) sec_apply_sz_kernel(SecDev S, const d
     }
 }
 
+// model::moprXvec_repr (src/model.cc:1762-1834), off-diagonal branch, for the spin-1/2 ladder operators
+// A = sum_r c_r S^-_r (lower = 1: acts on up spins, the target sector has one more down spin) or sum_r c_r S^+_r
+// (lower = 0).  Every term flips one spin of the OLD representative; the produced state is brought to its representative
+// in the NEW sector and
+//     y[i] += sqrt(nu_old[j] / nu_new[i]) * x[j] * c_r * exp(-2 pi i k_new . disp_i / L)
+// (restated and pinned to the compiled reference in tests/repr_builders.py: apply_sminus).  Scatter with fp64 atomics:
+// the reference itself adds these contributions from several threads in no fixed order, so agreement is to rounding.
+// y must be zero on entry.
+__global__ void __launch_bounds__(kSBlock) sec_apply_ladder_kernel(SecDev So, SecDev Sn, const double2 *__restrict__ phase_new, const double2 *__restrict__ coef,
+                                                                   int lower, const double2 *__restrict__ x, double2 *y)
+{
+    __shared__ double2 c[kMaxTrans];
+    if (threadIdx.x < So.nsites) c[threadIdx.x] = coef[threadIdx.x];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < So.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double2 xj = x[r];
+        const double nj = So.nu[r];
+        if (!(hypot(xj.x, xj.y) >= 2e-12) || !(nj >= 2e-12)) continue;                 // :1752
+        uint32_t a, b;
+        sec_halves(So, So.keys[r], a, b);
+        const uint32_t st = spread_bits(a) | (spread_bits(b) << 1);
+        for (int site = 0; site < So.nsites; site++) {
+            const uint32_t bit = 1u << site;
+            if (lower ? (st & bit) != 0u : (st & bit) == 0u) continue;                 // S^- needs an up spin (digit 0), S^+ a down spin
+            const uint32_t s2 = st ^ bit;
+            uint32_t ca = 0, cb = 0;
+            const int i = sec_canon(Sn, squeeze_bits(s2), squeeze_bits(s2 >> 1), ca, cb);
+            if (i < 0) continue;
+            const int64_t tgt = sec_lookup(Sn, sec_key(Sn, ca, cb));
+            if (tgt < 0) continue;
+            const double ni = Sn.nu[tgt];
+            if (!(ni >= 2e-12)) continue;                                              // :1810
+            const double w = sqrt(nj / ni);
+            const double2 ph = phase_new[i];                                           // exp(+2 pi i k.disp/L): conjugated below
+            const double2 t1 = make_double2(w * xj.x, w * xj.y);
+            const double2 t2 = make_double2(t1.x * c[site].x - t1.y * c[site].y, t1.x * c[site].y + t1.y * c[site].x);
+            atomicAdd(&y[tgt].x, t2.x * ph.x + t2.y * ph.y);
+            atomicAdd(&y[tgt].y, t2.y * ph.x - t2.x * ph.y);
+        }
+    }
+}
+
 static double wall_clock() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct FlagToInt { __host__ __device__ int operator()(uint8_t f) const { return (int)f; } };
 static int sgrid(int64_t n) { int64_t g = (n + kSBlock - 1) / kSBlock; if (g < 1) g = 1; if (g > 148 * 64) g = 148 * 64; return (int)g; }
@@ -623,6 +665,30 @@ int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const doub
         QB_LAUNCH_COUNT();
         e = cudaStreamSynchronize(c.stream);
     }
+    cudaFree(d_coef);
+    QB_CUDA(e);
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+int qbgpu_sector_apply_ladder(qbgpu_sector_t S_old, qbgpu_sector_t S_new, int lower, const double *coef_reim, const void *x_old_dev, void *y_new_dev)
+{
+    if (!S_old || !S_new || !coef_reim || !x_old_dev || !y_new_dev) return fail(QBGPU_ERR_ARG, "sector_apply_ladder: null argument");
+    if (S_old->nsites != S_new->nsites || S_old->dim != S_new->dim || memcmp(S_old->L, S_new->L, sizeof(S_old->L)) != 0)
+        return fail(QBGPU_ERR_ARG, "sector_apply_ladder: the two sectors must share the lattice");
+    if (S_new->ndown != S_old->ndown + (lower ? 1 : -1))
+        return fail(QBGPU_ERR_ARG, "sector_apply_ladder: the target sector must have one more (S^-) or one fewer (S^+) down spin");
+    Context &c = ctx();
+    double2 *d_coef = nullptr;
+    QB_CUDA(cudaMalloc(&d_coef, sizeof(double2) * kMaxTrans));
+    cudaError_t e = cudaMemcpyAsync(d_coef, coef_reim, sizeof(double2) * S_old->nsites, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(y_new_dev, 0, sizeof(double2) * (size_t)S_new->n, c.stream);
+    if (e == cudaSuccess && S_old->n > 0) {
+        sec_apply_ladder_kernel<<<sgrid(S_old->n), kSBlock, 0, c.stream>>>(S_old->dev, S_new->dev, S_new->d_phase, d_coef, lower ? 1 : 0,
+                                                                            (const double2 *)x_old_dev, (double2 *)y_new_dev);
+        QB_LAUNCH_COUNT();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     cudaFree(d_coef);
     QB_CUDA(e);
     QB_CUDA(cudaGetLastError());

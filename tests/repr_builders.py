@@ -370,6 +370,33 @@ def szq_coefficients(L, q):
     return np.array([cmath.exp(complex(0.0, -Q * x)) / math.sqrt(float(L)) for x in range(L)])
 
 
+def apply_splus(S_old, S_new, coef, x):
+    """The same branch for A = sum_r coef[r] S^+_r (acts on down spins; the new sector has one fewer).  No reference
+    vector pins it directly; tests pin it to apply_sminus through <w, A v> = <A^+ w, v>."""
+    return _apply_ladder(S_old, S_new, coef, x, 1)
+
+
+def _apply_ladder(S_old, S_new, coef, x, digit):
+    u = np.uint64
+    y = np.zeros(S_new.n, dtype=np.complex128)
+    ok = (np.abs(x) >= 2e-12) & (S_old.nu >= 2e-12)
+    rows = np.nonzero(ok)[0]
+    phase = np.conj(np.asarray(S_new.phase))
+    for r in range(S_old.N):
+        act = rows[((S_old.states[rows] >> u(r)) & u(1)) == digit]
+        if act.size == 0:
+            continue
+        s2 = S_old.states[act] ^ (u(1) << u(r))
+        a2, b2 = S_new.unzip(s2)
+        i, ca, cb = S_new.canon(a2, b2)
+        tgt = S_new.index(ca, cb)
+        keep = S_new.nu[tgt] >= 2e-12
+        act, i, tgt = act[keep], i[keep], tgt[keep]
+        val = np.sqrt(S_old.nu[act] / S_new.nu[tgt]) * x[act] * coef[r] * phase[i]
+        np.add.at(y, tgt, val)
+    return y
+
+
 def apply_sminus(S_old, S_new, coef, x):
     """model::moprXvec_repr (src/model.cc:1762-1834), off-diagonal branch, for A = sum_r coef[r] S^-_r on spin-1/2:
     every term lowers one up spin of the old representative; the produced state is brought to its representative in the

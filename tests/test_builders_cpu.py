@@ -202,3 +202,9 @@ def test_sector_sminus_operator_matches_reference_moprXvec(name):
     y = R.apply_sminus(S0, S1, R.szq_coefficients(L, q), z["phi0"])
     assert y.size == z["Aphi0"].size and np.abs(y - z["Aphi0"]).max() < 1e-14
     assert abs(np.linalg.norm(y) - meta["dyn_norm"]) < 1e-13
+    # S^+ with conjugated coefficients is the adjoint map between the two sectors: <w, A v> = <A^+ w, v>
+    rng = np.random.default_rng(2)
+    w = rng.normal(size=S1.n) + 1j * rng.normal(size=S1.n)
+    w[S1.nu == 0] = 0.0
+    up = R.apply_splus(S1, S0, np.conj(R.szq_coefficients(L, q)), w)
+    assert abs(np.vdot(w, y) - np.vdot(up, z["phi0"])) < 1e-13

@@ -204,3 +204,37 @@ def test_unsupported_uses_fail_loudly():
         M.to_dense()
     with pytest.raises(qb.QbgpuError):
         M.download_expanded()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Also first-run-pending (same reason, same xfail): the ladder operators between momentum sectors (sectors.cu:
+# sec_apply_ladder_kernel), against the vectors and Lanczos coefficients the compiled reference produced.
+@pytest.mark.parametrize("name", ["heis16_smq3", "heis12_smq5"])
+def test_sector_ladder_operator_and_dynamic_lanczos_match_the_reference(name):
+    """model::moprXvec_repr, off-diagonal branch (src/model.cc:1762-1834) + measure_repr_dynamic (:1897-1912) for S^-_q:
+    qb_ref heis_chain_smq wrote phi0, S^-_q phi0 (in the sector with one more down spin, momentum k0 - q) and the dnmcs
+    coefficients (tests/golden, oracle/make_golden.py)."""
+    import json
+    import repr_builders as R
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    L, q, k0, maxit = meta["L"], meta["q"], meta["k0"], meta["maxit"]
+    s0, s1 = qb.Sector([L], L // 2, [k0]), qb.Sector([L], L // 2 + 1, [k0 - q])
+    coef = R.szq_coefficients(L, q)
+    y = s0.apply_ladder(s1, coef, z["phi0"], lower=True).to_numpy()
+    assert y.size == z["Aphi0"].size and np.abs(y - z["Aphi0"]).max() < 1e-14
+    H1 = s1.heisenberg(R.chain_bonds(L))
+    hess = np.zeros(2 * maxit)
+    m, norm = qb.measure_repr_dynamic(coef, s0, s1, H1, z["phi0"], maxit, hess, op="s-")
+    assert abs(norm - meta["dyn_norm"]) < 1e-13
+    k = min(m, 10)
+    assert np.abs(hess[maxit:maxit + k] - z["dyn_a"][:k]).max() < 1e-10
+    assert np.abs(hess[:k] - z["dyn_b"][:k]).max() < 1e-10
+    # S^+ with conjugated coefficients is the adjoint map: <w, A v> = <A^+ w, v>  (checked on the CPU restatement too)
+    rng = np.random.default_rng(2)
+    w = rng.normal(size=s1.dim) + 1j * rng.normal(size=s1.dim)
+    w[s1.norms() == 0.0] = 0.0
+    up = s1.apply_ladder(s0, np.conj(coef), w, lower=False).to_numpy()
+    assert abs(np.vdot(w, y) - np.vdot(up, z["phi0"])) <= 1e-12 * max(1.0, abs(np.vdot(w, y)))
+    with pytest.raises(qb.QbgpuError):
+        s0.apply_ladder(s0, coef, z["phi0"])                          # wrong Sz in the target sector

@@ -147,9 +147,15 @@ int qbgpu_dscal(int64_t n, double a, double *x);
  * Same arguments and meaning as the reference templates; `v` etc. are HOST or DEVICE per `where`.
  *
  * qbgpu_lanczos_*: lanczos<T,MAT>(k, np, maxit, m, dim, mat, v, hessenberg, purpose), src/lanczos.cc:134-266,
- *   for k == 0 and purposes "sr_val0", "sr_val1" (phi0 at v+2n) and "dnmcs".  hessenberg[2*maxit]: b in
+ *   for purposes "sr_val0", "sr_val1" (phi0 at v+2n) and "dnmcs".  hessenberg[2*maxit]: b in
  *   [0,maxit), a in [maxit,2maxit).  On return *m = steps performed; v[(m%2)*n] holds v_m and v[((m+1)%2)*n]
- *   holds v_{m-1} like the reference (normalised).
+ *   holds v_{m-1} like the reference (normalised).  k > 0 resumes (qbasis.h:1044-1061): on entry v holds the
+ *   normalised v[k-1], v[k] in those slots and hessenberg a[0..k-1], b[0..k]; the stop rule's counters restart, as in
+ *   the reference's lanczos() without checkpoints.
+ * qbgpu_lanczos_resume_*: the same with the four quantities the reference's checkpoint carries across an
+ *   interruption (src/ckpt.cc, lczs_mlns.dat): stop_state[4] = {cnt_accuE0, accuracy, theta0_prev, theta1_prev}, read
+ *   on entry and updated on return, so that a run cut into pieces stops at the step the uninterrupted run stops at.
+ *   quantum_basis_b200/ckpt.py writes and reads the reference's out_Qckpt/ files around it.
  * qbgpu_eigenvec_cg_*: eigenvec_CG<T,MAT>(dim, maxit, m, mat, E0, accu, v, r, p, pp), src/lanczos.cc:281-341,
  *   entered with *m == 0.
  * qbgpu_energy_scale_*: energy_scale<T,MAT>(dim, mat, v, lo, hi, extend, iters), src/kpm.cc:45-88 (start vector
@@ -162,6 +168,10 @@ int qbgpu_lanczos_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int6
                     double *hessenberg, const char *purpose, int where);
 int qbgpu_lanczos_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v,
                     double *hessenberg, const char *purpose, int where);
+int qbgpu_lanczos_resume_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, double *v,
+                           double *hessenberg, const char *purpose, int where, double *stop_state);
+int qbgpu_lanczos_resume_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v,
+                           double *hessenberg, const char *purpose, int where, double *stop_state);
 int qbgpu_eigenvec_cg_d(qbgpu_matrix_t A, int64_t maxit, int64_t *m, double E0, double *accu,
                         double *v, double *r, double *p, double *pp, int where);
 int qbgpu_eigenvec_cg_z(qbgpu_matrix_t A, int64_t maxit, int64_t *m, const double E0[2], double *accu,

@@ -373,6 +373,22 @@ static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, 
             js.integer("lanczos_steps", m); js.num("lanczos_E0", ritz[0]); js.num("lanczos_seconds", dt);
             if (m > 1) js.num("lanczos_E1_ritz", ritz[1]);
             js.arr("lanczos_b", hess.data(), m + 1); js.arr("lanczos_a", hess.data() + maxit, m);
+        } else if (opt == "--lanczos-ckpt" && a + 3 < argc) {
+            /* the reference's lanczos with its own checkpoints enabled (src/ckpt.cc; out_Qckpt/ under the work directory):
+               called as lanczos(0, NP, maxit, ...) it either starts from vec_randomize(seed=1) and leaves the checkpoint of
+               step NP behind, or -- when out_Qckpt/ already holds a checkpoint, whoever wrote it -- resumes from there */
+            std::string purpose = argv[++a];
+            MKL_INT maxit = atoll(argv[++a]), np = atoll(argv[++a]);
+            std::vector<double> hess(2 * maxit, 0.0), ritz, s;
+            std::vector<T> v(3 * n);
+            qbasis::vec_randomize(n, v.data(), 1);
+            MKL_INT m = 0;
+            qbasis::enable_ckpt = true;
+            qbasis::lanczos(static_cast<MKL_INT>(0), np, maxit, m, n, H, v.data(), hess.data(), purpose);
+            qbasis::enable_ckpt = false;
+            qbasis::hess_eigen(hess.data(), maxit, m, "sr", ritz, s);
+            js.integer("ckpt_steps", m); js.num("ckpt_E0", ritz[0]);
+            js.arr("ckpt_b", hess.data(), m + 1); js.arr("ckpt_a", hess.data() + maxit, m);
         } else if (opt == "--cg" && a + 2 < argc) {
             /* reference eigenvec_CG as called from locate_E0_lanczos (src/model.cc:1209-1218) */
             double E0 = atof(argv[++a]);
@@ -403,7 +419,7 @@ static void usage() {
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
-        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --cg E0 F | --energy-scale ITERS\n");
+        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --energy-scale ITERS\n");
     exit(2);
 }
 

@@ -57,6 +57,8 @@ _SIGS = {
     "qbgpu_zscal": [i64, vp, vp], "qbgpu_dscal": [i64, dbl, vp],
     "qbgpu_lanczos_d": [vp, i64, i64, i64, C.POINTER(i64), vp, vp, C.c_char_p, C.c_int],
     "qbgpu_lanczos_z": [vp, i64, i64, i64, C.POINTER(i64), vp, vp, C.c_char_p, C.c_int],
+    "qbgpu_lanczos_resume_d": [vp, i64, i64, i64, C.POINTER(i64), vp, vp, C.c_char_p, C.c_int, vp],
+    "qbgpu_lanczos_resume_z": [vp, i64, i64, i64, C.POINTER(i64), vp, vp, C.c_char_p, C.c_int, vp],
     "qbgpu_eigenvec_cg_d": [vp, i64, C.POINTER(i64), dbl, C.POINTER(dbl), vp, vp, vp, vp, C.c_int],
     "qbgpu_eigenvec_cg_z": [vp, i64, C.POINTER(i64), vp, C.POINTER(dbl), vp, vp, vp, vp, C.c_int],
     "qbgpu_energy_scale_d": [vp, vp, C.POINTER(dbl), C.POINTER(dbl), dbl, i64, C.c_int],

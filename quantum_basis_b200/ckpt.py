@@ -1,0 +1,242 @@
+"""Checkpoint / restart of the Lanczos loop in the reference's on-disk format (src/ckpt.cc).
+
+The reference writes, after every Lanczos step of a "sr_val*" run with checkpoints enabled, into ``out_Qckpt/``:
+    HessenbergA.dat   a[0..m-1]        HessenbergB.dat   b[0..m]          (vec_disk_write format: int64 n, raw, CRC-32)
+    lanczosV<m-1>.dat, lanczosV<m>.dat the two live vectors               lanczosY0.dat  phi0 (every purpose but "sr_val0")
+    lczs_mlns.dat     int32 cnt_accuE0, double accuracy, theta0_prev, theta1_prev   (the stop rule's memory)
+behind a two-phase commit: ``lczs_updt.Qckpt1`` (the step being written) -> ``*.new`` files -> ``lczs_updt.Qckpt2`` (new
+data complete) -> old files removed, new ones renamed -> both markers removed (ckpt_lanczos_update, src/ckpt.cc:177-292).
+On start-up an interrupted update is rolled forward (Qckpt2 present) or rewound by one step (ckpt_lanczos_init, :13-167).
+
+This module reads and writes exactly those files, so a run of the device loop can be resumed by the reference on a CPU and
+vice versa, and drives `qbgpu_lanczos_resume_*` in pieces of `every` steps (a device-resident loop should not copy two
+vectors to disk per step: SURVEY section 5).  Purposes: "sr_val0", "sr_val1"; for "dnmcs" the reference saves nothing
+(its update has no branch for it), and neither does this.  Host-side only: no device code here.
+"""
+import os
+import struct
+
+import numpy as np
+
+from ._lib import QbgpuError
+from . import csr as _csr
+
+DIRNAME = "out_Qckpt"
+_NEWABLE = ("HessenbergA.dat", "HessenbergB.dat", "lanczosY0.dat", "lanczosY1.dat", "lczs_mlns.dat")
+
+
+def _p(d, name):
+    return os.path.join(d, name)
+
+
+def _rm(path):
+    try:
+        os.remove(path)
+    except FileNotFoundError:
+        pass
+
+
+def _read_marker(path):
+    with open(path, "rb") as f:
+        return struct.unpack("<q", f.read(8))[0]
+
+
+def _vec_len(path):
+    """Element count in the header of a vec_disk_write file (0 when the file is missing or too short)."""
+    try:
+        with open(path, "rb") as f:
+            b = f.read(8)
+        return struct.unpack("<q", b)[0] if len(b) == 8 else 0
+    except FileNotFoundError:
+        return 0
+
+
+def _write_marker(path, m):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<q", int(m)))
+
+
+class _Interrupted(Exception):
+    """Raised by the test hook of lanczos_store to model a crash in the middle of an update."""
+
+
+def lanczos_store(dirpath, m, maxit, dim, v, hessenberg, purpose, stop_state, _crash_after=None):
+    """ckpt_lanczos_update (src/ckpt.cc:177-292) for the "val" purposes.  v: host array holding the reference's columns
+    (v[(m%2)*dim:] = v_m, v[((m-1)%2)*dim:] = v_{m-1}, phi0 at 2*dim for "sr_val1"); hessenberg[2*maxit];
+    stop_state = (cnt_accuE0, accuracy, theta0_prev, theta1_prev).  (_crash_after: "new_files" | "commit" stops there, for
+    the recovery tests.)"""
+    if "val" not in purpose:
+        return                                                            # the reference has no branch for "dnmcs"
+    os.makedirs(dirpath, exist_ok=True)
+    hess = np.asarray(hessenberg, dtype=np.float64)
+    v = np.asarray(v)
+    _rm(_p(dirpath, "lczs_updt.Qckpt1"))
+    _rm(_p(dirpath, "lczs_updt.Qckpt2"))
+    _write_marker(_p(dirpath, "lczs_updt.Qckpt1"), m)
+    _csr.vec_disk_write(_p(dirpath, "HessenbergA.dat.new"), hess[maxit:maxit + m])
+    _csr.vec_disk_write(_p(dirpath, "HessenbergB.dat.new"), hess[:m + 1])
+    if m > 0 and not os.path.exists(_p(dirpath, f"lanczosV{m - 1}.dat")):
+        _csr.vec_disk_write(_p(dirpath, f"lanczosV{m - 1}.dat"), v[((m - 1) % 2) * dim:((m - 1) % 2 + 1) * dim])
+    _csr.vec_disk_write(_p(dirpath, f"lanczosV{m}.dat"), v[(m % 2) * dim:(m % 2 + 1) * dim])
+    if "val0" not in purpose:
+        _csr.vec_disk_write(_p(dirpath, "lanczosY0.dat.new"), v[2 * dim:3 * dim])
+    with open(_p(dirpath, "lczs_mlns.dat.new"), "wb") as f:
+        f.write(struct.pack("<i", int(stop_state[0])))
+        f.write(struct.pack("<ddd", float(stop_state[1]), float(stop_state[2]), float(stop_state[3])))
+    if _crash_after == "new_files":
+        raise _Interrupted()
+    _write_marker(_p(dirpath, "lczs_updt.Qckpt2"), m)                     # from here on the new data are the valid ones
+    if _crash_after == "commit":
+        raise _Interrupted()
+    _rm(_p(dirpath, "HessenbergA.dat"))
+    _rm(_p(dirpath, "HessenbergB.dat"))
+    for name in os.listdir(dirpath):                                      # vectors older than v_{m-1}
+        if name.startswith("lanczosV") and name.endswith(".dat") and name[8:-4].isdigit() and int(name[8:-4]) < m - 1:
+            _rm(_p(dirpath, name))
+    _rm(_p(dirpath, "lanczosY0.dat"))
+    _rm(_p(dirpath, "lanczosY1.dat"))
+    _rm(_p(dirpath, "lczs_mlns.dat"))
+    os.replace(_p(dirpath, "HessenbergA.dat.new"), _p(dirpath, "HessenbergA.dat"))
+    os.replace(_p(dirpath, "HessenbergB.dat.new"), _p(dirpath, "HessenbergB.dat"))
+    if "val0" not in purpose:
+        os.replace(_p(dirpath, "lanczosY0.dat.new"), _p(dirpath, "lanczosY0.dat"))
+    os.replace(_p(dirpath, "lczs_mlns.dat.new"), _p(dirpath, "lczs_mlns.dat"))
+    _rm(_p(dirpath, "lczs_updt.Qckpt1"))
+    _rm(_p(dirpath, "lczs_updt.Qckpt2"))
+
+
+def _recover(dirpath, maxit):
+    """The start-up logic of ckpt_lanczos_init (src/ckpt.cc:37-106): finish or undo an interrupted update; returns k."""
+    q1, q2 = _p(dirpath, "lczs_updt.Qckpt1"), _p(dirpath, "lczs_updt.Qckpt2")
+    if os.path.exists(q1) and os.path.getsize(q1) == 8:
+        k = _read_marker(q1)
+        if os.path.exists(q2):                                            # new data complete: roll forward
+            if not os.path.exists(_p(dirpath, f"lanczosV{k}.dat")):
+                raise QbgpuError(f"checkpoint: lanczosV{k}.dat is missing although the update of step {k} was committed")
+            for name in _NEWABLE:
+                if os.path.exists(_p(dirpath, name + ".new")):
+                    _rm(_p(dirpath, name))
+                    os.replace(_p(dirpath, name + ".new"), _p(dirpath, name))
+            for kk in range(0, k - 1):
+                _rm(_p(dirpath, f"lanczosV{kk}.dat"))
+            _rm(q1)
+            _rm(q2)
+        else:                                                             # rewind
+            # The reference checkpoints every step, so it rewinds ONE step (k - 1).  Written every N steps, the last
+            # committed step is N steps back: it is the one the old HessenbergB.dat describes (b[0..k] = k + 1 numbers).
+            k -= 1
+            if not (os.path.exists(_p(dirpath, f"lanczosV{k}.dat")) and (k == 0 or os.path.exists(_p(dirpath, f"lanczosV{k - 1}.dat")))
+                    and _vec_len(_p(dirpath, "HessenbergB.dat")) == k + 1):
+                k = max(_vec_len(_p(dirpath, "HessenbergB.dat")) - 1, 0)
+                if k > 0 and not (os.path.exists(_p(dirpath, f"lanczosV{k}.dat")) and os.path.exists(_p(dirpath, f"lanczosV{k - 1}.dat"))):
+                    raise QbgpuError(f"checkpoint: cannot rewind to step {k}: its vectors are missing")
+            for name in _NEWABLE:
+                _rm(_p(dirpath, name + ".new"))
+            for name in os.listdir(dirpath):
+                if name.startswith("lanczosV") and name.endswith(".dat") and name[8:-4].isdigit() and int(name[8:-4]) > k:
+                    _rm(_p(dirpath, name))
+            _rm(q1)
+        return k
+    k_bgn = 0
+    while k_bgn < maxit and not os.path.exists(_p(dirpath, f"lanczosV{k_bgn}.dat")):
+        k_bgn += 1
+    if k_bgn == maxit:
+        return 0
+    k = k_bgn
+    while os.path.exists(_p(dirpath, f"lanczosV{k + 1}.dat")):
+        k += 1
+    return k
+
+
+def lanczos_load(dirpath, maxit, dim, dtype, purpose):
+    """ckpt_lanczos_init (src/ckpt.cc:13-167) for the "val" purposes: returns (k, v, hessenberg, stop_state) -- k = 0 and
+    zeroed arrays when there is nothing to resume from.  v has 2 columns ("sr_val0") or 3."""
+    dt = np.dtype(dtype)
+    ncol = 2 if "val0" in purpose else 3
+    v = np.zeros(ncol * dim, dtype=dt)
+    hess = np.zeros(2 * maxit)
+    state = [0, 0.0, 0.0, 0.0]
+    if "val" not in purpose or not os.path.isdir(dirpath):
+        return 0, v, hess, state
+    k = _recover(dirpath, maxit)
+    if k <= 0:
+        return 0, v, hess, state
+
+    def need(name, n, dtp):
+        a = _csr.vec_disk_read(_p(dirpath, name), n, dtp)
+        if a is None:
+            raise QbgpuError(f"checkpoint: {name} is missing or damaged (size, length or CRC-32)")
+        return a
+    v[((k - 1) % 2) * dim:((k - 1) % 2 + 1) * dim] = need(f"lanczosV{k - 1}.dat", dim, dt)
+    v[(k % 2) * dim:(k % 2 + 1) * dim] = need(f"lanczosV{k}.dat", dim, dt)
+    if "val0" not in purpose:
+        v[2 * dim:3 * dim] = need("lanczosY0.dat", dim, dt)
+    with open(_p(dirpath, "lczs_mlns.dat"), "rb") as f:
+        b = f.read()
+    if len(b) != 28:
+        raise QbgpuError("checkpoint: lczs_mlns.dat has the wrong size")
+    state = [struct.unpack("<i", b[:4])[0], *struct.unpack("<ddd", b[4:])]
+    hess[maxit:maxit + k] = need("HessenbergA.dat", k, np.float64)
+    hess[:k + 1] = need("HessenbergB.dat", k + 1, np.float64)
+    return k, v, hess, state
+
+
+def lanczos_clean(dirpath):
+    """ckpt_lanczos_clean (src/ckpt.cc:305-345): remove the Lanczos files of a finished run."""
+    if not os.path.isdir(dirpath):
+        return
+    for name in os.listdir(dirpath):
+        if name in _NEWABLE or (name.startswith("lanczosV") and name.endswith(".dat")) or name.startswith("lczs_updt.Qckpt") \
+                or (name.endswith(".new") and name[:-4] in _NEWABLE):
+            _rm(_p(dirpath, name))
+
+
+def stop_state_from_coefficients(hessenberg, maxit, m, precision=2e-12):
+    """The stop rule's memory after step m, replayed from (a, b) alone (src/lanczos.cc:228-248): what lczs_mlns.dat would
+    hold.  Host-side helper for writing a checkpoint from a run that did not track it (O(m^2) per call)."""
+    from scipy.linalg import eigh_tridiagonal
+    hess = np.asarray(hessenberg, dtype=np.float64)
+    cnt, accuracy, t0, t1 = 0, 0.0, 0.0, 0.0
+    for j in range(2, m + 1):
+        w, s = eigh_tridiagonal(hess[maxit:maxit + j], hess[1:j])
+        if j > 3:
+            accuracy = abs(hess[j] * s[j - 1, 0])
+            cnt = cnt + 1 if abs((w[0] - t0) / w[0]) < precision else 0
+            if cnt > 15 and accuracy < precision:
+                break                                                     # the reference stops before updating theta*_prev
+        t0, t1 = w[0], w[1]
+    return [cnt, accuracy, t0, t1]
+
+
+def lanczos_checkpointed(mat, v, hessenberg, purpose, maxit, every=50, dirpath=DIRNAME, max_chunks=None):
+    """lanczos(0, maxit-1, maxit, ...) with the reference's checkpoints, written every `every` steps: resumes from
+    `dirpath` when it holds a checkpoint (its vectors and coefficients replace the caller's), otherwise starts from v[0:dim].
+    v: host array with 2 ("sr_val0") or 3 columns; hessenberg[2*maxit].  Returns the final step count m.
+    `max_chunks` stops after that many pieces, leaving the checkpoint on disk (an interruption, for tests)."""
+    import ctypes as C
+    from ._lib import check, lib, QBGPU_HOST
+    if purpose not in ("sr_val0", "sr_val1"):
+        raise QbgpuError("checkpointed Lanczos: purpose must be sr_val0 or sr_val1")
+    dim = mat.dim
+    k, v_ck, h_ck, state = lanczos_load(dirpath, maxit, dim, mat.dtype, purpose)
+    if k > 0:
+        v[:v_ck.size] = v_ck
+        hessenberg[:] = h_ck
+    st = (C.c_double * 4)(*[float(x) for x in state])
+    f = lib().qbgpu_lanczos_resume_z if mat.is_complex else lib().qbgpu_lanczos_resume_d
+    m = C.c_int64(k)
+    chunks = 0
+    while True:
+        np_ = min(every, maxit - 1 - k)
+        if np_ <= 0:
+            break
+        check(f(mat.handle, k, np_, maxit, C.byref(m), C.c_void_p(v.ctypes.data), C.c_void_p(hessenberg.ctypes.data),
+                purpose.encode(), QBGPU_HOST, st))
+        done = m.value < k + np_ or (int(st[0]) > 15 and st[1] < _csr.lanczos_precision)
+        if m.value > k:
+            lanczos_store(dirpath, m.value, maxit, dim, v, hessenberg, purpose, list(st))
+        k = m.value
+        chunks += 1
+        if done or (max_chunks is not None and chunks >= max_chunks):
+            break
+    return k

@@ -136,8 +136,12 @@ static int check_single(const qbgpu_matrix *A, bool cplx)
 
 // ------------------------------------------------------------------------------------------------- lanczos
 // state layout: see include/qbgpu.h (lanczos_step_*).
+// k > 0 resumes (src/lanczos.cc:144-148, qbasis.h:1044-1061): v holds the normalised v[k-1], v[k] in their slots, hess
+// holds a[0..k-1] and b[0..k].  stop_state (optional, in/out) = {cnt_accuE0, accuracy, theta0_prev, theta1_prev}: what the
+// reference's checkpoint carries across an interruption (ckpt.cc: lczs_mlns.dat); without it a resumed run restarts the
+// stop rule's counters, like the reference's lanczos() called with k > 0 and checkpoints disabled.
 static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
-                        double *hess, const char *purpose, int where, bool stop_on_breakdown = true)
+                        double *hess, const char *purpose, int where, bool stop_on_breakdown = true, double *stop_state = nullptr)
 {
     QB_TRY(ensure_init());
     QB_TRY(check_single(A, cplx));
@@ -146,10 +150,10 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     const bool is_val1 = strstr(purpose, "val1") != nullptr;
     const bool is_dn = strcmp(purpose, "dnmcs") == 0;
     if (!is_val && !is_dn) return fail(QBGPU_ERR_ARG, "lanczos: purpose must be sr_val0, sr_val1 or dnmcs");
-    if (k != 0) return fail(QBGPU_ERR_STATE, "lanczos: resuming from k > 0 (checkpoint restart) is not supported");
     const int64_t mm = k + np;
-    if (!(mm < maxit && np >= 0)) return fail(QBGPU_ERR_ARG, "lanczos: need k + np < maxit");      // src/lanczos.cc:147
+    if (!(mm < maxit && k >= 0 && np >= 0)) return fail(QBGPU_ERR_ARG, "lanczos: need k >= 0, np >= 0 and k + np < maxit");   // src/lanczos.cc:147
     *m_out = k;
+    if (stop_state && is_val && (int)stop_state[0] > 15 && stop_state[1] < kLanczosPrecision) return QBGPU_OK;   // :149 (already converged)
     if (np == 0) return QBGPU_OK;                                                                  // :150
     Context &c = ctx();
     const int64_t n = A->n;
@@ -161,7 +165,7 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     if (where == QBGPU_HOST) {
         QB_TRY(dv.alloc(vb * n * nvec));
         U = (char *)dv.p;
-        QB_CUDA(cudaMemcpyAsync(U, v, vb * n, cudaMemcpyHostToDevice, c.stream));
+        QB_CUDA(cudaMemcpyAsync(U, v, vb * n * (k > 0 ? 2 : 1), cudaMemcpyHostToDevice, c.stream));    // a resumed run needs both live vectors
         if (is_val1) QB_CUDA(cudaMemcpyAsync(U + 2 * vb * n, (char *)v + 2 * vb * n, vb * n, cudaMemcpyHostToDevice, c.stream));
     } else if (where == QBGPU_DEVICE) {
         U = (char *)v;
@@ -172,16 +176,21 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     QB_TRY(dhess.alloc(sizeof(double) * 2 * maxit));
     double *state = (double *)dstate.p;
     double *b_dev = (double *)dhess.p, *a_dev = b_dev + maxit;
-    const double init[8] = {1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // state = {scale of ux, scale of uz, b_prev, ...}: both live vectors of a resumed run are normalised and b_prev = b[k]
+    const double init[8] = {1.0, k > 0 ? 1.0 : 0.0, k > 0 ? hess[k] : 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     QB_CUDA(cudaMemcpyAsync(state, init, sizeof init, cudaMemcpyHostToDevice, c.stream));
     QB_CUDA(cudaMemsetAsync(dhess.p, 0, sizeof(double) * 2 * maxit, c.stream));
     QB_CUDA(cudaStreamSynchronize(c.stream));              // `init` is on the host stack
-    for (int64_t j = 0; j < 2 * maxit; j++) hess[j] = 0.0; // the caller's array as the reference leaves it (zeros beyond m)
+    // the caller's array as the reference leaves it: zeros beyond what is known (b[0..k], a[0..k-1] are kept on a resume)
+    for (int64_t j = (k > 0 ? k + 1 : 0); j < maxit; j++) hess[j] = 0.0;
+    for (int64_t j = maxit + k; j < 2 * maxit; j++) hess[j] = 0.0;
 
     std::vector<double> ritz(mm + 1);
-    int cnt_accuE0 = 0;
-    double theta0_prev = 0.0;
-    int64_t m = 0;
+    int cnt_accuE0 = stop_state ? (int)stop_state[0] : 0;
+    double accuracy = stop_state ? stop_state[1] : 0.0;
+    double theta0_prev = stop_state ? stop_state[2] : (k > 0 && is_val ? tridiag_smallest(hess, maxit, k) : 0.0);
+    bool converged = false;
+    int64_t m = k;
     // QBGPU_VERBOSE: per-phase device time of the loop (events around the three passes) and host time of the stop rule
     const bool prof = getenv("QBGPU_VERBOSE") != nullptr;
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -243,7 +252,8 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
                 if (cnt_accuE0 > 15) {                      // only now is the residual estimate |b_m s_{m-1}| needed
                     double s_last = 0.0;
                     if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
-                    if (fabs(hess[m] * s_last) < kLanczosPrecision) break;
+                    accuracy = fabs(hess[m] * s_last);
+                    if (accuracy < kLanczosPrecision) { converged = true; break; }
                 }
             }
             theta0_prev = theta0;
@@ -255,6 +265,17 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
         for (auto &e : pe) cudaEventDestroy(e);
     }
     *m_out = m;
+    if (stop_state && is_val && m > k) {
+        // what ckpt_lanczos_update would save at this step (src/lanczos.cc:231-248): the residual estimate of step m and,
+        // unless the run stopped on the rule (the reference breaks before updating them), this step's Ritz values
+        double s_last = 0.0;
+        std::vector<double> rz(m + 1);
+        if (hess_eigen_host(hess, maxit, m, rz.data(), nullptr, &s_last)) return fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge");
+        stop_state[0] = (double)cnt_accuE0;
+        if (m > 3) stop_state[1] = fabs(hess[m] * s_last);
+        if (!converged) { stop_state[2] = rz[0]; stop_state[3] = m > 1 ? rz[1] : 0.0; }
+        (void)accuracy;
+    }
     // hand the two live vectors back normalised, in the reference's slots: v_m at (m%2), v_{m-1} at ((m-1)%2)
     QB_TRY(scale_copy(n, cplx, state + 0, 1.0, Ubuf[m % 2], Ubuf[m % 2]));
     QB_TRY(scale_copy(n, cplx, state + 1, 1.0, Ubuf[(m - 1) % 2], Ubuf[(m - 1) % 2]));
@@ -480,17 +501,17 @@ static int native_end(NativeRun &N, qbgpu_matrix *A, bool cplx, void *v, unsigne
 }
 
 static int lanczos_native(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
-                          double *hess, const char *purpose, int where)
+                          double *hess, const char *purpose, int where, double *stop_state)
 {
     QB_TRY(ensure_init());
     QB_TRY(check_single(A, cplx));
     if (!m_out || !v || !hess || !purpose) return fail(QBGPU_ERR_ARG, "lanczos: null argument");
-    if (np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);      // nothing to do / argument errors
+    if (np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where, true, stop_state);   // nothing to do / argument errors
     const bool val1 = strstr(purpose, "val1") != nullptr;
     const int nvec = val1 ? 3 : 2;
     NativeRun N;
-    QB_TRY(native_begin(N, A, cplx, v, nvec, val1 ? 0x5u : 0x1u, where, true));
-    QB_TRY(lanczos_impl(&N.R, N.loop_cplx, k, np, maxit, m_out, N.work.p, hess, purpose, QBGPU_DEVICE));
+    QB_TRY(native_begin(N, A, cplx, v, nvec, (val1 ? 0x5u : 0x1u) | (k > 0 ? 0x2u : 0u), where, true));
+    QB_TRY(lanczos_impl(&N.R, N.loop_cplx, k, np, maxit, m_out, N.work.p, hess, purpose, QBGPU_DEVICE, true, stop_state));
     return native_end(N, A, cplx, v, 0x3u, nvec, where);    // the two live vectors, like the reference's slots
 }
 
@@ -558,10 +579,11 @@ static int kpm_native(qbgpu_matrix *A, bool cplx, const void *phi, double lo, do
 }
 
 static int lanczos_dispatch(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64_t maxit, int64_t *m_out, void *v,
-                            double *hess, const char *purpose, int where)
+                            double *hess, const char *purpose, int where, double *stop_state = nullptr)
 {
-    if (A && A->perm) return lanczos_native(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);
-    if (!A || !real_mode_enabled(A, cplx) || !v || !purpose || np <= 0) return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where);
+    if (A && A->perm) return lanczos_native(A, cplx, k, np, maxit, m_out, v, hess, purpose, where, stop_state);
+    if (!A || !real_mode_enabled(A, cplx) || !v || !purpose || np <= 0 || k < 0)
+        return lanczos_impl(A, cplx, k, np, maxit, m_out, v, hess, purpose, where, true, stop_state);
     QB_TRY(ensure_init());
     Context &c = ctx();
     const int64_t n = A->n;
@@ -572,24 +594,26 @@ static int lanczos_dispatch(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, i
     if (where == QBGPU_HOST) {
         QB_TRY(dc.alloc(16 * n * nvec));
         Uc = (char *)dc.p;
-        QB_CUDA(cudaMemcpyAsync(Uc, v, 16 * n, cudaMemcpyHostToDevice, c.stream));
+        QB_CUDA(cudaMemcpyAsync(Uc, v, 16 * n * (k > 0 ? 2 : 1), cudaMemcpyHostToDevice, c.stream));   // a resumed run has two live vectors
         if (val1) QB_CUDA(cudaMemcpyAsync(Uc + 32 * n, (char *)v + 32 * n, 16 * n, cudaMemcpyHostToDevice, c.stream));
     } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
-    bool real0 = false, real2 = true;
+    bool real0 = false, real1 = true, real2 = true;
     QB_TRY(is_all_real(n, Uc, &real0));
+    if (k > 0) QB_TRY(is_all_real(n, Uc + 16 * n, &real1));
     if (val1) QB_TRY(is_all_real(n, Uc + 32 * n, &real2));
     int rc;
-    if (real0 && real2) {
+    if (real0 && real1 && real2) {
         QB_TRY(dr.alloc(8 * n * nvec));
         double *Ur = (double *)dr.p;
         QB_TRY(vec_take_real(n, Uc, Ur));
+        if (k > 0) QB_TRY(vec_take_real(n, Uc + 16 * n, Ur + n));
         if (val1) QB_TRY(vec_take_real(n, Uc + 32 * n, Ur + 2 * n));
         qbgpu_matrix R = *A;                               // same arrays, fp64 vectors
         R.api_complex = false;
-        rc = lanczos_impl(&R, false, k, np, maxit, m_out, Ur, hess, purpose, QBGPU_DEVICE);
+        rc = lanczos_impl(&R, false, k, np, maxit, m_out, Ur, hess, purpose, QBGPU_DEVICE, true, stop_state);
         if (rc == QBGPU_OK) { QB_TRY(vec_put_real(n, Ur, Uc)); QB_TRY(vec_put_real(n, Ur + n, Uc + 16 * n)); }
     } else {
-        rc = lanczos_impl(A, true, k, np, maxit, m_out, Uc, hess, purpose, QBGPU_DEVICE);
+        rc = lanczos_impl(A, true, k, np, maxit, m_out, Uc, hess, purpose, QBGPU_DEVICE, true, stop_state);
     }
     if (rc == QBGPU_OK && where == QBGPU_HOST) QB_CUDA(cudaMemcpyAsync(v, Uc, 32 * n, cudaMemcpyDeviceToHost, c.stream));
     QB_CUDA(cudaStreamSynchronize(c.stream));
@@ -703,6 +727,11 @@ int qbgpu_lanczos_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int6
 { return lanczos_dispatch(A, false, k, np, maxit, m, v, hess, purpose, where); }
 int qbgpu_lanczos_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v, double *hess, const char *purpose, int where)
 { return lanczos_dispatch(A, true, k, np, maxit, m, v, hess, purpose, where); }
+
+int qbgpu_lanczos_resume_d(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, double *v, double *hess, const char *purpose, int where, double *stop_state)
+{ return lanczos_dispatch(A, false, k, np, maxit, m, v, hess, purpose, where, stop_state); }
+int qbgpu_lanczos_resume_z(qbgpu_matrix_t A, int64_t k, int64_t np, int64_t maxit, int64_t *m, void *v, double *hess, const char *purpose, int where, double *stop_state)
+{ return lanczos_dispatch(A, true, k, np, maxit, m, v, hess, purpose, where, stop_state); }
 
 int qbgpu_eigenvec_cg_d(qbgpu_matrix_t A, int64_t maxit, int64_t *m, double E0, double *accu, double *v, double *r, double *p, double *pp, int where)
 { return cg_dispatch(A, false, maxit, m, make_double2(E0, 0.0), accu, v, r, p, pp, where); }

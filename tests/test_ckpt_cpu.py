@@ -1,0 +1,156 @@
+"""Checkpoint compatibility with the reference (src/ckpt.cc) -- CPU tests, no GPU.
+
+quantum_basis_b200/ckpt.py reads and writes the reference's out_Qckpt/ files.  Both directions are run against the
+compiled, unmodified reference (oracle/_ref/qb_ref --lanczos-ckpt: the reference's own lanczos() with enable_ckpt = true):
+  * the reference stops after 20 steps -> ckpt.lanczos_load reads its files -> a numpy restatement of the loop continues
+    to the reference's own stopping step and E0;
+  * the oracle runs 25 steps -> ckpt.lanczos_store writes the files -> the REFERENCE resumes from them and arrives at the
+    step count, E0 and coefficients of its uninterrupted run (tests/golden/heis12_full.npz).
+The device loop that sits between load and store in production (qbgpu_lanczos_resume_*) is covered by the GPU tests.
+"""
+import os
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+from quantum_basis_b200 import ckpt
+
+MAXIT = 200
+PREC = 2e-12
+
+
+@pytest.fixture(scope="module")
+def case(oracle):
+    if not oracle.have_qb_ref():
+        pytest.skip("oracle/_ref/qb_ref is not built (needs /root/reference at build time)")
+    A, meta, ex = oracle.load_golden("heis12_full")
+    work = tempfile.mkdtemp(prefix="qb_ckpt_")
+    path = os.path.join(work, "A.qbcsr")
+    oracle.write_qbcsr(path, A)
+    yield A, meta, ex, work, path
+    shutil.rmtree(work, ignore_errors=True)
+
+
+def _numpy_resume(oracle, A, k, v, hess, state, maxit):
+    """The reference's loop (src/lanczos.cc:193-264, purpose sr_val0) continued from step k on host arrays."""
+    n = A.dim
+    cnt, accuracy, t0, t1 = int(state[0]), state[1], state[2], state[3]
+    m = k
+    col = lambda j: v[(j % 2) * n:(j % 2 + 1) * n]   # noqa: E731
+    if cnt > 15 and accuracy < PREC:
+        return m
+    while m < maxit - 1:
+        m += 1
+        w = -hess[m - 1] * col(m - 2) + oracle.spmv(A, col(m - 1).copy())
+        hess[maxit + m - 1] = np.vdot(col(m - 1), w).real
+        w = w - hess[maxit + m - 1] * col(m - 1)
+        hess[m] = np.linalg.norm(w)
+        col(m)[:] = w / hess[m]
+        if abs(hess[m]) < PREC:
+            break
+        ritz, s = oracle.hess_eigen(hess, maxit, m)
+        if m > 3:
+            accuracy = abs(hess[m] * s[m - 1, 0])
+            cnt = cnt + 1 if abs((ritz[0] - t0) / ritz[0]) < PREC else 0
+            if cnt > 15 and accuracy < PREC:
+                break
+        t0, t1 = ritz[0], ritz[1]
+    return m
+
+
+def test_resume_from_a_checkpoint_written_by_the_reference(oracle, case):
+    A, meta, ex, work, path = case
+    n = A.dim
+    w = os.path.join(work, "ref_writes")
+    r = oracle.run_qb_ref(["file_z", path, "--lanczos-ckpt", "sr_val0", MAXIT, 20], workdir=w)
+    assert r["ckpt_steps"] == 20
+    d = os.path.join(w, ckpt.DIRNAME)
+    k, v, hess, state = ckpt.lanczos_load(d, MAXIT, n, np.complex128, "sr_val0")
+    assert k == 20
+    assert np.array_equal(hess[MAXIT:MAXIT + 20], np.asarray(r["ckpt_a"])) and np.array_equal(hess[:21], np.asarray(r["ckpt_b"]))
+    assert np.abs(hess[MAXIT:MAXIT + 20] - ex["lanczos_a"][:20]).max() < 1e-12
+    vk, vk1 = v[(k % 2) * n:(k % 2 + 1) * n], v[((k - 1) % 2) * n:((k - 1) % 2 + 1) * n]
+    assert abs(np.linalg.norm(vk) - 1) < 1e-12 and abs(np.linalg.norm(vk1) - 1) < 1e-12 and abs(np.vdot(vk1, vk)) < 1e-10
+    # the stop rule's memory (lczs_mlns.dat) against a replay from the coefficients alone
+    replay = ckpt.stop_state_from_coefficients(hess, MAXIT, k)
+    assert state[0] == replay[0] and abs(state[2] - replay[2]) < 1e-10 and abs(state[3] - replay[3]) < 1e-10
+    assert abs(state[1] - replay[1]) <= 1e-6 * abs(replay[1]) + 1e-14
+    m = _numpy_resume(oracle, A, k, v, hess, state, MAXIT)
+    ritz, _ = oracle.hess_eigen(hess, MAXIT, m)
+    assert m == meta["lanczos_steps"]                                  # stops where the uninterrupted reference run stops
+    assert abs(ritz[0] - meta["lanczos_E0"]) <= 1e-10 * abs(meta["lanczos_E0"])
+
+
+def test_the_reference_resumes_from_a_checkpoint_written_here(oracle, case):
+    A, meta, ex, work, path = case
+    n = A.dim
+    k = 25
+    m, a, b, vbuf = oracle.lanczos(A, oracle.vec_randomize(n, 1), maxit=k + 1)     # exactly k steps
+    assert m == k
+    hess = np.zeros(2 * MAXIT)
+    hess[MAXIT:MAXIT + k] = a
+    hess[:k + 1] = b
+    w = os.path.join(work, "we_write")
+    d = os.path.join(w, ckpt.DIRNAME)
+    ckpt.lanczos_store(d, k, MAXIT, n, np.asarray(vbuf)[:2 * n], hess, "sr_val0", ckpt.stop_state_from_coefficients(hess, MAXIT, k))
+    assert sorted(os.listdir(d)) == ["HessenbergA.dat", "HessenbergB.dat", f"lanczosV{k - 1}.dat", f"lanczosV{k}.dat", "lczs_mlns.dat"]
+    r = oracle.run_qb_ref(["file_z", path, "--lanczos-ckpt", "sr_val0", MAXIT, MAXIT - 1], workdir=w)
+    assert r["ckpt_steps"] == meta["lanczos_steps"]
+    assert abs(r["ckpt_E0"] - meta["lanczos_E0"]) <= 1e-10 * abs(meta["lanczos_E0"])
+    assert np.abs(np.asarray(r["ckpt_a"])[:30] - ex["lanczos_a"][:30]).max() < 1e-9
+    # and a run the reference finished is recognised as finished: nothing left to do
+    k2, v2, h2, st2 = ckpt.lanczos_load(d, MAXIT, n, np.complex128, "sr_val0")
+    assert k2 == meta["lanczos_steps"] and st2[0] > 15 and st2[1] < PREC
+    assert _numpy_resume(oracle, A, k2, v2, h2, st2, MAXIT) == k2
+
+
+@pytest.mark.parametrize("every", [1, 7])
+@pytest.mark.parametrize("crash", ["new_files", "commit"])
+def test_an_interrupted_update_is_rolled_forward_or_rewound(oracle, case, every, crash):
+    """Two-phase commit (src/ckpt.cc:37-106): a crash before the commit marker rewinds to the last committed step (one step
+    back for the reference's every-step checkpoints, `every` steps back here), a crash after it rolls forward."""
+    A, meta, ex, work, path = case
+    n = A.dim
+    d = tempfile.mkdtemp(prefix="qb_ckpt_crash_")
+    try:
+        k1, k2 = 12, 12 + every
+        states = {}
+        for k in (k1, k2):
+            m, a, b, vbuf = oracle.lanczos(A, oracle.vec_randomize(n, 1), maxit=k + 1)
+            hess = np.zeros(2 * MAXIT); hess[MAXIT:MAXIT + k] = a; hess[:k + 1] = b
+            states[k] = (np.asarray(vbuf)[:2 * n].copy(), hess)
+        st = lambda k: ckpt.stop_state_from_coefficients(states[k][1], MAXIT, k)   # noqa: E731
+        ckpt.lanczos_store(d, k1, MAXIT, n, states[k1][0], states[k1][1], "sr_val0", st(k1))
+        with pytest.raises(ckpt._Interrupted):
+            ckpt.lanczos_store(d, k2, MAXIT, n, states[k2][0], states[k2][1], "sr_val0", st(k2), _crash_after=crash)
+        k, v, hess, state = ckpt.lanczos_load(d, MAXIT, n, np.complex128, "sr_val0")
+        want = k2 if crash == "commit" else k1
+        assert k == want
+        assert np.array_equal(hess, states[want][1])
+        for j in (k, k - 1):
+            assert np.array_equal(v[(j % 2) * n:(j % 2 + 1) * n], states[want][0][(j % 2) * n:(j % 2 + 1) * n])
+        left = sorted(os.listdir(d))
+        assert left == sorted(["HessenbergA.dat", "HessenbergB.dat", f"lanczosV{k - 1}.dat", f"lanczosV{k}.dat", "lczs_mlns.dat"])
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_damaged_files_are_refused(oracle, case):
+    A, meta, ex, work, path = case
+    n = A.dim
+    d = tempfile.mkdtemp(prefix="qb_ckpt_bad_")
+    try:
+        m, a, b, vbuf = oracle.lanczos(A, oracle.vec_randomize(n, 1), maxit=9)
+        hess = np.zeros(2 * MAXIT); hess[MAXIT:MAXIT + 8] = a; hess[:9] = b
+        ckpt.lanczos_store(d, 8, MAXIT, n, np.asarray(vbuf)[:2 * n], hess, "sr_val0", [0, 0.0, 0.0, 0.0])
+        with open(os.path.join(d, "lanczosV8.dat"), "r+b") as f:
+            f.seek(100); f.write(b"\x00\x01\x02\x03")                 # CRC-32 no longer matches
+        with pytest.raises(ckpt.QbgpuError):
+            ckpt.lanczos_load(d, MAXIT, n, np.complex128, "sr_val0")
+        ckpt.lanczos_clean(d)
+        assert ckpt.lanczos_load(d, MAXIT, n, np.complex128, "sr_val0")[0] == 0
+        assert ckpt.lanczos_load(os.path.join(d, "nowhere"), MAXIT, n, np.complex128, "dnmcs")[0] == 0
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

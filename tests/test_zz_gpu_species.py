@@ -238,3 +238,54 @@ def test_sector_ladder_operator_and_dynamic_lanczos_match_the_reference(name):
     assert abs(np.vdot(w, y) - np.vdot(up, z["phi0"])) <= 1e-12 * max(1.0, abs(np.vdot(w, y)))
     with pytest.raises(qb.QbgpuError):
         s0.apply_ladder(s0, coef, z["phi0"])                          # wrong Sz in the target sector
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Also first-run-pending: resuming the device Lanczos loop (k > 0, qbgpu_lanczos_resume_*) and the reference-format
+# checkpoints around it (quantum_basis_b200/ckpt.py; the file protocol itself is covered on the CPU by test_ckpt_cpu.py).
+def test_lanczos_resume_and_checkpoints(oracle, tmp_path):
+    import ctypes as C
+    from quantum_basis_b200 import ckpt
+    A, meta, ex = oracle.load_golden("heis12_full")
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    n, maxit = A.dim, 200
+    # uninterrupted
+    v0, h0 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
+    v0[:n] = oracle.vec_randomize(n, 1)
+    m0 = qb.lanczos(0, maxit - 1, maxit, n, M, v0, h0, "sr_val0")
+    assert m0 == meta["lanczos_steps"]
+    # cut in two with the plain entry point: same coefficients; the stop rule restarts its counters, so it may run longer
+    v1, h1 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
+    v1[:n] = oracle.vec_randomize(n, 1)
+    assert qb.lanczos(0, 20, maxit, n, M, v1, h1, "sr_val0") == 20
+    m1 = qb.lanczos(20, maxit - 1 - 20, maxit, n, M, v1, h1, "sr_val0")
+    assert m1 >= m0 and np.abs(h1[maxit:maxit + 30] - h0[maxit:maxit + 30]).max() < 1e-11 and np.abs(h1[:30] - h0[:30]).max() < 1e-11
+    # cut in pieces WITH the stop rule's memory: stops at the same step
+    L = qb.lib()
+    v2, h2 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
+    v2[:n] = oracle.vec_randomize(n, 1)
+    st, m, k = (C.c_double * 4)(0, 0, 0, 0), C.c_int64(0), 0
+    while True:
+        _lib.check(L.qbgpu_lanczos_resume_z(M.handle, k, min(13, maxit - 1 - k), maxit, C.byref(m), C.c_void_p(v2.ctypes.data),
+                                            C.c_void_p(h2.ctypes.data), b"sr_val0", 0, st))
+        if m.value < k + 13:
+            break
+        k = m.value
+    assert m.value == m0
+    assert abs(qb.hess_eigen(h2, maxit, m.value)[0][0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+    # the reference's files around it: interrupted after two pieces, then resumed; then resumed from the REFERENCE's checkpoint
+    d = str(tmp_path / ckpt.DIRNAME)
+    v3, h3 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
+    v3[:n] = oracle.vec_randomize(n, 1)
+    assert ckpt.lanczos_checkpointed(M, v3, h3, "sr_val0", maxit, every=10, dirpath=d, max_chunks=2) == 20
+    v4, h4 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)          # a fresh process would start like this
+    assert ckpt.lanczos_checkpointed(M, v4, h4, "sr_val0", maxit, every=10, dirpath=d) == m0
+    assert abs(qb.hess_eigen(h4, maxit, m0)[0][0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+    if oracle.have_qb_ref():
+        w = str(tmp_path / "ref")
+        path = str(tmp_path / "A.qbcsr")
+        oracle.write_qbcsr(path, A)
+        oracle.run_qb_ref(["file_z", path, "--lanczos-ckpt", "sr_val0", maxit, 20], workdir=w)
+        v5, h5 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
+        assert ckpt.lanczos_checkpointed(M, v5, h5, "sr_val0", maxit, every=50, dirpath=os.path.join(w, ckpt.DIRNAME)) == m0
+        assert abs(qb.hess_eigen(h5, maxit, m0)[0][0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])

@@ -156,8 +156,9 @@ int qbgpu_dscal(int64_t n, double a, double *x);
  *   interruption (src/ckpt.cc, lczs_mlns.dat): stop_state[4] = {cnt_accuE0, accuracy, theta0_prev, theta1_prev}, read
  *   on entry and updated on return, so that a run cut into pieces stops at the step the uninterrupted run stops at.
  *   quantum_basis_b200/ckpt.py writes and reads the reference's out_Qckpt/ files around it.
- * qbgpu_eigenvec_cg_*: eigenvec_CG<T,MAT>(dim, maxit, m, mat, E0, accu, v, r, p, pp), src/lanczos.cc:281-341,
- *   entered with *m == 0.
+ * qbgpu_eigenvec_cg_*: eigenvec_CG<T,MAT>(dim, maxit, m, mat, E0, accu, v, r, p, pp), src/lanczos.cc:281-341;
+ *   *m == 0 starts from the guess in v, *m > 0 continues from (v, r, p) of step m (what the reference's CG checkpoint
+ *   holds: CG_{V,R,P}<m>.dat, src/ckpt.cc:345-480); loops while *m < maxit.
  * qbgpu_energy_scale_*: energy_scale<T,MAT>(dim, mat, v, lo, hi, extend, iters), src/kpm.cc:45-88 (start vector
  *   vec_randomize(seed=1) drawn inside, as the reference does).
  * qbgpu_kpm_moments_*: NEW (the reference has no Chebyshev code): mu_k = <phi|T_k((H-c)/s)|phi>, k < nmom,

@@ -399,6 +399,19 @@ static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, 
             qbasis::eigenvec_CG(n, maxit, m, H, static_cast<T>(E0), accu, v.data() + 2 * n, v.data(), v.data() + n, v.data() + 3 * n);
             js.integer("cg_steps", m); js.num("cg_accuracy", accu); js.num("cg_seconds", now_s() - t0);
             dump_vec(argv[++a], v.data() + 2 * n, sizeof(T) * n);
+        } else if (opt == "--cg-ckpt" && a + 3 < argc) {
+            /* the reference's eigenvec_CG with its checkpoints enabled (src/ckpt.cc:345-480): runs until step MAXIT (leaving
+               CG_{V,R,P}<MAXIT>.dat in out_Qckpt/) or to convergence, starting from vec_randomize(seed=1) or from whatever CG
+               checkpoint out_Qckpt/ holds */
+            double E0 = atof(argv[++a]);
+            MKL_INT maxit = atoll(argv[++a]), m = 0; double accu = 0.0;
+            std::vector<T> v(4 * n);
+            qbasis::vec_randomize(n, v.data() + 2 * n, 1);
+            qbasis::enable_ckpt = true;
+            qbasis::eigenvec_CG(n, maxit, m, H, static_cast<T>(E0), accu, v.data() + 2 * n, v.data(), v.data() + n, v.data() + 3 * n);
+            qbasis::enable_ckpt = false;
+            js.integer("cgck_steps", m); js.num("cgck_accuracy", accu);
+            dump_vec(argv[++a], v.data() + 2 * n, sizeof(T) * n);
         } else if (opt == "--energy-scale" && a + 1 < argc) {
             /* reference energy_scale (src/kpm.cc:45-88); start vector = vec_randomize default seed */
             MKL_INT iters = atoll(argv[++a]);
@@ -419,7 +432,7 @@ static void usage() {
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
-        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --energy-scale ITERS\n");
+        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --cg-ckpt E0 MAXIT F | --energy-scale ITERS\n");
     exit(2);
 }
 
@@ -444,6 +457,7 @@ int main(int argc, char **argv)
         const std::string &s = av[i];
         if ((s == "--dump" || s == "file_z" || s == "file_d") && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
         if ((s == "--mv" || s == "--cg" || s == "--vec-write") && i + 2 < argc) av[i + 2] = absolutise(av[i + 2]);
+        if (s == "--cg-ckpt" && i + 3 < argc) av[i + 3] = absolutise(av[i + 3]);
         if (s == "--dump-vecs" && i + 1 < argc) av[i + 1] = absolutise(av[i + 1]);
     }
     std::vector<char *> cargv;

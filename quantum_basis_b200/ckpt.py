@@ -11,7 +11,9 @@ On start-up an interrupted update is rolled forward (Qckpt2 present) or rewound 
 This module reads and writes exactly those files, so a run of the device loop can be resumed by the reference on a CPU and
 vice versa, and drives `qbgpu_lanczos_resume_*` in pieces of `every` steps (a device-resident loop should not copy two
 vectors to disk per step: SURVEY section 5).  Purposes: "sr_val0", "sr_val1"; for "dnmcs" the reference saves nothing
-(its update has no branch for it), and neither does this.  Host-side only: no device code here.
+(its update has no branch for it), and neither does this.  The conjugate-gradient loop's checkpoints (CG_{V,R,P}<m>.dat,
+src/ckpt.cc:345-520) are handled the same way around `qbgpu_eigenvec_cg_*` entered with m > 0.  Host-side only: no device
+code here.
 """
 import os
 import struct
@@ -189,6 +191,94 @@ def lanczos_clean(dirpath):
         if name in _NEWABLE or (name.startswith("lanczosV") and name.endswith(".dat")) or name.startswith("lczs_updt.Qckpt") \
                 or (name.endswith(".new") and name[:-4] in _NEWABLE):
             _rm(_p(dirpath, name))
+
+
+# ------------------------------------------------------------------------------------------------------------ CG
+def cg_store(dirpath, m, v, r, p):
+    """ckpt_CG_update (src/ckpt.cc:430-476): CG_{V,R,P}<m>.dat behind the markers CG_updt.Qckpt1/2; the files of the
+    previous step are removed once the new ones are complete."""
+    os.makedirs(dirpath, exist_ok=True)
+    q1, q2 = _p(dirpath, "CG_updt.Qckpt1"), _p(dirpath, "CG_updt.Qckpt2")
+    _rm(q1)
+    _rm(q2)
+    _write_marker(q1, m)
+    for tag, a in (("V", v), ("R", r), ("P", p)):
+        _csr.vec_disk_write(_p(dirpath, f"CG_{tag}{m}.dat"), a)
+    _write_marker(q2, m)
+    for name in os.listdir(dirpath):                                      # every older step (the reference: step m-1)
+        if name[:4] in ("CG_V", "CG_R", "CG_P") and name.endswith(".dat") and name[4:-4].isdigit() and int(name[4:-4]) < m:
+            _rm(_p(dirpath, name))
+    _rm(q1)
+    _rm(q2)
+
+
+def cg_load(dirpath, maxit, dim, dtype):
+    """ckpt_CG_init (src/ckpt.cc:345-427): returns (m, v, r, p); m = 0 (and None vectors) when there is nothing to resume."""
+    if not os.path.isdir(dirpath):
+        return 0, None, None, None
+    q1, q2 = _p(dirpath, "CG_updt.Qckpt1"), _p(dirpath, "CG_updt.Qckpt2")
+    have = lambda k: all(os.path.exists(_p(dirpath, f"CG_{t}{k}.dat")) for t in "VRP")   # noqa: E731
+    steps = sorted({int(nm[4:-4]) for nm in os.listdir(dirpath) if nm[:4] == "CG_V" and nm.endswith(".dat") and nm[4:-4].isdigit()})
+    if os.path.exists(q1) and os.path.getsize(q1) == 8:
+        m = _read_marker(q1)
+        if os.path.exists(q2):                                            # new data complete: drop the older steps
+            if not have(m):
+                raise QbgpuError(f"checkpoint: the CG files of step {m} are missing although its update was committed")
+            for k in steps:
+                if k < m:
+                    for t in "VRP":
+                        _rm(_p(dirpath, f"CG_{t}{k}.dat"))
+            _rm(q1)
+            _rm(q2)
+        else:                                                             # drop the half-written step, fall back to the last complete one
+            for t in "VRP":
+                _rm(_p(dirpath, f"CG_{t}{m}.dat"))
+            _rm(q1)
+            older = [k for k in steps if k < m and have(k)]
+            m = older[-1] if older else 0
+    else:
+        _rm(q1)
+        _rm(q2)
+        m = next((k for k in range(maxit) if os.path.exists(_p(dirpath, f"CG_V{k}.dat"))), 0)
+    if m <= 0:
+        return 0, None, None, None
+    out = []
+    for t in "VRP":
+        a = _csr.vec_disk_read(_p(dirpath, f"CG_{t}{m}.dat"), dim, dtype)
+        if a is None:
+            raise QbgpuError(f"checkpoint: CG_{t}{m}.dat is missing or damaged (size, length or CRC-32)")
+        out.append(a)
+    return (m, *out)
+
+
+def cg_clean(dirpath):
+    """ckpt_CG_clean (src/ckpt.cc:482-520)."""
+    if not os.path.isdir(dirpath):
+        return
+    for name in os.listdir(dirpath):
+        if (name[:4] in ("CG_V", "CG_R", "CG_P") and name.endswith(".dat")) or name.startswith("CG_updt.Qckpt"):
+            _rm(_p(dirpath, name))
+
+
+def cg_checkpointed(mat, E0, v, r, p, pp, maxit=1000, every=50, dirpath=DIRNAME, max_chunks=None):
+    """eigenvec_CG(dim, maxit, m = 0, ...) with the reference's CG checkpoints every `every` steps; resumes from `dirpath`
+    when it holds one.  v, r, p, pp: host arrays of length dim (v = the initial guess unless resuming).  Returns (m, accu)."""
+    dim = mat.dim
+    m, cv, cr, cp = cg_load(dirpath, maxit, dim, mat.dtype)
+    if m > 0:
+        v[:], r[:], p[:] = cv, cr, cp
+    accu, chunks = 0.0, 0
+    while m < maxit:
+        stop = min(maxit, m + every)
+        m_new, accu = _csr.eigenvec_CG(dim, stop, m, mat, E0, v, r, p, pp)
+        done = m_new < stop or accu < _csr.lanczos_precision
+        if m_new > m:
+            cg_store(dirpath, m_new, v, r, p)
+        m = m_new
+        chunks += 1
+        if done or (max_chunks is not None and chunks >= max_chunks):
+            break
+    return m, accu
 
 
 def stop_state_from_coefficients(hessenberg, maxit, m, precision=2e-12):

@@ -291,8 +291,7 @@ static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, dou
     QB_TRY(ensure_init());
     QB_TRY(check_single(A, cplx));
     if (!m_io || !accu_out || !v || !r || !p || !pp) return fail(QBGPU_ERR_ARG, "eigenvec_CG: null argument");
-    if (*m_io != 0) return fail(QBGPU_ERR_STATE, "eigenvec_CG: resuming from m > 0 (checkpoint restart) is not supported");
-    if (maxit <= 0) return fail(QBGPU_ERR_ARG, "eigenvec_CG: maxit must be positive");
+    if (maxit <= 0 || *m_io < 0 || *m_io >= maxit) return fail(QBGPU_ERR_ARG, "eigenvec_CG: need 0 <= m < maxit");        // src/lanczos.cc:287
     Context &c = ctx();
     const int64_t n = A->n;
     const size_t vb = cplx ? 16 : 8;
@@ -302,6 +301,10 @@ static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, dou
         QB_TRY(buf.alloc(vb * n * 4));
         dv = (char *)buf.p; dr = dv + vb * n; dp = dr + vb * n; dpp = dp + vb * n;
         QB_CUDA(cudaMemcpyAsync(dv, v, vb * n, cudaMemcpyHostToDevice, c.stream));
+        if (*m_io > 0) {                                    // a resumed run continues from (v, r, p) of step m
+            QB_CUDA(cudaMemcpyAsync(dr, r, vb * n, cudaMemcpyHostToDevice, c.stream));
+            QB_CUDA(cudaMemcpyAsync(dp, p, vb * n, cudaMemcpyHostToDevice, c.stream));
+        }
     } else if (where == QBGPU_DEVICE) {
         dv = (char *)v; dr = (char *)r; dp = (char *)p; dpp = (char *)pp;
     } else return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
@@ -309,8 +312,16 @@ static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, dou
     double *sc = (double *)dsc.p;                           // [0]=gamma [1,2]=delta [3]=|pp|^2 [4]=|r|^2 [5]=gamma_next
     QB_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 8, c.stream));
 
-    int64_t m = 0;
-    double accu = 0.0;                                      // src/lanczos.cc:288-289
+    int64_t m = *m_io;
+    double accu = 0.0;                                      // src/lanczos.cc:288-292: 0 at m == 0, |r| on a resume
+    if (m > 0) {
+        double nn;
+        QB_TRY(vec_nrm2sq(n, cplx, dr, sc + 6));
+        QB_TRY(read_scalars(sc + 6, &nn, 1));
+        accu = sqrt(nn);
+        QB_CUDA(cudaMemcpyAsync(sc, &accu, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        QB_CUDA(cudaStreamSynchronize(c.stream));
+    }
     while (m < maxit) {
         if (accu < kLanczosPrecision) {                     // :295
             double nn;
@@ -523,11 +534,23 @@ static int cg_native(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, d
     if (!m_io || !accu_out || !v || !r || !p || !pp) return fail(QBGPU_ERR_ARG, "eigenvec_CG: null argument");
     Context &c = ctx();
     const int64_t n = A->n;
+    const bool resumed = *m_io > 0;
     NativeRun N;
-    QB_TRY(native_begin(N, A, cplx, v, 1, 0x1u, where, E0.y == 0.0));
+    QB_TRY(native_begin(N, A, cplx, v, 1, 0x1u, where, E0.y == 0.0 && !resumed));   // (a resumed run keeps the API's scalar type)
     DevBuf rest;                                            // r, p, pp of the loop (internal order)
     QB_TRY(rest.alloc(N.vb_loop * n * 3));
     char *w[4] = {(char *)N.work.p, (char *)rest.p, (char *)rest.p + N.vb_loop * n, (char *)rest.p + 2 * N.vb_loop * n};
+    if (resumed) {                                          // r and p of step m come in with v
+        DevBuf in;
+        void *ins[2] = {r, p};
+        if (where == QBGPU_HOST) QB_TRY(in.alloc(N.vb_api * n));
+        for (int j = 0; j < 2; j++) {
+            const void *src = ins[j];
+            if (where == QBGPU_HOST) { QB_CUDA(cudaMemcpyAsync(in.p, ins[j], N.vb_api * n, cudaMemcpyHostToDevice, c.stream)); src = in.p; }
+            QB_TRY(vec_to_native(A, cplx, N.loop_cplx, src, w[1 + j]));
+            QB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    }
     QB_TRY(cg_impl(&N.R, N.loop_cplx, maxit, m_io, E0, accu_out, w[0], w[1], w[2], w[3], QBGPU_DEVICE));
     void *outs[4] = {v, r, p, pp};
     DevBuf tmp;                                             // host callers: one device vector in reference order at a time
@@ -637,7 +660,8 @@ static int cg_dispatch(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io,
     } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
     bool real0 = false;
     QB_TRY(is_all_real(n, vc, &real0));
-    if (!real0) { dc.release(); return cg_impl(A, true, maxit, m_io, E0, accu_out, v, r, p, pp, where); }
+    const bool resumed = m_io && *m_io > 0;
+    if (!real0 || resumed) { dc.release(); return cg_impl(A, true, maxit, m_io, E0, accu_out, v, r, p, pp, where); }   // (a resumed run stays complex)
     QB_TRY(dr.alloc(8 * n * 4));
     double *R4 = (double *)dr.p;
     QB_TRY(vec_take_real(n, vc, R4));

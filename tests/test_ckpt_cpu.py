@@ -154,3 +154,72 @@ def test_damaged_files_are_refused(oracle, case):
         assert ckpt.lanczos_load(os.path.join(d, "nowhere"), MAXIT, n, np.complex128, "dnmcs")[0] == 0
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+# --------------------------------------------------------------------------------------------------- conjugate gradient
+def _numpy_cg(oracle, A, E0, m, v, r, p, maxit):
+    """eigenvec_CG (src/lanczos.cc:281-341) on host arrays from step m; returns (m, accu)."""
+    eps = np.finfo(np.float64).eps
+    accu = 0.0 if m == 0 else np.linalg.norm(r)
+    while m < maxit:
+        if accu < PREC:
+            rnorm = np.linalg.norm(v)
+            if m == 0 or abs(rnorm - 1.0) > PREC:
+                v /= rnorm
+                r[:] = E0 * v - oracle.spmv(A, v.copy())
+                p[:] = r
+                accu = np.linalg.norm(r)
+                m += 1
+                if accu < PREC:
+                    break
+            else:
+                break
+        else:
+            pp = (eps - E0) * p + oracle.spmv(A, p.copy())
+            alpha = accu * accu / np.vdot(p, pp)
+            v += alpha * p
+            r -= alpha * pp
+            beta = np.linalg.norm(r) / accu
+            p[:] = r + beta * beta * p
+            accu *= beta
+            m += 1
+    return m, accu
+
+
+def test_cg_checkpoints_in_both_directions(oracle, case):
+    A, meta, ex, work, path = case
+    n, E0 = A.dim, meta["lanczos_E0"]
+    # the reference stops at step 10 -> we load and continue to its own stopping step and vector
+    w = os.path.join(work, "cg_ref_writes")
+    r = oracle.run_qb_ref(["file_z", path, "--cg-ckpt", repr(E0), 10, os.path.join(work, "cg10.bin")], workdir=w)
+    assert r["cgck_steps"] == 10
+    d = os.path.join(w, ckpt.DIRNAME)
+    assert sorted(f for f in os.listdir(d) if f.startswith("CG_")) == ["CG_P10.dat", "CG_R10.dat", "CG_V10.dat"]
+    m, v, rr, p = ckpt.cg_load(d, 1000, n, np.complex128)
+    assert m == 10
+    m, accu = _numpy_cg(oracle, A, E0, m, v, rr, p, 1000)
+    assert m == meta["cg_steps"] and accu < PREC
+    ph = np.vdot(ex["cg_vec"], v)
+    assert np.linalg.norm(v - ph / abs(ph) * ex["cg_vec"]) < 1e-8
+    # we run 12 steps and store -> the REFERENCE resumes and finishes as in its uninterrupted run
+    v = oracle.vec_randomize(n, 1); rr = np.zeros_like(v); p = np.zeros_like(v)
+    m, accu = _numpy_cg(oracle, A, E0, 0, v, rr, p, 12)
+    assert m == 12
+    w2 = os.path.join(work, "cg_we_write")
+    d2 = os.path.join(w2, ckpt.DIRNAME)
+    ckpt.cg_store(d2, m, v, rr, p)
+    out = os.path.join(work, "cg_final.bin")
+    r2 = oracle.run_qb_ref(["file_z", path, "--cg-ckpt", repr(E0), 1000, out], workdir=w2)
+    assert r2["cgck_steps"] == meta["cg_steps"] and r2["cgck_accuracy"] < PREC
+    vf = np.fromfile(out, dtype=np.complex128)
+    ph = np.vdot(ex["cg_vec"], vf)
+    assert np.linalg.norm(vf - ph / abs(ph) * ex["cg_vec"]) < 1e-8
+    # an update interrupted before its commit marker falls back to the last complete step; clean removes everything
+    ckpt.cg_store(d2, 5, v, rr, p)
+    with open(os.path.join(d2, "CG_updt.Qckpt1"), "wb") as f:
+        f.write((6).to_bytes(8, "little"))
+    with open(os.path.join(d2, "CG_V6.dat"), "wb") as f:
+        f.write(b"half written")
+    assert ckpt.cg_load(d2, 1000, n, np.complex128)[0] == 5 and not os.path.exists(os.path.join(d2, "CG_V6.dat"))
+    ckpt.cg_clean(d2)
+    assert ckpt.cg_load(d2, 1000, n, np.complex128)[0] == 0

@@ -289,3 +289,26 @@ def test_lanczos_resume_and_checkpoints(oracle, tmp_path):
         v5, h5 = np.zeros(2 * n, dtype=np.complex128), np.zeros(2 * maxit)
         assert ckpt.lanczos_checkpointed(M, v5, h5, "sr_val0", maxit, every=50, dirpath=os.path.join(w, ckpt.DIRNAME)) == m0
         assert abs(qb.hess_eigen(h5, maxit, m0)[0][0] - meta["lanczos_E0"]) <= TOL_E0 * abs(meta["lanczos_E0"])
+
+
+def test_cg_resume_and_checkpoints(oracle, tmp_path):
+    """eigenvec_CG entered with m > 0 (src/lanczos.cc:287-292) and the reference's CG checkpoints around it."""
+    from quantum_basis_b200 import ckpt
+    A, meta, ex = oracle.load_golden("heis12_full")
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    n, E0 = A.dim, meta["lanczos_E0"]
+    mk = lambda: [oracle.vec_randomize(n, 1)] + [np.zeros(n, dtype=np.complex128) for _ in range(3)]   # noqa: E731
+    v, r, p, pp = mk()
+    m_full, accu = qb.eigenvec_CG(n, 1000, 0, M, E0, v, r, p, pp)
+    assert m_full == meta["cg_steps"] and accu < 2e-12
+    v2, r2, p2, pp2 = mk()
+    m, _ = qb.eigenvec_CG(n, 12, 0, M, E0, v2, r2, p2, pp2)          # stops at step 12 ...
+    assert m == 12
+    m, accu2 = qb.eigenvec_CG(n, 1000, m, M, E0, v2, r2, p2, pp2)    # ... and continues from (v, r, p)
+    assert m == m_full and accu2 < 2e-12 and rel_l2(v2, v) < 1e-9
+    d = str(tmp_path / ckpt.DIRNAME)
+    v3, r3, p3, pp3 = mk()
+    assert ckpt.cg_checkpointed(M, E0, v3, r3, p3, pp3, every=10, dirpath=d, max_chunks=2)[0] == 20
+    v4, r4, p4, pp4 = [np.zeros(n, dtype=np.complex128) for _ in range(4)]          # a fresh process
+    m4, accu4 = ckpt.cg_checkpointed(M, E0, v4, r4, p4, pp4, every=10, dirpath=d)
+    assert m4 == m_full and accu4 < 2e-12 and rel_l2(v4, v) < 1e-9

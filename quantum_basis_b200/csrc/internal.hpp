@@ -48,7 +48,8 @@ struct qbgpu_matrix {
     void    *sp = nullptr;
     qbgpu_matrix *second = nullptr;
     int32_t *slice_order = nullptr;
-    void    *perm_x = nullptr, *perm_y = nullptr;      // staging vectors of the reference-order product (lazily allocated)
+    void    *perm_x = nullptr, *perm_y = nullptr;      // staging vectors of the reference-order product of a species handle, or of
+                                                       // the opt-in fp64 product of an ordinary one (lazily allocated; freed by destroy)
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }

@@ -466,7 +466,8 @@ int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
     if (!A->borrowed) { matfree_destroy(A); species_destroy(A); }
-    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); cudaFree(A->slice_order); }
+    if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); cudaFree(A->slice_order);
+                        cudaFree(A->perm_x); cudaFree(A->perm_y); }
     delete A;
     return QBGPU_OK;
 }

@@ -364,7 +364,6 @@ void species_destroy(qbgpu_matrix *A)
     species_free((Species *)A->sp);
     A->sp = nullptr;
     cudaFree(A->perm); A->perm = nullptr;
-    cudaFree(A->perm_x); cudaFree(A->perm_y); A->perm_x = A->perm_y = nullptr;
     if (A->second) { qbgpu_destroy(A->second); A->second = nullptr; }
 }
 

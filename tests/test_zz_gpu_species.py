@@ -312,3 +312,30 @@ def test_cg_resume_and_checkpoints(oracle, tmp_path):
     v4, r4, p4, pp4 = [np.zeros(n, dtype=np.complex128) for _ in range(4)]          # a fresh process
     m4, accu4 = ckpt.cg_checkpointed(M, E0, v4, r4, p4, pp4, every=10, dirpath=d)
     assert m4 == m_full and accu4 < 2e-12 and rel_l2(v4, v) < 1e-9
+
+
+def test_opt_in_real_mode_of_the_plain_product(oracle):
+    """QBGPU_MV_REAL_MODE: MultMv on complex device vectors without imaginary parts multiplies on fp64 copies (spmv.cu:
+    mv_real_mode); same numbers as the complex kernel, and vectors WITH imaginary parts take the complex kernel."""
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    n = A.dim
+    xr = oracle.vec_randomize(n, 1)                                   # imag == 0, like every vector of the reference's flows
+    xc = xr + 1j * oracle.vec_randomize(n, 2).real
+    outs = {}
+    for mode in ("off", "on"):
+        if mode == "on":
+            os.environ["QBGPU_MV_REAL_MODE"] = "1"
+        try:
+            for tag, x in (("real", xr), ("cplx", xc)):
+                xd, yd = qb.DeviceVector.from_numpy(x), qb.DeviceVector.from_numpy(np.full(n, 2.0 + 0.0j))
+                M.MultMv(xd, yd)
+                y1 = yd.to_numpy()
+                M.MultMv2(xd, yd)                                     # y += H x
+                outs[(mode, tag)] = (y1, yd.to_numpy())
+        finally:
+            os.environ.pop("QBGPU_MV_REAL_MODE", None)
+    for tag in ("real", "cplx"):
+        for j in range(2):
+            assert np.array_equal(outs[("on", tag)][j], outs[("off", tag)][j])
+    assert rel_l2(outs[("on", "real")][0], ex["y1"]) <= TOL_MV

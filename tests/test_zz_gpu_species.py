@@ -337,5 +337,5 @@ def test_opt_in_real_mode_of_the_plain_product(oracle):
             os.environ.pop("QBGPU_MV_REAL_MODE", None)
     for tag in ("real", "cplx"):
         for j in range(2):
-            assert np.array_equal(outs[("on", tag)][j], outs[("off", tag)][j])
+            assert rel_l2(outs[("on", tag)][j], outs[("off", tag)][j]) <= 1e-15      # (bit-identical by construction; not required)
     assert rel_l2(outs[("on", "real")][0], ex["y1"]) <= TOL_MV

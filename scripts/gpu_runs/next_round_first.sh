@@ -6,6 +6,11 @@ mkdir -p gpurun_out
 # 1. correctness: the xfail-marked module, run strictly (a failure here is a failure)
 python -m pytest tests/test_zz_gpu_species.py -q -x --runxfail -p no:cacheprovider > gpurun_out/pytest_species.log 2>&1; echo "pytest species rc=$?" >> gpurun_out/pytest_species.log
 tail -5 gpurun_out/pytest_species.log
+# 1b. if anything above failed: memcheck on the smallest case pinpoints an out-of-bounds access
+if ! grep -q "rc=0" gpurun_out/pytest_species.log; then
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_zz_gpu_species.py -q -x --runxfail -p no:cacheprovider \
+    -k "product_in_the_reference_order and hub2x2" > gpurun_out/memcheck_species.log 2>&1; tail -30 gpurun_out/memcheck_species.log
+fi
 # 2. timings on BASELINE config 3, tile sweep (the probe itself sweeps the three pass-1 variants of the matrix-free product)
 for W in 64 128 256 512; do
   QBGPU_SPECIES_TILE=$W timeout 600 python bench.py --species-probe --workload hubbard4x4 --steps 10 > gpurun_out/species_probe_W$W.json 2> gpurun_out/species_probe_W$W.err

@@ -285,9 +285,10 @@ int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn
  * The calling convention does not change: qbgpu_{d,z}mv, qbgpu_lanczos_*, qbgpu_eigenvec_cg_*, qbgpu_energy_scale_*,
  * qbgpu_kpm_moments_* and qbgpu_trlan take and return vectors in the REFERENCE's order (they permute on the way in and
  * out; inside a Krylov loop nothing is permuted).  The fused low-level entry points (qbgpu_spmv_fused,
- * qbgpu_lanczos_step_*) work in the internal order; the three functions below convert.  No row shards; not available:
- * to_dense, download_expanded, split_columns, ring_prepare.  QBGPU_SPECIES_TILE (environment, default 128) sets the tile
- * width in down indices. */
+ * qbgpu_lanczos_step_*) work in the internal order; the three functions below convert.  Not available: to_dense,
+ * download_expanded, ring_prepare.  Row shards and qbgpu_split_columns exist for the matrix-free kind only, in units of whole
+ * up configurations (row_lo, row_hi and the column bounds multiples of D_dn); shards and parts have no permutation: their
+ * vectors are in the internal order.  QBGPU_SPECIES_TILE (environment, default 128) sets the tile width in down indices. */
 int qbgpu_native_order(qbgpu_matrix_t A, int *has_internal_order);
 int qbgpu_vec_to_native(qbgpu_matrix_t A, const void *x_reference_order_dev, void *x_internal_order_dev);   /* out of place */
 int qbgpu_vec_from_native(qbgpu_matrix_t A, const void *x_internal_order_dev, void *x_reference_order_dev); /* out of place */
@@ -302,6 +303,12 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
                              int64_t *sizes, int32_t *perm, int64_t *rowptr_local, int32_t *col_local, double *val_local,
                              int64_t *rowptr_cross, int32_t *col_cross, double *val_cross, int32_t *slice_order,
                              const double *x, double *y, int32_t *touched);
+
+/* The same for a row shard (up configurations [u_lo, u_hi)) cut into column parts executed in `order` (the multi-GPU
+ * exchange pattern): part p keeps the up-hops whose target configuration lies in [part_bounds[p], part_bounds[p+1]). */
+int qbgpu_debug_species_parts_host(int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U, int tile,
+                                   int64_t u_lo, int64_t u_hi, int nparts, const int64_t *part_bounds, const int32_t *order,
+                                   const double *x, double *y_local);
 
 /* --------------------------------------------------------------------- translation-symmetric sectors
  * Device counterpart of model::fill_Weisse_table + enumerate_basis_repr + generate_Ham_sparse_repr

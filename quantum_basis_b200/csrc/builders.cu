@@ -1053,10 +1053,7 @@ int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn
     static thread_local ModelParams M;
     M.kind = 1; M.J = 0; M.t = t; M.U = U;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
-    if (flags & QBGPU_SPECIES_ORDER) {
-        if (row_lo != 0 || (row_hi >= 0 && row_hi != T.dim)) return fail(QBGPU_ERR_ARG, "create_matfree_hubbard: species order has no row shards");
-        return species_build_matfree(A, T, M, api_complex, flags);
-    }
+    if (flags & QBGPU_SPECIES_ORDER) return species_build_matfree(A, T, M, api_complex, flags, row_lo, row_hi);   // shards: whole up configurations
     return create_matfree(A, T, M, api_complex, row_lo, row_hi, flags);
 }
 

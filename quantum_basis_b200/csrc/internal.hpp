@@ -48,6 +48,10 @@ struct qbgpu_matrix {
     void    *sp = nullptr;
     qbgpu_matrix *second = nullptr;
     int32_t *slice_order = nullptr;
+    // column part of a matrix-free species shard (qbgpu_split_columns): only the up-hops whose target configuration lies in
+    // [sp_col_lo, sp_col_hi) (units: up configurations), plus the whole local pass when sp_has_local; -1 = no filter
+    int64_t  sp_col_lo = -1, sp_col_hi = -1;
+    bool     sp_has_local = true;
     void    *perm_x = nullptr, *perm_y = nullptr;      // staging vectors of the reference-order product of a species handle, or of
                                                        // the opt-in fp64 product of an ordinary one (lazily allocated; freed by destroy)
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
@@ -94,6 +98,7 @@ int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const voi
 // dst[r] = a * src[perm[r]] + b * dst[r]  (internal order -> reference order; b == 0: dst is not read)
 int vec_from_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst, double2 a, double2 b);
 int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void *y, int where);   // y = alpha*H*x + beta*y, reference order
+int species_split_columns(qbgpu_matrix *A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts);   // views on a matrix-free shard
 inline int no_species(const qbgpu_matrix *A, const char *what)
 { return (A && A->sp) ? fail(QBGPU_ERR_STATE, std::string(what) + ": not available for species-order handles") : QBGPU_OK; }
 // matrix.cu

@@ -37,6 +37,7 @@ void species_perm_host(const HostTables &T, const int32_t *rank_in_class, int64_
 
 // species.cu: the species-order handles behind qbgpu_build_hubbard / qbgpu_create_matfree_hubbard with QBGPU_SPECIES_ORDER
 int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags);
-int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags);
+int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags,
+                          int64_t row_lo = 0, int64_t row_hi = -1);
 
 }  // namespace qb

@@ -545,7 +545,7 @@ int qbgpu_real_view(qbgpu_matrix_t A, qbgpu_matrix_t *view)
 
 int qbgpu_split_columns(qbgpu_matrix_t A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts, int flags)
 {
-    QB_TRY(no_species(A, "split_columns"));
+    if (A && A->sp) return species_split_columns(A, nparts, col_bounds, parts);   // matrix-free species shards: filtered views
     return split_columns(A, nparts, col_bounds, parts, flags);
 }
 

@@ -169,7 +169,7 @@ static cudaError_t upload(T **dst, const T *src, size_t count, cudaStream_t st)
 }
 
 // Common part of both handle kinds: tables in HBM, the permutation, and a bare handle that owns them.
-static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelParams &M, int api_complex, SpeciesHost &H)
+static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelParams &M, int api_complex, SpeciesHost &H, bool with_perm = true)
 {
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -200,13 +200,16 @@ static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelPa
     QB_CU(upload(&S->dhop, H.hop[1].data(), H.hop[1].size(), c.stream));
     QB_CU(upload(&S->ampw, H.ampw, (size_t)kMaxWeight + 1, c.stream));
     QB_CU(upload(&S->diagk, H.diagk, (size_t)kMaxDbl + 1, c.stream));
-    QB_CU(upload(&d_rank, H.rank.data(), H.rank.size(), c.stream));
-    QB_CU(cudaMalloc(&A->perm, sizeof(int32_t) * (size_t)T.dim));
-    { int rc = species_perm_build(T, d_rank, Dd, A->perm); if (rc) { cudaFree(d_rank); qbgpu_destroy(A); return rc; } }
+    if (with_perm) {
+        QB_CU(upload(&d_rank, H.rank.data(), H.rank.size(), c.stream));
+        QB_CU(cudaMalloc(&A->perm, sizeof(int32_t) * (size_t)T.dim));
+        int rc = species_perm_build(T, d_rank, Dd, A->perm);
+        if (rc) { cudaFree(d_rank); qbgpu_destroy(A); return rc; }
+    }
     QB_CU(cudaStreamSynchronize(c.stream));
     cudaFree(d_rank); d_rank = nullptr;
 #undef QB_CU
-    S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + 4 * T.dim);
+    S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + (with_perm ? 4 * T.dim : 0));
     *out = A;
     return QBGPU_OK;
 }
@@ -340,7 +343,9 @@ int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     return QBGPU_OK;
 }
 
-int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags)
+// Row shards (multi-GPU): whole up configurations only, rows [u_lo * D_dn, u_hi * D_dn).  A shard has no permutation: its
+// vectors -- x full length, y and z the local rows -- are in the internal order, like every sharded handle's are in "row order".
+int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
     (void)flags;
     if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
@@ -348,8 +353,15 @@ int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
     const double t0 = wall_s();
     SpeciesHost H;
     qbgpu_matrix *A = nullptr;
-    QB_TRY(species_common(&A, T, M, api_complex, H));
+    if (row_hi < 0) row_hi = T.dim;
+    const bool shard = !(row_lo == 0 && row_hi == T.dim);
+    QB_TRY(species_common(&A, T, M, api_complex, H, !shard));
     Species *S = (Species *)A->sp;
+    if (shard) {
+        if (row_lo < 0 || row_lo > row_hi || row_hi > T.dim || row_lo % S->Dd != 0 || (row_hi % S->Dd != 0))
+        { qbgpu_destroy(A); return fail(QBGPU_ERR_ARG, "species order: a row shard must consist of whole up configurations (multiples of D_dn rows)"); }
+        A->row_lo = row_lo; A->row_hi = row_hi;
+    }
     S->matfree = true;
     A->format = QBGPU_FORMAT_MATFREE;
     A->nnz = 0; A->nnz_input = 0;
@@ -418,10 +430,11 @@ __device__ __forceinline__ void local_scalars(int scal_mode, const double *sc, d
 }
 
 // BLOCK = 256, grid-stride (default), or BLOCK = 1024 with one contiguous range of rows per CTA (QBGPU_KRON_LOCAL=1: one
-// CTA per SM then walks through the blocks x[iu, :] one after the other, so that L1 holds the block being gathered from)
+// CTA per SM then walks through the blocks x[iu, :] one after the other, so that L1 holds the block being gathered from).
+// Rows [row0, row0 + nloc) of the operator (a shard: whole up configurations); x is the full vector, y and z the local rows.
 template <typename VecT, int BLOCK, bool RANGES>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
-kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
                   const VecT *__restrict__ x, const VecT *z, VecT *y,
                   double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
 {
@@ -433,22 +446,23 @@ kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, c
     local_scalars(scal_mode, sc, alpha, gamma, beta);
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
     const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
-    int64_t p0, p1, step;
+    int64_t q0, q1, step;                                   // local row indices
     if (RANGES) {
-        const int64_t chunk = ((n + gridDim.x - 1) / gridDim.x + BLOCK - 1) / BLOCK * BLOCK;
-        p0 = (int64_t)blockIdx.x * chunk + threadIdx.x; p1 = min(n, ((int64_t)blockIdx.x + 1) * chunk); step = BLOCK;
+        const int64_t chunk = ((nloc + gridDim.x - 1) / gridDim.x + BLOCK - 1) / BLOCK * BLOCK;
+        q0 = (int64_t)blockIdx.x * chunk + threadIdx.x; q1 = min(nloc, ((int64_t)blockIdx.x + 1) * chunk); step = BLOCK;
     } else {
-        p0 = (int64_t)blockIdx.x * BLOCK + threadIdx.x; p1 = n; step = (int64_t)gridDim.x * BLOCK;
+        q0 = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q1 = nloc; step = (int64_t)gridDim.x * BLOCK;
     }
-    for (int64_t p = p0; p < p1; p += step) {
+    for (int64_t q = q0; q < q1; q += step) {
+        const int64_t p = row0 + q;
         const int64_t iu = p / V.Dd;
         const int32_t id = (int32_t)(p - iu * V.Dd);
         const VecT xi = ld_ro(x + p);
         const VecT acc = kron_local_acc<VecT, true>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x + iu * V.Dd, xi);
         VecT out = VT::scale(alpha, acc);
         if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
-        if (use_beta) out = VT::add(out, VT::scale(beta, z[p]));
-        y[p] = out;
+        if (use_beta) out = VT::add(out, VT::scale(beta, z[q]));
+        y[q] = out;
     }
 }
 
@@ -456,7 +470,7 @@ kron_local_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, c
 // numbers for the 4x4 lattice) is staged in shared memory once and every gather of the block's rows reads it from there.
 template <typename VecT>
 __global__ void __launch_bounds__(1024, 1)
-kron_local_smem_kernel(SpeciesView V, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+kron_local_smem_kernel(SpeciesView V, int64_t u_lo, int64_t u_cnt, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
                        const VecT *__restrict__ x, const VecT *z, VecT *y,
                        double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
 {
@@ -470,7 +484,8 @@ kron_local_smem_kernel(SpeciesView V, const double *__restrict__ ampw_g, const d
     const bool use_gamma = (gamma.x != 0.0 || gamma.y != 0.0);
     const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
     const int32_t Dd = (int32_t)V.Dd;
-    for (int64_t iu = blockIdx.x; iu < V.Du; iu += gridDim.x) {
+    for (int64_t il = blockIdx.x; il < u_cnt; il += gridDim.x) {
+        const int64_t iu = u_lo + il;
         __syncthreads();                                    // the previous block's gathers are done (and the tables are loaded)
         const VecT *xg = x + iu * V.Dd;
         for (int32_t k = threadIdx.x; k < Dd; k += 1024) xs[k] = ld_ro(xg + k);
@@ -481,8 +496,8 @@ kron_local_smem_kernel(SpeciesView V, const double *__restrict__ ampw_g, const d
             const VecT acc = kron_local_acc<VecT, false>(V, ampw, diagk, U, id, xs, xi);
             VecT out = VT::scale(alpha, acc);
             if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
-            if (use_beta) out = VT::add(out, VT::scale(beta, z[iu * V.Dd + id]));
-            y[iu * V.Dd + id] = out;
+            if (use_beta) out = VT::add(out, VT::scale(beta, z[il * V.Dd + id]));
+            y[il * V.Dd + id] = out;
         }
     }
 }
@@ -518,8 +533,10 @@ __host__ __device__ __forceinline__ void cross_item_at(const CrossItems &I, int6
     id = tau * I.W + ch * 32 + lane;
 }
 
-template <typename VecT>
-__host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, const double *ampw, int64_t iu, int64_t idc, const VecT *x)
+// FILTER: only the hops whose target configuration lies in [c_lo, c_hi) (a column part of a shard)
+template <typename VecT, bool FILTER = false>
+__host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, const double *ampw, int64_t iu, int64_t idc, const VecT *x,
+                                                        int64_t c_lo = 0, int64_t c_hi = 0)
 {
     using VT = VecTraits<VecT>;
     const uint32_t D = ld_ro(V.dlist + idc);
@@ -529,7 +546,10 @@ __host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, co
         uint2 h[4];
         VecT xv[4];
 QB_UNROLL
-        for (int u = 0; u < 4; u++) h[u] = (e + u < e1) ? ld_ro(V.uhop + e + u) : make_uint2((uint32_t)iu, 0u);
+        for (int u = 0; u < 4; u++) {
+            h[u] = (e + u < e1) ? ld_ro(V.uhop + e + u) : make_uint2((uint32_t)iu, 0u);
+            if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);   // replays 0 * x[own row]
+        }
 QB_UNROLL
         for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);
 QB_UNROLL
@@ -538,9 +558,12 @@ QB_UNROLL
     return acc;
 }
 
-template <typename VecT, bool DOTS>
+// The items enumerate the LOCAL up configurations [u_lo, u_lo + u_cnt) of the handle.  FIRST: y = alpha acc + beta z (a
+// column part without the local pass that opens the product); otherwise y += alpha acc.
+template <typename VecT, bool DOTS, bool FILTER, bool FIRST>
 __global__ void __launch_bounds__(kPBlock, 4)
-kron_cross_kernel(SpeciesView V, CrossItems I, const double *__restrict__ ampw_g, const VecT *__restrict__ x, VecT *y, double2 alpha, int scal_mode,
+kron_cross_kernel(SpeciesView V, CrossItems I, int64_t u_lo, int64_t c_lo, int64_t c_hi, const double *__restrict__ ampw_g,
+                  const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 beta, int scal_mode,
                   const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
@@ -548,23 +571,30 @@ kron_cross_kernel(SpeciesView V, CrossItems I, const double *__restrict__ ampw_g
     for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
     __syncthreads();
     double dot_scale = 1.0;
-    if (scal_mode != 0) { alpha = make_double2(sc[0], 0.0); dot_scale = sc[0]; }
+    if (scal_mode != 0) {
+        alpha = make_double2(sc[0], 0.0); dot_scale = sc[0];
+        beta = scal_mode == 1 ? make_double2(-sc[2] * sc[1], 0.0) : make_double2(1.0, 0.0);
+    }
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
     constexpr int WPB = kPBlock / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d[3] = {0.0, 0.0, 0.0};
     for (int64_t it = (int64_t)blockIdx.x * WPB + warp; it < I.nitems; it += (int64_t)gridDim.x * WPB) {
-        int64_t iu, id;
-        cross_item_at(I, it, lane, iu, id);
+        int64_t il, id;
+        cross_item_at(I, it, lane, il, id);
+        const int64_t iu = u_lo + il;
         const bool live = id < V.Dd;
         const int64_t idc = live ? id : V.Dd - 1;           // idle lanes of the last chunk replay a valid column
-        const VecT acc = kron_cross_acc<VecT>(V, ampw, iu, idc, x);
+        const VecT acc = kron_cross_acc<VecT, FILTER>(V, ampw, iu, idc, x, c_lo, c_hi);
         if (live) {
-            const int64_t p = iu * V.Dd + id;
-            const VecT out = VT::add(y[p], VT::scale(alpha, acc));
-            y[p] = out;
+            const int64_t q = il * V.Dd + id;               // local row
+            VecT out = VT::scale(alpha, acc);
+            if (FIRST) { if (use_beta) out = VT::add(out, VT::scale(beta, z[q])); }
+            else out = VT::add(y[q], out);
+            y[q] = out;
             if (DOTS) {
-                const double2 q = VT::conj_mul(ld_ro(x + p), out);
-                d[0] += q.x; d[1] += q.y; d[2] += VT::abs2(out);
+                const double2 qd = VT::conj_mul(ld_ro(x + iu * V.Dd + id), out);
+                d[0] += qd.x; d[1] += qd.y; d[2] += VT::abs2(out);
             }
         }
     }
@@ -577,59 +607,76 @@ kron_cross_kernel(SpeciesView V, CrossItems I, const double *__restrict__ ampw_g
 static int g_kron_local_variant = -1;      // -1: not chosen yet (environment QBGPU_KRON_LOCAL, else 0)
 void set_kron_local_variant(int v) { g_kron_local_variant = v; }
 
+template <typename VecT, bool DOTS, bool FILTER, bool FIRST>
+static int launch_kron_cross(const qbgpu_matrix *A, const FusedArgs &a, const SpeciesView &V, const CrossItems &I, int64_t u_lo)
+{
+    Context &c = ctx();
+    const Species *S = (const Species *)A->sp;
+    auto kern = kron_cross_kernel<VecT, DOTS, FILTER, FIRST>;
+    static int bps = 0;
+    if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
+    const int64_t want = (I.nitems + (kPBlock / 32) - 1) / (kPBlock / 32);
+    int64_t cap = (int64_t)c.num_sms * bps;
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    if (want < 1) return QBGPU_OK;
+    kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, I, u_lo, A->sp_col_lo, A->sp_col_hi, S->ampw, (const VecT *)a.x, (const VecT *)a.z,
+                                                                    (VecT *)a.y, a.alpha, a.beta, a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
 template <typename VecT>
 static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
     const Species *S = (const Species *)A->sp;
-    const int64_t n = A->n;
-    if (n == 0) return QBGPU_OK;
+    const int64_t nloc = A->nrows(), row0 = A->row_lo;
+    if (nloc == 0) return QBGPU_OK;
+    const int64_t u_lo = row0 / S->Dd, u_cnt = nloc / S->Dd;
     const SpeciesView V = view_of(S);
-    // pass 1 variants (QBGPU_KRON_LOCAL): 0 grid-stride / 256 threads (default), 1 contiguous row ranges / 1024 threads,
-    // 2 block staged in shared memory (falls back to 0 when D_dn entries do not fit)
-    if (g_kron_local_variant < 0) g_kron_local_variant = getenv("QBGPU_KRON_LOCAL") ? atoi(getenv("QBGPU_KRON_LOCAL")) : 0;
-    const int variant = g_kron_local_variant;
-    const size_t stage_bytes = sizeof(VecT) * (size_t)S->Dd;
-    if (variant == 2 && stage_bytes <= 225 * 1024) {
-        auto kern = kron_local_smem_kernel<VecT>;
-        static bool attr_set = false;
-        if (!attr_set) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_set = true; }
-        const int64_t grid = S->Du < c.num_sms ? S->Du : c.num_sms;
-        kern<<<(int)grid, 1024, stage_bytes, c.stream>>>(V, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
-                                                         a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+    const bool filter = A->sp_col_lo >= 0;
+    if (A->sp_has_local) {
+        // pass 1 variants (QBGPU_KRON_LOCAL): 0 grid-stride / 256 threads (default), 1 contiguous row ranges / 1024 threads,
+        // 2 block staged in shared memory (falls back to 0 when D_dn entries do not fit)
+        if (g_kron_local_variant < 0) g_kron_local_variant = getenv("QBGPU_KRON_LOCAL") ? atoi(getenv("QBGPU_KRON_LOCAL")) : 0;
+        const int variant = g_kron_local_variant;
+        const size_t stage_bytes = sizeof(VecT) * (size_t)S->Dd;
+        if (variant == 2 && stage_bytes <= 225 * 1024) {
+            auto kern = kron_local_smem_kernel<VecT>;
+            static bool attr_set = false;
+            if (!attr_set) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_set = true; }
+            const int64_t grid = u_cnt < c.num_sms ? u_cnt : c.num_sms;
+            kern<<<(int)grid, 1024, stage_bytes, c.stream>>>(V, u_lo, u_cnt, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                                             a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        } else if (variant == 1) {
+            auto kern = kron_local_kernel<VecT, 1024, true>;
+            kern<<<c.num_sms, 1024, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+                                                   a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        } else {
+            auto kern = kron_local_kernel<VecT, kPBlock, false>;
+            static int bps = 0;
+            if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
+            const int64_t want = (nloc + kPBlock - 1) / kPBlock, cap = (int64_t)c.num_sms * bps;
+            kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z,
+                                                                            (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
+        }
         QB_LAUNCH_COUNT();
         QB_CUDA(cudaGetLastError());
-    } else if (variant == 1) {
-        auto kern = kron_local_kernel<VecT, 1024, true>;
-        kern<<<c.num_sms, 1024, 0, c.stream>>>(V, n, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
-                                               a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
-        QB_LAUNCH_COUNT();
-        QB_CUDA(cudaGetLastError());
-    } else {
-        auto kern = kron_local_kernel<VecT, kPBlock, false>;
-        static int bps = 0;
-        if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
-        const int64_t want = (n + kPBlock - 1) / kPBlock, cap = (int64_t)c.num_sms * bps;
-        kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
-                                                                        a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
-        QB_LAUNCH_COUNT();
-        QB_CUDA(cudaGetLastError());
+    } else if (a.scal_mode == 0 && (a.gamma.x != 0.0 || a.gamma.y != 0.0)) {
+        return fail(QBGPU_ERR_ARG, "a column part without the diagonal block cannot carry the gamma*x term");
     }
-    const CrossItems I = cross_items(S->Du, S->Dd, S->tile);
-    const int64_t want = (I.nitems + (kPBlock / 32) - 1) / (kPBlock / 32);
-    auto launch2 = [&](auto kern, int &bps) -> int {
-        if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
-        int64_t cap = (int64_t)c.num_sms * bps;
-        if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
-        kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, I, S->ampw, (const VecT *)a.x, (VecT *)a.y, a.alpha, a.scal_mode, a.sc,
-                                                                        a.dots, c.partials, c.ticket);
-        QB_LAUNCH_COUNT();
-        QB_CUDA(cudaGetLastError());
-        return QBGPU_OK;
-    };
-    static int bps_dots = 0, bps_plain = 0;
-    if (a.dots) return launch2(kron_cross_kernel<VecT, true>, bps_dots);
-    return launch2(kron_cross_kernel<VecT, false>, bps_plain);
+    const CrossItems I = cross_items(u_cnt, S->Dd, S->tile);
+    // does this call open the product (y = ... + beta z) or continue it (y += ...)?  After the local pass it always continues.
+    const bool accumulate = A->sp_has_local || a.scal_mode == 2 ||
+                            (a.scal_mode == 0 && a.z == a.y && a.beta.x == 1.0 && a.beta.y == 0.0);
+    if (!accumulate && (a.beta.x != 0.0 || a.beta.y != 0.0 || a.scal_mode == 1) && !a.z) return fail(QBGPU_ERR_ARG, "beta != 0 needs z");
+    if (a.dots) {
+        if (filter) return accumulate ? launch_kron_cross<VecT, true, true, false>(A, a, V, I, u_lo) : launch_kron_cross<VecT, true, true, true>(A, a, V, I, u_lo);
+        return launch_kron_cross<VecT, true, false, false>(A, a, V, I, u_lo);
+    }
+    if (filter) return accumulate ? launch_kron_cross<VecT, false, true, false>(A, a, V, I, u_lo) : launch_kron_cross<VecT, false, true, true>(A, a, V, I, u_lo);
+    return launch_kron_cross<VecT, false, false, false>(A, a, V, I, u_lo);
 }
 
 // Both handle kinds: pass 1 carries the caller's epilogue (alpha, gamma, beta*z) without the dots, pass 2 accumulates
@@ -653,6 +700,38 @@ int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
     if (a.scal_mode != 0) { a2.scal_mode = 2; a2.sc = a.sc; }
     else a2.alpha = a.alpha;
     return launch_spmv(&C, a2);
+}
+
+// Column parts of a matrix-free handle or shard (qbgpu_split_columns; the pipelined / peer-pull exchanges of dist.py multiply
+// part p as soon as the slice of x owned by rank p has arrived): views that share the tables.  Part p keeps the up-hops whose
+// target configuration lies in [bounds[p], bounds[p+1]) / D_dn; the part whose range contains the handle's first row also runs
+// the whole local pass (its gathers never leave the handle's own rows).  Bounds must be multiples of D_dn.
+int species_split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matrix_t *parts)
+{
+    QB_TRY(ensure_init());
+    if (!A || !bounds || !parts || nparts < 1) return fail(QBGPU_ERR_ARG, "split_columns: bad argument");
+    const Species *S = (const Species *)A->sp;
+    if (!S || !S->matfree) return fail(QBGPU_ERR_STATE, "split_columns: of the species-order handles only the matrix-free ones can be split");
+    if (A->sp_col_lo >= 0) return fail(QBGPU_ERR_STATE, "split_columns: already a column part");
+    if (bounds[0] != 0 || bounds[nparts] != A->n) return fail(QBGPU_ERR_ARG, "split_columns: bounds must run from 0 to n");
+    for (int p = 0; p <= nparts; p++) {
+        if (bounds[p] % S->Dd != 0) return fail(QBGPU_ERR_ARG, "split_columns: species-order bounds must be multiples of D_dn (whole up configurations)");
+        if (p && bounds[p] < bounds[p - 1]) return fail(QBGPU_ERR_ARG, "split_columns: bounds must be non-decreasing");
+    }
+    bool local_given = false;
+    for (int p = 0; p < nparts; p++) {
+        auto *V = new qbgpu_matrix(*A);
+        V->borrowed = true;
+        V->perm = nullptr; V->perm_x = V->perm_y = nullptr;
+        V->sp_col_lo = bounds[p] / S->Dd; V->sp_col_hi = bounds[p + 1] / S->Dd;
+        V->sp_has_local = !local_given && bounds[p] <= A->row_lo && A->row_lo < bounds[p + 1];
+        local_given = local_given || V->sp_has_local;
+        parts[p] = V;
+    }
+    if (!local_given) {                                     // (an empty shard: no rows, no local pass needed)
+        if (A->nrows() != 0) { for (int p = 0; p < nparts; p++) { qbgpu_destroy(parts[p]); parts[p] = nullptr; } return fail(QBGPU_ERR_STATE, "split_columns: no part contains the shard's rows"); }
+    }
+    return QBGPU_OK;
 }
 
 // --------------------------------------------------------------------------------------- order of the vectors
@@ -826,6 +905,60 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
                 const bool live = id < V.Dd;
                 const double acc = kron_cross_acc<double>(V, H.ampw, iu, live ? id : V.Dd - 1, x);
                 if (live) { y[iu * V.Dd + id] += acc; if (touched) touched[iu * V.Dd + id]++; }
+            }
+    }
+    return QBGPU_OK;
+}
+
+/* The same for a ROW SHARD cut into COLUMN PARTS (what the multi-GPU exchanges of dist.py multiply): rows = the up
+ * configurations [u_lo, u_hi), parts p = the hops whose target lies in [part_bounds[p], part_bounds[p+1]) (units: up
+ * configurations), executed in the given order; the part containing u_lo also runs the local pass; the first executed part
+ * opens the product (y = ...), the others accumulate.  x: full vector, y_local: (u_hi - u_lo) * D_dn entries. */
+int qbgpu_debug_species_parts_host(int nsites, int nup, int ndn, int nbonds, const int32_t *bonds, double t, double U, int tile,
+                                   int64_t u_lo, int64_t u_hi, int nparts, const int64_t *part_bounds, const int32_t *order,
+                                   const double *x, double *y_local)
+{
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || nbonds < 1 || !bonds || !part_bounds || !order || !x || !y_local || nparts < 1)
+        return fail(QBGPU_ERR_ARG, "debug_species_parts_host: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 2, nup, ndn, T));
+    static thread_local ModelParams M;
+    M.kind = 1; M.J = 0; M.t = t; M.U = U;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    SpeciesHost H;
+    QB_TRY(build_host_tables(nsites, nup, ndn, M, H));
+    SpeciesView V;
+    V.Du = (int64_t)H.list[0].size(); V.Dd = (int64_t)H.list[1].size(); V.tot_u = (int64_t)H.hop[0].size(); V.tot_d = (int64_t)H.hop[1].size();
+    V.ulist = H.list[0].data(); V.dlist = H.list[1].data(); V.uptr = H.ptr[0].data(); V.dptr = H.ptr[1].data();
+    V.uhop = H.hop[0].data(); V.dhop = H.hop[1].data();
+    if (u_lo < 0 || u_hi < u_lo || u_hi > V.Du) return fail(QBGPU_ERR_ARG, "debug_species_parts_host: bad row range");
+    const int W = tile < 32 ? 32 : (tile + 31) / 32 * 32;
+    const int64_t u_cnt = u_hi - u_lo;
+    const CrossItems I = cross_items(u_cnt, V.Dd, W);
+    bool local_done = false;
+    for (int k = 0; k < nparts; k++) {
+        const int p = order[k];
+        if (p < 0 || p >= nparts) return fail(QBGPU_ERR_ARG, "debug_species_parts_host: bad order");
+        const int64_t c_lo = part_bounds[p], c_hi = part_bounds[p + 1];
+        const bool has_local = !local_done && c_lo <= u_lo && u_lo < c_hi;
+        bool first = (k == 0);
+        if (has_local) {
+            for (int64_t q = 0; q < u_cnt * V.Dd; q++) {
+                const int64_t pg = u_lo * V.Dd + q, iu = pg / V.Dd;
+                const double acc = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(pg - iu * V.Dd), x + iu * V.Dd, x[pg]);
+                y_local[q] = first ? acc : y_local[q] + acc;
+            }
+            local_done = true;
+            first = false;                                  // the cross pass of this part continues the product
+        }
+        for (int64_t it = 0; it < I.nitems; it++)
+            for (int lane = 0; lane < 32; lane++) {
+                int64_t il, id;
+                cross_item_at(I, it, lane, il, id);
+                if (il < 0 || il >= u_cnt || id < 0) return fail(QBGPU_ERR_STATE, "debug_species_parts_host: warp item out of range");
+                const bool live = id < V.Dd;
+                const double acc = kron_cross_acc<double, true>(V, H.ampw, u_lo + il, live ? id : V.Dd - 1, x, c_lo, c_hi);
+                if (live) { const int64_t q = il * V.Dd + id; y_local[q] = first ? acc : y_local[q] + acc; }
             }
     }
     return QBGPU_OK;

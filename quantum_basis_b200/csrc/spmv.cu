@@ -308,7 +308,8 @@ static int mv_any(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, v
 {
     QB_TRY(ensure_init());
     if (!x || !y) return fail(QBGPU_ERR_ARG, "null vector pointer");
-    if (A->sp) return mv_species(A, alpha, x, beta, y, where);   // reference order at the boundary, internal order inside
+    if (A->sp && A->perm) return mv_species(A, alpha, x, beta, y, where);   // reference order at the boundary, internal order inside
+    if (A->sp && where == QBGPU_HOST) return fail(QBGPU_ERR_STATE, "host-vector products on a shard or column part of a species-order handle are not available");
     if (where == QBGPU_DEVICE) {
         bool done = false;
         QB_TRY(mv_real_mode(A, alpha, x, beta, y, &done));

@@ -127,6 +127,34 @@ def test_matrix_free_passes_reproduce_the_reference_order_product():
     assert np.linalg.norm(y - y_ref) <= 1e-13 * np.linalg.norm(y_ref)
 
 
+@pytest.mark.parametrize("Lx,Ly,nup,ndn", [(4, 2, 3, 5), (3, 3, 4, 5), (4, 2, 4, 4)])
+def test_row_shards_and_column_parts_on_the_host(Lx, Ly, nup, ndn):
+    """The multi-GPU pattern of dist.py on the matrix-free species product: every rank owns a range of up configurations and
+    multiplies column part p when the slice of rank p has arrived -- own part first (peer pulls) or in rank order (pipelined
+    broadcasts, where a part WITHOUT the local pass opens the product).  Same __host__ __device__ functions as the kernels."""
+    ns, bonds = Lx * Ly, lb.square_bonds(Lx, Ly)
+    t, U = 1.0, 1.1
+    local, cross = sb.species_parts(ns, nup, ndn, bonds, t, U)
+    H = (local + cross).tocsr()
+    Du, Dd = sb.configurations(ns, nup).size, sb.configurations(ns, ndn).size
+    x = np.random.default_rng(5).standard_normal(Du * Dd)
+    L = _lib.lib()
+    b = np.ascontiguousarray(np.asarray(bonds, dtype=np.int32).reshape(-1, 2))
+    p = lambda a: C.c_void_p(a.ctypes.data)   # noqa: E731
+    for world in (2, 3, 5):
+        chunk = -(-Du // world)
+        pb = np.array([min(Du, q * chunk) for q in range(world)] + [Du], dtype=np.int64)
+        for rank in range(world):
+            u_lo, u_hi = int(pb[rank]), int(pb[rank + 1])
+            want = (H @ x)[u_lo * Dd:u_hi * Dd]
+            for order in ([rank] + [q for q in range(world) if q != rank], list(range(world)), list(range(world))[::-1]):
+                o = np.array(order, dtype=np.int32)
+                y = np.full(max(1, (u_hi - u_lo) * Dd), 7.0)                # must be overwritten, not accumulated into
+                _lib.check(L.qbgpu_debug_species_parts_host(ns, nup, ndn, b.shape[0], p(b), t, U, 32, u_lo, u_hi, world, p(pb), p(o), p(x), p(y)))
+                if u_hi > u_lo:
+                    assert np.linalg.norm(y[:want.size] - want) <= 1e-13 * np.linalg.norm(want), (world, rank, order)
+
+
 def test_bad_arguments_fail_loudly():
     L = _lib.lib()
     b = np.array([[0, 1]], dtype=np.int32)

@@ -339,3 +339,42 @@ def test_opt_in_real_mode_of_the_plain_product(oracle):
         for j in range(2):
             assert rel_l2(outs[("on", tag)][j], outs[("off", tag)][j]) <= 1e-15      # (bit-identical by construction; not required)
     assert rel_l2(outs[("on", "real")][0], ex["y1"]) <= TOL_MV
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_matrix_free_row_shards_and_column_parts(world):
+    """Multi-GPU building blocks of the matrix-free species product on one device: every 'rank' holds a shard of whole up
+    configurations, split into one column part per owner; multiplying the parts in the exchange's order (own part first, or
+    rank order) reproduces the rows of the full product.  Vectors are in the internal order (shards have no permutation)."""
+    import ctypes as C
+    from quantum_basis_b200 import dist
+    ns, nu, nd, bonds, U, mk = _case("hub3x3_45")
+    full = mk(mf=True)
+    n = full.dim
+    Du = SB.configurations(ns, nu).size
+    Dd = n // Du
+    rng = np.random.default_rng(8)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    xd, yd = qb.DeviceVector.from_numpy(x), qb.DeviceVector(n)
+    L = qb.lib()
+    one, zero = (C.c_double * 2)(1.0, 0.0), (C.c_double * 2)(0.0, 0.0)
+    _lib.check(L.qbgpu_spmv_fused(full.handle, C.c_void_p(xd.ptr), None, C.c_void_p(yd.ptr), one, zero, zero, None))   # internal order
+    want = yd.to_numpy()
+    chunk = -(-Du // world) * Dd
+    bounds = [min(n, q * chunk) for q in range(world)] + [n]
+    for rank in range(world):
+        lo, hi = bounds[rank], bounds[rank + 1]
+        S = qb.hubbard(ns, nu, nd, bonds, 1.0, U, matrix_free=True, flags=SPECIES, rows=(lo, hi))
+        assert not S.has_internal_order() and S.info.row_lo == lo and S.info.row_hi == hi
+        ys = qb.DeviceVector.from_numpy(np.full(hi - lo, 5.0 + 1.0j))
+        S.MultMv(xd, ys)                                              # the unsplit shard
+        assert rel_l2(ys.to_numpy(), want[lo:hi]) <= 1e-14
+        parts = dist.DeviceKernels.split(qb, S, bounds)
+        for order in ([rank] + [q for q in range(world) if q != rank], list(range(world))):
+            yp = qb.DeviceVector.from_numpy(np.full(hi - lo, -3.0 + 2.0j))
+            for k, p in enumerate(order):
+                b = (C.c_double * 2)(0.0 if k == 0 else 1.0, 0.0)
+                _lib.check(L.qbgpu_zmv(parts[p].handle, one, C.c_void_p(xd.ptr), b, C.c_void_p(yp.ptr), 1))
+            assert rel_l2(yp.to_numpy(), want[lo:hi]) <= 1e-14, (rank, order)
+    with pytest.raises(qb.QbgpuError):
+        qb.hubbard(ns, nu, nd, bonds, 1.0, U, matrix_free=True, flags=SPECIES, rows=(0, Dd + 1))   # not whole up configurations

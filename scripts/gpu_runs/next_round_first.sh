@@ -18,3 +18,6 @@ for W in 64 128 256 512; do
 done
 # 3. the term-coded replay kernel v3 left over from round 1
 QBGPU_TERMS_KERNEL=3 timeout 300 python scripts/terms_check.py > gpurun_out/terms_check_v3.txt 2>&1; tail -3 gpurun_out/terms_check_v3.txt
+# 4. the C++ examples through the adaptor (reference asserts: chain L = 16 all momenta; Hubbard 4x2 E0, all three handle kinds)
+g++ -std=c++17 -O2 -I include examples/square_fermi_hubbard.cc -L quantum_basis_b200 -lqbgpu -Wl,-rpath,$PWD/quantum_basis_b200 -o /tmp/square_fermi_hubbard \
+  && /tmp/square_fermi_hubbard 4 2 4 4 > gpurun_out/example_hubbard.txt 2>&1; echo "example rc=$?" >> gpurun_out/example_hubbard.txt; cat gpurun_out/example_hubbard.txt

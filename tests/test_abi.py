@@ -186,18 +186,19 @@ int main() {
     assert "sector:" in r.stdout and "csr_mat:" in r.stdout and "failed" in r.stdout
 
 
-def test_cpp_example_builds_against_the_library(tmp_path):
-    """examples/chain_heisenberg_momentum.cc (the reference's chain example through the adaptor) compiles and links; without
-    a device it stops with the library's error message and a non-zero status."""
+@pytest.mark.parametrize("src,args", [("chain_heisenberg_momentum.cc", ["12"]), ("square_fermi_hubbard.cc", ["4", "2", "4", "4"])])
+def test_cpp_example_builds_against_the_library(tmp_path, src, args):
+    """The reference's chain and square-lattice Hubbard examples through the C++ adaptor compile and link; without a device
+    they stop with the library's error message and a non-zero status."""
     import shutil
     import subprocess
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("no g++")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = tmp_path / "chain_example"
+    exe = tmp_path / "example"
     libdir = os.path.join(root, "quantum_basis_b200")
-    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "chain_heisenberg_momentum.cc"),
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", src),
                     "-o", str(exe), "-L", libdir, "-lqbgpu", "-Wl,-rpath," + libdir], check=True)
-    r = subprocess.run([str(exe), "12"], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    r = subprocess.run([str(exe)] + args, capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 2 and "no CUDA device" in r.stderr

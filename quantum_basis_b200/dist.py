@@ -18,12 +18,26 @@ import time
 import numpy as np
 
 
-def equal_row_bounds(n, parts):
+# Rows per owner are a multiple of this.  32: no 32-byte sector of a vector and no 32-row slice of the layout straddles two
+# owners.  Species-order shards (whole up configurations, csrc/species.cu) set it to a multiple of D_dn before the operators
+# are built -- species_row_align() -- and restore it afterwards.
+ROW_ALIGN = 32
+
+
+def species_row_align(d_dn):
+    """Alignment for shards of a species-order handle: whole up configurations (multiples of D_dn rows) and, for fp64
+    vectors, a multiple of 4 rows so that no 32-byte sector straddles two owners."""
+    from math import gcd
+    return d_dn * 4 // gcd(d_dn, 4)
+
+
+def equal_row_bounds(n, parts, align=None):
     """Contiguous row partition with equal row counts (the last block may be shorter); chunk = rows per block, a multiple
-    of 32 so that no 32-byte sector of a vector (and no 32-row slice of the layout) straddles two owners."""
+    of `align` (default: the module's ROW_ALIGN)."""
+    align = ROW_ALIGN if align is None else align
     chunk = (n + parts - 1) // parts
     if parts > 1:
-        chunk = (chunk + 31) // 32 * 32
+        chunk = (chunk + align - 1) // align * align
     return [min(n, p * chunk) for p in range(parts + 1)], chunk
 
 

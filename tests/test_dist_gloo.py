@@ -364,3 +364,74 @@ def test_peer_exchange_operator_logic_with_empty_blocks(schedule):
             assert sched.startswith("matching") and got == sorted(p for p in range(world) if p != r and (p - r) % world != 2)
         else:
             assert sched == "ring" and got == sorted(p for p in range(world) if p != r)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The same orchestration over shards of a species-order handle (csrc/species.cu): rows per owner are whole up
+# configurations (dist.ROW_ALIGN = species_row_align(D_dn)) and the vectors are in the internal order.  The kernels are the
+# oracle-backed ones above on P H P^T; what is under test is that nothing in the operators depends on the 32-row alignment.
+def _species_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import scipy.sparse as sp
+    import oracle_lib as O
+    import species_builders as SB
+    from quantum_basis_b200 import dist as qdist
+    A, meta, ex = O.load_golden("hubbard4x2")                    # 4x2, N_up = N_dn = 4: D_up = D_dn = 70
+    n = A.dim
+    perm = SB.species_perm(8, 4, 4)
+    P = sp.csr_matrix((np.ones(n), (perm, np.arange(n))), shape=(n, n))
+    F = (P @ A.to_scipy_full() @ P.T).tocsr()
+    d_dn = 70
+    qdist.ROW_ALIGN = qdist.species_row_align(d_dn)
+    bounds, chunk = qdist.equal_row_bounds(n, world)
+    assert chunk % d_dn == 0 and chunk % 4 == 0 and all(b % d_dn == 0 for b in bounds)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    kern = OracleKernels(F[lo:hi], lo, hi, n)
+    x = np.empty(n, dtype=np.complex128); x[perm] = O.vec_randomize(n, 1)
+    want = np.empty(n, dtype=np.complex128); want[perm] = ex["y1"]
+    x_loc = kern.alloc(chunk)
+    OracleKernels._c(x_loc)[: hi - lo] = x[lo:hi]
+    errs = []
+    op = qdist.ShardedOperator(kern, n, rank, world, qdist.TorchComm())
+    y_loc = kern.alloc(chunk)
+    op.matvec(x_loc, y_loc)
+    errs.append(np.linalg.norm(OracleKernels._c(y_loc)[: hi - lo] - want[lo:hi]) / np.linalg.norm(want[lo:hi]))
+    pop = qdist.PipelinedOperator(kern, n, rank, world, qdist.TorchComm())
+    kern.set_col_bounds(pop.col_bounds)
+    y2 = kern.alloc(chunk)
+    pop.matvec(x_loc, y2)
+    errs.append(np.linalg.norm(OracleKernels._c(y2)[: hi - lo] - want[lo:hi]) / np.linalg.norm(want[lo:hi]))
+    state = torch.zeros(8, dtype=torch.float64); state[0] = 1.0
+    a_dev = torch.zeros(64, dtype=torch.float64); b_dev = torch.zeros(64, dtype=torch.float64)
+    qdist.pipelined_lanczos(pop, x_loc.clone(), kern.alloc(chunk), 64, 25, state, a_dev, b_dev)
+    q.put((rank, max(errs), a_dev.numpy().copy(), b_dev.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_species_aligned_shards_over_gloo(world, oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_species_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    A, meta, ex = oracle.load_golden("hubbard4x2")
+    for rank, err, a_s, b_s in res:
+        assert err < 1e-13
+        assert np.abs(a_s[:20] - ex["dn_a"][:20]).max() < 1e-10  # the compiled reference's coefficients: the order does not matter
+        assert np.abs(b_s[1:20] - ex["dn_b"][1:20]).max() < 1e-10
+
+
+def test_species_row_align():
+    from quantum_basis_b200.dist import species_row_align, equal_row_bounds
+    assert species_row_align(12870) == 25740 and species_row_align(70) == 140 and species_row_align(924) == 924
+    b, chunk = equal_row_bounds(165636900, 8, align=species_row_align(12870))
+    assert chunk % 12870 == 0 and b[-1] == 165636900 and all(x % 12870 == 0 for x in b)

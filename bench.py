@@ -356,6 +356,9 @@ def main():
     ap.add_argument("--no-lanczos", action="store_true", help="skip the E0 time-to-solution leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-species", action="store_true", help="skip the species-order probe (hubbard workloads, child process)")
+    ap.add_argument("--layout", default="default", choices=["default", "species", "species-matfree"],
+                    help="hubbard workloads, one GPU: measure the main line on a QBGPU_SPECIES_ORDER handle (stored or matrix-free) "
+                         "instead of the ordinary one; same operator, same calling convention (vectors in the reference's order)")
     ap.add_argument("--species-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.species_probe:
@@ -390,11 +393,20 @@ def main():
 
     # ---------------------------------------------------------------- single GPU
     t0 = time.time()
-    M = build_matrix(qb, args.workload)
+    if args.layout == "default":
+        M = build_matrix(qb, args.workload)
+    else:
+        fam_, p_ = WORKLOADS[args.workload]
+        if fam_ != "hubbard":
+            raise SystemExit("--layout species*: the species order exists for the Hubbard model only")
+        M = qb.hubbard(p_["Lx"] * p_["Ly"], p_["nup"], p_["ndn"], square_bonds(p_["Lx"], p_["Ly"]), p_["t"], p_["U"],
+                       flags=128, matrix_free=(args.layout == "species-matfree"))
     torch.cuda.synchronize()
     t_build = time.time() - t0
     inf = M.info
     n, Z = inf.n, inf.nnz_stored
+    if Z == 0:                                   # matrix-free: the algorithmic bytes of SURVEY 8d refer to the stored operator
+        Z = 2 * workload_upper_nnz(args.workload) - n
     s_val = 8 if inf.val_is_real else 16
     s_vec = 16
     B = algorithmic_bytes(Z, n, n, s_val, s_vec)
@@ -488,12 +500,15 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "reference_upper_entries": workload_upper_nnz(args.workload),
-                       "S_val": s_val, "S_vec": s_vec, "layout": "sliced-jagged" if inf.format == 8 else f"csr-vector lanes={inf.lanes}",
+                       "S_val": s_val, "S_vec": s_vec,
+                       "layout": ({"species": "species order, two sliced-jagged parts", "species-matfree": "species order, matrix-free"}[args.layout]
+                                  if args.layout != "default" else "sliced-jagged" if inf.format == 8 else f"csr-vector lanes={inf.lanes}"),
                        "l2": "flush between steps" if need_flush else "inputs larger than L2", "matrix_bytes": inf.device_bytes,
                        "vectors": "complex128 x and y (the reference's model<complex<double>> calling convention)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_NCU.get(args.workload), "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
-                         "kernel": "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel"},
+                         "traffic": TRAFFIC_NCU.get(args.workload) if args.layout == "default" else None, "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
+                         "kernel": ("kron_local_kernel + kron_cross_kernel" if args.layout == "species-matfree" else
+                                    "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel")},
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
                     "ms_per_step": 1e3 * e2e_s},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,

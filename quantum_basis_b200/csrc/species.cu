@@ -805,9 +805,19 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
     const bool cplx = A->api_complex;
     const size_t vb = cplx ? 16 : 8;
     const size_t bytes = vb * (size_t)A->n;
-    if (A->borrowed) return fail(QBGPU_ERR_STATE, "mv on a view of a species-order handle: use the owning handle");
-    if (!A->perm_x) QB_CUDA(cudaMalloc(&A->perm_x, bytes));
-    if (!A->perm_y) QB_CUDA(cudaMalloc(&A->perm_y, bytes));
+    // staging vectors in the internal order: the handle's own (lazily allocated, freed by destroy); a view (e.g. the fp64
+    // view of qbgpu_real_view) owns nothing and borrows the context's staging vectors, which host-vector products need themselves
+    void *px = nullptr, *py = nullptr;
+    if (!A->borrowed) {
+        if (!A->perm_x) QB_CUDA(cudaMalloc(&A->perm_x, bytes));
+        if (!A->perm_y) QB_CUDA(cudaMalloc(&A->perm_y, bytes));
+        px = A->perm_x; py = A->perm_y;
+    } else {
+        if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_STATE, "host-vector products on a view of a species-order handle: use the owning handle");
+        if (c.stage_x_bytes < bytes) { if (c.stage_x) QB_CUDA(cudaFree(c.stage_x)); c.stage_x = nullptr; c.stage_x_bytes = 0; QB_CUDA(cudaMalloc(&c.stage_x, bytes)); c.stage_x_bytes = bytes; }
+        if (c.stage_y_bytes < bytes) { if (c.stage_y) QB_CUDA(cudaFree(c.stage_y)); c.stage_y = nullptr; c.stage_y_bytes = 0; QB_CUDA(cudaMalloc(&c.stage_y, bytes)); c.stage_y_bytes = bytes; }
+        px = c.stage_x; py = c.stage_y;
+    }
     const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
     const void *xd = x;
     void *yd = y;
@@ -818,11 +828,11 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
         if (use_beta) QB_CUDA(cudaMemcpyAsync(c.stage_y, y, bytes, cudaMemcpyHostToDevice, c.stream));
         xd = c.stage_x; yd = c.stage_y;
     } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
-    QB_TRY(vec_to_native(A, cplx, cplx, xd, A->perm_x));
+    QB_TRY(vec_to_native(A, cplx, cplx, xd, px));
     FusedArgs fa;
-    fa.x = A->perm_x; fa.y = A->perm_y;
+    fa.x = px; fa.y = py;
     QB_TRY(launch_spmv(A, fa));
-    QB_TRY(vec_from_native(A, cplx, cplx, A->perm_y, yd, alpha, beta));
+    QB_TRY(vec_from_native(A, cplx, cplx, py, yd, alpha, beta));
     if (where == QBGPU_HOST) {
         QB_CUDA(cudaMemcpyAsync(y, yd, bytes, cudaMemcpyDeviceToHost, c.stream));
         QB_CUDA(cudaStreamSynchronize(c.stream));

@@ -21,3 +21,7 @@ QBGPU_TERMS_KERNEL=3 timeout 300 python scripts/terms_check.py > gpurun_out/term
 # 4. the C++ examples through the adaptor (reference asserts: chain L = 16 all momenta; Hubbard 4x2 E0, all three handle kinds)
 g++ -std=c++17 -O2 -I include examples/square_fermi_hubbard.cc -L quantum_basis_b200 -lqbgpu -Wl,-rpath,$PWD/quantum_basis_b200 -o /tmp/square_fermi_hubbard \
   && /tmp/square_fermi_hubbard 4 2 4 4 > gpurun_out/example_hubbard.txt 2>&1; echo "example rc=$?" >> gpurun_out/example_hubbard.txt; cat gpurun_out/example_hubbard.txt
+# 5. the full bench line on the species-order handles (headline contract: reference-order vectors, e2e, Lanczos, clocks)
+for lay in species species-matfree; do
+  timeout 900 python bench.py --layout $lay --no-species --no-cpu > gpurun_out/bench_layout_$lay.json 2> gpurun_out/bench_layout_$lay.err; tail -c 1200 gpurun_out/bench_layout_$lay.json
+done

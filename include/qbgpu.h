@@ -188,6 +188,10 @@ int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double h
  * length n, HOST or DEVICE per `where`, element type of the handle.  *nconv = converged pairs, *nprod = products used. */
 int qbgpu_trlan(qbgpu_matrix_t A, int nev, int ncv, int maxit, double tol, int *nconv, int *nprod, double *eigenvals,
                 void *eigenvecs, int where);
+/* The same for the algebraically LARGEST eigenvalues (the iram(..., "lr") call of model<T>::locate_Emax_iram,
+ * src/model.cc:1370-1422): the iteration runs on -H; eigenvals come back in descending order. */
+int qbgpu_trlan_largest(qbgpu_matrix_t A, int nev, int ncv, int maxit, double tol, int *nconv, int *nprod, double *eigenvals,
+                        void *eigenvecs, int where);
 /* host-side dense Hermitian eigensolver used for the projected matrix (cyclic complex Jacobi): a and s are m x m complex,
  * column-major; w ascending, columns of s are the eigenvectors */
 int qbgpu_herm_eigen(int m, const void *a_colmajor, double *w, void *s_colmajor);

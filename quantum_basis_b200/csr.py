@@ -530,14 +530,15 @@ def iram(dim, mat, v0, nev, ncv, maxit, order="sr"):
     return len(w), w[idx], U[:, idx]
 
 
-def trlan(mat, nev, ncv, maxit=0, tol=0.0, vectors=True):
-    """Device-resident thick-restart Lanczos (qbgpu_trlan): the `nev` lowest eigenpairs with `ncv` basis vectors in HBM.
-    Returns (nconv, eigenvals[nev], eigenvecs[n, nev] or None, products)."""
+def trlan(mat, nev, ncv, maxit=0, tol=0.0, vectors=True, largest=False):
+    """Device-resident thick-restart Lanczos (qbgpu_trlan): the `nev` lowest (or, largest=True, highest) eigenpairs with
+    `ncv` basis vectors in HBM.  Returns (nconv, eigenvals[nev], eigenvecs[n, nev] or None, products)."""
     w = np.zeros(nev)
     U = np.zeros(mat.dim * nev, dtype=mat.dtype) if vectors else None
     nconv, nprod = C.c_int(0), C.c_int(0)
-    check(lib().qbgpu_trlan(mat.handle, nev, ncv, maxit, tol, C.byref(nconv), C.byref(nprod), _ptr(w),
-                            _ptr(U) if vectors else None, _lib.QBGPU_HOST))
+    f = lib().qbgpu_trlan_largest if largest else lib().qbgpu_trlan
+    check(f(mat.handle, nev, ncv, maxit, tol, C.byref(nconv), C.byref(nprod), _ptr(w),
+            _ptr(U) if vectors else None, _lib.QBGPU_HOST))
     return nconv.value, w, (U.reshape(nev, mat.dim).T if vectors else None), nprod.value
 
 
@@ -572,6 +573,31 @@ def locate_E0_iram(mat, nev=2, ncv=6, maxit=0, device_resident=False):
     if nconv > 1:
         out["gap"] = w[1] - w[0]
     return out
+
+
+def locate_Emax_iram(mat, nev=2, ncv=6, maxit=0, device_resident=False, fake_pos=100.0):
+    """The csr_mat branch of model<T>::locate_Emax_iram (src/model.cc:1370-1422): the highest eigenpairs (order "lr");
+    Emax = the first eigenvalue below fake_pos (momentum sectors carry artificial diagonal entries >= fake_pos for their
+    zero-norm representatives, src/model.cc:737-740, 1417-1421).  Returns dict(eigenvals, eigenvecs, nconv, Emax)."""
+    if not (nev > 0 and ncv > nev + 1):
+        raise QbgpuError("need nev > 0 and ncv > nev + 1")                        # the reference's asserts, :1388-1389
+    if maxit <= 0:
+        maxit = nev * 100                                                        # :1390
+    if device_resident and mat.dim > 30:
+        nconv, w, U, nprod = trlan(mat, nev, ncv, maxit, largest=True)
+        vecs = [U[:, j].copy() for j in range(nev)]
+    else:
+        v0 = np.ones(mat.dim, dtype=mat.dtype)                                   # :1403
+        nconv, w, U = iram(mat.dim, mat, v0, nev, ncv, max(maxit, 20), "lr")
+        vecs = [U[:, j].copy() for j in range(U.shape[1])]
+    if nconv <= 0:
+        raise QbgpuError("locate_Emax_iram: nothing converged")                   # the reference's assert, :1413
+    emax = w[0]
+    for e in w[:max(nconv, 1)]:                                                  # :1417-1421
+        if e < fake_pos:
+            emax = e
+            break
+    return {"eigenvals": list(w), "eigenvecs": vecs, "nconv": nconv, "Emax": emax}
 
 
 def locate_E0_lanczos(mat, nev=1, ncv=1, maxit=1000, device_vectors=False):

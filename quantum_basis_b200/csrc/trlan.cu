@@ -207,8 +207,10 @@ static int multi_axpy(int64_t n, int64_t ld, const VecT *V, int nc, const double
 
 // ------------------------------------------------------------------------------------------------- driver
 template <typename VecT>
+// largest: the algebraically largest eigenvalues (ARPACK's "LA", the reference's order "lr"): the same iteration on -H --
+// every product is taken with alpha = -1 -- and the Ritz values negated on the way out.
 static int trlan_typed(qbgpu_matrix *A, int nev, int ncv, int maxit, double tol, int *nconv_out, int *nprod_out, double *evals,
-                       void *evecs, int where, uint32_t seed)
+                       void *evecs, int where, uint32_t seed, bool largest = false)
 {
     Context &c = ctx();
     constexpr bool cplx = sizeof(VecT) == 16;
@@ -237,6 +239,7 @@ static int trlan_typed(qbgpu_matrix *A, int nev, int ncv, int maxit, double tol,
         for (int j = k; j < ncv; j++) {                    // extend the basis: columns k..ncv-1, residual in column ncv
             FusedArgs fa;
             fa.x = col(j); fa.y = col(j + 1);
+            if (largest) fa.alpha = make_double2(-1.0, 0.0);
             QB_TR(launch_spmv(A, fa));
             nprod++;
             // classical Gram-Schmidt against columns 0..j, repeated when the DGKS test asks for it
@@ -298,7 +301,7 @@ static int trlan_typed(qbgpu_matrix *A, int nev, int ncv, int maxit, double tol,
         restarts++;
         // the next pass starts at j = keep: its Gram-Schmidt recomputes column `keep` of T (diagonal and couplings)
     }
-    for (int i = 0; i < nev; i++) evals[i] = theta[i];
+    for (int i = 0; i < nev; i++) evals[i] = largest ? -theta[i] : theta[i];
     if (evecs && A->perm) {
         // species-order handle: the basis lives in the handle's internal order; hand the Ritz vectors back in the reference's
         // (column ncv, the residual, is free by now and serves as the staging vector of host callers)
@@ -344,6 +347,19 @@ int qbgpu_trlan(qbgpu_matrix_t A, int nev, int ncv, int maxit, double tol, int *
     if (where != QBGPU_HOST && where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
     return A->api_complex ? trlan_typed<double2>(A, nev, ncv, maxit, tol, nconv, nprod, eigenvals, eigenvecs, where, 1)
                           : trlan_typed<double>(A, nev, ncv, maxit, tol, nconv, nprod, eigenvals, eigenvecs, where, 1);
+}
+
+int qbgpu_trlan_largest(qbgpu_matrix_t A, int nev, int ncv, int maxit, double tol, int *nconv, int *nprod, double *eigenvals, void *eigenvecs, int where)
+{
+    QB_TRY(ensure_init());
+    if (!A || !nconv || !eigenvals) return fail(QBGPU_ERR_ARG, "trlan: null argument");
+    if (A->row_lo != 0 || A->row_hi != A->n) return fail(QBGPU_ERR_STATE, "trlan needs an unsharded handle");
+    if (nev <= 0 || nev >= A->n - 1) return fail(QBGPU_ERR_ARG, "0 < nev < N-1 should be satisfied.");        // src/lanczos.cc:502
+    if (ncv <= nev + 1 || ncv > 48 || ncv >= A->n) return fail(QBGPU_ERR_ARG, "trlan: need nev + 1 < ncv <= 48 and ncv < N");   // src/model.cc:1389
+    if (maxit <= 0) maxit = nev * 100;                                                                       // src/model.cc:1390
+    if (where != QBGPU_HOST && where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
+    return A->api_complex ? trlan_typed<double2>(A, nev, ncv, maxit, tol, nconv, nprod, eigenvals, eigenvecs, where, 1, true)
+                          : trlan_typed<double>(A, nev, ncv, maxit, tol, nconv, nprod, eigenvals, eigenvecs, where, 1, true);
 }
 
 }  // extern "C"

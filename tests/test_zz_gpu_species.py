@@ -380,3 +380,21 @@ def test_matrix_free_row_shards_and_column_parts(world):
             assert rel_l2(yp.to_numpy(), want[lo:hi]) <= 1e-14, (rank, order)
     with pytest.raises(qb.QbgpuError):
         qb.hubbard(ns, nu, nd, bonds, 1.0, U, matrix_free=True, flags=SPECIES, rows=(0, Dd + 1))   # not whole up configurations
+
+
+@pytest.mark.parametrize("name", ["tri4x4_k01", "hubbard4x2"])
+def test_locate_Emax_iram(oracle, name):
+    """model<T>::locate_Emax_iram (src/model.cc:1370-1422): the highest eigenvalues through the host-ARPACK seam and through
+    the device-resident thick-restart Lanczos on -H; Emax skips the artificial states of zero-norm representatives."""
+    A, meta, ex = oracle.load_golden(name)
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    w = np.linalg.eigvalsh(M.to_dense())[::-1]
+    for dev in (False, True):
+        out = qb.locate_Emax_iram(M, nev=2, ncv=10, maxit=400, device_resident=dev)
+        assert out["nconv"] >= 1
+        assert abs(out["eigenvals"][0] - w[0]) <= 1e-9 * abs(w[0])
+        want = next(e for e in w if e < 100.0)
+        if out["Emax"] < 100.0:                                       # reached only when an eigenvalue below fake_pos is among the nev
+            assert abs(out["Emax"] - want) <= 1e-8 * abs(want)
+        v = out["eigenvecs"][0]
+        assert np.linalg.norm(oracle.spmv(A, v.copy()) - out["eigenvals"][0] * v) < 1e-6

@@ -266,6 +266,18 @@ int qbgpu_build_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, int nbonds,
                            int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                         double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* model::moprXvec_full (src/model.cc:1468-1538) for an operator made of one-site DIAGONAL terms, on a complex device vector
+ * in the reference's Lin order of the full basis the generators above use:
+ *   kind 0 (heisenberg, n0 = ndown):      A = sum_r coef0[r] S^z_r                          (coef1 ignored)
+ *   kind 1 (hubbard, n0 = nup, n1 = ndn): A = sum_r coef0[r] n_up,r + coef1[r] n_dn,r      (S^z_q: coef1 = -coef0)
+ * y_j = x_j * <state_j|A|state_j>, rows with |x_j| < 2e-12 skipped like the reference (:1500).  Followed by the norm, the
+ * scaling and qbgpu_lanczos_z(..., "dnmcs") this is model::measure_full_dynamic (src/model.cc:1697-1712), the dynamic part of
+ * the reference's examples/trans_absent/latt_square/square_Fermi_Hubbard.cc.  The _host variant runs the same row function
+ * on host arrays (test hook; no device is touched). */
+int qbgpu_full_apply_diag(int kind, int nsites, int n0, int n1, const double *coef0_reim, const double *coef1_reim,
+                          const void *x_dev, void *y_dev);
+int qbgpu_debug_full_apply_diag_host(int kind, int nsites, int n0, int n1, const double *coef0_reim, const double *coef1_reim,
+                                     const void *x_host, void *y_host);
 /* Matrix-free handles: the counterpart of the reference's model<T>::MultMv / MultMv2 with matrix_free == true
  * (src/model.cc:942-1121: every row is recomputed on the fly from the Hamiltonian terms and the Lin tables instead of
  * being read from a stored matrix).  Same arguments as the generators; nothing but the basis states (8 bytes per row)

@@ -106,8 +106,36 @@ def make_dynamic():
         print(f"{name}: dim={phi0.size} E0={res['E0']:.12f} norm={res['dyn_norm']:.12f} steps={res['dyn_steps']} -> {os.path.getsize(out)/1e3:.0f} kB")
 
 
+FULL_DYNAMIC_CASES = {
+    # name: (Lx, Ly, nup, ndn, t, U, qm, qn, maxit) -- qb_ref hubbard_full_szq: the dynamic part of
+    # examples/trans_absent/latt_square/square_Fermi_Hubbard.cc in the full basis (moprXvec_full + measure_full_dynamic,
+    # src/model.cc:1468-1538, 1697-1712) with S^z_q = sum_r 0.5/sqrt(N) exp(i q.r) (n_up,r - n_dn,r)
+    "hubbard4x2_szq10": (4, 2, 4, 4, 1.0, 1.1, 1, 0, 60),
+    "hubbard4x2_szq21": (4, 2, 4, 4, 1.0, 1.1, 2, 1, 60),
+}
+
+
+def make_full_dynamic():
+    only = sys.argv[2:]
+    for name, (Lx, Ly, nup, ndn, t, U, qm, qn, maxit) in FULL_DYNAMIC_CASES.items():
+        if only and name not in only:
+            continue
+        wd = tempfile.mkdtemp(prefix="qbfdyn_")
+        pre = os.path.join(wd, "v")
+        res = O.run_qb_ref(["hubbard_full_szq", Lx, Ly, nup, ndn, t, U, qm, qn, maxit, "--dump-vecs", pre], threads=4, workdir=wd)
+        phi0 = np.fromfile(pre + "_phi0.bin", dtype=np.complex128)
+        aphi = np.fromfile(pre + "_Aphi0.bin", dtype=np.complex128)
+        meta = {"case": name, "flow": "hubbard_full_szq", "Lx": Lx, "Ly": Ly, "nup": nup, "ndn": ndn, "t": t, "U": U, "qm": qm, "qn": qn,
+                "maxit": maxit, "E0": res["E0"], "dyn_norm": res["dyn_norm"], "dyn_steps": res["dyn_steps"]}
+        out = os.path.join(O.GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(out, phi0=phi0, Aphi0=aphi, dyn_a=np.array(res["dyn_a"]), dyn_b=np.array(res["dyn_b"]), meta=json.dumps(meta))
+        print(f"{name}: dim={phi0.size} E0={res['E0']:.12f} norm={res['dyn_norm']:.12f} steps={res['dyn_steps']} -> {os.path.getsize(out)/1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     if sys.argv[1:2] == ["dynamic"]:
         make_dynamic()
+    elif sys.argv[1:2] == ["full_dynamic"]:
+        make_full_dynamic()
     else:
         main()

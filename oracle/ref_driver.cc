@@ -318,6 +318,45 @@ static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxi
     js.arr("dyn_b", hess.data(), m); js.arr("dyn_a", hess.data() + maxit, m);
 }
 
+/* The dynamic part of examples/trans_absent/latt_square/square_Fermi_Hubbard.cc (:147-186) in the FULL basis: E0 and phi0 by
+   locate_E0_lanczos, then S^z_q phi0 (moprXvec_full, src/model.cc:1468-1538) with
+   S^z_q = sum_r 0.5/sqrt(N) exp(i q.r) (n_up,r - n_dn,r), and measure_full_dynamic's dnmcs coefficients (:1697-1712). */
+static void flow_hubbard_full_szq(int Lx, int Ly, double nup, double ndn, double t, double U, int qm, int qn, MKL_INT maxit,
+                                  const std::string &vec_prefix, Json &js)
+{
+    Built b = build_hubbard(Lx, Ly, nup, ndn, t, U);
+    Model &M = *b.model;
+    M.locate_E0_lanczos(qbasis::which_sym::full, 1, 1);
+    js.num("E0", M.eigenvals_full[0]);
+    js.integer("dim0", M.dim_full[0]);
+    qbasis::lattice latt("square", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    auto cu = std::vector<std::vector<cplx>>(4, std::vector<cplx>(4, 0.0));
+    auto cd = cu;
+    cu[0][1] = 1.0; cu[2][3] = 1.0; cd[0][2] = 1.0; cd[1][3] = -1.0;
+    Mopr Szq;
+    const double PI = 3.1415926535897932;
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) {
+        const double qdotr = 2.0 * PI * (qm * x / static_cast<double>(Lx) + qn * y / static_cast<double>(Ly));
+        auto coeff = 0.5 / sqrt(static_cast<double>(Lx * Ly)) * std::exp(cplx{0.0, qdotr});
+        uint32_t si; std::vector<int> work(latt.dim);
+        latt.coor2site({x, y}, 0, si, work);
+        Opr cui(si, 0, true, cu), cdi(si, 0, true, cd);
+        auto cuid = cui; cuid.dagger(); auto cdid = cdi; cdid.dagger();
+        Szq += coeff * (cuid * cui - cdid * cdi);
+    }
+    if (!vec_prefix.empty()) {
+        std::vector<cplx> vnew(M.dim_full[0]);
+        M.moprXvec_full(Szq, 0, 0, static_cast<MKL_INT>(0), vnew.data());
+        dump_vec(vec_prefix + "_phi0.bin", M.eigenvecs_full.data(), sizeof(cplx) * M.dim_full[0]);
+        dump_vec(vec_prefix + "_Aphi0.bin", vnew.data(), sizeof(cplx) * M.dim_full[0]);
+    }
+    std::vector<double> hess(2 * maxit, 0.0);
+    MKL_INT m = 0; double norm = 0.0;
+    M.measure_full_dynamic(Szq, 0, 0, maxit, m, norm, hess.data());
+    js.num("dyn_norm", norm); js.integer("dyn_steps", m);
+    js.arr("dyn_b", hess.data(), m); js.arr("dyn_a", hess.data() + maxit, m);
+}
+
 template <typename T>
 static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, Json &js)
 {
@@ -431,6 +470,7 @@ static void usage() {
         "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
+        "        hubbard_full_szq Lx Ly NUP NDN T U QM QN MAXIT [--dump-vecs PREFIX]  (full basis: E0, S^z_q phi0, measure_full_dynamic)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
         " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --cg-ckpt E0 MAXIT F | --energy-scale ITERS\n");
     exit(2);
@@ -479,6 +519,13 @@ int main(int argc, char **argv)
         std::string prefix;
         if (a + 1 < argc && std::string(argv[a]) == "--dump-vecs") { prefix = argv[a + 1]; a += 2; }
         flow_heis_chain_szq(L, sz, k0, q, maxit, prefix, js, c == "heis_chain_smq" ? 'm' : 'z');
+    } else if (c == "hubbard_full_szq") {
+        if (a + 9 > argc) usage();
+        int Lx = atoi(argv[a]), Ly = atoi(argv[a + 1]); double nu = atof(argv[a + 2]), nd = atof(argv[a + 3]), t = atof(argv[a + 4]), U = atof(argv[a + 5]);
+        int qm = atoi(argv[a + 6]), qn = atoi(argv[a + 7]); MKL_INT maxit = atoll(argv[a + 8]); a += 9;
+        std::string prefix;
+        if (a + 1 < argc && std::string(argv[a]) == "--dump-vecs") { prefix = argv[a + 1]; a += 2; }
+        flow_hubbard_full_szq(Lx, Ly, nu, nd, t, U, qm, qn, maxit, prefix, js);
     } else if (c == "file_z" || c == "file_d") {
         if (a >= argc) usage();
         std::string path = argv[a++];

@@ -416,6 +416,41 @@ def measure_repr_dynamic(coef, sec_old, sec_new, mat_new, phi0, maxit, hessenber
     return m, nr.value
 
 
+def full_apply_diag(kind, nsites, n0, n1, coef0, coef1, x, out=None):
+    """model::moprXvec_full (src/model.cc:1468-1538) for one-site diagonal operators on a full-basis vector in the reference's
+    Lin order: kind "heisenberg" (A = sum_r coef0[r] S^z_r, n0 = ndown) or "hubbard" (A = sum_r coef0[r] n_up,r + coef1[r] n_dn,r).
+    x: DeviceVector or host array (complex128) -> DeviceVector."""
+    k = {"heisenberg": 0, "hubbard": 1}[kind]
+    c0 = np.ascontiguousarray(coef0, dtype=np.complex128)
+    c1 = np.ascontiguousarray(coef1 if coef1 is not None else np.zeros(nsites), dtype=np.complex128)
+    if c0.size != nsites or c1.size != nsites:
+        raise QbgpuError("one coefficient per site")
+    xd = x if isinstance(x, DeviceVector) else DeviceVector.from_numpy(np.ascontiguousarray(x, dtype=np.complex128))
+    y = out if out is not None else DeviceVector(xd.n)
+    check(lib().qbgpu_full_apply_diag(k, nsites, n0, n1, C.c_void_p(c0.ctypes.data), C.c_void_p(c1.ctypes.data),
+                                      C.c_void_p(xd.ptr), C.c_void_p(y.ptr)))
+    return y
+
+
+def measure_full_dynamic(kind, nsites, n0, n1, coef0, coef1, mat, phi0, maxit, hessenberg):
+    """model<T>::measure_full_dynamic (src/model.cc:1697-1712) for one-site diagonal operators (e.g. S^z_q of the Hubbard
+    model: coef1 = -coef0), everything on the device: vec = A phi0, norm = |vec|, then lanczos(0, maxit-1, maxit, ..., "dnmcs")
+    from vec/norm on `mat` (a full-basis handle in the reference's order, ordinary or species).  Returns (m, norm)."""
+    n = mat.dim
+    v = DeviceVector(2 * n)
+    v.zero()
+    full_apply_diag(kind, nsites, n0, n1, coef0, coef1, phi0, out=v.view(0, n))
+    nr = C.c_double()
+    check(lib().qbgpu_dznrm2(n, C.c_void_p(v.ptr), C.byref(nr)))
+    if abs(nr.value) < lanczos_precision:
+        v.free()
+        return 0, nr.value
+    check(lib().qbgpu_zscal(n, (C.c_double * 2)(1.0 / nr.value, 0.0), C.c_void_p(v.ptr)))
+    m = lanczos(0, maxit - 1, maxit, n, mat, v, hessenberg, "dnmcs")
+    v.free()
+    return m, nr.value
+
+
 def vec_randomize(n, seed=1, dtype=np.complex128, device=False):
     """src/miscellaneous.cc:371-388, generated on the device."""
     v = DeviceVector(n, dtype)

@@ -427,6 +427,113 @@ __device__ __forceinline__ double row_entries_walk(const SectorTables &S, const 
     return diag;
 }
 
+// ------------------------------------------------------------------ one-site diagonal operators in the full basis
+// model::moprXvec_full (src/model.cc:1468-1538) for A = sum_r c_r O_r with O_r diagonal in the site basis -- S^z_r for spins
+// (digit 0 = up: +1/2), c0_r n_up,r + c1_r n_dn,r for electrons (S^z_q of the Hubbard model: c1 = -c0) -- on a vector in
+// the reference's Lin order: y_j = x_j * sum_r c_r <state_j| O_r |state_j>, rows with |x_j| < lanczos_precision skipped
+// (:1500).  With measure_full_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1697-1712, the
+// dynamic part of the reference's examples/trans_absent/latt_square/square_Fermi_Hubbard.cc.
+__host__ __device__ __forceinline__ double2 onsite_diag_weight(const SectorTables &S, int64_t r, const double2 *c0, const double2 *c1)
+{
+    uint32_t la, lb;
+    unrank_row(S, r, la, lb);
+    double2 w = make_double2(0.0, 0.0);
+    if (S.bps == 1) {
+        const uint32_t dn = spread16(la) | (spread16(lb) << 1);                          // bit s set = site s down
+        for (int s = 0; s < S.nsites; s++) {
+            const double sz = ((dn >> s) & 1u) ? -0.5 : 0.5;
+            w.x += c0[s].x * sz; w.y += c0[s].y * sz;
+        }
+    } else {
+        const uint32_t occ0 = (la & 0x55555555u) | ((lb & 0x55555555u) << 1);              // same words as row_entries_walk
+        const uint32_t occ1 = ((la >> 1) & 0x55555555u) | (lb & 0xAAAAAAAAu);
+        for (int s = 0; s < S.nsites; s++) {
+            if ((occ0 >> s) & 1u) { w.x += c0[s].x; w.y += c0[s].y; }
+            if ((occ1 >> s) & 1u) { w.x += c1[s].x; w.y += c1[s].y; }
+        }
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(kBBlock) full_apply_diag_kernel(SectorTables S, int64_t n, const double2 *__restrict__ c0g, const double2 *__restrict__ c1g,
+                                                                  const double2 *__restrict__ x, double2 *y)
+{
+    __shared__ double2 c0[32], c1[32];
+    if (threadIdx.x < 32) { c0[threadIdx.x] = c0g[threadIdx.x]; c1[threadIdx.x] = c1g[threadIdx.x]; }
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double2 xj = x[r];
+        double2 out = make_double2(0.0, 0.0);
+        if (hypot(xj.x, xj.y) >= 2e-12) {
+            const double2 w = onsite_diag_weight(S, r, c0, c1);
+            out = make_double2(xj.x * w.x - xj.y * w.y, xj.x * w.y + xj.y * w.x);
+        }
+        y[r] = out;
+    }
+}
+
+// host == true: the same row function on host arrays (CPU tests), nothing touches the device
+static int full_apply_diag(int kind, int nsites, int n0, int n1, const double *c0_reim, const double *c1_reim, const void *x, void *y, bool host)
+{
+    if (nsites < 2 || nsites > 32 || !c0_reim || !x || !y || (kind == 1 && !c1_reim) || (kind != 0 && kind != 1))
+        return fail(QBGPU_ERR_ARG, "full_apply_diag: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, kind == 0 ? 1 : 2, n0, kind == 0 ? 0 : n1, T));
+    if (T.dim <= 0) return fail(QBGPU_ERR_ARG, "full_apply_diag: empty sector");
+    double2 c0[32], c1[32];
+    for (int s = 0; s < 32; s++) {
+        c0[s] = s < nsites ? make_double2(c0_reim[2 * s], c0_reim[2 * s + 1]) : make_double2(0.0, 0.0);
+        c1[s] = (s < nsites && kind == 1) ? make_double2(c1_reim[2 * s], c1_reim[2 * s + 1]) : make_double2(0.0, 0.0);
+    }
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    if (host) {
+        S.Jb = T.Jb.data(); S.rankA = T.rankA.data(); S.alist = T.alist.data(); S.class_off = T.class_off.data();
+        const double2 *xs = (const double2 *)x;
+        double2 *ys = (double2 *)y;
+        for (int64_t r = 0; r < T.dim; r++) {
+            const double2 xj = xs[r];
+            double2 out = make_double2(0.0, 0.0);
+            if (hypot(xj.x, xj.y) >= 2e-12) {
+                const double2 w = onsite_diag_weight(S, r, c0, c1);
+                out = make_double2(xj.x * w.x - xj.y * w.y, xj.x * w.y + xj.y * w.x);
+            }
+            ys[r] = out;
+        }
+        return QBGPU_OK;
+    }
+    QB_TRY(ensure_init());
+    Context &c = ctx();
+    int64_t *d_Jb = nullptr;
+    int32_t *d_rank = nullptr, *d_off = nullptr;
+    uint32_t *d_alist = nullptr;
+    double2 *d_c = nullptr;
+    auto cleanup = [&]() { cudaFree(d_Jb); cudaFree(d_rank); cudaFree(d_off); cudaFree(d_alist); cudaFree(d_c); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_Jb, sizeof(int64_t) * T.Jb.size()));
+    QB_CU(cudaMalloc(&d_rank, sizeof(int32_t) * T.rankA.size()));
+    QB_CU(cudaMalloc(&d_alist, sizeof(uint32_t) * T.alist.size()));
+    QB_CU(cudaMalloc(&d_off, sizeof(int32_t) * T.class_off.size()));
+    QB_CU(cudaMalloc(&d_c, sizeof(double2) * 64));
+    QB_CU(cudaMemcpyAsync(d_Jb, T.Jb.data(), sizeof(int64_t) * T.Jb.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_rank, T.rankA.data(), sizeof(int32_t) * T.rankA.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_c, c0, sizeof(double2) * 32, cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_c + 32, c1, sizeof(double2) * 32, cudaMemcpyHostToDevice, c.stream));
+    S.Jb = d_Jb; S.rankA = d_rank; S.alist = d_alist; S.class_off = d_off;
+    int64_t g = (T.dim + kBBlock - 1) / kBBlock;
+    if (g > 148 * 64) g = 148 * 64;
+    full_apply_diag_kernel<<<(int)g, kBBlock, 0, c.stream>>>(S, T.dim, d_c, d_c + 32, (const double2 *)x, (double2 *)y);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));               // c0 / c1 live on this stack frame
+    QB_CU(cudaGetLastError());
+#undef QB_CU
+    cleanup();
+    return QBGPU_OK;
+}
+
 // The product with no stored matrix: one thread per row (32 consecutive rows per warp, like the sliced-jagged
 // kernel, so one Hamiltonian term sends the lanes of a warp to neighbouring columns), the row's entries regenerated by
 // row_entries() and consumed at once.  The reference's counterpart is model<T>::MultMv2 with matrix_free == true
@@ -1016,6 +1123,14 @@ int64_t matfree_bytes(const qbgpu_matrix *A) { return A->mf ? ((const MatFree *)
 using namespace qb;
 
 extern "C" {
+
+int qbgpu_full_apply_diag(int kind, int nsites, int n0, int n1, const double *coef0_reim, const double *coef1_reim,
+                          const void *x_dev, void *y_dev)
+{ return full_apply_diag(kind, nsites, n0, n1, coef0_reim, coef1_reim, x_dev, y_dev, false); }
+
+int qbgpu_debug_full_apply_diag_host(int kind, int nsites, int n0, int n1, const double *coef0_reim, const double *coef1_reim,
+                                     const void *x_host, void *y_host)
+{ return full_apply_diag(kind, nsites, n0, n1, coef0_reim, coef1_reim, x_host, y_host, true); }
 
 int64_t qbgpu_dim_heisenberg(int nsites, int ndown)
 {

@@ -155,3 +155,26 @@ def hubbard_upper_csr(nsites, nup, ndn, bonds, t=1.0, U=1.1, dtype=np.complex128
                 vals.append(np.where(sg == 1, -amp, amp))
     ia, ja, val = _to_upper_csr(n, np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))
     return n, ia, ja, val.astype(dtype)
+
+
+def square_szq_coefficients(Lx, Ly, qm, qn):
+    """coeff_r of S^z_q = sum_r coeff_r (n_up,r - n_dn,r) as examples/trans_absent/latt_square/square_Fermi_Hubbard.cc:156-160
+    builds it: 0.5/sqrt(N) exp(+i 2 pi (qm x/Lx + qn y/Ly)), site r = x + y*Lx."""
+    c = np.zeros(Lx * Ly, dtype=np.complex128)
+    for x in range(Lx):
+        for y in range(Ly):
+            c[x + y * Lx] = 0.5 / np.sqrt(Lx * Ly) * np.exp(2j * np.pi * (qm * x / Lx + qn * y / Ly))
+    return c
+
+
+def apply_onsite_diag(nsites, bps, counts, coef0, coef1, x, precision=2e-12):
+    """model::moprXvec_full (src/model.cc:1468-1538) for one-site diagonal operators in Lin order: spins (bps = 1):
+    sum_r coef0[r] S^z_r; electrons (bps = 2): sum_r coef0[r] n_up,r + coef1[r] n_dn,r.  Rows with |x_j| < precision are skipped."""
+    st = basis_states(nsites, bps, counts)
+    w = np.zeros(st.size, dtype=np.complex128)
+    for s in range(nsites):
+        if bps == 1:
+            w += coef0[s] * np.where((st >> s) & 1, -0.5, 0.5)
+        else:
+            w += coef0[s] * ((st >> (2 * s)) & 1) + coef1[s] * ((st >> (2 * s + 1)) & 1)
+    return np.where(np.abs(x) >= precision, x * w, 0.0)

@@ -208,3 +208,37 @@ def test_sector_sminus_operator_matches_reference_moprXvec(name):
     w[S1.nu == 0] = 0.0
     up = R.apply_splus(S1, S0, np.conj(R.szq_coefficients(L, q)), w)
     assert abs(np.vdot(w, y) - np.vdot(up, z["phi0"])) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["hubbard4x2_szq10", "hubbard4x2_szq21"])
+def test_full_basis_szq_matches_reference_moprXvec_full(name):
+    """model::moprXvec_full (src/model.cc:1468-1538) for S^z_q of the Hubbard model in the full basis: the numpy restatement
+    and the library's row function (run on the host through qbgpu_debug_full_apply_diag_host) against the vector the
+    compiled reference produced in the flow of examples/trans_absent/latt_square/square_Fermi_Hubbard.cc (golden)."""
+    import ctypes as C
+    import json
+    import os
+    import lin_builders as LB
+    from quantum_basis_b200 import _lib
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    Lx, Ly, nup, ndn = meta["Lx"], meta["Ly"], meta["nup"], meta["ndn"]
+    c = LB.square_szq_coefficients(Lx, Ly, meta["qm"], meta["qn"])
+    y = LB.apply_onsite_diag(Lx * Ly, 2, (nup, ndn), c, -c, z["phi0"])
+    assert np.abs(y - z["Aphi0"]).max() < 1e-15
+    assert abs(np.linalg.norm(y) - meta["dyn_norm"]) < 1e-14
+    yl = np.zeros_like(y)
+    c0, c1, x = np.ascontiguousarray(c), np.ascontiguousarray(-c), np.ascontiguousarray(z["phi0"])
+    p = lambda a: C.c_void_p(a.ctypes.data)   # noqa: E731
+    _lib.check(_lib.lib().qbgpu_debug_full_apply_diag_host(1, Lx * Ly, nup, ndn, p(c0), p(c1), p(x), p(yl)))
+    assert np.abs(yl - z["Aphi0"]).max() < 1e-15
+    # spins through the same entry point: S^z_total on any Sz-sector vector is Sz times the vector
+    n = 924
+    xs = (np.random.default_rng(1).standard_normal(n) + 0j)
+    ys = np.zeros(n, dtype=np.complex128)
+    ones = np.ones(12, dtype=np.complex128)
+    _lib.check(_lib.lib().qbgpu_debug_full_apply_diag_host(0, 12, 6, 0, p(ones), p(ones), p(xs), p(ys)))
+    assert np.abs(ys).max() < 1e-15                                   # Sz_total = 0 at half filling
+    _lib.check(_lib.lib().qbgpu_debug_full_apply_diag_host(0, 12, 5, 0, p(ones), p(ones), p(np.ascontiguousarray(xs[:792])), p(ys)))
+    assert np.abs(ys[:792] - 1.0 * xs[:792]).max() < 1e-15            # 7 up, 5 down: Sz_total = +1
+    assert np.array_equal(LB.apply_onsite_diag(12, 1, (5,), ones, None, xs[:792]), ys[:792])

@@ -398,3 +398,26 @@ def test_locate_Emax_iram(oracle, name):
             assert abs(out["Emax"] - want) <= 1e-8 * abs(want)
         v = out["eigenvecs"][0]
         assert np.linalg.norm(oracle.spmv(A, v.copy()) - out["eigenvals"][0] * v) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["hubbard4x2_szq10", "hubbard4x2_szq21"])
+def test_full_basis_dynamic_flow_matches_the_reference(name):
+    """model::moprXvec_full + measure_full_dynamic (src/model.cc:1468-1538, 1697-1712) for S^z_q of the Hubbard model -- the
+    dynamic part of the reference's examples/trans_absent/latt_square/square_Fermi_Hubbard.cc -- on the ordinary handle and on
+    both species-order handles, against the vector and the Lanczos coefficients of the compiled reference (golden)."""
+    import json
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    Lx, Ly, nup, ndn, maxit = meta["Lx"], meta["Ly"], meta["nup"], meta["ndn"], meta["maxit"]
+    ns, bonds = Lx * Ly, B.square_bonds(Lx, Ly)
+    c = B.square_szq_coefficients(Lx, Ly, meta["qm"], meta["qn"])
+    y = qb.full_apply_diag("hubbard", ns, nup, ndn, c, -c, z["phi0"]).to_numpy()
+    assert np.abs(y - z["Aphi0"]).max() < 1e-15
+    for kw in (dict(), dict(flags=SPECIES), dict(flags=SPECIES, matrix_free=True)):
+        M = qb.hubbard(ns, nup, ndn, bonds, meta["t"], meta["U"], **kw)
+        hess = np.zeros(2 * maxit)
+        m, norm = qb.measure_full_dynamic("hubbard", ns, nup, ndn, c, -c, M, z["phi0"], maxit, hess)
+        assert abs(norm - meta["dyn_norm"]) < 1e-13
+        k = min(m, 12)
+        assert np.abs(hess[maxit:maxit + k] - z["dyn_a"][:k]).max() < 1e-9, kw
+        assert np.abs(hess[1:k] - z["dyn_b"][1:k]).max() < 1e-9, kw

@@ -405,7 +405,18 @@ __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, co
     VecT acc = VT::zero();
     mac(acc, diagk[popc_hd(U & D)], xi);
     const int e1 = ld_ro(V.dptr + id + 1);
-    for (int e = ld_ro(V.dptr + id); e < e1; e += 4) {
+    int e = ld_ro(V.dptr + id);
+    for (; e + 4 <= e1; e += 4) {                           // full trips: no bounds checks
+        uint2 h[4];
+        VecT xv[4];
+QB_UNROLL
+        for (int u = 0; u < 4; u++) h[u] = ld_ro(V.dhop + e + u);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + h[u].x); else xv[u] = xb[h[u].x]; }
+QB_UNROLL
+        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
+    }
+    if (e < e1) {                                           // the last, partial trip: past the end it replays 0 * x[own row]
         uint2 h[4];
         VecT xv[4];
 QB_UNROLL
@@ -542,13 +553,27 @@ __host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, co
     const uint32_t D = ld_ro(V.dlist + idc);
     const int e1 = ld_ro(V.uptr + iu + 1);
     VecT acc = VT::zero();
-    for (int e = ld_ro(V.uptr + iu); e < e1; e += 4) {
+    int e = ld_ro(V.uptr + iu);
+    for (; e + 4 <= e1; e += 4) {                           // full trips: no bounds checks (the list is warp-uniform)
+        uint2 h[4];
+        VecT xv[4];
+QB_UNROLL
+        for (int u = 0; u < 4; u++) {
+            h[u] = ld_ro(V.uhop + e + u);
+            if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);   // replays 0 * x[own row]
+        }
+QB_UNROLL
+        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);
+QB_UNROLL
+        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, D, ampw), xv[u]);
+    }
+    if (e < e1) {                                           // the last, partial trip
         uint2 h[4];
         VecT xv[4];
 QB_UNROLL
         for (int u = 0; u < 4; u++) {
             h[u] = (e + u < e1) ? ld_ro(V.uhop + e + u) : make_uint2((uint32_t)iu, 0u);
-            if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);   // replays 0 * x[own row]
+            if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);
         }
 QB_UNROLL
         for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);

@@ -81,8 +81,13 @@ struct SpeciesView {
 __host__ __device__ __forceinline__ double hop_value(uint32_t meta, uint32_t other, const double *ampw)
 {
     const double a = ampw[meta >> 25];
-    const int sg = (int)((meta >> 24) & 1u) ^ (popc_hd(other & (meta & kHopMask)) & 1);
+    const uint32_t sg = ((meta >> 24) ^ (uint32_t)popc_hd(other & (meta & kHopMask))) & 1u;
+    // flip the sign bit with integer logic (a select on the two halves plus a negation on the fp64 pipe otherwise)
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(a) ^ (int)(sg << 31), __double2loint(a));
+#else
     return sg ? -a : a;
+#endif
 }
 
 struct SpeciesHost {

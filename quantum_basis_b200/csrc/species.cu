@@ -400,10 +400,11 @@ int64_t species_bytes(const qbgpu_matrix *A)
 // pass 1: y = alpha * (diagonal + down hops) x + gamma x + beta z.  One thread per row, rows ascending: the gathers of a
 // row fall into its own block x[iu, :].  Four hop entries per trip: their table loads, then their gathers, are issued
 // together; past the end of the list the trip replays "0 * x[own row]".
-// xb = the block x[iu, :] of the row -- in global memory (GLOBAL: read-only path) or staged in shared memory
+// The block x[iu, :] of the row is xb[col0 .. col0 + D_dn): xb = x and col0 = iu * D_dn in global memory (GLOBAL: read-only
+// path; n < 2^31, so the column fits 32 bits), or xb = the block staged in shared memory and col0 = 0.
 template <typename VecT, bool GLOBAL>
 __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, const double *ampw, const double *diagk, uint32_t U, int32_t id,
-                                                        const VecT *xb, VecT xi)
+                                                        const VecT *xb, uint32_t col0, VecT xi)
 {
     using VT = VecTraits<VecT>;
     const uint32_t D = ld_ro(V.dlist + id);
@@ -417,7 +418,7 @@ __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, co
 QB_UNROLL
         for (int u = 0; u < 4; u++) h[u] = ld_ro(V.dhop + e + u);
 QB_UNROLL
-        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + h[u].x); else xv[u] = xb[h[u].x]; }
+        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + (col0 + h[u].x)); else xv[u] = xb[col0 + h[u].x]; }
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
     }
@@ -427,7 +428,7 @@ QB_UNROLL
 QB_UNROLL
         for (int u = 0; u < 4; u++) h[u] = (e + u < e1) ? ld_ro(V.dhop + e + u) : make_uint2((uint32_t)id, 0u);
 QB_UNROLL
-        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + h[u].x); else xv[u] = xb[h[u].x]; }
+        for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + (col0 + h[u].x)); else xv[u] = xb[col0 + h[u].x]; }
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
     }
@@ -474,7 +475,7 @@ kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__res
         const int64_t iu = p / V.Dd;
         const int32_t id = (int32_t)(p - iu * V.Dd);
         const VecT xi = ld_ro(x + p);
-        const VecT acc = kron_local_acc<VecT, true>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x + iu * V.Dd, xi);
+        const VecT acc = kron_local_acc<VecT, true>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x, (uint32_t)(iu * V.Dd), xi);
         VecT out = VT::scale(alpha, acc);
         if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
         if (use_beta) out = VT::add(out, VT::scale(beta, z[q]));
@@ -509,7 +510,7 @@ kron_local_smem_kernel(SpeciesView V, int64_t u_lo, int64_t u_cnt, const double 
         const uint32_t U = ld_ro(V.ulist + iu);
         for (int32_t id = threadIdx.x; id < Dd; id += 1024) {
             const VecT xi = xs[id];
-            const VecT acc = kron_local_acc<VecT, false>(V, ampw, diagk, U, id, xs, xi);
+            const VecT acc = kron_local_acc<VecT, false>(V, ampw, diagk, U, id, xs, 0u, xi);
             VecT out = VT::scale(alpha, acc);
             if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
             if (use_beta) out = VT::add(out, VT::scale(beta, z[il * V.Dd + id]));
@@ -556,6 +557,7 @@ __host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, co
 {
     using VT = VecTraits<VecT>;
     const uint32_t D = ld_ro(V.dlist + idc);
+    const uint32_t Dd32 = (uint32_t)V.Dd, idc32 = (uint32_t)idc;
     const int e1 = ld_ro(V.uptr + iu + 1);
     VecT acc = VT::zero();
     int e = ld_ro(V.uptr + iu);
@@ -568,7 +570,7 @@ QB_UNROLL
             if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);   // replays 0 * x[own row]
         }
 QB_UNROLL
-        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);
+        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (h[u].x * Dd32 + idc32));      // n < 2^31: the column fits 32 bits
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, D, ampw), xv[u]);
     }
@@ -581,7 +583,7 @@ QB_UNROLL
             if (FILTER && ((int64_t)h[u].x < c_lo || (int64_t)h[u].x >= c_hi)) h[u] = make_uint2((uint32_t)iu, 0u);
         }
 QB_UNROLL
-        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (int64_t)h[u].x * V.Dd + idc);
+        for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (h[u].x * Dd32 + idc32));      // n < 2^31: the column fits 32 bits
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, D, ampw), xv[u]);
     }
@@ -934,7 +936,7 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
     if (x && y) {
         for (int64_t p = 0; p < n; p++) {
             const int64_t iu = p / V.Dd;
-            y[p] = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(p - iu * V.Dd), x + iu * V.Dd, x[p]);
+            y[p] = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(p - iu * V.Dd), x, (uint32_t)(iu * V.Dd), x[p]);
         }
         const CrossItems I = cross_items(V.Du, V.Dd, W);
         for (int64_t it = 0; it < I.nitems; it++)
@@ -985,7 +987,7 @@ int qbgpu_debug_species_parts_host(int nsites, int nup, int ndn, int nbonds, con
         if (has_local) {
             for (int64_t q = 0; q < u_cnt * V.Dd; q++) {
                 const int64_t pg = u_lo * V.Dd + q, iu = pg / V.Dd;
-                const double acc = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(pg - iu * V.Dd), x + iu * V.Dd, x[pg]);
+                const double acc = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(pg - iu * V.Dd), x, (uint32_t)(iu * V.Dd), x[pg]);
                 y_local[q] = first ? acc : y_local[q] + acc;
             }
             local_done = true;

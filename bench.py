@@ -571,7 +571,7 @@ def main():
             del xh, yh, xh_t, yh_t, flush_buf
             torch.cuda.empty_cache()
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--species-probe", "--workload", args.workload,
-                                  "--steps", str(max(5, min(args.steps, 20)))], capture_output=True, text=True, timeout=420)
+                                  "--steps", str(max(5, min(args.steps, 20)))], capture_output=True, text=True, timeout=300)
             lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             line["species_order"] = json.loads(lines[-1]) if lines else {"error": f"exit {res.returncode}: {res.stderr[-400:]}"}
         except Exception as e:

@@ -412,13 +412,27 @@ __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, co
     mac(acc, diagk[popc_hd(U & D)], xi);
     const int e1 = ld_ro(V.dptr + id + 1);
     int e = ld_ro(V.dptr + id);
-    for (; e + 4 <= e1; e += 4) {                           // full trips: no bounds checks
+    // full trips, no bounds checks; the next trip's table entries are fetched while this trip's gathers are in flight (a lane
+    // reads its own list here, so a table load costs an L2 round trip that would otherwise sit in front of every gather)
+    uint2 hn[4];
+    bool more = e + 4 <= e1;
+    if (more) {
+QB_UNROLL
+        for (int u = 0; u < 4; u++) hn[u] = ld_ro(V.dhop + e + u);
+    }
+    while (more) {
         uint2 h[4];
         VecT xv[4];
 QB_UNROLL
-        for (int u = 0; u < 4; u++) h[u] = ld_ro(V.dhop + e + u);
+        for (int u = 0; u < 4; u++) h[u] = hn[u];
+        e += 4;
+        more = e + 4 <= e1;
 QB_UNROLL
         for (int u = 0; u < 4; u++) { if (GLOBAL) xv[u] = ld_ro(xb + (col0 + h[u].x)); else xv[u] = xb[col0 + h[u].x]; }
+        if (more) {
+QB_UNROLL
+            for (int u = 0; u < 4; u++) hn[u] = ld_ro(V.dhop + e + u);
+        }
 QB_UNROLL
         for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
     }

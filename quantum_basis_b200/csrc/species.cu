@@ -63,6 +63,7 @@ struct Species {
     uint2 *uhop = nullptr, *dhop = nullptr;       // (.x = target configuration index, .y = mask | sign | weight), sorted by target
     double *ampw = nullptr;                       // [128] amplitude of a bond of multiplicity w: -t added w times (LIL accumulation)
     double *diagk = nullptr;                      // [33]  U added k times
+    double amp_uni = 0.0;                         // != 0: every bond has the same multiplicity and this is its amplitude
     int tile = 128;                               // W: down indices per tile of the cross pass (multiple of 32)
     bool matfree = false;
     int64_t bytes = 0;
@@ -90,6 +91,17 @@ __host__ __device__ __forceinline__ double hop_value(uint32_t meta, uint32_t oth
 #endif
 }
 
+// the same when every bond has the same multiplicity (the usual case): the amplitude is a kernel argument, no table lookup
+__host__ __device__ __forceinline__ double hop_value_uni(uint32_t meta, uint32_t other, double amp)
+{
+    const uint32_t sg = ((meta >> 24) ^ (uint32_t)popc_hd(other & (meta & kHopMask))) & 1u;
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(amp) ^ (int)(sg << 31), __double2loint(amp));
+#else
+    return sg ? -amp : amp;
+#endif
+}
+
 struct SpeciesHost {
     std::vector<uint32_t> list[2];
     std::vector<int32_t> ptr[2];
@@ -97,6 +109,7 @@ struct SpeciesHost {
     std::vector<int32_t> rank;                    // rank of a word among the words with the same popcount
     double ampw[kMaxWeight + 1];
     double diagk[kMaxDbl + 1];
+    int uniform_w = 0;                            // the common bond multiplicity, 0 when the bonds differ
 };
 
 // The hop tables, with the formulas of tests/species_builders.py: for the hop f -> t of a species on the word `w`
@@ -143,6 +156,8 @@ static int build_host_tables(int nsites, int nup, int ndn, const ModelParams &M,
             H.ptr[sp][c + 1] = (int32_t)H.hop[sp].size();
         }
     }
+    H.uniform_w = M.nbonds > 0 ? M.bonds[0].w : 0;
+    for (int b = 1; b < M.nbonds; b++) if (M.bonds[b].w != H.uniform_w) H.uniform_w = 0;
     for (int w = 0; w <= kMaxWeight; w++) { double a = 0.0; for (int r = 0; r < w; r++) a += -M.t; H.ampw[w] = a; }
     for (int k = 0; k <= kMaxDbl; k++) { double d = 0.0; for (int r = 0; r < k; r++) d += M.U; H.diagk[k] = d; }
     return QBGPU_OK;
@@ -214,6 +229,7 @@ static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelPa
     QB_CU(cudaStreamSynchronize(c.stream));
     cudaFree(d_rank); d_rank = nullptr;
 #undef QB_CU
+    S->amp_uni = H.uniform_w > 0 ? H.ampw[H.uniform_w] : 0.0;
     S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + (with_perm ? 4 * T.dim : 0));
     *out = A;
     return QBGPU_OK;
@@ -402,9 +418,9 @@ int64_t species_bytes(const qbgpu_matrix *A)
 // together; past the end of the list the trip replays "0 * x[own row]".
 // The block x[iu, :] of the row is xb[col0 .. col0 + D_dn): xb = x and col0 = iu * D_dn in global memory (GLOBAL: read-only
 // path; n < 2^31, so the column fits 32 bits), or xb = the block staged in shared memory and col0 = 0.
-template <typename VecT, bool GLOBAL>
+template <typename VecT, bool GLOBAL, bool UNI = false>
 __host__ __device__ __forceinline__ VecT kron_local_acc(const SpeciesView &V, const double *ampw, const double *diagk, uint32_t U, int32_t id,
-                                                        const VecT *xb, uint32_t col0, VecT xi)
+                                                        const VecT *xb, uint32_t col0, VecT xi, double amp_uni = 0.0)
 {
     using VT = VecTraits<VecT>;
     const uint32_t D = ld_ro(V.dlist + id);
@@ -434,7 +450,7 @@ QB_UNROLL
             for (int u = 0; u < 4; u++) hn[u] = ld_ro(V.dhop + e + u);
         }
 QB_UNROLL
-        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, U, ampw), xv[u]);
+        for (int u = 0; u < 4; u++) mac(acc, UNI ? hop_value_uni(h[u].y, U, amp_uni) : hop_value(h[u].y, U, ampw), xv[u]);
     }
     if (e < e1) {                                           // the last, partial trip: past the end it replays 0 * x[own row]
         uint2 h[4];
@@ -463,9 +479,9 @@ __device__ __forceinline__ void local_scalars(int scal_mode, const double *sc, d
 // BLOCK = 256, grid-stride (default), or BLOCK = 1024 with one contiguous range of rows per CTA (QBGPU_KRON_LOCAL=1: one
 // CTA per SM then walks through the blocks x[iu, :] one after the other, so that L1 holds the block being gathered from).
 // Rows [row0, row0 + nloc) of the operator (a shard: whole up configurations); x is the full vector, y and z the local rows.
-template <typename VecT, int BLOCK, bool RANGES>
+template <typename VecT, int BLOCK, bool RANGES, bool UNI>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
-kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g, double amp_uni,
                   const VecT *__restrict__ x, const VecT *z, VecT *y,
                   double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
 {
@@ -489,7 +505,7 @@ kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__res
         const int64_t iu = p / V.Dd;
         const int32_t id = (int32_t)(p - iu * V.Dd);
         const VecT xi = ld_ro(x + p);
-        const VecT acc = kron_local_acc<VecT, true>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x, (uint32_t)(iu * V.Dd), xi);
+        const VecT acc = kron_local_acc<VecT, true, UNI>(V, ampw, diagk, ld_ro(V.ulist + iu), id, x, (uint32_t)(iu * V.Dd), xi, amp_uni);
         VecT out = VT::scale(alpha, acc);
         if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
         if (use_beta) out = VT::add(out, VT::scale(beta, z[q]));
@@ -499,9 +515,9 @@ kron_local_kernel(SpeciesView V, int64_t row0, int64_t nloc, const double *__res
 
 // QBGPU_KRON_LOCAL=2: one CTA of 1024 threads per up configuration; the block x[iu, :] (D_dn entries: 206 KB of complex
 // numbers for the 4x4 lattice) is staged in shared memory once and every gather of the block's rows reads it from there.
-template <typename VecT>
+template <typename VecT, bool UNI>
 __global__ void __launch_bounds__(1024, 1)
-kron_local_smem_kernel(SpeciesView V, int64_t u_lo, int64_t u_cnt, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+kron_local_smem_kernel(SpeciesView V, int64_t u_lo, int64_t u_cnt, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g, double amp_uni,
                        const VecT *__restrict__ x, const VecT *z, VecT *y,
                        double2 alpha, double2 gamma, double2 beta, int scal_mode, const double *__restrict__ sc)
 {
@@ -524,7 +540,7 @@ kron_local_smem_kernel(SpeciesView V, int64_t u_lo, int64_t u_cnt, const double 
         const uint32_t U = ld_ro(V.ulist + iu);
         for (int32_t id = threadIdx.x; id < Dd; id += 1024) {
             const VecT xi = xs[id];
-            const VecT acc = kron_local_acc<VecT, false>(V, ampw, diagk, U, id, xs, 0u, xi);
+            const VecT acc = kron_local_acc<VecT, false, UNI>(V, ampw, diagk, U, id, xs, 0u, xi, amp_uni);
             VecT out = VT::scale(alpha, acc);
             if (use_gamma) out = VT::add(out, VT::scale(gamma, xi));
             if (use_beta) out = VT::add(out, VT::scale(beta, z[il * V.Dd + id]));
@@ -565,9 +581,9 @@ __host__ __device__ __forceinline__ void cross_item_at(const CrossItems &I, int6
 }
 
 // FILTER: only the hops whose target configuration lies in [c_lo, c_hi) (a column part of a shard)
-template <typename VecT, bool FILTER = false>
+template <typename VecT, bool FILTER = false, bool UNI = false>
 __host__ __device__ __forceinline__ VecT kron_cross_acc(const SpeciesView &V, const double *ampw, int64_t iu, int64_t idc, const VecT *x,
-                                                        int64_t c_lo = 0, int64_t c_hi = 0)
+                                                        int64_t c_lo = 0, int64_t c_hi = 0, double amp_uni = 0.0)
 {
     using VT = VecTraits<VecT>;
     const uint32_t D = ld_ro(V.dlist + idc);
@@ -586,7 +602,7 @@ QB_UNROLL
 QB_UNROLL
         for (int u = 0; u < 4; u++) xv[u] = ld_ro(x + (h[u].x * Dd32 + idc32));      // n < 2^31: the column fits 32 bits
 QB_UNROLL
-        for (int u = 0; u < 4; u++) mac(acc, hop_value(h[u].y, D, ampw), xv[u]);
+        for (int u = 0; u < 4; u++) mac(acc, (UNI && !FILTER) ? hop_value_uni(h[u].y, D, amp_uni) : hop_value(h[u].y, D, ampw), xv[u]);
     }
     if (e < e1) {                                           // the last, partial trip
         uint2 h[4];
@@ -606,9 +622,9 @@ QB_UNROLL
 
 // The items enumerate the LOCAL up configurations [u_lo, u_lo + u_cnt) of the handle.  FIRST: y = alpha acc + beta z (a
 // column part without the local pass that opens the product); otherwise y += alpha acc.
-template <typename VecT, bool DOTS, bool FILTER, bool FIRST>
+template <typename VecT, bool DOTS, bool FILTER, bool FIRST, bool UNI>
 __global__ void __launch_bounds__(kPBlock, 4)
-kron_cross_kernel(SpeciesView V, CrossItems I, int64_t u_lo, int64_t c_lo, int64_t c_hi, const double *__restrict__ ampw_g,
+kron_cross_kernel(SpeciesView V, CrossItems I, int64_t u_lo, int64_t c_lo, int64_t c_hi, const double *__restrict__ ampw_g, double amp_uni,
                   const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 beta, int scal_mode,
                   const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
 {
@@ -631,7 +647,7 @@ kron_cross_kernel(SpeciesView V, CrossItems I, int64_t u_lo, int64_t c_lo, int64
         const int64_t iu = u_lo + il;
         const bool live = id < V.Dd;
         const int64_t idc = live ? id : V.Dd - 1;           // idle lanes of the last chunk replay a valid column
-        const VecT acc = kron_cross_acc<VecT, FILTER>(V, ampw, iu, idc, x, c_lo, c_hi);
+        const VecT acc = kron_cross_acc<VecT, FILTER, UNI>(V, ampw, iu, idc, x, c_lo, c_hi, amp_uni);
         if (live) {
             const int64_t q = il * V.Dd + id;               // local row
             VecT out = VT::scale(alpha, acc);
@@ -653,19 +669,19 @@ kron_cross_kernel(SpeciesView V, CrossItems I, int64_t u_lo, int64_t c_lo, int64
 static int g_kron_local_variant = -1;      // -1: not chosen yet (environment QBGPU_KRON_LOCAL, else 0)
 void set_kron_local_variant(int v) { g_kron_local_variant = v; }
 
-template <typename VecT, bool DOTS, bool FILTER, bool FIRST>
+template <typename VecT, bool DOTS, bool FILTER, bool FIRST, bool UNI = false>
 static int launch_kron_cross(const qbgpu_matrix *A, const FusedArgs &a, const SpeciesView &V, const CrossItems &I, int64_t u_lo)
 {
     Context &c = ctx();
     const Species *S = (const Species *)A->sp;
-    auto kern = kron_cross_kernel<VecT, DOTS, FILTER, FIRST>;
+    auto kern = kron_cross_kernel<VecT, DOTS, FILTER, FIRST, UNI>;
     static int bps = 0;
     if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
     const int64_t want = (I.nitems + (kPBlock / 32) - 1) / (kPBlock / 32);
     int64_t cap = (int64_t)c.num_sms * bps;
     if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
     if (want < 1) return QBGPU_OK;
-    kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, I, u_lo, A->sp_col_lo, A->sp_col_hi, S->ampw, (const VecT *)a.x, (const VecT *)a.z,
+    kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, I, u_lo, A->sp_col_lo, A->sp_col_hi, S->ampw, S->amp_uni, (const VecT *)a.x, (const VecT *)a.z,
                                                                     (VecT *)a.y, a.alpha, a.beta, a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
@@ -688,23 +704,24 @@ static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
         if (g_kron_local_variant < 0) g_kron_local_variant = getenv("QBGPU_KRON_LOCAL") ? atoi(getenv("QBGPU_KRON_LOCAL")) : 0;
         const int variant = g_kron_local_variant;
         const size_t stage_bytes = sizeof(VecT) * (size_t)S->Dd;
+        const bool uni = S->amp_uni != 0.0;              // every bond with the same multiplicity: amplitude as an argument
         if (variant == 2 && stage_bytes <= 225 * 1024) {
-            auto kern = kron_local_smem_kernel<VecT>;
-            static bool attr_set = false;
-            if (!attr_set) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_set = true; }
+            auto kern = uni ? kron_local_smem_kernel<VecT, true> : kron_local_smem_kernel<VecT, false>;
+            QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
             const int64_t grid = u_cnt < c.num_sms ? u_cnt : c.num_sms;
-            kern<<<(int)grid, 1024, stage_bytes, c.stream>>>(V, u_lo, u_cnt, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+            kern<<<(int)grid, 1024, stage_bytes, c.stream>>>(V, u_lo, u_cnt, S->ampw, S->diagk, S->amp_uni, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
                                                              a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
         } else if (variant == 1) {
-            auto kern = kron_local_kernel<VecT, 1024, true>;
-            kern<<<c.num_sms, 1024, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
+            auto kern = uni ? kron_local_kernel<VecT, 1024, true, true> : kron_local_kernel<VecT, 1024, true, false>;
+            kern<<<c.num_sms, 1024, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, S->amp_uni, (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y,
                                                    a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
         } else {
-            auto kern = kron_local_kernel<VecT, kPBlock, false>;
-            static int bps = 0;
-            if (bps == 0) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0)); if (bps < 1) bps = 1; }
+            auto kern = uni ? kron_local_kernel<VecT, kPBlock, false, true> : kron_local_kernel<VecT, kPBlock, false, false>;
+            int bps = 0;
+            QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPBlock, 0));
+            if (bps < 1) bps = 1;
             const int64_t want = (nloc + kPBlock - 1) / kPBlock, cap = (int64_t)c.num_sms * bps;
-            kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, (const VecT *)a.x, (const VecT *)a.z,
+            kern<<<(int)(want < cap ? want : cap), kPBlock, 0, c.stream>>>(V, row0, nloc, S->ampw, S->diagk, S->amp_uni, (const VecT *)a.x, (const VecT *)a.z,
                                                                             (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc);
         }
         QB_LAUNCH_COUNT();
@@ -719,9 +736,11 @@ static int launch_kron(const qbgpu_matrix *A, const FusedArgs &a)
     if (!accumulate && (a.beta.x != 0.0 || a.beta.y != 0.0 || a.scal_mode == 1) && !a.z) return fail(QBGPU_ERR_ARG, "beta != 0 needs z");
     if (a.dots) {
         if (filter) return accumulate ? launch_kron_cross<VecT, true, true, false>(A, a, V, I, u_lo) : launch_kron_cross<VecT, true, true, true>(A, a, V, I, u_lo);
+        if (S->amp_uni != 0.0) return launch_kron_cross<VecT, true, false, false, true>(A, a, V, I, u_lo);
         return launch_kron_cross<VecT, true, false, false>(A, a, V, I, u_lo);
     }
     if (filter) return accumulate ? launch_kron_cross<VecT, false, true, false>(A, a, V, I, u_lo) : launch_kron_cross<VecT, false, true, true>(A, a, V, I, u_lo);
+    if (S->amp_uni != 0.0) return launch_kron_cross<VecT, false, false, false, true>(A, a, V, I, u_lo);
     return launch_kron_cross<VecT, false, false, false>(A, a, V, I, u_lo);
 }
 
@@ -950,7 +969,9 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
     if (x && y) {
         for (int64_t p = 0; p < n; p++) {
             const int64_t iu = p / V.Dd;
-            y[p] = kron_local_acc<double, false>(V, H.ampw, H.diagk, V.ulist[iu], (int32_t)(p - iu * V.Dd), x, (uint32_t)(iu * V.Dd), x[p]);
+            const int32_t idl = (int32_t)(p - iu * V.Dd);
+            y[p] = H.uniform_w > 0 ? kron_local_acc<double, false, true>(V, H.ampw, H.diagk, V.ulist[iu], idl, x, (uint32_t)(iu * V.Dd), x[p], H.ampw[H.uniform_w])
+                                   : kron_local_acc<double, false, false>(V, H.ampw, H.diagk, V.ulist[iu], idl, x, (uint32_t)(iu * V.Dd), x[p]);
         }
         const CrossItems I = cross_items(V.Du, V.Dd, W);
         for (int64_t it = 0; it < I.nitems; it++)
@@ -959,7 +980,8 @@ int qbgpu_debug_species_host(int nsites, int nup, int ndn, int nbonds, const int
                 cross_item_at(I, it, lane, iu, id);
                 if (iu < 0 || iu >= V.Du || id < 0) return fail(QBGPU_ERR_STATE, "debug_species_host: warp item out of range");
                 const bool live = id < V.Dd;
-                const double acc = kron_cross_acc<double>(V, H.ampw, iu, live ? id : V.Dd - 1, x);
+                const double acc = H.uniform_w > 0 ? kron_cross_acc<double, false, true>(V, H.ampw, iu, live ? id : V.Dd - 1, x, 0, 0, H.ampw[H.uniform_w])
+                                                   : kron_cross_acc<double, false, false>(V, H.ampw, iu, live ? id : V.Dd - 1, x);
                 if (live) { y[iu * V.Dd + id] += acc; if (touched) touched[iu * V.Dd + id]++; }
             }
     }

@@ -155,6 +155,19 @@ def test_row_shards_and_column_parts_on_the_host(Lx, Ly, nup, ndn):
                     assert np.linalg.norm(y[:want.size] - want) <= 1e-13 * np.linalg.norm(want), (world, rank, order)
 
 
+def test_tables_at_config3_scale_reproduce_the_stored_entry_count():
+    """BASELINE config 3 (4x4, N_up = N_dn = 8): the two hop tables describe exactly the 5,819,376,420 entries of the expanded
+    matrix -- D_up (dn hops + D_dn diagonals) + D_dn (up hops) -- and are built in a fraction of a second."""
+    L = _lib.lib()
+    b = np.ascontiguousarray(np.asarray(lb.square_bonds(4, 4), dtype=np.int32).reshape(-1, 2))
+    sizes = np.zeros(4, dtype=np.int64)
+    null = C.c_void_p(0)
+    _lib.check(L.qbgpu_debug_species_host(16, 8, 8, b.shape[0], C.c_void_p(b.ctypes.data), 1.0, 1.1, 128, C.c_void_p(sizes.ctypes.data), *([null] * 11)))
+    Du, Dd, tu, td = (int(v) for v in sizes)
+    assert (Du, Dd) == (12870, 12870) and tu == td == 219648
+    assert Du * (td + Dd) + Dd * tu == 5819376420
+
+
 def test_bad_arguments_fail_loudly():
     L = _lib.lib()
     b = np.array([[0, 1]], dtype=np.int32)

@@ -226,7 +226,7 @@ def species_probe(args):
     (QBGPU_SPECIES_ORDER, csrc/species.cu) -- parity against the ordinary handle first, then timings.  Run in a process of
     its own because these kernels had not met hardware when they were committed: whatever happens here cannot touch the
     numbers of the main line.  Prints one JSON object."""
-    os.environ["QBGPU_MV_REAL_MODE"] = "1"                 # opt-in fp64 route of MultMv, for this child only (read at the first product)
+    os.environ.setdefault("QBGPU_MV_REAL_MODE", "1")       # opt-in fp64 route of MultMv on ORDINARY handles, for this child only
     import numpy as np
     import torch
     import quantum_basis_b200 as qb
@@ -239,7 +239,7 @@ def species_probe(args):
     fam, p = WORKLOADS[args.workload]
     ns = p["Lx"] * p["Ly"]
     peak, _ = measured_peak()
-    out = {"workload": args.workload, "tile": int(os.environ.get("QBGPU_SPECIES_TILE", "128"))}
+    out = {"workload": args.workload, "tile": os.environ.get("QBGPU_SPECIES_TILE", "default (stored 64, matrix-free 128)")}
 
     def timed(fn, steps):
         for _ in range(3):
@@ -302,6 +302,12 @@ def species_probe(args):
             ms = timed(lambda: M.MultMv(x, y), args.steps)
             B16 = algorithmic_bytes(Z, n, n, 8, 16)
             r["reference_order_complex"] = {"ms_per_product": ms, "achieved_GBs": B16 / ms / 1e6, "frac_of_measured_peak": B16 / ms / 1e6 / peak}
+            # (a') the same call on a vector WITH imaginary parts: no fp64 route, the complex passes
+            xc = qb.vec_randomize(n, 2, device=True)
+            assert L.qbgpu_zaxpy(n, (C.c_double * 2)(0.0, 1.0), C.c_void_p(x.ptr), C.c_void_p(xc.ptr)) == 0      # xc = r2 + i r1
+            ms = timed(lambda: M.MultMv(xc, y), args.steps)
+            r["reference_order_genuinely_complex"] = {"ms_per_product": ms, "achieved_GBs": B16 / ms / 1e6, "frac_of_measured_peak": B16 / ms / 1e6 / peak}
+            xc.free()
             # (b) vectors kept in the internal order (what the Krylov loops do between their first and last step)
             xn, yn = M.to_native(x), qb.DeviceVector(n)
             ms = timed(lambda: fused(M.handle, C.c_void_p(xn.ptr), None, C.c_void_p(yn.ptr), one, zero, zero, None), args.steps)

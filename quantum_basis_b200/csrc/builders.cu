@@ -272,8 +272,8 @@ static int build_generic(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     QB_CU(cudaStreamSynchronize(c.stream));
     A->nnz = nnz;
     A->nnz_input = (nnz + T.dim) / 2;                       // what the reference would store (upper triangle incl. diagonal), full handle
-    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1)));
-    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (nnz ? nnz : 1)));
+    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1) + 64));
+    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (nnz ? nnz : 1) + 64));
     if (A->val_real) build_fill_kernel<double><<<(int)g, kBBlock, 0, c.stream>>>(S, d_M, row_lo, nloc, A->rowptr, A->col, (double *)A->val);
     else             build_fill_kernel<double2><<<(int)g, kBBlock, 0, c.stream>>>(S, d_M, row_lo, nloc, A->rowptr, A->col, (double2 *)A->val);
     QB_LAUNCH_COUNT();

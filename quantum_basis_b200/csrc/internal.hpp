@@ -45,6 +45,7 @@ struct qbgpu_matrix {
     // "local" part (diagonal + hops of the down electrons: inside the block of one up configuration) and `second` the
     // "cross" part (hops of the up electrons), whose 32-row slices are traversed in `slice_order` (tiles of down indices).
     int32_t *perm = nullptr;
+    int32_t *perm_inv = nullptr;     // perm_inv[p] = the reference's row of internal index p (the way in gathers, so both ways write coalesced)
     void    *sp = nullptr;
     qbgpu_matrix *second = nullptr;
     int32_t *slice_order = nullptr;
@@ -82,6 +83,15 @@ int sjds_convert(qbgpu_matrix *A, bool forward);
 int value_dict_encode(qbgpu_matrix *A);               // matrix.cu: try to replace fp64 values by 1-byte codes
 int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &args);
 void set_sjds_variant(int v);
+// sjds_bulk.cu: the same product with the matrix stream moved by cp.async.bulk into per-warp shared-memory rings, and the
+// block-local product (rows of block u reference only columns of block u) with the block of x staged in shared memory
+int launch_spmv_sjds_bulk(const qbgpu_matrix *A, const FusedArgs &args);
+int sjds_bulk_mode();
+bool sjds_bulk_wanted(const qbgpu_matrix *A);
+void set_sjds_bulk_mode(int m);
+bool block_smem_applicable(const qbgpu_matrix *A, int64_t D);
+int launch_spmv_block_smem(const qbgpu_matrix *A, const FusedArgs &args, int64_t D);
+void set_block_smem_variant(int v);
 int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &args);     // builders.cu
 void matfree_destroy(qbgpu_matrix *A);
 int64_t matfree_bytes(const qbgpu_matrix *A);

@@ -166,8 +166,8 @@ static int convert_device(qbgpu_matrix *A, int64_t n, int64_t base, const int64_
     if (herr & kErrColRange) { cleanup(); return fail(QBGPU_ERR_ARG, "create_csr: column index out of range"); }
     A->nnz = nnz;
     T *oval = nullptr;
-    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1)));
-    QB_CU(cudaMalloc(&oval, sizeof(T) * (nnz ? nnz : 1)));
+    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1) + 64));
+    QB_CU(cudaMalloc(&oval, sizeof(T) * (nnz ? nnz : 1) + 64));
     A->val = oval;
     A->val_real = (sizeof(T) == sizeof(double));
     fill_rows_kernel<T><<<grid_for(n), kCBlock, 0, c.stream>>>(n, base, d_rs, d_re, d_col, d_val, sym, lo, hi, A->rowptr, d_cnt_t, d_cursor,
@@ -185,7 +185,7 @@ static int convert_device(qbgpu_matrix *A, int64_t n, int64_t base, const int64_
         // every imaginary part is exactly zero (always the case for the reference's model<complex> with real
         // couplings): store fp64 values, 12 instead of 20 bytes per entry
         double *rv = nullptr;
-        QB_CU(cudaMalloc(&rv, sizeof(double) * (nnz ? nnz : 1)));
+        QB_CU(cudaMalloc(&rv, sizeof(double) * (nnz ? nnz : 1) + 64));
         demote_kernel<<<grid_for(nnz), kCBlock, 0, c.stream>>>(nnz, (const double2 *)oval, rv);
         QB_LAUNCH_COUNT();
         QB_CU(cudaStreamSynchronize(c.stream));
@@ -335,7 +335,7 @@ int value_dict_encode(qbgpu_matrix *A)
     for (size_t j = 0; j < keys.size(); j++) { dict[j] = keys[j].first; slot_code[keys[j].second] = (int)j; }
     QB_CU(cudaMalloc(&d_slot_code, sizeof(int) * kDictSlots));
     QB_CU(cudaMalloc(&d_dict, sizeof(double) * 256));
-    QB_CU(cudaMalloc(&d_code, (size_t)A->nnz));
+    QB_CU(cudaMalloc(&d_code, (size_t)A->nnz + 64));
     QB_CU(cudaMemcpyAsync(d_slot_code, slot_code.data(), sizeof(int) * kDictSlots, cudaMemcpyHostToDevice, c.stream));
     QB_CU(cudaMemcpyAsync(d_dict, dict.data(), sizeof(double) * 256, cudaMemcpyHostToDevice, c.stream));
     dict_encode_kernel<<<grid_for(A->nnz), kCBlock, 0, c.stream>>>(A->nnz, (const double *)A->val, d_slots, d_slot_code, d_code);
@@ -425,8 +425,8 @@ static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbg
         QB_CU(cudaMemcpyAsync(&nnz, P->rowptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
         QB_CU(cudaStreamSynchronize(c.stream));
         P->nnz = nnz; P->nnz_input = nnz;
-        QB_CU(cudaMalloc(&P->col, sizeof(int32_t) * (nnz ? nnz : 1)));
-        QB_CU(cudaMalloc(&P->val, P->val_bytes() * (nnz ? nnz : 1)));
+        QB_CU(cudaMalloc(&P->col, sizeof(int32_t) * (nnz ? nnz : 1) + 64));
+        QB_CU(cudaMalloc(&P->val, P->val_bytes() * (nnz ? nnz : 1) + 64));
         if (A->val_real) split_copy_kernel<double><<<grid_for(nloc), kCBlock, 0, c.stream>>>(nloc, A->rowptr, A->col, (const double *)A->val, p, bounds[p], bounds[p + 1], P->rowptr, P->col, (double *)P->val);
         else             split_copy_kernel<double2><<<grid_for(nloc), kCBlock, 0, c.stream>>>(nloc, A->rowptr, A->col, (const double2 *)A->val, p, bounds[p], bounds[p + 1], P->rowptr, P->col, (double2 *)P->val);
         QB_LAUNCH_COUNT();

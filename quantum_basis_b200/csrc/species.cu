@@ -6,7 +6,8 @@
 // No re-ordering of ONE pass over the rows removes that (profiles/r01_cache_sim_orders_and_tiles.txt).  Two passes do,
 // once the basis is indexed by the two spin species separately:
 //
-//     p = iu * D_dn + id ,   iu = rank of the up-occupancy word, id = rank of the down-occupancy word (ascending words)
+//     p = iu * D_dn + id ,   iu = rank of the up-occupancy word, id = rank of the down-occupancy word
+//                             (words ordered by (odd-site bits, even-site bits): see build_host_tables)
 //
 //     H = [ U * (double occupancies) + hops of the DOWN electrons ]   "local" part: same iu, i.e. inside one contiguous
 //                                                                     block x[iu, :] of D_dn entries (206 KB for 4x4)
@@ -51,6 +52,14 @@ constexpr uint32_t kHopMask = 0xFFFFFFu;      // hop entry .y = interval mask (2
 constexpr int kMaxWeight = 127;
 constexpr int kMaxDbl = 32;
 
+static int grid_rows(int64_t n) { int64_t g = (n + kPBlock - 1) / kPBlock; if (g < 1) g = 1; if (g > 148 * 32) g = 148 * 32; return (int)g; }
+
+__global__ void __launch_bounds__(kPBlock) invert_perm_kernel(int64_t n, const int32_t *__restrict__ perm, int32_t *perm_inv)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        perm_inv[perm[r]] = (int32_t)r;
+}
+
 static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Device-resident tables of a species-order handle (owned through qbgpu_matrix::sp).
@@ -58,13 +67,13 @@ struct Species {
     int nsites = 0;
     int64_t Du = 0, Dd = 0;
     int64_t tot_u = 0, tot_d = 0;                 // hop-table entries of the two species
-    uint32_t *ulist = nullptr, *dlist = nullptr;  // occupancy words, ascending
+    uint32_t *ulist = nullptr, *dlist = nullptr;  // occupancy words in the species order
     int32_t *uptr = nullptr, *dptr = nullptr;     // [D + 1] offsets into the hop tables
     uint2 *uhop = nullptr, *dhop = nullptr;       // (.x = target configuration index, .y = mask | sign | weight), sorted by target
     double *ampw = nullptr;                       // [128] amplitude of a bond of multiplicity w: -t added w times (LIL accumulation)
     double *diagk = nullptr;                      // [33]  U added k times
     double amp_uni = 0.0;                         // != 0: every bond has the same multiplicity and this is its amplitude
-    int tile = 128;                               // W: down indices per tile of the cross pass (multiple of 32)
+    int tile = 64;                                // W: down indices per tile of the cross pass (multiple of 32)
     bool matfree = false;
     int64_t bytes = 0;
 };
@@ -120,15 +129,31 @@ static int build_host_tables(int nsites, int nup, int ndn, const ModelParams &M,
     if (nsites < 2 || nsites > 24) return fail(QBGPU_ERR_ARG, "species order: between 2 and 24 sites");
     const uint32_t nw = 1u << nsites;
     H.rank.assign(nw, 0);
-    std::vector<int32_t> cnt(nsites + 1, 0);
-    for (uint32_t w = 0; w < nw; w++) H.rank[w] = cnt[__builtin_popcount(w)]++;
+    // Order of the configurations of one species: by (bits of the odd sites, bits of the even sites), odd sites major.  Any
+    // order serves the two passes; THIS one makes the species order a block-wise refinement of the reference's Lin order
+    // (label of the odd sites major, src/basis.cc:1144-1190): the rows of one odd-site label -- contiguous in the reference's
+    // order -- occupy a rectangle [iu0, iu0 + Cu) x [id0, id0 + Cd) of the internal order, so the permutation at the
+    // boundary (vec_to_native / vec_from_native) moves whole blocks and both of its sides stay sector-efficient.
+    auto order_key = [nsites](uint32_t w) {
+        uint32_t odd = 0, even = 0;
+        for (int s = 0; s < nsites; s++) { const uint32_t bit = (w >> s) & 1u; if (s & 1) odd |= bit << (s >> 1); else even |= bit << (s >> 1); }
+        return ((uint64_t)odd << 32) | even;
+    };
     const int nel[2] = {nup, ndn};
     for (int b = 0; b < M.nbonds; b++)
         if (M.bonds[b].w > kMaxWeight) return fail(QBGPU_ERR_ARG, "species order: a bond is repeated more than 127 times");
+    {   // rank of every word among the words of its popcount class, in that order
+        std::vector<std::vector<uint32_t>> cls(nsites + 1);
+        for (uint32_t w = 0; w < nw; w++) cls[__builtin_popcount(w)].push_back(w);
+        for (auto &c : cls) {
+            std::sort(c.begin(), c.end(), [&](uint32_t a, uint32_t b) { return order_key(a) < order_key(b); });
+            for (size_t k = 0; k < c.size(); k++) H.rank[c[k]] = (int32_t)k;
+        }
+    }
     for (int sp = 0; sp < 2; sp++) {
-        H.list[sp].clear();
-        H.list[sp].reserve(cnt[nel[sp]]);
+        H.list[sp].assign((size_t)0, 0u);
         for (uint32_t w = 0; w < nw; w++) if (__builtin_popcount(w) == nel[sp]) H.list[sp].push_back(w);
+        std::sort(H.list[sp].begin(), H.list[sp].end(), [&](uint32_t a, uint32_t b) { return order_key(a) < order_key(b); });
         const size_t D = H.list[sp].size();
         H.ptr[sp].assign(D + 1, 0);
         H.hop[sp].clear();
@@ -205,7 +230,7 @@ static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelPa
     A->sp = S;
     A->n = T.dim; A->row_lo = 0; A->row_hi = T.dim; A->api_complex = api_complex != 0; A->val_real = true;
     S->nsites = T.nsites; S->Du = Du; S->Dd = Dd; S->tot_u = (int64_t)H.hop[0].size(); S->tot_d = (int64_t)H.hop[1].size();
-    int W = 128;
+    int W = 64;                                            // measured on BASELINE config 3: 64 -> 14.6 ms, 128 -> 14.75, 256 -> 15.8 (fp64 vectors)
     if (const char *e = getenv("QBGPU_SPECIES_TILE")) W = atoi(e);
     if (W < 32) W = 32;
     W = (W + 31) / 32 * 32;
@@ -225,12 +250,15 @@ static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelPa
         QB_CU(cudaMalloc(&A->perm, sizeof(int32_t) * (size_t)T.dim));
         int rc = species_perm_build(T, d_rank, Dd, A->perm);
         if (rc) { cudaFree(d_rank); qbgpu_destroy(A); return rc; }
+        QB_CU(cudaMalloc(&A->perm_inv, sizeof(int32_t) * (size_t)T.dim));
+        invert_perm_kernel<<<grid_rows(T.dim), kPBlock, 0, c.stream>>>(T.dim, A->perm, A->perm_inv);
+        QB_LAUNCH_COUNT();
     }
     QB_CU(cudaStreamSynchronize(c.stream));
     cudaFree(d_rank); d_rank = nullptr;
 #undef QB_CU
     S->amp_uni = H.uniform_w > 0 ? H.ampw[H.uniform_w] : 0.0;
-    S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + (with_perm ? 4 * T.dim : 0));
+    S->bytes = (int64_t)(4 * (Du + Dd) + 4 * (Du + Dd + 2) + 8 * (S->tot_u + S->tot_d) + 8 * (kMaxWeight + 1 + kMaxDbl + 1) + (with_perm ? 8 * T.dim : 0));
     *out = A;
     return QBGPU_OK;
 }
@@ -296,7 +324,6 @@ __global__ void __launch_bounds__(kPBlock) species_fill_kernel(SpeciesView V, in
         species_fill_row<ValT>(V, ampw, diagk, p, col_l, val_l, col_c, val_c);
 }
 
-static int grid_rows(int64_t n) { int64_t g = (n + kPBlock - 1) / kPBlock; if (g < 1) g = 1; if (g > 148 * 32) g = 148 * 32; return (int)g; }
 
 // traversal order of the cross part's 32-row slices: by (tile of the slice's first down index, slice index)
 static void make_slice_order(int64_t n, int64_t Dd, int W, std::vector<int32_t> &order)
@@ -332,10 +359,10 @@ int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
 #define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
     QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (n + 1)));
     QB_CU(cudaMalloc(&C->rowptr, sizeof(int64_t) * (n + 1)));
-    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(A->nnz ? A->nnz : 1)));
-    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (size_t)(A->nnz ? A->nnz : 1)));
-    QB_CU(cudaMalloc(&C->col, sizeof(int32_t) * (size_t)(C->nnz ? C->nnz : 1)));
-    QB_CU(cudaMalloc(&C->val, C->val_bytes() * (size_t)(C->nnz ? C->nnz : 1)));
+    QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(A->nnz ? A->nnz : 1) + 64));
+    QB_CU(cudaMalloc(&A->val, A->val_bytes() * (size_t)(A->nnz ? A->nnz : 1) + 64));
+    QB_CU(cudaMalloc(&C->col, sizeof(int32_t) * (size_t)(C->nnz ? C->nnz : 1) + 64));
+    QB_CU(cudaMalloc(&C->val, C->val_bytes() * (size_t)(C->nnz ? C->nnz : 1) + 64));
     const SpeciesView V = view_of(S);
     species_rowptr_kernel<<<grid_rows(n + 1), kPBlock, 0, c.stream>>>(V, n, A->rowptr, C->rowptr);
     QB_LAUNCH_COUNT();
@@ -384,6 +411,7 @@ int species_build_matfree(qbgpu_matrix_t *out, const HostTables &T, const ModelP
         A->row_lo = row_lo; A->row_hi = row_hi;
     }
     S->matfree = true;
+    if (!getenv("QBGPU_SPECIES_TILE")) S->tile = 128;       // (the matrix-free cross pass prefers the wider tile: 14.1 ms against 15.0)
     A->format = QBGPU_FORMAT_MATFREE;
     A->nnz = 0; A->nnz_input = 0;
     A->convert_s = wall_s() - t0;
@@ -397,6 +425,7 @@ void species_destroy(qbgpu_matrix *A)
     species_free((Species *)A->sp);
     A->sp = nullptr;
     cudaFree(A->perm); A->perm = nullptr;
+    cudaFree(A->perm_inv); A->perm_inv = nullptr;
     if (A->second) { qbgpu_destroy(A->second); A->second = nullptr; }
 }
 
@@ -753,10 +782,12 @@ int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
     if (S->matfree) return A->api_complex ? launch_kron<double2>(A, a) : launch_kron<double>(A, a);
     if (!A->second) return fail(QBGPU_ERR_STATE, "species-order handle without its cross part");
     qbgpu_matrix L = *A;                                    // plain views: the production kernels see two ordinary matrices
-    L.sp = nullptr; L.second = nullptr; L.perm = nullptr;
+    L.sp = nullptr; L.second = nullptr; L.perm = nullptr; L.perm_inv = nullptr;
     FusedArgs a1 = a;
     a1.dots = nullptr;
-    QB_TRY(launch_spmv(&L, a1));
+    // pass 1: every gather stays inside the block of one up configuration -> the block of x lives in shared memory
+    if (block_smem_applicable(&L, S->Dd)) QB_TRY(launch_spmv_block_smem(&L, a1, S->Dd));
+    else QB_TRY(launch_spmv(&L, a1));
     qbgpu_matrix C = *A->second;
     C.api_complex = A->api_complex;                        // a real view of the handle (fp64 vectors) covers both parts
     FusedArgs a2;
@@ -787,7 +818,7 @@ int species_split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qb
     for (int p = 0; p < nparts; p++) {
         auto *V = new qbgpu_matrix(*A);
         V->borrowed = true;
-        V->perm = nullptr; V->perm_x = V->perm_y = nullptr;
+        V->perm = nullptr; V->perm_inv = nullptr; V->perm_x = V->perm_y = nullptr;
         V->sp_col_lo = bounds[p] / S->Dd; V->sp_col_hi = bounds[p + 1] / S->Dd;
         V->sp_has_local = !local_given && bounds[p] <= A->row_lo && A->row_lo < bounds[p + 1];
         local_given = local_given || V->sp_has_local;
@@ -806,11 +837,27 @@ template <> __device__ __forceinline__ double2 cvt<double2, double>(double v) { 
 template <> __device__ __forceinline__ double cvt<double, double2>(double2 v) { return v.x; }
 template <> __device__ __forceinline__ double2 cvt<double2, double2>(double2 v) { return v; }
 
+// Both ways GATHER (coalesced writes, reads that stay inside the rectangle one block of the reference's order maps to, so the
+// sectors they touch are complete within the L2's reach): a scattering way in wrote partial sectors -- 1.55 ms against 0.9 ms
+// for the way out on BASELINE config 3 (profiles/r02_mv_reference_order_launches.csv).
 template <typename SrcT, typename DstT>
-__global__ void __launch_bounds__(kPBlock) to_native_kernel(int64_t n, const int32_t *__restrict__ perm, const SrcT *__restrict__ src, DstT *dst)
+__global__ void __launch_bounds__(kPBlock) to_native_kernel(int64_t n, const int32_t *__restrict__ perm_inv, const SrcT *__restrict__ src, DstT *dst)
 {
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        dst[perm[r]] = cvt<DstT, SrcT>(src[r]);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        dst[p] = cvt<DstT, SrcT>(src[perm_inv[p]]);
+}
+
+// the way in of the real-content product: dst[p] = Re src[perm_inv[p]]; *flag = 1 as soon as one imaginary part is not zero
+__global__ void __launch_bounds__(kPBlock) to_native_real_check_kernel(int64_t n, const int32_t *__restrict__ perm_inv, const double2 *__restrict__ src,
+                                                                       double *dst, int *flag)
+{
+    bool any = false;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = src[perm_inv[p]];
+        dst[p] = v.x;
+        any = any || (v.y != 0.0);
+    }
+    if (any) *(volatile int *)flag = 1;
 }
 
 template <typename SrcT, typename DstT, bool ACC>
@@ -827,14 +874,14 @@ __global__ void __launch_bounds__(kPBlock) from_native_kernel(int64_t n, const i
 
 int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const void *src, void *dst)
 {
-    if (!A || !A->perm) return fail(QBGPU_ERR_STATE, "vec_to_native: the handle has no internal order");
+    if (!A || !A->perm || !A->perm_inv) return fail(QBGPU_ERR_STATE, "vec_to_native: the handle has no internal order");
     Context &c = ctx();
     const int64_t n = A->n;
     const int g = grid_rows(n);
-    if (src_cplx && dst_cplx) to_native_kernel<double2, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double2 *)src, (double2 *)dst);
-    else if (src_cplx) to_native_kernel<double2, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double2 *)src, (double *)dst);
-    else if (dst_cplx) to_native_kernel<double, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double *)src, (double2 *)dst);
-    else to_native_kernel<double, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm, (const double *)src, (double *)dst);
+    if (src_cplx && dst_cplx) to_native_kernel<double2, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double2 *)src, (double2 *)dst);
+    else if (src_cplx) to_native_kernel<double2, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double2 *)src, (double *)dst);
+    else if (dst_cplx) to_native_kernel<double, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double *)src, (double2 *)dst);
+    else to_native_kernel<double, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double *)src, (double *)dst);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
@@ -893,11 +940,39 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
         if (use_beta) QB_CUDA(cudaMemcpyAsync(c.stage_y, y, bytes, cudaMemcpyHostToDevice, c.stream));
         xd = c.stage_x; yd = c.stage_y;
     } else if (where != QBGPU_DEVICE) return fail(QBGPU_ERR_ARG, "where must be QBGPU_HOST or QBGPU_DEVICE");
-    QB_TRY(vec_to_native(A, cplx, cplx, xd, px));
-    FusedArgs fa;
-    fa.x = px; fa.y = py;
-    QB_TRY(launch_spmv(A, fa));
-    QB_TRY(vec_from_native(A, cplx, cplx, py, yd, alpha, beta));
+    // Real content behind the complex API: through model<complex<double>> every vector is complex<double>, but with real
+    // couplings H is real (val_real) and so is every vector the reference's flows produce.  The way in looks at
+    // the imaginary parts while it permutes (one pass either way); if they are all exactly zero the two passes run on the
+    // fp64 copy -- half the vector bytes, half the gather sectors, the block of x fits the shared memory of pass 1 -- and the
+    // way out widens the result.  Exact: the real parts go through the identical fma sequence, the imaginary parts are exact
+    // zeros either way.  A vector with any non-zero imaginary part takes the complex passes (QBGPU_MV_REAL_MODE=0: always).
+    bool real_content = false;
+    static const bool real_mode_on = !(getenv("QBGPU_MV_REAL_MODE") && atoi(getenv("QBGPU_MV_REAL_MODE")) == 0);
+    if (cplx && A->val_real && real_mode_on) {
+        int *flag = (int *)(c.scal_dev + 57);
+        QB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
+        to_native_real_check_kernel<<<grid_rows(A->n), kPBlock, 0, c.stream>>>(A->n, A->perm_inv, (const double2 *)xd, (double *)px, flag);
+        QB_LAUNCH_COUNT();
+        QB_CUDA(cudaGetLastError());
+        int h = 1;
+        QB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaStreamSynchronize(c.stream));
+        real_content = (h == 0);
+    }
+    if (real_content) {
+        qbgpu_matrix R = *A;                                // same arrays, fp64 vectors
+        R.api_complex = false;
+        FusedArgs fa;
+        fa.x = px; fa.y = py;
+        QB_TRY(launch_spmv(&R, fa));
+        QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
+    } else {
+        QB_TRY(vec_to_native(A, cplx, cplx, xd, px));
+        FusedArgs fa;
+        fa.x = px; fa.y = py;
+        QB_TRY(launch_spmv(A, fa));
+        QB_TRY(vec_from_native(A, cplx, cplx, py, yd, alpha, beta));
+    }
     if (where == QBGPU_HOST) {
         QB_CUDA(cudaMemcpyAsync(y, yd, bytes, cudaMemcpyDeviceToHost, c.stream));
         QB_CUDA(cudaStreamSynchronize(c.stream));

@@ -6,7 +6,7 @@ QBGPU_SPECIES_ORDER handles keep the vectors *internally* in the order
 
     p = rank(up configuration) * D_dn + rank(down configuration)
 
-(configurations = occupancy words of one spin species, ranked in ascending integer order), in which
+(configurations = occupancy words of one spin species, ranked by (odd-site bits, even-site bits), see _order_key), in which
     H = [ U * (double occupancies)  +  hops of the down electrons ]      "local" part : stays inside the block of one iu
       + [ hops of the up electrons ]                                      "cross" part : same id, another iu
 and every entry factorises as (amplitude and sign from the hopping species' own configuration) x (parity of the OTHER
@@ -24,20 +24,38 @@ import numpy as np
 import lin_builders as lb
 
 
+def _order_key(words, nsites):
+    """Sort key of an occupancy word: (bits of the odd sites, bits of the even sites), odd sites major.  With this key the
+    species order refines the reference's Lin order block-wise: the rows of one odd-site label (a contiguous block of the
+    reference's order) occupy a RECTANGLE [iu0, iu0 + Cu) x [id0, id0 + Cd) of the species order, so the permutation between
+    the two orders moves whole blocks -- cache-friendly in both directions (csrc/species.cu: build_host_tables)."""
+    odd = np.zeros_like(words)
+    even = np.zeros_like(words)
+    for s_ in range(nsites):
+        bit = (words >> s_) & 1
+        if s_ % 2:
+            odd |= bit << (s_ // 2)
+        else:
+            even |= bit << (s_ // 2)
+    return (odd << nsites) | even
+
+
 def configurations(nsites, nel):
-    """Occupancy words of one species with `nel` electrons, ascending."""
+    """Occupancy words of one species with `nel` electrons, in the species order (see _order_key)."""
     allw = np.arange(1 << nsites, dtype=np.int64)
-    return allw[lb._popcount(allw) == nel]
+    w = allw[lb._popcount(allw) == nel]
+    return w[np.argsort(_order_key(w, nsites), kind="stable")]
 
 
 def rank_in_class(nsites):
-    """rank[w] = position of w among the words with the same popcount (ascending)."""
+    """rank[w] = position of w among the words with the same popcount, in the species order."""
     allw = np.arange(1 << nsites, dtype=np.int64)
     pc = lb._popcount(allw)
+    key = _order_key(allw, nsites)
     rank = np.zeros(allw.size, dtype=np.int64)
     for c in range(nsites + 1):
         sel = np.nonzero(pc == c)[0]
-        rank[sel] = np.arange(sel.size)
+        rank[sel[np.argsort(key[sel], kind="stable")]] = np.arange(sel.size)
     return rank
 
 

@@ -45,6 +45,10 @@ WORKLOADS = {
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
+# the species step (profiles/r02_mv_reference_order_launches.csv): way in 7.24 + 1.32, pass 1 40.35 + 1.30, pass 2 39.31 + 1.31, way out 2.28 + 2.60 GB
+TRAFFIC_NCU_SPECIES = {"hubbard4x4": 95714000000}
+KERNEL_SHARES_SPECIES = {"hubbard4x4": {"to_native_real_check_kernel": 0.081, "sjds_block_smem_kernel": 0.435, "spmv_sjds_bulk_kernel": 0.429, "from_native_kernel": 0.054,
+                                        "source": "profiles/r02_mv_reference_order_launches.csv (ncu gpu__time_duration.sum: 1.37 / 7.31 / 7.20 / 0.91 ms)"}}
 TRAFFIC_NCU = {"hubbard4x4": 133686405000,     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
                "tri31_k10": 13300097712,       # profiles/r01_ncu_full_spmv_sjds_tri31_k10_details.csv: 13.14 GB read + 0.158 GB write
                "heis_chain32_k0": 8834161656}  # profiles/r01_ncu_full_spmv_sjds_heis_chain32_k0_details.csv: 8.53 GB read + 0.302 GB write
@@ -108,46 +112,95 @@ def algorithmic_bytes(nnz, nrows_local, n, s_val, s_vec):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def _host_ram_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
 def run_reference(args, workload):
     """The reference's own CPU implementation (unmodified sources compiled under oracle/_ref) on this host's cores.
-    Each step is one csr_mat<complex<double>>::MultMv on a bounded sample: the same model family at the largest size the
-    reference's own assembler builds in seconds; the rate is scaled to the workload by stored entries."""
+
+    Hubbard workloads: the reference's csr_mat<complex<double>> of the workload ITSELF (config 3: 2,992,506,660 stored entries,
+    73 GB in the reference's ILP64 layout) is filled directly -- without the LIL intermediate the reference's assembler needs
+    (> 140 GB; oracle/ref_driver.cc: hubbard_direct, pinned bit for bit to the reference's own assembly on 4x3) -- and
+    every step is one csr_mat::MultMv of the reference: same config, measured, nothing scaled.  If the host cannot hold it
+    (or QB_REF_SAMPLE=1), and for the other families: a bounded sample of the same model at the largest size the reference's
+    own assembler builds in seconds; then `value` is the SAMPLE's measured rate, `config.workload` names the sample, and the
+    figure scaled by stored entries to the full workload is reported separately as `scaled_value` (an extrapolation)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     fam, p = WORKLOADS[workload]
     cores = os.cpu_count() or 1
+    if not O.have_qb_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/qb_ref was not built (needs /root/reference at build time)"}))
+        return
+    nnz_upper_full = workload_upper_nnz(workload)
+    base = {"metric": "H*v/sec", "unit": "H*v/s", "impl": "reference", "n_gpus": 0, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (complex128 values and vectors, int64 indices)", "data": "synthetic"}
+    kernel_note = "MKL replaced by the shim's restated mkl_sparse_z_mv (row-partitioned OpenMP), BLAS-1 = OpenBLAS"
+    if fam == "hubbard" and not os.environ.get("QB_REF_SAMPLE"):
+        from math import comb
+        ns = p["Lx"] * p["Ly"]
+        n = comb(ns, p["nup"]) * comb(ns, p["ndn"])
+        need_gb = (24 * nnz_upper_full + 8 * n + 2 * 16 * n) / 1e9 * 1.03 + 4.0
+        if _host_ram_available_gb() >= need_gb:
+            steps, warm = max(1, args.steps), max(0, args.warmup)
+            est = 0.65e-9 * nnz_upper_full * 16.0 / max(cores, 1)            # seconds per product at the measured ns/entry
+            if est * (steps + warm) > 150.0:                                 # keep the arm within a few minutes
+                warm = min(warm, 1)
+                steps = max(3, int(150.0 / est) - warm)
+            res = O.run_qb_ref(["hubbard_direct", p["Lx"], p["Ly"], p["nup"], p["ndn"], p["t"], p["U"], "--time-mv", steps, warm],
+                               threads=cores, timeout=3000)
+            t_step = res["mv_total_s"] / res["mv_reps"]
+            value = 1.0 / t_step
+            desc = (f"the workload itself: csr_mat<complex<double>> of {workload} (dim {res['dim']:,}, {res['nnz']:,} stored upper-triangle entries) filled "
+                    f"directly in {res['build_seconds']:.0f} s (oracle/ref_driver.cc: hubbard_direct), {res['mv_reps']} x the reference's csr_mat::MultMv at "
+                    f"{1e3 * t_step:.1f} ms each ({1e9 * t_step / res['nnz']:.2f} ns per stored entry); {kernel_note}")
+            line = dict(base, value=value, steps=res["mv_reps"], warmup=warm, ms_per_step=1e3 * t_step,
+                        config={"workload": workload, "dim": res["dim"], "reference_upper_entries": res["nnz"], "same_config_as_gpu_arm": True,
+                                "requested_steps": args.steps, "host_build_seconds": res["build_seconds"]},
+                        cpu_baseline={"value": value, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": desc},
+                        e2e={"value": value, "unit": "H*v/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+            print(json.dumps(line))
+            return
     if fam == "hubbard":
         sample_args = ["hubbard", 4, 3, 6, 6, p["t"], p["U"]]
+        sample_name = "hubbard4x3"
         sample_desc = "Fermi-Hubbard 4x3, N_up=N_dn=6 (dim 853,776; 12,030,480 stored upper-triangle entries), reference-assembled"
     elif fam == "heisenberg_k":
         sample_args = ["heis_chain_k", 20, 0, p["k"] % 20]
+        sample_name = f"heis_chain20_k{p['k'] % 20}"
         sample_desc = f"Heisenberg chain L=20, Sz=0, momentum sector k={p['k'] % 20}, reference-assembled"
     elif fam == "orbit":
         sample_args = ["tri_k", 4, 5, 0, 3, 2]
+        sample_name = "tri4x5_k32"
         sample_desc = "triangular 4x5 Heisenberg, Sz=0, momentum sector (3,2) (complex csr_mat, the largest 2-D sector the reference assembles in seconds), reference-assembled"
     else:
         Ls = min(p["L"], 22)
         sample_args = ["heis_chain", Ls, "sz", 0]
+        sample_name = f"heis_chain{Ls}"
         sample_desc = f"Heisenberg chain L={Ls}, Sz=0, reference-assembled"
-    if not O.have_qb_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/qb_ref was not built (needs /root/reference at build time)"}))
-        return
     res = O.run_qb_ref(sample_args + ["--time-mv", max(1, args.steps), max(0, args.warmup)], threads=cores, timeout=3000)
     t_step = res["mv_total_s"] / res["mv_reps"]
     nnz_sample = res["nnz"]
-    # stored (upper-triangle) entries of the full workload: closed form from the expanded count of the generator family
-    nnz_upper_full = workload_upper_nnz(workload)
     scale = nnz_upper_full / nnz_sample
-    value = 1.0 / (t_step * scale)
-    line = {"metric": "H*v/sec", "value": value, "unit": "H*v/s", "impl": "reference", "n_gpus": 0, "steps": res["mv_reps"],
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_step * scale, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64 (complex128 values and vectors, int64 indices)", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample_desc, "scaled_by_stored_entries": scale},
-            "cpu_baseline": {"value": value, "unit": "H*v/s", "cores": cores, "kind": "reference",
-                             "sample": f"{sample_desc}; {res['mv_reps']} x csr_mat::MultMv at {1e3 * t_step:.2f} ms each "
-                                       f"({1e9 * t_step / nnz_sample:.2f} ns per stored entry), scaled x{scale:.1f} to {workload}; "
-                                       "MKL replaced by the shim's restated mkl_sparse_z_mv (row-partitioned OpenMP), BLAS-1 = OpenBLAS"},
-            "e2e": {"value": value, "unit": "H*v/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    same = abs(scale - 1.0) < 1e-12
+    value = 1.0 / t_step                          # the SAMPLE's measured rate; nothing scaled in value / ms_per_step
+    line = dict(base, value=value, steps=res["mv_reps"], ms_per_step=1e3 * t_step,
+                scaled_value=1.0 / (t_step * scale), scaled_ms_per_step=1e3 * t_step * scale,
+                scaled_note=f"extrapolated x{scale:.1f} by stored entries from the sample to {workload}: an estimate, not a measurement",
+                config={"workload": workload if same else sample_name, "sample": sample_desc, "sample_of": workload, "same_config_as_gpu_arm": same,
+                        "scaled_by_stored_entries": scale},
+                cpu_baseline={"value": value, "unit": "H*v/s", "cores": cores, "kind": "reference",
+                              "sample": f"{sample_desc}; {res['mv_reps']} x csr_mat::MultMv at {1e3 * t_step:.2f} ms each "
+                                        f"({1e9 * t_step / nnz_sample:.2f} ns per stored entry); {kernel_note}"},
+                e2e={"value": value, "unit": "H*v/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line))
 
 
@@ -362,9 +415,11 @@ def main():
     ap.add_argument("--no-lanczos", action="store_true", help="skip the E0 time-to-solution leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-species", action="store_true", help="skip the species-order probe (hubbard workloads, child process)")
-    ap.add_argument("--layout", default="default", choices=["default", "species", "species-matfree"],
-                    help="hubbard workloads, one GPU: measure the main line on a QBGPU_SPECIES_ORDER handle (stored or matrix-free) "
-                         "instead of the ordinary one; same operator, same calling convention (vectors in the reference's order)")
+    ap.add_argument("--layout", default="default", choices=["default", "ordinary", "species", "species-matfree"],
+                    help="hubbard workloads, one GPU: which handle the main line measures.  default = species (the stored two-part "
+                         "QBGPU_SPECIES_ORDER handle: same entries, same 12 bytes each, two passes); ordinary = the one-pass "
+                         "sliced-jagged handle in the reference's order; species-matfree = nothing stored.  Same operator, same "
+                         "calling convention everywhere: complex128 device vectors in the reference's order through MultMv")
     ap.add_argument("--species-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.species_probe:
@@ -399,10 +454,12 @@ def main():
 
     # ---------------------------------------------------------------- single GPU
     t0 = time.time()
+    fam_, p_ = WORKLOADS[args.workload]
     if args.layout == "default":
+        args.layout = "species" if fam_ == "hubbard" else "ordinary"
+    if args.layout == "ordinary":
         M = build_matrix(qb, args.workload)
     else:
-        fam_, p_ = WORKLOADS[args.workload]
         if fam_ != "hubbard":
             raise SystemExit("--layout species*: the species order exists for the Hubbard model only")
         M = qb.hubbard(p_["Lx"] * p_["Ly"], p_["nup"], p_["ndn"], square_bonds(p_["Lx"], p_["Ly"]), p_["t"], p_["U"],
@@ -473,6 +530,8 @@ def main():
         yr = qb.DeviceVector(n, np.float64)
         extras["real_vectors"] = dict(S_val=s_val, S_vec=8, **roof(algorithmic_bytes(Z, n, n, s_val, 8), time_products(Mr, xr, yr, args.steps)))
         try:
+            if args.layout != "ordinary":
+                raise RuntimeError("skipped on species handles")
             Md = build_matrix(qb, args.workload, flags=16)
             if Md.info.value_dict:
                 nd = Md.info.value_dict
@@ -482,6 +541,31 @@ def main():
             Md = None
             extras["value_dict_error"] = str(e)
         xr.free(); yr.free()
+
+    # ---------------------------------------------------------------- parity at the BASELINE size: sampled rows recomputed on the host
+    # in long double from the Lin tables (qbgpu_debug_rows_host: the generators' own row function, pinned entry for entry to
+    # matrices the compiled reference assembled) -- full-basis families only (the sector assemblers have no host twin)
+    parity = None
+    if fam_ in ("hubbard", "heisenberg"):
+        M.MultMv(x, y)
+        xh0, yh0 = x.to_numpy(), y.to_numpy()
+        rng = np.random.default_rng(20261017)
+        rows = np.unique(rng.integers(0, n, size=min(100000, n), dtype=np.int64))
+        yr = np.zeros(2 * rows.size)
+        if fam_ == "hubbard":
+            bl = np.array(square_bonds(p_["Lx"], p_["Ly"]), dtype=np.int32).ravel()
+            rc = L.qbgpu_debug_rows_host(1, p_["Lx"] * p_["Ly"], p_["nup"], p_["ndn"], len(bl) // 2, bl.ctypes.data, 0.0, p_["t"], p_["U"],
+                                         rows.size, rows.ctypes.data, xh0.ctypes.data, 1, yr.ctypes.data)
+        else:
+            bl = np.array([(q, (q + 1) % p_["L"]) for q in range(p_["L"])], dtype=np.int32).ravel()
+            rc = L.qbgpu_debug_rows_host(0, p_["L"], p_["L"] // 2, 0, len(bl) // 2, bl.ctypes.data, 1.0, 0.0, 0.0,
+                                         rows.size, rows.ctypes.data, xh0.ctypes.data, 1, yr.ctypes.data)
+        assert rc == 0, L.qbgpu_last_error()
+        yr = yr.view(np.complex128)
+        err = float(np.linalg.norm(yh0[rows] - yr) / np.linalg.norm(yr))
+        parity = {"rows": int(rows.size), "rel_l2_error": err, "bound": 1e-12, "ok": bool(err <= 1e-12),
+                  "how": "y = MultMv(x) of the timed handle against rows recomputed on the host in long double (Lin tables + the generators' row function)"}
+        del xh0, yh0
 
     # ---------------------------------------------------------------- e2e: host vectors through the reference-facing call
     M.MultMv(x, y)
@@ -507,17 +591,24 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "reference_upper_entries": workload_upper_nnz(args.workload),
                        "S_val": s_val, "S_vec": s_vec,
-                       "layout": ({"species": "species order, two sliced-jagged parts", "species-matfree": "species order, matrix-free"}[args.layout]
-                                  if args.layout != "default" else "sliced-jagged" if inf.format == 8 else f"csr-vector lanes={inf.lanes}"),
+                       "layout": ({"species": "species order: two sliced-jagged parts (diagonal + down hops | up hops), two passes",
+                                   "species-matfree": "species order, matrix-free"}[args.layout]
+                                  if args.layout != "ordinary" else "sliced-jagged" if inf.format == 8 else f"csr-vector lanes={inf.lanes}"),
                        "l2": "flush between steps" if need_flush else "inputs larger than L2", "matrix_bytes": inf.device_bytes,
-                       "vectors": "complex128 x and y (the reference's model<complex<double>> calling convention)"},
+                       "vectors": "complex128 x and y in the reference's order (the model<complex<double>> calling convention); x = vec_randomize(seed 1), "
+                                  "imag == 0 like every vector of the reference's flows" + (": the species handle detects it while permuting and runs its two passes "
+                                  "on fp64 copies (genuinely complex x: species_order.stored.reference_order_genuinely_complex)" if args.layout != "ordinary" else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_NCU.get(args.workload) if args.layout == "default" else None, "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
+                         "traffic": (TRAFFIC_NCU.get(args.workload) if args.layout == "ordinary" else TRAFFIC_NCU_SPECIES.get(args.workload) if args.layout == "species" else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels in the committed ncu capture (profiles/), not measured in this run",
+                         "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
                          "kernel": ("kron_local_kernel + kron_cross_kernel" if args.layout == "species-matfree" else
-                                    "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel")},
+                                    "one step = to_native_real_check_kernel + sjds_block_smem_kernel<double,double> (pass 1) + spmv_sjds_bulk_kernel<double,double> (pass 2, UBLKCP) + from_native_kernel"
+                                    if args.layout == "species" else "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel"),
+                         "kernel_shares_ncu": (KERNEL_SHARES_SPECIES.get(args.workload) if args.layout == "species" else None)},
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
                     "ms_per_step": 1e3 * e2e_s},
-            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall, "parity_sampled": parity,
             "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds, **SECTOR_PHASES}}
     line.update(extras)
 

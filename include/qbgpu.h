@@ -80,6 +80,9 @@ const char *qbgpu_version(void);
  * row i = [row_start[i], row_end[i]).  sym_upper != 0 is csr_mat::sym (src/qbasis.h:981): only col >= row is
  * stored and (i,j>i,v) stands for v at (i,j) and conj(v) at (j,i).  The device copy is independent of the host
  * arrays (they may be freed, cf. HamMat_csr_repr[0].destroy() in the reference's examples).
+ * PRECONDITION (checked; QBGPU_ERR_ARG otherwise): the referenced columns of every row are strictly ascending -- what
+ * csr_mat(lil_mat&) always produces (src/sparse.cc:202-233: the LIL rows are sorted lists).  With sym_upper the entries
+ * below the diagonal are not referenced (FILL_UPPER) and may be in any order.
  * The *_shard variants keep only rows [row_lo,row_hi) of the expanded matrix (multi-GPU row partition). */
 int qbgpu_create_dcsr(qbgpu_matrix_t *A, int64_t n, const int64_t *row_start, const int64_t *row_end,
                       const int64_t *col, const double *val, int sym_upper, int flags);
@@ -382,6 +385,12 @@ int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
  * id 1000 + v selects pass 1 of the matrix-free species-order product instead: v = 0 grid-stride rows (default),
  * 1 contiguous row ranges with one 1024-thread CTA per SM, 2 block x[iu, :] staged in shared memory. */
 int qbgpu_debug_set_variant(int id);
+/* Rows of a full-basis Heisenberg (kind 0, n0 = down spins) or Hubbard (kind 1, n0/n1 = N_up/N_dn) operator recomputed on the
+ * HOST in long double from the Lin tables (reference src/basis.cc:1144-1190) and the generators' own row function: the
+ * size-independent parity check of bench.py on the BASELINE-size matrices.  rows: indices in the reference's order; x_host: the
+ * full vector (x_complex: re,im pairs); y_out: 2 doubles per listed row.  No device involved. */
+int qbgpu_debug_rows_host(int kind, int nsites, int n0, int n1, int nbonds, const int32_t *bonds, double J, double t, double U,
+                          int64_t nrows, const int64_t *rows, const void *x_host, int x_complex, double *y_out);
 /* |col - row| beyond which a gathered entry is loaded with the L2 evict-first policy (kernels with the per-entry
  * gather policy only) */
 int qbgpu_debug_set_far_rows(int64_t rows);

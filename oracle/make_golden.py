@@ -132,8 +132,56 @@ def make_full_dynamic():
         print(f"{name}: dim={phi0.size} E0={res['E0']:.12f} norm={res['dyn_norm']:.12f} steps={res['dyn_steps']} -> {os.path.getsize(out)/1e3:.0f} kB")
 
 
+KPM_CASES = {
+    # name: (golden matrix the moments are computed on, seed of phi, number of moments, energy_scale iterations)
+    "kpm_heis16_k3": ("heis16_k3", 3, 64, 40),
+    "kpm_tri4x4_k01": ("tri4x4_k01", 3, 64, 40),
+    "kpm_hubbard4x2": ("hubbard4x2", 5, 96, 40),
+}
+
+
+def make_kpm():
+    """Chebyshev moments on the reference's own csr_mat::MultMv and energy_scale (qb_ref --kpm): pins the KPM path, for
+    which the reference has no routine of its own."""
+    only = sys.argv[2:]
+    for name, (mat, seed, nmom, iters) in KPM_CASES.items():
+        if only and name not in only:
+            continue
+        A, meta0, _ = O.load_golden(mat)
+        wd = tempfile.mkdtemp(prefix="qbkpm_")
+        path = os.path.join(wd, "A.qbcsr")
+        O.write_qbcsr(path, A)
+        res = O.run_qb_ref(["file_z", path, "--kpm", seed, nmom, iters], threads=1, workdir=wd)
+        meta = {"case": name, "matrix": mat, "seed": seed, "nmom": nmom, "iters": iters, "lo": res["kpm_lo"], "hi": res["kpm_hi"]}
+        out = os.path.join(O.GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(out, moments=np.array(res["kpm_moments"]), meta=json.dumps(meta))
+        print(f"{name}: lo={res['kpm_lo']:.12f} hi={res['kpm_hi']:.12f} mu[:4]={res['kpm_moments'][:4]} -> {os.path.getsize(out)/1e3:.1f} kB")
+
+
+def make_digest():
+    """Hubbard 4x3 (N_up = N_dn = 6; dim 853,776 -- the largest instance of BASELINE config 3's model the reference assembles
+    in seconds): too large to commit whole, so a digest of the REFERENCE's own run: 4096 sampled entries of
+    y = csr_mat::MultMv(vec_randomize(1)), |y|, the Lanczos coefficients, step count and E0."""
+    wd = tempfile.mkdtemp(prefix="qbdig_")
+    y1 = os.path.join(wd, "y1.bin")
+    res = O.run_qb_ref(["hubbard", 4, 3, 6, 6, 1.0, 1.1, "--mv", 1, y1, "--lanczos", "sr_val0", 1000], threads=8, workdir=wd)
+    y = np.fromfile(y1, dtype=np.complex128)
+    rng = np.random.default_rng(43)
+    idx = np.sort(rng.choice(y.size, size=4096, replace=False)).astype(np.int64)
+    meta = {"case": "hubbard4x3_digest", "qb_ref_args": ["hubbard", 4, 3, 6, 6, 1.0, 1.1], "dim": int(res["dim"]), "nnz": int(res["nnz"]),
+            "lanczos_steps": res["lanczos_steps"], "lanczos_E0": res["lanczos_E0"], "y_norm": float(np.linalg.norm(y)),
+            "max_abs_imag": res["max_abs_imag"]}
+    out = os.path.join(O.GOLDEN_DIR, "hubbard4x3_digest.npz")
+    np.savez_compressed(out, idx=idx, y_at_idx=y[idx], lanczos_a=np.array(res["lanczos_a"]), lanczos_b=np.array(res["lanczos_b"]), meta=json.dumps(meta))
+    print(f"hubbard4x3_digest: dim={res['dim']} nnz={res['nnz']} steps={res['lanczos_steps']} E0={res['lanczos_E0']:.12f} -> {os.path.getsize(out)/1e3:.0f} kB")
+
+
 if __name__ == "__main__":
-    if sys.argv[1:2] == ["dynamic"]:
+    if sys.argv[1:2] == ["kpm"]:
+        make_kpm()
+    elif sys.argv[1:2] == ["digest"]:
+        make_digest()
+    elif sys.argv[1:2] == ["dynamic"]:
         make_dynamic()
     elif sys.argv[1:2] == ["full_dynamic"]:
         make_full_dynamic()

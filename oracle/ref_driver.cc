@@ -357,6 +357,120 @@ static void flow_hubbard_full_szq(int Lx, int Ly, double nup, double ndn, double
     js.arr("dyn_b", hess.data(), m); js.arr("dyn_a", hess.data() + maxit, m);
 }
 
+/* ------------------------------------------------------------------------------------------------ hubbard_direct
+ * The reference's csr_mat<complex<double>> of the square-lattice Hubbard model filled DIRECTLY -- ia/ja/val in the layout of
+ * src/sparse.cc:202-233 (upper triangle, every diagonal stored, columns ascending), rows in the Lin order of
+ * src/basis.cc:1144-1190 -- without the LIL intermediate, whose forward_list nodes need > 140 GB for BASELINE config 3
+ * (SURVEY F6).  Only the ASSEMBLY is restated (same statement as tests/lin_builders.py: hubbard_upper_csr; `--check` compares
+ * it bit for bit with what the reference's own generate_Ham_sparse_full assembles, tests/test_oracle.py runs that on 4x3);
+ * the matrix then lives in the reference's own class and every action (--time-mv: csr_mat::MultMv, --lanczos, ...) is the
+ * reference's code.  This is what lets `bench.py --impl reference` time the reference on config 3 itself. */
+static inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+
+static void fill_hubbard_direct(qbasis::csr_mat<cplx> &H, int Lx, int Ly, int nup, int ndn, double t, double U)
+{
+    const int ns = Lx * Ly, nA = (ns + 1) / 2, nB = ns / 2;
+    if (2 * nA > 24) { fprintf(stderr, "hubbard_direct: at most 24 sites\n"); exit(2); }
+    /* merged bonds with multiplicity, in the order the example adds them (x outer, y inner; +x then +y) */
+    struct Bd { int i, j, w; };
+    std::vector<Bd> bonds;
+    auto site = [&](int x, int y) { return ((x % Lx + Lx) % Lx) + ((y % Ly + Ly) % Ly) * Lx; };
+    auto add = [&](int i, int j) { for (auto &b : bonds) if ((b.i == i && b.j == j) || (b.i == j && b.j == i)) { b.w++; return; } bonds.push_back({i, j, 1}); };
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) { add(site(x, y), site(x + 1, y)); add(site(x, y), site(x, y + 1)); }
+    /* Lin tables: a-label = digits (up + 2 dn) of the even sites, b-label = of the odd sites; classes by (n_up, n_dn) */
+    const uint32_t sizeA = 1u << (2 * nA), sizeB = 1u << (2 * nB);
+    const int nc = nA + 1;
+    auto counts = [](uint32_t lab, int &c0, int &c1) { c0 = popc32(lab & 0x55555555u); c1 = popc32(lab & 0xAAAAAAAAu); };
+    std::vector<int32_t> csize(nc * nc, 0), rankA(sizeA), class_off(nc * nc, 0);
+    for (uint32_t a = 0; a < sizeA; a++) { int c0, c1; counts(a, c0, c1); rankA[a] = csize[c0 * nc + c1]++; }
+    { int32_t acc = 0; for (int k = 0; k < nc * nc; k++) { class_off[k] = acc; acc += csize[k]; } }
+    std::vector<uint32_t> alist(sizeA);
+    for (uint32_t a = 0; a < sizeA; a++) { int c0, c1; counts(a, c0, c1); alist[class_off[c0 * nc + c1] + rankA[a]] = a; }
+    std::vector<int64_t> Jb((size_t)sizeB + 1, 0);
+    int64_t run = 0;
+    for (uint32_t b = 0; b < sizeB; b++) {
+        Jb[b] = run;
+        int c0, c1; counts(b, c0, c1);
+        const int n0 = nup - c0, n1 = ndn - c1;
+        if (n0 >= 0 && n0 <= nA && n1 >= 0 && n1 <= nA) run += csize[n0 * nc + n1];
+    }
+    Jb[sizeB] = run;
+    const int64_t n = run;
+    auto parity_below = [](uint32_t la, uint32_t lb, int s) {
+        const int ka = (s + 1) >> 1, kb = s >> 1;
+        const uint32_t ma = ka >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ka)) - 1u), mb = kb >= 16 ? 0xFFFFFFFFu : ((1u << (2 * kb)) - 1u);
+        return (popc32(la & ma) + popc32(lb & mb)) & 1;
+    };
+    /* one row: upper-triangle entries (col >= row), unsorted; returns their number */
+    auto row_upper = [&](int64_t r, uint32_t la, uint32_t lb, int64_t *cols, double *vals) {
+        int cnt = 0;
+        double diag = 0.0;
+        const int ndbl = popc32(la & (la >> 1) & 0x55555555u) + popc32(lb & (lb >> 1) & 0x55555555u);
+        for (int k = 0; k < ndbl; k++) diag += U;
+        cols[cnt] = r; vals[cnt] = diag; cnt++;
+        for (const auto &b : bonds) {
+            double amp = 0.0;
+            for (int k = 0; k < b.w; k++) amp += -t;
+            for (int dir = 0; dir < 2; dir++) {
+                const int to = dir ? b.j : b.i, from = dir ? b.i : b.j;
+                for (int sp = 0; sp < 2; sp++) {
+                    const uint32_t bf = 1u << (2 * (from >> 1) + sp), bt = 1u << (2 * (to >> 1) + sp);
+                    const uint32_t lf = (from & 1) ? lb : la, lt = (to & 1) ? lb : la;
+                    if (!(lf & bf) || (lt & bt)) continue;
+                    int sg = parity_below(la, lb, from);
+                    if (sp == 1 && (lf & (1u << (2 * (from >> 1))))) sg ^= 1;
+                    uint32_t na = la, nb = lb;
+                    if (from & 1) nb ^= bf; else na ^= bf;
+                    sg ^= parity_below(na, nb, to);
+                    const uint32_t lt2 = (to & 1) ? nb : na;
+                    if (sp == 1 && (lt2 & (1u << (2 * (to >> 1))))) sg ^= 1;
+                    if (to & 1) nb ^= bt; else na ^= bt;
+                    const int64_t c = Jb[nb] + rankA[na];
+                    if (c > r) { cols[cnt] = c; vals[cnt] = sg ? -amp : amp; cnt++; }
+                }
+            }
+        }
+        return cnt;
+    };
+    auto state_of = [&](int64_t r, uint32_t lb_hint, uint32_t &la) {
+        int c0, c1; counts(lb_hint, c0, c1);
+        la = alist[class_off[(nup - c0) * nc + (ndn - c1)] + (int32_t)(r - Jb[lb_hint])];
+    };
+    H.dim = n; H.sym = true;
+    H.ia = new MKL_INT[n + 1];
+    const int maxrow = 1 + 4 * (int)bonds.size();
+    /* pass 1: row lengths (parallel over b-labels: the rows of one label are contiguous) */
+    #pragma omp parallel
+    {
+        std::vector<int64_t> cols(maxrow); std::vector<double> vals(maxrow);
+        #pragma omp for schedule(dynamic, 64)
+        for (int64_t b = 0; b < (int64_t)sizeB; b++)
+            for (int64_t r = Jb[b]; r < Jb[b + 1]; r++) { uint32_t la; state_of(r, (uint32_t)b, la); H.ia[r + 1] = row_upper(r, la, (uint32_t)b, cols.data(), vals.data()); }
+    }
+    H.ia[0] = 0;
+    for (int64_t r = 0; r < n; r++) H.ia[r + 1] += H.ia[r];
+    H.nnz = H.ia[n];
+    H.ja = new MKL_INT[H.nnz];
+    H.val = new cplx[H.nnz];
+    /* pass 2: fill, columns ascending inside a row */
+    #pragma omp parallel
+    {
+        std::vector<int64_t> cols(maxrow); std::vector<double> vals(maxrow); std::vector<int> idx(maxrow);
+        #pragma omp for schedule(dynamic, 64)
+        for (int64_t b = 0; b < (int64_t)sizeB; b++)
+            for (int64_t r = Jb[b]; r < Jb[b + 1]; r++) {
+                uint32_t la; state_of(r, (uint32_t)b, la);
+                const int cnt = row_upper(r, la, (uint32_t)b, cols.data(), vals.data());
+                for (int k = 0; k < cnt; k++) idx[k] = k;
+                std::sort(idx.begin(), idx.begin() + cnt, [&](int x, int y) { return cols[x] < cols[y]; });
+                MKL_INT at = H.ia[r];
+                for (int k = 0; k < cnt; k++) { H.ja[at] = cols[idx[k]]; H.val[at] = cplx(vals[idx[k]], 0.0); at++; }
+            }
+    }
+    /* the handle the reference's constructor creates (src/sparse.cc:258) */
+    if (mkl_sparse_z_create_csr(&H.handle, SPARSE_INDEX_BASE_ZERO, H.dim, H.dim, H.ia, H.ia + 1, H.ja, H.val) != SPARSE_STATUS_SUCCESS) { fprintf(stderr, "create_csr failed\n"); exit(2); }
+}
+
 template <typename T>
 static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, Json &js)
 {
@@ -451,6 +565,38 @@ static void run_actions(qbasis::csr_mat<T> &H, int argc, char **argv, int argi, 
             qbasis::enable_ckpt = false;
             js.integer("cgck_steps", m); js.num("cgck_accuracy", accu);
             dump_vec(argv[++a], v.data() + 2 * n, sizeof(T) * n);
+        } else if (opt == "--kpm" && a + 3 < argc) {
+            /* Chebyshev moments mu_k = Re <phi| T_k(Ht) |phi>, Ht = (H - c)/s, on the REFERENCE's own pieces: [lo, hi] from the
+               reference's energy_scale (src/kpm.cc:45-88; extend 0.1, ITERS iterations), every product the reference's
+               csr_mat::MultMv (src/sparse.cc:291-297), dots accumulated in long double; phi = vec_randomize(SEED).
+               The reference itself has no Chebyshev recurrence: this is the plain three-term recurrence
+               T_0 = phi, T_1 = Ht phi, T_{k+1} = 2 Ht T_k - T_{k-1}, written here so that the moments the GPU path produces
+               are pinned to numbers computed with the reference's product. */
+            uint32_t seed = (uint32_t)atoi(argv[++a]);
+            MKL_INT nmom = atoll(argv[++a]), iters = atoll(argv[++a]);
+            std::vector<T> w(2 * n); double lo, hi;
+            qbasis::energy_scale(n, H, w.data(), lo, hi, 0.1, iters);
+            const double cc = 0.5 * (hi + lo), ss = 0.5 * (hi - lo);
+            std::vector<T> phi(n), t0(n), t1(n), t2(n);
+            qbasis::vec_randomize(n, phi.data(), seed);
+            std::vector<double> mu(nmom, 0.0);
+            auto redot = [&](const std::vector<T> &u, const std::vector<T> &v) {      /* Re <u, v> */
+                long double acc = 0.0L;
+                for (MKL_INT j = 0; j < n; j++) acc += (long double)std::real(std::conj(cplx(u[j])) * cplx(v[j]));
+                return (double)acc;
+            };
+            t0 = phi;
+            mu[0] = redot(phi, t0);
+            H.MultMv(t0.data(), t1.data());
+            for (MKL_INT j = 0; j < n; j++) t1[j] = (t1[j] - cc * t0[j]) / ss;
+            if (nmom > 1) mu[1] = redot(phi, t1);
+            for (MKL_INT k = 2; k < nmom; k++) {
+                H.MultMv(t1.data(), t2.data());
+                for (MKL_INT j = 0; j < n; j++) t2[j] = 2.0 * (t2[j] - cc * t1[j]) / ss - t0[j];
+                mu[k] = redot(phi, t2);
+                t0.swap(t1); t1.swap(t2);
+            }
+            js.num("kpm_lo", lo); js.num("kpm_hi", hi); js.arr("kpm_moments", mu.data(), nmom);
         } else if (opt == "--energy-scale" && a + 1 < argc) {
             /* reference energy_scale (src/kpm.cc:45-88); start vector = vec_randomize default seed */
             MKL_INT iters = atoll(argv[++a]);
@@ -467,12 +613,13 @@ static void usage() {
     fprintf(stderr,
         "usage: qb_ref [--threads T] [--workdir D] --out results.json <case> <args...> [actions]\n"
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
+        "        hubbard_direct Lx Ly NUP NDN T U [--check]  (csr_mat filled without the LIL intermediate; --check: compare with the reference's assembly) |\n"
         "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         "        hubbard_full_szq Lx Ly NUP NDN T U QM QN MAXIT [--dump-vecs PREFIX]  (full basis: E0, S^z_q phi0, measure_full_dynamic)\n"
         " model actions (before matrix actions): --locate-E0 NEV NCV (reference model::locate_E0_lanczos)\n"
-        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --cg-ckpt E0 MAXIT F | --energy-scale ITERS\n");
+        " matrix actions: --dump F | --vec-write SEED F | --mv SEED F | --time-mv REPS WARM | --lanczos PURPOSE MAXIT | --lanczos-ckpt PURPOSE MAXIT NP | --cg E0 F | --cg-ckpt E0 MAXIT F | --energy-scale ITERS | --kpm SEED NMOM ITERS\n");
     exit(2);
 }
 
@@ -526,6 +673,31 @@ int main(int argc, char **argv)
         std::string prefix;
         if (a + 1 < argc && std::string(argv[a]) == "--dump-vecs") { prefix = argv[a + 1]; a += 2; }
         flow_hubbard_full_szq(Lx, Ly, nu, nd, t, U, qm, qn, maxit, prefix, js);
+    } else if (c == "hubbard_direct") {
+        if (a + 6 > argc) usage();
+        int Lx = atoi(argv[a]), Ly = atoi(argv[a + 1]), nu = atoi(argv[a + 2]), nd = atoi(argv[a + 3]); double t = atof(argv[a + 4]), U = atof(argv[a + 5]); a += 6;
+        qbasis::csr_mat<cplx> H;
+        fill_hubbard_direct(H, Lx, Ly, nu, nd, t, U);
+        js.num("build_seconds", now_s() - t0);
+        if (a < argc && std::string(argv[a]) == "--check") {       /* bit for bit against the reference's own assembly */
+            a++;
+            Built b = build_hubbard(Lx, Ly, nu, nd, t, U);
+            auto &R = b.model->HamMat_csr_full[0];
+            bool same = R.dim == H.dim && R.nnz == H.nnz && R.sym == H.sym;
+            /* ia, ja exactly; values by ==, i.e. identical up to the sign of a zero imaginary part (the reference's
+               operator products leave -0.0 there on entries with a negative amplitude; no product can tell the difference) */
+            if (same) same = memcmp(R.ia, H.ia, sizeof(MKL_INT) * (H.dim + 1)) == 0 && memcmp(R.ja, H.ja, sizeof(MKL_INT) * H.nnz) == 0;
+            if (same) for (MKL_INT k = 0; k < H.nnz && same; k++) same = R.val[k] == H.val[k];
+            js.integer("direct_equals_reference_assembly", same ? 1 : 0);
+            if (!same && R.dim == H.dim && R.nnz == H.nnz) {             /* say where (diagnostics) */
+                long long d_ia = 0, d_ja = 0, d_val = 0, d_val_num = 0;
+                for (MKL_INT i = 0; i <= H.dim; i++) d_ia += R.ia[i] != H.ia[i];
+                for (MKL_INT k = 0; k < H.nnz; k++) { d_ja += R.ja[k] != H.ja[k]; d_val += memcmp(&R.val[k], &H.val[k], sizeof(cplx)) != 0; d_val_num += R.val[k] != H.val[k]; }
+                js.integer("direct_diff_ia", d_ia); js.integer("direct_diff_ja", d_ja); js.integer("direct_diff_val_bits", d_val); js.integer("direct_diff_val_numeric", d_val_num);
+                js.integer("direct_sym_ref", R.sym ? 1 : 0);
+            }
+        }
+        run_actions(H, argc, argv, a, js);
     } else if (c == "file_z" || c == "file_d") {
         if (a >= argc) usage();
         std::string path = argv[a++];

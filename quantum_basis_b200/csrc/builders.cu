@@ -55,21 +55,22 @@ __host__ __device__ __forceinline__ void unrank_row(const SectorTables &S, int64
     la = S.alist[off + (int32_t)(row - S.Jb[lb])];
 }
 
-__device__ __forceinline__ int64_t col_of(const SectorTables &S, uint32_t la, uint32_t lb) { return S.Jb[lb] + S.rankA[la]; }
+__host__ __device__ __forceinline__ int64_t col_of(const SectorTables &S, uint32_t la, uint32_t lb) { return S.Jb[lb] + S.rankA[la]; }
 
 // parity of the fermions on sites < s (electron digits 0,1,2,3 carry 0,1,1,2 fermions: popcount of the 2-bit digit)
-__device__ __forceinline__ int parity_below(uint32_t la, uint32_t lb, int s)
+__host__ __device__ __forceinline__ int parity_below(uint32_t la, uint32_t lb, int s)
 {
     const int ka = (s + 1) >> 1, kb = s >> 1;               // A sites 0,2,..,<s : ceil(s/2) of them; B sites: floor(s/2)
     const uint32_t ma = ka >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ka)) - 1u);
     const uint32_t mb = kb >= 16 ? 0xFFFFFFFFu : ((1u << (2 * kb)) - 1u);
-    return (__popc(la & ma) + __popc(lb & mb)) & 1;
+    return (popc_hd(la & ma) + popc_hd(lb & mb)) & 1;
 }
 
 // Enumerate the off-diagonal entries of the row whose basis state is (la, lb); returns the diagonal value.
-// emit(col, val) is called once per entry; distinct calls give distinct columns.
+// emit(col, val) is called once per entry; distinct calls give distinct columns.  Compiled for the host too: the sampled-row
+// check of bench.py (qbgpu_debug_rows_host) recomputes rows of the BASELINE-size matrices with exactly this function.
 template <class Emit>
-__device__ __forceinline__ double row_entries(const SectorTables &S, const ModelParams &M, uint32_t la, uint32_t lb, Emit emit)
+__host__ __device__ __forceinline__ double row_entries(const SectorTables &S, const ModelParams &M, uint32_t la, uint32_t lb, Emit emit)
 {
     double diag = 0.0;
     if (M.kind == 0) {
@@ -93,7 +94,7 @@ __device__ __forceinline__ double row_entries(const SectorTables &S, const Model
         // H = -t sum_{b,s} (c+_is c_js + h.c.) + U sum_i n_up n_dn ; digit = up + 2*dn
         const uint32_t dbl = (la & (la >> 1) & 0x55555555u);
         const uint32_t dbl_b = (lb & (lb >> 1) & 0x55555555u);
-        const int ndbl = __popc(dbl) + __popc(dbl_b);
+        const int ndbl = popc_hd(dbl) + popc_hd(dbl_b);
         for (int r = 0; r < ndbl; r++) diag += M.U;
         for (int b = 0; b < M.nbonds; b++) {
             double amp = 0.0;
@@ -1131,6 +1132,41 @@ int qbgpu_full_apply_diag(int kind, int nsites, int n0, int n1, const double *co
 int qbgpu_debug_full_apply_diag_host(int kind, int nsites, int n0, int n1, const double *coef0_reim, const double *coef1_reim,
                                      const void *x_host, void *y_host)
 { return full_apply_diag(kind, nsites, n0, n1, coef0_reim, coef1_reim, x_host, y_host, true); }
+
+/* Rows of a full-basis operator recomputed on the HOST in extended precision, no device involved: for each listed row r (the
+ * reference's Lin order) the basis state is unranked from the Lin tables, the row is regenerated by row_entries() -- the
+ * function the device generators run, pinned entry for entry to matrices assembled by the compiled reference
+ * (tests/test_gpu_parity.py) -- and y_r = sum_c H_rc x_c is accumulated in long double.  kind 0: Heisenberg (n0 = down spins),
+ * 1: Hubbard (n0, n1 = N_up, N_dn).  x_host: the full vector (complex: re,im pairs); y_out: 2 doubles per listed row. */
+int qbgpu_debug_rows_host(int kind, int nsites, int n0, int n1, int nbonds, const int32_t *bonds, double J, double t, double U,
+                          int64_t nrows, const int64_t *rows, const void *x_host, int x_complex, double *y_out)
+{
+    if (nsites < 2 || nbonds < 1 || !bonds || !rows || !x_host || !y_out || nrows < 0 || (kind != 0 && kind != 1)) return fail(QBGPU_ERR_ARG, "debug_rows_host: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, kind == 0 ? 1 : 2, n0, kind == 0 ? 0 : n1, T));
+    static thread_local ModelParams M;
+    M.kind = kind; M.J = J; M.t = t; M.U = U;
+    QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = T.Jb.data(); S.rankA = T.rankA.data(); S.alist = T.alist.data(); S.class_off = T.class_off.data(); S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    const double *xr = (const double *)x_host;
+    for (int64_t k = 0; k < nrows; k++) {
+        const int64_t r = rows[k];
+        if (r < 0 || r >= T.dim) return fail(QBGPU_ERR_ARG, "debug_rows_host: row out of range");
+        uint32_t la, lb;
+        unrank_row(S, r, la, lb);
+        long double are = 0.0L, aim = 0.0L;
+        const double diag = row_entries(S, M, la, lb, [&](int64_t c, double v) {
+            if (x_complex) { are += (long double)v * xr[2 * c]; aim += (long double)v * xr[2 * c + 1]; }
+            else are += (long double)v * xr[c];
+        });
+        if (x_complex) { are += (long double)diag * xr[2 * r]; aim += (long double)diag * xr[2 * r + 1]; }
+        else are += (long double)diag * xr[r];
+        y_out[2 * k] = (double)are; y_out[2 * k + 1] = (double)aim;
+    }
+    return QBGPU_OK;
+}
 
 int64_t qbgpu_dim_heisenberg(int nsites, int ndown)
 {

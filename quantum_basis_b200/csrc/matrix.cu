@@ -29,6 +29,7 @@ constexpr int kCBlock = 256;
 
 // error flag bits written by the conversion kernels
 constexpr int kErrColRange = 1;
+constexpr int kErrColOrder = 2;   // a row whose referenced columns are not strictly ascending
 
 template <typename T> struct ValOps;
 template <> struct ValOps<double>  { __device__ static double conj(double v) { return v; }  __device__ static double imag_abs(double) { return 0.0; } };
@@ -41,11 +42,17 @@ __global__ void __launch_bounds__(kCBlock) count_kernel(int64_t n, int64_t base,
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int cu = 0;
+        int64_t prev = -1;
         for (int64_t p = rs[i] - base; p < re[i] - base; p++) {
             const int64_t j = col[p];
             if (j < 0 || j >= n) { atomicOr(err, kErrColRange); continue; }
+            if (sym && j < i) continue;                     // FILL_UPPER: the lower part is not referenced
+            // the device layout keeps the referenced entries of a row in input order and every later stage (column
+            // blocks of the multi-GPU exchanges, the ring order) relies on ascending columns -- what the reference's
+            // csr_mat(lil_mat&) always produces (sorted forward_list, src/sparse.cc:202-233); anything else is refused
+            if (j <= prev) atomicOr(err, kErrColOrder);
+            prev = j;
             if (sym) {
-                if (j < i) continue;                        // FILL_UPPER: the lower part is not referenced
                 cu++;
                 if (j != i && j >= lo && j < hi) atomicAdd(&cnt_t[j - lo], 1);
             } else {
@@ -164,6 +171,7 @@ static int convert_device(qbgpu_matrix *A, int64_t n, int64_t base, const int64_
     QB_CU(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     QB_CU(cudaStreamSynchronize(c.stream));
     if (herr & kErrColRange) { cleanup(); return fail(QBGPU_ERR_ARG, "create_csr: column index out of range"); }
+    if (herr & kErrColOrder) { cleanup(); return fail(QBGPU_ERR_ARG, "create_csr: the columns of a row must be strictly ascending (as csr_mat(lil_mat&) stores them, reference src/sparse.cc:202-233)"); }
     A->nnz = nnz;
     T *oval = nullptr;
     QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (nnz ? nnz : 1) + 64));

@@ -242,3 +242,27 @@ def test_full_basis_szq_matches_reference_moprXvec_full(name):
     _lib.check(_lib.lib().qbgpu_debug_full_apply_diag_host(0, 12, 5, 0, p(ones), p(ones), p(np.ascontiguousarray(xs[:792])), p(ys)))
     assert np.abs(ys[:792] - 1.0 * xs[:792]).max() < 1e-15            # 7 up, 5 down: Sz_total = +1
     assert np.array_equal(LB.apply_onsite_diag(12, 1, (5,), ones, None, xs[:792]), ys[:792])
+
+
+@pytest.mark.parametrize("name", ["hubbard4x2"])
+def test_host_row_function_against_the_reference_assembled_matrix(oracle, name):
+    """qbgpu_debug_rows_host (the sampled-row parity check bench.py runs on the BASELINE-size matrices: rows regenerated on the
+    host from the Lin tables by the generators' own row function, accumulated in long double) against the long-double product
+    on the matrix the compiled reference assembled."""
+    import ctypes as C
+    import quantum_basis_b200 as qb
+    L = qb.lib()
+    A, meta, ex = oracle.load_golden(name)
+    n = A.dim
+    x = oracle.vec_randomize(n, 1) + 1j * oracle.vec_randomize(n, 2).real
+    want = oracle.spmv_ld(A, x)
+    rows = np.arange(n, dtype=np.int64)
+    y = np.zeros(2 * n)
+    bonds = np.array(B.square_bonds(4, 2), dtype=np.int32).ravel()
+    rc = L.qbgpu_debug_rows_host(1, 8, 4, 4, len(bonds) // 2, bonds.ctypes.data, 0.0, 1.0, 1.1, n, rows.ctypes.data, x.ctypes.data, 1, y.ctypes.data)
+    assert rc == 0
+    assert np.linalg.norm(y.view(np.complex128) - want) <= 1e-15 * np.linalg.norm(want)
+    with pytest.raises(Exception):
+        bad = np.array([n], dtype=np.int64)
+        from quantum_basis_b200 import _lib
+        _lib.check(L.qbgpu_debug_rows_host(1, 8, 4, 4, len(bonds) // 2, bonds.ctypes.data, 0.0, 1.0, 1.1, 1, bad.ctypes.data, x.ctypes.data, 1, y.ctypes.data))

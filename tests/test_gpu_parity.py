@@ -4,6 +4,8 @@ the committed reference outputs (tests/golden) and the reference's published gol
 Tolerances (BASELINE.json north_star): per-product relative l2 <= 1e-12; E0 relative <= 1e-10; KPM moments <= 1e-9.
 Integer/index work (expanded layout, generator output, vec_randomize sequence) is compared exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -67,6 +69,14 @@ def test_create_rejects_bad_input(oracle):
         qb.csr_mat(A.dim, A.ia, ja, A.val, True)
     with pytest.raises(qb.QbgpuError):
         qb.csr_mat(A.dim, A.ia[:-1], A.ja, A.val, True)
+    # columns of a row out of order (two referenced entries swapped): refused, not silently mis-split later
+    r = int(np.argmax(np.diff(A.ia) >= 3))
+    ja2, val2 = A.ja.copy(), A.val.copy()
+    p = A.ia[r]
+    ja2[p + 1], ja2[p + 2] = A.ja[p + 2], A.ja[p + 1]
+    val2[p + 1], val2[p + 2] = A.val[p + 2], A.val[p + 1]
+    with pytest.raises(qb.QbgpuError, match="ascending"):
+        qb.csr_mat(A.dim, A.ia, ja2, val2, True)
 
 
 # ---------------------------------------------------------------------------------------------- products
@@ -899,3 +909,55 @@ def test_device_sectors_reproduce_the_published_sector_energies():
         E = qb.locate_E0_lanczos(sec.heisenberg(R.triangular_bonds(4, 4)), nev=1, ncv=0)["eigenvals"][0]
         assert abs(E - e0) < 1e-8, (mn, E)
         sec.free()
+
+
+@pytest.mark.parametrize("name", ["kpm_heis16_k3", "kpm_tri4x4_k01", "kpm_hubbard4x2"])
+def test_kpm_moments_pinned_to_the_references_product(oracle, name):
+    """Chebyshev moments of the device loop (qbgpu_kpm_moments_z: two moments per product through the doubling identities)
+    against the moments oracle/ref_driver.cc computed with the compiled reference's own csr_mat::MultMv and energy_scale
+    (tests/golden/kpm_*.npz): 1e-9, BASELINE.json's bound."""
+    import json
+    z = np.load(os.path.join(oracle.GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    A, m0, _ = oracle.load_golden(meta["matrix"])
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    phi = oracle.vec_randomize(A.dim, meta["seed"])
+    mu = qb.kpm_moments(M, phi, meta["lo"], meta["hi"], meta["nmom"])
+    assert np.abs(mu - z["moments"]).max() < 1e-9
+    lo, hi = qb.energy_scale(A.dim, M, np.zeros(2 * A.dim, dtype=np.complex128), 0.1, meta["iters"])      # the reference's bounds, on the device
+    assert abs(lo - meta["lo"]) < 1e-8 and abs(hi - meta["hi"]) < 1e-8
+
+
+@pytest.mark.parametrize("kind", ["ordinary", "species", "species_matfree", "matfree"])
+def test_hubbard4x3_against_the_references_own_run(oracle, kind):
+    """BASELINE config 3's model at the largest size the reference itself assembles in seconds (4x3, N_up = N_dn = 6, dim
+    853,776): every handle kind, generated on the device, against the digest of the compiled reference's run
+    (tests/golden/hubbard4x3_digest.npz): sampled entries of y = MultMv(vec_randomize(1)) and |y| to 1e-12, the Lanczos step
+    count, and E0 = -16.879382788684 to 1e-10."""
+    import json
+    import lin_builders as B
+    from quantum_basis_b200 import _lib
+    z = np.load(os.path.join(oracle.GOLDEN_DIR, "hubbard4x3_digest.npz"))
+    meta = json.loads(str(z["meta"]))
+    bonds = B.square_bonds(4, 3)
+    kw = {"ordinary": {}, "species": dict(flags=_lib.SPECIES_ORDER), "species_matfree": dict(flags=_lib.SPECIES_ORDER, matrix_free=True),
+          "matfree": dict(matrix_free=True)}[kind]
+    M = qb.hubbard(12, 6, 6, bonds, 1.0, 1.1, **kw)
+    n = M.dim
+    assert n == meta["dim"]
+    x = qb.vec_randomize(n, 1, device=True)
+    y = qb.DeviceVector(n)
+    M.MultMv(x, y)
+    yh = y.to_numpy()
+    assert np.linalg.norm(yh[z["idx"]] - z["y_at_idx"]) <= 1e-12 * np.linalg.norm(z["y_at_idx"])
+    assert abs(np.linalg.norm(yh) - meta["y_norm"]) <= 1e-12 * meta["y_norm"]
+    v = np.zeros(2 * n, dtype=np.complex128)
+    v[:n] = oracle.vec_randomize(n, 1)
+    hess = np.zeros(2000)
+    m = qb.lanczos(0, 999, 1000, n, M, v, hess, "sr_val0")
+    assert abs(m - meta["lanczos_steps"]) <= 1
+    e0 = qb.hess_eigen(hess, 1000, m)[0][0]
+    assert abs(e0 - meta["lanczos_E0"]) <= 1e-10 * abs(meta["lanczos_E0"])
+    assert abs(e0 + 16.879382788684) < 1e-9
+    k = 20
+    assert np.abs(hess[1000:1000 + k] - z["lanczos_a"][:k]).max() < 1e-10 and np.abs(hess[1:k] - z["lanczos_b"][1:k]).max() < 1e-10

@@ -292,6 +292,12 @@ int qbgpu_create_matfree_heisenberg(qbgpu_matrix_t *A, int nsites, int ndown, in
                                     int api_complex, int flags, int64_t row_lo, int64_t row_hi);
 int qbgpu_create_matfree_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbonds, const int32_t *bonds,
                                  double t, double U, int api_complex, int flags, int64_t row_lo, int64_t row_hi);
+/* The two parts of a STORED species-order handle or row shard as handles of their own (views sharing the arrays): `local` =
+ * diagonal + hops of the down electrons (its gathers never leave the handle's own rows: on a shard it needs no remote data),
+ * `cross` = hops of the up electrons.  The multi-GPU product: start the exchange of x, multiply the local part (y = ...),
+ * wait for the slices, multiply the cross part (y += ...).  Destroy the views before the handle. */
+int qbgpu_species_parts(qbgpu_matrix_t A, qbgpu_matrix_t *local_part, qbgpu_matrix_t *cross_part);
+
 /* --------------------------------------------------------------------- species order (Hubbard, QBGPU_SPECIES_ORDER)
  * In the reference's Lin-table order every hopping term of the Hubbard matrix sends a row far away in the index space,
  * and the gathers of x cost ~19 vector sizes of DRAM traffic per product instead of 1.  With QBGPU_SPECIES_ORDER the
@@ -384,6 +390,38 @@ int64_t qbgpu_dim_hubbard(int nsites, int nup, int ndn);
  * (only in builds with -DQBGPU_TUNING_VARIANTS; otherwise a no-op).  id 0 = production configuration.
  * id 1000 + v selects pass 1 of the matrix-free species-order product instead: v = 0 grid-stride rows (default),
  * 1 contiguous row ranges with one 1024-thread CTA per SM, 2 block x[iu, :] staged in shared memory. */
+/* ---------------------------------------------------------------------------- multi-GPU drivers (csrc/dist.cu)
+ * One process per GPU; everything a rank needs from its peers travels through peer memory (CUDA IPC over NVLink): copy-engine
+ * pulls of the vector slices and a push-based, deterministic all-reduce kernel for the scalars -- no MPI / NCCL inside, so a
+ * C or C++ host (the reference is one: model<T>::locate_E0_lanczos, src/model.cc:1124-1316) can drive the GPUs of a box with
+ * this library alone.  The host hands the 64-byte handles around by any means it has.
+ *   create   every rank: rows [bounds[r], bounds[r+1]) belong to rank r; vectors are complex128 or fp64
+ *   export   64 bytes to give to every other rank;  connect: all ranks' handles, rank-major (world * 64 bytes)
+ * A shard is (local_part, rest): for a species-order shard the two views of qbgpu_species_parts (the local part needs no
+ * remote data and runs while the slices travel); for any other row shard local_part = NULL and rest = the shard.
+ * All entry points are collective: every rank calls them in the same order. */
+typedef struct qbgpu_dist *qbgpu_dist_t;
+int qbgpu_dist_create(qbgpu_dist_t *D, int rank, int world, int64_t n, const int64_t *bounds, int vec_complex);
+int qbgpu_dist_export(qbgpu_dist_t D, void *handle64);
+int qbgpu_dist_connect(qbgpu_dist_t D, const void *handles_world_x_64);
+int qbgpu_dist_destroy(qbgpu_dist_t D);
+int qbgpu_dist_own(qbgpu_dist_t D, int b, void **own_slice_dev, int64_t *nloc);   /* this rank's rows of vector buffer b (0 | 1) */
+int qbgpu_dist_full(qbgpu_dist_t D, int b, void **full_vector_dev);
+int qbgpu_dist_barrier(qbgpu_dist_t D);                                            /* stream-ordered, device-side */
+int qbgpu_dist_allreduce(qbgpu_dist_t D, double *dev, int count);                  /* in-place sum of <= 8 device doubles, rank order */
+int qbgpu_dist_randomize(qbgpu_dist_t D, int b, uint32_t seed, const int32_t *ref_row_dev);
+int qbgpu_species_ref_rows(int nsites, int nup, int ndn, int64_t row_lo, int64_t row_hi, int32_t *ref_rows_dev);
+int qbgpu_dist_mv(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int b, void *y_local_dev, int barrier);
+/* lanczos(0, np, maxit, ...) of src/lanczos.cc:134-266 on the shards: "sr_val0" with the stop rule of :228-248, or "dnmcs" */
+int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int64_t np, int64_t maxit, int64_t *m,
+                       double *hess, const char *purpose, int stop_on_breakdown);
+/* energy_scale of src/kpm.cc:45-88; Chebyshev moments of the own slices of X[0]; eigenvec_CG of src/lanczos.cc:281-341 */
+int qbgpu_dist_energy_scale(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, const int32_t *ref_row_dev, double *lo, double *hi,
+                            double extend, int64_t iters);
+int qbgpu_dist_kpm_moments(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, double lo, double hi, int64_t nmom, double *mu);
+int qbgpu_dist_eigenvec_cg(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int64_t maxit, int64_t *m, const double E0[2],
+                           double *accu, void *v_dev, void *r_dev, void *p_dev, void *pp_dev);
+
 int qbgpu_debug_set_variant(int id);
 /* Rows of a full-basis Heisenberg (kind 0, n0 = down spins) or Hubbard (kind 1, n0/n1 = N_up/N_dn) operator recomputed on the
  * HOST in long double from the Lin tables (reference src/basis.cc:1144-1190) and the generators' own row function: the

@@ -223,6 +223,13 @@ class csr_mat:
         check(lib().qbgpu_native_order(self.handle, C.byref(f)))
         return bool(f.value)
 
+    def species_parts(self):
+        """(local, cross): the two parts of a stored species-order handle or row shard as handles of their own (views).  The
+        local part's gathers never leave the handle's own rows -- on a shard it needs no remote data."""
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib().qbgpu_species_parts(self.handle, C.byref(a), C.byref(b)))
+        return csr_mat._adopt(a, True), csr_mat._adopt(b, True)
+
     def native_perm(self):
         """perm[r] = internal index of the reference's basis state r (species-order handles)."""
         p = np.empty(self.dim, dtype=np.int32)

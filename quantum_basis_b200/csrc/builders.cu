@@ -348,6 +348,48 @@ int species_perm_build(const HostTables &T, const int32_t *d_rank_in_class, int6
     return QBGPU_OK;
 }
 
+// the inverse on a row range of the species order: out[p - lo] = the reference's row r with species index p, lo <= p < hi
+__global__ void __launch_bounds__(kBBlock) species_ref_rows_kernel(SectorTables S, int64_t n, const int32_t *__restrict__ rank_in_class, int64_t Dd,
+                                                                   int64_t lo, int64_t hi, int32_t *out)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = species_index_of_row(S, r, rank_in_class, Dd);
+        if (p >= lo && p < hi) out[p - lo] = (int32_t)r;
+    }
+}
+
+int species_ref_rows_build(const HostTables &T, const int32_t *d_rank_in_class, int64_t Dd, int64_t lo, int64_t hi, int32_t *d_out)
+{
+    Context &c = ctx();
+    if (T.bps != 2) return fail(QBGPU_ERR_ARG, "species order: electron sectors only");
+    int64_t *d_Jb = nullptr;
+    int32_t *d_rank = nullptr, *d_off = nullptr;
+    uint32_t *d_alist = nullptr;
+    auto cleanup = [&]() { cudaFree(d_Jb); cudaFree(d_rank); cudaFree(d_off); cudaFree(d_alist); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    QB_CU(cudaMalloc(&d_Jb, sizeof(int64_t) * T.Jb.size()));
+    QB_CU(cudaMalloc(&d_rank, sizeof(int32_t) * T.rankA.size()));
+    QB_CU(cudaMalloc(&d_alist, sizeof(uint32_t) * T.alist.size()));
+    QB_CU(cudaMalloc(&d_off, sizeof(int32_t) * T.class_off.size()));
+    QB_CU(cudaMemcpyAsync(d_Jb, T.Jb.data(), sizeof(int64_t) * T.Jb.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_rank, T.rankA.data(), sizeof(int32_t) * T.rankA.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_alist, T.alist.data(), sizeof(uint32_t) * T.alist.size(), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMemcpyAsync(d_off, T.class_off.data(), sizeof(int32_t) * T.class_off.size(), cudaMemcpyHostToDevice, c.stream));
+    SectorTables S;
+    S.nsites = T.nsites; S.bps = T.bps; S.nA = T.nA; S.nB = T.nB; S.t0 = T.t0; S.t1 = T.t1; S.dim = T.dim;
+    S.Jb = d_Jb; S.rankA = d_rank; S.alist = d_alist; S.class_off = d_off; S.sizeB = (uint32_t)(T.Jb.size() - 1);
+    int64_t g = (T.dim + kBBlock - 1) / kBBlock;
+    if (g < 1) g = 1;
+    if (g > 148 * 64) g = 148 * 64;
+    species_ref_rows_kernel<<<(int)g, kBBlock, 0, c.stream>>>(S, T.dim, d_rank_in_class, Dd, lo, hi, d_out);
+    QB_LAUNCH_COUNT();
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+#undef QB_CU
+    cleanup();
+    return QBGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ matrix-free
 // Neighbour tables for the matrix-free kernel: instead of testing every (bond, direction, spin) -- 128 tests per row on
 // the 4x4 lattice, a quarter of which fire -- the kernel walks the set bits of "occupied site" words and, for each,
@@ -1230,10 +1272,7 @@ int qbgpu_build_hubbard(qbgpu_matrix_t *A, int nsites, int nup, int ndn, int nbo
     static thread_local ModelParams M;
     M.kind = 1; M.J = 0; M.t = t; M.U = U;
     QB_TRY(merge_bonds(nsites, nbonds, bonds, M));
-    if (flags & QBGPU_SPECIES_ORDER) {
-        if (row_lo != 0 || (row_hi >= 0 && row_hi != T.dim)) return fail(QBGPU_ERR_ARG, "build_hubbard: species order has no row shards");
-        return species_build_stored(A, T, M, api_complex, flags);
-    }
+    if (flags & QBGPU_SPECIES_ORDER) return species_build_stored(A, T, M, api_complex, flags, row_lo, row_hi);   // shards: whole up configurations
     return build_generic(A, T, M, api_complex, flags, row_lo, row_hi);
 }
 

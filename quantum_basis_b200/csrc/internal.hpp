@@ -49,6 +49,9 @@ struct qbgpu_matrix {
     void    *sp = nullptr;
     qbgpu_matrix *second = nullptr;
     int32_t *slice_order = nullptr;
+    // > 0: rows [u*block_D, (u+1)*block_D) reference only columns of the same block (the local part of a species handle):
+    // the product may stage the block of x in shared memory (sjds_bulk.cu: sjds_block_smem_kernel)
+    int64_t  block_D = 0;
     // column part of a matrix-free species shard (qbgpu_split_columns): only the up-hops whose target configuration lies in
     // [sp_col_lo, sp_col_hi) (units: up configurations), plus the whole local pass when sp_has_local; -1 = no filter
     int64_t  sp_col_lo = -1, sp_col_hi = -1;

@@ -72,7 +72,7 @@ static int tridiag_ql(int64_t m, double *d, double *e, double *z, double *zlast)
 // count, to machine precision.  O(m) per evaluation: the per-step part of the stop rule (the relative change of the
 // lowest Ritz value, src/lanczos.cc:232-239) needs nothing else; the O(m^2) QL solve for the residual estimate
 // |b_m s_{m-1}| (:231) is only run once that change has stayed below the threshold for more than 15 steps.
-static double tridiag_smallest(const double *hess, int64_t maxit, int64_t m)
+double tridiag_smallest(const double *hess, int64_t maxit, int64_t m)
 {
     const double *a = hess + maxit, *b = hess;             // b[j] couples j-1 and j (j = 1..m-1)
     double lo = a[0], hi = a[0];
@@ -101,7 +101,7 @@ static double tridiag_smallest(const double *hess, int64_t maxit, int64_t m)
 }
 
 // ritz ascending ("sr"); s (optional) full vectors; s_last0 (optional) = last component of the lowest vector
-static int hess_eigen_host(const double *hess, int64_t maxit, int64_t m, double *ritz, double *s, double *s_last0)
+int hess_eigen_host(const double *hess, int64_t maxit, int64_t m, double *ritz, double *s, double *s_last0)
 {
     std::vector<double> d(m), e(m), z, zl;
     std::vector<int64_t> ord(m);

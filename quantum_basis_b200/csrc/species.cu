@@ -275,10 +275,15 @@ __host__ __device__ __forceinline__ void species_rowptr_at(const SpeciesView &V,
     rc = V.Dd * u0 + id * len;
 }
 
-__global__ void __launch_bounds__(kPBlock) species_rowptr_kernel(SpeciesView V, int64_t n, int64_t *rp_local, int64_t *rp_cross)
+// rows [p0, p1] of the full operator (a row shard: whole up configurations); offsets relative to the shard's first entry
+__global__ void __launch_bounds__(kPBlock) species_rowptr_kernel(SpeciesView V, int64_t n, int64_t p0, int64_t p1, int64_t base_l, int64_t base_c,
+                                                                 int64_t *rp_local, int64_t *rp_cross)
 {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += (int64_t)gridDim.x * blockDim.x)
-        species_rowptr_at(V, n, p, rp_local[p], rp_cross[p]);
+    for (int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= p1; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rl, rc;
+        species_rowptr_at(V, n, p, rl, rc);
+        rp_local[p - p0] = rl - base_l; rp_cross[p - p0] = rc - base_c;
+    }
 }
 
 template <typename ValT> __host__ __device__ __forceinline__ void put_entry(int32_t *col, ValT *val, int64_t at, int32_t c, double v)
@@ -290,12 +295,13 @@ template <typename ValT> __host__ __device__ __forceinline__ void put_entry(int3
 // both parts of row p, columns ascending
 template <typename ValT>
 __host__ __device__ __forceinline__ void species_fill_row(const SpeciesView &V, const double *ampw, const double *diagk, int64_t p,
-                                                          int32_t *col_l, ValT *val_l, int32_t *col_c, ValT *val_c)
+                                                          int32_t *col_l, ValT *val_l, int32_t *col_c, ValT *val_c,
+                                                          int64_t base_l = 0, int64_t base_c = 0)
 {
     const int64_t iu = p / V.Dd, id = p - iu * V.Dd;
     const uint32_t U = V.ulist[iu], D = V.dlist[id];
     // local part: down hops sorted by target, the diagonal (always stored, src/sparse.cc:44-54) at its sorted position
-    int64_t at = iu * (V.tot_d + V.Dd) + (int64_t)V.dptr[id] + id;
+    int64_t at = iu * (V.tot_d + V.Dd) + (int64_t)V.dptr[id] + id - base_l;
     bool diag_done = false;
     for (int e = V.dptr[id]; e < V.dptr[id + 1]; e++) {
         const uint2 h = V.dhop[e];
@@ -305,7 +311,7 @@ __host__ __device__ __forceinline__ void species_fill_row(const SpeciesView &V, 
     if (!diag_done) put_entry(col_l, val_l, at++, (int32_t)p, diagk[popc_hd(U & D)]);
     // cross part: up hops, sorted by target
     const int64_t u0 = V.uptr[iu], len = (int64_t)V.uptr[iu + 1] - u0;
-    at = V.Dd * u0 + id * len;
+    at = V.Dd * u0 + id * len - base_c;
     for (int64_t e = u0; e < u0 + len; e++) {
         const uint2 h = V.uhop[e];
         put_entry(col_c, val_c, at++, (int32_t)((int64_t)h.x * V.Dd + id), hop_value(h.y, D, ampw));
@@ -313,15 +319,16 @@ __host__ __device__ __forceinline__ void species_fill_row(const SpeciesView &V, 
 }
 
 template <typename ValT>
-__global__ void __launch_bounds__(kPBlock) species_fill_kernel(SpeciesView V, int64_t n, const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
+__global__ void __launch_bounds__(kPBlock) species_fill_kernel(SpeciesView V, int64_t p0, int64_t p1, int64_t base_l, int64_t base_c,
+                                                               const double *__restrict__ ampw_g, const double *__restrict__ diagk_g,
                                                                int32_t *col_l, ValT *val_l, int32_t *col_c, ValT *val_c)
 {
     __shared__ double ampw[kMaxWeight + 1], diagk[kMaxDbl + 1];
     for (int k = threadIdx.x; k <= kMaxWeight; k += blockDim.x) ampw[k] = ampw_g[k];
     for (int k = threadIdx.x; k <= kMaxDbl; k += blockDim.x) diagk[k] = diagk_g[k];
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
-        species_fill_row<ValT>(V, ampw, diagk, p, col_l, val_l, col_c, val_c);
+    for (int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (int64_t)gridDim.x * blockDim.x)
+        species_fill_row<ValT>(V, ampw, diagk, p, col_l, val_l, col_c, val_c, base_l, base_c);
 }
 
 
@@ -337,40 +344,55 @@ static void make_slice_order(int64_t n, int64_t Dd, int W, std::vector<int32_t> 
     for (int64_t s = 0; s < ns; s++) order[start[((s * 32) % Dd) / W]++] = (int32_t)s;
 }
 
-int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags)
+// row_lo/row_hi: a row shard (multi-GPU) -- whole up configurations only, rows [u_lo * D_dn, u_hi * D_dn); it has no
+// permutation: its vectors (x full length, y and z the local rows) are in the internal order, as every sharded handle's are
+// in "row order".  The local part of a shard references only columns of the shard's own rows.
+int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelParams &M, int api_complex, int flags, int64_t row_lo, int64_t row_hi)
 {
     if (!out) return fail(QBGPU_ERR_ARG, "null handle pointer");
     *out = nullptr;
     const double t0 = wall_s();
     SpeciesHost H;
     qbgpu_matrix *A = nullptr;
-    QB_TRY(species_common(&A, T, M, api_complex, H));
+    if (row_hi < 0) row_hi = T.dim;
+    const bool shard = !(row_lo == 0 && row_hi == T.dim);
+    QB_TRY(species_common(&A, T, M, api_complex, H, !shard));
     Context &c = ctx();
     Species *S = (Species *)A->sp;
-    const int64_t n = A->n, Dd = S->Dd, Du = S->Du;
+    const int64_t n = A->n, Dd = S->Dd;
+    if (shard) {
+        if (row_lo < 0 || row_lo > row_hi || row_hi > n || row_lo % Dd != 0 || row_hi % Dd != 0)
+        { qbgpu_destroy(A); return fail(QBGPU_ERR_ARG, "species order: a row shard must consist of whole up configurations (multiples of D_dn rows)"); }
+        A->row_lo = row_lo; A->row_hi = row_hi;
+    }
+    const int64_t nloc = row_hi - row_lo, u_lo = row_lo / Dd, u_hi = row_hi / Dd;
     auto *C = new qbgpu_matrix;                             // the cross part
     A->second = C;
-    C->n = n; C->row_lo = 0; C->row_hi = n; C->api_complex = A->api_complex;
+    C->n = n; C->row_lo = row_lo; C->row_hi = row_hi; C->api_complex = A->api_complex;
     A->val_real = C->val_real = !(flags & QBGPU_KEEP_COMPLEX) || !api_complex;
-    A->nnz = Du * (S->tot_d + Dd);
-    C->nnz = Dd * S->tot_u;
-    A->nnz_input = (A->nnz + C->nnz + n) / 2;               // what the reference would store: upper triangle incl. the diagonal
+    const int64_t base_l = u_lo * (S->tot_d + Dd), base_c = Dd * (int64_t)H.ptr[0][u_lo];
+    A->nnz = (u_hi - u_lo) * (S->tot_d + Dd);
+    C->nnz = Dd * ((int64_t)H.ptr[0][u_hi] - (int64_t)H.ptr[0][u_lo]);
+    A->nnz_input = (A->nnz + C->nnz + nloc) / 2;            // what the reference would store: upper triangle incl. the diagonal
     C->nnz_input = C->nnz;
+    A->block_D = Dd;                                        // pass 1 may keep the block of x in shared memory (sjds_bulk.cu)
 #define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
-    QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (n + 1)));
-    QB_CU(cudaMalloc(&C->rowptr, sizeof(int64_t) * (n + 1)));
+    QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (nloc + 1)));
+    QB_CU(cudaMalloc(&C->rowptr, sizeof(int64_t) * (nloc + 1)));
     QB_CU(cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(A->nnz ? A->nnz : 1) + 64));
     QB_CU(cudaMalloc(&A->val, A->val_bytes() * (size_t)(A->nnz ? A->nnz : 1) + 64));
     QB_CU(cudaMalloc(&C->col, sizeof(int32_t) * (size_t)(C->nnz ? C->nnz : 1) + 64));
     QB_CU(cudaMalloc(&C->val, C->val_bytes() * (size_t)(C->nnz ? C->nnz : 1) + 64));
     const SpeciesView V = view_of(S);
-    species_rowptr_kernel<<<grid_rows(n + 1), kPBlock, 0, c.stream>>>(V, n, A->rowptr, C->rowptr);
+    species_rowptr_kernel<<<grid_rows(nloc + 1), kPBlock, 0, c.stream>>>(V, n, row_lo, row_hi, base_l, base_c, A->rowptr, C->rowptr);
     QB_LAUNCH_COUNT();
-    if (A->val_real)
-        species_fill_kernel<double><<<grid_rows(n), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, A->col, (double *)A->val, C->col, (double *)C->val);
-    else
-        species_fill_kernel<double2><<<grid_rows(n), kPBlock, 0, c.stream>>>(V, n, S->ampw, S->diagk, A->col, (double2 *)A->val, C->col, (double2 *)C->val);
-    QB_LAUNCH_COUNT();
+    if (nloc > 0) {
+        if (A->val_real)
+            species_fill_kernel<double><<<grid_rows(nloc), kPBlock, 0, c.stream>>>(V, row_lo, row_hi, base_l, base_c, S->ampw, S->diagk, A->col, (double *)A->val, C->col, (double *)C->val);
+        else
+            species_fill_kernel<double2><<<grid_rows(nloc), kPBlock, 0, c.stream>>>(V, row_lo, row_hi, base_l, base_c, S->ampw, S->diagk, A->col, (double2 *)A->val, C->col, (double2 *)C->val);
+        QB_LAUNCH_COUNT();
+    }
     QB_CU(cudaStreamSynchronize(c.stream));
     QB_CU(cudaGetLastError());
     // layout: always the sliced-jagged kernels (the traversal order of the cross part exists only there)
@@ -381,7 +403,7 @@ int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     }
     { int rc = sjds_convert(A, true); if (rc == QBGPU_OK) rc = sjds_convert(C, true); if (rc) { qbgpu_destroy(A); return rc; } }
     std::vector<int32_t> order;
-    make_slice_order(n, Dd, S->tile, order);
+    make_slice_order(nloc, Dd, S->tile, order);
     QB_CU(upload(&C->slice_order, order.data(), order.size(), c.stream));
     QB_CU(cudaStreamSynchronize(c.stream));
 #undef QB_CU
@@ -786,8 +808,7 @@ int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
     FusedArgs a1 = a;
     a1.dots = nullptr;
     // pass 1: every gather stays inside the block of one up configuration -> the block of x lives in shared memory
-    if (block_smem_applicable(&L, S->Dd)) QB_TRY(launch_spmv_block_smem(&L, a1, S->Dd));
-    else QB_TRY(launch_spmv(&L, a1));
+    QB_TRY(launch_spmv(&L, a1));                            // (block_D set: launch_spmv_sjds takes the block-local kernel when it fits)
     qbgpu_matrix C = *A->second;
     C.api_complex = A->api_complex;                        // a real view of the handle (fp64 vectors) covers both parts
     FusedArgs a2;
@@ -985,6 +1006,47 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
 using namespace qb;
 
 extern "C" {
+
+/* The two parts of a STORED species-order handle or shard as handles of their own (views: they share the arrays, destroy
+ * frees nothing): `local` = diagonal + hops of the down electrons -- its gathers stay inside the handle's own rows, so on a
+ * row shard it needs NO remote data; `cross` = hops of the up electrons, traversed by tiles, gathers from every rank's rows.
+ * A sharded product is then: start the exchange; local part (y = ...); wait for the slices; cross part (y += ...). */
+int qbgpu_species_parts(qbgpu_matrix_t A, qbgpu_matrix_t *local, qbgpu_matrix_t *cross)
+{
+    QB_TRY(ensure_init());
+    if (!A || !local || !cross) return fail(QBGPU_ERR_ARG, "null argument");
+    const Species *S = (const Species *)A->sp;
+    if (!S || S->matfree || !A->second) return fail(QBGPU_ERR_STATE, "species_parts: needs a stored species-order handle");
+    auto *Lv = new qbgpu_matrix(*A);
+    Lv->borrowed = true; Lv->sp = nullptr; Lv->second = nullptr; Lv->perm = nullptr; Lv->perm_inv = nullptr; Lv->perm_x = Lv->perm_y = nullptr;
+    auto *Cv = new qbgpu_matrix(*A->second);
+    Cv->borrowed = true; Cv->api_complex = A->api_complex; Cv->perm_x = Cv->perm_y = nullptr;
+    *local = Lv; *cross = Cv;
+    return QBGPU_OK;
+}
+
+/* For a row range [row_lo, row_hi) of the species order of the Hubbard sector (nsites, N_up, N_dn): ref_rows_dev[p - row_lo] =
+ * the row of the reference's Lin order that has internal index p.  What a rank of a sharded run needs to fill its slice of a
+ * vector that is defined in the reference's order (qbgpu_dist_randomize: the start vector vec_randomize(seed)). */
+int qbgpu_species_ref_rows(int nsites, int nup, int ndn, int64_t row_lo, int64_t row_hi, int32_t *ref_rows_dev)
+{
+    QB_TRY(ensure_init());
+    if (nsites < 2 || nup < 0 || ndn < 0 || nup > nsites || ndn > nsites || !ref_rows_dev) return fail(QBGPU_ERR_ARG, "species_ref_rows: bad argument");
+    HostTables T;
+    QB_TRY(make_tables(nsites, 2, nup, ndn, T));
+    static thread_local ModelParams M;
+    M.kind = 1; M.J = 0; M.t = 0; M.U = 0; M.nbonds = 0;
+    SpeciesHost H;
+    QB_TRY(build_host_tables(nsites, nup, ndn, M, H));
+    const int64_t Dd = (int64_t)H.list[1].size();
+    if (row_lo < 0 || row_hi < row_lo || row_hi > T.dim) return fail(QBGPU_ERR_ARG, "species_ref_rows: bad row range");
+    int32_t *d_rank = nullptr;
+    QB_CUDA(cudaMalloc(&d_rank, sizeof(int32_t) * H.rank.size()));
+    cudaError_t e = cudaMemcpyAsync(d_rank, H.rank.data(), sizeof(int32_t) * H.rank.size(), cudaMemcpyHostToDevice, ctx().stream);
+    int rc = e == cudaSuccess ? species_ref_rows_build(T, d_rank, Dd, row_lo, row_hi, ref_rows_dev) : cuda_fail(e, "upload rank table", __FILE__, __LINE__);
+    cudaFree(d_rank);
+    return rc;
+}
 
 int qbgpu_native_order(qbgpu_matrix_t A, int *has_internal_order)
 {

@@ -341,6 +341,63 @@ class PeerExchangeOperator:
             self.k.lanczos_step_a_part(g, self.X[b], uz, state, False, idx == last - 1)
 
 
+class SpeciesPeerOperator(PeerExchangeOperator):
+    """The sharded product of a STORED species-order Hubbard handle (csrc/species.cu) with the peer-pull exchange: rows are
+    whole up configurations, vectors are in the internal order, and the shard comes as two parts (qbgpu_species_parts):
+
+        local  = diagonal + hops of the down electrons: gathers stay inside the rank's own rows -> needs NO remote data
+        cross  = hops of the up electrons: gathers from every rank's rows
+
+    so one product is: start every pull; local part (y = ...) while the slices travel; wait; cross part (y += ...) -- two
+    kernels, instead of one column block per owner with its own pass over the row metadata and over y.  kernels.parts =
+    [local, cross] (DeviceKernels over the two views)."""
+
+    def __init__(self, qb, kernels, n, rank, world, comm, torch_mod, d_dn, lanes=None, mode=None, ctas=None):
+        global ROW_ALIGN
+        saved = ROW_ALIGN
+        ROW_ALIGN = species_row_align(d_dn)
+        try:
+            super().__init__(qb, kernels, n, rank, world, comm, torch_mod, lanes=lanes, mode=mode, ctas=ctas)
+        finally:
+            ROW_ALIGN = saved
+
+    def configure(self, kernels, groups=None, mode=None, ctas=None, lanes=None, schedule=None):
+        rank, world = self.rank, self.world
+        self.k = kernels
+        self.groups = [(p, p + 1) for p in range(world)]
+        self.own_group = rank
+        # every slice is needed by the cross part; ring order, one reader per source at every step
+        self.order = [(rank + d) % world for d in range(1, world)]
+        self.group_order = list(self.order)
+        self.skipped_blocks = 0
+        self.schedule = "ring (all slices; local part overlaps the pulls)"
+        if mode is not None:
+            self.mode = mode
+        if ctas is not None:
+            self.ctas = ctas
+        if lanes is not None:
+            self.lanes = lanes
+
+    def _wait_all(self):
+        for p in self.order:
+            if self.bounds[p + 1] > self.bounds[p]:
+                assert self.L.qbgpu_peer_wait(p) == 0, self.L.qbgpu_last_error()
+
+    def matvec(self, b, y_local, barrier=True):
+        if barrier:
+            self.comm.all_reduce(self.token)
+        self.pull(b)
+        self.k.multmv_part(0, self.X[b], y_local, accumulate=False)       # local part: own rows only
+        self._wait_all()
+        self.k.multmv_part(1, self.X[b], y_local, accumulate=True)        # cross part
+
+    def lanczos_step_a(self, b, uz, state):
+        self.pull(b)
+        self.k.lanczos_step_a_part(0, self.X[b], uz, state, True, False)
+        self._wait_all()
+        self.k.lanczos_step_a_part(1, self.X[b], uz, state, False, True)
+
+
 def matching_rounds(needs):
     """needs[r][p]: reader r needs the slice of owner p.  Returns rounds; rounds[k][r] = the owner r pulls from in round k
     (or None).  Repeated maximum bipartite matching (Kuhn's augmenting paths, deterministic): for a regular graph every
@@ -491,6 +548,150 @@ class DeviceKernels:
         assert self.L.qbgpu_lanczos_step_c(self._p(state), self._p(a_dev), self._p(b_dev), m) == 0, self.L.qbgpu_last_error()
 
 
+# ----------------------------------------------------------------------------------------------- native drivers
+class NativeDist:
+    """ctypes face of csrc/dist.cu: the multi-GPU Krylov drivers behind the C ABI (qbgpu_dist_*).  One process per GPU; the
+    vector slices and the scalars travel through peer memory (CUDA IPC), nothing in the loops touches NCCL or the host side of
+    torch.distributed -- `exchange` is only used ONCE, to hand the 64-byte handles around (any all-gather of bytes will do:
+    here torch.distributed.all_gather_object; a C++ host would use files, pipes or MPI)."""
+
+    def __init__(self, qb, n, bounds, rank, world, complex_vectors, exchange):
+        self.qb, self.L, self.n, self.rank, self.world = qb, qb.lib(), n, rank, world
+        self.bounds = [int(b) for b in bounds]
+        self.complex = bool(complex_vectors)
+        self.dtype = np.complex128 if self.complex else np.float64
+        self.h = C.c_void_p()
+        b = np.array(self.bounds, dtype=np.int64)
+        self._chk(self.L.qbgpu_dist_create(C.byref(self.h), rank, world, n, b.ctypes.data, int(self.complex)))
+        hb = (C.c_ubyte * 64)()
+        self._chk(self.L.qbgpu_dist_export(self.h, hb))
+        allh = exchange(bytes(hb))
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(allh))
+        self._chk(self.L.qbgpu_dist_connect(self.h, blob))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libqbgpu status {rc}: {self.L.qbgpu_last_error().decode(errors='replace')}")
+
+    @property
+    def nloc(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def own(self, b):
+        p, nl = C.c_void_p(), C.c_int64()
+        self._chk(self.L.qbgpu_dist_own(self.h, b, C.byref(p), C.byref(nl)))
+        return p.value
+
+    def full(self, b):
+        p = C.c_void_p()
+        self._chk(self.L.qbgpu_dist_full(self.h, b, C.byref(p)))
+        return p.value
+
+    def upload_own(self, b, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert arr.size == self.nloc
+        if arr.size:
+            self._chk(self.L.qbgpu_memcpy_h2d(C.c_void_p(self.own(b)), C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+    def download_own(self, b):
+        out = np.empty(self.nloc, dtype=self.dtype)
+        if out.size:
+            self._chk(self.L.qbgpu_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(self.own(b)), out.nbytes))
+        return out
+
+    def barrier(self):
+        self._chk(self.L.qbgpu_dist_barrier(self.h))
+
+    def randomize(self, b, seed, ref_rows_ptr=None):
+        self._chk(self.L.qbgpu_dist_randomize(self.h, b, seed, C.c_void_p(ref_rows_ptr) if ref_rows_ptr else None))
+
+    @staticmethod
+    def _hp(m):
+        return m.handle if m is not None else None
+
+    def mv(self, local, rest, b, y_ptr, barrier=True):
+        self._chk(self.L.qbgpu_dist_mv(self.h, self._hp(local), rest.handle, b, C.c_void_p(y_ptr), int(barrier)))
+
+    def lanczos(self, local, rest, np_, maxit, purpose="sr_val0", stop_on_breakdown=True):
+        hess = np.zeros(2 * maxit)
+        m = C.c_int64(0)
+        self._chk(self.L.qbgpu_dist_lanczos(self.h, self._hp(local), rest.handle, np_, maxit, C.byref(m), C.c_void_p(hess.ctypes.data),
+                                            purpose.encode(), int(stop_on_breakdown)))
+        return int(m.value), hess
+
+    def energy_scale(self, local, rest, extend=0.1, iters=128, ref_rows_ptr=None):
+        lo, hi = C.c_double(), C.c_double()
+        self._chk(self.L.qbgpu_dist_energy_scale(self.h, self._hp(local), rest.handle, C.c_void_p(ref_rows_ptr) if ref_rows_ptr else None,
+                                                 C.byref(lo), C.byref(hi), extend, iters))
+        return lo.value, hi.value
+
+    def kpm_moments(self, local, rest, lo, hi, nmom):
+        mu = np.zeros(nmom)
+        self._chk(self.L.qbgpu_dist_kpm_moments(self.h, self._hp(local), rest.handle, lo, hi, nmom, C.c_void_p(mu.ctypes.data)))
+        return mu
+
+    def eigenvec_cg(self, local, rest, E0, v_ptr, r_ptr, p_ptr, pp_ptr, maxit=1000):
+        m, accu = C.c_int64(0), C.c_double(0.0)
+        e0 = (C.c_double * 2)(float(np.real(E0)), float(np.imag(E0)))
+        self._chk(self.L.qbgpu_dist_eigenvec_cg(self.h, self._hp(local), rest.handle, maxit, C.byref(m), e0, C.byref(accu),
+                                                C.c_void_p(v_ptr), C.c_void_p(r_ptr), C.c_void_p(p_ptr), C.c_void_p(pp_ptr)))
+        return int(m.value), accu.value
+
+    def destroy(self):
+        if self.h:
+            self.L.qbgpu_dist_destroy(self.h)
+            self.h = None
+
+
+def species_order_key(words, nsites):
+    """the order of the configurations of one species in csrc/species.cu (build_host_tables): odd-site bits major"""
+    words = np.asarray(words, dtype=np.int64)
+    odd = np.zeros_like(words)
+    even = np.zeros_like(words)
+    for s_ in range(nsites):
+        bit = (words >> s_) & 1
+        if s_ % 2:
+            odd |= bit << (s_ // 2)
+        else:
+            even |= bit << (s_ // 2)
+    return (odd << nsites) | even
+
+
+def species_nnz_balanced_bounds(nsites, nup, ndn, bonds, world):
+    """Row bounds (multiples of D_dn: whole up configurations) that balance the STORED ENTRIES of the species-order shards:
+    rows of one up configuration u hold D_dn * (1 + h_dn) local entries (the same for every u) plus D_dn * h_up(u) cross
+    entries, h_up(u) = number of hops available to the up electrons in u.  Returns (bounds, D_dn)."""
+    from math import comb
+    allw = np.arange(1 << nsites, dtype=np.int64)
+    pc = np.zeros_like(allw)
+    for s_ in range(nsites):
+        pc += (allw >> s_) & 1
+    ups = allw[pc == nup]
+    ups = ups[np.argsort(species_order_key(ups, nsites), kind="stable")]
+    hops = np.zeros(ups.size, dtype=np.int64)
+    seen = set()
+    for (i, j) in bonds:
+        key = (min(i, j), max(i, j))
+        if key in seen:
+            continue
+        seen.add(key)
+        hops += (((ups >> i) & 1) != ((ups >> j) & 1)).astype(np.int64)
+    dd = comb(nsites, ndn)
+    dns = allw[pc == ndn]
+    hd = 0
+    for (i, j) in seen:
+        hd += int((((dns >> i) & 1) != ((dns >> j) & 1)).sum())
+    w = dd + hd + dd * hops                                  # stored entries of the rows of each up configuration
+    cum = np.concatenate([[0], np.cumsum(w)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world)))
+    cuts.append(ups.size)
+    cuts = [min(max(c, cuts[k - 1] if k else 0), ups.size) for k, c in enumerate(cuts)]
+    return [c * dd for c in cuts], dd
+
+
 def _timed(torch, dist, stream, fn, steps, warmup):
     """warmup + `steps` timed calls bracketed by barrier + synchronize; device time, max over ranks (ms per step)."""
     for _ in range(warmup):
@@ -507,11 +708,145 @@ def _timed(torch, dist, stream, fn, steps, warmup):
     return float(t.item())
 
 
+def bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, ClockSampler):
+    """bench.py's N > 1 arm for the Hubbard workloads: stored species-order shards (whole up configurations, balanced by
+    stored entries), the native drivers of csrc/dist.cu -- peer-memory pulls overlapped with the local part, the push-based
+    all-reduce kernel -- and the Lanczos loop with the reference's stop rule, so that E0 and its time-to-solution are
+    measured at every N.  Strong scaling: the total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    import quantum_basis_b200 as qb
+    from quantum_basis_b200.bench_support import square_bonds
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = qb.lib()
+    stream = torch.cuda.current_stream()
+    fam, p = WORKLOADS[args.workload]
+    ns = p["Lx"] * p["Ly"]
+    bonds = square_bonds(p["Lx"], p["Ly"])
+    n = L.qbgpu_dim_hubbard(ns, p["nup"], p["ndn"])
+    bounds, d_dn = species_nnz_balanced_bounds(ns, p["nup"], p["ndn"], bonds, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    nloc = hi - lo
+    t0 = time.time()
+    M = qb.hubbard(ns, p["nup"], p["ndn"], bonds, p["t"], p["U"], flags=128, rows=(lo, hi))     # complex API handle, real values
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    inf = M.info
+
+    def exchange(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    peak, peak_src = measured_peak()
+    res = {}
+    ref_rows = torch.empty(max(nloc, 1), dtype=torch.int32, device="cuda")
+    assert L.qbgpu_species_ref_rows(ns, p["nup"], p["ndn"], lo, hi, C.c_void_p(ref_rows.data_ptr())) == 0, L.qbgpu_last_error()
+    nnz_all = torch.tensor([inf.nnz_stored], dtype=torch.int64, device="cuda")
+    dist.all_reduce(nnz_all)
+    Z = int(nnz_all.item())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.qbgpu_kernel_launches(1)
+    launches = 0
+    for tag, cplx in (("fp64", False), ("complex128", True)):
+        Mv = M if cplx else M.real_view()
+        loc, cross = Mv.species_parts()
+        D = NativeDist(qb, n, bounds, rank, world, cplx, exchange)
+        D.randomize(0, 1, ref_rows.data_ptr())                       # the reference's start vector vec_randomize(seed 1), this rank's rows
+        y = torch.zeros((2 if cplx else 1) * max(nloc, 1), dtype=torch.float64, device="cuda")
+        ms = _timed(torch, dist, stream, lambda: D.mv(loc, cross, 0, y.data_ptr(), barrier=True), args.steps, args.warmup)
+        launches += int(L.qbgpu_kernel_launches(1))
+        # the parts alone (no exchange): where the time goes
+        one_, zero_ = (C.c_double * 2)(1.0, 0.0), (C.c_double * 2)(0.0, 0.0)
+        if cplx:
+            flocal = lambda: L.qbgpu_zmv(loc.handle, one_, C.c_void_p(D.full(0)), zero_, C.c_void_p(y.data_ptr()), 1)            # noqa: E731
+            fcross = lambda: L.qbgpu_zmv(cross.handle, one_, C.c_void_p(D.full(0)), one_, C.c_void_p(y.data_ptr()), 1)           # noqa: E731
+        else:
+            flocal = lambda: L.qbgpu_dmv(loc.handle, 1.0, C.c_void_p(D.full(0)), 0.0, C.c_void_p(y.data_ptr()), 1)               # noqa: E731
+            fcross = lambda: L.qbgpu_dmv(cross.handle, 1.0, C.c_void_p(D.full(0)), 1.0, C.c_void_p(y.data_ptr()), 1)             # noqa: E731
+        ms_local = _timed(torch, dist, stream, flocal, max(3, args.steps // 2), 2)
+        ms_cross = _timed(torch, dist, stream, fcross, max(3, args.steps // 2), 2)
+        nb_remote = (n - nloc) * (16 if cplx else 8)
+        res[tag] = {"ms_per_product": ms, "products_per_s": 1e3 / ms, "local_part_ms": ms_local, "cross_part_ms": ms_cross,
+                    "exposed_exchange_ms": max(0.0, ms - ms_local - ms_cross), "remote_bytes_pulled_per_rank": nb_remote}
+        if not cplx and not args.no_lanczos:
+            # E0 by the reference's Lanczos with its stop rule, on the shards (fp64: H and the start vector are real)
+            D.randomize(0, 1, ref_rows.data_ptr())
+            torch.cuda.synchronize(); dist.barrier()
+            tl = time.time()
+            m, hess = D.lanczos(loc, cross, 999, 1000, "sr_val0")
+            torch.cuda.synchronize(); dist.barrier()
+            tl = time.time() - tl
+            tmax = torch.tensor([tl], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ritz, _ = qb.hess_eigen(hess, 1000, m)
+            res["lanczos"] = {"vectors": "fp64 (real mode)", "steps": m, "seconds": float(tmax.item()), "iters_per_s": m / float(tmax.item()),
+                              "E0": float(ritz[0]), "stop_rule": "src/lanczos.cc:228-248 on the all-reduced (a, b), identical on every rank",
+                              "a0": float(hess[1000]), "b1": float(hess[1])}
+        if not cplx:
+            # e2e: every rank uploads its slice of x (fp64: the complex API vector has no imaginary part) and downloads its slice of y
+            xh = torch.empty(max(nloc, 1), dtype=torch.float64).pin_memory()
+            yh = torch.empty(max(nloc, 1), dtype=torch.float64).pin_memory()
+            xh[:nloc] = torch.from_numpy(D.download_own(0))
+
+            def e2e_step():
+                assert L.qbgpu_memcpy_h2d(C.c_void_p(D.own(0)), C.c_void_p(xh.data_ptr()), nloc * 8) == 0
+                D.mv(loc, cross, 0, y.data_ptr(), barrier=True)
+                assert L.qbgpu_memcpy_d2h(C.c_void_p(yh.data_ptr()), C.c_void_p(y.data_ptr()), nloc * 8) == 0
+            for _ in range(2):
+                e2e_step()
+            torch.cuda.synchronize(); dist.barrier()
+            te = time.time()
+            ne = max(3, min(args.steps, 10))
+            for _ in range(ne):
+                e2e_step()
+            torch.cuda.synchronize(); dist.barrier()
+            e2e_s = torch.tensor([(time.time() - te) / ne], dtype=torch.float64, device="cuda")
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+            res["e2e_s"] = float(e2e_s.item())
+        D.destroy()
+        loc.destroy(); cross.destroy()
+    clocks = sampler.stop()
+    if rank == 0:
+        ms = res["fp64"]["ms_per_product"]
+        B_local = algorithmic_bytes(inf.nnz_stored, nloc, n, 8, 8)
+        kern_ms = res["fp64"]["local_part_ms"] + res["fp64"]["cross_part_ms"]
+        line = {"metric": "H*v/sec", "value": 1e3 / ms, "unit": "H*v/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "S_val": 8, "S_vec": 8,
+                           "partition": "species-order row shards: whole up configurations, balanced by stored entries (nnz)",
+                           "rows_per_rank": [bounds[q + 1] - bounds[q] for q in range(world)],
+                           "exchange": "peer-memory pulls (CUDA IPC, copy engines, ring order) overlapped with the local part; cross part after the arrival; "
+                                       "device-side push all-reduce kernel as barrier (csrc/dist.cu: no NCCL in the loop)",
+                           "vectors": "x = this rank's rows of vec_randomize(seed 1) in the internal order; fp64: the complex128 vectors of the reference's "
+                                      "calling convention have imag == 0 (what the single-GPU MultMv detects); the complex128 product is reported beside it",
+                           "n1_note": "the 1-GPU line includes the reference-order boundary (permutation in and out, 2.3 ms of its 16.9 ms); shards work in the internal order",
+                           "l2": "inputs larger than L2"},
+                "roofline": {"bound": "hbm", "achieved": B_local / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": B_local / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "local_product_ms": kern_ms,
+                             "note": "per GPU (rank 0's shard): both parts of the local rows' product without the exchange; the exchange is in `value`"},
+                "e2e": {"value": 1.0 / res["e2e_s"], "unit": "H*v/s", "h2d_bytes_per_step": nloc * 8, "d2h_bytes_per_step": nloc * 8,
+                        "ms_per_step": 1e3 * res["e2e_s"], "note": "per rank: its fp64 slice of x up, its slice of y down, pinned host memory"},
+                "products": {k: v for k, v in res.items() if k in ("fp64", "complex128")},
+                "gpu_launches": launches, "clocks": clocks, "host_phases": {"generate_shard_s": t_build}}
+        if "lanczos" in res:
+            line["lanczos"] = res["lanczos"]
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def bench_sharded(args, WORKLOADS, build_matrix, algorithmic_bytes, measured_peak, ClockSampler, workload_upper_nnz):
     """bench.py's N > 1 arm: H row-sharded over the ranks (strong scaling: the total work is fixed).  One product =
     exchange of x + the local rows' product, timed on the device, max over ranks.  Two exchange schemes are timed and the
     faster is the headline: (A) one all_gather then the whole shard, (B) one broadcast per owner overlapped with the
     per-owner column blocks."""
+    if WORKLOADS[args.workload][0] == "hubbard" and not os.environ.get("QB_DIST_LEGACY"):
+        return bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, ClockSampler)
     import torch
     import torch.distributed as dist
     import quantum_basis_b200 as qb

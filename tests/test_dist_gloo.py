@@ -435,3 +435,53 @@ def test_species_row_align():
     assert species_row_align(12870) == 25740 and species_row_align(70) == 140 and species_row_align(924) == 924
     b, chunk = equal_row_bounds(165636900, 8, align=species_row_align(12870))
     assert chunk % 12870 == 0 and b[-1] == 165636900 and all(x % 12870 == 0 for x in b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-side logic of the native multi-GPU path (csrc/dist.cu behind quantum_basis_b200.dist.NativeDist): the shard bounds and
+# the one-off exchange of the IPC handles.  The device side is covered on GPUs by scripts/dist_native_check.py.
+def test_species_nnz_balanced_bounds():
+    import lin_builders as LB
+    import species_builders as SB
+    from quantum_basis_b200 import dist as qd
+    for (Lx, Ly, nu, nd) in ((4, 2, 4, 4), (4, 3, 6, 6), (3, 3, 4, 5)):
+        ns, bonds = Lx * Ly, LB.square_bonds(Lx, Ly)
+        Du, Dd = SB.configurations(ns, nu).size, SB.configurations(ns, nd).size
+        lp, cp = SB.species_parts(ns, nu, nd, bonds) if Du * Dd < 200000 else (None, None)
+        for world in (1, 2, 3, 8):
+            b, dd = qd.species_nnz_balanced_bounds(ns, nu, nd, bonds, world)
+            assert dd == Dd and b[0] == 0 and b[-1] == Du * Dd and len(b) == world + 1
+            assert all(x % Dd == 0 for x in b) and all(b[k] <= b[k + 1] for k in range(world))
+            if lp is not None and world > 1:
+                nnz = (np.diff(lp.indptr) + np.diff(cp.indptr)).astype(np.int64)
+                per = [int(nnz[b[k]:b[k + 1]].sum()) for k in range(world)]
+                # balanced to within the entries of two up configurations
+                assert max(per) - min(per) <= 2 * int(nnz.reshape(Du, Dd).sum(axis=1).max()), (world, per)
+    w = np.arange(1 << 10)
+    assert np.array_equal(qd.species_order_key(w, 10), SB._order_key(w, 10))
+
+
+def _handle_exchange_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    mine = bytes([rank]) * 64                       # stands for the 64-byte CUDA IPC handle of this rank's buffers
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    blob = b"".join(out)
+    q.put((rank, len(blob), [blob[64 * p] for p in range(world)]))
+    dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_over_gloo():
+    """what NativeDist does once at start-up: every rank contributes 64 bytes, every rank receives all of them rank-major"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29641
+    ps = [ctx.Process(target=_handle_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p_ in ps:
+        p_.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p_ in ps:
+        p_.join(timeout=60)
+    assert got == [(0, 128, [0, 1]), (1, 128, [0, 1])]

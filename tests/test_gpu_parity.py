@@ -961,3 +961,39 @@ def test_hubbard4x3_against_the_references_own_run(oracle, kind):
     assert abs(e0 + 16.879382788684) < 1e-9
     k = 20
     assert np.abs(hess[1000:1000 + k] - z["lanczos_a"][:k]).max() < 1e-10 and np.abs(hess[1:k] - z["lanczos_b"][1:k]).max() < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------- native multi-GPU drivers
+def _run_dist_check(nproc):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "scripts", "dist_native_check.py")
+    if nproc == 1:
+        cmd = [sys.executable, script, "4", "3", "6", "6"]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", script, "4", "3", "6", "6"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert res.returncode == 0 and lines, (res.stdout[-1500:], res.stderr[-1500:])
+    import json
+    out = json.loads(lines[-1])
+    assert out["all_ranks_ok"], out
+    return out
+
+
+def test_native_dist_drivers_one_rank():
+    """csrc/dist.cu (qbgpu_dist_*: sharded product, Lanczos with the reference's stop rule, eigenvec_CG, energy_scale, KPM
+    moments) on ONE rank against the single-GPU entry points -- same loops, no peers (scripts/dist_native_check.py)."""
+    out = _run_dist_check(1)
+    assert abs(out["fp64_lanczos"]["E0"] + 16.879382788684) < 1e-9
+
+
+def test_native_dist_drivers_two_ranks():
+    """The same on TWO GPUs: peer-memory pulls, the push all-reduce kernel, E0 equal to the single-GPU run to 1e-10."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    out = _run_dist_check(2)
+    assert abs(out["fp64_lanczos"]["E0"] - out["fp64_lanczos"]["E0_single"]) <= 1e-10 * abs(out["fp64_lanczos"]["E0_single"])

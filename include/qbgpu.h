@@ -405,6 +405,17 @@ int qbgpu_dist_create(qbgpu_dist_t *D, int rank, int world, int64_t n, const int
 int qbgpu_dist_export(qbgpu_dist_t D, void *handle64);
 int qbgpu_dist_connect(qbgpu_dist_t D, const void *handles_world_x_64);
 int qbgpu_dist_destroy(qbgpu_dist_t D);
+/* refinement of a shard: parts that need no remote data (they run while the slices travel) / parts that follow the arrival;
+ * and the row ranges of the peers' slices that are fetched at all (default: every slice, whole) */
+int qbgpu_dist_set_parts(qbgpu_dist_t D, int n_early, const qbgpu_matrix_t *early, int n_late, const qbgpu_matrix_t *late);
+int qbgpu_dist_set_pull_plan(qbgpu_dist_t D, int nseg, const int32_t *owner, const int64_t *first_row, const int64_t *nrows, int lanes);
+/* the cross part of a stored species-order handle or shard cut by column ranges (owning handles, same rows and traversal) */
+int qbgpu_species_split_cross(qbgpu_matrix_t A, int nparts, const int64_t *col_bounds, qbgpu_matrix_t *parts);
+/* a view of a sliced-jagged handle (a part of a species shard) restricted to its local rows [r0, r1): whole 32-row slices, and
+ * for a tile-ordered cross part multiples of tile_period = D_dn; products through it address y / z at the view's rows */
+int qbgpu_row_view(qbgpu_matrix_t A, int64_t r0, int64_t r1, int64_t tile_period, int tile, qbgpu_matrix_t *view);
+/* late part j may start as soon as the first wait_after[j] segments of the pull plan have arrived (default: all of them) */
+int qbgpu_dist_set_wait_points(qbgpu_dist_t D, int n_late, const int32_t *wait_after);
 int qbgpu_dist_own(qbgpu_dist_t D, int b, void **own_slice_dev, int64_t *nloc);   /* this rank's rows of vector buffer b (0 | 1) */
 int qbgpu_dist_full(qbgpu_dist_t D, int b, void **full_vector_dev);
 int qbgpu_dist_barrier(qbgpu_dist_t D);                                            /* stream-ordered, device-side */

@@ -89,6 +89,9 @@ _SIGS = {
     "qbgpu_native_perm": [vp, vp], "qbgpu_species_parts": [vp, C.POINTER(vp), C.POINTER(vp)],
     "qbgpu_dist_create": [C.POINTER(vp), C.c_int, C.c_int, i64, vp, C.c_int], "qbgpu_dist_export": [vp, vp], "qbgpu_dist_connect": [vp, vp],
     "qbgpu_dist_destroy": [vp], "qbgpu_dist_own": [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)], "qbgpu_dist_full": [vp, C.c_int, C.POINTER(vp)],
+    "qbgpu_dist_set_parts": [vp, C.c_int, vp, C.c_int, vp], "qbgpu_dist_set_pull_plan": [vp, C.c_int, vp, vp, vp, C.c_int],
+    "qbgpu_species_split_cross": [vp, C.c_int, vp, vp], "qbgpu_row_view": [vp, i64, i64, i64, C.c_int, C.POINTER(vp)],
+    "qbgpu_dist_set_wait_points": [vp, C.c_int, vp],
     "qbgpu_dist_barrier": [vp], "qbgpu_dist_allreduce": [vp, vp, C.c_int], "qbgpu_dist_randomize": [vp, C.c_int, C.c_uint32, vp],
     "qbgpu_species_ref_rows": [C.c_int, C.c_int, C.c_int, i64, i64, vp],
     "qbgpu_dist_mv": [vp, vp, vp, C.c_int, vp, C.c_int],

@@ -173,8 +173,11 @@ def lanczos_load(dirpath, maxit, dim, dtype, purpose):
     v[(k % 2) * dim:(k % 2 + 1) * dim] = need(f"lanczosV{k}.dat", dim, dt)
     if "val0" not in purpose:
         v[2 * dim:3 * dim] = need("lanczosY0.dat", dim, dt)
-    with open(_p(dirpath, "lczs_mlns.dat"), "rb") as f:
-        b = f.read()
+    try:
+        with open(_p(dirpath, "lczs_mlns.dat"), "rb") as f:
+            b = f.read()
+    except OSError as e:
+        raise QbgpuError(f"checkpoint: lczs_mlns.dat is missing or unreadable ({e})")
     if len(b) != 28:
         raise QbgpuError("checkpoint: lczs_mlns.dat has the wrong size")
     state = [struct.unpack("<i", b[:4])[0], *struct.unpack("<ddd", b[4:])]
@@ -271,6 +274,11 @@ def cg_checkpointed(mat, E0, v, r, p, pp, maxit=1000, every=50, dirpath=DIRNAME,
     while m < maxit:
         stop = min(maxit, m + every)
         m_new, accu = _csr.eigenvec_CG(dim, stop, m, mat, E0, v, r, p, pp)
+        if accu < _csr.lanczos_precision and m_new == stop and stop < maxit:
+            # converged exactly at the chunk boundary: the loop left at m == maxit WITHOUT the reference's closing pass
+            # (src/lanczos.cc:295-317: check |v|, renormalise and restart if | |v| - 1 | > 2e-12), which the uninterrupted
+            # loop would still run -- give it one more step of room so that it runs here too
+            m_new, accu = _csr.eigenvec_CG(dim, stop + 1, m_new, mat, E0, v, r, p, pp)
         done = m_new < stop or accu < _csr.lanczos_precision
         if m_new > m:
             cg_store(dirpath, m_new, v, r, p)

@@ -23,6 +23,7 @@
 #include "internal.hpp"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -53,6 +54,18 @@ struct qbgpu_dist {
     unsigned epoch = 0;
     int *timeout_flag = nullptr;          // device: a waiter gave up
     double *scal = nullptr;               // device scratch (64 doubles)
+    // optional refinement of a shard (qbgpu_dist_set_parts): parts that need no remote data run while the slices travel
+    // (`early`: the local part, and the cross entries whose columns lie in the rank's own rows), the others after the arrival
+    std::vector<qbgpu_matrix_t> early, late;
+    // optional pull plan (qbgpu_dist_set_pull_plan): only these row ranges of the peers' slices are fetched
+    struct Seg { int owner; int64_t first, rows; };
+    std::vector<Seg> plan;
+    bool has_plan = false;
+    int lanes = 1;
+    // optional wait points (qbgpu_dist_set_wait_points): late part j starts once the first wait_after[j] plan segments arrived
+    std::vector<int> wait_after;
+    cudaEvent_t wait_ev[8] = {};
+    bool row_views = false;               // some part covers only a sub-range of the rank's rows: dots are taken in a pass of their own
     int64_t lo() const { return bounds[rank]; }
     int64_t hi() const { return bounds[rank + 1]; }
     int64_t nloc() const { return hi() - lo(); }
@@ -122,22 +135,48 @@ static int dist_allreduce_array(qbgpu_dist *D, double *dev, int64_t count)
     return QBGPU_OK;
 }
 
-// pulls of every peer's slice of X[b] (ring order: at step d every GPU serves exactly one reader); one copy lane
+// pulls of the peers' slices of X[b] -- all of them, or the row ranges of the pull plan -- in ring order (at distance d every
+// GPU serves one reader); `lanes` copy streams (pulls on one lane run back to back).  The pulls are ordered after the point of
+// the compute stream marked by dist_pull_mark(): the caller marks, launches what needs no remote data, and only then spends
+// the host time of enqueueing the transfers.
+static int dist_pull_mark(qbgpu_dist *D) { return D->world > 1 ? peer_mark_fence() : QBGPU_OK; }
 static int dist_pull(qbgpu_dist *D, int b)
 {
+    if (D->has_plan) {
+        const bool wp = !D->wait_after.empty();            // wait points: everything on lane 0, which completes in order
+        int k = 0;
+        auto mark = [&](int done) -> int {
+            for (size_t j = 0; j < D->wait_after.size(); j++) if (D->wait_after[j] == done) QB_TRY(peer_record_on_lane(0, D->wait_ev[j]));
+            return QBGPU_OK;
+        };
+        if (wp) QB_TRY(mark(0));
+        for (const auto &sg : D->plan) {
+            const size_t off = D->off_x[b] + D->esize * (size_t)sg.first;
+            const size_t nb = D->esize * (size_t)sg.rows;
+            if (nb) QB_TRY(peer_pull_fenced(wp ? 0 : sg.owner % D->lanes, sg.owner, D->base + off, D->peers.base[sg.owner] + off, nb));   // one lane per owner: its last event covers all its segments
+            k++;
+            if (wp) QB_TRY(mark(k));
+        }
+        return QBGPU_OK;
+    }
     for (int d = 1; d < D->world; d++) {
         const int p = (D->rank + d) % D->world;
         const size_t off = D->off_x[b] + D->esize * (size_t)D->bounds[p];
         const size_t nb = D->esize * (size_t)(D->bounds[p + 1] - D->bounds[p]);
-        if (nb) QB_TRY(qbgpu_peer_pull_async(0, p, D->base + off, D->peers.base[p] + off, nb));
+        if (nb) QB_TRY(peer_pull_fenced(p % D->lanes, p, D->base + off, D->peers.base[p] + off, nb));
     }
     return QBGPU_OK;
 }
+// order the compute stream behind every pull: the LAST pull recorded per owner slot (a slot's event is re-recorded by
+// every pull from that owner, and pulls on one lane complete in order; with several lanes every owner's last event is waited for)
 static int dist_wait(qbgpu_dist *D)
 {
+    bool seen[kMaxRanks] = {};
+    if (D->has_plan) { for (const auto &sg : D->plan) if (sg.rows) seen[sg.owner] = true; }
+    else for (int p = 0; p < D->world; p++) seen[p] = p != D->rank && D->bounds[p + 1] > D->bounds[p];
     for (int d = 1; d < D->world; d++) {
         const int p = (D->rank + d) % D->world;
-        if (D->bounds[p + 1] > D->bounds[p]) QB_TRY(qbgpu_peer_wait(p));
+        if (seen[p]) QB_TRY(qbgpu_peer_wait(p));
     }
     return QBGPU_OK;
 }
@@ -145,24 +184,99 @@ static int dist_wait(qbgpu_dist *D)
 // y_local = alpha*(H x)_local + gamma*x_local + beta*z_local (+ partial dots) with x = X[b], whose slices are final on every
 // rank (the caller's previous all-reduce was the barrier).  local_part may be null (an ordinary row shard: one product
 // after the arrival); with a species shard the local part opens the product while the slices travel.
-static int dist_product(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, int b, const FusedArgs &args)
+static void dist_sequence(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, std::vector<const qbgpu_matrix *> &seq, size_t &n_early)
 {
-    QB_TRY(dist_pull(D, b));
+    seq.clear(); n_early = 0;
+    if (!D->early.empty() || !D->late.empty()) {
+        for (auto h : D->early) seq.push_back(h);
+        n_early = seq.size();
+        for (auto h : D->late) seq.push_back(h);
+    } else {
+        if (local_part) { seq.push_back(local_part); n_early = 1; }
+        seq.push_back(rest);
+    }
+}
+
+// y / z pointer of a part: a row view addresses the rows it covers
+static inline void *part_rows(const qbgpu_dist *D, const qbgpu_matrix *P, void *base)
+{ return base ? (char *)base + D->esize * (size_t)(P->row_lo - D->lo()) : nullptr; }
+
+// order the compute stream behind the arrival of what late part j needs
+static int dist_wait_for_late(qbgpu_dist *D, size_t j, bool &waited_all)
+{
+    if (!D->wait_after.empty() && j < D->wait_after.size()) {
+        if (D->wait_after[j] > 0 || true) QB_CUDA(cudaStreamWaitEvent(ctx().stream, D->wait_ev[j], 0));
+        return QBGPU_OK;
+    }
+    if (!waited_all) { QB_TRY(dist_wait(D)); waited_all = true; }
+    return QBGPU_OK;
+}
+
+// pulls_issued: the caller has already enqueued the pulls of X[b] (the Lanczos loop does, one step ahead)
+static int dist_product(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, int b, const FusedArgs &args, bool pulls_issued = false)
+{
+    if (!pulls_issued) QB_TRY(dist_pull_mark(D));
     FusedArgs a = args;
     a.x = D->X(b);
-    if (local_part) {
-        FusedArgs a1 = a;
-        a1.dots = nullptr;
-        QB_TRY(launch_spmv(local_part, a1));
-        QB_TRY(dist_wait(D));
-        FusedArgs a2;
-        a2.x = a.x; a2.y = a.y; a2.z = a.y; a2.dots = a.dots;
-        a2.beta = make_double2(1.0, 0.0);
-        if (a.scal_mode != 0) { a2.scal_mode = 2; a2.sc = a.sc; } else a2.alpha = a.alpha;
-        QB_TRY(launch_spmv(rest, a2));
-    } else {
-        QB_TRY(dist_wait(D));
-        QB_TRY(launch_spmv(rest, a));
+    // the parts in execution order: [early ...] wait [late ...]; the first opens the product (alpha, gamma, beta*z), the
+    // others accumulate into the same y, the last carries the running dots (or, with row views, a pass of its own does)
+    std::vector<const qbgpu_matrix *> seq;
+    size_t n_early = 0;
+    dist_sequence(D, local_part, rest, seq, n_early);
+    const bool sep_dots = D->row_views && a.dots;
+    bool pulled = pulls_issued, waited = false;
+    for (size_t i = 0; i < seq.size(); i++) {
+        if (i >= n_early) {
+            if (!pulled) { QB_TRY(dist_pull(D, b)); pulled = true; }
+            QB_TRY(dist_wait_for_late(D, i - n_early, waited));
+        }
+        const bool first = i == 0, last = i + 1 == seq.size();
+        FusedArgs ai;
+        if (first) { ai = a; }
+        else {
+            ai.x = a.x; ai.y = a.y; ai.z = a.y;
+            ai.beta = make_double2(1.0, 0.0);
+            if (a.scal_mode != 0) { ai.scal_mode = 2; ai.sc = a.sc; } else ai.alpha = a.alpha;
+        }
+        ai.y = part_rows(D, seq[i], ai.y);
+        ai.z = part_rows(D, seq[i], const_cast<void *>(ai.z));
+        ai.dots = (last && !sep_dots) ? a.dots : nullptr;
+        QB_TRY(launch_spmv(seq[i], ai));
+        if (i + 1 == n_early && !pulled) { QB_TRY(dist_pull(D, b)); pulled = true; }      // enqueue the transfers while the early parts run
+    }
+    if (!pulled) QB_TRY(dist_pull(D, b));
+    if (!waited) QB_TRY(dist_wait(D));
+    if (sep_dots) {                                         // dots[0..1] = <x_own, y>, dots[2] = |y|^2 over the rank's rows
+        const int64_t nl = D->nloc();
+        if (nl) { QB_TRY(vec_dotc(nl, D->cplx, D->own(b), a.y, a.dots)); QB_TRY(vec_nrm2sq(nl, D->cplx, a.y, a.dots + 2)); }
+        else QB_CUDA(cudaMemsetAsync(a.dots, 0, sizeof(double) * 3, ctx().stream));
+    }
+    return QBGPU_OK;
+}
+
+// Lanczos step a over the same sequence of parts (first: w = sx*H*ux - b*sz*uz; others accumulate; last: the partial <v, w>)
+static int dist_lanczos_step_a(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, int bx, void *uz, double *state, bool pulls_issued)
+{
+    if (!pulls_issued) QB_TRY(dist_pull_mark(D));
+    std::vector<const qbgpu_matrix *> seq;
+    size_t n_early = 0;
+    dist_sequence(D, local_part, rest, seq, n_early);
+    bool pulled = pulls_issued, waited = false;
+    for (size_t i = 0; i < seq.size(); i++) {
+        if (i >= n_early) {
+            if (!pulled) { QB_TRY(dist_pull(D, bx)); pulled = true; }
+            QB_TRY(dist_wait_for_late(D, i - n_early, waited));
+        }
+        const bool last = i + 1 == seq.size() && !D->row_views;
+        QB_TRY(lanczos_step_a(seq[i], D->X(bx), part_rows(D, seq[i], uz), state, i == 0, last));
+        if (i + 1 == n_early && !pulled) { QB_TRY(dist_pull(D, bx)); pulled = true; }
+    }
+    if (!pulled) QB_TRY(dist_pull(D, bx));
+    if (!waited) QB_TRY(dist_wait(D));
+    if (D->row_views) {                                     // state[3] = sx * Re <ux_own, w> over the rank's rows, in a pass of its own
+        const int64_t nl = D->nloc();
+        if (nl) QB_TRY(vec_dotc_scaled(nl, D->cplx, D->own(bx), uz, state + 3, state + 0));
+        else QB_CUDA(cudaMemsetAsync(state + 3, 0, sizeof(double), ctx().stream));
     }
     return QBGPU_OK;
 }
@@ -265,7 +379,64 @@ int qbgpu_dist_destroy(qbgpu_dist_t D)
     cudaDeviceSynchronize();
     for (int p = 0; p < D->world; p++) if (p != D->rank && D->peers.base[p]) cudaIpcCloseMemHandle(D->peers.base[p]);
     cudaFree(D->base); cudaFree(D->timeout_flag); cudaFree(D->scal);
+    for (auto &e : D->wait_ev) if (e) cudaEventDestroy(e);
     delete D;
+    return QBGPU_OK;
+}
+
+/* Refine the shard: `early` parts need no remote data (the local part; the cross entries whose columns are the rank's own rows)
+ * and run while the slices travel, `late` parts follow the arrival.  Together they must hold exactly the shard's entries (the
+ * loops then ignore the decomposition passed per call).  n_early = n_late = 0 clears the refinement. */
+int qbgpu_dist_set_parts(qbgpu_dist_t D, int n_early, const qbgpu_matrix_t *early, int n_late, const qbgpu_matrix_t *late)
+{
+    if (!D || n_early < 0 || n_late < 0 || (n_early && !early) || (n_late && !late)) return fail(QBGPU_ERR_ARG, "dist_set_parts: bad argument");
+    D->early.clear(); D->late.clear();
+    for (int i = 0; i < n_early + n_late; i++) {
+        qbgpu_matrix_t h = i < n_early ? early[i] : late[i - n_early];
+        if (!h || h->n != D->n || h->row_lo < D->lo() || h->row_hi > D->hi() || h->row_lo > h->row_hi || h->api_complex != D->cplx)
+        { D->early.clear(); D->late.clear(); D->row_views = false; return fail(QBGPU_ERR_ARG, "dist_set_parts: a part does not match this rank's rows / vector type"); }
+        if (i == 0 && (h->row_lo != D->lo() || h->row_hi != D->hi()))
+        { D->early.clear(); D->late.clear(); D->row_views = false; return fail(QBGPU_ERR_ARG, "dist_set_parts: the first part opens the product and must cover all of the rank's rows"); }
+        (i < n_early ? D->early : D->late).push_back(h);
+    }
+    D->row_views = false;
+    for (auto h : D->early) D->row_views = D->row_views || h->row_lo != D->lo() || h->row_hi != D->hi();
+    for (auto h : D->late) D->row_views = D->row_views || h->row_lo != D->lo() || h->row_hi != D->hi();
+    D->wait_after.clear();
+    return QBGPU_OK;
+}
+
+/* Fetch only these row ranges of the peers' slices (rows [first[k], first[k] + rows[k]) lie inside owner[k]'s rows): what the
+ * late parts actually reference.  nseg = 0 with a null list restores "every slice, whole".  lanes: copy streams in use (1..8). */
+int qbgpu_dist_set_pull_plan(qbgpu_dist_t D, int nseg, const int32_t *owner, const int64_t *first, const int64_t *rows, int lanes)
+{
+    if (!D || nseg < 0 || (nseg && (!owner || !first || !rows))) return fail(QBGPU_ERR_ARG, "dist_set_pull_plan: bad argument");
+    D->plan.clear();
+    D->has_plan = owner != nullptr;
+    D->lanes = lanes < 1 ? 1 : (lanes > 8 ? 8 : lanes);
+    for (int k = 0; k < nseg; k++) {
+        const int p = owner[k];
+        if (p < 0 || p >= D->world || p == D->rank || first[k] < D->bounds[p] || rows[k] < 0 || first[k] + rows[k] > D->bounds[p + 1])
+        { D->plan.clear(); D->has_plan = false; return fail(QBGPU_ERR_ARG, "dist_set_pull_plan: a segment does not lie inside its owner's rows"); }
+        D->plan.push_back({p, first[k], rows[k]});
+    }
+    return QBGPU_OK;
+}
+
+/* Late part j may start as soon as the first wait_after[j] segments of the pull plan have arrived (non-decreasing, the last one
+ * = the number of segments).  Needs a pull plan; the transfers then all use one copy lane (they complete in order). */
+int qbgpu_dist_set_wait_points(qbgpu_dist_t D, int n_late, const int32_t *wait_after)
+{
+    if (!D || n_late < 0 || (n_late && !wait_after)) return fail(QBGPU_ERR_ARG, "dist_set_wait_points: bad argument");
+    D->wait_after.clear();
+    if (n_late == 0) return QBGPU_OK;
+    if (!D->has_plan || n_late != (int)D->late.size() || n_late > 8) return fail(QBGPU_ERR_STATE, "dist_set_wait_points: needs a pull plan and one entry per late part (at most 8)");
+    for (int j = 0; j < n_late; j++) {
+        if (wait_after[j] < 0 || wait_after[j] > (int)D->plan.size() || (j && wait_after[j] < wait_after[j - 1])) return fail(QBGPU_ERR_ARG, "dist_set_wait_points: must be non-decreasing and within the plan");
+        if (!D->wait_ev[j]) QB_CUDA(cudaEventCreateWithFlags(&D->wait_ev[j], cudaEventDisableTiming));
+    }
+    if (wait_after[n_late - 1] != (int)D->plan.size()) return fail(QBGPU_ERR_ARG, "dist_set_wait_points: the last late part must wait for the whole plan");
+    D->wait_after.assign(wait_after, wait_after + n_late);
     return QBGPU_OK;
 }
 
@@ -371,29 +542,39 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
     int cnt_accuE0 = 0;
     double theta0_prev = 0.0;
     int64_t m = 0;
+    // QBGPU_VERBOSE: device time of the phases of a step (events on the compute stream) and host time between the steps
+    const bool prof = getenv("QBGPU_VERBOSE") != nullptr;
+    cudaEvent_t pe[6] = {};
+    double tph[5] = {0, 0, 0, 0, 0};
+    if (prof) for (auto &e : pe) cudaEventCreate(&e);
+    auto rec = [&](int i) { if (prof) cudaEventRecord(pe[i], c.stream); };
     while (m < np) {
         m++;
         const int bx = (int)((m - 1) % 2), bz = (int)(m % 2);
         void *uz = D->own(bz);
         // step a: w = sx*H*ux - b*sz*uz into uz; state[3] = partial <v, w>
-        QB_TRY(dist_pull(D, bx));
-        if (local_part) {
-            if (int rc = lanczos_step_a(local_part, D->X(bx), uz, state, true, false)) return done(rc);
-            if (int rc = dist_wait(D)) return done(rc);
-            if (int rc = lanczos_step_a(rest, D->X(bx), uz, state, false, true)) return done(rc);
-        } else {
-            if (int rc = dist_wait(D)) return done(rc);
-            if (int rc = lanczos_step_a(rest, D->X(bx), uz, state, true, true)) return done(rc);
-        }
+        rec(0);
+        if (int rc = dist_lanczos_step_a(D, local_part, rest, bx, uz, state, /*pulls_issued=*/m > 1)) return done(rc);
+        rec(1);
         if (int rc = dist_allreduce(D, state + 3, 1)) return done(rc);
+        rec(2);
         if (int rc = lanczos_step_b(nloc, cplx, D->own(bx), uz, state)) return done(rc);
+        rec(3);
         if (int rc = dist_allreduce(D, state + 6, 1)) return done(rc);      // also the barrier that makes X[bz] final everywhere
+        rec(4);
+        // the slices of the NEXT step's vector (unnormalised: its scale travels as a scalar) are final now: start fetching
+        // them before the host reads the coefficients back and decides whether there is a next step (if not: harmless)
+        if (m < np) { if (int rc = dist_pull_mark(D)) return done(rc); if (int rc = dist_pull(D, bz)) return done(rc); }
         if (int rc = lanczos_step_c(state, a_dev, b_dev, m)) return done(rc);
         cudaMemcpyAsync(c.scal_host, a_dev + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, c.stream);
         cudaMemcpyAsync(c.scal_host + 1, b_dev + m, sizeof(double), cudaMemcpyDeviceToHost, c.stream);
         if (cudaStreamSynchronize(c.stream) != cudaSuccess) return done(cuda_fail(cudaGetLastError(), "dist_lanczos: step", __FILE__, __LINE__));
         hess[maxit + m - 1] = c.scal_host[0];
         hess[m] = c.scal_host[1];
+        if (prof) {
+            cudaEventRecord(pe[5], c.stream); cudaEventSynchronize(pe[5]);
+            for (int i = 0; i < 5; i++) { float f = 0; cudaEventElapsedTime(&f, pe[i], pe[i + 1]); tph[i] += f; }
+        }
         if (m == 1) continue;
         if (stop_on_breakdown && fabs(hess[m]) < kLanczosPrecisionD) break;                        // src/lanczos.cc:216
         if (is_val) {                                                                              // :228-248
@@ -411,6 +592,12 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
         }
     }
     *m_out = m;
+    if (prof) {
+        if (D->rank == 0) fprintf(stderr, "[qbgpu dist_lanczos] %lld steps on %d ranks, device ms per step: product %.3f | all-reduce %.3f | update pass %.3f | all-reduce %.3f | scalars+readback %.3f\n",
+                                  (long long)m, D->world, tph[0] / m, tph[1] / m, tph[2] / m, tph[3] / m, tph[4] / m);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
+    if (int rc = dist_wait(D)) return done(rc);             // (a fetch started for a step that did not happen)
     // hand the two live vectors back normalised (their scales live in state[0], state[1])
     if (nloc) {
         if (int rc = scale_copy(nloc, cplx, state + 0, 1.0, D->own((int)(m % 2)), D->own((int)(m % 2)))) return done(rc);

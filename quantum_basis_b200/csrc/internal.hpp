@@ -52,12 +52,16 @@ struct qbgpu_matrix {
     // > 0: rows [u*block_D, (u+1)*block_D) reference only columns of the same block (the local part of a species handle):
     // the product may stage the block of x in shared memory (sjds_bulk.cu: sjds_block_smem_kernel)
     int64_t  block_D = 0;
+    bool     owns_order = false;       // a row view (qbgpu_row_view) shares every array but owns its slice_order
     // column part of a matrix-free species shard (qbgpu_split_columns): only the up-hops whose target configuration lies in
     // [sp_col_lo, sp_col_hi) (units: up configurations), plus the whole local pass when sp_has_local; -1 = no filter
     int64_t  sp_col_lo = -1, sp_col_hi = -1;
     bool     sp_has_local = true;
     void    *perm_x = nullptr, *perm_y = nullptr;      // staging vectors of the reference-order product of a species handle, or of
                                                        // the opt-in fp64 product of an ordinary one (lazily allocated; freed by destroy)
+    // the device whose context first multiplied with this handle (the creating thread's): a product issued from a thread
+    // bound to ANOTHER device (the context is thread-local) is refused instead of running on the wrong device or stream
+    mutable int device = -1;
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
@@ -101,6 +105,9 @@ int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view);     // sjds.cu
 int peer_ring_flags(const int **flags, int **timeout_flag);                 // peer.cu: arrival flags by ring distance
+int peer_mark_fence();                                                      // peer.cu: pulls enqueued later are ordered after THIS point of the compute stream
+int peer_pull_fenced(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes);
+int peer_record_on_lane(int lane, cudaEvent_t ev);                          // peer.cu: an event behind everything enqueued on that copy lane so far
 // species.cu
 int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &args);      // the two-pass products of species-order handles
 void species_destroy(qbgpu_matrix *A);
@@ -116,6 +123,7 @@ inline int no_species(const qbgpu_matrix *A, const char *what)
 { return (A && A->sp) ? fail(QBGPU_ERR_STATE, std::string(what) + ": not available for species-order handles") : QBGPU_OK; }
 // matrix.cu
 int alloc_matrix_arrays(qbgpu_matrix *A);
+int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matrix_t *out, int flags);   // owning part handles by column range
 // expand a device-resident reference-format CSR (int64 row_start/row_end/col, offsets from 0) into a new handle
 int create_from_device_csr(qbgpu_matrix_t *out, int64_t n, const int64_t *d_rs, const int64_t *d_re, const int64_t *d_col,
                            const void *d_val, bool val_complex, int64_t nnz_input, int sym, int flags, bool api_complex);

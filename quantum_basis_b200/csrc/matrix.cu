@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kCBlock) split_copy_kernel(int64_t nloc, const
     }
 }
 
-static int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matrix_t *out, int flags)
+int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matrix_t *out, int flags)
 {
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -476,6 +476,7 @@ int qbgpu_destroy(qbgpu_matrix_t A)
     if (!A->borrowed) { matfree_destroy(A); species_destroy(A); }
     if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); cudaFree(A->slice_order);
                         cudaFree(A->perm_x); cudaFree(A->perm_y); }
+    else if (A->owns_order) cudaFree(A->slice_order);
     delete A;
     return QBGPU_OK;
 }

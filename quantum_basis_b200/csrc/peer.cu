@@ -66,6 +66,33 @@ static int peer_init()
     return QBGPU_OK;
 }
 
+// Two-step form of qbgpu_peer_pull_async for callers that want to launch kernels BETWEEN the point the pulls are ordered after
+// and the (host-side) enqueueing of the pulls: peer_mark_fence() records that point on the compute stream, peer_pull_fenced()
+// enqueues a pull ordered after it -- not after whatever was launched on the compute stream since (csrc/dist.cu: the part of
+// the product that needs no remote data is launched first and runs while the host is still enqueueing the transfers).
+int peer_mark_fence()
+{
+    QB_TRY(peer_init());
+    QB_CUDA(cudaEventRecord(g_peer.fence, ctx().stream));
+    return QBGPU_OK;
+}
+int peer_pull_fenced(int lane, int slot, void *dst_local, const void *src_peer, size_t bytes)
+{
+    if (lane < 0 || lane >= kPeerLanes || slot < 0 || slot >= kPeerLanes || !dst_local || !src_peer) return fail(QBGPU_ERR_ARG, "peer_pull: bad argument");
+    QB_CUDA(cudaStreamWaitEvent(g_peer.lane[lane], g_peer.fence, 0));
+    QB_CUDA(cudaMemcpyAsync(dst_local, src_peer, bytes, cudaMemcpyDefault, g_peer.lane[lane]));
+    QB_CUDA(cudaEventRecord(g_peer.arrived[slot], g_peer.lane[lane]));
+    return QBGPU_OK;
+}
+
+int peer_record_on_lane(int lane, cudaEvent_t ev)
+{
+    QB_TRY(peer_init());
+    if (lane < 0 || lane >= kPeerLanes) return fail(QBGPU_ERR_ARG, "peer_record_on_lane: bad lane");
+    QB_CUDA(cudaEventRecord(ev, g_peer.lane[lane]));
+    return QBGPU_OK;
+}
+
 int peer_ring_flags(const int **flags, int **timeout_flag)
 {
     QB_TRY(peer_init());

@@ -591,8 +591,12 @@ static int launch_block_smem_cfg(const qbgpu_matrix *A, const FusedArgs &a, int6
     const size_t smem = ((size_t)D * sizeof(VecT) + 127) / 128 * 128;
     static size_t smem_set = 0;
     if (smem_set < smem) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
-    int bps = 0;
-    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, smem));
+    static int bps = 0;
+    static size_t bps_smem = 0;
+    if (bps == 0 || bps_smem != smem) {                     // (per instantiation; the block size of a handle never changes)
+        QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, smem));
+        bps_smem = smem;
+    }
     if (bps < 1) return fail(QBGPU_ERR_STATE, "block-local product: the block does not fit in shared memory");
     const int64_t u_lo = A->row_lo / D, u_cnt = A->nrows() / D;
     if (u_cnt == 0) return QBGPU_OK;

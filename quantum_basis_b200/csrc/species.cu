@@ -1025,6 +1025,66 @@ int qbgpu_species_parts(qbgpu_matrix_t A, qbgpu_matrix_t *local, qbgpu_matrix_t 
     return QBGPU_OK;
 }
 
+/* The CROSS part of a stored species-order handle or shard cut by column ranges: parts[p] holds the entries with columns in
+ * [bounds[p], bounds[p+1]) (bounds[0] = 0, bounds[nparts] = n; owning handles with the same rows, the same tile-ordered
+ * traversal and the sliced-jagged layout).  On a row shard the part whose columns are the shard's own rows needs no remote
+ * data: about 60 % of the cross entries of BASELINE config 3 on eight ranks (qbgpu_dist_set_parts). */
+int qbgpu_species_split_cross(qbgpu_matrix_t A, int nparts, const int64_t *bounds, qbgpu_matrix_t *parts)
+{
+    QB_TRY(ensure_init());
+    if (!A || !bounds || !parts || nparts < 1) return fail(QBGPU_ERR_ARG, "species_split_cross: bad argument");
+    const Species *S = (const Species *)A->sp;
+    if (!S || S->matfree || !A->second || A->borrowed) return fail(QBGPU_ERR_STATE, "species_split_cross: needs the owning stored species-order handle");
+    qbgpu_matrix *Cx = A->second;
+    if (Cx->ndict) return fail(QBGPU_ERR_STATE, "species_split_cross: not available with dictionary-coded values");
+    QB_TRY(split_columns(Cx, nparts, bounds, parts, QBGPU_FORMAT_SELL | QBGPU_NO_AUTOTUNE));
+    const int64_t ns = (Cx->nrows() + 31) / 32;
+    for (int p = 0; p < nparts; p++) {
+        parts[p]->api_complex = A->api_complex;
+        if (ns > 0) {
+            cudaError_t e = cudaMalloc(&parts[p]->slice_order, sizeof(int32_t) * (size_t)ns);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(parts[p]->slice_order, Cx->slice_order, sizeof(int32_t) * (size_t)ns, cudaMemcpyDeviceToDevice, ctx().stream);
+            if (e != cudaSuccess) { for (int q = 0; q < nparts; q++) { qbgpu_destroy(parts[q]); parts[q] = nullptr; } return cuda_fail(e, "copy of the slice order", __FILE__, __LINE__); }
+        }
+    }
+    QB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QBGPU_OK;
+}
+
+/* A view of a sliced-jagged handle restricted to its local rows [r0, r1) (both multiples of 32; for a tile-ordered cross part
+ * also multiples of tile_period = D_dn, so that the view's first row is the first down configuration again): same arrays, its
+ * own traversal order.  Products through the view read and write y / z at the VIEW's rows (the caller offsets the pointers by
+ * r0 entries, or uses the multi-GPU drivers, which do).  A late part cut by rows lets the first half start as soon as ITS
+ * slices have arrived (qbgpu_dist_set_pull_plan: wait points). */
+int qbgpu_row_view(qbgpu_matrix_t A, int64_t r0, int64_t r1, int64_t tile_period, int tile, qbgpu_matrix_t *view)
+{
+    QB_TRY(ensure_init());
+    if (!A || !view) return fail(QBGPU_ERR_ARG, "null argument");
+    *view = nullptr;
+    if (A->sp || A->mf || A->format != QBGPU_FORMAT_SELL) return fail(QBGPU_ERR_STATE, "row_view: needs a stored sliced-jagged handle (a part of a species handle, a shard)");
+    const int64_t nl = A->nrows();
+    if (r0 < 0 || r1 < r0 || r1 > nl || r0 % 32 != 0 || (r1 % 32 != 0 && r1 != nl)) return fail(QBGPU_ERR_ARG, "row_view: the row range must consist of whole 32-row slices");
+    if (A->slice_order && (tile_period <= 0 || r0 % tile_period != 0)) return fail(QBGPU_ERR_ARG, "row_view: a tile-ordered part must be cut at multiples of its tile period (D_dn)");
+    auto *V = new qbgpu_matrix(*A);
+    V->borrowed = true; V->owns_order = false;
+    V->perm_x = V->perm_y = nullptr;
+    V->row_lo = A->row_lo + r0; V->row_hi = A->row_lo + r1;
+    V->rowptr = A->rowptr + r0;
+    V->rowinfo = A->rowinfo + r0;
+    V->nnz = 0; V->nnz_input = 0;
+    if (A->slice_order) {
+        std::vector<int32_t> order;
+        make_slice_order(r1 - r0, tile_period, tile < 32 ? 64 : tile, order);
+        V->slice_order = nullptr;
+        cudaError_t e = upload(&V->slice_order, order.data(), order.size(), ctx().stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+        if (e != cudaSuccess) { cudaFree(V->slice_order); delete V; return cuda_fail(e, "row_view: slice order", __FILE__, __LINE__); }
+        V->owns_order = true;
+    }
+    *view = V;
+    return QBGPU_OK;
+}
+
 /* For a row range [row_lo, row_hi) of the species order of the Hubbard sector (nsites, N_up, N_dn): ref_rows_dev[p - row_lo] =
  * the row of the reference's Lin order that has internal index p.  What a rank of a sharded run needs to fill its slice of a
  * vector that is defined in the reference's order (qbgpu_dist_randomize: the start vector vec_randomize(seed)). */

@@ -692,6 +692,196 @@ def species_nnz_balanced_bounds(nsites, nup, ndn, bonds, world):
     return [c * dd for c in cuts], dd
 
 
+def _species_up_configs(nsites, nup):
+    allw = np.arange(1 << nsites, dtype=np.int64)
+    pc = np.zeros_like(allw)
+    for s_ in range(nsites):
+        pc += (allw >> s_) & 1
+    ups = allw[pc == nup]
+    ups = ups[np.argsort(species_order_key(ups, nsites), kind="stable")]
+    rank_of = np.full(1 << nsites, -1, dtype=np.int64)
+    rank_of[ups] = np.arange(ups.size)
+    return ups, rank_of
+
+
+def species_needed_mask(nsites, nup, bonds, u_lo, u_hi, own=None):
+    """need[u'] = the up-hops of the configurations [u_lo, u_hi) reach configuration u' (those inside `own` = (lo, hi) excluded)"""
+    ups, rank_of = _species_up_configs(nsites, nup)
+    mine = ups[u_lo:u_hi]
+    need = np.zeros(ups.size, dtype=bool)
+    seen = set()
+    for (i, j) in bonds:
+        key = (min(i, j), max(i, j))
+        if key in seen:
+            continue
+        seen.add(key)
+        act = mine[((mine >> i) & 1) != ((mine >> j) & 1)]
+        need[rank_of[act ^ ((1 << i) | (1 << j))]] = True
+    o = own if own is not None else (u_lo, u_hi)
+    need[o[0]:o[1]] = False
+    return need
+
+
+def _mask_to_segments(need, world_bounds_u, dd, me, gap):
+    """(owner, first_row, nrows) per run of needed configurations (runs closer than `gap` merged, never across owners), ring order"""
+    world = len(world_bounds_u) - 1
+    segs = []
+    covered = np.zeros(need.size, dtype=bool)
+    for p in range(world):
+        a, b = world_bounds_u[p], world_bounds_u[p + 1]
+        idx = np.nonzero(need[a:b])[0] + a
+        if idx.size == 0:
+            continue
+        breaks = np.nonzero(np.diff(idx) - 1 > gap)[0]
+        starts = np.concatenate([[idx[0]], idx[breaks + 1]])
+        ends = np.concatenate([idx[breaks], [idx[-1]]])
+        for s0, e0 in zip(starts, ends):
+            segs.append((p, int(s0) * dd, int(e0 - s0 + 1) * dd))
+            covered[s0:e0 + 1] = True
+    segs.sort(key=lambda t: ((t[0] - me) % world, t[1]))
+    return segs, covered
+
+
+def species_needed_rows(nsites, nup, ndn, bonds, u_lo, u_hi, world_bounds_u, gap=8, row_cuts=None):
+    """Row ranges of the OTHER ranks' slices that the cross part of the shard [u_lo, u_hi) (units: up configurations) references:
+    the targets of the up-hops of its configurations.  Neighbouring targets closer than `gap` configurations are fetched as one
+    range (fewer transfers).  Returns (segments, wait_after): segments = [(owner, first_row, nrows)] ordered by ring distance
+    from the shard's rank; with row_cuts = [u_lo, c1, ..., u_hi] the segments the rows [u_lo, c1) need come first, then what
+    [c1, c2) needs in addition, ..., and wait_after[j] = number of segments that must have arrived before row block j starts."""
+    from math import comb
+    dd = comb(nsites, ndn)
+    world = len(world_bounds_u) - 1
+    me = next((r for r in range(world) if world_bounds_u[r] <= u_lo < world_bounds_u[r + 1]), 0) if u_hi > u_lo else 0
+    cuts = row_cuts if row_cuts else [u_lo, u_hi]
+    segs, wait_after = [], []
+    have = None
+    for k in range(len(cuts) - 1):
+        need = species_needed_mask(nsites, nup, bonds, cuts[k], cuts[k + 1], own=(u_lo, u_hi))
+        if have is not None:
+            need &= ~have
+        sg, cov = _mask_to_segments(need, world_bounds_u, dd, me, gap)
+        have = cov if have is None else (have | cov)
+        segs += sg
+        wait_after.append(len(segs))
+    return segs, wait_after
+
+
+class SpeciesShard:
+    """A stored species-order row shard prepared for the native drivers (csrc/dist.cu).  Ways to run it (`install`):
+
+      plain_whole_slices   local part while every peer's whole slice travels, then the cross part
+      plain_needed_rows    the same, fetching only the row ranges the cross part references
+      rows<k>_needed_rows  the cross part cut into k row blocks: block j starts as soon as the ranges ITS rows reference have
+                           arrived (they are fetched first), so most of the cross part overlaps the rest of the exchange
+      refined_needed_rows  the cross entries whose columns are the rank's own rows run with the local part (no remote data),
+                           the others after the arrival (costs a second pass over the row metadata)"""
+
+    def __init__(self, qb, M, nsites, nup, ndn, bonds, bounds, rank, world, real, gap=8):
+        from math import comb
+        self.qb, self.L = qb, qb.lib()
+        self.args = (nsites, nup, ndn, bonds)
+        self.bounds, self.rank, self.world, self.gap, self.real, self.M = bounds, rank, world, gap, real, M
+        self.n, self.lo, self.hi = M.info.n, bounds[rank], bounds[rank + 1]
+        self.dd = comb(nsites, ndn)
+        self.tile = 64
+        self.view = M.real_view() if real else M
+        self.local, self.cross = self.view.species_parts()
+        self._owned, self._views = [], []
+        self._split = None
+        self.ub = [x // self.dd for x in bounds]
+        self.plans = {}
+        self.installed = ([self.local], [self.cross])
+        self.plan = []
+
+    def _plan(self, cuts=None):
+        key = tuple(cuts) if cuts else None
+        if key not in self.plans:
+            ns, nu, nd, bonds = self.args
+            self.plans[key] = (species_needed_rows(ns, nu, nd, bonds, self.lo // self.dd, self.hi // self.dd, self.ub, gap=self.gap, row_cuts=cuts)
+                               if self.world > 1 else ([], [0] * (len(cuts) - 1 if cuts else 1)))
+        return self.plans[key]
+
+    def _refined(self):
+        if self._split is None:
+            cuts = sorted({0, self.lo, self.hi, self.n})
+            b = np.array(cuts, dtype=np.int64)
+            hs = (C.c_void_p * (len(cuts) - 1))()
+            rc = self.L.qbgpu_species_split_cross(self.M.handle, len(cuts) - 1, b.ctypes.data, hs)
+            assert rc == 0, self.L.qbgpu_last_error()
+            owned = [self.qb.csr_mat._adopt(C.c_void_p(hs[k]), True) for k in range(len(cuts) - 1)]
+            self._owned += owned
+            parts = [(cuts[k], cuts[k + 1], (p_.real_view() if self.real else p_)) for k, p_ in enumerate(owned)]
+            self._views += [p_[2] for p_ in parts if self.real]
+            early = [self.local] + [p_ for (a, b_, p_) in parts if a == self.lo and b_ == self.hi]
+            late = [p_ for (a, b_, p_) in parts if not (a == self.lo and b_ == self.hi) and p_.info.nnz_stored > 0]
+            self.own_cross_fraction = sum(p_.info.nnz_stored for p_ in early[1:]) / max(1, self.cross.info.nnz_stored)
+            self._split = (early, late)
+        return self._split
+
+    def _row_blocks(self, k):
+        """the cross part cut into k row blocks at multiples of lcm(32, D_dn) rows; returns (views, cuts in up configurations)"""
+        from math import gcd
+        step_u = 32 // gcd(32, self.dd)                     # up configurations per lcm(32, D_dn) rows
+        u_lo, u_hi = self.lo // self.dd, self.hi // self.dd
+        cuts = [u_lo]
+        for j in range(1, k):
+            c = u_lo + ((u_hi - u_lo) * j // k) // step_u * step_u
+            if c > cuts[-1]:
+                cuts.append(c)
+        cuts.append(u_hi)
+        views = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            h = C.c_void_p()
+            rc = self.L.qbgpu_row_view(self.cross.handle, (a - u_lo) * self.dd, (b - u_lo) * self.dd, self.dd, self.tile, C.byref(h))
+            assert rc == 0, self.L.qbgpu_last_error()
+            views.append(self.qb.csr_mat._adopt(h, not self.real))
+        self._views += views
+        return views, cuts
+
+    def install(self, D, mode="plain_needed_rows", lanes=1):
+        none = (None, None, None)
+        cuts = None
+        if mode == "plain_whole_slices" or mode == "plain_needed_rows":
+            early, late = [self.local], [self.cross]
+        elif mode == "refined_needed_rows":
+            early, late = self._refined()
+        elif mode.startswith("rows") and mode.endswith("_needed_rows"):
+            views, cuts = self._row_blocks(int(mode[4:-12]))
+            early, late = [self.local], views
+        else:
+            raise ValueError(mode)
+        ne, nl = len(early), len(late)
+        ea = (C.c_void_p * max(ne, 1))(*[p_.handle for p_ in early])
+        la = (C.c_void_p * max(nl, 1))(*[p_.handle for p_ in late])
+        D._chk(self.L.qbgpu_dist_set_parts(D.h, ne, ea, nl, la))
+        self.installed = (early, late)
+        if mode == "plain_whole_slices" or D.world == 1:
+            D._chk(self.L.qbgpu_dist_set_pull_plan(D.h, 0, *none, lanes))
+            self.plan = []
+            return
+        plan, wait_after = self._plan(cuts)
+        self.plan = plan
+        ow = np.array([t[0] for t in plan] or [0], dtype=np.int32)
+        fi = np.array([t[1] for t in plan] or [0], dtype=np.int64)
+        nr = np.array([t[2] for t in plan] or [0], dtype=np.int64)
+        D._chk(self.L.qbgpu_dist_set_pull_plan(D.h, len(plan), ow.ctypes.data, fi.ctypes.data, nr.ctypes.data, lanes))
+        if cuts is not None and nl > 1:
+            wa = np.array(wait_after, dtype=np.int32)
+            D._chk(self.L.qbgpu_dist_set_wait_points(D.h, nl, wa.ctypes.data))
+
+    @property
+    def pulled_rows(self):
+        return sum(t[2] for t in self.plan) if self.plan else (self.n - (self.hi - self.lo) if self.world > 1 else 0)
+
+    def destroy(self):
+        for v_ in self._views + [self.local, self.cross]:
+            v_.destroy()
+        if self.real:
+            self.view.destroy()
+        for p_ in self._owned:
+            p_.destroy()
+
+
 def _timed(torch, dist, stream, fn, steps, warmup):
     """warmup + `steps` timed calls bracketed by barrier + synchronize; device time, max over ranks (ms per step)."""
     for _ in range(warmup):
@@ -752,28 +942,51 @@ def bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, Clo
     L.qbgpu_kernel_launches(1)
     launches = 0
     for tag, cplx in (("fp64", False), ("complex128", True)):
-        Mv = M if cplx else M.real_view()
-        loc, cross = Mv.species_parts()
+        shard = SpeciesShard(qb, M, ns, p["nup"], p["ndn"], bonds, bounds, rank, world, real=not cplx)
+        loc, cross = shard.local, shard.cross
         D = NativeDist(qb, n, bounds, rank, world, cplx, exchange)
+        lanes = int(os.environ.get("QB_DIST_LANES", "1"))
         D.randomize(0, 1, ref_rows.data_ptr())                       # the reference's start vector vec_randomize(seed 1), this rank's rows
         y = torch.zeros((2 if cplx else 1) * max(nloc, 1), dtype=torch.float64, device="cuda")
+        # three ways to run the same shard; the fastest (max over ranks) is the headline and serves the Lanczos leg
+        modes = (["plain_whole_slices", "plain_needed_rows", "rows2_needed_rows", "rows3_needed_rows", "rows4_needed_rows", "refined_needed_rows"]
+                 if world > 1 else ["plain_whole_slices"])
+        if os.environ.get("QB_DIST_MODES"):
+            modes = os.environ["QB_DIST_MODES"].split(",")
+        tv = {}
+        for vname in modes:
+            shard.install(D, vname, lanes=lanes)
+            D.barrier()
+            tv[vname] = _timed(torch, dist, stream, lambda: D.mv(loc, cross, 0, y.data_ptr(), barrier=True), max(5, args.steps // 2), 3)
+        best = min(tv, key=tv.get)
+        shard.install(D, best, lanes=lanes)
         ms = _timed(torch, dist, stream, lambda: D.mv(loc, cross, 0, y.data_ptr(), barrier=True), args.steps, args.warmup)
         launches += int(L.qbgpu_kernel_launches(1))
         # the parts alone (no exchange): where the time goes
         one_, zero_ = (C.c_double * 2)(1.0, 0.0), (C.c_double * 2)(0.0, 0.0)
-        if cplx:
-            flocal = lambda: L.qbgpu_zmv(loc.handle, one_, C.c_void_p(D.full(0)), zero_, C.c_void_p(y.data_ptr()), 1)            # noqa: E731
-            fcross = lambda: L.qbgpu_zmv(cross.handle, one_, C.c_void_p(D.full(0)), one_, C.c_void_p(y.data_ptr()), 1)           # noqa: E731
-        else:
-            flocal = lambda: L.qbgpu_dmv(loc.handle, 1.0, C.c_void_p(D.full(0)), 0.0, C.c_void_p(y.data_ptr()), 1)               # noqa: E731
-            fcross = lambda: L.qbgpu_dmv(cross.handle, 1.0, C.c_void_p(D.full(0)), 1.0, C.c_void_p(y.data_ptr()), 1)             # noqa: E731
-        ms_local = _timed(torch, dist, stream, flocal, max(3, args.steps // 2), 2)
-        ms_cross = _timed(torch, dist, stream, fcross, max(3, args.steps // 2), 2)
-        nb_remote = (n - nloc) * (16 if cplx else 8)
-        res[tag] = {"ms_per_product": ms, "products_per_s": 1e3 / ms, "local_part_ms": ms_local, "cross_part_ms": ms_cross,
-                    "exposed_exchange_ms": max(0.0, ms - ms_local - ms_cross), "remote_bytes_pulled_per_rank": nb_remote}
+
+        def run_parts(parts, first_opens):
+            for k_, pt in enumerate(parts):
+                beta = 0.0 if (first_opens and k_ == 0) else 1.0
+                yp = y.data_ptr() + (pt.info.row_lo - lo) * (16 if cplx else 8)           # a row view addresses its own rows
+                if cplx:
+                    L.qbgpu_zmv(pt.handle, one_, C.c_void_p(D.full(0)), (C.c_double * 2)(beta, 0.0), C.c_void_p(yp), 1)
+                else:
+                    L.qbgpu_dmv(pt.handle, 1.0, C.c_void_p(D.full(0)), beta, C.c_void_p(yp), 1)
+        early_, late_ = shard.installed
+        ms_early = _timed(torch, dist, stream, lambda: run_parts(early_, True), max(3, args.steps // 2), 2)
+        ms_late = _timed(torch, dist, stream, lambda: run_parts(late_, False), max(3, args.steps // 2), 2) if late_ else 0.0
+        ms_local, ms_cross = ms_early, ms_late
+        esz = 16 if cplx else 8
+        res[tag] = {"ms_per_product": ms, "products_per_s": 1e3 / ms, "early_parts_ms": ms_early, "late_parts_ms": ms_late,
+                    "exposed_exchange_ms": max(0.0, ms - ms_early - ms_late), "decomposition": best, "decompositions_ms": tv,
+                    "remote_bytes_pulled_rank0": shard.pulled_rows * esz,
+                    "remote_bytes_if_whole_slices_rank0": (n - nloc) * esz, "pull_segments_rank0": len(shard.plan),
+                    "parts": "early (no remote data: local part + cross entries with own columns) | late (the other cross entries)"}
         if not cplx and not args.no_lanczos:
             # E0 by the reference's Lanczos with its stop rule, on the shards (fp64: H and the start vector are real)
+            D.randomize(0, 1, ref_rows.data_ptr())
+            D.lanczos(loc, cross, 6, 1000, "sr_val0")                # warm-up: every kernel of the loop has been loaded and launched once
             D.randomize(0, 1, ref_rows.data_ptr())
             torch.cuda.synchronize(); dist.barrier()
             tl = time.time()
@@ -785,6 +998,7 @@ def bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, Clo
             ritz, _ = qb.hess_eigen(hess, 1000, m)
             res["lanczos"] = {"vectors": "fp64 (real mode)", "steps": m, "seconds": float(tmax.item()), "iters_per_s": m / float(tmax.item()),
                               "E0": float(ritz[0]), "stop_rule": "src/lanczos.cc:228-248 on the all-reduced (a, b), identical on every rank",
+                              "timing": "start vector to converged E0, wall clock, max over ranks, after a 6-step warm-up run (kernels loaded)",
                               "a0": float(hess[1000]), "b1": float(hess[1])}
         if not cplx:
             # e2e: every rank uploads its slice of x (fp64: the complex API vector has no imaginary part) and downloads its slice of y
@@ -808,18 +1022,19 @@ def bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, Clo
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
             res["e2e_s"] = float(e2e_s.item())
         D.destroy()
-        loc.destroy(); cross.destroy()
+        shard.destroy()
     clocks = sampler.stop()
     if rank == 0:
         ms = res["fp64"]["ms_per_product"]
         B_local = algorithmic_bytes(inf.nnz_stored, nloc, n, 8, 8)
-        kern_ms = res["fp64"]["local_part_ms"] + res["fp64"]["cross_part_ms"]
+        kern_ms = res["fp64"]["early_parts_ms"] + res["fp64"]["late_parts_ms"]
         line = {"metric": "H*v/sec", "value": 1e3 / ms, "unit": "H*v/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "dim": n, "stored_entries": Z, "S_val": 8, "S_vec": 8,
                            "partition": "species-order row shards: whole up configurations, balanced by stored entries (nnz)",
                            "rows_per_rank": [bounds[q + 1] - bounds[q] for q in range(world)],
-                           "exchange": "peer-memory pulls (CUDA IPC, copy engines, ring order) overlapped with the local part; cross part after the arrival; "
+                           "exchange": "peer-memory pulls (CUDA IPC, copy engines, ring order) of the row ranges the late parts reference only, overlapped with the "
+                                       "parts that need no remote data (local part + cross entries with own columns); the other cross entries after the arrival; "
                                        "device-side push all-reduce kernel as barrier (csrc/dist.cu: no NCCL in the loop)",
                            "vectors": "x = this rank's rows of vec_randomize(seed 1) in the internal order; fp64: the complex128 vectors of the reference's "
                                       "calling convention have imag == 0 (what the single-GPU MultMv detects); the complex128 product is reported beside it",

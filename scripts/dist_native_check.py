@@ -74,9 +74,13 @@ def main():
     assert L.qbgpu_species_ref_rows(ns, nup, ndn, lo, hi, C.c_void_p(ref_rows.data_ptr())) == 0, L.qbgpu_last_error()
     M = qb.hubbard(ns, nup, ndn, bonds, 1.0, 1.1, flags=128, rows=(lo, hi))
     for tag, cplx in (("fp64", False), ("complex", True)):
-        Mv = M if cplx else M.real_view()
-        loc, cross = Mv.species_parts()
+        # refined shard (early / late parts, pull plan) unless QB_DIST_PLAIN=1: then the plain (local, cross) decomposition
+        shard = qd.SpeciesShard(qb, M, ns, nup, ndn, bonds, bounds, rank, world, real=not cplx, gap=2)
+        loc, cross = shard.local, shard.cross
         D = qd.NativeDist(qb, n, bounds, rank, world, cplx, exchange)
+        mode = os.environ.get("QB_DIST_MODE", "rows2_needed_rows" if cplx else "refined_needed_rows")
+        shard.install(D, mode, lanes=int(os.environ.get("QB_DIST_LANES", "1")))
+        out[f"{tag}_shard"] = {"mode": mode, "early": len(shard.installed[0]), "late": len(shard.installed[1]), "segments": len(shard.plan)}
         D.randomize(0, 1, ref_rows.data_ptr())
         got = D.download_own(0)
         check(f"{tag}_start_vector", np.abs(got - (x_int[lo:hi] if cplx else x_int[lo:hi].real)).max() <= 1e-15, "rows of vec_randomize(1) in the internal order")
@@ -113,7 +117,7 @@ def main():
             dist.all_reduce(part)
         res, nrm = float(part[0].sqrt().item()), float(part[1].sqrt().item())
         check(f"{tag}_eigenvec_cg", accu < 2e-12 and res < 1e-9 and abs(nrm - 1.0) < 1e-10, {"steps": mc, "accuracy": accu, "residual": res, "norm": nrm})
-        D.destroy(); loc.destroy(); cross.destroy()
+        D.destroy(); shard.destroy()
     M.destroy(); full.destroy()
 
     # ------------------------------------------------------------------ an ordinary row shard (reference order, no local part)

@@ -45,10 +45,11 @@ WORKLOADS = {
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
-# the species step (profiles/r02_mv_reference_order_launches.csv): way in 7.24 + 1.32, pass 1 40.35 + 1.30, pass 2 39.31 + 1.31, way out 2.28 + 2.60 GB
-TRAFFIC_NCU_SPECIES = {"hubbard4x4": 95714000000}
-KERNEL_SHARES_SPECIES = {"hubbard4x4": {"to_native_real_check_kernel": 0.081, "sjds_block_smem_kernel": 0.435, "spmv_sjds_bulk_kernel": 0.429, "from_native_kernel": 0.054,
-                                        "source": "profiles/r02_mv_reference_order_launches.csv (ncu gpu__time_duration.sum: 1.37 / 7.31 / 7.20 / 0.91 ms)"}}
+# the species step (profiles/r02_mv_reference_order_fused_out_launches.csv): way in 3.43 + 1.36, pass 1 40.43 + 1.31,
+# pass 2 (writes the reference's order itself) 40.34 + 2.85 GB
+TRAFFIC_NCU_SPECIES = {"hubbard4x4": 89720000000}
+KERNEL_SHARES_SPECIES = {"hubbard4x4": {"to_native_tiled_kernel": 0.057, "sjds_block_smem_kernel": 0.476, "spmv_sjds_bulk_kernel": 0.466,
+                                        "source": "profiles/r02_mv_reference_order_fused_out_launches.csv (ncu gpu__time_duration.sum: 0.95 / 7.94 / 7.77 ms)"}}
 TRAFFIC_NCU = {"hubbard4x4": 133686405000,     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
                "tri31_k10": 13300097712,       # profiles/r01_ncu_full_spmv_sjds_tri31_k10_details.csv: 13.14 GB read + 0.158 GB write
                "heis_chain32_k0": 8834161656}  # profiles/r01_ncu_full_spmv_sjds_heis_chain32_k0_details.csv: 8.53 GB read + 0.302 GB write
@@ -603,7 +604,7 @@ def main():
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels in the committed ncu capture (profiles/), not measured in this run",
                          "algorithmic_bytes": B, "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0,
                          "kernel": ("kron_local_kernel + kron_cross_kernel" if args.layout == "species-matfree" else
-                                    "one step = to_native_real_check_kernel + sjds_block_smem_kernel<double,double> (pass 1) + spmv_sjds_bulk_kernel<double,double> (pass 2, UBLKCP) + from_native_kernel"
+                                    "one step = to_native_tiled_kernel (way in, checks imag == 0) + sjds_block_smem_kernel<double,double> (pass 1) + spmv_sjds_bulk_kernel<double,double,..,OUT> (pass 2, UBLKCP; writes y in the reference's order)"
                                     if args.layout == "species" else "spmv_sjds_kernel<double,double2>" if inf.format == 8 else "spmv_csr_vector_kernel"),
                          "kernel_shares_ncu": (KERNEL_SHARES_SPECIES.get(args.workload) if args.layout == "species" else None)},
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,

@@ -81,6 +81,16 @@ struct FusedArgs {
     int         scal_mode = 0;
     const double *sc = nullptr;    // device scalars for scal_mode != 0
     double     *dots = nullptr;    // device: out[0]=Re sum conj(x)y, out[1]=Im, out[2]=sum|y|^2 ; null = no dots
+    // species handles, real-content route of MultMv (species.cu: mv_species): the way in fused into pass 1.  When x_ref is set,
+    // x (fp64, internal order) is an OUTPUT of the block-local kernel: it stages the block from the complex vector in the
+    // reference's order through perm_inv, writes it to x for pass 2, and raises *imag_flag if an imaginary part is not zero.
+    const void *x_ref = nullptr;
+    const int32_t *perm_inv = nullptr;
+    int        *imag_flag = nullptr;
+    // the way OUT fused into the closing pass (fp64 vectors, y += H_cross x): instead of y[row] the bulk-streamed kernel writes
+    // y_ref[perm_inv[row]] = out_alpha * (y, 0) -- complex, in the reference's order -- and the separate permutation is skipped
+    void       *y_ref = nullptr;
+    double2     out_alpha = {1.0, 0.0};
 };
 
 // spmv.cu
@@ -95,8 +105,10 @@ void set_sjds_variant(int v);
 int launch_spmv_sjds_bulk(const qbgpu_matrix *A, const FusedArgs &args);
 int sjds_bulk_mode();
 bool sjds_bulk_wanted(const qbgpu_matrix *A);
+bool sjds_bulk_out_fusable(const qbgpu_matrix *cross_part);      // the closing pass of this part can write the reference-order result itself
 void set_sjds_bulk_mode(int m);
 bool block_smem_applicable(const qbgpu_matrix *A, int64_t D);
+bool sjds_block_variant_ok();
 int launch_spmv_block_smem(const qbgpu_matrix *A, const FusedArgs &args, int64_t D);
 void set_block_smem_variant(int v);
 int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &args);     // builders.cu

@@ -441,7 +441,8 @@ int launch_spmv_sjds(const qbgpu_matrix *A, const FusedArgs &a)
     // tile-ordered cross parts (and, on request, every handle): the matrix stream through cp.async.bulk + mbarrier rings
     // (sjds_bulk.cu); QBGPU_SJDS_BULK=0 or a tuning variant of the register-fed kernel selects the kernels below
     if (A->block_D > 0 && !a.dots && A->ring_world <= 1 && g_sjds_variant == 0 && block_smem_applicable(A, A->block_D)) return launch_spmv_block_smem(A, a, A->block_D);
-    if (A->ring_world <= 1 && g_sjds_variant == 0 && sjds_bulk_wanted(A)) return launch_spmv_sjds_bulk(A, a);
+    if (A->ring_world <= 1 && (g_sjds_variant == 0 || a.y_ref) && sjds_bulk_wanted(A)) return launch_spmv_sjds_bulk(A, a);
+    if (a.y_ref) return fail(QBGPU_ERR_STATE, "fused way out: only the bulk-streamed kernel writes the reference's order (internal)");
     if (A->ring_world > 1) {
         if (A->ndict) return A->api_complex ? launch_sjds_ring_typed<uint8_t, double2>(A, a) : launch_sjds_ring_typed<uint8_t, double>(A, a);
         if (!A->api_complex) return launch_sjds_ring_typed<double, double>(A, a);

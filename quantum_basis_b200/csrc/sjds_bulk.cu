@@ -106,19 +106,28 @@ template <typename VecT> struct SegState {
     int cnt;              // entries (0: nothing was copied, nothing to wait for)
     bool last, live, full; // last segment of its slice; this lane writes a row in the epilogue; every lane has all KSEG diagonals
     int64_t row;
+    int32_t rref;         // OUT: the reference's row of this lane's row (perm_inv), requested together with the gathers
     VecT zv, xi;          // epilogue operands, requested together with the gathers
 };
 
 // PIPE: two segments are in the consumer at a time -- the gathers of segment j+1 are issued before the products of
 // segment j are accumulated (ping-pong register sets), so a warp always has up to 2*KSEG gathers in flight.
-template <typename ValT, typename VecT, bool DOTS, bool KEEP, bool ORD, int NW, int NST, int KSEG, int MINB, bool PIPE>
+__device__ __forceinline__ double real_of(double v) { return v; }
+__device__ __forceinline__ double real_of(double2 v) { return v.x; }
+
+// OUT: the way out of a species handle fused into this (closing, accumulating) pass: y_ref[perm_inv[row]] = out_alpha * (y, 0)
+// instead of y[row] = y (fp64 vectors only; see FusedArgs::y_ref).  The rows of a tile that share a sector of y_ref are
+// closed within microseconds of each other (neighbouring up configurations of the same tile), so L2 merges the halves.
+template <typename ValT, typename VecT, bool DOTS, bool KEEP, bool ORD, int NW, int NST, int KSEG, int MINB, bool PIPE, bool OUT = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int64_t *__restrict__ rowptr,
                       const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                       const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                       int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
-                      const double *__restrict__ vdict, const int32_t *__restrict__ order)
+                      const double *__restrict__ vdict, const int32_t *__restrict__ order,
+                      const int32_t *__restrict__ perm_inv = nullptr, double2 *y_ref = nullptr, double2 out_alpha = {1.0, 0.0})
 {
+    static_assert(!OUT || (sizeof(VecT) == 8 && !DOTS), "the fused way out serves the fp64 closing pass");
     using VT = VecTraits<VecT>;
     using ST = BulkStage<ValT, KSEG>;
     using Seg = SegState<VecT>;
@@ -238,7 +247,7 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
         g.last = g.k0 + KSEG >= maxlen;
         g.full = g.k0 + KSEG <= minlen;
         g.row = (int64_t)s * 32 + (g.info >> 24);
-        g.live = g.last && g.row < nrows && !(KEEP && len == 0);      // padding ranks of the last slice point past the last row
+        g.live = g.last && g.row < nrows && !(KEEP && !OUT && len == 0);      // padding ranks of the last slice point past the last row
         if (g.cnt > 0) {
             mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
             phases ^= 1u << st;
@@ -259,6 +268,7 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
         if (g.live) {
             if (use_beta) g.zv = z[g.row];
             if (use_gamma || DOTS) g.xi = x[row_lo + g.row];
+            if constexpr (OUT) g.rref = perm_inv[row_lo + g.row];
         }
     };
 
@@ -298,7 +308,10 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
             VecT out = VT::scale(s_scal[0], acc);
             if (use_gamma) out = VT::add(out, VT::scale(s_scal[1], g.xi));
             if (use_beta) out = VT::add(out, VT::scale(s_scal[2], g.zv));
-            y[g.row] = out;
+            if constexpr (OUT) {
+                const double re = real_of(out);
+                y_ref[g.rref] = make_double2(out_alpha.x * re, out_alpha.y * re);
+            } else y[g.row] = out;
             if (DOTS) {
                 const double2 p = VT::conj_mul(g.xi, out);
                 d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
@@ -364,12 +377,20 @@ bool sjds_bulk_wanted(const qbgpu_matrix *A)
     return m < 10 ? true : A->slice_order != nullptr;
 }
 
-template <typename ValT, typename VecT, bool DOTS, bool KEEP, bool ORD, int NW, int NST, int KSEG, int MINB, bool PIPE>
+// may the closing pass over this (cross) part write the reference-order result itself?  (environment QBGPU_FUSE_WAY_OUT=0: no)
+bool sjds_bulk_out_fusable(const qbgpu_matrix *A)
+{
+    static int allow = -1;
+    if (allow < 0) { const char *e = getenv("QBGPU_FUSE_WAY_OUT"); allow = e ? atoi(e) != 0 : 1; }
+    return allow && A && A->format == QBGPU_FORMAT_SELL && A->slice_order && A->ring_world <= 1 && sjds_bulk_mode() >= 10;
+}
+
+template <typename ValT, typename VecT, bool DOTS, bool KEEP, bool ORD, int NW, int NST, int KSEG, int MINB, bool PIPE, bool OUT = false>
 static int launch_bulk_cfg(const qbgpu_matrix *A, const FusedArgs &a)
 {
     Context &c = ctx();
     using ST = BulkStage<ValT, KSEG>;
-    auto kern = spmv_sjds_bulk_kernel<ValT, VecT, DOTS, KEEP, ORD, NW, NST, KSEG, MINB, PIPE>;
+    auto kern = spmv_sjds_bulk_kernel<ValT, VecT, DOTS, KEEP, ORD, NW, NST, KSEG, MINB, PIPE, OUT>;
     constexpr size_t smem = 64 * NW + (size_t)NW * NST * ST::BYTES;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
@@ -387,7 +408,8 @@ static int launch_bulk_cfg(const qbgpu_matrix *A, const FusedArgs &a)
     const int grid = (int)(want < cap ? want : cap);
     kern<<<grid, NW * 32, smem, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                             (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
-                                            a.scal_mode, a.sc, a.dots, c.partials, c.ticket, A->vdict, A->slice_order);
+                                            a.scal_mode, a.sc, a.dots, c.partials, c.ticket, A->vdict, A->slice_order,
+                                            OUT ? a.perm_inv : nullptr, OUT ? (double2 *)a.y_ref : nullptr, a.out_alpha);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
@@ -423,6 +445,12 @@ static int launch_bulk_typed(const qbgpu_matrix *A, const FusedArgs &a, int mode
 {
     const bool dots = a.dots != nullptr;
     const bool keep = !dots && a.scal_mode == 0 && a.z == a.y && a.beta.x == 1.0 && a.beta.y == 0.0 && a.gamma.x == 0.0 && a.gamma.y == 0.0;
+    if (a.y_ref) {                                          // the closing pass of a species product writes the reference's order
+        if constexpr (sizeof(VecT) == 8) {
+            if (keep && A->slice_order && a.perm_inv) return launch_bulk_cfg<ValT, VecT, false, true, true, 8, 4, 8, 2, true, true>(A, a);
+        }
+        return fail(QBGPU_ERR_STATE, "fused way out: not the closing pass of a species handle (internal)");
+    }
     if (A->slice_order) {
         if (keep) return launch_bulk_mode<ValT, VecT, false, true, true>(A, a, mode);
         return dots ? launch_bulk_mode<ValT, VecT, true, false, true>(A, a, mode) : launch_bulk_mode<ValT, VecT, false, false, true>(A, a, mode);
@@ -450,12 +478,14 @@ __global__ void __launch_bounds__(NT, MINB)
 sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, int64_t u_cnt, const int64_t *__restrict__ rowptr,
                        const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                        const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
-                       int scal_mode, const double *__restrict__ sc, const double *__restrict__ vdict, int use_bulk)
+                       int scal_mode, const double *__restrict__ sc, const double *__restrict__ vdict, int use_bulk,
+                       const double2 *__restrict__ x_ref, const int32_t *__restrict__ perm_inv, VecT *x_out, int *imag_flag)
 {
     using VT = VecTraits<VecT>;
     constexpr bool kDict = sizeof(ValT) == 1;
     using ArithT = typename std::conditional<kDict, double, ValT>::type;
     constexpr int NWARP = NT / 32;
+    bool any_imag = false;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sdict[kDict ? 256 : 1];
     __shared__ __align__(8) unsigned long long xbar_storage;
@@ -487,18 +517,43 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
         const int64_t c0 = (u_lo + ub) * D;                 // first column (= first global row) of the block
         const int64_t r0 = c0 - row_lo, r1 = r0 + D;        // local rows of the block
         __syncthreads();                                    // every warp has finished reading the previous block from xs
-        if (use_bulk) {
+        bool x_ready = true, staged = false;
+        if constexpr (sizeof(VecT) == 8) {
+            if (x_ref) {
+                // the way in, fused: this block of the internal order gathered from the complex vector in the reference's order
+                // (the rows of one odd-site label are a rectangle here: the neighbouring blocks read the other halves of the same
+                // sectors at about the same time, so L2 serves them); kept for pass 2 in x_out; loads of four rounds first
+                constexpr int R = 4;
+                for (int64_t j0 = threadIdx.x; j0 < D; j0 += (int64_t)R * NT) {
+                    int32_t r[R];
+                    double2 v[R];
+#pragma unroll
+                    for (int u = 0; u < R; u++) { const int64_t j = j0 + (int64_t)u * NT; if (j < D) r[u] = perm_inv[c0 + j]; }
+#pragma unroll
+                    for (int u = 0; u < R; u++) { const int64_t j = j0 + (int64_t)u * NT; if (j < D) v[u] = ldx_plain(x_ref + r[u]); }
+#pragma unroll
+                    for (int u = 0; u < R; u++) {
+                        const int64_t j = j0 + (int64_t)u * NT;
+                        if (j < D) { xs[j] = v[u].x; x_out[c0 + j] = v[u].x; any_imag = any_imag || (v[u].y != 0.0); }
+                    }
+                }
+                __syncthreads();
+                staged = true;
+            }
+        }
+        if (staged) {
+        } else if (use_bulk) {
             if (threadIdx.x == 0) {
                 fence_proxy_async_smem();
                 const uint32_t bytes = (uint32_t)(D * (int64_t)sizeof(VecT));
                 mbar_expect_tx(xbar, bytes);
                 bulk_g2s_plain(smem_u32(xs), x + c0, bytes, xbar);
             }
+            x_ready = false;
         } else {
             for (int64_t j = threadIdx.x; j < D; j += NT) xs[j] = x[c0 + j];
             __syncthreads();
         }
-        bool x_ready = !use_bulk;
         const int64_t s_last = last_slice(ub);
         for (int64_t s = first_slice(ub); s <= s_last; s += NWARP) {
             if (pref_s != s) { info_n = rowinfo[s * 32 + lane]; base_n = rowptr[s * 32]; }      // (first slice of the kernel, or a skipped block)
@@ -578,6 +633,7 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
         }
         if (!x_ready) { mbar_wait(xbar, xphase); xphase ^= 1u; }                           // (a warp without any slice in this block)
     }
+    if (any_imag && imag_flag) *(volatile int *)imag_flag = 1;
 }
 
 static int g_block_smem_variant = -1;
@@ -603,9 +659,11 @@ static int launch_block_smem_cfg(const qbgpu_matrix *A, const FusedArgs &a, int6
     const int64_t cap = (int64_t)c.num_sms * bps;
     const int grid = (int)(u_cnt < cap ? u_cnt : cap);
     const int use_bulk = ((D * (int64_t)sizeof(VecT)) % 16 == 0 && D * (int64_t)sizeof(VecT) < (1 << 20)) ? 1 : 0;
+    const bool fuse_in = a.x_ref != nullptr && sizeof(VecT) == 8;      // (the caller only sets x_ref for fp64 vectors)
     kern<<<grid, NT, smem, c.stream>>>(A->nrows(), A->row_lo, D, u_lo, u_cnt, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                        (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc,
-                                       A->vdict, use_bulk);
+                                       A->vdict, use_bulk, fuse_in ? (const double2 *)a.x_ref : nullptr, a.perm_inv,
+                                       fuse_in ? (VecT *)const_cast<void *>(a.x) : nullptr, a.imag_flag);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;
@@ -643,6 +701,8 @@ bool block_smem_applicable(const qbgpu_matrix *A, int64_t D)
     if (max_kb > 220) max_kb = 220;
     return (size_t)D * A->vec_bytes() <= max_kb * 1024;
 }
+
+bool sjds_block_variant_ok() { return g_block_smem_variant != 0; }
 
 int launch_spmv_block_smem(const qbgpu_matrix *A, const FusedArgs &a, int64_t D)
 {

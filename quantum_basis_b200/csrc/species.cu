@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(kPBlock) invert_perm_kernel(int64_t n, const i
         perm_inv[perm[r]] = (int32_t)r;
 }
 
+__global__ void tile_descriptor_kernel(int64_t nblk, const int64_t *__restrict__ blk_start, int32_t Dd, const int32_t *__restrict__ perm, int4 *desc);
+
 static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Device-resident tables of a species-order handle (owned through qbgpu_matrix::sp).
@@ -74,6 +76,9 @@ struct Species {
     double *diagk = nullptr;                      // [33]  U added k times
     double amp_uni = 0.0;                         // != 0: every bond has the same multiplicity and this is its amplitude
     int tile = 64;                                // W: down indices per tile of the cross pass (multiple of 32)
+    int64_t *blk_start = nullptr;                 // [nblk + 1] first row (reference order) of every non-empty odd-site label
+    int4 *blk_desc = nullptr;                     // [nblk] the rectangle of the internal order a block maps to: (iu0, id0, Cd, rows)
+    int64_t nblk = 0, blk_max_rows = 0;
     bool matfree = false;
     int64_t bytes = 0;
 };
@@ -192,7 +197,7 @@ static void species_free(Species *S)
 {
     if (!S) return;
     cudaFree(S->ulist); cudaFree(S->dlist); cudaFree(S->uptr); cudaFree(S->dptr); cudaFree(S->uhop); cudaFree(S->dhop);
-    cudaFree(S->ampw); cudaFree(S->diagk);
+    cudaFree(S->ampw); cudaFree(S->diagk); cudaFree(S->blk_start); cudaFree(S->blk_desc);
     delete S;
 }
 
@@ -252,6 +257,18 @@ static int species_common(qbgpu_matrix **out, const HostTables &T, const ModelPa
         if (rc) { cudaFree(d_rank); qbgpu_destroy(A); return rc; }
         QB_CU(cudaMalloc(&A->perm_inv, sizeof(int32_t) * (size_t)T.dim));
         invert_perm_kernel<<<grid_rows(T.dim), kPBlock, 0, c.stream>>>(T.dim, A->perm, A->perm_inv);
+        QB_LAUNCH_COUNT();
+        // the non-empty blocks of the reference's order (rows of one odd-site label): the tiles of the way in
+        std::vector<int64_t> blk;
+        int64_t max_rows = 0;
+        for (size_t b = 0; b + 1 < T.Jb.size(); b++)
+            if (T.Jb[b + 1] > T.Jb[b]) { blk.push_back(T.Jb[b]); max_rows = std::max(max_rows, T.Jb[b + 1] - T.Jb[b]); }
+        blk.push_back(T.dim);
+        S->nblk = (int64_t)blk.size() - 1;
+        S->blk_max_rows = max_rows;
+        QB_CU(upload(&S->blk_start, blk.data(), blk.size(), c.stream));
+        QB_CU(cudaMalloc(&S->blk_desc, sizeof(int4) * (size_t)(S->nblk ? S->nblk : 1)));
+        tile_descriptor_kernel<<<(int)std::min<int64_t>(S->nblk > 0 ? S->nblk : 1, 148 * 8), kPBlock, 0, c.stream>>>(S->nblk, S->blk_start, (int32_t)Dd, A->perm, S->blk_desc);
         QB_LAUNCH_COUNT();
     }
     QB_CU(cudaStreamSynchronize(c.stream));
@@ -806,7 +823,8 @@ int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
     qbgpu_matrix L = *A;                                    // plain views: the production kernels see two ordinary matrices
     L.sp = nullptr; L.second = nullptr; L.perm = nullptr; L.perm_inv = nullptr;
     FusedArgs a1 = a;
-    a1.dots = nullptr;
+    a1.dots = nullptr;                                      // (a1 keeps x_ref / perm_inv / imag_flag: the fused way in belongs to pass 1)
+    a1.y_ref = nullptr;                                     // (... and the fused way out to pass 2)
     // pass 1: every gather stays inside the block of one up configuration -> the block of x lives in shared memory
     QB_TRY(launch_spmv(&L, a1));                            // (block_D set: launch_spmv_sjds takes the block-local kernel when it fits)
     qbgpu_matrix C = *A->second;
@@ -816,6 +834,7 @@ int launch_spmv_species(const qbgpu_matrix *A, const FusedArgs &a)
     a2.beta = make_double2(1.0, 0.0);
     if (a.scal_mode != 0) { a2.scal_mode = 2; a2.sc = a.sc; }
     else a2.alpha = a.alpha;
+    if (a.y_ref) { a2.y_ref = a.y_ref; a2.out_alpha = a.out_alpha; a2.perm_inv = A->perm_inv; }
     return launch_spmv(&C, a2);
 }
 
@@ -868,6 +887,106 @@ __global__ void __launch_bounds__(kPBlock) to_native_kernel(int64_t n, const int
         dst[p] = cvt<DstT, SrcT>(src[perm_inv[p]]);
 }
 
+// The way in, tile by tile: one CTA takes one block of the reference's order (the rows of one odd-site label: contiguous there,
+// a rectangle [iu0, iu0 + Cu) x [id0, id0 + Cd) of the internal order, see build_host_tables), reads it coalesced, transposes it
+// into the rectangle's own row-major order in shared memory and writes Cu runs of Cd contiguous entries.  Both sides touch
+// every sector once (the element-wise gather read 7.2 GB for a 2.65 GB vector on BASELINE config 3).  CHECK: *flag = 1 as soon
+// as one imaginary part of the source is not zero (the real-content route of mv_species).
+// per block of the reference's order: the rectangle it maps to (computed once, when the handle is created)
+__global__ void __launch_bounds__(kPBlock) tile_descriptor_kernel(int64_t nblk, const int64_t *__restrict__ blk_start, int32_t Dd,
+                                                                  const int32_t *__restrict__ perm, int4 *desc)
+{
+    __shared__ int s_lo_u, s_hi_u, s_lo_d, s_hi_d;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t r0 = blk_start[blk];
+        const int na = (int)(blk_start[blk + 1] - r0);
+        if (threadIdx.x == 0) { s_lo_u = 0x7fffffff; s_hi_u = -1; s_lo_d = 0x7fffffff; s_hi_d = -1; }
+        __syncthreads();
+        int lo_u = 0x7fffffff, hi_u = -1, lo_d = 0x7fffffff, hi_d = -1;
+        for (int t = threadIdx.x; t < na; t += kPBlock) {
+            const int32_t p = perm[r0 + t];
+            const int iu = p / Dd, id = p - iu * Dd;
+            lo_u = min(lo_u, iu); hi_u = max(hi_u, iu); lo_d = min(lo_d, id); hi_d = max(hi_d, id);
+        }
+        lo_u = __reduce_min_sync(0xffffffffu, lo_u); hi_u = __reduce_max_sync(0xffffffffu, hi_u);
+        lo_d = __reduce_min_sync(0xffffffffu, lo_d); hi_d = __reduce_max_sync(0xffffffffu, hi_d);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_lo_u, lo_u); atomicMax(&s_hi_u, hi_u); atomicMin(&s_lo_d, lo_d); atomicMax(&s_hi_d, hi_d); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int cu = s_hi_u - s_lo_u + 1, cd = s_hi_d - s_lo_d + 1;
+            desc[blk] = make_int4(s_lo_u, s_lo_d, ((int64_t)cu * cd == na) ? cd : 0, na);     // .z == 0: not a rectangle (never, by construction)
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int kTBlock = 512;
+template <typename SrcT, typename DstT, bool CHECK>
+__global__ void __launch_bounds__(kTBlock) to_native_tiled_kernel(int64_t nblk, const int64_t *__restrict__ blk_start, const int4 *__restrict__ desc, int32_t Dd,
+                                                                  const int32_t *__restrict__ perm, const SrcT *__restrict__ src, DstT *dst, int *flag)
+{
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    DstT *tile = (DstT *)tile_raw;
+    bool any = false;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t r0 = blk_start[blk];
+        const int4 d = desc[blk];
+        const int iu0 = d.x, id0 = d.y, cd = d.z, na = d.w;
+        constexpr int UN = 4;                               // loads of four rounds first, then their scatters
+        for (int t0 = threadIdx.x; t0 < na; t0 += UN * kTBlock) {
+            int32_t p[UN];
+            SrcT v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) { const int t = t0 + u * kTBlock; if (t < na) { p[u] = perm[r0 + t]; v[u] = src[r0 + t]; } }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int t = t0 + u * kTBlock;
+                if (t < na) {
+                    if constexpr (CHECK) any = any || (v[u].y != 0.0);
+                    if (cd) { const int iu = p[u] / Dd, id = p[u] - iu * Dd; tile[(iu - iu0) * cd + (id - id0)] = cvt<DstT, SrcT>(v[u]); }
+                    else dst[p[u]] = cvt<DstT, SrcT>(v[u]);
+                }
+            }
+        }
+        __syncthreads();
+        if (cd) {
+            for (int t = threadIdx.x; t < na; t += kTBlock) {
+                const int row = t / cd, col = t - row * cd;
+                dst[(int64_t)(iu0 + row) * Dd + id0 + col] = tile[t];
+            }
+        }
+        __syncthreads();
+    }
+    if constexpr (CHECK) { if (any) *(volatile int *)flag = 1; }
+}
+
+template <typename SrcT, typename DstT, bool CHECK>
+static int launch_to_native_tiled(const qbgpu_matrix *A, const void *src, void *dst, int *flag)
+{
+    Context &c = ctx();
+    const Species *S = (const Species *)A->sp;
+    auto kern = to_native_tiled_kernel<SrcT, DstT, CHECK>;
+    const size_t smem = sizeof(DstT) * (size_t)S->blk_max_rows;
+    static size_t smem_set = 0;
+    if (smem > smem_set) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    static int bps = 0;
+    static size_t bps_smem = 0;
+    if (bps == 0 || bps_smem != smem) { QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kTBlock, smem)); bps_smem = smem; if (bps < 1) bps = 1; }
+    int64_t g = S->nblk < (int64_t)c.num_sms * bps ? S->nblk : (int64_t)c.num_sms * bps;      // one wave of resident CTAs, blocks round-robin
+    if (g < 1) g = 1;
+    kern<<<(int)g, kTBlock, smem, c.stream>>>(S->nblk, S->blk_start, S->blk_desc, (int32_t)S->Dd, A->perm, (const SrcT *)src, (DstT *)dst, flag);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+// the tiles fit in shared memory and the handle carries the block table
+static bool to_native_tiled_ok(const qbgpu_matrix *A, size_t elem)
+{
+    const Species *S = (const Species *)A->sp;
+    static const bool off = getenv("QBGPU_PERM_TILED") && atoi(getenv("QBGPU_PERM_TILED")) == 0;
+    return !off && S && S->blk_start && S->blk_desc && S->nblk > 0 && elem * (size_t)S->blk_max_rows <= 200 * 1024;
+}
+
 // the way in of the real-content product: dst[p] = Re src[perm_inv[p]]; *flag = 1 as soon as one imaginary part is not zero
 __global__ void __launch_bounds__(kPBlock) to_native_real_check_kernel(int64_t n, const int32_t *__restrict__ perm_inv, const double2 *__restrict__ src,
                                                                        double *dst, int *flag)
@@ -899,6 +1018,12 @@ int vec_to_native(const qbgpu_matrix *A, bool src_cplx, bool dst_cplx, const voi
     Context &c = ctx();
     const int64_t n = A->n;
     const int g = grid_rows(n);
+    if (to_native_tiled_ok(A, dst_cplx ? 16 : 8)) {
+        if (src_cplx && dst_cplx) return launch_to_native_tiled<double2, double2, false>(A, src, dst, nullptr);
+        if (src_cplx) return launch_to_native_tiled<double2, double, false>(A, src, dst, nullptr);
+        if (dst_cplx) return launch_to_native_tiled<double, double2, false>(A, src, dst, nullptr);
+        return launch_to_native_tiled<double, double, false>(A, src, dst, nullptr);
+    }
     if (src_cplx && dst_cplx) to_native_kernel<double2, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double2 *)src, (double2 *)dst);
     else if (src_cplx) to_native_kernel<double2, double><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double2 *)src, (double *)dst);
     else if (dst_cplx) to_native_kernel<double, double2><<<g, kPBlock, 0, c.stream>>>(n, A->perm_inv, (const double *)src, (double2 *)dst);
@@ -967,32 +1092,77 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
     // fp64 copy -- half the vector bytes, half the gather sectors, the block of x fits the shared memory of pass 1 -- and the
     // way out widens the result.  Exact: the real parts go through the identical fma sequence, the imaginary parts are exact
     // zeros either way.  A vector with any non-zero imaginary part takes the complex passes (QBGPU_MV_REAL_MODE=0: always).
-    bool real_content = false;
     static const bool real_mode_on = !(getenv("QBGPU_MV_REAL_MODE") && atoi(getenv("QBGPU_MV_REAL_MODE")) == 0);
-    if (cplx && A->val_real && real_mode_on) {
-        int *flag = (int *)(c.scal_dev + 57);
-        QB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
-        to_native_real_check_kernel<<<grid_rows(A->n), kPBlock, 0, c.stream>>>(A->n, A->perm_inv, (const double2 *)xd, (double *)px, flag);
-        QB_LAUNCH_COUNT();
-        QB_CUDA(cudaGetLastError());
-        int h = 1;
-        QB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-        QB_CUDA(cudaStreamSynchronize(c.stream));
-        real_content = (h == 0);
-    }
-    if (real_content) {
-        qbgpu_matrix R = *A;                                // same arrays, fp64 vectors
-        R.api_complex = false;
-        FusedArgs fa;
-        fa.x = px; fa.y = py;
-        QB_TRY(launch_spmv(&R, fa));
-        QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
-    } else {
+    // opt-in (QBGPU_FUSE_WAY_IN=1), measured on BASELINE config 3 and SLOWER: the gathers of the staging phase are exposed in every
+    // block (pass 1: 7.31 -> 8.96 ms) while the tiled way in of its own costs 1.24 ms
+    static const bool fuse_in_on = getenv("QBGPU_FUSE_WAY_IN") && atoi(getenv("QBGPU_FUSE_WAY_IN")) != 0;
+    const Species *S = (const Species *)A->sp;
+    int *flag = (int *)(c.scal_dev + 57);
+    auto complex_route = [&]() -> int {
         QB_TRY(vec_to_native(A, cplx, cplx, xd, px));
         FusedArgs fa;
         fa.x = px; fa.y = py;
         QB_TRY(launch_spmv(A, fa));
-        QB_TRY(vec_from_native(A, cplx, cplx, py, yd, alpha, beta));
+        return vec_from_native(A, cplx, cplx, py, yd, alpha, beta);
+    };
+    auto read_flag = [&](int &h) -> int {
+        h = 1;
+        QB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        QB_CUDA(cudaStreamSynchronize(c.stream));
+        return QBGPU_OK;
+    };
+    if (cplx && A->val_real && real_mode_on) {
+        qbgpu_matrix R = *A;                                // same arrays, fp64 vectors
+        R.api_complex = false;
+        qbgpu_matrix Lp = R;                                // (what launch_spmv_species will hand to pass 1)
+        Lp.sp = nullptr; Lp.second = nullptr;
+        // The way in can ride in pass 1 when that pass is the block-local kernel (it stages every block of x in shared memory
+        // anyway: it then gathers the block from the reference-order vector itself and leaves the fp64 copy behind for pass 2)
+        // and y is not read (beta == 0: the whole product can be repeated on the complex route if an imaginary part turns up).
+        const bool fuse = fuse_in_on && !use_beta && !S->matfree && A->second && block_smem_applicable(&Lp, S->Dd) && sjds_block_variant_ok();
+        QB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c.stream));
+        if (fuse) {
+            FusedArgs fa;
+            fa.x = px; fa.y = py;
+            fa.x_ref = xd; fa.perm_inv = A->perm_inv; fa.imag_flag = flag;
+            QB_TRY(launch_spmv(&R, fa));
+            QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
+            int h;
+            QB_TRY(read_flag(h));
+            if (h != 0) QB_TRY(complex_route());            // rare: a vector with imaginary parts; y was not read, so simply redo
+        } else {
+            if (to_native_tiled_ok(A, 8)) QB_TRY((launch_to_native_tiled<double2, double, true>(A, xd, px, flag)));
+            else {
+                to_native_real_check_kernel<<<grid_rows(A->n), kPBlock, 0, c.stream>>>(A->n, A->perm_inv, (const double2 *)xd, (double *)px, flag);
+                QB_LAUNCH_COUNT();
+                QB_CUDA(cudaGetLastError());
+            }
+            int h;
+            if (!use_beta) {
+                // y is not read: run the fp64 passes at once and look at the flag afterwards (the read-back then costs no idle
+                // time on the device); a vector with imaginary parts -- rare -- simply repeats the product on the complex route
+                // ... and the closing pass writes the reference's order itself (sjds_bulk.cu, OUT): the separate way out -- 0.9 ms
+                // of 17 on BASELINE config 3 -- is gone for 2 GB more traffic in pass 2
+                const bool fuse_out = !S->matfree && A->second && A->row_lo == 0 && A->row_hi == A->n && sjds_bulk_out_fusable(A->second);
+                FusedArgs fa;
+                fa.x = px; fa.y = py;
+                if (fuse_out) { fa.y_ref = yd; fa.out_alpha = alpha; }
+                QB_TRY(launch_spmv(&R, fa));
+                if (!fuse_out) QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
+                QB_TRY(read_flag(h));
+                if (h != 0) QB_TRY(complex_route());
+            } else {
+                QB_TRY(read_flag(h));
+                if (h == 0) {
+                    FusedArgs fa;
+                    fa.x = px; fa.y = py;
+                    QB_TRY(launch_spmv(&R, fa));
+                    QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
+                } else QB_TRY(complex_route());
+            }
+        }
+    } else {
+        QB_TRY(complex_route());
     }
     if (where == QBGPU_HOST) {
         QB_CUDA(cudaMemcpyAsync(y, yd, bytes, cudaMemcpyDeviceToHost, c.stream));

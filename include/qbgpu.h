@@ -362,6 +362,12 @@ int qbgpu_sector_norms(qbgpu_sector_t S, double *nu_host);
  * add_Ham calls); fake_pos is model's constructor argument (default 100, src/qbasis.h:1337). */
 int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J,
                                   double fake_pos, int flags);
+/* The same Hamiltonian WITHOUT stored entries: the handle regenerates every row inside the product -- model<T>::MultMv2 with
+ * matrix_free == true, repr branch (src/model.cc:1016-1107): y[i] += x[j] * sqrt(nu_i/nu_j) * conj(c) * exp(2 pi i k.disp_i/L) for
+ * every term, fake_pos + i/dim on zero-norm rows.  Works with every entry point that takes a handle (products, Lanczos, CG, KPM).
+ * The handle borrows the sector's device tables: destroy it before the sector. */
+int qbgpu_sector_matfree_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J,
+                                    double fake_pos);
 /* model::moprXvec_repr (src/model.cc:1716-1846) for A = sum_r c_r S^z_r (coef_reim[2*nsites], site order): device
  * vectors x_old (sector S_old) -> y_new (sector S_new, same lattice and Sz, momentum shifted by the operator's q).
  * With measure_repr_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1897-1912. */

@@ -363,6 +363,16 @@ class Sector:
         check(lib().qbgpu_sector_build_heisenberg(self._h, C.byref(h), nb, C.c_void_p(b.ctypes.data), float(J), float(fake_pos), flags))
         return csr_mat._adopt(h, True)
 
+    def heisenberg_matrix_free(self, bonds, J=1.0, fake_pos=100.0):
+        """The handle of model<T>::MultMv2 with matrix_free == true on this sector (src/model.cc:1016-1107): no stored entries,
+        rows regenerated inside every product.  Keeps the sector alive for as long as the handle lives."""
+        b, nb = _bond_array(bonds)
+        h = C.c_void_p()
+        check(lib().qbgpu_sector_matfree_heisenberg(self._h, C.byref(h), nb, C.c_void_p(b.ctypes.data), float(J), float(fake_pos)))
+        m = csr_mat._adopt(h, True)
+        m._sector = self
+        return m
+
     def apply_sz(self, new_sector, coef, x, out=None):
         """model::moprXvec_repr (src/model.cc:1716-1846) for A = sum_r coef[r] S^z_r: x (DeviceVector or host array in this
         sector) -> DeviceVector in `new_sector` (written into `out` when given)."""
@@ -447,6 +457,32 @@ def measure_full_dynamic(kind, nsites, n0, n1, coef0, coef1, mat, phi0, maxit, h
     v = DeviceVector(2 * n)
     v.zero()
     full_apply_diag(kind, nsites, n0, n1, coef0, coef1, phi0, out=v.view(0, n))
+    nr = C.c_double()
+    check(lib().qbgpu_dznrm2(n, C.c_void_p(v.ptr), C.byref(nr)))
+    if abs(nr.value) < lanczos_precision:
+        v.free()
+        return 0, nr.value
+    check(lib().qbgpu_zscal(n, (C.c_double * 2)(1.0 / nr.value, 0.0), C.c_void_p(v.ptr)))
+    m = lanczos(0, maxit - 1, maxit, n, mat, v, hessenberg, "dnmcs")
+    v.free()
+    return m, nr.value
+
+
+def measure_vrnl_dynamic(vec_new, mat, maxit, hessenberg):
+    """model<T>::measure_vrnl_dynamic (src/model.cc:2132-2143) from the point where the device path starts: `mat` is the handle
+    of HamMat_csr_vrnl[sec] (assembled on the host by generate_Ham_sparse_vrnl, src/model.cc:839-924, and uploaded like any other
+    csr_mat -- host assembly is outside the hot path) and `vec_new` = moprXgs_vrnl(Bq) = N * Aq |phi> (host array or DeviceVector,
+    complex128, length dim).  norm = |vec_new|; if it is not below lanczos_precision: lanczos(0, maxit-1, maxit, m, dim, HamMat,
+    vec_new / norm, hessenberg, "dnmcs").  Returns (m, norm)."""
+    n = mat.dim
+    v = DeviceVector(2 * n)
+    v.zero()
+    src = vec_new if isinstance(vec_new, DeviceVector) else DeviceVector.from_numpy(np.ascontiguousarray(vec_new, dtype=np.complex128))
+    if src.n < n:
+        raise QbgpuError("vec_new must hold dim entries")
+    check(lib().qbgpu_zaxpy(n, (C.c_double * 2)(1.0, 0.0), C.c_void_p(src.ptr), C.c_void_p(v.ptr)))      # v[:dim] = vec_new (v is zero)
+    if src is not vec_new:
+        src.free()
     nr = C.c_double()
     check(lib().qbgpu_dznrm2(n, C.c_void_p(v.ptr), C.byref(nr)))
     if abs(nr.value) < lanczos_precision:

@@ -186,7 +186,7 @@ int qbgpu_debug_set_variant(int id)
 {
     if (id >= 1000 && id < 1010) { qb::set_kron_local_variant(id - 1000); return QBGPU_OK; }   // pass 1 of the matrix-free species product
     if (id >= 2000 && id < 2020) { qb::set_sjds_bulk_mode(id - 2000); return QBGPU_OK; }       // bulk-streamed sliced-jagged product: 0 off, 1.. configuration
-    if (id >= 3000 && id < 3010) { qb::set_block_smem_variant(id - 3000); return QBGPU_OK; }   // block-local product (pass 1 of the stored species handle)
+    if (id >= 3000 && id < 3030) { qb::set_block_smem_variant(id - 3000); return QBGPU_OK; }   // block-local product (pass 1 of the stored species handle)
     qb::set_sjds_variant(id);
     return QBGPU_OK;
 }

@@ -33,6 +33,7 @@ struct qbgpu_matrix {
     // QBGPU_FORMAT_MATFREE: no stored entries at all; `mf` owns the sector tables, the bond list and the per-row
     // basis states from which every row is regenerated inside the product (builders.cu).
     void    *mf = nullptr;
+    void    *mf_sec = nullptr;     // matrix-free product over a translation-symmetric sector (sectors.cu); borrows the sector's tables
     // ring-fused row shard (qbgpu_ring_prepare): every row's entries are rotated so that the columns owned by this rank
     // come first, then those of rank+1, ... (ring order); the product then consumes the vector slices in the order the
     // peer pulls deliver them and waits, entry by entry, on the arrival flags of peer.cu.
@@ -62,6 +63,7 @@ struct qbgpu_matrix {
     // the device whose context first multiplied with this handle (the creating thread's): a product issued from a thread
     // bound to ANOTHER device (the context is thread-local) is refused instead of running on the wrong device or stream
     mutable int device = -1;
+    mutable bool last_x_had_imag = false;      // mv_species: the previous vector had non-zero imaginary parts -> look at the flag BEFORE the fp64 passes
     double  upload_s = 0, convert_s = 0, autotune_s = 0;
     int64_t nrows() const { return row_hi - row_lo; }
     size_t  val_bytes() const { return ndict ? 1 : (val_real ? 8 : 16); }
@@ -113,6 +115,8 @@ int launch_spmv_block_smem(const qbgpu_matrix *A, const FusedArgs &args, int64_t
 void set_block_smem_variant(int v);
 int launch_spmv_matfree(const qbgpu_matrix *A, const FusedArgs &args);     // builders.cu
 void matfree_destroy(qbgpu_matrix *A);
+int launch_spmv_sector_matfree(const qbgpu_matrix *A, const FusedArgs &a);      // sectors.cu
+void sector_matfree_destroy(qbgpu_matrix *A);
 int64_t matfree_bytes(const qbgpu_matrix *A);
 void set_sjds_far_rows(int64_t r);      // in-place CSR <-> sliced-jagged re-ordering of col/val
 int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view);     // sjds.cu

@@ -404,7 +404,7 @@ int split_columns(qbgpu_matrix *A, int nparts, const int64_t *bounds, qbgpu_matr
     if (!A || !bounds || !out || nparts < 1 || nparts > kMaxParts) return fail(QBGPU_ERR_ARG, "split_columns: bad argument (1..16 parts)");
     if (bounds[0] != 0 || bounds[nparts] != A->n) return fail(QBGPU_ERR_ARG, "split_columns: bounds must run from 0 to n");
     for (int p = 0; p < nparts; p++) if (bounds[p + 1] < bounds[p]) return fail(QBGPU_ERR_ARG, "split_columns: bounds must be non-decreasing");
-    if (A->ndict || A->mf) return fail(QBGPU_ERR_STATE, "split_columns: not available for dictionary-coded or matrix-free handles");
+    if (A->ndict || A->mf || A->mf_sec) return fail(QBGPU_ERR_STATE, "split_columns: not available for dictionary-coded or matrix-free handles");
     const bool was_jagged = (A->format == QBGPU_FORMAT_SELL);
     QB_TRY(sjds_convert(A, false));                         // needs plain CSR order (restored below)
     const int64_t nloc = A->nrows();
@@ -473,7 +473,7 @@ int qbgpu_create_zcsr_shard(qbgpu_matrix_t *A, int64_t n, const int64_t *rs, con
 int qbgpu_destroy(qbgpu_matrix_t A)
 {
     if (!A) return QBGPU_OK;                               // like mkl_sparse_destroy on csr_mat's empty objects
-    if (!A->borrowed) { matfree_destroy(A); species_destroy(A); }
+    if (!A->borrowed) { matfree_destroy(A); sector_matfree_destroy(A); species_destroy(A); }
     if (!A->borrowed) { cudaFree(A->rowptr); cudaFree(A->col); cudaFree(A->val); cudaFree(A->rowinfo); cudaFree(A->vdict); cudaFree(A->slice_order);
                         cudaFree(A->perm_x); cudaFree(A->perm_y); }
     else if (A->owns_order) cudaFree(A->slice_order);
@@ -488,7 +488,7 @@ int qbgpu_matrix_get_info(qbgpu_matrix_t A, qbgpu_matrix_info *info)
     info->nnz_stored = A->nnz + (A->second ? A->second->nnz : 0); info->nnz_input = A->nnz_input;
     info->val_is_real = A->val_real; info->value_dict = A->ndict; info->api_is_complex = A->api_complex;
     info->format = A->format; info->lanes = A->lanes;
-    info->device_bytes = A->sp ? species_bytes(A) : A->mf ? matfree_bytes(A) : (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
+    info->device_bytes = A->sp ? species_bytes(A) : A->mf ? matfree_bytes(A) : A->mf_sec ? (int64_t)sizeof(double) * 0 : (int64_t)(A->nnz * (4 + A->val_bytes()) + 8 * (A->nrows() + 1));
     info->upload_seconds = A->upload_s; info->convert_seconds = A->convert_s; info->autotune_seconds = A->autotune_s;
     return QBGPU_OK;
 }
@@ -498,7 +498,7 @@ int qbgpu_download_expanded(qbgpu_matrix_t A, int64_t *rowptr, int32_t *col, voi
     QB_TRY(ensure_init());
     if (!A || !rowptr || !col || !val) return fail(QBGPU_ERR_ARG, "null argument");
     QB_TRY(no_species(A, "download_expanded"));
-    if (A->mf) return fail(QBGPU_ERR_STATE, "matrix-free handle: there are no stored entries to download");
+    if (A->mf || A->mf_sec) return fail(QBGPU_ERR_STATE, "matrix-free handle: there are no stored entries to download");
     const bool jag = (A->format == QBGPU_FORMAT_SELL);      // hand back plain CSR order whatever the resident layout
     if (jag) QB_TRY(sjds_convert(A, false));
     QB_CUDA(cudaStreamSynchronize(ctx().stream));

@@ -271,6 +271,75 @@ __global__ void __launch_bounds__(kSBlock) sec_rows_kernel(SecDev S, const SecTe
     }
 }
 
+// Matrix-free product over the sector: model<T>::MultMv2, repr branch (src/model.cc:1016-1107).  Row i is regenerated from the
+// bond list exactly as sec_rows_kernel stores it, but as the FULL row seen from i (the reference does the same: every term, no
+// upper-triangle filter, y[i] += x[j] * sqrt(nu_i/nu_j) * conj(c) * exp(2 pi i k.disp_i/L)), and consumed at once.  Zero-norm rows
+// carry fake_pos + i/dim on the diagonal (:1022-1025).  Nothing is stored: the sector's tables (keys, norms, sublattice tables)
+// are all that lives in HBM -- the reference's own answer to dimensions whose csr_mat does not fit.
+template <bool DOTS>
+__global__ void __launch_bounds__(kSBlock) sec_matfree_spmv_kernel(SecDev S, const SecTerms *Tp, const double2 *__restrict__ phase,
+                                                                   const double2 *__restrict__ x, const double2 *z, double2 *y,
+                                                                   double2 alpha, double2 gamma, double2 beta, int scal_mode,
+                                                                   const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket)
+{
+    using VT = VecTraits<double2>;
+    __shared__ SecTerms T;
+    for (int i = threadIdx.x; i < (int)(sizeof(SecTerms) / 4); i += blockDim.x) ((int *)&T)[i] = ((const int *)Tp)[i];
+    __syncthreads();
+    double dot_scale = 1.0;
+    if (scal_mode != 0) {                                              // the fused Lanczos step (internal.hpp: FusedArgs)
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+        dot_scale = sx;
+    }
+    const bool use_beta = (beta.x != 0.0 || beta.y != 0.0);
+    double d[3] = {0.0, 0.0, 0.0};
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const double nu_i = S.nu[r];
+        const double2 xi = x[r];
+        double2 acc = VT::zero();
+        if (nu_i == 0.0) {
+            mac(acc, __dadd_rn(T.fake_pos, __ddiv_rn((double)r, (double)S.n)), xi);
+        } else {
+            uint32_t a, b;
+            sec_halves(S, S.keys[r], a, b);
+            const uint32_t s = spread_bits(a) | (spread_bits(b) << 1);
+            double dg = 0.0;
+            for (int t = 0; t < T.nterms; t++)
+                dg = __dadd_rn(dg, (((s >> T.p[t]) ^ (s >> T.q[t])) & 1u) ? -0.25 * T.J : 0.25 * T.J);
+            mac(acc, dg, xi);
+            for (int t = 0; t < T.nterms; t++) {
+                if (!(((s >> T.p[t]) ^ (s >> T.q[t])) & 1u)) continue;
+                const uint32_t s2 = s ^ ((1u << T.p[t]) | (1u << T.q[t]));
+                uint32_t ca = 0, cb = 0;
+                const int i = sec_canon(S, squeeze_bits(s2), squeeze_bits(s2 >> 1), ca, cb);
+                if (i < 0) continue;
+                const int64_t j = sec_lookup(S, sec_key(S, ca, cb));
+                if (j < 0) continue;                                   // not in the sector
+                const double nu_j = S.nu[j];
+                if (nu_j == 0.0) continue;
+                const double w = __dmul_rn(__dsqrt_rn(__ddiv_rn(nu_i, nu_j)), 0.5 * T.J);
+                const double2 ph = phase[i];
+                mac(acc, make_double2(__dmul_rn(w, ph.x), __dmul_rn(w, ph.y)), x[j]);
+            }
+        }
+        double2 out = VT::scale(alpha, acc);
+        if (gamma.x != 0.0 || gamma.y != 0.0) out = VT::add(out, VT::scale(gamma, xi));
+        if (use_beta) out = VT::add(out, VT::scale(beta, z[r]));
+        y[r] = out;
+        if (DOTS) {
+            const double2 p = VT::conj_mul(xi, out);
+            d[0] += p.x; d[1] += p.y; d[2] += VT::abs2(out);
+        }
+    }
+    if (DOTS) {
+        d[0] *= dot_scale; d[1] *= dot_scale;
+        block_reduce_finalize<3, kSBlock>(d, partials, ticket, dots_out);
+    }
+}
+
 __global__ void __launch_bounds__(kSBlock) sec_len_kernel(int64_t n, const int64_t *start, const int64_t *end, int64_t *len)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) len[r] = end[r] - start[r];
@@ -431,6 +500,12 @@ bool lin_tables_exist(const std::vector<uint32_t> &keys, int nsub)
     return true;
 }
 
+struct SecMatFree {                      // what a matrix-free sector handle owns: the term list; everything else is the sector's
+    SecDev dev;
+    SecTerms *d_T = nullptr;
+    const double2 *phase = nullptr;
+};
+
 void sector_free(qbgpu_sector *S)
 {
     if (!S) return;
@@ -439,6 +514,37 @@ void sector_free(qbgpu_sector *S)
 }
 
 }  // namespace
+
+int qb::launch_spmv_sector_matfree(const qbgpu_matrix *A, const FusedArgs &a)
+{
+    Context &c = ctx();
+    const SecMatFree *M = (const SecMatFree *)A->mf_sec;
+    if (!A->api_complex) return fail(QBGPU_ERR_STATE, "matrix-free sector handle: complex vectors only");
+    auto kern = a.dots ? sec_matfree_spmv_kernel<true> : sec_matfree_spmv_kernel<false>;
+    int blocks_per_sm = 0;
+    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kSBlock, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int64_t n = A->n;
+    if (n == 0) return QBGPU_OK;
+    int64_t want = (n + kSBlock - 1) / kSBlock;
+    int64_t cap = (int64_t)c.num_sms * blocks_per_sm;
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    const int grid = (int)(want < cap ? want : cap);
+    kern<<<grid, kSBlock, 0, c.stream>>>(M->dev, M->d_T, M->phase, (const double2 *)a.x, (const double2 *)a.z, (double2 *)a.y, a.alpha, a.gamma, a.beta,
+                                         a.scal_mode, a.sc, a.dots, c.partials, c.ticket);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
+void qb::sector_matfree_destroy(qbgpu_matrix *A)
+{
+    SecMatFree *M = (SecMatFree *)A->mf_sec;
+    if (!M) return;
+    cudaFree(M->d_T);
+    delete M;
+    A->mf_sec = nullptr;
+}
 
 extern "C" {
 
@@ -756,6 +862,40 @@ int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbond
     int rc = create_from_device_csr(A, n, d_start, d_end, d_col, d_val, true, upper, 1, flags, true);
     cleanup();
     return rc;
+}
+
+/* Matrix-free handle over a sector: model<T>::MultMv / MultMv2 with matrix_free == true, repr branch (src/model.cc:1016-1107).
+ * The handle borrows the sector's device tables: destroy it before the sector. */
+int qbgpu_sector_matfree_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J, double fake_pos)
+{
+    QB_TRY(ensure_init());
+    if (!S || !A || !bonds || nbonds < 1) return fail(QBGPU_ERR_ARG, "sector_matfree_heisenberg: bad arguments");
+    if (nbonds > kMaxTerms) return fail(QBGPU_ERR_ARG, "sector_matfree_heisenberg: at most 128 bonds");
+    Context &c = ctx();
+    *A = nullptr;
+    std::vector<std::pair<int, int>> bs;
+    for (int t = 0; t < nbonds; t++) {
+        const int p = bonds[2 * t], q = bonds[2 * t + 1];
+        if (p < 0 || q < 0 || p >= S->nsites || q >= S->nsites || p == q) return fail(QBGPU_ERR_ARG, "sector_matfree_heisenberg: bad bond");
+        bs.push_back({std::min(p, q), std::max(p, q)});
+    }
+    std::stable_sort(bs.begin(), bs.end());                             // the term order of the stored assembly (diagonal sums bit for bit)
+    SecTerms T;
+    memset(&T, 0, sizeof(T));
+    T.nterms = nbonds; T.J = J; T.fake_pos = fake_pos;
+    for (int t = 0; t < nbonds; t++) { T.p[t] = (uint8_t)bs[t].first; T.q[t] = (uint8_t)bs[t].second; }
+    auto *M = new SecMatFree;
+    M->dev = S->dev; M->phase = S->d_phase;
+    if (cudaMalloc(&M->d_T, sizeof(SecTerms)) != cudaSuccess) { delete M; return cuda_fail(cudaGetLastError(), "cudaMalloc(terms)", __FILE__, __LINE__); }
+    if (cudaMemcpyAsync(M->d_T, &T, sizeof(SecTerms), cudaMemcpyHostToDevice, c.stream) != cudaSuccess || cudaStreamSynchronize(c.stream) != cudaSuccess) {
+        cudaFree(M->d_T); delete M; return cuda_fail(cudaGetLastError(), "upload(terms)", __FILE__, __LINE__);
+    }
+    auto *H = new qbgpu_matrix;
+    H->n = S->n; H->row_lo = 0; H->row_hi = S->n; H->api_complex = true; H->val_real = false;
+    H->format = QBGPU_FORMAT_MATFREE; H->nnz = 0; H->nnz_input = 0;
+    H->mf_sec = M;
+    *A = H;
+    return QBGPU_OK;
 }
 
 }  // extern "C"

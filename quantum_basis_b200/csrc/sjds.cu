@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kSBlock) ring_rotate_kernel(int64_t nrows, con
 int ring_prepare(qbgpu_matrix *A, int rank, int world, int64_t chunk, qbgpu_matrix **view)
 {
     Context &c = ctx();
-    if (!A || A->mf || A->borrowed) return fail(QBGPU_ERR_ARG, "ring_prepare: needs an owning, stored matrix handle");
+    if (!A || A->mf || A->mf_sec || A->borrowed) return fail(QBGPU_ERR_ARG, "ring_prepare: needs an owning, stored matrix handle");
     if (!view) return fail(QBGPU_ERR_ARG, "ring_prepare: null view pointer");
     *view = nullptr;
     if (A->ring_world) return fail(QBGPU_ERR_STATE, "ring_prepare: already in ring order");

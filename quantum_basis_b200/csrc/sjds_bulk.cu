@@ -636,6 +636,240 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
     if (any_imag && imag_flag) *(volatile int *)imag_flag = 1;
 }
 
+// ------------------------------------------------------------------- (3) block-local product, x in smem AND the stream in rings
+// Kernel (2) feeds the matrix stream through registers: 1024 threads x 4 diagonals = 48 KB in flight per SM is all its 64
+// registers per thread allow, just short of what 1/148 of the HBM bandwidth times the loaded DRAM latency asks for (5.3 TB/s,
+// long-scoreboard stalls 11.8 per issue: profiles/r02_ncu_full_mv_reference_order_hubbard4x4.csv).  Here the two halves of this
+// file meet: the block of x sits in shared memory (one bulk copy per block, its successor prefetched into L2), and the matrix
+// stream arrives through the per-warp stage rings of kernel (1) -- 24 stages = 79 KB in flight with 8 warps -- so nothing a warp
+// touches in its loop is further away than shared memory.  The producer cursor runs ahead across block boundaries (the stream
+// does not depend on x); the consumers meet at a CTA barrier per block.  Same accumulation order as kernels (1) and (2).
+template <typename ValT, typename VecT, int NW, int NST, int KSEG>
+__global__ void __launch_bounds__(NW * 32, 1)
+sjds_block_bulk_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, int64_t u_cnt, const int64_t *__restrict__ rowptr,
+                       const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
+                       const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
+                       int scal_mode, const double *__restrict__ sc, const double *__restrict__ vdict, uint32_t xs_off, uint32_t ring_off)
+{
+    using VT = VecTraits<VecT>;
+    using ST = BulkStage<ValT, KSEG>;
+    static_assert(KSEG % 2 == 0 && KSEG >= 2, "diagonal k accumulates into accumulator k & 1 (the order of sjds.cu)");
+    constexpr bool kDict = sizeof(ValT) == 1;
+    using ArithT = typename std::conditional<kDict, double, ValT>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double sdict[kDict ? 256 : 1];
+    if (kDict) { for (int i = threadIdx.x; i < 256; i += NW * 32) sdict[i] = vdict[i]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const VecT *xs = (const VecT *)(smem_raw + xs_off);
+    unsigned char *wbase = smem_raw + ring_off + (size_t)warp * NST * ST::BYTES;
+    const uint32_t bar0 = smem_u32(smem_raw + 64 * warp);       // [NW][8] stage barriers, then the barrier of the x block
+    const uint32_t xbar = smem_u32(smem_raw + 64 * NW);
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < NST; st++) mbar_init(bar0 + 8 * st, 1);
+        if (warp == 0) mbar_init(xbar, 1);
+        mbar_fence_init();
+    }
+    if (scal_mode != 0) {
+        const double sx = sc[0], sz = sc[1], bprev = sc[2];
+        alpha = make_double2(sx, 0.0);
+        gamma = make_double2(0.0, 0.0);
+        beta = scal_mode == 1 ? make_double2(-bprev * sz, 0.0) : make_double2(1.0, 0.0);
+    }
+    __shared__ double2 s_scal[3];
+    if (threadIdx.x == 0) { s_scal[0] = alpha; s_scal[1] = gamma; s_scal[2] = beta; }
+    __syncthreads();
+    const bool use_gamma = (s_scal[1].x != 0.0 || s_scal[1].y != 0.0);
+    const bool use_beta = (s_scal[2].x != 0.0 || s_scal[2].y != 0.0);
+    const uint64_t pol_s = pol_evict_first();
+    const uint32_t xbytes = (uint32_t)(D * (int64_t)sizeof(VecT));
+
+    auto s_first = [&](int64_t ub) -> int { return (int)(((u_lo + ub) * D - row_lo) >> 5); };
+    auto s_last = [&](int64_t ub) -> int { return (int)(((u_lo + ub + 1) * D - row_lo - 1) >> 5); };
+    // successor of (ub, s) in this warp's sequence: the slices s_first(ub) + warp, + NW, ... of the CTA's blocks ub, ub + grid, ...
+    auto next_slice = [&](int64_t &ub, int &s) -> bool {
+        s += NW;
+        while (ub < u_cnt) {
+            if (s <= s_last(ub)) return true;
+            ub += gridDim.x;
+            if (ub < u_cnt) s = s_first(ub) + warp;
+        }
+        return false;
+    };
+    // ---- producer cursor (current slice) and the slice after it, whose row metadata is requested one slice ahead
+    int64_t pub = blockIdx.x;
+    int ps = (pub < u_cnt ? s_first(pub) : 0) + warp - NW;
+    bool p_more = next_slice(pub, ps);
+    uint32_t pinfo = p_more ? rowinfo[(int64_t)ps * 32 + lane] : 0u;
+    int64_t pbase = p_more ? rowptr[(int64_t)ps * 32] : 0;
+    int pk = 0, poff = 0;
+    int64_t nub = pub;
+    int ns = ps;
+    bool n_more = p_more && next_slice(nub, ns);
+    uint32_t ninfo = n_more ? rowinfo[(int64_t)ns * 32 + lane] : 0u;
+    int64_t nbase = n_more ? rowptr[(int64_t)ns * 32] : 0;
+    uint32_t phases = 0;
+    int n_issued = 0, n_cons = 0;
+
+    auto issue = [&]() {
+        const int st = n_issued % NST;
+        n_issued++;
+        const int len = (int)(pinfo & kLenMaskB);
+        const int maxlen = __shfl_sync(0xffffffffu, len, 0);
+        const int hi = min(len, pk + KSEG), lo = min(len, pk);
+        const int cnt = (int)__reduce_add_sync(0xffffffffu, (unsigned)(hi - lo));
+        unsigned char *sb = wbase + (size_t)st * ST::BYTES;
+        __syncwarp();
+        ((uint32_t *)(sb + 32))[lane] = pinfo;
+        if (lane == 0) {
+            const int64_t beg = pbase + poff;
+            int *hdr = (int *)sb;
+            *(int64_t *)hdr = beg; hdr[2] = cnt; hdr[3] = pk; hdr[4] = ps; hdr[5] = (int)pub;
+            if (cnt > 0) {
+                fence_proxy_async_smem();
+                const int64_t c0 = beg & ~3LL, c1 = (beg + cnt + 3) & ~3LL;
+                const int64_t v0 = beg & ~(int64_t)(ST::VALIGN - 1), v1 = (beg + cnt + ST::VALIGN - 1) & ~(int64_t)(ST::VALIGN - 1);
+                const uint32_t cb = (uint32_t)(c1 - c0) * 4u, vb = (uint32_t)((v1 - v0) * (int64_t)sizeof(ValT));
+                const uint32_t bar = bar0 + 8 * st;
+                mbar_expect_tx(bar, cb + vb);
+                bulk_g2s(smem_u32(sb + ST::HDR_BYTES), col + c0, cb, bar, pol_s);
+                bulk_g2s(smem_u32(sb + ST::HDR_BYTES + ST::COL_BYTES), val + v0, vb, bar, pol_s);
+            }
+        }
+        __syncwarp();
+        poff += cnt;
+        pk += KSEG;
+        if (pk >= maxlen) {                                 // slice finished (an empty slice is one empty segment)
+            p_more = n_more;
+            pub = nub; ps = ns; pinfo = ninfo; pbase = nbase; pk = 0; poff = 0;
+            if (n_more) {
+                n_more = next_slice(nub, ns);
+                ninfo = n_more ? rowinfo[(int64_t)ns * 32 + lane] : 0u;
+                nbase = n_more ? rowptr[(int64_t)ns * 32] : 0;
+            }
+        }
+    };
+
+#pragma unroll 1
+    for (int st = 0; st < NST && p_more; st++) issue();
+
+    VecT acc0 = VT::zero(), acc1 = VT::zero(), zv = VT::zero();
+    uint32_t xphase = 0;
+#pragma unroll 1
+    for (int64_t ub = blockIdx.x; ub < u_cnt; ub += gridDim.x) {
+        const int64_t c0 = (u_lo + ub) * D;                 // first column (= first global row) of the block
+        const int64_t r0 = c0 - row_lo, r1 = r0 + D;        // local rows of the block
+        __syncthreads();                                    // every warp has finished reading the previous block from xs
+        if (threadIdx.x == 0) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(xbar, xbytes);
+            bulk_g2s_plain(smem_u32(xs), x + c0, xbytes, xbar);
+            if (ub + gridDim.x < u_cnt)                     // the CTA's next block: into L2 now, so that the switch finds it there
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + c0 + (int64_t)gridDim.x * D), "r"(xbytes) : "memory");
+        }
+        mbar_wait(xbar, xphase);
+        xphase ^= 1u;
+#pragma unroll 1
+        while (n_cons < n_issued) {
+            const int st = n_cons % NST;
+            unsigned char *sb = wbase + (size_t)st * ST::BYTES;
+            if (((const int *)sb)[5] != (int)ub) break;     // the next segment belongs to a later block
+            const int4 h = *(const int4 *)sb;               // beg (lo, hi), cnt, k0
+            const int s = ((const int *)sb)[4];
+            const uint32_t info = ((const uint32_t *)(sb + 32))[lane];
+            const int len = (int)(info & kLenMaskB);
+            const int maxlen = __shfl_sync(0xffffffffu, len, 0);
+            const int minlen = __shfl_sync(0xffffffffu, len, 31);
+            const int cnt = h.z, k0 = h.w;
+            const int64_t row = (int64_t)s * 32 + (info >> 24);
+            const bool mine = row >= r0 && row < r1;        // a slice that straddles two blocks is streamed for both
+            if (k0 == 0) {
+                acc0 = VT::zero(); acc1 = VT::zero();
+                if (mine && use_beta) zv = z[row];          // requested with the first segment, used after the last
+            }
+            if (cnt > 0) {
+                mbar_wait(bar0 + 8 * st, (phases >> st) & 1u);
+                phases ^= 1u << st;
+                const int32_t *scol = (const int32_t *)(sb + ST::HDR_BYTES) + (h.x & 3) + lane;
+                const ValT *sval = (const ValT *)(sb + ST::HDR_BYTES + ST::COL_BYTES) + (h.x & (ST::VALIGN - 1)) + lane;
+                if (k0 + KSEG <= minlen) {                  // full segment: entry (u, lane) at u*32 + lane
+                    int idx[KSEG];
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) idx[u] = mine ? (int)((int64_t)scol[u * 32] - c0) : 0;
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) {
+                        const VecT xv = xs[idx[u]];
+                        ArithT w;
+                        if constexpr (kDict) w = sdict[sval[u * 32]]; else w = sval[u * 32];
+                        if (u & 1) mac(acc1, w, xv); else mac(acc0, w, xv);
+                    }
+                } else {
+                    // ragged segment, in batches like the full one (offsets, then all columns, then all gathers, then the
+                    // products): lanes without diagonal k0 + u read entry 0 of the stage and x[0] of the block and skip the fma.
+                    // (A first version branched per diagonal: 8 serialised LDS -> LDS -> DFMA chains per segment, and two
+                    // thirds of this part's segments are ragged: profiles/r02_ncu_block_bulk_first_version.txt)
+                    bool a[KSEG];
+                    int o[KSEG], idx[KSEG];
+                    int off = 0;
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) {
+                        a[u] = (k0 + u < len) && mine;
+                        o[u] = a[u] ? off : 0;
+                        off += __popc(__ballot_sync(0xffffffffu, k0 + u < len));
+                    }
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) { const int c = scol[o[u]]; idx[u] = a[u] ? (int)((int64_t)c - c0) : 0; }
+                    VecT xv[KSEG];
+                    ArithT w[KSEG];
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) xv[u] = xs[idx[u]];
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) { if constexpr (kDict) w[u] = sdict[sval[o[u]]]; else w[u] = sval[o[u]]; }
+#pragma unroll
+                    for (int u = 0; u < KSEG; u++) {
+                        if (a[u]) { if (u & 1) mac(acc1, w[u], xv[u]); else mac(acc0, w[u], xv[u]); }
+                    }
+                }
+            }
+            if (k0 + KSEG >= maxlen && mine) {              // last segment of the slice: the epilogue of sjds.cu
+                const VecT acc = VT::add(acc0, acc1);
+                VecT out = VT::scale(s_scal[0], acc);
+                if (use_gamma) out = VT::add(out, VT::scale(s_scal[1], xs[row - r0]));
+                if (use_beta) out = VT::add(out, VT::scale(s_scal[2], zv));
+                y[row] = out;
+            }
+            __syncwarp();                                   // every lane is done with the stage before it is refilled
+            n_cons++;
+            if (p_more) issue();
+        }
+    }
+}
+
+template <typename ValT, typename VecT, int NW, int NST, int KSEG>
+static int launch_block_bulk_cfg(const qbgpu_matrix *A, const FusedArgs &a, int64_t D, bool probe_only = false)
+{
+    Context &c = ctx();
+    using ST = BulkStage<ValT, KSEG>;
+    auto kern = sjds_block_bulk_kernel<ValT, VecT, NW, NST, KSEG>;
+    const size_t xs_off = ((size_t)64 * NW + 16 + 127) / 128 * 128;
+    const size_t ring_off = xs_off + ((size_t)D * sizeof(VecT) + 127) / 128 * 128;
+    const size_t smem = ring_off + (size_t)NW * NST * ST::BYTES;
+    if (smem > 227 * 1024 || (D * (int64_t)sizeof(VecT)) % 16 != 0 || D * (int64_t)sizeof(VecT) >= (1 << 20)) return probe_only ? 1 : fail(QBGPU_ERR_STATE, "block-local bulk product: block and rings do not fit in shared memory");
+    if (probe_only) return 0;
+    static size_t smem_set = 0;
+    if (smem_set < smem) { QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    const int64_t u_lo = A->row_lo / D, u_cnt = A->nrows() / D;
+    if (u_cnt == 0) return QBGPU_OK;
+    const int64_t cap = (int64_t)c.num_sms;                 // one CTA per SM
+    const int grid = (int)(u_cnt < cap ? u_cnt : cap);
+    kern<<<grid, NW * 32, smem, c.stream>>>(A->nrows(), A->row_lo, D, u_lo, u_cnt, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
+                                            (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc,
+                                            A->vdict, (uint32_t)xs_off, (uint32_t)ring_off);
+    QB_LAUNCH_COUNT();
+    QB_CUDA(cudaGetLastError());
+    return QBGPU_OK;
+}
+
 static int g_block_smem_variant = -1;
 void set_block_smem_variant(int v) { g_block_smem_variant = v; }
 
@@ -672,8 +906,13 @@ static int launch_block_smem_cfg(const qbgpu_matrix *A, const FusedArgs &a, int6
 template <typename ValT, typename VecT>
 static int launch_block_smem_typed(const qbgpu_matrix *A, const FusedArgs &a, int64_t D)
 {
+    // default 1: the register-fed kernel (2).  20 = the ring-fed kernel (3) with 24 warps x 2 stages x 6 diagonals where block +
+    // rings fit in shared memory, else (2): measured on BASELINE config 3 it is 2 % faster alone (7.72 against 7.89 ms,
+    // profiles/r02_block_bulk_sweep_hubbard4x4.txt) and a wash inside the whole product (16.61 against 16.66 ms), so the
+    // simpler kernel stays the default.  10..18: other ring shapes (tuning builds).
     if (g_block_smem_variant < 0) g_block_smem_variant = getenv("QBGPU_BLOCK_SMEM") ? atoi(getenv("QBGPU_BLOCK_SMEM")) : 1;
     switch (g_block_smem_variant) {
+    case 20: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 24, 2, 6>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 24, 2, 6>(A, a, D); break;
 #ifdef QBGPU_TUNING_VARIANTS
     case 2: return launch_block_smem_cfg<ValT, VecT, 1024, 4, 1>(A, a, D);
     case 3: return launch_block_smem_cfg<ValT, VecT, 512, 16, 1>(A, a, D);
@@ -682,8 +921,19 @@ static int launch_block_smem_typed(const qbgpu_matrix *A, const FusedArgs &a, in
     case 6: return launch_block_smem_cfg<ValT, VecT, 1024, 6, 1>(A, a, D);
 #endif
     case 7: return launch_block_smem_cfg<ValT, VecT, 1024, 8, 1>(A, a, D);
-    default: return launch_block_smem_cfg<ValT, VecT, 1024, 4, 1>(A, a, D);
+    // 10..: the stream through stage rings (kernel (3)); needs block + rings within 227 KB and no fused way in
+    case 10: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 8, 4, 8>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 8, 4, 8>(A, a, D); break;
+    case 11: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 12, 3, 8>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 12, 3, 8>(A, a, D); break;
+    case 12: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 16, 2, 8>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 16, 2, 8>(A, a, D); break;
+    case 13: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 8, 5, 6>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 8, 5, 6>(A, a, D); break;
+    case 14: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 16, 3, 4>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 16, 3, 4>(A, a, D); break;
+    case 15: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 8, 3, 10>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 8, 3, 10>(A, a, D); break;
+    case 16: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 32, 2, 4>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 32, 2, 4>(A, a, D); break;
+    case 17: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 24, 2, 6>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 24, 2, 6>(A, a, D); break;
+    case 18: if (!a.x_ref && launch_block_bulk_cfg<ValT, VecT, 20, 3, 4>(A, a, D, true) == 0) return launch_block_bulk_cfg<ValT, VecT, 20, 3, 4>(A, a, D); break;
+    default: break;
     }
+    return launch_block_smem_cfg<ValT, VecT, 1024, 4, 1>(A, a, D);
 }
 
 // Can the block-local kernel serve this handle?  (sliced-jagged layout, rows = whole blocks of D, block fits in shared memory)

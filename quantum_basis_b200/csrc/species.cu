@@ -1137,28 +1137,31 @@ int mv_species(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, void
                 QB_LAUNCH_COUNT();
                 QB_CUDA(cudaGetLastError());
             }
-            int h;
-            if (!use_beta) {
-                // y is not read: run the fp64 passes at once and look at the flag afterwards (the read-back then costs no idle
-                // time on the device); a vector with imaginary parts -- rare -- simply repeats the product on the complex route
-                // ... and the closing pass writes the reference's order itself (sjds_bulk.cu, OUT): the separate way out -- 0.9 ms
-                // of 17 on BASELINE config 3 -- is gone for 2 GB more traffic in pass 2
-                const bool fuse_out = !S->matfree && A->second && A->row_lo == 0 && A->row_hi == A->n && sjds_bulk_out_fusable(A->second);
+            // The closing pass can write the reference's order itself (sjds_bulk.cu, OUT) when y is not read: the separate way
+            // out -- 0.9 ms of 17 on BASELINE config 3 -- is gone for 2 GB more traffic in pass 2.
+            const bool fuse_out = !use_beta && !S->matfree && A->second && A->row_lo == 0 && A->row_hi == A->n && sjds_bulk_out_fusable(A->second);
+            auto real_route = [&]() -> int {
                 FusedArgs fa;
                 fa.x = px; fa.y = py;
                 if (fuse_out) { fa.y_ref = yd; fa.out_alpha = alpha; }
                 QB_TRY(launch_spmv(&R, fa));
                 if (!fuse_out) QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
+                return QBGPU_OK;
+            };
+            int h;
+            if (!use_beta && !A->last_x_had_imag) {
+                // y is not read: run the fp64 passes at once and look at the flag afterwards (the read-back then costs no idle
+                // time on the device); a vector with imaginary parts simply repeats the product on the complex route -- and
+                // the handle remembers it: the next call looks at the flag first (a caller with complex vectors pays the wasted
+                // passes once, not per product)
+                QB_TRY(real_route());
                 QB_TRY(read_flag(h));
+                A->last_x_had_imag = h != 0;
                 if (h != 0) QB_TRY(complex_route());
             } else {
                 QB_TRY(read_flag(h));
-                if (h == 0) {
-                    FusedArgs fa;
-                    fa.x = px; fa.y = py;
-                    QB_TRY(launch_spmv(&R, fa));
-                    QB_TRY(vec_from_native(A, false, true, py, yd, alpha, beta));
-                } else QB_TRY(complex_route());
+                A->last_x_had_imag = h != 0;
+                if (h == 0) QB_TRY(real_route()); else QB_TRY(complex_route());
             }
         }
     } else {
@@ -1231,7 +1234,7 @@ int qbgpu_row_view(qbgpu_matrix_t A, int64_t r0, int64_t r1, int64_t tile_period
     QB_TRY(ensure_init());
     if (!A || !view) return fail(QBGPU_ERR_ARG, "null argument");
     *view = nullptr;
-    if (A->sp || A->mf || A->format != QBGPU_FORMAT_SELL) return fail(QBGPU_ERR_STATE, "row_view: needs a stored sliced-jagged handle (a part of a species handle, a shard)");
+    if (A->sp || A->mf || A->mf_sec || A->format != QBGPU_FORMAT_SELL) return fail(QBGPU_ERR_STATE, "row_view: needs a stored sliced-jagged handle (a part of a species handle, a shard)");
     const int64_t nl = A->nrows();
     if (r0 < 0 || r1 < r0 || r1 > nl || r0 % 32 != 0 || (r1 % 32 != 0 && r1 != nl)) return fail(QBGPU_ERR_ARG, "row_view: the row range must consist of whole 32-row slices");
     if (A->slice_order && (tile_period <= 0 || r0 % tile_period != 0)) return fail(QBGPU_ERR_ARG, "row_view: a tile-ordered part must be cut at multiples of its tile period (D_dn)");

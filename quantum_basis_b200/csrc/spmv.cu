@@ -129,6 +129,7 @@ int launch_spmv(const qbgpu_matrix *A, const FusedArgs &a, int lanes_override)
         else if (A->device != dev) return fail(QBGPU_ERR_STATE, "this handle lives on device " + std::to_string(A->device) + " but the calling thread's context is bound to device " + std::to_string(dev) + " (qbgpu_init(device) in this thread)");
     }
     if (A->sp) return launch_spmv_species(A, a);             // two passes in the handle's internal order (species.cu)
+    if (A->mf_sec) return launch_spmv_sector_matfree(A, a);
     if (A->format == QBGPU_FORMAT_MATFREE) return launch_spmv_matfree(A, a);
     if (A->format == QBGPU_FORMAT_SELL) return launch_spmv_sjds(A, a);
     if (A->ndict) return fail(QBGPU_ERR_STATE, "dictionary-coded values need the sliced-jagged layout");

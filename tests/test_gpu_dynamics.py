@@ -87,3 +87,22 @@ def test_full_basis_dynamic_flow_matches_the_reference(name):
         g_ours = _continued_fraction(hess[maxit:maxit + mr], hess[:mr], w)
         g_ref = _continued_fraction(z["dyn_a"][:mr], z["dyn_b"][:mr], w)
         assert np.abs(g_ours - g_ref).max() <= 1e-3 * np.abs(g_ref).max(), kw
+
+
+def test_measure_vrnl_dynamic_is_the_references_dnmcs_run_on_an_uploaded_csr(oracle):
+    """measure_vrnl_dynamic (src/model.cc:2132-2143): norm, scale, lanczos(0, maxit-1, maxit, ..., "dnmcs") on a host-assembled
+    csr_mat.  The variational basis itself is host assembly; the flow from the uploaded matrix on is pinned to the reference's
+    dnmcs coefficients on the golden matrices (a start vector scaled by 3.7 must give the same coefficients and norm 3.7)."""
+    for name in ("heis16_k3", "hubbard4x2"):
+        A, meta, ex = oracle.load_golden(name)
+        M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+        x = oracle.vec_randomize(A.dim, 1) * 3.7
+        hess = np.zeros(120)
+        m, norm = qb.measure_vrnl_dynamic(x, M, 60, hess)
+        assert m == meta["dn_steps"] == 59
+        assert abs(norm - 3.7) < 1e-12
+        assert np.abs(hess[60:80] - ex["dn_a"][:20]).max() < 1e-11
+        assert np.abs(hess[:20] - ex["dn_b"][:20]).max() < 1e-11
+    hess = np.zeros(120)
+    m, norm = qb.measure_vrnl_dynamic(np.zeros(A.dim, dtype=np.complex128), M, 60, hess)       # src/model.cc:2140: nothing to do
+    assert m == 0 and norm == 0.0 and not hess.any()

@@ -708,6 +708,48 @@ def test_device_sector_real_momenta_are_stored_as_fp64_and_config2_style_sector_
     assert abs(E[0] / 24 - (-0.4438)) < 2e-3         # Bethe-ansatz energy density -ln2 + 1/4 up to finite-size corrections
 
 
+@pytest.mark.parametrize("L,ndown,k,bonds", [([16], 8, [3], "chain"), ([12], 6, [0], "chain"), ([4, 4], 8, [1, 2], "tri"),
+                                             ([4, 4], 8, [2, 2], "tri"), ([6, 2], 6, [3, 1], "tri")])
+def test_matrix_free_sector_product_equals_the_stored_sector_matrix(L, ndown, k, bonds):
+    """model<T>::MultMv / MultMv2 with matrix_free == true, repr branch (src/model.cc:1016-1107): rows regenerated inside the
+    product -- against the stored handle of the same sector (which is the reference's matrix bit for bit, tests above), sectors
+    with zero-norm representatives (their fake diagonal, :1022-1025) included; then MultMv2's accumulate form and the fused loops."""
+    import repr_builders as R
+    bl = R.chain_bonds(L[0]) if bonds == "chain" else R.triangular_bonds(*L)
+    sec = qb.Sector(L, ndown, k)
+    Hs, Hf = sec.heisenberg(bl, flags=1), sec.heisenberg_matrix_free(bl)
+    n = sec.dim
+    assert Hf.dim == n and Hf.info.nnz_stored == 0
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    ys, yf = np.zeros(n, dtype=np.complex128), np.zeros(n, dtype=np.complex128)
+    Hs.MultMv(x, ys); Hf.MultMv(x, yf)
+    assert rel_l2(yf, ys) < TOL_MV
+    y0 = rng.normal(size=n) + 1j * rng.normal(size=n)
+    y2 = y0.copy()
+    Hf.MultMv2(x, y2)
+    assert rel_l2(y2, y0 + ys) < TOL_MV
+    if n > 40:
+        Es = qb.locate_E0_lanczos(Hs, nev=1, ncv=0)["eigenvals"][0]
+        Ef = qb.locate_E0_lanczos(Hf, nev=1, ncv=0)["eigenvals"][0]
+        assert abs(Es - Ef) <= TOL_E0 * abs(Es)
+    del Hf, Hs
+    sec.free()
+
+
+def test_matrix_free_sector_reaches_the_published_E0(oracle):
+    """The k=3 sector of the L=16 chain without a stored matrix: E0 of the reference's example
+    (examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_half.cc:102-117)."""
+    A, meta, ex = oracle.load_golden("heis16_k3")
+    sec = qb.Sector([16], 8, [3])
+    Hf = sec.heisenberg_matrix_free(_sector_bonds([16]))
+    y = np.zeros(A.dim, dtype=np.complex128)
+    Hf.MultMv(oracle.vec_randomize(A.dim, 1), y)
+    assert rel_l2(y, ex["y1"]) < TOL_MV                      # y1 = the compiled reference's csr_mat::MultMv on vec_randomize(seed 1)
+    E = qb.locate_E0_lanczos(Hf, nev=1, ncv=0)["eigenvals"]
+    assert abs(E[0] - meta["golden_E0"]) < 1e-8
+
+
 # ------------------------------------------------------------------ S^z_q between momentum sectors + dnmcs Lanczos (config 5)
 def _dyn_golden(name):
     import json

@@ -254,28 +254,35 @@ static int dist_product(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbg
     return QBGPU_OK;
 }
 
-// Lanczos step a over the same sequence of parts (first: w = sx*H*ux - b*sz*uz; others accumulate; last: the partial <v, w>)
-static int dist_lanczos_step_a(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, int bx, void *uz, double *state, bool pulls_issued)
+// Lanczos step a over the same sequence of parts (first: w = sx*H*ux - b*sz*uz; others accumulate; last: the partial <v, w>).
+// `w`: where the product goes -- uz itself (in place) or a scratch vector of the rank's rows.  With a scratch vector the EARLY
+// parts (they need no remote data) can be launched before the host knows whether there is a next step: a step that does not
+// happen leaves the exchange buffers untouched.  phase 0: the whole step; 1: only the early parts (no pulls, no waits);
+// 2: the rest of a step whose early parts and pulls have been issued.
+static int dist_lanczos_step_a(qbgpu_dist *D, const qbgpu_matrix *local_part, const qbgpu_matrix *rest, int bx, void *uz, void *w, double *state,
+                               bool pulls_issued, int phase = 0)
 {
-    if (!pulls_issued) QB_TRY(dist_pull_mark(D));
+    if (!pulls_issued && phase != 1) QB_TRY(dist_pull_mark(D));
     std::vector<const qbgpu_matrix *> seq;
     size_t n_early = 0;
     dist_sequence(D, local_part, rest, seq, n_early);
+    void *w_out = (w && w != uz) ? w : nullptr;
     bool pulled = pulls_issued, waited = false;
-    for (size_t i = 0; i < seq.size(); i++) {
+    for (size_t i = (phase == 2 ? n_early : 0); i < (phase == 1 ? n_early : seq.size()); i++) {
         if (i >= n_early) {
             if (!pulled) { QB_TRY(dist_pull(D, bx)); pulled = true; }
             QB_TRY(dist_wait_for_late(D, i - n_early, waited));
         }
         const bool last = i + 1 == seq.size() && !D->row_views;
-        QB_TRY(lanczos_step_a(seq[i], D->X(bx), part_rows(D, seq[i], uz), state, i == 0, last));
-        if (i + 1 == n_early && !pulled) { QB_TRY(dist_pull(D, bx)); pulled = true; }
+        QB_TRY(lanczos_step_a(seq[i], D->X(bx), part_rows(D, seq[i], uz), state, i == 0, last, w_out ? part_rows(D, seq[i], w_out) : nullptr));
+        if (phase == 0 && i + 1 == n_early && !pulled) { QB_TRY(dist_pull(D, bx)); pulled = true; }
     }
+    if (phase == 1) return QBGPU_OK;
     if (!pulled) QB_TRY(dist_pull(D, bx));
     if (!waited) QB_TRY(dist_wait(D));
     if (D->row_views) {                                     // state[3] = sx * Re <ux_own, w> over the rank's rows, in a pass of its own
         const int64_t nl = D->nloc();
-        if (nl) QB_TRY(vec_dotc_scaled(nl, D->cplx, D->own(bx), uz, state + 3, state + 0));
+        if (nl) QB_TRY(vec_dotc_scaled(nl, D->cplx, D->own(bx), w_out ? w_out : uz, state + 3, state + 0));
         else QB_CUDA(cudaMemsetAsync(state + 3, 0, sizeof(double), ctx().stream));
     }
     return QBGPU_OK;
@@ -542,6 +549,20 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
     int cnt_accuE0 = 0;
     double theta0_prev = 0.0;
     int64_t m = 0;
+    // Speculation (QBGPU_DIST_SPECULATE=0: off): the product of a step goes to a scratch vector w, step b writes uz = w - a v.
+    // The early parts of step m+1 (they read only the rank's own rows of the new vector) are then launched BEFORE the host has
+    // read (a_m, b_{m+1}) back and evaluated the stop rule: the device works through the read-back, the O(m) Ritz solve and
+    // the enqueueing of the next step's transfers (0.4 ms of 2.9 per step on eight GPUs: profiles/r02_dist_lanczos_phases_n8.txt)
+    // instead of idling.  A step that does not happen only wrote w.
+    const bool speculate = !(getenv("QBGPU_DIST_SPECULATE") && atoi(getenv("QBGPU_DIST_SPECULATE")) == 0);
+    void *w = nullptr;
+    cudaEvent_t ev_ab = nullptr;
+    if (speculate && nloc) {
+        if (cudaMalloc(&w, D->esize * (size_t)nloc) != cudaSuccess) return done(cuda_fail(cudaGetLastError(), "dist_lanczos: scratch vector", __FILE__, __LINE__));
+        if (cudaEventCreateWithFlags(&ev_ab, cudaEventDisableTiming) != cudaSuccess) { cudaFree(w); return done(cuda_fail(cudaGetLastError(), "dist_lanczos: event", __FILE__, __LINE__)); }
+    }
+    auto done2 = [&](int rc) { if (ev_ab) { cudaStreamSynchronize(c.stream); cudaEventDestroy(ev_ab); } cudaFree(w); return done(rc); };
+    bool early_issued = false;                              // the early parts of the coming step are already in the stream
     // QBGPU_VERBOSE: device time of the phases of a step (events on the compute stream) and host time between the steps
     const bool prof = getenv("QBGPU_VERBOSE") != nullptr;
     cudaEvent_t pe[6] = {};
@@ -552,27 +573,35 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
         m++;
         const int bx = (int)((m - 1) % 2), bz = (int)(m % 2);
         void *uz = D->own(bz);
-        // step a: w = sx*H*ux - b*sz*uz into uz; state[3] = partial <v, w>
+        // step a: w = sx*H*ux - b*sz*uz (into the scratch vector, or over uz); state[3] = partial <v, w>
         rec(0);
-        if (int rc = dist_lanczos_step_a(D, local_part, rest, bx, uz, state, /*pulls_issued=*/m > 1)) return done(rc);
+        if (int rc = dist_lanczos_step_a(D, local_part, rest, bx, uz, w, state, /*pulls_issued=*/m > 1, early_issued ? 2 : 0)) return done2(rc);
+        early_issued = false;
         rec(1);
-        if (int rc = dist_allreduce(D, state + 3, 1)) return done(rc);
+        if (int rc = dist_allreduce(D, state + 3, 1)) return done2(rc);
         rec(2);
-        if (int rc = lanczos_step_b(nloc, cplx, D->own(bx), uz, state)) return done(rc);
+        if (int rc = lanczos_step_b(nloc, cplx, D->own(bx), uz, state, w)) return done2(rc);
         rec(3);
-        if (int rc = dist_allreduce(D, state + 6, 1)) return done(rc);      // also the barrier that makes X[bz] final everywhere
+        if (int rc = dist_allreduce(D, state + 6, 1)) return done2(rc);      // also the barrier that makes X[bz] final everywhere
         rec(4);
-        // the slices of the NEXT step's vector (unnormalised: its scale travels as a scalar) are final now: start fetching
-        // them before the host reads the coefficients back and decides whether there is a next step (if not: harmless)
-        if (m < np) { if (int rc = dist_pull_mark(D)) return done(rc); if (int rc = dist_pull(D, bz)) return done(rc); }
-        if (int rc = lanczos_step_c(state, a_dev, b_dev, m)) return done(rc);
+        if (int rc = lanczos_step_c(state, a_dev, b_dev, m)) return done2(rc);
         cudaMemcpyAsync(c.scal_host, a_dev + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, c.stream);
         cudaMemcpyAsync(c.scal_host + 1, b_dev + m, sizeof(double), cudaMemcpyDeviceToHost, c.stream);
-        if (cudaStreamSynchronize(c.stream) != cudaSuccess) return done(cuda_fail(cudaGetLastError(), "dist_lanczos: step", __FILE__, __LINE__));
+        if (ev_ab) cudaEventRecord(ev_ab, c.stream);
+        rec(5);
+        // the slices of the NEXT step's vector (unnormalised: its scale travels as a scalar) are final now: start fetching
+        // them -- and, with the scratch vector, multiplying by the early parts -- before the host reads the coefficients back
+        // and decides whether there is a next step (if not: harmless)
+        if (m < np) {
+            if (int rc = dist_pull_mark(D)) return done2(rc);
+            if (w) { if (int rc = dist_lanczos_step_a(D, local_part, rest, bz, D->own(bx), w, state, true, 1)) return done2(rc); early_issued = true; }
+            if (int rc = dist_pull(D, bz)) return done2(rc);
+        }
+        if ((ev_ab ? cudaEventSynchronize(ev_ab) : cudaStreamSynchronize(c.stream)) != cudaSuccess) return done2(cuda_fail(cudaGetLastError(), "dist_lanczos: step", __FILE__, __LINE__));
         hess[maxit + m - 1] = c.scal_host[0];
         hess[m] = c.scal_host[1];
         if (prof) {
-            cudaEventRecord(pe[5], c.stream); cudaEventSynchronize(pe[5]);
+            cudaEventSynchronize(pe[5]);
             for (int i = 0; i < 5; i++) { float f = 0; cudaEventElapsedTime(&f, pe[i], pe[i + 1]); tph[i] += f; }
         }
         if (m == 1) continue;
@@ -584,7 +613,7 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
                 if (accu_E0 < kLanczosPrecisionD) cnt_accuE0++; else cnt_accuE0 = 0;
                 if (cnt_accuE0 > 15) {
                     double s_last = 0.0;
-                    if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return done(fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge"));
+                    if (hess_eigen_host(hess, maxit, m, ritz.data(), nullptr, &s_last)) return done2(fail(QBGPU_ERR_NUMERIC, "hess_eigen: QL did not converge"));
                     if (fabs(hess[m] * s_last) < kLanczosPrecisionD) break;
                 }
             }
@@ -597,14 +626,14 @@ int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t
                                   (long long)m, D->world, tph[0] / m, tph[1] / m, tph[2] / m, tph[3] / m, tph[4] / m);
         for (auto &e : pe) cudaEventDestroy(e);
     }
-    if (int rc = dist_wait(D)) return done(rc);             // (a fetch started for a step that did not happen)
+    if (int rc = dist_wait(D)) return done2(rc);             // (a fetch started for a step that did not happen)
     // hand the two live vectors back normalised (their scales live in state[0], state[1])
     if (nloc) {
-        if (int rc = scale_copy(nloc, cplx, state + 0, 1.0, D->own((int)(m % 2)), D->own((int)(m % 2)))) return done(rc);
-        if (int rc = scale_copy(nloc, cplx, state + 1, 1.0, D->own((int)((m - 1) % 2)), D->own((int)((m - 1) % 2)))) return done(rc);
+        if (int rc = scale_copy(nloc, cplx, state + 0, 1.0, D->own((int)(m % 2)), D->own((int)(m % 2)))) return done2(rc);
+        if (int rc = scale_copy(nloc, cplx, state + 1, 1.0, D->own((int)((m - 1) % 2)), D->own((int)((m - 1) % 2)))) return done2(rc);
     }
-    if (int rc = dist_allreduce(D, D->scal + 8, 0)) return done(rc);
-    return done(dist_timed_out(D, "dist_lanczos"));
+    if (int rc = dist_allreduce(D, D->scal + 8, 0)) return done2(rc);
+    return done2(dist_timed_out(D, "dist_lanczos"));
 }
 
 /* energy_scale of src/kpm.cc:45-88 on the shards: iters-1 Lanczos steps from vec_randomize(seed 1), bounds widened by extend. */

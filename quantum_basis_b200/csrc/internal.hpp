@@ -149,7 +149,7 @@ int vec_dotc_scaled(int64_t n, bool cplx, const void *x, const void *y, double *
 int vec_nrm2sq(int64_t n, bool cplx, const void *x, double *out_dev);
 // Lanczos step a on one (block of a) handle: w = sx*H*ux - b*sz*uz (first) or w += sx*H_p*ux (later blocks) written to uz;
 // when `last`, state[3] = sum Re conj(sx*ux_i) w_i over the local rows.
-int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last);
+int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last, void *w_out = nullptr);   // w_out: the product goes there instead of over uz (dist.cu: speculative early parts)
 int vec_axpy(int64_t n, bool cplx, double2 a, const void *x, void *y);
 int vec_scal(int64_t n, bool cplx, double2 a, void *x);
 int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed);
@@ -157,7 +157,7 @@ int read_scalars(const double *dev, double *host, int count);   // stream-ordere
 int vec_imag_norm2(int64_t n, const void *x, double *out_dev);
 int vec_take_real(int64_t n, const void *cplx_in, double *real_out);
 int vec_put_real(int64_t n, const double *real_in, void *cplx_out);
-int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state);
+int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state, const void *w_in = nullptr);                    // w_in: uz = w_in - a*sx*ux (out of place)
 int lanczos_step_c(double *state, double *a_dev, double *b_dev, int64_t m);
 int cg_update_vr(int64_t n, bool cplx, const double *sc, void *v, void *r, const void *p, const void *pp);
 int cg_update_p(int64_t n, bool cplx, double *sc, const void *r, void *p);

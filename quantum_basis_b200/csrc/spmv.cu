@@ -328,10 +328,11 @@ static int mv_any(qbgpu_matrix *A, double2 alpha, const void *x, double2 beta, v
     return launch_spmv(A, a);
 }
 
-int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last)
+int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, double *state, bool first, bool last, void *w_out)
 {
     FusedArgs a;
     a.x = ux_full; a.z = uz_local; a.y = uz_local;
+    if (w_out) { a.y = w_out; if (!first) a.z = w_out; }   // the opening part reads uz and writes w; the others accumulate into w
     a.scal_mode = first ? 1 : 2; a.sc = state;
     a.beta = make_double2(1.0, 0.0);                       // placeholder: the kernel derives beta from the state
     // complex vectors: the dot rides in the product's epilogue (+0.5 ms on BASELINE config 3).  fp64 vectors: the
@@ -341,7 +342,7 @@ int lanczos_step_a(const qbgpu_matrix *A, const void *ux_full, void *uz_local, d
     a.dots = (last && fuse_dot) ? state + 3 : nullptr;     // state[3]=alpha partial, [4]=Im (unused), [5]=|w|^2 (unused)
     QB_TRY(launch_spmv(A, a));
     if (last && !fuse_dot)
-        QB_TRY(vec_dotc_scaled(A->nrows(), false, (const double *)ux_full + A->row_lo, uz_local, state + 3, state + 0));
+        QB_TRY(vec_dotc_scaled(A->nrows(), false, (const double *)ux_full + A->row_lo, w_out ? w_out : uz_local, state + 3, state + 0));
     return QBGPU_OK;
 }
 

@@ -200,7 +200,7 @@ int vec_randomize(int64_t n, bool cplx, void *x, uint32_t seed)
 // state: [0]=sx [1]=sz [2]=b_prev [3]=alpha [4],[5] scratch [6]=norm2 [7] spare  (see include/qbgpu.h)
 // step b: w' = uz - alpha*sx*ux -> uz ; state[6] = sum |w'|^2   (reference: axpy + nrm2, src/lanczos.cc:206-208)
 template <typename VecT>
-__global__ void __launch_bounds__(kVBlock, 4) lanczos_b_kernel(int64_t n, const VecT *__restrict__ ux, VecT *uz, double *state,
+__global__ void __launch_bounds__(kVBlock, 4) lanczos_b_kernel(int64_t n, const VecT *__restrict__ ux, const VecT *win, VecT *uz, double *state,
                                                                double *partials, unsigned *ticket)
 {
     using VT = VecTraits<VecT>;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kVBlock, 4) lanczos_b_kernel(int64_t n, const 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
         VecT w[4], v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int64_t j = i + k * stride; if (j < n) { w[k] = uz[j]; v[k] = ux[j]; } }
+        for (int k = 0; k < 4; k++) { const int64_t j = i + k * stride; if (j < n) { w[k] = win[j]; v[k] = ux[j]; } }      // (win == uz: in place)
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int64_t j = i + k * stride;
@@ -234,11 +234,12 @@ __global__ void lanczos_c_kernel(double *state, double *a_dev, double *b_dev, in
     state[2] = b;
 }
 
-int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state)
+int lanczos_step_b(int64_t nloc, bool cplx, const void *ux_local, void *uz_local, double *state, const void *w_in)
 {
     Context &c = ctx();
-    if (cplx) LAUNCH_V(lanczos_b_kernel<double2>, nloc, nloc, (const double2 *)ux_local, (double2 *)uz_local, state, c.partials, c.ticket);
-    else      LAUNCH_V(lanczos_b_kernel<double>, nloc, nloc, (const double *)ux_local, (double *)uz_local, state, c.partials, c.ticket);
+    if (!w_in) w_in = uz_local;
+    if (cplx) LAUNCH_V(lanczos_b_kernel<double2>, nloc, nloc, (const double2 *)ux_local, (const double2 *)w_in, (double2 *)uz_local, state, c.partials, c.ticket);
+    else      LAUNCH_V(lanczos_b_kernel<double>, nloc, nloc, (const double *)ux_local, (const double *)w_in, (double *)uz_local, state, c.partials, c.ticket);
     return QBGPU_OK;
 }
 int lanczos_step_c(double *state, double *a_dev, double *b_dev, int64_t m)

@@ -51,6 +51,8 @@ def main():
         nonlocal ok
         ok = ok and bool(cond)
         out[name] = detail if cond else {"FAILED": detail}
+        if not cond:
+            print(f"[dist_native_check] rank {rank}: {name} FAILED: {detail}", file=sys.stderr, flush=True)
 
     # ------------------------------------------------------------------ species-order shards, fp64 and complex vectors
     n = L.qbgpu_dim_hubbard(ns, nup, ndn)

@@ -368,6 +368,16 @@ int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbond
  * The handle borrows the sector's device tables: destroy it before the sector. */
 int qbgpu_sector_matfree_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J,
                                     double fake_pos);
+/* A (N_up, N_dn, momentum) sector of single-orbital electrons on an untilted lattice of at most 16 sites -- fill_Weisse_table +
+ * enumerate_basis_repr (src/model.cc:205-249, 275-487) for the reference's "electron" orbital (src/basis.cc:49-96: two bits per
+ * site, bit 0 up, bit 1 down; qbgpu_sector_states returns these patterns).  Same representatives, row order and norms as the
+ * reference, the fermionic translation signs included (src/basis.cc:593-620, 2134-2147). */
+int qbgpu_sector_create_electron(qbgpu_sector_t *S, int dim, const int32_t *L, int nup, int ndn, const int32_t *k);
+/* generate_Ham_sparse_repr (src/model.cc:688-836) for H = -t sum_hops c+_{to,s} c_{from,s} + U sum_i n_up,i n_dn,i on such a sector.
+ * hops[3*nhops] = (to, from, spin) DIRECTED, in the order of the caller's add_Ham calls (they are re-ordered like
+ * mopr::operator+= does, src/operators.cc:901-925).  Bit-identical to the reference's csr_mat on 4x2 and 4x3 clusters. */
+int qbgpu_sector_build_hubbard(qbgpu_sector_t S, qbgpu_matrix_t *A, int nhops, const int32_t *hops, double t, double U,
+                               double fake_pos, int flags);
 /* model::moprXvec_repr (src/model.cc:1716-1846) for A = sum_r c_r S^z_r (coef_reim[2*nsites], site order): device
  * vectors x_old (sector S_old) -> y_new (sector S_new, same lattice and Sz, momentum shifted by the operator's q).
  * With measure_repr_dynamic's normalisation and qbgpu_lanczos_z(..., "dnmcs") this is src/model.cc:1897-1912. */

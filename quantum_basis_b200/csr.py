@@ -408,6 +408,33 @@ class Sector:
             pass
 
 
+class ElectronSector(Sector):
+    """One (N_up, N_dn, momentum) sector of single-orbital electrons on an untilted lattice (at most 16 sites): the device
+    counterpart of model::fill_Weisse_table + enumerate_basis_repr for the reference's "electron" orbital (two bits per site,
+    bit 0 up, bit 1 down), fermionic translation signs included (src/basis.cc:593-620, 2134-2147).  `hubbard()` assembles
+    generate_Ham_sparse_repr's matrix (src/model.cc:688-836) for the Hubbard model directly in HBM -- the momentum-resolved
+    flow of examples/trans_symmetric/latt_square/square_Fermi_Hubbard.cc."""
+
+    def __init__(self, L, nup, ndn, momentum):
+        La = np.ascontiguousarray(L, dtype=np.int32)
+        ka = np.ascontiguousarray(momentum, dtype=np.int32)
+        if La.size != ka.size:
+            raise QbgpuError("momentum needs one integer per lattice direction")
+        self._h = C.c_void_p()
+        check(lib().qbgpu_sector_create_electron(C.byref(self._h), int(La.size), C.c_void_p(La.ctypes.data), int(nup), int(ndn), C.c_void_p(ka.ctypes.data)))
+        info = _lib.SectorInfo()
+        check(lib().qbgpu_sector_get_info(self._h, C.byref(info)))
+        self.dim, self.zero_norm, self.nsites, self.lin_order = info.dim, info.zero_norm, info.nsites, bool(info.lin_order)
+        self.enumerate_seconds, self.norms_seconds = info.enumerate_seconds, info.norms_seconds
+
+    def hubbard(self, hops, t=1.0, U=1.1, fake_pos=100.0, flags=0):
+        """hops: directed (to, from, spin) triples in the order of the caller's add_Ham calls."""
+        h3 = np.ascontiguousarray(np.asarray(hops, dtype=np.int32).reshape(-1, 3))
+        h = C.c_void_p()
+        check(lib().qbgpu_sector_build_hubbard(self._h, C.byref(h), int(h3.shape[0]), C.c_void_p(h3.ctypes.data), float(t), float(U), float(fake_pos), flags))
+        return csr_mat._adopt(h, True)
+
+
 def measure_repr_dynamic(coef, sec_old, sec_new, mat_new, phi0, maxit, hessenberg, op="sz"):
     """model<T>::measure_repr_dynamic (src/model.cc:1897-1912) for A = sum_r coef[r] S^z_r (op="sz"), S^-_r ("s-") or
     S^+_r ("s+"), everything on the device: vec = A phi0 mapped into sec_new (moprXvec_repr), norm = |vec|, then

@@ -58,6 +58,10 @@ struct SecDev {                        // passed to kernels by value
     uint8_t fwd_swap[kMaxTrans], fwd_ja[kMaxTrans], fwd_jb[kMaxTrans];   // T_i (a,b)
     uint8_t inv_swap[kMaxTrans], inv_ja[kMaxTrans], inv_jb[kMaxTrans];   // T_i^{-1} (a,b)
     uint8_t bad[kMaxTrans];            // k.t not an integer: a stabiliser t kills the norm
+    // single-orbital electrons (two bits per site: bit 0 up, bit 1 down; nsub then counts the BITS of a half state):
+    int electron;
+    int16_t kt[kMaxTrans];             // k.t in units of 1/N
+    const uint16_t *invmask;           // [ntrans][16]  invmask[i*16 + s1] = sites s2 > s1 that translation i moves in front of s1
 };
 
 __host__ __device__ __forceinline__ uint32_t spread_bits(uint32_t x)
@@ -77,6 +81,31 @@ __host__ __device__ __forceinline__ uint32_t squeeze_bits(uint32_t x)
     x = (x | (x >> 4)) & 0x00FF00FFu;
     x = (x | (x >> 8)) & 0x0000FFFFu;
     return x;
+}
+
+// two-bit digits: half digit t -> parent digit 2t (even half) / 2t+1 (odd half)
+__host__ __device__ __forceinline__ uint32_t spread_digits(uint32_t x)
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t squeeze_digits(uint32_t x)
+{
+    x &= 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+template <class SD> __device__ __forceinline__ uint32_t sec_zip(const SD &S, uint32_t a, uint32_t b)
+{ return S.electron ? (spread_digits(a) | (spread_digits(b) << 2)) : (spread_bits(a) | (spread_bits(b) << 1)); }
+template <class SD> __device__ __forceinline__ void sec_unzip(const SD &S, uint32_t st, uint32_t &a, uint32_t &b)
+{
+    if (S.electron) { a = squeeze_digits(st); b = squeeze_digits(st >> 2); }
+    else { a = squeeze_bits(st); b = squeeze_bits(st >> 1); }
 }
 
 __device__ __forceinline__ void sec_move(const SecDev &S, int swap, int ja, int jb, uint32_t a, uint32_t b, uint32_t &ao, uint32_t &bo)
@@ -102,12 +131,12 @@ __device__ __forceinline__ int sec_canon(const SecDev &S, uint32_t a, uint32_t b
 
 __device__ __forceinline__ uint32_t sec_key(const SecDev &S, uint32_t a, uint32_t b)
 {
-    return S.lin_order ? ((b << S.nsub) | a) : (spread_bits(a) | (spread_bits(b) << 1));
+    return S.lin_order ? ((b << S.nsub) | a) : sec_zip(S, a, b);
 }
 __device__ __forceinline__ void sec_halves(const SecDev &S, uint32_t key, uint32_t &a, uint32_t &b)
 {
     if (S.lin_order) { a = key & ((1u << S.nsub) - 1u); b = key >> S.nsub; }
-    else { a = squeeze_bits(key); b = squeeze_bits(key >> 1); }
+    else sec_unzip(S, key, a, b);
 }
 __device__ __forceinline__ int64_t sec_lookup(const SecDev &S, uint32_t key)
 {
@@ -186,7 +215,174 @@ __global__ void __launch_bounds__(kSBlock) sec_states_kernel(SecDev S, uint32_t 
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
         uint32_t a, b;
         sec_halves(S, S.keys[r], a, b);
-        out[r] = spread_bits(a) | (spread_bits(b) << 1);
+        out[r] = sec_zip(S, a, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ single-orbital electrons
+// The Weisse tables compare bit patterns, so representatives, distances and the basis order are found exactly as for spins
+// (two bits per site instead of one); what fermions add (tests/repr_builders_fermion.py pins this against the compiled reference):
+//   * a translation permutes the singly occupied sites and picks up the parity of that permutation
+//     (mbasis_elem::transform, src/basis.cc:593-620);
+//   * norm_trans_repr (src/basis.cc:2134-2147): a stabiliser t needs k.t + sgn_t/2 integer;
+//   * generate_Ham_sparse_repr (src/model.cc:815-820): the element carries (-1)^sgn of the translation that maps the
+//     representative onto the state the hopping term produced.
+__device__ __forceinline__ int el_trans_sign(const SecDev &S, uint32_t st, int i)
+{
+    const uint32_t m = squeeze_bits(st ^ (st >> 1));                    // singly occupied sites
+    int sg = 0;
+    for (uint32_t r = m; r; r &= r - 1) sg += __popc(m & S.invmask[i * 16 + (__ffs(r) - 1)]);
+    return sg & 1;
+}
+
+__global__ void __launch_bounds__(kSBlock) el_flag_kernel(SecDev S, const uint16_t *__restrict__ reps, int nreps, int nup, int ndn, int64_t ncand,
+                                                          uint8_t *flag)
+{
+    const uint32_t MU = 0x5555u;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(c / nreps), a = reps[c % nreps];
+        uint8_t ok = 0;
+        if (__popc(a & MU) + __popc(b & MU) == nup && __popc((a >> 1) & MU) + __popc((b >> 1) & MU) == ndn && a <= S.rep[b]) {
+            ok = 1;
+            const int db = S.dist[b];
+            for (int i = 0; i < S.ntrans; i++) {
+                uint32_t ai, bb;
+                sec_move(S, S.inv_swap[i], S.inv_ja[i], S.inv_jb[i], a, b, ai, bb);
+                if (ai == a && (int)S.dist[bb] < db) { ok = 0; break; }
+            }
+        }
+        flag[c] = ok;
+    }
+}
+
+__global__ void __launch_bounds__(kSBlock) el_lin_to_zip_kernel(int64_t n, int nsub, uint32_t *keys)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        keys[i] = spread_digits(k & ((1u << nsub) - 1u)) | (spread_digits(k >> nsub) << 2);
+    }
+}
+
+__global__ void __launch_bounds__(kSBlock) el_norm_kernel(SecDev S, double *nu, unsigned long long *zero_count)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t a, b;
+        sec_halves(S, S.keys[r], a, b);
+        const uint32_t st = sec_zip(S, a, b);
+        int cnt = 0, bad = 0;
+        for (int i = 0; i < S.ntrans; i++) {
+            uint32_t ai, bb;
+            sec_move(S, S.fwd_swap[i], S.fwd_ja[i], S.fwd_jb[i], a, b, ai, bb);
+            if (ai == a && bb == b) {
+                cnt++;
+                if (((int)S.kt[i] + el_trans_sign(S, st, i) * (S.nsites / 2)) % S.nsites != 0) bad = 1;
+            }
+        }
+        const double v = bad ? 0.0 : (double)(S.ntrans / cnt);
+        nu[r] = v;
+        if (bad) atomicAdd(zero_count, 1ull);
+    }
+}
+
+constexpr int kMaxHops = 256;
+struct ElTerms {
+    int nterms;
+    double t, U, fake_pos;
+    uint8_t to[kMaxHops], from[kMaxHops], sp[kMaxHops];      // directed hops c+_{to,sp} c_{from,sp} in the order of mopr::operator+=
+};
+
+__device__ __forceinline__ bool el_hop(uint32_t st, int to, int from, int sp, uint32_t &s2, int &sg)
+{
+    const uint32_t bf = 1u << (2 * from + sp), bt = 1u << (2 * to + sp);
+    if (!(st & bf) || (st & bt)) return false;
+    sg = __popc(st & ((1u << (2 * from)) - 1u)) & 1;                   // oprXphi's sign rule, src/basis.cc:2717-2731
+    if (sp) sg ^= (st >> (2 * from)) & 1u;
+    const uint32_t s1 = st ^ bf;
+    sg ^= __popc(s1 & ((1u << (2 * to)) - 1u)) & 1;
+    if (sp) sg ^= (s1 >> (2 * to)) & 1u;
+    s2 = s1 ^ bt;
+    return true;
+}
+
+// upper bound of the stored row length: the diagonal plus one entry per applicable hop
+__global__ void __launch_bounds__(kSBlock) el_cap_kernel(SecDev S, const ElTerms *Tp, int64_t *cap)
+{
+    __shared__ ElTerms T;
+    for (int i = threadIdx.x; i < (int)(sizeof(ElTerms) / 4); i += blockDim.x) ((int *)&T)[i] = ((const int *)Tp)[i];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= S.n; r += (int64_t)gridDim.x * blockDim.x) {
+        int c = 0;
+        if (r < S.n) {
+            c = 1;
+            if (S.nu[r] != 0.0) {
+                uint32_t a, b;
+                sec_halves(S, S.keys[r], a, b);
+                const uint32_t st = sec_zip(S, a, b);
+                for (int t = 0; t < T.nterms; t++) {
+                    const uint32_t bf = 1u << (2 * T.from[t] + T.sp[t]), bt = 1u << (2 * T.to[t] + T.sp[t]);
+                    c += ((st & bf) && !(st & bt)) ? 1 : 0;
+                }
+            }
+        }
+        cap[r] = c;
+    }
+}
+
+// generate_Ham_sparse_repr (src/model.cc:688-836) for H = -t sum c+c + U sum n_up n_dn, upper triangle, lil_mat::add's rule
+__global__ void __launch_bounds__(kSBlock) el_rows_kernel(SecDev S, const ElTerms *Tp, const double2 *__restrict__ phase,
+                                                          const int64_t *__restrict__ start, int64_t *row_end, int64_t *ocol, double2 *oval)
+{
+    __shared__ ElTerms T;
+    for (int i = threadIdx.x; i < (int)(sizeof(ElTerms) / 4); i += blockDim.x) ((int *)&T)[i] = ((const int *)Tp)[i];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S.n; r += (int64_t)gridDim.x * blockDim.x) {
+        int64_t *col = ocol + start[r];
+        double2 *val = oval + start[r];
+        const double nu_i = S.nu[r];
+        if (nu_i == 0.0) {                                             // src/model.cc:737-740
+            col[0] = r; val[0] = make_double2(__dadd_rn(T.fake_pos, __ddiv_rn((double)r, (double)S.n)), 0.0);
+            row_end[r] = start[r] + 1;
+            continue;
+        }
+        uint32_t a, b;
+        sec_halves(S, S.keys[r], a, b);
+        const uint32_t st = sec_zip(S, a, b);
+        const int ndbl = __popc(st & (st >> 1) & 0x55555555u);
+        double dg = 0.0;
+        for (int q = 0; q < ndbl; q++) dg = __dadd_rn(dg, T.U);
+        int len = 1;
+        col[0] = r; val[0] = make_double2(dg, 0.0);
+        for (int t = 0; t < T.nterms; t++) {
+            uint32_t s2;
+            int sg;
+            if (!el_hop(st, T.to[t], T.from[t], T.sp[t], s2, sg)) continue;
+            uint32_t a2, b2, ca = 0, cb = 0;
+            sec_unzip(S, s2, a2, b2);
+            const int i = sec_canon(S, a2, b2, ca, cb);
+            if (i < 0) continue;
+            const int64_t j = sec_lookup(S, sec_key(S, ca, cb));
+            if (j < r) continue;                                       // upper triangle (and j = -1: not in the sector)
+            const double nu_j = S.nu[j];
+            if (nu_j == 0.0) continue;
+            const double amp = sg ? T.t : -T.t;                        // (-t) * (-1)^sg
+            const double x = __dmul_rn(__dsqrt_rn(__ddiv_rn(nu_i, nu_j)), amp);
+            const double2 ph = phase[i];
+            double re = __dmul_rn(x, ph.x), im = __dmul_rn(x, ph.y);
+            if (el_trans_sign(S, sec_zip(S, ca, cb), i)) { re = -re; im = -im; }      // src/model.cc:815-820
+            int e = 0;
+            while (e < len && col[e] != j) e++;
+            if (e < len) {                                             // lil_mat::add, src/sparse.cc:57-81
+                val[e].x = __dadd_rn(val[e].x, re); val[e].y = __dadd_rn(val[e].y, im);
+                if (j != r && hypot(val[e].x, val[e].y) < 1e-14) { len--; col[e] = col[len]; val[e] = val[len]; }
+            } else { col[len] = j; val[len] = make_double2(re, im); len++; }
+        }
+        for (int x1 = 1; x1 < len; x1++) {                             // ascending columns
+            const int64_t c = col[x1]; const double2 v = val[x1];
+            int y1 = x1 - 1;
+            while (y1 >= 0 && col[y1] > c) { col[y1 + 1] = col[y1]; val[y1 + 1] = val[y1]; y1--; }
+            col[y1 + 1] = c; val[y1 + 1] = v;
+        }
+        row_end[r] = start[r] + len;
     }
 }
 
@@ -428,6 +624,9 @@ using namespace qb;
 
 struct qbgpu_sector {
     int dim = 0, L[3] = {1, 1, 1}, k[3] = {0, 0, 0}, spec = 0, nsites = 0, nsub = 0, ntrans = 0, nsubtrans = 0, ndown = 0;
+    bool electron = false;                           // two bits per site (nup = ndown field, ndn below); nsub = bits of a half state
+    int ndn = 0;
+    uint16_t *d_invmask = nullptr;
     int64_t n = 0, zero_norm = 0;
     SecDev dev{};
     uint16_t *d_subT = nullptr, *d_rep = nullptr;
@@ -509,7 +708,7 @@ struct SecMatFree {                      // what a matrix-free sector handle own
 void sector_free(qbgpu_sector *S)
 {
     if (!S) return;
-    cudaFree(S->d_subT); cudaFree(S->d_rep); cudaFree(S->d_dist); cudaFree(S->d_keys); cudaFree(S->d_seg); cudaFree(S->d_nu); cudaFree(S->d_phase);
+    cudaFree(S->d_subT); cudaFree(S->d_rep); cudaFree(S->d_dist); cudaFree(S->d_keys); cudaFree(S->d_seg); cudaFree(S->d_nu); cudaFree(S->d_phase); cudaFree(S->d_invmask);
     delete S;
 }
 
@@ -548,7 +747,10 @@ void qb::sector_matfree_destroy(qbgpu_matrix *A)
 
 extern "C" {
 
-int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndown, const int32_t *k)
+}  // extern "C"
+
+// spins (one bit per site, n0 = ndown) or single-orbital electrons (two bits per site, n0 = nup, n1 = ndn)
+static int sector_create_impl(qbgpu_sector_t *out, int dim, const int32_t *L, bool electron, int n0, int n1, const int32_t *k)
 {
     QB_TRY(ensure_init());
     Context &c = ctx();
@@ -557,17 +759,20 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     int spec = -1, N = 1;
     for (int d = 0; d < dim; d++) { if (L[d] < 1) return fail(QBGPU_ERR_ARG, "sector_create: bad lattice size"); N *= L[d]; if (spec < 0 && L[d] % 2 == 0) spec = d; }
     if (spec < 0) return fail(QBGPU_ERR_ARG, "sector_create: no even direction (the reference's divide_lattice needs one, src/lattice.cc:1076-1083)");
-    if (N > 32 || N < 2) return fail(QBGPU_ERR_ARG, "sector_create: 2..32 sites");
-    if (ndown < 0 || ndown > N) return fail(QBGPU_ERR_ARG, "sector_create: bad ndown");
+    if (N > (electron ? 16 : 32) || N < 2) return fail(QBGPU_ERR_ARG, electron ? "sector_create: 2..16 sites for electrons" : "sector_create: 2..32 sites");
+    if (n0 < 0 || n0 > N || n1 < 0 || n1 > N) return fail(QBGPU_ERR_ARG, "sector_create: bad particle numbers");
+    const int ndown = n0;
     const double t0 = wall_clock();
     auto *S = new qbgpu_sector;
-    S->dim = dim; S->spec = spec; S->nsites = N; S->nsub = N / 2; S->ntrans = N; S->nsubtrans = N / 2; S->ndown = ndown;
+    const int nhs = N / 2;                                              // sites of a half
+    const int bps = electron ? 2 : 1;                                   // bits per site
+    S->dim = dim; S->spec = spec; S->nsites = N; S->nsub = nhs * bps; S->ntrans = N; S->nsubtrans = N / 2; S->ndown = n0; S->ndn = n1; S->electron = electron;
     for (int d = 0; d < dim; d++) { S->L[d] = L[d]; S->k[d] = k[d]; }
     HostLattice par(dim, S->L, spec);
     int Ls[3] = {S->L[0], S->L[1], S->L[2]};
     Ls[spec] /= 2;
     HostLattice sub(dim, Ls, spec);
-    const int nsub = S->nsub, nst = sub.N;
+    const int nsub = S->nsub, nst = sub.N;                              // nsub: BITS of a half state
     const uint32_t half = 1u << nsub;
     S->disps = par.disps; S->coor = par.coor;
 
@@ -575,10 +780,11 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     std::vector<std::vector<int>> splans;
     for (auto &d : sub.disps) splans.push_back(sub.plan(d));
     std::vector<uint16_t> subT((size_t)nst * half);
+    const uint32_t dmask = (1u << bps) - 1u;
     for (int j = 0; j < nst; j++)
         for (uint32_t x = 0; x < half; x++) {
             uint32_t y = 0;
-            for (int s = 0; s < nsub; s++) if ((x >> s) & 1u) y |= 1u << splans[j][s];
+            for (int s = 0; s < nhs; s++) y |= ((x >> (bps * s)) & dmask) << (bps * splans[j][s]);
             subT[(size_t)j * half + x] = (uint16_t)y;
         }
     std::vector<uint16_t> rep(half);
@@ -600,16 +806,23 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     std::vector<int> fs(N), fa(N), fb(N);
     for (int i = 0; i < N; i++) {
         const std::vector<int> p = par.plan(par.disps[i]);
-        std::vector<int> pa(nsub), pb(nsub);
-        if (p[0] % 2 == 0) { fs[i] = 0; for (int t = 0; t < nsub; t++) { pa[t] = p[2 * t] / 2; pb[t] = (p[2 * t + 1] - 1) / 2; } }
-        else               { fs[i] = 1; for (int t = 0; t < nsub; t++) { pa[t] = p[2 * t + 1] / 2; pb[t] = (p[2 * t] - 1) / 2; } }
+        std::vector<int> pa(nhs), pb(nhs);
+        if (p[0] % 2 == 0) { fs[i] = 0; for (int t = 0; t < nhs; t++) { pa[t] = p[2 * t] / 2; pb[t] = (p[2 * t + 1] - 1) / 2; } }
+        else               { fs[i] = 1; for (int t = 0; t < nhs; t++) { pa[t] = p[2 * t + 1] / 2; pb[t] = (p[2 * t] - 1) / 2; } }
         auto ia = sp_index.find(pa), ib = sp_index.find(pb);
         if (ia == sp_index.end() || ib == sp_index.end()) { sector_free(S); return fail(QBGPU_ERR_STATE, "sector_create: translation does not factor over the sublattices"); }
         fa[i] = ia->second; fb[i] = ib->second;
     }
     SecDev &D = S->dev;
     D.nsites = N; D.nsub = nsub; D.ntrans = N; D.shift = std::max(0, 2 * nsub - 16); D.lin_order = 1;
+    D.electron = electron ? 1 : 0; D.invmask = nullptr;
+    std::vector<uint16_t> invmask((size_t)N * 16, 0);
     for (int i = 0; i < N; i++) {
+        if (electron) {                                                 // inversions of translation i: mbasis_elem::transform's bubble-sort count
+            const std::vector<int> p = par.plan(par.disps[i]);
+            for (int s1 = 0; s1 < N; s1++)
+                for (int s2 = s1 + 1; s2 < N; s2++) if (p[s1] > p[s2]) invmask[(size_t)i * 16 + s1] |= (uint16_t)(1u << s2);
+        }
         std::vector<int> m(dim);
         for (int d = 0; d < dim; d++) m[d] = (S->L[d] - par.disps[i][d]) % S->L[d];
         const int iv = dindex[m];
@@ -618,6 +831,7 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
         long long num = 0;                                              // src/basis.cc:2129-2147
         for (int d = 0; d < dim; d++) { const int kk = ((S->k[d] % S->L[d]) + S->L[d]) % S->L[d]; num += (long long)kk * par.disps[i][d] * (N / S->L[d]); }
         D.bad[i] = (num % N != 0) ? 1 : 0;
+        D.kt[i] = (int16_t)(num % N);
         double e = 0.0;                                                 // src/model.cc:808-814
         for (int d = 0; d < dim; d++) e += S->k[d] * par.disps[i][d] / static_cast<double>(S->L[d]);
         S->phase.push_back(std::exp(std::complex<double>(0.0, 2.0 * 3.1415926535897932 * e)));
@@ -641,6 +855,11 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     QB_CU(cudaMemcpyAsync(S->d_dist, dist.data(), half, cudaMemcpyHostToDevice, c.stream));
     QB_CU(cudaMemcpyAsync(d_reps, reps.data(), reps.size() * 2, cudaMemcpyHostToDevice, c.stream));
     QB_CU(cudaMemcpyAsync(S->d_phase, S->phase.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, c.stream));
+    if (electron) {
+        QB_CU(cudaMalloc(&S->d_invmask, invmask.size() * 2));
+        QB_CU(cudaMemcpyAsync(S->d_invmask, invmask.data(), invmask.size() * 2, cudaMemcpyHostToDevice, c.stream));
+        D.invmask = S->d_invmask;
+    }
     D.subT = S->d_subT; D.rep = S->d_rep; D.dist = S->d_dist;
 
     // representatives: flag the candidates (even half a sublattice representative), compact in Lin order
@@ -648,7 +867,8 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     const int64_t ncand = (int64_t)nreps << nsub;
     if (ncand > 2147483647LL) { cleanup(); sector_free(S); return fail(QBGPU_ERR_STATE, "sector_create: candidate count overflow"); }
     QB_CU(cudaMalloc(&d_flag, ncand));
-    sec_flag_kernel<<<sgrid(ncand), kSBlock, 0, c.stream>>>(D, d_reps, nreps, ndown, ncand, d_flag);
+    if (electron) el_flag_kernel<<<sgrid(ncand), kSBlock, 0, c.stream>>>(D, d_reps, nreps, n0, n1, ncand, d_flag);
+    else sec_flag_kernel<<<sgrid(ncand), kSBlock, 0, c.stream>>>(D, d_reps, nreps, ndown, ncand, d_flag);
     QB_LAUNCH_COUNT();
     QB_CU(cudaMalloc(&d_nsel, sizeof(int)));
     uint32_t *d_all = nullptr;
@@ -683,7 +903,8 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
         D.lin_order = lin_tables_exist(hk, nsub) ? 1 : 0;
     }
     if (!D.lin_order) {
-        sec_lin_to_zip_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(S->n, nsub, S->d_keys);
+        if (electron) el_lin_to_zip_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(S->n, nsub, S->d_keys);
+        else sec_lin_to_zip_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(S->n, nsub, S->d_keys);
         QB_LAUNCH_COUNT();
         QB_CU(cudaMalloc(&d_sorted, sizeof(uint32_t) * (size_t)S->n));
         size_t tb = 0;
@@ -707,7 +928,8 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     QB_CU(cudaMalloc(&S->d_nu, sizeof(double) * (size_t)S->n));
     QB_CU(cudaMalloc(&d_zero, sizeof(unsigned long long)));
     QB_CU(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), c.stream));
-    sec_norm_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(D, S->d_nu, d_zero);
+    if (electron) el_norm_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(D, S->d_nu, d_zero);
+    else sec_norm_kernel<<<sgrid(S->n), kSBlock, 0, c.stream>>>(D, S->d_nu, d_zero);
     QB_LAUNCH_COUNT();
     unsigned long long z = 0;
     QB_CU(cudaMemcpyAsync(&z, d_zero, sizeof(z), cudaMemcpyDeviceToHost, c.stream));
@@ -721,6 +943,17 @@ int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndow
     *out = S;
     return QBGPU_OK;
 }
+
+extern "C" {
+
+int qbgpu_sector_create(qbgpu_sector_t *out, int dim, const int32_t *L, int ndown, const int32_t *k)
+{ return sector_create_impl(out, dim, L, false, ndown, 0, k); }
+
+/* A (N_up, N_dn, momentum) sector of single-orbital electrons on an untilted lattice of at most 16 sites: the device counterpart
+ * of fill_Weisse_table + enumerate_basis_repr for the reference's "electron" orbital (src/basis.cc:49-96; two bits per site, bit 0
+ * up, bit 1 down).  Same representatives, order and norms as the reference (translation signs: src/basis.cc:593-620, 2134-2147). */
+int qbgpu_sector_create_electron(qbgpu_sector_t *out, int dim, const int32_t *L, int nup, int ndn, const int32_t *k)
+{ return sector_create_impl(out, dim, L, true, nup, ndn, k); }
 
 int qbgpu_sector_destroy(qbgpu_sector_t S) { sector_free(S); return QBGPU_OK; }
 
@@ -759,6 +992,7 @@ int qbgpu_sector_norms(qbgpu_sector_t S, double *nu_host)
 int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const double *coef_reim, const void *x_old_dev, void *y_new_dev)
 {
     if (!S_old || !S_new || !coef_reim || !x_old_dev || !y_new_dev) return fail(QBGPU_ERR_ARG, "sector_apply_sz: null argument");
+    if (S_old->electron || S_new->electron) return fail(QBGPU_ERR_STATE, "sector_apply_sz: spin sectors only");
     if (S_old->n != S_new->n || S_old->nsites != S_new->nsites || S_old->ndown != S_new->ndown || S_old->dim != S_new->dim ||
         memcmp(S_old->L, S_new->L, sizeof(S_old->L)) != 0 || S_old->dev.lin_order != S_new->dev.lin_order)
         return fail(QBGPU_ERR_ARG, "sector_apply_sz: the two sectors must share lattice and Sz (same representatives)");
@@ -780,6 +1014,7 @@ int qbgpu_sector_apply_sz(qbgpu_sector_t S_old, qbgpu_sector_t S_new, const doub
 int qbgpu_sector_apply_ladder(qbgpu_sector_t S_old, qbgpu_sector_t S_new, int lower, const double *coef_reim, const void *x_old_dev, void *y_new_dev)
 {
     if (!S_old || !S_new || !coef_reim || !x_old_dev || !y_new_dev) return fail(QBGPU_ERR_ARG, "sector_apply_ladder: null argument");
+    if (S_old->electron || S_new->electron) return fail(QBGPU_ERR_STATE, "sector_apply_ladder: spin sectors only");
     if (S_old->nsites != S_new->nsites || S_old->dim != S_new->dim || memcmp(S_old->L, S_new->L, sizeof(S_old->L)) != 0)
         return fail(QBGPU_ERR_ARG, "sector_apply_ladder: the two sectors must share the lattice");
     if (S_new->ndown != S_old->ndown + (lower ? 1 : -1))
@@ -804,6 +1039,7 @@ int qbgpu_sector_apply_ladder(qbgpu_sector_t S_old, qbgpu_sector_t S_new, int lo
 int qbgpu_sector_build_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbonds, const int32_t *bonds, double J, double fake_pos, int flags)
 {
     if (!S || !A || !bonds || nbonds < 1) return fail(QBGPU_ERR_ARG, "sector_build_heisenberg: bad arguments");
+    if (S->electron) return fail(QBGPU_ERR_STATE, "sector_build_heisenberg: this is an electron sector (qbgpu_sector_build_hubbard)");
     if (nbonds > kMaxTerms) return fail(QBGPU_ERR_ARG, "sector_build_heisenberg: at most 128 bonds");
     Context &c = ctx();
     *A = nullptr;
@@ -870,6 +1106,7 @@ int qbgpu_sector_matfree_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbo
 {
     QB_TRY(ensure_init());
     if (!S || !A || !bonds || nbonds < 1) return fail(QBGPU_ERR_ARG, "sector_matfree_heisenberg: bad arguments");
+    if (S->electron) return fail(QBGPU_ERR_STATE, "sector_matfree_heisenberg: this is an electron sector");
     if (nbonds > kMaxTerms) return fail(QBGPU_ERR_ARG, "sector_matfree_heisenberg: at most 128 bonds");
     Context &c = ctx();
     *A = nullptr;
@@ -896,6 +1133,78 @@ int qbgpu_sector_matfree_heisenberg(qbgpu_sector_t S, qbgpu_matrix_t *A, int nbo
     H->mf_sec = M;
     *A = H;
     return QBGPU_OK;
+}
+
+/* generate_Ham_sparse_repr (src/model.cc:688-836) for the single-orbital Hubbard model on an electron sector:
+ * H = -t sum_hops c+_{to,s} c_{from,s} + U sum_i n_up,i n_dn,i.  hops[3*nhops] = (to, from, spin) DIRECTED, in the order the
+ * caller's add_Ham calls insert them (the reference's example: per bond c+_up,i c_up,j ; c+_up,j c_up,i ; c+_dn,i c_dn,j ;
+ * c+_dn,j c_dn,i); they are re-ordered here like mopr::operator+= does (src/operators.cc:901-925: ascending (lower site, higher
+ * site), equal keys in REVERSE order of insertion) because the accumulation order decides the last bits and lil_mat's erase rule. */
+int qbgpu_sector_build_hubbard(qbgpu_sector_t S, qbgpu_matrix_t *A, int nhops, const int32_t *hops, double t, double U, double fake_pos, int flags)
+{
+    if (!S || !A || !hops || nhops < 1) return fail(QBGPU_ERR_ARG, "sector_build_hubbard: bad arguments");
+    if (!S->electron) return fail(QBGPU_ERR_STATE, "sector_build_hubbard: needs an electron sector (qbgpu_sector_create_electron)");
+    if (nhops > kMaxHops) return fail(QBGPU_ERR_ARG, "sector_build_hubbard: at most 256 directed hops");
+    Context &c = ctx();
+    *A = nullptr;
+    std::vector<int> order(nhops);
+    for (int q = 0; q < nhops; q++) {
+        const int to = hops[3 * q], fr = hops[3 * q + 1], sp = hops[3 * q + 2];
+        if (to < 0 || fr < 0 || to >= S->nsites || fr >= S->nsites || to == fr || sp < 0 || sp > 1) return fail(QBGPU_ERR_ARG, "sector_build_hubbard: bad hop");
+        order[q] = q;
+    }
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        const int lx = std::min(hops[3 * x], hops[3 * x + 1]), hx = std::max(hops[3 * x], hops[3 * x + 1]);
+        const int ly = std::min(hops[3 * y], hops[3 * y + 1]), hy = std::max(hops[3 * y], hops[3 * y + 1]);
+        if (lx != ly) return lx < ly;
+        if (hx != hy) return hx < hy;
+        return x > y;                                                   // equal keys: the later insertion comes first
+    });
+    ElTerms T;
+    memset(&T, 0, sizeof(T));
+    T.nterms = nhops; T.t = t; T.U = U; T.fake_pos = fake_pos;
+    for (int pos = 0; pos < nhops; pos++) { const int q = order[pos]; T.to[pos] = (uint8_t)hops[3 * q]; T.from[pos] = (uint8_t)hops[3 * q + 1]; T.sp[pos] = (uint8_t)hops[3 * q + 2]; }
+
+    ElTerms *d_T = nullptr;
+    int64_t *d_cap = nullptr, *d_start = nullptr, *d_end = nullptr, *d_col = nullptr, *d_sum = nullptr;
+    double2 *d_val = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(d_T); cudaFree(d_cap); cudaFree(d_start); cudaFree(d_end); cudaFree(d_col); cudaFree(d_val); cudaFree(d_tmp); cudaFree(d_sum); };
+#define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    const int64_t n = S->n;
+    QB_CU(cudaMalloc(&d_T, sizeof(ElTerms)));
+    QB_CU(cudaMemcpyAsync(d_T, &T, sizeof(ElTerms), cudaMemcpyHostToDevice, c.stream));
+    QB_CU(cudaMalloc(&d_cap, sizeof(int64_t) * (n + 1)));
+    QB_CU(cudaMalloc(&d_start, sizeof(int64_t) * (n + 1)));
+    QB_CU(cudaMalloc(&d_end, sizeof(int64_t) * (n + 1)));
+    el_cap_kernel<<<sgrid(n + 1), kSBlock, 0, c.stream>>>(S->dev, d_T, d_cap);
+    QB_LAUNCH_COUNT();
+    size_t tb = 0;
+    QB_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_cap, d_start, n + 1, c.stream));
+    QB_CU(cudaMalloc(&d_tmp, tb ? tb : 1));
+    QB_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cap, d_start, n + 1, c.stream));
+    int64_t total = 0;
+    QB_CU(cudaMemcpyAsync(&total, d_start + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaMalloc(&d_col, sizeof(int64_t) * (size_t)total));
+    QB_CU(cudaMalloc(&d_val, sizeof(double2) * (size_t)total));
+    el_rows_kernel<<<sgrid(n), kSBlock, 0, c.stream>>>(S->dev, d_T, S->d_phase, d_start, d_end, d_col, d_val);
+    QB_LAUNCH_COUNT();
+    sec_len_kernel<<<sgrid(n), kSBlock, 0, c.stream>>>(n, d_start, d_end, d_cap);
+    QB_LAUNCH_COUNT();
+    cudaFree(d_tmp); d_tmp = nullptr;
+    QB_CU(cudaMalloc(&d_sum, sizeof(int64_t)));
+    QB_CU(cub::DeviceReduce::Sum(nullptr, tb, d_cap, d_sum, n, c.stream));
+    QB_CU(cudaMalloc(&d_tmp, tb ? tb : 1));
+    QB_CU(cub::DeviceReduce::Sum(d_tmp, tb, d_cap, d_sum, n, c.stream));
+    int64_t upper = 0;
+    QB_CU(cudaMemcpyAsync(&upper, d_sum, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
+#undef QB_CU
+    int rc = create_from_device_csr(A, n, d_start, d_end, d_col, d_val, true, upper, 1, flags, true);
+    cleanup();
+    return rc;
 }
 
 }  // extern "C"

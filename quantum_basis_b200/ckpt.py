@@ -263,14 +263,14 @@ def cg_clean(dirpath):
             _rm(_p(dirpath, name))
 
 
-def cg_checkpointed(mat, E0, v, r, p, pp, maxit=1000, every=50, dirpath=DIRNAME, max_chunks=None):
+def cg_checkpointed(mat, E0, v, r, p, pp, maxit=1000, every=50, dirpath=DIRNAME, max_chunks=None, return_done=False):
     """eigenvec_CG(dim, maxit, m = 0, ...) with the reference's CG checkpoints every `every` steps; resumes from `dirpath`
     when it holds one.  v, r, p, pp: host arrays of length dim (v = the initial guess unless resuming).  Returns (m, accu)."""
     dim = mat.dim
     m, cv, cr, cp = cg_load(dirpath, maxit, dim, mat.dtype)
     if m > 0:
         v[:], r[:], p[:] = cv, cr, cp
-    accu, chunks = 0.0, 0
+    accu, chunks, done = 0.0, 0, False
     while m < maxit:
         stop = min(maxit, m + every)
         m_new, accu = _csr.eigenvec_CG(dim, stop, m, mat, E0, v, r, p, pp)
@@ -286,6 +286,8 @@ def cg_checkpointed(mat, E0, v, r, p, pp, maxit=1000, every=50, dirpath=DIRNAME,
         chunks += 1
         if done or (max_chunks is not None and chunks >= max_chunks):
             break
+    if return_done:
+        return m, accu, bool(done) if chunks else False
     return m, accu
 
 
@@ -306,7 +308,7 @@ def stop_state_from_coefficients(hessenberg, maxit, m, precision=2e-12):
     return [cnt, accuracy, t0, t1]
 
 
-def lanczos_checkpointed(mat, v, hessenberg, purpose, maxit, every=50, dirpath=DIRNAME, max_chunks=None):
+def lanczos_checkpointed(mat, v, hessenberg, purpose, maxit, every=50, dirpath=DIRNAME, max_chunks=None, return_done=False):
     """lanczos(0, maxit-1, maxit, ...) with the reference's checkpoints, written every `every` steps: resumes from
     `dirpath` when it holds a checkpoint (its vectors and coefficients replace the caller's), otherwise starts from v[0:dim].
     v: host array with 2 ("sr_val0") or 3 columns; hessenberg[2*maxit].  Returns the final step count m.
@@ -323,10 +325,11 @@ def lanczos_checkpointed(mat, v, hessenberg, purpose, maxit, every=50, dirpath=D
     st = (C.c_double * 4)(*[float(x) for x in state])
     f = lib().qbgpu_lanczos_resume_z if mat.is_complex else lib().qbgpu_lanczos_resume_d
     m = C.c_int64(k)
-    chunks = 0
+    chunks, done, finished = 0, False, False
     while True:
         np_ = min(every, maxit - 1 - k)
         if np_ <= 0:
+            finished = True                                            # maxit - 1 steps: the reference's loop ends here too
             break
         check(f(mat.handle, k, np_, maxit, C.byref(m), C.c_void_p(v.ctypes.data), C.c_void_p(hessenberg.ctypes.data),
                 purpose.encode(), QBGPU_HOST, st))
@@ -337,4 +340,217 @@ def lanczos_checkpointed(mat, v, hessenberg, purpose, maxit, every=50, dirpath=D
         chunks += 1
         if done or (max_chunks is not None and chunks >= max_chunks):
             break
+    if return_done:
+        return k, finished or done
     return k
+
+
+# ------------------------------------------------------------------------------------------- the outer state machine
+# model<T>::locate_E0_lanczos with enable_ckpt (src/model.cc:1124-1316) remembers WHICH of its four stages are done -- E0 (simple
+# Lanczos), V0 (CG), E1 (Lanczos orthogonal to phi0), V1 (CG) -- in out_Qckpt/lczs_E0_sym<s>_sec<n>[_K<k...>].Qckpt: four bools,
+# MKL_INT nconv, double E0, E1, gap = 36 bytes (ckpt_lczsE0_init / _updt, src/model.cc:2522-2749), updated through <name>1 (new
+# content) and <name>2 (new content complete) so that a crash at any point leaves either the old or the new state; the finished
+# eigenvectors go to eigenvec{0,1}_sym<s>_sec<n>[_K...].dat in the vec_disk_write format.
+_E0_STATE = struct.Struct("<????qddd")
+
+
+def _e0_names(dirpath, sym, sec, momentum):
+    tag = f"_sym{int(sym)}_sec{int(sec)}"
+    if int(sym) == 1 and momentum is not None:
+        tag += "_K" + "".join(str(int(k)) for k in momentum)
+    return (_p(dirpath, "lczs_E0" + tag + ".Qckpt"), _p(dirpath, "eigenvec0" + tag + ".dat"), _p(dirpath, "eigenvec1" + tag + ".dat"))
+
+
+def e0_state_init(dirpath=DIRNAME, sym=0, sec=0, momentum=None):
+    """ckpt_lczsE0_init (src/model.cc:2519-2657) without the vector loads: create the state file when there is none (or a
+    truncated one), roll an interrupted update forward when its new content was complete, then read the state.
+    Returns dict(E0_done, V0_done, E1_done, V1_done, nconv, E0, E1, gap)."""
+    if os.path.exists(dirpath) and not os.path.isdir(dirpath):
+        os.remove(dirpath)
+    os.makedirs(dirpath, exist_ok=True)
+    f0, _, _ = _e0_names(dirpath, sym, sec, momentum)
+    f1, f2 = f0 + "1", f0 + "2"
+    size = _E0_STATE.size
+    fresh = dict(E0_done=False, V0_done=False, E1_done=False, V1_done=False, nconv=0, E0=0.0, E1=0.0, gap=0.0)
+    if (not os.path.exists(f0) and not os.path.exists(f1)) or (os.path.exists(f0) and os.path.getsize(f0) != size):
+        with open(f0, "wb") as f:
+            f.write(_E0_STATE.pack(False, False, False, False, 0, 0.0, 0.0, 0.0))
+        return fresh
+    updating = os.path.exists(f1) and os.path.getsize(f1) == size
+    if updating and os.path.exists(f2):                    # new data finished writing: take it, drop the stage's own checkpoints
+        _rm(f0)
+        with open(f1, "rb") as a, open(f0, "wb") as b:
+            b.write(a.read())
+        lanczos_clean(dirpath)
+        cg_clean(dirpath)
+    _rm(f1)
+    _rm(f2)
+    with open(f0, "rb") as f:
+        e0d, v0d, e1d, v1d, nconv, E0, E1, gap = _E0_STATE.unpack(f.read(size))
+    return dict(E0_done=e0d, V0_done=v0d, E1_done=e1d, V1_done=v1d, nconv=nconv, E0=E0, E1=E1, gap=gap)
+
+
+def e0_state_update(st, dirpath=DIRNAME, sym=0, sec=0, momentum=None, eigenvecs=None, _crash_after=None):
+    """ckpt_lczsE0_updt (src/model.cc:2659-2746): the new state into <name>1; eigenvec0 recorded from the CG checkpoint when V0
+    has just finished, eigenvec0/1 from `eigenvecs` (two host vectors) when V1 has; <name>2 marks the new content complete;
+    then the old state is replaced and the stage's own checkpoints are removed.  `_crash_after`: test hook (1: after <name>1,
+    2: after <name>2, 3: after the old state was removed)."""
+    f0, ev0, ev1 = _e0_names(dirpath, sym, sec, momentum)
+    f1, f2 = f0 + "1", f0 + "2"
+    if not os.path.exists(f0):
+        raise QbgpuError("e0_state_update: no state file (e0_state_init first)")
+    _rm(f1)
+    _rm(f2)
+    blob = _E0_STATE.pack(bool(st["E0_done"]), bool(st["V0_done"]), bool(st["E1_done"]), bool(st["V1_done"]), int(st["nconv"]),
+                          float(st["E0"]), float(st["E1"]), float(st["gap"]))
+    with open(f1, "wb") as f:
+        f.write(blob)
+    if _crash_after == 1:
+        raise _Interrupted()
+    if st["E0_done"] and st["V0_done"] and not st["E1_done"] and not st["V1_done"]:      # record eigenvec0: the CG loop's last V
+        for name in sorted(os.listdir(dirpath)):
+            if name.startswith("CG_V") and name.endswith(".dat") and name[4:-4].isdigit():
+                _rm(ev0)
+                with open(_p(dirpath, name), "rb") as a, open(ev0, "wb") as b:
+                    b.write(a.read())
+    if st["V1_done"]:
+        if eigenvecs is None or len(eigenvecs) != 2:
+            raise QbgpuError("e0_state_update: V1_done needs the two eigenvectors")
+        if not os.path.exists(ev0):
+            _csr.vec_disk_write(ev0, eigenvecs[0])
+        _csr.vec_disk_write(ev1, eigenvecs[1])
+    with open(f2, "wb") as f:                              # before / after this point a restart uses the old / new data
+        f.write(blob)
+    if _crash_after == 2:
+        raise _Interrupted()
+    _rm(f0)
+    if _crash_after == 3:
+        raise _Interrupted()
+    with open(f0, "wb") as f:
+        f.write(blob)
+    lanczos_clean(dirpath)
+    cg_clean(dirpath)
+    _rm(f1)
+    _rm(f2)
+
+
+def locate_E0_lanczos_checkpointed(mat, nev=1, ncv=1, maxit=1000, every=50, dirpath=DIRNAME, sym=0, sec=0, momentum=None,
+                                   max_chunks=None):
+    """model<T>::locate_E0_lanczos with enable_ckpt == true (src/model.cc:1124-1316 + 2519-2746), csr_mat branch: the four stages
+    E0 / V0 / E1 / V1 with the reference's state file between them and the reference's Lanczos / CG checkpoints inside them
+    (lanczos_checkpointed, cg_checkpointed: pieces of `every` steps on the device).  A run that is interrupted -- `max_chunks`
+    pieces in total, for tests, or a real crash -- is continued by calling the function again with the same `dirpath`: finished
+    stages are skipped, the running one resumes from its own checkpoint, phi0 comes back from eigenvec0*.dat.
+    Returns dict(eigenvals, eigenvecs, nconv, finished, state)."""
+    if not (0 < nev <= 2 and nev - 1 <= ncv <= nev):
+        raise QbgpuError("need 0 < nev <= 2 and nev-1 <= ncv <= nev")
+    n, dt = mat.dim, mat.dtype
+    f0, ev0, ev1 = _e0_names(dirpath, sym, sec, momentum)
+    st = e0_state_init(dirpath, sym, sec, momentum)
+    budget = [max_chunks]
+
+    def take():                                            # pieces still allowed in this call (None: no limit)
+        return None if budget[0] is None else max(budget[0], 0)
+
+    def spent(k):
+        if budget[0] is not None:
+            budget[0] -= k
+
+    out = {"eigenvals": [], "eigenvecs": [], "finished": False}
+    rnd = lambda seed: _csr.vec_randomize(n, seed, dtype=dt)                  # noqa: E731
+    hess = np.zeros(2 * maxit)
+    v = np.zeros((4 if ncv > 0 else 2) * n, dtype=dt)
+    v[:n] = rnd(1)                                                             # :1165
+
+    def pieces(total_steps_before, total_steps_after):
+        return -(-(total_steps_after - total_steps_before) // every) if total_steps_after > total_steps_before else 1
+
+    if not st["E0_done"]:                                                      # :1173-1200
+        if take() == 0:
+            return dict(out, state=st)
+        k0 = lanczos_load(dirpath, maxit, n, dt, "sr_val0")[0]
+        m, done = lanczos_checkpointed(mat, v, hess, "sr_val0", maxit, every, dirpath, take(), return_done=True)
+        spent(pieces(k0, m))
+        if not done:
+            return dict(out, state=st)
+        ritz, _ = _csr.hess_eigen(hess, maxit, m)
+        st.update(E0_done=True, E0=float(ritz[0]), nconv=0)
+        out["lanczos_steps"] = m
+        e0_state_update(st, dirpath, sym, sec, momentum)
+    out["eigenvals"].append(st["E0"])
+    if ncv == 0:
+        out["finished"] = True
+        return dict(out, nconv=st["nconv"], state=st)
+
+    if st["V0_done"] and not st["V1_done"]:                                   # :2614-2627: phi0 back from the disk
+        v[2 * n:3 * n] = _csr.vec_disk_read(ev0, n, dt)
+    if not st["V0_done"]:                                                      # :1208-1233
+        if take() == 0:
+            return dict(out, state=st)
+        v[2 * n:3 * n] = rnd(1)
+        k0 = cg_load(dirpath, maxit, n, dt)[0]
+        m, accu, done = cg_checkpointed(mat, st["E0"], v[2 * n:3 * n], v[0:n], v[n:2 * n], v[3 * n:4 * n], maxit, every, dirpath, take(),
+                                        return_done=True)
+        spent(pieces(k0, m))
+        if not done:
+            return dict(out, state=st)
+        out["cg_steps"], out["cg_accuracy"] = m, accu
+        if not any(x.startswith("CG_V") for x in os.listdir(dirpath)):        # (converged without a stored piece: store the result)
+            cg_store(dirpath, max(m, 1), v[2 * n:3 * n], v[0:n], v[n:2 * n])
+        st.update(V0_done=True, nconv=1)
+        e0_state_update(st, dirpath, sym, sec, momentum)
+
+    if nev == 2 and not st["E1_done"]:                                         # :1236-1268
+        if take() == 0:
+            return dict(out, state=st)
+        k0, v_ck, h_ck, _ = lanczos_load(dirpath, maxit, n, dt, "sr_val1")
+        if k0 == 0:
+            phi0 = v[2 * n:3 * n]
+            w = rnd(1)
+            w = w - np.vdot(phi0, w) * phi0
+            v[:n] = w / np.linalg.norm(w)
+            v[n:2 * n] = 0
+        hess[:] = 0.0
+        v3 = v[:3 * n]
+        m, done = lanczos_checkpointed(mat, v3, hess, "sr_val1", maxit, every, dirpath, take(), return_done=True)
+        spent(pieces(k0, m))
+        if not done:
+            return dict(out, state=st)
+        ritz, _ = _csr.hess_eigen(hess, maxit, m)
+        st.update(E1_done=True, E1=float(ritz[0]), gap=float(ritz[0]) - st["E0"])
+        out["lanczos_steps_E1"] = m
+        e0_state_update(st, dirpath, sym, sec, momentum)
+    if nev == 2:
+        out["eigenvals"].append(st["E1"])
+        out["gap"] = st["gap"]
+
+    if ncv == 1:                                                               # :1270-1276
+        out["eigenvecs"].append(v[2 * n:3 * n].copy())
+        out["finished"] = True
+        return dict(out, nconv=st["nconv"], state=st)
+
+    if st["V1_done"]:                                                          # :2628-2652
+        out["eigenvecs"] = [_csr.vec_disk_read(ev0, n, dt), _csr.vec_disk_read(ev1, n, dt)]
+        out["finished"] = True
+        return dict(out, nconv=st["nconv"], state=st)
+    if take() == 0:                                                            # :1278-1315
+        return dict(out, state=st)
+    v5 = np.zeros(5 * n, dtype=dt)
+    v5[2 * n:3 * n] = v[2 * n:3 * n]
+    v5[3 * n:4 * n] = rnd(8)                                                   # seed + 7
+    k0 = cg_load(dirpath, maxit, n, dt)[0]
+    m, accu, done = cg_checkpointed(mat, st["E1"], v5[3 * n:4 * n], v5[0:n], v5[n:2 * n], v5[4 * n:5 * n], maxit, every, dirpath, take(),
+                                    return_done=True)
+    spent(pieces(k0, m))
+    if not done and m < maxit:
+        return dict(out, state=st)
+    out["cg_steps_E1"], out["cg_accuracy_E1"] = m, accu
+    v0, v1 = v5[2 * n:3 * n].copy(), v5[3 * n:4 * n].copy()
+    if st["gap"] < _csr.lanczos_precision:                                     # orthogonalise a degenerate pair, :1302-1311
+        v1 = v1 - np.vdot(v0, v1) * v0
+        v1 /= np.linalg.norm(v1)
+    st.update(V1_done=True, nconv=2)
+    e0_state_update(st, dirpath, sym, sec, momentum, eigenvecs=[v0, v1])
+    out["eigenvecs"] = [v0, v1]
+    out["finished"] = True
+    return dict(out, nconv=2, state=st)

@@ -223,3 +223,40 @@ def test_cg_checkpoints_in_both_directions(oracle, case):
     assert ckpt.cg_load(d2, 1000, n, np.complex128)[0] == 5 and not os.path.exists(os.path.join(d2, "CG_V6.dat"))
     ckpt.cg_clean(d2)
     assert ckpt.cg_load(d2, 1000, n, np.complex128)[0] == 0
+
+
+# ------------------------------------------------------------------------------------------- the outer E0 / V0 / E1 / V1 state file
+def test_e0_state_file_has_the_references_layout_and_survives_a_crash_at_every_point(tmp_path):
+    """ckpt_lczsE0_init / ckpt_lczsE0_updt (src/model.cc:2519-2746): 4 bools + MKL_INT nconv + E0, E1, gap = 36 bytes; an update
+    interrupted before its new content is complete leaves the OLD state, one interrupted after it is rolled FORWARD (and the
+    finished stage's own Lanczos / CG checkpoints are dropped, as the reference does)."""
+    import struct
+    d = str(tmp_path / ckpt.DIRNAME)
+    st = ckpt.e0_state_init(d, sym=1, sec=0, momentum=[3])
+    f0 = os.path.join(d, "lczs_E0_sym1_sec0_K3.Qckpt")
+    assert os.path.getsize(f0) == 4 * 1 + 8 + 3 * 8 == 36                     # filesize_ideal, src/model.cc:2543
+    assert st == dict(E0_done=False, V0_done=False, E1_done=False, V1_done=False, nconv=0, E0=0.0, E1=0.0, gap=0.0)
+    st.update(E0_done=True, E0=-7.25)
+    ckpt.e0_state_update(st, d, 1, 0, [3])
+    assert struct.unpack("<????qddd", open(f0, "rb").read()) == (True, False, False, False, 0, -7.25, 0.0, 0.0)
+    assert ckpt.e0_state_init(d, 1, 0, [3])["E0"] == -7.25
+    assert sorted(os.listdir(d)) == ["lczs_E0_sym1_sec0_K3.Qckpt"]
+    # a stage's own checkpoint that must survive an update that did not commit, and go when it did
+    open(os.path.join(d, "HessenbergA.dat"), "wb").write(b"x")
+    new = dict(st, V0_done=True, nconv=1)
+    for crash, expect_new in ((1, False), (2, True), (3, True)):
+        with pytest.raises(ckpt._Interrupted):
+            ckpt.e0_state_update(new, d, 1, 0, [3], _crash_after=crash)
+        got = ckpt.e0_state_init(d, 1, 0, [3])
+        assert got["V0_done"] == expect_new and got["E0"] == -7.25
+        assert not os.path.exists(f0 + "1") and not os.path.exists(f0 + "2") and os.path.getsize(f0) == 36
+        assert os.path.exists(os.path.join(d, "HessenbergA.dat")) == (not expect_new)
+        if expect_new:                                                         # back to the old state for the next round
+            ckpt.e0_state_update(st, d, 1, 0, [3])
+            open(os.path.join(d, "HessenbergA.dat"), "wb").write(b"x")
+    # the full basis carries no momentum tag (src/model.cc:2545-2552)
+    ckpt.e0_state_init(d, sym=0, sec=2)
+    assert os.path.exists(os.path.join(d, "lczs_E0_sym0_sec2.Qckpt"))
+    # V1_done without the vectors is refused
+    with pytest.raises(Exception):
+        ckpt.e0_state_update(dict(st, V0_done=True, E1_done=True, V1_done=True), d, 1, 0, [3])

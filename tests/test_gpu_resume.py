@@ -112,3 +112,43 @@ def test_opt_in_real_mode_of_the_plain_product(oracle):
         for j in range(2):
             assert rel_l2(outs[("on", tag)][j], outs[("off", tag)][j]) <= 1e-15      # (bit-identical by construction; not required)
     assert rel_l2(outs[("on", "real")][0], ex["y1"]) <= TOL_MV
+
+
+def test_outer_state_machine_resumes_every_stage_and_matches_the_uninterrupted_run(oracle, tmp_path):
+    """model<T>::locate_E0_lanczos with enable_ckpt (src/model.cc:1124-1316, 2519-2746): E0 / V0 / E1 / V1 interrupted after
+    every piece of 10 steps and continued by calling again -- same energies and vectors as the uninterrupted device run, the
+    reference's state file and eigenvector files on disk at the end."""
+    import struct
+    from quantum_basis_b200 import ckpt
+    A, meta, ex = oracle.load_golden("heis12_full")
+    M = qb.csr_mat(A.dim, A.ia, A.ja, A.val, A.sym)
+    n = A.dim
+    ref = qb.locate_E0_lanczos(M, nev=2, ncv=2, maxit=300)
+    d = str(tmp_path / ckpt.DIRNAME)
+    calls, res = 0, None
+    while True:
+        res = ckpt.locate_E0_lanczos_checkpointed(M, nev=2, ncv=2, maxit=300, every=10, dirpath=d, max_chunks=1)
+        calls += 1
+        assert calls < 200
+        if res["finished"]:
+            break
+    assert calls > 8                                                          # it really was interrupted in every stage
+    assert abs(res["eigenvals"][0] - ref["eigenvals"][0]) < 1e-10 and abs(res["eigenvals"][1] - ref["eigenvals"][1]) < 1e-8
+    assert abs(res["eigenvals"][0] - meta["lanczos_E0"]) < 1e-10              # the compiled reference's E0
+    assert abs(abs(np.vdot(res["eigenvecs"][0], ref["eigenvecs"][0])) - 1.0) < 1e-6
+    for j in (0, 1):                                                           # both are eigenvectors (E1 may be degenerate: no overlap test)
+        y = np.zeros(n, dtype=np.complex128)
+        M.MultMv(np.ascontiguousarray(res["eigenvecs"][j]), y)
+        assert np.linalg.norm(y - res["eigenvals"][j] * res["eigenvecs"][j]) < (1e-8 if j == 0 else 1e-5)
+        assert abs(np.linalg.norm(res["eigenvecs"][j]) - 1.0) < 1e-9
+    assert abs(np.vdot(res["eigenvecs"][0], res["eigenvecs"][1])) < 1e-6
+    f0 = os.path.join(d, "lczs_E0_sym0_sec0.Qckpt")
+    flags = struct.unpack("<????qddd", open(f0, "rb").read())
+    assert flags[:5] == (True, True, True, True, 2) and abs(flags[5] - res["eigenvals"][0]) < 1e-14
+    v0 = qb.vec_disk_read(os.path.join(d, "eigenvec0_sym0_sec0.dat"), n, M.dtype)
+    v1 = qb.vec_disk_read(os.path.join(d, "eigenvec1_sym0_sec0.dat"), n, M.dtype)
+    assert v0 is not None and v1 is not None and abs(abs(np.vdot(v0, res["eigenvecs"][0])) - 1.0) < 1e-12
+    assert sorted(x for x in os.listdir(d) if not x.startswith("eigenvec")) == ["lczs_E0_sym0_sec0.Qckpt"]      # stage checkpoints cleaned
+    # a finished run is returned from the disk without any device work
+    again = ckpt.locate_E0_lanczos_checkpointed(M, nev=2, ncv=2, maxit=300, every=10, dirpath=d, max_chunks=0)
+    assert again["finished"] and np.array_equal(again["eigenvecs"][1], v1)

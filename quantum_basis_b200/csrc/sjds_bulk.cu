@@ -479,7 +479,8 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
                        const uint32_t *__restrict__ rowinfo, const int32_t *__restrict__ col, const ValT *__restrict__ val,
                        const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                        int scal_mode, const double *__restrict__ sc, const double *__restrict__ vdict, int use_bulk,
-                       const double2 *__restrict__ x_ref, const int32_t *__restrict__ perm_inv, VecT *x_out, int *imag_flag)
+                       const double2 *__restrict__ x_ref, const int32_t *__restrict__ perm_inv, VecT *x_out, int *imag_flag,
+                       int64_t P, int64_t EP)
 {
     using VT = VecTraits<VecT>;
     constexpr bool kDict = sizeof(ValT) == 1;
@@ -512,6 +513,14 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
     auto last_slice = [&](int64_t ub) -> int64_t { return ((u_lo + ub + 1) * D - row_lo - 1) >> 5; };
     uint32_t info_n = 0;
     int64_t base_n = 0, pref_s = -1;                        // pref_s: the slice info_n / base_n belong to
+    // periodic row metadata (qbgpu_matrix::period_slices): FULL slices read the entries of the first period, which stay in L2
+    // (0.8 MB on BASELINE config 3) instead of streaming 0.8 GB of rowinfo / rowptr per product; the last, partial slice is its own
+    const int64_t nfull = P > 0 ? (nrows >> 5) : 0;
+    auto ld_info = [&](int64_t s) -> uint32_t { const int64_t q = (P > 0 && s < nfull) ? s % P : s; return rowinfo[q * 32 + lane]; };
+    auto ld_base = [&](int64_t s) -> int64_t {
+        if (P > 0 && s < nfull) { const int64_t k = s / P; return rowptr[(s - k * P) * 32] + k * EP; }
+        return rowptr[s * 32];
+    };
 
     for (int64_t ub = blockIdx.x; ub < u_cnt; ub += gridDim.x) {
         const int64_t c0 = (u_lo + ub) * D;                 // first column (= first global row) of the block
@@ -556,14 +565,14 @@ sjds_block_smem_kernel(int64_t nrows, int64_t row_lo, int64_t D, int64_t u_lo, i
         }
         const int64_t s_last = last_slice(ub);
         for (int64_t s = first_slice(ub); s <= s_last; s += NWARP) {
-            if (pref_s != s) { info_n = rowinfo[s * 32 + lane]; base_n = rowptr[s * 32]; }      // (first slice of the kernel, or a skipped block)
+            if (pref_s != s) { info_n = ld_info(s); base_n = ld_base(s); }                      // (first slice of the kernel, or a skipped block)
             const uint32_t info = info_n;
             const int64_t base = base_n;
             {   // request the next slice of this warp: in this block, or the first one of its next block
                 int64_t sn = s + NWARP;
                 bool have = sn <= s_last;
                 if (!have && ub + gridDim.x < u_cnt) { sn = first_slice(ub + gridDim.x); have = sn <= last_slice(ub + gridDim.x); }
-                if (have) { info_n = rowinfo[sn * 32 + lane]; base_n = rowptr[sn * 32]; pref_s = sn; }
+                if (have) { info_n = ld_info(sn); base_n = ld_base(sn); pref_s = sn; }
             }
             const int len = (int)(info & kLenMaskB);
             const int64_t row = s * 32 + (info >> 24);
@@ -897,7 +906,7 @@ static int launch_block_smem_cfg(const qbgpu_matrix *A, const FusedArgs &a, int6
     kern<<<grid, NT, smem, c.stream>>>(A->nrows(), A->row_lo, D, u_lo, u_cnt, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                        (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta, a.scal_mode, a.sc,
                                        A->vdict, use_bulk, fuse_in ? (const double2 *)a.x_ref : nullptr, a.perm_inv,
-                                       fuse_in ? (VecT *)const_cast<void *>(a.x) : nullptr, a.imag_flag);
+                                       fuse_in ? (VecT *)const_cast<void *>(a.x) : nullptr, a.imag_flag, A->period_slices, A->period_entries);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;

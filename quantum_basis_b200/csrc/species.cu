@@ -393,6 +393,13 @@ int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     A->nnz_input = (A->nnz + C->nnz + nloc) / 2;            // what the reference would store: upper triangle incl. the diagonal
     C->nnz_input = C->nnz;
     A->block_D = Dd;                                        // pass 1 may keep the block of x in shared memory (sjds_bulk.cu)
+    {   // every block of the local part has the same rows (lengths depend on the down configuration only): periodic metadata
+        int64_t g = 32, r = Dd % 32;
+        while (r) { const int64_t t = g % r; g = r; r = t; }               // gcd(32, Dd)
+        const int64_t pb = 32 / g;                                          // blocks per period
+        static const bool off = getenv("QBGPU_PERIODIC_META") && atoi(getenv("QBGPU_PERIODIC_META")) == 0;
+        if (!off && (u_hi - u_lo) >= 2 * pb) { A->period_slices = pb * Dd / 32; A->period_entries = pb * (S->tot_d + Dd); }
+    }
 #define QB_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qbgpu_destroy(A); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
     QB_CU(cudaMalloc(&A->rowptr, sizeof(int64_t) * (nloc + 1)));
     QB_CU(cudaMalloc(&C->rowptr, sizeof(int64_t) * (nloc + 1)));

@@ -50,6 +50,9 @@ struct qbgpu_matrix {
     void    *sp = nullptr;
     qbgpu_matrix *second = nullptr;
     int32_t *slice_order = nullptr;
+    // per traversal item: x = the slice (= slice_order[it]), y = 0x80000000 | len when the slice's 32 rows all have `len` entries and
+    // rank = row (the producer of the bulk-streamed kernel then needs no rowinfo load: 8 bytes per slice instead of 4 + 128)
+    uint2   *ord_desc = nullptr;
     // > 0: rows [u*block_D, (u+1)*block_D) reference only columns of the same block (the local part of a species handle):
     // the product may stage the block of x in shared memory (sjds_bulk.cu: sjds_block_smem_kernel)
     int64_t  block_D = 0;

@@ -125,7 +125,8 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
                       const VecT *__restrict__ x, const VecT *z, VecT *y, double2 alpha, double2 gamma, double2 beta,
                       int scal_mode, const double *__restrict__ sc, double *dots_out, double *partials, unsigned *ticket,
                       const double *__restrict__ vdict, const int32_t *__restrict__ order,
-                      const int32_t *__restrict__ perm_inv = nullptr, double2 *y_ref = nullptr, double2 out_alpha = {1.0, 0.0})
+                      const int32_t *__restrict__ perm_inv = nullptr, double2 *y_ref = nullptr, double2 out_alpha = {1.0, 0.0},
+                      const uint2 *__restrict__ ord_desc = nullptr)
 {
     static_assert(!OUT || (sizeof(VecT) == 8 && !DOTS), "the fused way out serves the fp64 closing pass");
     using VT = VecTraits<VecT>;
@@ -171,18 +172,31 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
     const int stride = (int)gridDim.x * NW;                // (slice counts are < 2^31: rows < 2^31 by the int32 columns)
     const int nsl = (int)nslices;
     int p_it = (int)blockIdx.x * NW + warp;
-    auto slice_of = [&](int it) -> int { if constexpr (ORD) return it < nsl ? order[it] : 0; else return it; };
+    // traversal item -> (slice, descriptor).  With descriptors (qbgpu_matrix::ord_desc) one 8-byte load names the slice AND, for a
+    // slice whose 32 rows all have the same length in rank = row order (most of a cross part), replaces the 128-byte rowinfo load
+    auto item_of = [&](int it) -> uint2 {
+        if constexpr (ORD) {
+            if (it >= nsl) return make_uint2(0u, 0u);
+            if (ord_desc) return ord_desc[it];
+            return make_uint2((uint32_t)order[it], 0u);
+        } else return make_uint2((uint32_t)it, 0u);
+    };
+    auto info_of = [&](uint2 d) -> uint32_t {
+        return (d.y & 0x80000000u) ? (((uint32_t)lane << 24) | (d.y & kLenMaskB)) : rowinfo[(int64_t)d.x * 32 + lane];
+    };
     bool p_more = p_it < nsl;
-    int ps = slice_of(p_it);
-    uint32_t pinfo = p_more ? rowinfo[(int64_t)ps * 32 + lane] : 0u;
+    const uint2 pd = item_of(p_it);
+    int ps = (int)pd.x;
+    uint32_t pinfo = p_more ? info_of(pd) : 0u;
     int64_t pbase = p_more ? rowptr[(int64_t)ps * 32] : 0;
     int pk = 0, poff = 0;
     // one slice ahead: requested when the producer enters a slice, consumed when it enters the next (no exposed latency)
     int n_it = p_it + stride;
-    int ns = slice_of(n_it);
-    uint32_t ninfo = n_it < nsl ? rowinfo[(int64_t)ns * 32 + lane] : 0u;
+    const uint2 nd0 = item_of(n_it);
+    int ns = (int)nd0.x;
+    uint32_t ninfo = n_it < nsl ? info_of(nd0) : 0u;
     int64_t nbase = n_it < nsl ? rowptr[(int64_t)ns * 32] : 0;
-    int nn_s = slice_of(n_it + stride);                                              // ORD: the index after that (a dependent load)
+    uint2 nn_d = item_of(n_it + stride);                                             // ORD: the item after that (a dependent load)
 
     uint32_t phases = 0;                                   // bit s = parity the consumer waits for on stage s
     int n_issued = 0;                                      // segments issued so far; segment i lives in stage i % NST
@@ -221,11 +235,11 @@ spmv_sjds_bulk_kernel(int64_t nslices, int64_t nrows, int64_t row_lo, const int6
             p_more = p_it < nsl;
             ps = ns; pinfo = ninfo; pbase = nbase; pk = 0; poff = 0;
             n_it += stride;
-            ns = nn_s;
+            ns = (int)nn_d.x;
             const bool nv = n_it < nsl;
-            ninfo = nv ? rowinfo[(int64_t)ns * 32 + lane] : 0u;
+            ninfo = nv ? info_of(nn_d) : 0u;
             nbase = nv ? rowptr[(int64_t)ns * 32] : 0;
-            nn_s = slice_of(n_it + stride);
+            nn_d = item_of(n_it + stride);
         }
     };
 
@@ -409,7 +423,8 @@ static int launch_bulk_cfg(const qbgpu_matrix *A, const FusedArgs &a)
     kern<<<grid, NW * 32, smem, c.stream>>>(nslices, nrows, A->row_lo, A->rowptr, A->rowinfo, A->col, (const ValT *)A->val,
                                             (const VecT *)a.x, (const VecT *)a.z, (VecT *)a.y, a.alpha, a.gamma, a.beta,
                                             a.scal_mode, a.sc, a.dots, c.partials, c.ticket, A->vdict, A->slice_order,
-                                            OUT ? a.perm_inv : nullptr, OUT ? (double2 *)a.y_ref : nullptr, a.out_alpha);
+                                            OUT ? a.perm_inv : nullptr, OUT ? (double2 *)a.y_ref : nullptr, a.out_alpha,
+                                            ORD ? A->ord_desc : nullptr);
     QB_LAUNCH_COUNT();
     QB_CUDA(cudaGetLastError());
     return QBGPU_OK;

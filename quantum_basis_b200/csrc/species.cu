@@ -350,6 +350,20 @@ __global__ void __launch_bounds__(kPBlock) species_fill_kernel(SpeciesView V, in
 
 
 // traversal order of the cross part's 32-row slices: by (tile of the slice's first down index, slice index)
+__global__ void __launch_bounds__(256) ord_desc_kernel(int64_t nsl, const int32_t *__restrict__ order, const uint32_t *__restrict__ rowinfo, uint2 *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x / 32;
+    for (int64_t it = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); it < nsl; it += (int64_t)gridDim.x * wpb) {
+        const int s = order[it];
+        const uint32_t info = rowinfo[(int64_t)s * 32 + lane];
+        const uint32_t len0 = __shfl_sync(0xffffffffu, info, 0) & 0xFFFFFFu;
+        const bool same = (info >> 24) == (uint32_t)lane && (info & 0xFFFFFFu) == len0;
+        const bool uni = __all_sync(0xffffffffu, same);
+        if (lane == 0) out[it] = make_uint2((uint32_t)s, uni ? (0x80000000u | len0) : 0u);
+    }
+}
+
 static void make_slice_order(int64_t n, int64_t Dd, int W, std::vector<int32_t> &order)
 {
     const int64_t ns = (n + 31) / 32;
@@ -429,7 +443,20 @@ int species_build_stored(qbgpu_matrix_t *out, const HostTables &T, const ModelPa
     std::vector<int32_t> order;
     make_slice_order(nloc, Dd, S->tile, order);
     QB_CU(upload(&C->slice_order, order.data(), order.size(), c.stream));
+    {   // traversal descriptors of the cross part (sjds_bulk.cu): most of its slices hold 32 rows of one up configuration, all
+        // with the same number of up hops.  Opt-in (QBGPU_ORD_DESC=1): measured on BASELINE config 3 it saves 0.5 GB of rowinfo
+        // traffic per product and is still 0.12 ms SLOWER through MultMv (16.75 against 16.63 ms on the same box; the Lanczos
+        // loop gains 1 %): the rowinfo loads were prefetched a slice ahead anyway, the synthesis adds producer instructions.
+        static const bool on = getenv("QBGPU_ORD_DESC") && atoi(getenv("QBGPU_ORD_DESC")) != 0;
+        const int64_t nsl = (int64_t)order.size();
+        if (on && nsl > 0 && C->rowinfo) {
+            QB_CU(cudaMalloc(&C->ord_desc, sizeof(uint2) * (size_t)nsl));
+            ord_desc_kernel<<<(int)std::min<int64_t>((nsl + 7) / 8, 148 * 16), 256, 0, c.stream>>>(nsl, C->slice_order, C->rowinfo, C->ord_desc);
+            QB_LAUNCH_COUNT();
+        }
+    }
     QB_CU(cudaStreamSynchronize(c.stream));
+    QB_CU(cudaGetLastError());
 #undef QB_CU
     S->matfree = false;
     A->convert_s = wall_s() - t0;
@@ -1256,6 +1283,7 @@ int qbgpu_row_view(qbgpu_matrix_t A, int64_t r0, int64_t r1, int64_t tile_period
         std::vector<int32_t> order;
         make_slice_order(r1 - r0, tile_period, tile < 32 ? 64 : tile, order);
         V->slice_order = nullptr;
+        V->ord_desc = nullptr;                              // (the descriptors describe the whole part's traversal)
         cudaError_t e = upload(&V->slice_order, order.data(), order.size(), ctx().stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
         if (e != cudaSuccess) { cudaFree(V->slice_order); delete V; return cuda_fail(e, "row_view: slice order", __FILE__, __LINE__); }

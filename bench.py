@@ -45,11 +45,11 @@ WORKLOADS = {
 }
 L2_BYTES = 126e6
 # DRAM bytes per product (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu captures, per workload
-# the species step (profiles/r02_mv_reference_order_fused_out_launches.csv): way in 3.43 + 1.36, pass 1 40.43 + 1.31,
-# pass 2 (writes the reference's order itself) 40.34 + 2.85 GB
-TRAFFIC_NCU_SPECIES = {"hubbard4x4": 89720000000}
-KERNEL_SHARES_SPECIES = {"hubbard4x4": {"to_native_tiled_kernel": 0.057, "sjds_block_smem_kernel": 0.476, "spmv_sjds_bulk_kernel": 0.466,
-                                        "source": "profiles/r02_mv_reference_order_fused_out_launches.csv (ncu gpu__time_duration.sum: 0.95 / 7.94 / 7.77 ms)"}}
+# the species step (profiles/r02_ncu_full_mv_reference_order_hubbard4x4.csv): way in 3.43 + 1.36, pass 1 38.90 + 1.29,
+# pass 2 (writes the reference's order itself) 40.33 + 2.84 GB
+TRAFFIC_NCU_SPECIES = {"hubbard4x4": 88150000000}
+KERNEL_SHARES_SPECIES = {"hubbard4x4": {"to_native_tiled_kernel": 0.057, "sjds_block_smem_kernel": 0.474, "spmv_sjds_bulk_kernel": 0.469,
+                                        "source": "profiles/r02_ncu_full_mv_reference_order_hubbard4x4.csv (ncu gpu__time_duration.sum: 0.95 / 7.80 / 7.71 ms)"}}
 TRAFFIC_NCU = {"hubbard4x4": 133686405000,     # profiles/r01_ncu_full_spmv_sjds_hubbard4x4_details.csv: 131.03 GB read + 2.65 GB write
                "tri31_k10": 13300097712,       # profiles/r01_ncu_full_spmv_sjds_tri31_k10_details.csv: 13.14 GB read + 0.158 GB write
                "heis_chain32_k0": 8834161656}  # profiles/r01_ncu_full_spmv_sjds_heis_chain32_k0_details.csv: 8.53 GB read + 0.302 GB write
@@ -73,38 +73,81 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (clocks + throttle reasons)."""
+    """SM clock and throttle reasons DURING the timed region.  Samples come from NVML in a thread of this process (20 ms period,
+    time-stamped; no process start-up inside a sub-second region); if NVML cannot be used, from an `nvidia-smi -lms` child.  The
+    sampler is started before the warm-up; begin() / stop() mark the timed window and only samples inside it count (if the window
+    was too short to catch one, the samples nearest to it are used and `samples_in_window` says 0)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1, self.max_mhz = index, [], None, None, None, None
+        self._stop = threading.Event()
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.time(), mhz, {name for bit, name in self.REASONS if mask & bit}))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.02)
+            threading.Thread(target=loop, daemon=True).start()
+            self.source = "nvml"
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 8 and r[1].replace(".", "").isdigit():
+                if r[2].replace(".", "").isdigit():
+                    self.max_mhz = max(self.max_mhz or 0.0, float(r[2]))
+                names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                self.rows.append((time.time(), float(r[1]), {n for n, v in zip(names, r[4:8]) if v.lower().startswith("active")}))
+
+    def begin(self):
+        self.t0 = time.time()
 
     def stop(self):
+        self.t1 = time.time()
+        time.sleep(0.03)                                   # (let a sample that straddles the end land)
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = list(self.rows)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for r in rows if t0 <= r[0] <= self.t1 + 0.03]
+        used = inside
+        if not used and rows:                              # window shorter than the sampling period: the nearest samples
+            used = sorted(rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - self.t1)))[:2]
+        sm = sorted(r[1] for r in used)
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in used:
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(used), "samples_in_window": len(inside), "source": self.source}
 
 
 def algorithmic_bytes(nnz, nrows_local, n, s_val, s_vec):
@@ -479,14 +522,15 @@ def main():
 
     x = qb.vec_randomize(n, 1, device=True)
     y = qb.DeviceVector(n)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                         # running before the warm-up; begin() marks the timed window
     for _ in range(args.warmup):
         M.MultMv(x, y)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     L.qbgpu_kernel_launches(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    sampler.begin()
     wall0 = time.time()
     for k in range(args.steps):
         if need_flush:

@@ -170,4 +170,24 @@ int cg_update_vr(int64_t n, bool cplx, const double *sc, void *v, void *r, const
 int cg_update_p(int64_t n, bool cplx, double *sc, const void *r, void *p);
 int scale_copy(int64_t n, bool cplx, const double *scale_dev, double scale_imm, const void *src, void *dst);
 
+// Scope guards for the device buffers and events of a function that leaves early through QB_TRY / QB_CUDA (an error after an
+// allocation -- e.g. out of memory at BASELINE config 3 -- must not leave the earlier ones behind: a retry would fail too).
+struct DevBufGuard {
+    void *p = nullptr;
+    DevBufGuard() = default;
+    DevBufGuard(const DevBufGuard &) = delete;
+    DevBufGuard &operator=(const DevBufGuard &) = delete;
+    ~DevBufGuard() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+template <int N> struct EventGuard {
+    cudaEvent_t e[N] = {};
+    int n = 0;
+    EventGuard() = default;
+    EventGuard(const EventGuard &) = delete;
+    EventGuard &operator=(const EventGuard &) = delete;
+    ~EventGuard() { for (int i = 0; i < n; i++) cudaEventDestroy(e[i]); }
+    cudaError_t create(unsigned flags = cudaEventDefault) { cudaError_t r = cudaEventCreateWithFlags(&e[n], flags); if (r == cudaSuccess) n++; return r; }
+};
+
 }  // namespace qb

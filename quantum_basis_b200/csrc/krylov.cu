@@ -193,9 +193,10 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     int64_t m = k;
     // QBGPU_VERBOSE: per-phase device time of the loop (events around the three passes) and host time of the stop rule
     const bool prof = getenv("QBGPU_VERBOSE") != nullptr;
-    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+    EventGuard<4> pg;                                       // (destroyed on every way out of the loop, error returns included)
     double t_a = 0, t_b = 0, t_c = 0, t_host = 0;
-    if (prof) for (auto &e : pe) QB_CUDA(cudaEventCreate(&e));
+    if (prof) for (int i = 0; i < 4; i++) QB_CUDA(pg.create());
+    cudaEvent_t *pe = pg.e;
     while (m < mm) {
         m++;
         // one fused Lanczos step (src/lanczos.cc:167-187 for m == 1, :194-214 otherwise)
@@ -262,7 +263,6 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
     if (prof) {
         fprintf(stderr, "[qbgpu lanczos] %lld steps, per step: product+epilogue %.3f ms, update pass %.3f ms, scalar kernel %.4f ms, host stop rule %.3f ms (n=%lld, %s vectors)\n",
                 (long long)m, t_a / m, t_b / m, t_c / m, t_host / m, (long long)n, cplx ? "complex" : "fp64");
-        for (auto &e : pe) cudaEventDestroy(e);
     }
     *m_out = m;
     if (stop_state && is_val && m > k) {

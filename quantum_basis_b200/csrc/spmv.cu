@@ -169,14 +169,16 @@ int autotune(qbgpu_matrix *A, int flags)
     if ((flags & QBGPU_NO_AUTOTUNE) || nrows < 4096) return QBGPU_OK;
     const bool verbose = getenv("QBGPU_VERBOSE") != nullptr;
     const size_t vb = A->vec_bytes();
-    void *x = nullptr, *y = nullptr;
-    QB_CUDA(cudaMalloc(&x, vb * (size_t)A->n));
-    QB_CUDA(cudaMalloc(&y, vb * (size_t)nrows));
+    DevBufGuard gx, gy;                                     // (freed on every way out of this function)
+    EventGuard<3> ge;
+    QB_CUDA(gx.alloc(vb * (size_t)A->n));
+    QB_CUDA(gy.alloc(vb * (size_t)nrows));
+    void *x = gx.p, *y = gy.p;
     QB_TRY(vec_randomize(A->n, A->api_complex, x, 1));
-    cudaEvent_t e0, e1, t0;
-    QB_CUDA(cudaEventCreate(&e0));
-    QB_CUDA(cudaEventCreate(&e1));
-    QB_CUDA(cudaEventCreate(&t0));
+    QB_CUDA(ge.create());
+    QB_CUDA(ge.create());
+    QB_CUDA(ge.create());
+    const cudaEvent_t e0 = ge.e[0], e1 = ge.e[1], t0 = ge.e[2];
     FusedArgs a;
     a.x = x; a.y = y;
     auto time3 = [&](int l, float &ms) -> int {
@@ -211,8 +213,6 @@ int autotune(qbgpu_matrix *A, int flags)
     QB_CUDA(cudaEventSynchronize(e1));
     QB_CUDA(cudaEventElapsedTime(&tot, t0, e1));
     A->autotune_s = tot * 1e-3;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0);
-    cudaFree(x); cudaFree(y);
     return QBGPU_OK;
 }
 
@@ -248,8 +248,9 @@ static int mv_host(const qbgpu_matrix *A, double2 alpha, const void *x, double2 
     QB_CUDA(cudaMemcpyAsync(c.stage_x, x, vb * (size_t)A->n, cudaMemcpyHostToDevice, c.stream));
     if (use_beta) QB_CUDA(cudaMemcpyAsync(c.stage_y, y, vb * (size_t)nloc, cudaMemcpyHostToDevice, c.stream));
     const int chunks = nloc >= (1 << 20) ? 8 : 1;
-    cudaEvent_t ev[8];
-    for (int k = 0; k < chunks; k++) QB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    EventGuard<8> ge;                                       // (destroyed on every way out)
+    for (int k = 0; k < chunks; k++) QB_CUDA(ge.create(cudaEventDisableTiming));
+    cudaEvent_t *ev = ge.e;
     for (int k = 0; k < chunks; k++) {
         // chunk boundaries on multiples of 32 rows so that a chunk is a whole number of slices in either layout
         const int64_t r0 = (nloc * k / chunks) & ~31LL, r1 = (k + 1 == chunks) ? nloc : ((nloc * (k + 1) / chunks) & ~31LL);
@@ -271,7 +272,6 @@ static int mv_host(const qbgpu_matrix *A, double2 alpha, const void *x, double2 
     }
     QB_CUDA(cudaStreamSynchronize(c.copy_stream));
     QB_CUDA(cudaStreamSynchronize(c.stream));
-    for (int k = 0; k < chunks; k++) cudaEventDestroy(ev[k]);
     return QBGPU_OK;
 }
 
@@ -296,8 +296,9 @@ static int mv_real_mode(qbgpu_matrix *A, double2 alpha, const void *x, double2 b
     if (use_beta) QB_TRY(vec_imag_norm2(n, y, t + 1));
     QB_TRY(read_scalars(t, h, use_beta ? 2 : 1));
     if (h[0] != 0.0 || h[1] != 0.0) return QBGPU_OK;
-    if (!A->perm_x) QB_CUDA(cudaMalloc(&A->perm_x, sizeof(double) * (size_t)n));
-    if (!A->perm_y) QB_CUDA(cudaMalloc(&A->perm_y, sizeof(double) * (size_t)n));
+    // (an allocation failure here is not an error of the product: fall back to the complex kernels)
+    if (!A->perm_x && cudaMalloc(&A->perm_x, sizeof(double) * (size_t)n) != cudaSuccess) { (void)cudaGetLastError(); A->perm_x = nullptr; return QBGPU_OK; }
+    if (!A->perm_y && cudaMalloc(&A->perm_y, sizeof(double) * (size_t)n) != cudaSuccess) { (void)cudaGetLastError(); A->perm_y = nullptr; return QBGPU_OK; }
     QB_TRY(vec_take_real(n, x, (double *)A->perm_x));
     if (use_beta) QB_TRY(vec_take_real(n, y, (double *)A->perm_y));
     qbgpu_matrix R = *A;                                    // same arrays, fp64 vectors

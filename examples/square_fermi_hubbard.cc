@@ -1,4 +1,4 @@
-// examples/square_fermi_hubbard.cc -- the ground-state part of the reference's
+// examples/square_fermi_hubbard.cc -- the reference's
 // examples/trans_absent/latt_square/square_Fermi_Hubbard.cc on the GPU through the C++ adaptor: the Lx x Ly Fermi-Hubbard
 // model (periodic, t = 1, U = 1.1) at fixed N_up, N_dn, generated in HBM in the reference's basis order and sign
 // convention, E0 by the fused device Lanczos with the reference's argument list -- through the ordinary handle, through
@@ -69,6 +69,36 @@ int main(int argc, char **argv)
             if (k == 0) first = E0;
             if (std::abs(E0 - first) > 1e-10 * std::abs(first)) bad++;
             if (Lx == 4 && Ly == 2 && nup == 4 && ndn == 4 && std::abs(E0 + 14.07605866) > 1e-8) bad++;   // square_Fermi_Hubbard.cc:112
+        }
+        // The momentum-resolved part (examples/trans_symmetric/latt_square/square_Fermi_Hubbard.cc): every (m, n) sector built on
+        // the device with the reference's representatives, norms and matrix elements, E0 per sector.  Their minimum is the E0
+        // above; for 4 x 2 at (4, 4) the list is the reference's E0_list (:112-119, index = Ly m + n).
+        if (Lx * Ly <= 16 && Lx % 2 == 0) {                            // (the site numbering above is the sector code's when x is the even direction)
+            const double E0_list_4x2[8] = {-14.07605866, -10.50470669, -12.16861094, -12.19847764, -10.54300366, -14.03137587, -12.16861094, -12.19847764};
+            std::vector<int32_t> hops;                                   // per bond: c+_up,i c_up,j ; c+_up,j c_up,i ; c+_dn,i c_dn,j ; c+_dn,j c_dn,i
+            // the sector code numbers sites with the first even direction fastest (src/lattice.cc:591-615); for Lx even that is x
+            for (size_t b = 0; b + 1 < bonds.size(); b += 2)
+                for (int sp = 0; sp < 2; sp++) {
+                    hops.push_back(bonds[b]); hops.push_back(bonds[b + 1]); hops.push_back(sp);
+                    hops.push_back(bonds[b + 1]); hops.push_back(bonds[b]); hops.push_back(sp);
+                }
+            double lowest = 1e300;
+            int64_t live = 0;
+            const auto t2 = std::chrono::steady_clock::now();
+            for (int m = 0; m < Lx; m++)
+                for (int n = 0; n < Ly; n++) {
+                    qbgpu::electron_sector sec({Lx, Ly}, nup, ndn, {m, n});
+                    live += sec.dim() - sec.info.zero_norm;
+                    auto H = sec.hubbard(hops, t, U);
+                    int64_t steps = 0;
+                    const double E = E0_by_lanczos(H, steps);
+                    std::printf("  k = (%d,%d)  dim = %lld (%lld with zero norm)  E0 = %.10f\n", m, n, (long long)sec.dim(), (long long)sec.info.zero_norm, E);
+                    if (E < lowest) lowest = E;
+                    if (Lx == 4 && Ly == 2 && nup == 4 && ndn == 4 && std::abs(E - E0_list_4x2[Ly * m + n]) > 1e-8) bad++;
+                }
+            std::printf("momentum sectors: %lld live representatives in all sectors, lowest E0 = %.10f, %.2f s\n", (long long)live, lowest,
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - t2).count());
+            if (std::abs(lowest - first) > 1e-8) bad++;
         }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());

@@ -134,6 +134,43 @@ public:
         check(qbgpu_sector_build_heisenberg(handle, &h, static_cast<int>(bonds.size() / 2), bonds.data(), J, fake_pos, flags), "qbgpu_sector_build_heisenberg");
         return csr_mat<std::complex<double>>::adopt(h);
     }
+    // the same operator without stored entries: model<T>::MultMv2 with matrix_free == true, repr branch (src/model.cc:1016-1107).
+    // The handle borrows this sector's tables: let it go out of scope before the sector does.
+    csr_mat<std::complex<double>> heisenberg_matrix_free(const std::vector<int32_t> &bonds, double J = 1.0, double fake_pos = 100.0) const
+    {
+        qbgpu_matrix_t h = nullptr;
+        check(qbgpu_sector_matfree_heisenberg(handle, &h, static_cast<int>(bonds.size() / 2), bonds.data(), J, fake_pos), "qbgpu_sector_matfree_heisenberg");
+        return csr_mat<std::complex<double>>::adopt(h);
+    }
+};
+
+// One (N_up, N_dn, momentum) sector of single-orbital electrons (the reference's "electron" orbital: two bits per site, bit 0 up,
+// bit 1 down; at most 16 sites): fill_Weisse_table + enumerate_basis_repr + generate_Ham_sparse_repr of
+// examples/trans_symmetric/latt_square/square_Fermi_Hubbard.cc on the device, fermionic translation signs included.
+class electron_sector {
+public:
+    qbgpu_sector_t handle = nullptr;
+    qbgpu_sector_info info{};
+    electron_sector(const std::vector<int> &L, int nup, int ndn, const std::vector<int> &momentum)
+    {
+        if (L.size() != momentum.size()) throw std::runtime_error("qbgpu::electron_sector: one momentum integer per lattice direction");
+        std::vector<int32_t> l(L.begin(), L.end()), k(momentum.begin(), momentum.end());
+        check(qbgpu_sector_create_electron(&handle, static_cast<int>(l.size()), l.data(), nup, ndn, k.data()), "qbgpu_sector_create_electron");
+        check(qbgpu_sector_get_info(handle, &info), "qbgpu_sector_get_info");
+    }
+    electron_sector(const electron_sector &) = delete;
+    electron_sector &operator=(const electron_sector &) = delete;
+    ~electron_sector() { if (handle) qbgpu_sector_destroy(handle); }
+    int64_t dim() const { return info.dim; }
+    std::vector<uint32_t> states() const { std::vector<uint32_t> s(info.dim); check(qbgpu_sector_states(handle, s.data()), "qbgpu_sector_states"); return s; }
+    std::vector<double> norms() const { std::vector<double> s(info.dim); check(qbgpu_sector_norms(handle, s.data()), "qbgpu_sector_norms"); return s; }
+    // H = -t sum_hops c+_{to,s} c_{from,s} + U sum_i n_up,i n_dn,i ; hops = {to0, from0, spin0, to1, ...} DIRECTED, in add_Ham order
+    csr_mat<std::complex<double>> hubbard(const std::vector<int32_t> &hops, double t = 1.0, double U = 1.1, double fake_pos = 100.0, int flags = 0) const
+    {
+        qbgpu_matrix_t h = nullptr;
+        check(qbgpu_sector_build_hubbard(handle, &h, static_cast<int>(hops.size() / 3), hops.data(), t, U, fake_pos, flags), "qbgpu_sector_build_hubbard");
+        return csr_mat<std::complex<double>>::adopt(h);
+    }
 };
 
 }  // namespace qbgpu

@@ -653,7 +653,8 @@ def main():
                          "kernel_shares_ncu": (KERNEL_SHARES_SPECIES.get(args.workload) if args.layout == "species" else None)},
             "e2e": {"value": 1.0 / e2e_s, "unit": "H*v/s", "h2d_bytes_per_step": n * s_vec, "d2h_bytes_per_step": n * s_vec,
                     "ms_per_step": 1e3 * e2e_s},
-            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall, "parity_sampled": parity,
+            "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall,
+            "ms_per_step_median": sorted(per_step_ms)[len(per_step_ms) // 2], "ms_per_step_min": min(per_step_ms), "parity_sampled": parity,
             "host_phases": {"generate_matrix_s": t_build, "autotune_s": inf.autotune_seconds, **SECTOR_PHASES}}
     line.update(extras)
 

@@ -436,8 +436,14 @@ int qbgpu_dist_own(qbgpu_dist_t D, int b, void **own_slice_dev, int64_t *nloc); 
 int qbgpu_dist_full(qbgpu_dist_t D, int b, void **full_vector_dev);
 int qbgpu_dist_barrier(qbgpu_dist_t D);                                            /* stream-ordered, device-side */
 int qbgpu_dist_allreduce(qbgpu_dist_t D, double *dev, int count);                  /* in-place sum of <= 8 device doubles, rank order */
+/* own slice of X[b] <- this rank's rows of vec_randomize(n, seed) (src/miscellaneous.cc:371-388), normalised over all ranks;
+ * opens and closes with a barrier (no peer is still reading the slice; every slice is final before anybody pulls) */
 int qbgpu_dist_randomize(qbgpu_dist_t D, int b, uint32_t seed, const int32_t *ref_row_dev);
 int qbgpu_species_ref_rows(int nsites, int nup, int ndn, int64_t row_lo, int64_t row_hi, int32_t *ref_rows_dev);
+/* y_local = (H x)_local with x = X[b].  Who may touch a slice when: a rank's own product is finished once ITS pulls are, while
+ * its peers may still be reading its slice of X[b].  barrier bit 0 (1): barrier BEFORE the pulls (the slices the caller just
+ * wrote are final everywhere); bit 1 (2): barrier AFTER the product (every rank's pulls are done: the own slice of X[b] may be
+ * rewritten).  Without bit 1 write the next x into the other buffer (the loops below ping-pong) or call qbgpu_dist_barrier. */
 int qbgpu_dist_mv(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int b, void *y_local_dev, int barrier);
 /* lanczos(0, np, maxit, ...) of src/lanczos.cc:134-266 on the shards: "sr_val0" with the stop rule of :228-248, or "dnmcs" */
 int qbgpu_dist_lanczos(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int64_t np, int64_t maxit, int64_t *m,

@@ -486,6 +486,10 @@ int qbgpu_dist_randomize(qbgpu_dist_t D, int b, uint32_t seed, const int32_t *re
     Context &c = ctx();
     const int64_t nloc = D->nloc();
     if (seed == 0) return fail(QBGPU_ERR_ARG, "dist_randomize: seed 0 (the constant vector) is not a shard case");
+    // opening barrier: a peer may still be pulling this rank's slice of X[b] for a product the caller issued before (a rank's
+    // own product is done as soon as ITS pulls are; nothing tells it about its readers) -- the slice is first written
+    // unnormalised and then scaled in place, so a reader caught in between would multiply by a half-scaled vector
+    QB_TRY(dist_allreduce(D, D->scal, 0));
     if (nloc) {
         const int grid = (int)std::min<int64_t>((nloc + 255) / 256, 148 * 16);
         if (D->cplx) dist_randomize_kernel<double2><<<grid, 256, 0, c.stream>>>(nloc, D->lo(), ref_row, (double2 *)D->own(b), seed);
@@ -503,17 +507,22 @@ int qbgpu_dist_randomize(qbgpu_dist_t D, int b, uint32_t seed, const int32_t *re
     return dist_timed_out(D, "dist_randomize");
 }
 
-/* y_local = H x: x = X[b] (own slice written by the caller), y_local: this rank's rows.  barrier != 0: pass a barrier first
- * (needed unless the caller's last call on this context was already an all-reduce after x was written). */
+/* y_local = H x: x = X[b] (own slice written by the caller), y_local: this rank's rows.  barrier bit 0 (1): pass a barrier
+ * first -- the peers' slices are final before they are pulled (needed unless the caller's last call on this context was
+ * already an all-reduce after x was written).  barrier bit 1 (2): pass a barrier after the product as well -- every rank's
+ * pulls of X[b] are complete, so the caller may overwrite its own slice of X[b] as soon as the call's work is done on the
+ * stream (without it, write the next x into the OTHER buffer, like the Krylov loops here do, or call qbgpu_dist_barrier). */
 int qbgpu_dist_mv(qbgpu_dist_t D, qbgpu_matrix_t local_part, qbgpu_matrix_t rest, int b, void *y_local, int barrier)
 {
     QB_TRY(ensure_init());
     QB_TRY(dist_check(D, local_part, rest));
     if (!y_local || (b != 0 && b != 1)) return fail(QBGPU_ERR_ARG, "dist_mv: bad argument");
-    if (barrier) QB_TRY(dist_allreduce(D, D->scal, 0));
+    if (barrier & 1) QB_TRY(dist_allreduce(D, D->scal, 0));
     FusedArgs a;
     a.y = y_local;
-    return dist_product(D, local_part, rest, b, a);
+    QB_TRY(dist_product(D, local_part, rest, b, a));
+    if (barrier & 2) QB_TRY(dist_allreduce(D, D->scal, 0));
+    return QBGPU_OK;
 }
 
 /* lanczos(0, np, maxit, m, dim, H, v, hessenberg, purpose) of src/lanczos.cc:134-266 on the shards.  Start: the normalised

@@ -610,6 +610,7 @@ class NativeDist:
         return m.handle if m is not None else None
 
     def mv(self, local, rest, b, y_ptr, barrier=True):
+        """barrier: True / 1 = before the pulls; 3 = also after the product (the own slice of X[b] may then be rewritten)"""
         self._chk(self.L.qbgpu_dist_mv(self.h, self._hp(local), rest.handle, b, C.c_void_p(y_ptr), int(barrier)))
 
     def lanczos(self, local, rest, np_, maxit, purpose="sr_val0", stop_on_breakdown=True):
@@ -1008,7 +1009,7 @@ def bench_sharded_species(args, WORKLOADS, algorithmic_bytes, measured_peak, Clo
 
             def e2e_step():
                 assert L.qbgpu_memcpy_h2d(C.c_void_p(D.own(0)), C.c_void_p(xh.data_ptr()), nloc * 8) == 0
-                D.mv(loc, cross, 0, y.data_ptr(), barrier=True)
+                D.mv(loc, cross, 0, y.data_ptr(), barrier=3)       # closing barrier too: the next step rewrites the own slice of X[0]
                 assert L.qbgpu_memcpy_d2h(C.c_void_p(yh.data_ptr()), C.c_void_p(y.data_ptr()), nloc * 8) == 0
             for _ in range(2):
                 e2e_step()

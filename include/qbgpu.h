@@ -226,6 +226,25 @@ int qbgpu_lanczos_step_a(qbgpu_matrix_t A, const void *ux_full, void *uz_local, 
 int qbgpu_lanczos_step_a_part(qbgpu_matrix_t A_part, const void *ux_full, void *uz_local, double *state_dev, int first, int last);
 int qbgpu_lanczos_step_b(qbgpu_matrix_t A, const void *ux_local, void *uz_local, double *state_dev);
 int qbgpu_lanczos_step_c(double *state_dev, double *a_dev, double *b_dev, int64_t m);
+/* eigenvec_CG, one call per pass of the reference's loop body (src/lanczos.cc:293-332), for a host that keeps the loop and
+ * replaces its body; unsharded handles, DEVICE vectors in the handle's element type and order, E0 = {re, im} (im ignored by
+ * d handles).  sc (8 device doubles, zeroed by the caller before the first call): [0]=gamma=|r| [1,2]=delta=<p,pp>
+ * [3]=|pp|^2 [4]=|r_new|^2 [5]=gamma_next [6]=scratch -- carried from call to call.
+ *   cg_restart (:297-314): v /= |v| ; r = (E0 - H) v ; p = r ; *accu = |r| ; *vnorm (may be NULL) = |v| on entry.  The caller
+ *                          decides when (m == 0, or accu < 2e-12 with | |v| - 1 | > 2e-12: qbgpu_dznrm2 / qbgpu_dnrm2).
+ *   cg_step    (:320-330): pp = (H - E0 + eps) p ; alpha = gamma^2 / delta ; v += alpha p ; r -= alpha pp ;
+ *                          beta = |r_new| / gamma ; p = r + beta^2 p ; gamma *= beta ; *accu = gamma
+ * qbgpu_eigenvec_cg_* is exactly this sequence (same kernels, same order: bit-identical results). */
+int qbgpu_cg_restart(qbgpu_matrix_t A, const double E0[2], double *sc_dev, void *v, void *r, void *p, double *vnorm, double *accu);
+int qbgpu_cg_step(qbgpu_matrix_t A, const double E0[2], double *sc_dev, void *v, void *r, void *p, void *pp, double *accu);
+/* One step of the Chebyshev recurrence (KPM) as ONE fused product: Ht = (H - c)/s, c = (hi+lo)/2, s = (hi-lo)/2 (the bounds of
+ * qbgpu_energy_scale_*).  first != 0: t_next = Ht t_cur ; otherwise t_next = 2 Ht t_cur - t_prev (t_next may alias t_prev: the
+ * recurrence written over T_{k-1}).  dots (3 device doubles, may be NULL): <t_cur_local, t_next> (re, im) and |t_next|^2 over the
+ * local rows -- the inner products of mu_{2k+1} = 2<T_k,T_{k+1}> - mu_1 and mu_{2k+2} = 2|T_{k+1}|^2 - mu_0.  t_cur: the full
+ * vector (n entries); t_prev / t_next: the handle's local rows (shards: all-reduce the dots).  qbgpu_kpm_moments_* is a loop of
+ * these. */
+int qbgpu_cheb_step(qbgpu_matrix_t A, double lo, double hi, int first, const void *t_cur_full, const void *t_prev_local,
+                    void *t_next_local, double *dots_dev);
 
 /* ------------------------------------------------------------- peer-memory exchange over NVLink (multi-GPU)
  * One process per GPU.  A rank exports its vector buffers (CUDA IPC), maps its peers', and pulls the slices it needs

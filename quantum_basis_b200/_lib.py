@@ -75,6 +75,9 @@ _SIGS = {
     "qbgpu_peer_pull_async": [C.c_int, C.c_int, vp, vp, C.c_size_t], "qbgpu_peer_wait": [C.c_int], "qbgpu_ring_prepare": [vp, C.c_int, C.c_int, i64, C.POINTER(vp)], "qbgpu_peer_ring_reset": [],
     "qbgpu_peer_pull_flag": [C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int], "qbgpu_peer_ring_status": [vp], "qbgpu_peer_pull_sm": [C.c_int, C.c_int, vp, vp, C.c_size_t, C.c_int], "qbgpu_lanczos_step_b": [vp, vp, vp, vp],
     "qbgpu_lanczos_step_c": [vp, vp, vp, i64],
+    "qbgpu_cg_restart": [vp, vp, vp, vp, vp, vp, C.POINTER(dbl), C.POINTER(dbl)],
+    "qbgpu_cg_step": [vp, vp, vp, vp, vp, vp, vp, C.POINTER(dbl)],
+    "qbgpu_cheb_step": [vp, dbl, dbl, C.c_int, vp, vp, vp, vp],
     "qbgpu_build_heisenberg": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, dbl, C.c_int, C.c_int, i64, i64],
     "qbgpu_build_hubbard": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, dbl, dbl, C.c_int, C.c_int, i64, i64],
     "qbgpu_create_matfree_heisenberg": [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, dbl, C.c_int, C.c_int, i64, i64],

@@ -577,6 +577,72 @@ def eigenvec_CG(dim, maxit, m, mat, E0, v, r, p, pp):
     return mm.value, accu.value
 
 
+def eigenvec_CG_stepwise(dim, maxit, m, mat, E0, v, r, p, pp):
+    """The reference's eigenvec_CG loop (src/lanczos.cc:293-332) kept on the HOST, its body replaced by the step-level entry points
+    qbgpu_cg_restart / qbgpu_cg_step -- what a maintainer does who wants to keep the loop (logging, checkpoints) and move only the
+    arithmetic.  Device vectors in the handle's own order and element type; starts at m == 0.  Returns (m, accu); the same
+    kernels in the same order as eigenvec_CG, hence the same bits (when that one does not switch to fp64 vectors)."""
+    if dim != mat.dim or m != 0:
+        raise QbgpuError("eigenvec_CG_stepwise: dim must match the matrix and m must be 0")
+    if _where(v, r, p, pp) != _lib.QBGPU_DEVICE:
+        raise QbgpuError("eigenvec_CG_stepwise: device vectors only")
+    L = lib()
+    sc = DeviceVector(8, np.float64)
+    sc.zero()
+    e = (C.c_double * 2)(complex(E0).real, complex(E0).imag)
+    accu, vn = C.c_double(0.0), C.c_double(0.0)
+    nrm = L.qbgpu_dznrm2 if mat.is_complex else L.qbgpu_dnrm2
+    while m < maxit:
+        if accu.value < lanczos_precision:                                   # :295
+            check(nrm(dim, _ptr(v), C.byref(vn)))
+            if m == 0 or abs(vn.value - 1.0) > lanczos_precision:            # :297 re-normalise and restart
+                check(L.qbgpu_cg_restart(mat.handle, e, _ptr(sc), _ptr(v), _ptr(r), _ptr(p), C.byref(vn), C.byref(accu)))
+                m += 1
+                if accu.value < lanczos_precision:                           # :315
+                    break
+            else:
+                break                                                        # :317
+        else:
+            check(L.qbgpu_cg_step(mat.handle, e, _ptr(sc), _ptr(v), _ptr(r), _ptr(p), _ptr(pp), C.byref(accu)))      # :320-330
+            m += 1
+    sc.free()
+    return m, accu.value
+
+
+def kpm_moments_stepwise(mat, phi, lo, hi, nmom):
+    """kpm_moments as a host loop over qbgpu_cheb_step (one fused product per two moments); phi: a device vector in the handle's
+    order and element type.  Same products and epilogue sums as qbgpu_kpm_moments_*."""
+    if _where(phi) != _lib.QBGPU_DEVICE:
+        raise QbgpuError("kpm_moments_stepwise: device vectors only")
+    L = lib()
+    n = mat.dim
+    T = [phi.clone(), DeviceVector(n, phi.dtype)]
+    nprod = nmom // 2 + 1
+    dots = DeviceVector(4 * (nprod + 1), np.float64)
+    dots.zero()
+    for k in range(nprod):
+        cur, nxt = T[k % 2], T[(k + 1) % 2]
+        check(L.qbgpu_cheb_step(mat.handle, lo, hi, int(k == 0), _ptr(cur), _ptr(nxt), _ptr(nxt), C.c_void_p(dots.ptr + 8 * 4 * (k + 1))))
+    h = dots.to_numpy()
+    nn = C.c_double(0.0)
+    check((L.qbgpu_dznrm2 if mat.is_complex else L.qbgpu_dnrm2)(n, _ptr(phi), C.byref(nn)))
+    mu0, mu1 = nn.value ** 2, h[4]
+    mu = np.zeros(nmom)
+    for j in range(nmom):
+        if j == 0:
+            mu[j] = mu0
+        elif j == 1:
+            mu[j] = mu1
+        elif j % 2 == 0:
+            mu[j] = 2.0 * h[4 * (j // 2) + 2] - mu0                          # mu_{2k+2} = 2 |T_{k+1}|^2 - mu_0
+        else:
+            mu[j] = 2.0 * h[4 * ((j - 1) // 2 + 1)] - mu1                    # mu_{2k+1} = 2 <T_k, T_{k+1}> - mu_1
+    for t in T:
+        t.free()
+    dots.free()
+    return mu
+
+
 def energy_scale(dim, mat, v, extend=0.1, iters=128):
     """energy_scale<T,MAT>(dim, mat, v, lo, hi, extend, iters); returns (lo, hi) (src/kpm.cc:45-88)."""
     where = _where(v)

@@ -285,6 +285,42 @@ static int lanczos_impl(qbgpu_matrix *A, bool cplx, int64_t k, int64_t np, int64
 }
 
 // --------------------------------------------------------------------------------------------- eigenvec_CG
+// The two branches of the reference's loop body (src/lanczos.cc:295-331) on device vectors; sc: 8 device doubles
+// [0]=gamma=|r| [1,2]=delta [3]=|pp|^2 [4]=|r_new|^2 [5]=gamma_next [6]=scratch.  Shared by the whole loop (cg_impl) and by the
+// step-level entry points qbgpu_cg_restart_* / qbgpu_cg_step_*.
+// :297-314  v <- v / rnorm ; r = (E0 - H) v in one pass, |r|^2 from the epilogue ; p = r ; accu = |r| (left in sc[0] as gamma)
+static int cg_restart_piece(qbgpu_matrix *A, bool cplx, double2 E0, double rnorm, double *sc, char *dv, char *dr, char *dp, double *accu)
+{
+    Context &c = ctx();
+    const int64_t n = A->n;
+    const size_t vb = cplx ? 16 : 8;
+    QB_TRY(vec_scal(n, cplx, make_double2(1.0 / rnorm, 0.0), dv));
+    FusedArgs fa;
+    fa.x = dv; fa.y = dr; fa.alpha = make_double2(-1.0, 0.0); fa.gamma = E0; fa.dots = sc + 1;
+    QB_TRY(launch_spmv(A, fa));
+    QB_CUDA(cudaMemcpyAsync(dp, dr, vb * n, cudaMemcpyDeviceToDevice, c.stream));   // p = r
+    double h[3];
+    QB_TRY(read_scalars(sc + 1, h, 3));
+    *accu = sqrt(h[2]);
+    QB_CUDA(cudaMemcpyAsync(sc, accu, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    QB_CUDA(cudaStreamSynchronize(c.stream));
+    return QBGPU_OK;
+}
+// :320-330  pp = (H - E0 + eps) p ; delta = <p,pp> ; v += alpha p ; r -= alpha pp ; p = r + beta p ; accu = |r_new|
+static int cg_iterate_piece(qbgpu_matrix *A, bool cplx, double2 E0, double *sc, char *dv, char *dr, char *dp, char *dpp, double *accu)
+{
+    Context &c = ctx();
+    const int64_t n = A->n;
+    FusedArgs fa;
+    fa.x = dp; fa.y = dpp; fa.alpha = make_double2(1.0, 0.0);
+    fa.gamma = make_double2(DBL_EPSILON - E0.x, -E0.y); fa.dots = sc + 1;
+    QB_TRY(launch_spmv(A, fa));
+    QB_TRY(cg_update_vr(n, cplx, sc, dv, dr, dp, dpp));          // :324-327
+    QB_TRY(cg_update_p(n, cplx, sc, dr, dp));                    // :327-330
+    QB_CUDA(cudaMemcpyAsync(sc, sc + 5, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    return read_scalars(sc, accu, 1);
+}
+
 static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, double2 E0, double *accu_out,
                    void *v, void *r, void *p, void *pp, int where)
 {
@@ -329,30 +365,14 @@ static int cg_impl(qbgpu_matrix *A, bool cplx, int64_t maxit, int64_t *m_io, dou
             QB_TRY(read_scalars(sc + 6, &nn, 1));
             const double rnorm = sqrt(nn);
             if (m == 0 || fabs(rnorm - 1.0) > kLanczosPrecision) {       // :297 re-normalise and restart
-                QB_TRY(vec_scal(n, cplx, make_double2(1.0 / rnorm, 0.0), dv));
-                FusedArgs fa;                               // r = (E0 - H) v in one pass; |r|^2 from the epilogue
-                fa.x = dv; fa.y = dr; fa.alpha = make_double2(-1.0, 0.0); fa.gamma = E0; fa.dots = sc + 1;
-                QB_TRY(launch_spmv(A, fa));
-                QB_CUDA(cudaMemcpyAsync(dp, dr, vb * n, cudaMemcpyDeviceToDevice, c.stream));   // p = r
-                double h[3];
-                QB_TRY(read_scalars(sc + 1, h, 3));
-                accu = sqrt(h[2]);
-                QB_CUDA(cudaMemcpyAsync(sc, &accu, sizeof(double), cudaMemcpyHostToDevice, c.stream));
-                QB_CUDA(cudaStreamSynchronize(c.stream));
+                QB_TRY(cg_restart_piece(A, cplx, E0, rnorm, sc, dv, dr, dp, &accu));
                 m++;
                 if (accu < kLanczosPrecision) break;        // :315
             } else {
                 break;                                      // :317
             }
         } else {
-            FusedArgs fa;                                   // pp = (H - E0 + eps) p ; delta = <p,pp>   (:320-323)
-            fa.x = dp; fa.y = dpp; fa.alpha = make_double2(1.0, 0.0);
-            fa.gamma = make_double2(DBL_EPSILON - E0.x, -E0.y); fa.dots = sc + 1;
-            QB_TRY(launch_spmv(A, fa));
-            QB_TRY(cg_update_vr(n, cplx, sc, dv, dr, dp, dpp));          // :324-327
-            QB_TRY(cg_update_p(n, cplx, sc, dr, dp));                    // :327-330
-            QB_CUDA(cudaMemcpyAsync(sc, sc + 5, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-            QB_TRY(read_scalars(sc, &accu, 1));
+            QB_TRY(cg_iterate_piece(A, cplx, E0, sc, dv, dr, dp, dpp, &accu));     // :320-330
             m++;
         }
     }
@@ -771,5 +791,48 @@ int qbgpu_kpm_moments_d(qbgpu_matrix_t A, const double *phi, double lo, double h
 { return kpm_dispatch(A, false, phi, lo, hi, nmom, mu, where); }
 int qbgpu_kpm_moments_z(qbgpu_matrix_t A, const void *phi, double lo, double hi, int64_t nmom, double *mu, int where)
 { return kpm_dispatch(A, true, phi, lo, hi, nmom, mu, where); }
+
+// ---------------------------------------------------------------- step-level entry points, DEVICE vectors
+// The bodies the loops above are made of, one call per step, for a host that keeps the reference's loop and replaces its body
+// (eigenvec_CG: src/lanczos.cc:293-332).  Element type and order of the vectors follow the handle (qbgpu_native_order); no
+// real-mode dispatch, no permutation.
+int qbgpu_cg_restart(qbgpu_matrix_t A, const double E0[2], double *sc_dev, void *v, void *r, void *p, double *vnorm, double *accu)
+{
+    QB_TRY(ensure_init());
+    if (!A || !E0 || !sc_dev || !v || !r || !p || !accu) return fail(QBGPU_ERR_ARG, "cg_restart: null argument");
+    QB_TRY(check_single(A, A->api_complex));
+    double nn = 0.0;
+    QB_TRY(vec_nrm2sq(A->n, A->api_complex, v, sc_dev + 6));
+    QB_TRY(read_scalars(sc_dev + 6, &nn, 1));
+    const double rnorm = sqrt(nn);
+    if (vnorm) *vnorm = rnorm;
+    if (!(rnorm > 0.0)) return fail(QBGPU_ERR_NUMERIC, "cg_restart: the vector is zero");
+    return cg_restart_piece(A, A->api_complex, make_double2(E0[0], A->api_complex ? E0[1] : 0.0), rnorm, sc_dev, (char *)v, (char *)r, (char *)p, accu);
+}
+
+int qbgpu_cg_step(qbgpu_matrix_t A, const double E0[2], double *sc_dev, void *v, void *r, void *p, void *pp, double *accu)
+{
+    QB_TRY(ensure_init());
+    if (!A || !E0 || !sc_dev || !v || !r || !p || !pp || !accu) return fail(QBGPU_ERR_ARG, "cg_step: null argument");
+    QB_TRY(check_single(A, A->api_complex));
+    return cg_iterate_piece(A, A->api_complex, make_double2(E0[0], A->api_complex ? E0[1] : 0.0), sc_dev, (char *)v, (char *)r, (char *)p, (char *)pp, accu);
+}
+
+// One step of the Chebyshev recurrence as ONE fused product (the body of kpm_impl): Ht = (H - c)/s, c = (hi+lo)/2, s = (hi-lo)/2;
+// first: t_next = Ht t_cur; otherwise t_next = 2 Ht t_cur - t_prev (t_next may alias t_prev).  dots (may be NULL): the local
+// rows' <t_cur, t_next> (2 doubles) and |t_next|^2 -- what the 2k / 2k+1 doubling identities need.  Works on shards too
+// (t_cur: the full vector; t_prev / t_next: the local rows), like qbgpu_spmv_fused.
+int qbgpu_cheb_step(qbgpu_matrix_t A, double lo, double hi, int first, const void *t_cur_full, const void *t_prev_local, void *t_next_local, double *dots_dev)
+{
+    QB_TRY(ensure_init());
+    if (!A || !t_cur_full || !t_next_local || !(hi > lo)) return fail(QBGPU_ERR_ARG, "cheb_step: bad argument");
+    if (!first && !t_prev_local) return fail(QBGPU_ERR_ARG, "cheb_step: t_prev is needed after the first step");
+    const double cc = 0.5 * (hi + lo), ss = 0.5 * (hi - lo);
+    FusedArgs fa;
+    fa.x = t_cur_full; fa.y = t_next_local; fa.dots = dots_dev;
+    if (first) { fa.alpha = make_double2(1.0 / ss, 0.0); fa.gamma = make_double2(-cc / ss, 0.0); }
+    else { fa.alpha = make_double2(2.0 / ss, 0.0); fa.gamma = make_double2(-2.0 * cc / ss, 0.0); fa.beta = make_double2(-1.0, 0.0); fa.z = t_prev_local; }
+    return launch_spmv(A, fa);
+}
 
 }  // extern "C"

@@ -3,8 +3,7 @@ eigenvec_CG loop, src/lanczos.cc:293-332, with the loop itself kept on the host)
 Chebyshev recurrence).  Checked against the oracle (residual of the eigenvector, the C restatement's moments) and against the
 whole-loop entry points, which are made of the same pieces.
 
-Written after the GPU minutes of round 2 were spent: this module compiled and its host logic was read against the loops, but it
-had not met hardware when it was committed -- it sorts last so that nothing else hides behind it.
+(First hardware run: the last GPU call of round 2, profiles/r02zk_pytest_gpu_full_suite_final.log.)
 """
 import numpy as np
 import pytest

@@ -92,6 +92,46 @@ public:
         if (is_complex) check(qbgpu_energy_scale_z(handle, v, &lo, &hi, extend, iters, QBGPU_HOST), "qbgpu_energy_scale_z");
         else check(qbgpu_energy_scale_d(handle, reinterpret_cast<double *>(v), &lo, &hi, extend, iters, QBGPU_HOST), "qbgpu_energy_scale_d");
     }
+    // Chebyshev moments mu_k = <phi|T_k((H - c)/s)|phi>, k < nmom, c = (hi+lo)/2, s = (hi-lo)/2 with (lo, hi) from energy_scale():
+    // the recurrence the north star places in kpm.cc (the reference's src/kpm.cc stops at energy_scale); host phi, one fused
+    // product per two moments on the device
+    std::vector<double> kpm_moments(const T *phi, double lo, double hi, int64_t nmom) const
+    {
+        std::vector<double> mu(static_cast<size_t>(nmom > 0 ? nmom : 0));
+        if (is_complex) check(qbgpu_kpm_moments_z(handle, phi, lo, hi, nmom, mu.data(), QBGPU_HOST), "qbgpu_kpm_moments_z");
+        else check(qbgpu_kpm_moments_d(handle, reinterpret_cast<const double *>(phi), lo, hi, nmom, mu.data(), QBGPU_HOST), "qbgpu_kpm_moments_d");
+        return mu;
+    }
+    // iram<T,MAT>(dim, mat, v0, nev, ncv, maxit, "sr" | "lr", nconv, eigenvals, eigenvecs) (src/lanczos.cc:497-603) without the
+    // PCIe round trip per product: thick-restart Lanczos with the basis in HBM.  eigenvecs (host, nev * dim entries) may be null.
+    void iram_device(int nev, int ncv, int maxit, const std::string &order, int &nconv, double *eigenvals, T *eigenvecs = nullptr) const
+    {
+        int nprod = 0;
+        if (order == "sr") check(qbgpu_trlan(handle, nev, ncv, maxit, 0.0, &nconv, &nprod, eigenvals, eigenvecs, QBGPU_HOST), "qbgpu_trlan");
+        else if (order == "lr") check(qbgpu_trlan_largest(handle, nev, ncv, maxit, 0.0, &nconv, &nprod, eigenvals, eigenvecs, QBGPU_HOST), "qbgpu_trlan_largest");
+        else throw std::runtime_error("qbgpu::csr_mat::iram_device: order must be \"sr\" or \"lr\"");
+    }
+    // Step-level members for a host that keeps the reference's loops and replaces their bodies (DEVICE pointers: qbgpu_malloc /
+    // qbgpu_memcpy_h2d; sc = 8 device doubles, zeroed before the first call).  cg_restart / cg_step are the two branches of
+    // eigenvec_CG's loop body (src/lanczos.cc:297-314 / :320-330); cheb_step is one fused product of T_{k+1} = 2 Ht T_k - T_{k-1}.
+    double cg_restart(const T &E0, double *sc_dev, T *v_dev, T *r_dev, T *p_dev, double *vnorm = nullptr) const
+    {
+        const double e[2] = {std::real(E0), std::imag(E0)};
+        double accu = 0.0;
+        check(qbgpu_cg_restart(handle, e, sc_dev, v_dev, r_dev, p_dev, vnorm, &accu), "qbgpu_cg_restart");
+        return accu;
+    }
+    double cg_step(const T &E0, double *sc_dev, T *v_dev, T *r_dev, T *p_dev, T *pp_dev) const
+    {
+        const double e[2] = {std::real(E0), std::imag(E0)};
+        double accu = 0.0;
+        check(qbgpu_cg_step(handle, e, sc_dev, v_dev, r_dev, p_dev, pp_dev, &accu), "qbgpu_cg_step");
+        return accu;
+    }
+    void cheb_step(double lo, double hi, bool first, const T *t_cur_dev, const T *t_prev_dev, T *t_next_dev, double *dots_dev = nullptr) const
+    {
+        check(qbgpu_cheb_step(handle, lo, hi, first ? 1 : 0, t_cur_dev, t_prev_dev, t_next_dev, dots_dev), "qbgpu_cheb_step");
+    }
 
 private:
     void mv(double alpha, const T *x, double beta, T *y) const

@@ -39,6 +39,15 @@ CASES = {
     "honeycomb3x2_general": (["honeycomb", 3, 2], -28.60363167,
                              "examples/trans_absent/latt_honeycomb/honeycomb_Spinless_Fermion.cc:129", True),
     "tj12": (["tj_chain", 12, 8, 0], -9.762087307, "src/main_test.cc:207-208 (ARPACK E0=E1)", False),
+    # the remaining full-basis examples of the reference: three-state sites, two orbitals, a three-site unit cell, boson amplitudes
+    "spin1_chain10": (["spin_one_chain", 10, 0], -14.09412995,
+                      "examples/trans_absent/latt_chain/chain_Heisenberg_spin_one.cc:96", True),
+    "kondo4": (["kondo_chain", 4, 4, 1, 4], -12.67762138, "examples/trans_absent/latt_chain/chain_Kondo.cc:126", True),
+    "kagome2x2_heis": (["kagome_heisenberg", 2, 2, 0], -5.444875217,
+                       "examples/trans_absent/latt_kagome/kagome_Heisenberg_spin_half.cc:175", True),
+    "kagome2x2_tj": (["kagome_tj", 2, 2, 8, 0], -15.41931496, "examples/trans_absent/latt_kagome/kagome_tJ.cc:232", False),
+    "bose3x3": (["bose_hubbard", 3, 3, 9, 2, 1, 1.1], -25.81136094,
+                "examples/trans_absent/latt_square/square_Bose_Hubbard.cc:100", True),
 }
 
 

@@ -261,6 +261,163 @@ static Built build_honeycomb(int Lx, int Ly) {
  * 95-128 with S^z instead of S^-): ground state of the sector (Sz, k0), then for momentum transfer q the sector k0 - q is
  * enumerated as sector 1, A = sum_x exp(-i 2 pi q x / L) / sqrt(L) S^z_x is applied to phi0 (model::moprXvec_repr,
  * src/model.cc:1716-1846) and model::measure_repr_dynamic (src/model.cc:1897-1912) returns the Lanczos coefficients. */
+/* ---- the remaining full-basis examples of the reference (examples/trans_absent): the published E0 of each pins the oracle
+ * on one more kind of matrix (three-state sites, two orbitals, a three-site unit cell, boson amplitudes sqrt(n)) ---- */
+
+/* spin-1 Heisenberg chain, PBC, Sz_total = szval (chain_Heisenberg_spin_one.cc: L = 10, Sz = 0 -> -14.09412995) */
+static Built build_spin_one_chain(int L, double szval) {
+    Built b; b.name = "spin_one_chain";
+    qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    const double h = 1.0 / sqrt(2.0);
+    std::vector<std::vector<cplx>> Sx(3, std::vector<cplx>(3, 0.0)), Sy = Sx;
+    Sx[0][1] = Sx[1][0] = Sx[1][2] = Sx[2][1] = h;
+    Sy[0][1] = Sy[1][2] = cplx(0.0, -h); Sy[1][0] = Sy[2][1] = cplx(0.0, h);
+    std::vector<cplx> Sz{1.0, 0.0, -1.0};
+    M.add_orbital(latt.Nsites, "spin-1");
+    Mopr Sz_tot;
+    for (int x = 0; x < L; x++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x}, 0, si, work); latt.coor2site({x + 1}, 0, sj, work);
+        Opr Sxi(si, 0, false, Sx), Syi(si, 0, false, Sy), Szi(si, 0, false, Sz);
+        Opr Sxj(sj, 0, false, Sx), Syj(sj, 0, false, Sy), Szj(sj, 0, false, Sz);
+        M.add_Ham(cplx(1.0, 0.0) * (Sxi * Sxj + Syi * Syj));
+        M.add_Ham(cplx(1.0, 0.0) * (Szi * Szj));
+        Sz_tot += Szi;
+    }
+    M.enumerate_basis_full({Sz_tot}, {szval});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* Kondo chain, PBC: electrons (orbital 0) coupled to local spins 1/2 (orbital 1), N_elec = nelec
+ * (chain_Kondo.cc: L = 4, t = 1, J_Kondo = 4, N_elec = L -> -12.67762138) */
+static Built build_kondo_chain(int L, double nelec, double t, double JK) {
+    Built b; b.name = "kondo_chain";
+    qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    auto cu = std::vector<std::vector<cplx>>(4, std::vector<cplx>(4, 0.0));
+    auto cd = cu;
+    cu[0][1] = 1.0; cu[2][3] = 1.0; cd[0][2] = 1.0; cd[1][3] = -1.0;
+    auto Sp = mat2(0, 1, 0, 0), Sm = mat2(0, 0, 1, 0);
+    std::vector<cplx> Sz{0.5, -0.5};
+    M.add_orbital(latt.Nsites, "electron");
+    M.add_orbital(latt.Nsites, "spin-1/2");
+    Mopr N_tot;
+    for (int x = 0; x < L; x++) {
+        uint32_t si, sj; std::vector<int> work(latt.dim);
+        latt.coor2site({x}, 0, si, work); latt.coor2site({x + 1}, 0, sj, work);
+        Opr cui(si, 0, true, cu), cdi(si, 0, true, cd), cuj(sj, 0, true, cu), cdj(sj, 0, true, cd);
+        auto cuid = cui; cuid.dagger(); auto cdid = cdi; cdid.dagger();
+        auto cujd = cuj; cujd.dagger(); auto cdjd = cdj; cdjd.dagger();
+        M.add_Ham(cplx(-t, 0.0) * (cuid * cuj)); M.add_Ham(cplx(-t, 0.0) * (cujd * cui));
+        M.add_Ham(cplx(-t, 0.0) * (cdid * cdj)); M.add_Ham(cplx(-t, 0.0) * (cdjd * cdi));
+        auto spi = cuid * cdi; auto smi = cdid * cui;                    // the electron's spin on site i
+        auto szi = cplx(0.5, 0.0) * (cuid * cui - cdid * cdi);
+        Opr Spi(si, 1, false, Sp), Smi(si, 1, false, Sm), Szi(si, 1, false, Sz);      // the local spin on site i
+        M.add_Ham(cplx(0.5 * JK, 0.0) * (Spi * smi + Smi * spi));
+        M.add_Ham(cplx(JK, 0.0) * (Szi * szi));
+        N_tot += (cuid * cui + cdid * cdi);
+    }
+    M.enumerate_basis_full({N_tot}, {nelec});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* the six bonds of one kagome unit cell (m, n), as (sublattice, cell) pairs -- the bonds of the reference's two kagome examples */
+struct KagomeBond { int sa, sb, dm, dn; };       // site (m, n; sa) -- site (m + dm, n + dn; sb)
+static const KagomeBond kKagomeBonds[6] = {{0, 2, 1, 0}, {0, 2, 0, 0}, {1, 0, 0, 1}, {1, 0, 0, 0}, {2, 1, -1, -1}, {2, 1, 0, 0}};
+
+/* spin-1/2 Heisenberg on the kagome lattice, PBC (kagome_Heisenberg_spin_half.cc: 2 x 2, Sz = 0 -> -5.444875217) */
+static Built build_kagome_heisenberg(int Lx, int Ly, double szval) {
+    Built b; b.name = "kagome_heisenberg";
+    qbasis::lattice latt("kagome", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    M.add_orbital(latt.Nsites, "spin-1/2");
+    for (int m = 0; m < Lx; m++) for (int n = 0; n < Ly; n++)
+        for (const auto &kb : kKagomeBonds) {
+            uint32_t si, sj; std::vector<int> work(latt.dim);
+            latt.coor2site({m, n}, kb.sa, si, work); latt.coor2site({m + kb.dm, n + kb.dn}, kb.sb, sj, work);
+            add_heisenberg_bond(M, si, sj, 1.0);
+        }
+    M.enumerate_basis_full({total_sz(latt.Nsites)}, {szval});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* t-J model on the kagome lattice, PBC (kagome_tJ.cc: 2 x 2, N = 8, Sz = 0, t = J = 1 -> -15.41931496) */
+static Built build_kagome_tj(int Lx, int Ly, double ntot, double szval) {
+    Built b; b.name = "kagome_tj";
+    qbasis::lattice latt("kagome", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    auto cu = std::vector<std::vector<cplx>>(3, std::vector<cplx>(3, 0.0));
+    auto cd = cu; cu[0][1] = 1.0; cd[0][2] = 1.0;
+    M.add_orbital(latt.Nsites, "tJ");
+    const double t = 1.0, J = 1.0;
+    struct Site { Opr cu, cd, cud, cdd; Mopr sp, sm, sz, n; };
+    auto site_ops = [&](uint32_t s) {
+        Opr c_u(s, 0, true, cu), c_d(s, 0, true, cd);
+        auto c_ud = c_u; c_ud.dagger(); auto c_dd = c_d; c_dd.dagger();
+        return Site{c_u, c_d, c_ud, c_dd, Mopr(c_ud * c_d), Mopr(c_dd * c_u), cplx(0.5, 0.0) * (c_ud * c_u - c_dd * c_d), c_ud * c_u + c_dd * c_d};
+    };
+    Mopr Sz_tot, N_tot;
+    for (int m = 0; m < Lx; m++) for (int n = 0; n < Ly; n++) {
+        std::vector<int> work(latt.dim);
+        for (const auto &kb : kKagomeBonds) {
+            uint32_t si, sj;
+            latt.coor2site({m, n}, kb.sa, si, work); latt.coor2site({m + kb.dm, n + kb.dn}, kb.sb, sj, work);
+            Site a = site_ops(si), c = site_ops(sj);
+            M.add_Ham(cplx(-t, 0.0) * (a.cud * c.cu)); M.add_Ham(cplx(-t, 0.0) * (c.cud * a.cu));
+            M.add_Ham(cplx(-t, 0.0) * (a.cdd * c.cd)); M.add_Ham(cplx(-t, 0.0) * (c.cdd * a.cd));
+            M.add_Ham(cplx(0.5 * J, 0.0) * (a.sp * c.sm + a.sm * c.sp));
+            M.add_Ham(cplx(J, 0.0) * (a.sz * c.sz));
+            M.add_Ham(cplx(-0.25 * J, 0.0) * (a.n * c.n));
+        }
+        for (int sub = 0; sub < 3; sub++) {
+            uint32_t s; latt.coor2site({m, n}, sub, s, work);
+            Site a = site_ops(s);
+            Sz_tot += a.sz; N_tot += a.n;
+        }
+    }
+    M.enumerate_basis_full({Sz_tot, N_tot}, {szval, ntot});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
+/* Bose-Hubbard model on the square lattice, PBC, at most nmax bosons per site
+ * (square_Bose_Hubbard.cc: 3 x 3, t = 1, U = 1.1, N = 9, Nmax = 2 -> -25.81136094) */
+static Built build_bose_hubbard(int Lx, int Ly, double ntot, int nmax, double t, double U) {
+    Built b; b.name = "bose_hubbard";
+    qbasis::lattice latt("square", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
+    b.model = std::make_unique<Model>(latt);
+    Model &M = *b.model;
+    qbasis::extra_info limit; limit.Nmax = static_cast<uint8_t>(nmax);
+    auto bm = std::vector<std::vector<cplx>>(nmax + 1, std::vector<cplx>(nmax + 1, 0.0));
+    for (int d = 0; d < nmax; d++) bm[d][d + 1] = cplx(sqrt(double(d + 1)), 0.0);
+    M.add_orbital(latt.Nsites, "boson", limit);
+    Mopr N_tot;
+    for (int x = 0; x < Lx; x++) for (int y = 0; y < Ly; y++) {
+        uint32_t si; std::vector<int> work(latt.dim);
+        latt.coor2site({x, y}, 0, si, work);
+        Opr bi(si, 0, false, bm); auto bid = bi; bid.dagger(); auto ni = bid * bi;
+        const int nb[2][2] = {{x + 1, y}, {x, y + 1}};
+        for (auto &r : nb) {
+            uint32_t sj; latt.coor2site({r[0], r[1]}, 0, sj, work);
+            Opr bj(sj, 0, false, bm); auto bjd = bj; bjd.dagger();
+            M.add_Ham(cplx(-t, 0.0) * (bid * bj)); M.add_Ham(cplx(-t, 0.0) * (bjd * bi));
+        }
+        M.add_Ham(cplx(0.5 * U, 0.0) * (ni * ni - ni));
+        N_tot += ni;
+    }
+    M.enumerate_basis_full({N_tot}, {ntot});
+    M.generate_Ham_sparse_full();
+    return b;
+}
+
 static void flow_heis_chain_szq(int L, double szval, int k0, int q, MKL_INT maxit, const std::string &vec_prefix, struct Json &js, char kind = 'z');
 
 struct Json {
@@ -615,6 +772,7 @@ static void usage() {
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
         "        hubbard_direct Lx Ly NUP NDN T U [--check]  (csr_mat filled without the LIL intermediate; --check: compare with the reference's assembly) |\n"
         "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
+        "        spin_one_chain L SZ | kondo_chain L NELEC T JK | kagome_heisenberg Lx Ly SZ | kagome_tj Lx Ly N SZ | bose_hubbard Lx Ly N NMAX T U |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         "        hubbard_full_szq Lx Ly NUP NDN T U QM QN MAXIT [--dump-vecs PREFIX]  (full basis: E0, S^z_q phi0, measure_full_dynamic)\n"
@@ -714,6 +872,11 @@ int main(int argc, char **argv)
         else if (c == "hubbard_k") { need(8); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double nu = atof(argv[a++]), nd = atof(argv[a++]), t = atof(argv[a++]), U = atof(argv[a++]); int km = atoi(argv[a++]), kn = atoi(argv[a++]); b = build_hubbard(Lx, Ly, nu, nd, t, U, km, kn); }
         else if (c == "tj_chain") { need(3); int L = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_tj_chain(L, N, sz); }
         else if (c == "honeycomb") { need(2); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); b = build_honeycomb(Lx, Ly); }
+        else if (c == "spin_one_chain") { need(2); int L = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_spin_one_chain(L, sz); }
+        else if (c == "kondo_chain") { need(4); int L = atoi(argv[a++]); double N = atof(argv[a++]), t = atof(argv[a++]), JK = atof(argv[a++]); b = build_kondo_chain(L, N, t, JK); }
+        else if (c == "kagome_heisenberg") { need(3); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_kagome_heisenberg(Lx, Ly, sz); }
+        else if (c == "kagome_tj") { need(4); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_kagome_tj(Lx, Ly, N, sz); }
+        else if (c == "bose_hubbard") { need(6); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double N = atof(argv[a++]); int nmax = atoi(argv[a++]); double t = atof(argv[a++]), U = atof(argv[a++]); b = build_bose_hubbard(Lx, Ly, N, nmax, t, U); }
         else usage();
         js.num("build_seconds", now_s() - t0);
         Model &M = *b.model;

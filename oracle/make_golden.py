@@ -48,6 +48,12 @@ CASES = {
     "kagome2x2_tj": (["kagome_tj", 2, 2, 8, 0], -15.41931496, "examples/trans_absent/latt_kagome/kagome_tJ.cc:232", False),
     "bose3x3": (["bose_hubbard", 3, 3, 9, 2, 1, 1.1], -25.81136094,
                 "examples/trans_absent/latt_square/square_Bose_Hubbard.cc:100", True),
+    # and two of their momentum sectors (generate_Ham_sparse_repr: complex Hermitian csr_mat of a three-state orbital; fermion
+    # signs of the translations on a three-site unit cell)
+    "spin1_chain12_k1": (["spin_one_chain_k", 12, 0, 1], -15.2458356,
+                         "examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_one.cc:99 (E0_list[1])", True),
+    "kagome2x2_tj_k10": (["kagome_tj_k", 2, 2, 8, 0, 1, 0], -14.40277723,
+                         "examples/trans_symmetric/latt_kagome/kagome_tJ.cc:239 (E0_list[1])", False),
 }
 
 

@@ -265,7 +265,7 @@ static Built build_honeycomb(int Lx, int Ly) {
  * on one more kind of matrix (three-state sites, two orbitals, a three-site unit cell, boson amplitudes sqrt(n)) ---- */
 
 /* spin-1 Heisenberg chain, PBC, Sz_total = szval (chain_Heisenberg_spin_one.cc: L = 10, Sz = 0 -> -14.09412995) */
-static Built build_spin_one_chain(int L, double szval) {
+static Built build_spin_one_chain(int L, double szval, int k = -1 /* >= 0: momentum sector (trans_symmetric/.../chain_Heisenberg_spin_one.cc) */) {
     Built b; b.name = "spin_one_chain";
     qbasis::lattice latt("chain", {static_cast<uint32_t>(L)}, {"pbc"});
     b.model = std::make_unique<Model>(latt);
@@ -286,8 +286,8 @@ static Built build_spin_one_chain(int L, double szval) {
         M.add_Ham(cplx(1.0, 0.0) * (Szi * Szj));
         Sz_tot += Szi;
     }
-    M.enumerate_basis_full({Sz_tot}, {szval});
-    M.generate_Ham_sparse_full();
+    if (k < 0) { M.enumerate_basis_full({Sz_tot}, {szval}); M.generate_Ham_sparse_full(); }
+    else { M.fill_Weisse_table(); M.enumerate_basis_repr({k}, {Sz_tot}, {szval}); M.generate_Ham_sparse_repr(); b.sym = qbasis::which_sym::repr; }
     return b;
 }
 
@@ -349,7 +349,7 @@ static Built build_kagome_heisenberg(int Lx, int Ly, double szval) {
 }
 
 /* t-J model on the kagome lattice, PBC (kagome_tJ.cc: 2 x 2, N = 8, Sz = 0, t = J = 1 -> -15.41931496) */
-static Built build_kagome_tj(int Lx, int Ly, double ntot, double szval) {
+static Built build_kagome_tj(int Lx, int Ly, double ntot, double szval, int km = -1, int kn = -1 /* >= 0: momentum sector (trans_symmetric/latt_kagome/kagome_tJ.cc) */) {
     Built b; b.name = "kagome_tj";
     qbasis::lattice latt("kagome", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
     b.model = std::make_unique<Model>(latt);
@@ -383,8 +383,8 @@ static Built build_kagome_tj(int Lx, int Ly, double ntot, double szval) {
             Sz_tot += a.sz; N_tot += a.n;
         }
     }
-    M.enumerate_basis_full({Sz_tot, N_tot}, {szval, ntot});
-    M.generate_Ham_sparse_full();
+    if (km < 0) { M.enumerate_basis_full({Sz_tot, N_tot}, {szval, ntot}); M.generate_Ham_sparse_full(); }
+    else { M.fill_Weisse_table(); M.enumerate_basis_repr({km, kn}, {Sz_tot, N_tot}, {szval, ntot}); M.generate_Ham_sparse_repr(); b.sym = qbasis::which_sym::repr; }
     return b;
 }
 
@@ -772,7 +772,7 @@ static void usage() {
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
         "        hubbard_direct Lx Ly NUP NDN T U [--check]  (csr_mat filled without the LIL intermediate; --check: compare with the reference's assembly) |\n"
         "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
-        "        spin_one_chain L SZ | kondo_chain L NELEC T JK | kagome_heisenberg Lx Ly SZ | kagome_tj Lx Ly N SZ | bose_hubbard Lx Ly N NMAX T U |\n"
+        "        spin_one_chain L SZ | spin_one_chain_k L SZ K | kondo_chain L NELEC T JK | kagome_heisenberg Lx Ly SZ | kagome_tj Lx Ly N SZ | kagome_tj_k Lx Ly N SZ M N | bose_hubbard Lx Ly N NMAX T U |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
         "        hubbard_full_szq Lx Ly NUP NDN T U QM QN MAXIT [--dump-vecs PREFIX]  (full basis: E0, S^z_q phi0, measure_full_dynamic)\n"
@@ -873,6 +873,8 @@ int main(int argc, char **argv)
         else if (c == "tj_chain") { need(3); int L = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_tj_chain(L, N, sz); }
         else if (c == "honeycomb") { need(2); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); b = build_honeycomb(Lx, Ly); }
         else if (c == "spin_one_chain") { need(2); int L = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_spin_one_chain(L, sz); }
+        else if (c == "spin_one_chain_k") { need(3); int L = atoi(argv[a++]); double sz = atof(argv[a++]); int k = atoi(argv[a++]); b = build_spin_one_chain(L, sz, k); }
+        else if (c == "kagome_tj_k") { need(6); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); int m = atoi(argv[a++]), n = atoi(argv[a++]); b = build_kagome_tj(Lx, Ly, N, sz, m, n); }
         else if (c == "kondo_chain") { need(4); int L = atoi(argv[a++]); double N = atof(argv[a++]), t = atof(argv[a++]), JK = atof(argv[a++]); b = build_kondo_chain(L, N, t, JK); }
         else if (c == "kagome_heisenberg") { need(3); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_kagome_heisenberg(Lx, Ly, sz); }
         else if (c == "kagome_tj") { need(4); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_kagome_tj(Lx, Ly, N, sz); }

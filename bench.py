@@ -248,6 +248,19 @@ def run_reference(args, workload):
     print(json.dumps(line))
 
 
+def hubbard_upper_nnz(Lx, Ly, nup, ndn):
+    """Entries the reference stores (upper triangle incl. every diagonal) for the square-lattice Hubbard model: (Z + n) / 2."""
+    from math import comb
+    ns = Lx * Ly
+    n = comb(ns, nup) * comb(ns, ndn)
+    bonds = {tuple(sorted(b)) for b in square_bonds(Lx, Ly)}
+    # each undirected bond, each spin: states with exactly one of the two sites occupied by that spin
+    z_off = 0
+    for _ in bonds:
+        z_off += 2 * comb(ns - 2, nup - 1) * comb(ns, ndn) + 2 * comb(ns - 2, ndn - 1) * comb(ns, nup)
+    return (z_off + n + n) // 2
+
+
 def workload_upper_nnz(workload):
     """Entries the reference stores (upper triangle incl. every diagonal) for a workload: (Z + n) / 2."""
     from math import comb
@@ -255,14 +268,7 @@ def workload_upper_nnz(workload):
     if fam in ("heisenberg_k", "orbit"):
         return _SECTOR_UPPER[workload]          # counted by the device assembler (qbgpu_matrix_info.nnz_input)
     if fam == "hubbard":
-        ns = p["Lx"] * p["Ly"]
-        n = comb(ns, p["nup"]) * comb(ns, p["ndn"])
-        bonds = {tuple(sorted(b)) for b in square_bonds(p["Lx"], p["Ly"])}
-        # each undirected bond, each spin: states with exactly one of the two sites occupied by that spin
-        z_off = 0
-        for _ in bonds:
-            z_off += 2 * comb(ns - 2, p["nup"] - 1) * comb(ns, p["ndn"]) + 2 * comb(ns - 2, p["ndn"] - 1) * comb(ns, p["nup"])
-        return (z_off + n + n) // 2
+        return hubbard_upper_nnz(p["Lx"], p["Ly"], p["nup"], p["ndn"])
     L = p["L"]
     n = comb(L, L // 2)
     z_off = L * 2 * comb(L - 2, L // 2 - 1)
@@ -272,6 +278,54 @@ def workload_upper_nnz(workload):
 _SECTOR_UPPER = {"heis_chain32_k0": 173901570, "heis_chain28_k1": 11831544, "heis_chain24_k3": 817580,    # from runs of the assembler
                  "tri31_k10": 242371008, "tri21_k10": 293829}
 SECTOR_PHASES = {}
+
+
+def cpu_baseline_sample(workload, max_entries=4.0e8):
+    """The bounded sample the `cpu_baseline` leg times (qb_ref arguments, description).  Hubbard workloads: the SAME lattice and
+    operator with fewer electrons -- N_up = N_dn lowered until the reference's csr_mat has at most `max_entries` stored entries
+    (config 3: N_up = N_dn = 5, dim 19,079,424, 298,910,976 entries = 7.2 GB, far beyond the caches, so the time per stored entry
+    is the large-matrix one; the 12 M entries of the 4x3 cluster gave 0.62 ns where config 3 itself takes 0.99) -- filled
+    directly like the reference arm's matrix (oracle/ref_driver.cc: hubbard_direct).  A workload that is small enough is its
+    own sample.  The other families: the largest instance of the same model the reference's assembler builds in seconds."""
+    fam, p = WORKLOADS[workload]
+    if fam == "hubbard":
+        nu, nd = p["nup"], p["ndn"]
+        while hubbard_upper_nnz(p["Lx"], p["Ly"], nu, nd) > max_entries and min(nu, nd) > 1:
+            nu, nd = nu - 1, nd - 1
+        return (["hubbard_direct", p["Lx"], p["Ly"], nu, nd, p["t"], p["U"]],
+                f"Fermi-Hubbard {p['Lx']}x{p['Ly']}, N_up={nu}, N_dn={nd} (the workload's lattice and operator"
+                + (")" if (nu, nd) == (p["nup"], p["ndn"]) else f" with fewer electrons; the workload has {p['nup']}, {p['ndn']})"))
+    if fam == "heisenberg_k":
+        return ["heis_chain_k", 20, 0, p["k"] % 20], f"Heisenberg chain L=20, Sz=0, momentum sector k={p['k'] % 20}, reference-assembled"
+    if fam == "orbit":
+        return ["tri_k", 4, 5, 0, 3, 2], "triangular 4x5 Heisenberg, Sz=0, momentum sector (3,2), reference-assembled"
+    Ls = min(p["L"], 22)
+    return ["heis_chain", Ls, "sz", 0], f"Heisenberg chain L={Ls}, Sz=0, reference-assembled"
+
+
+def cpu_baseline_leg(workload, reps=5, warm=2):
+    """`cpu_baseline` of the GPU arm's line: the compiled reference's csr_mat::MultMv (oracle/_ref) on this host's cores, on a
+    bounded sample of the workload (cpu_baseline_sample), scaled to the metric's unit by stored entries and labelled so; the
+    sample's own measured figures are in `sample_ms_per_product` / `sample_ns_per_entry`.  (`bench.py --impl reference` times the
+    reference on the workload itself.)  Never raises: the baseline is informative and must not cost the GPU line."""
+    cores = os.cpu_count() or 1
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        if not O.have_qb_ref():
+            return {"value": None, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/qb_ref not built"}
+        sample_args, desc = cpu_baseline_sample(workload)
+        res = O.run_qb_ref(sample_args + ["--time-mv", reps, warm], threads=cores, timeout=1200)
+        t_step = res["mv_total_s"] / res["mv_reps"]
+        scale = workload_upper_nnz(workload) / res["nnz"]
+        return {"value": 1.0 / (t_step * scale), "unit": "H*v/s", "cores": cores, "kind": "reference",
+                "sample_ms_per_product": 1e3 * t_step, "sample_ns_per_entry": 1e9 * t_step / res["nnz"], "scaled_by_stored_entries": scale,
+                "sample": f"{desc}: dim {res['dim']:,}, {res['nnz']:,} stored upper-triangle entries, {res['mv_reps']} x the reference's "
+                          f"csr_mat::MultMv at {1e3 * t_step:.2f} ms ({1e9 * t_step / res['nnz']:.2f} ns per stored entry)"
+                          + ("" if abs(scale - 1.0) < 1e-12 else f", scaled x{scale:.2f} by stored entries to {workload}")
+                          + f"; MKL replaced by the shim's restated mkl_sparse_z_mv, OpenMP {cores} threads"}
+    except Exception as e:
+        return {"value": None, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -688,26 +742,7 @@ def main():
 
     # ---------------------------------------------------------------- CPU baseline beside it (bounded sample)
     if not args.no_cpu:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import oracle_lib as O
-            fam, p = WORKLOADS[args.workload]
-            cores = os.cpu_count() or 1
-            if O.have_qb_ref():
-                sample_args = (["hubbard", 4, 3, 6, 6, 1.0, 1.1] if fam == "hubbard" else
-                               ["heis_chain_k", 20, 0, p["k"] % 20] if fam == "heisenberg_k" else
-                               ["tri_k", 4, 5, 0, 3, 2] if fam == "orbit" else ["heis_chain", min(p["L"], 22), "sz", 0])
-                res = O.run_qb_ref(sample_args + ["--time-mv", 5, 2], threads=cores, timeout=1200)
-                t_step = res["mv_total_s"] / res["mv_reps"]
-                scale = workload_upper_nnz(args.workload) / res["nnz"]
-                line["cpu_baseline"] = {"value": 1.0 / (t_step * scale), "unit": "H*v/s", "cores": cores, "kind": "reference",
-                                        "sample": f"qb_ref {' '.join(map(str, sample_args))}: dim {res['dim']}, {res['nnz']} stored entries, "
-                                                  f"{1e3 * t_step:.2f} ms per csr_mat::MultMv ({1e9 * t_step / res['nnz']:.2f} ns/entry), scaled x{scale:.1f} "
-                                                  f"by stored entries to {args.workload}; shim-restated mkl_sparse_z_mv, OpenMP {cores} threads"}
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/qb_ref not built"}
-        except Exception as e:   # the baseline is informative; never lose the GPU line over it
-            line["cpu_baseline"] = {"value": None, "unit": "H*v/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        line["cpu_baseline"] = cpu_baseline_leg(args.workload)
 
     # ---------------------------------------------------------------- species-order handles, in a process of their own
     # (hubbard workloads; everything above is already measured and this process gives its HBM back first)

@@ -50,3 +50,25 @@ def test_byte_formulas_match_the_survey():
     assert abs(bench.algorithmic_bytes(Z, n, n, 8, 16) / 1e9 - 76.5) < 0.1       # real values, complex vectors
     assert abs(bench.algorithmic_bytes(Z, n, n, 8, 8) / 1e9 - 73.8) < 0.1        # real / real
     assert bench.workload_upper_nnz("heis_chain20") == 1157156                    # BASELINE config 1
+
+
+def test_cpu_baseline_sample_is_the_same_lattice_and_bounded(oracle):
+    """The `cpu_baseline` leg of our arm: a bounded sample of the SAME model (for config 3 the 4x4 lattice with five electrons per
+    species: 0.3 G stored entries, far beyond the caches), scaled by stored entries; small workloads are their own sample."""
+    sys.path.insert(0, ROOT)
+    import bench
+    args, desc = bench.cpu_baseline_sample("hubbard4x4")
+    assert args == ["hubbard_direct", 4, 4, 5, 5, 1.0, 1.1] and "fewer electrons" in desc
+    assert bench.hubbard_upper_nnz(4, 4, 5, 5) == 298910976            # what the reference's csr_mat holds for it (qb_ref, measured)
+    assert bench.hubbard_upper_nnz(4, 4, 6, 6) > 4.0e8                 # the next larger filling is over the bound
+    assert bench.hubbard_upper_nnz(4, 3, 6, 6) == 12030480             # BASELINE.md section 3 (reference-assembled)
+    args, desc = bench.cpu_baseline_sample("hubbard4x3")
+    assert args == ["hubbard_direct", 4, 3, 6, 6, 1.0, 1.1] and "fewer" not in desc
+    assert bench.cpu_baseline_sample("heis_chain32_k0")[0] == ["heis_chain_k", 20, 0, 0]
+    if not oracle.have_qb_ref():
+        pytest.skip("oracle/_ref/qb_ref is not built (needs /root/reference at build time)")
+    r = bench.cpu_baseline_leg("hubbard4x3", reps=2, warm=1)          # its own sample: nothing scaled
+    assert r["kind"] == "reference" and r["value"] > 0 and r["scaled_by_stored_entries"] == 1.0 and "scaled x" not in r["sample"]
+    assert abs(r["value"] - 1e3 / r["sample_ms_per_product"]) < 1e-9 * r["value"]
+    r = bench.cpu_baseline_leg("heis_chain24")                         # a scaled sample says so
+    assert r["value"] > 0 and r["scaled_by_stored_entries"] > 1.0 and "scaled x" in r["sample"]

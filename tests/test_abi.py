@@ -214,3 +214,20 @@ def test_cpp_example_builds_against_the_library(tmp_path, src, args):
                     "-o", str(exe), "-L", libdir, "-lqbgpu", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([str(exe)] + args, capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode == 2 and "no CUDA device" in r.stderr
+
+
+def test_multi_gpu_cpp_example_builds_against_the_library(tmp_path):
+    """examples/dist_lanczos.cc (E0 on N GPUs from plain C++ over the qbgpu_dist_* entries) compiles and links against the header
+    and the library as they are; without a device every rank stops with the library's message and the program reports failure."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "dist_lanczos"
+    libdir = os.path.join(root, "quantum_basis_b200")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "dist_lanczos.cc"),
+                    "-o", str(exe), "-L", libdir, "-lqbgpu", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr

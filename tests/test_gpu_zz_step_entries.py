@@ -79,7 +79,7 @@ def test_cheb_step_loop_reproduces_the_moments(oracle, name):
 # The remaining full-basis examples of the reference (examples/trans_absent: spin-1 chain, Kondo chain, kagome Heisenberg,
 # kagome t-J, square Bose-Hubbard): matrices assembled by the compiled reference, each pinned by the E0 the reference's own
 # example asserts (tests/golden/*.npz, oracle/make_golden.py; on the CPU: tests/test_oracle.py).  The same checks as
-# tests/test_gpu_parity.py runs on the first nine goldens.  Added after the last GPU call of round 2: they sort last.
+# tests/test_gpu_parity.py runs on the first nine goldens.  (Hardware run: profiles/r02zl_pytest_gpu_more_reference_examples.log.)
 MORE = ["spin1_chain10", "kondo4", "kagome2x2_heis", "kagome2x2_tj", "bose3x3",
         # two momentum sectors of those models, assembled by the reference's generate_Ham_sparse_repr: complex Hermitian matrices
         # (the second one's imaginary parts are round-off, at most 1.7e-16 -- and must still be stored: they are not exactly 0)

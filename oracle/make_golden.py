@@ -54,6 +54,9 @@ CASES = {
                          "examples/trans_symmetric/latt_chain/chain_Heisenberg_spin_one.cc:99 (E0_list[1])", True),
     "kagome2x2_tj_k10": (["kagome_tj_k", 2, 2, 8, 0, 1, 0], -14.40277723,
                          "examples/trans_symmetric/latt_kagome/kagome_tJ.cc:239 (E0_list[1])", False),
+    # CPU oracle only (dim 85: too small for a meaningful device run): spinless fermions on the honeycomb lattice, momentum (1,1)
+    "honeycomb3x2_k11": (["honeycomb_k", 3, 2, 1, 1], -28.27163215,
+                         "examples/trans_symmetric/latt_honeycomb/honeycomb_Spinless_Fermion.cc:139 (E0_list[3])", True),
 }
 
 

@@ -226,7 +226,7 @@ static Built build_tj_chain(int L, double ntot, double sz) {
 
 /* Spinless fermions on the honeycomb lattice, stored as a GENERAL (full, non-symmetric-storage) CSR
  * (examples/trans_absent/latt_honeycomb/honeycomb_Spinless_Fermion.cc). */
-static Built build_honeycomb(int Lx, int Ly) {
+static Built build_honeycomb(int Lx, int Ly, int km = -1, int kn = -1 /* >= 0: momentum sector (trans_symmetric/latt_honeycomb) */) {
     Built b; b.name = "honeycomb";
     const double t = 1.0, V1 = 4.0;
     qbasis::lattice latt("honeycomb", {static_cast<uint32_t>(Lx), static_cast<uint32_t>(Ly)}, {"pbc", "pbc"});
@@ -250,8 +250,8 @@ static Built build_honeycomb(int Lx, int Ly) {
         Opr cj(sj, 0, true, c); auto cjd = cj; cjd.dagger();
         Nf += (ni + cjd * cj);
     }
-    M.enumerate_basis_full({Nf}, {double(Lx * Ly - 2)});
-    M.generate_Ham_sparse_full(0, false);
+    if (km < 0) { M.enumerate_basis_full({Nf}, {double(Lx * Ly - 2)}); M.generate_Ham_sparse_full(0, false); }
+    else { M.fill_Weisse_table(); M.enumerate_basis_repr({km, kn}, {Nf}, {double(Lx * Ly - 2)}); M.generate_Ham_sparse_repr(); b.sym = qbasis::which_sym::repr; }
     return b;
 }
 
@@ -771,7 +771,7 @@ static void usage() {
         "usage: qb_ref [--threads T] [--workdir D] --out results.json <case> <args...> [actions]\n"
         " cases: heis_chain L none|sz SZ | heis_chain_k L SZ K | tri Lx Ly SZ | tri_k Lx Ly SZ M N |\n"
         "        hubbard_direct Lx Ly NUP NDN T U [--check]  (csr_mat filled without the LIL intermediate; --check: compare with the reference's assembly) |\n"
-        "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | file_z F.qbcsr | file_d F.qbcsr |\n"
+        "        hubbard Lx Ly NUP NDN T U | hubbard_k Lx Ly NUP NDN T U M N | tj_chain L N SZ | honeycomb Lx Ly | honeycomb_k Lx Ly M N | file_z F.qbcsr | file_d F.qbcsr |\n"
         "        spin_one_chain L SZ | spin_one_chain_k L SZ K | kondo_chain L NELEC T JK | kagome_heisenberg Lx Ly SZ | kagome_tj Lx Ly N SZ | kagome_tj_k Lx Ly N SZ M N | bose_hubbard Lx Ly N NMAX T U |\n"
         "        heis_chain_szq L SZ K0 Q MAXIT [--dump-vecs PREFIX]  (E0 in sector K0, then S^z_Q phi0 and its dnmcs Lanczos in K0-Q)\n"
         "        heis_chain_smq ...                                    (same with S^-_Q: the target sector has Sz - 1)\n"
@@ -872,6 +872,7 @@ int main(int argc, char **argv)
         else if (c == "hubbard_k") { need(8); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double nu = atof(argv[a++]), nd = atof(argv[a++]), t = atof(argv[a++]), U = atof(argv[a++]); int km = atoi(argv[a++]), kn = atoi(argv[a++]); b = build_hubbard(Lx, Ly, nu, nd, t, U, km, kn); }
         else if (c == "tj_chain") { need(3); int L = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); b = build_tj_chain(L, N, sz); }
         else if (c == "honeycomb") { need(2); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); b = build_honeycomb(Lx, Ly); }
+        else if (c == "honeycomb_k") { need(4); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); int m = atoi(argv[a++]), n = atoi(argv[a++]); b = build_honeycomb(Lx, Ly, m, n); }
         else if (c == "spin_one_chain") { need(2); int L = atoi(argv[a++]); double sz = atof(argv[a++]); b = build_spin_one_chain(L, sz); }
         else if (c == "spin_one_chain_k") { need(3); int L = atoi(argv[a++]); double sz = atof(argv[a++]); int k = atoi(argv[a++]); b = build_spin_one_chain(L, sz, k); }
         else if (c == "kagome_tj_k") { need(6); int Lx = atoi(argv[a++]), Ly = atoi(argv[a++]); double N = atof(argv[a++]), sz = atof(argv[a++]); int m = atoi(argv[a++]), n = atoi(argv[a++]); b = build_kagome_tj(Lx, Ly, N, sz, m, n); }
